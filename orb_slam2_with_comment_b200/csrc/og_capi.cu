@@ -1,0 +1,649 @@
+// og_capi.cu — the extern "C" layer of liborbgpu.so (include/orbgpu.h): extractor handle, workspace layout in
+// HBM, launch sequence.  Host-side geometry follows the reference constructor and ComputePyramid /
+// ComputeKeyPointsOctTree line by line (cited inline); no pixel is ever touched on the host.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/orbgpu.h"
+#include "og_extract.cu"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define OG_CUDA(expr)                                                                                      \
+    do {                                                                                                   \
+        cudaError_t e_ = (expr);                                                                           \
+        if (e_ != cudaSuccess)                                                                             \
+            return fail(ORBGPU_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));              \
+    } while (0)
+
+inline int cv_round_f(float v) { return (int)lrintf(v); }
+inline int cv_round_d(double v) { return (int)lrint(v); }
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+struct orbgpu_extractor {
+    int device = 0;
+    int nfeatures = 0, nlevels = 0, ini_th = 0, min_th = 0;
+    double scale_factor = 1.2;  // ORBextractor.h:98 keeps the float argument in a double member
+    int max_w = 0, max_h = 0, max_batch = 0;
+    std::vector<float> scale, inv_scale, sigma2, inv_sigma2;
+    std::vector<int> quota, umax;
+    int kp_cap = 0;
+
+    cudaStream_t stream = nullptr;
+    // geometry is rebuilt whenever the frame size changes (buffers are sized for max_w x max_h)
+    int cur_w = 0, cur_h = 0;
+    og::ExtractParams P;
+    std::vector<og::Cell> cells;
+    // device buffers (capacity fixed at creation)
+    uint8_t *d_pyr = nullptr, *d_blur = nullptr, *d_images = nullptr, *d_ot = nullptr;
+    og::Cell* d_cells = nullptr;
+    og::Tap* d_taps = nullptr;
+    int32_t *d_cell_count = nullptr, *d_sel_count = nullptr, *d_counts = nullptr;
+    uint32_t *d_cand_xy = nullptr, *d_sel_xy = nullptr;
+    uint8_t *d_cand_resp = nullptr, *d_sel_resp = nullptr;
+    og::KeyPoint* d_kp = nullptr;
+    uint8_t* d_desc = nullptr;
+    size_t cap_pyr = 0, cap_cells = 0, cap_taps = 0, cap_cand = 0, cap_sel = 0, cap_ot = 0, cap_cellcount = 0;
+    int last_batch = 0, last_launches = 0;
+};
+
+namespace {
+
+struct Geometry {
+    og::ExtractParams P;
+    std::vector<og::Cell> cells;
+    std::vector<og::Tap> taps;            // all levels' x then y tables, concatenated
+    std::vector<size_t> xt_off, yt_off;   // offsets into taps
+    size_t pyr_bytes_per_frame = 0;
+};
+
+// cv::resize coefficient table for one axis.  Horizontal: fraction zeroed when the first
+// tap is clamped; vertical: weights kept, row indices clipped.
+void make_taps(int sn, int dn, bool horizontal, std::vector<og::Tap>& out) {
+    const double sc = (double)sn / dn;
+    for (int d = 0; d < dn; ++d) {
+        float f = (float)((d + 0.5) * sc - 0.5);
+        int s = (int)floorf(f);
+        f -= s;
+        og::Tap t;
+        if (horizontal) {
+            if (s < 0) { s = 0; f = 0.f; }
+            if (s >= sn - 1) { s = sn - 1; f = 0.f; }
+            t.s0 = (int16_t)s;
+            t.s1 = (int16_t)std::min(s + 1, sn - 1);
+        } else {
+            t.s0 = (int16_t)std::min(std::max(s, 0), sn - 1);
+            t.s1 = (int16_t)std::min(std::max(s + 1, 0), sn - 1);
+        }
+        t.w0 = (int16_t)cv_round_f((1.f - f) * 2048.f);
+        t.w1 = (int16_t)cv_round_f(f * 2048.f);
+        out.push_back(t);
+    }
+}
+
+size_t octree_ws_bytes(int cap, int node_cap) {
+    size_t b = 0;
+    auto take = [&](size_t bytes) { b += (bytes + 15) & ~size_t(15); };
+    take((size_t)cap * 4); take((size_t)cap * 4);
+    take((size_t)cap * 2); take((size_t)cap * 2);
+    take((size_t)cap); take((size_t)cap);
+    take((size_t)node_cap * sizeof(og::OtNode)); take((size_t)node_cap * sizeof(og::OtNode));
+    take((size_t)node_cap * sizeof(og::OtTmp));
+    for (int i = 0; i < 5; ++i) take((size_t)node_cap * 4);
+    take((size_t)og::kOctThreads * 16);
+    return b;
+}
+
+// Everything that depends on the frame size.  Returns an error string or "".
+std::string build_geometry(const orbgpu_extractor& ex, int w, int h, int batch_cap, Geometry& G) {
+    og::ExtractParams& P = G.P;
+    memset(&P, 0, sizeof(P));
+    P.n_levels = ex.nlevels;
+    P.ini_th = ex.ini_th;
+    P.min_th = ex.min_th;
+    for (int i = 0; i < 16; ++i) P.umax[i] = ex.umax[i];
+    // cv::fastAtan2 constants, evaluated in float like OpenCV's static initialisers (Appendix A.4)
+    const float sc = (float)(180.0 / 3.1415926535897932384626433832795);
+    P.atan.p1 = 0.9997878412794807f * sc;
+    P.atan.p3 = -0.3258083974640975f * sc;
+    P.atan.p5 = 0.1555786518463281f * sc;
+    P.atan.p7 = -0.04432655554792128f * sc;
+    P.atan.eps = (float)DBL_EPSILON;
+    P.factor_pi = (float)(3.1415926535897932384626433832795 / 180.f);  // ORBextractor.cc:107
+
+    size_t pyr_off = 0;
+    int cell_base = 0, cand_base = 0, sel_base = 0;
+    size_t ot_off = 0;
+    for (int l = 0; l < ex.nlevels; ++l) {
+        og::Level& L = P.lv[l];
+        L.w = cv_round_f((float)w * ex.inv_scale[l]);  // :1112
+        L.h = cv_round_f((float)h * ex.inv_scale[l]);
+        if (L.w < 62 || L.h < 62)  // maxBorder-minBorder = size-32 must hold one 30 px cell (:781-784)
+            return "image too small: pyramid level " + std::to_string(l) + " is " + std::to_string(L.w) + "x" +
+                   std::to_string(L.h) + " (every level needs a 30 px cell inside the 16 px border)";
+        L.pitch = (int)align_up((size_t)L.w + 2 * og::kXPad, 128);
+        L.rows = L.h + 2 * og::kEdge;
+        L.frame_stride = (long long)L.pitch * L.rows;
+        L.base = (long long)pyr_off;
+        pyr_off += (size_t)L.frame_stride * batch_cap;
+        if (l > 0) {
+            G.xt_off.push_back(G.taps.size());
+            make_taps(P.lv[l - 1].w, L.w, true, G.taps);
+            G.yt_off.push_back(G.taps.size());
+            make_taps(P.lv[l - 1].h, L.h, false, G.taps);
+        } else {
+            G.xt_off.push_back(0);
+            G.yt_off.push_back(0);
+        }
+        // detection grid, ORBextractor.cc:770-806
+        const int minBX = og::kEdge - 3, minBY = minBX;
+        const int maxBX = L.w - og::kEdge + 3, maxBY = L.h - og::kEdge + 3;
+        const float width = (float)(maxBX - minBX), height = (float)(maxBY - minBY);
+        const int nCols = (int)(width / 30.f), nRows = (int)(height / 30.f);
+        const int wCell = (int)ceilf(width / nCols), hCell = (int)ceilf(height / nRows);
+        L.cell_base = cell_base;
+        L.cand_base = cand_base;
+        int slot = 0, ncell = 0;
+        for (int i = 0; i < nRows; ++i) {
+            const float iniY = (float)(minBY + i * hCell);
+            float maxY = iniY + hCell + 6;
+            if (iniY >= maxBY - 3) continue;
+            if (maxY > maxBY) maxY = (float)maxBY;
+            for (int j = 0; j < nCols; ++j) {
+                const float iniX = (float)(minBX + j * wCell);
+                float maxX = iniX + wCell + 6;
+                if (iniX >= maxBX - 6) continue;
+                if (maxX > maxBX) maxX = (float)maxBX;
+                const int tw = (int)maxX - (int)iniX - 6, th = (int)maxY - (int)iniY - 6;
+                if (tw <= 0 || th <= 0) continue;  // cv::FAST tests nothing on a sub-image thinner than 7 px
+                if (tw > og::kCellMax || th > og::kCellMax) return "internal: cell larger than kCellMax";
+                og::Cell c;
+                c.level = (int16_t)l;
+                c.x0 = (int16_t)((int)iniX + 3);
+                c.y0 = (int16_t)((int)iniY + 3);
+                c.tw = (int16_t)tw;
+                c.th = (int16_t)th;
+                c.pad = 0;
+                c.slot = slot;
+                // 3x3 strict maxima cannot be 8-neighbours: at most one per 2x2 block
+                slot += ((tw + 1) / 2) * ((th + 1) / 2);
+                G.cells.push_back(c);
+                ++ncell;
+            }
+        }
+        L.n_cells = ncell;
+        L.cand_cap = std::max(slot, 1);
+        cell_base += ncell;
+        cand_base += L.cand_cap;
+        L.quota = ex.quota[l];
+        L.det_w = maxBX - minBX;
+        L.det_h = maxBY - minBY;
+        L.n_ini = (int)roundf((float)L.det_w / (float)L.det_h);  // :543
+        if (L.n_ini < 1)
+            return "unsupported aspect ratio: level " + std::to_string(l) + " is taller than 2:1 (the reference divides by zero here)";
+        L.hx = (float)L.det_w / (float)L.n_ini;  // :545
+        L.sel_cap = std::max(L.quota + 3, 4 * L.n_ini);
+        L.node_cap = L.sel_cap + 8;
+        if (L.node_cap > 65535) return "nfeatures too large for the 16-bit node index";
+        L.sel_base = sel_base;
+        sel_base += L.sel_cap;
+        L.scale = ex.scale[l];
+        L.kp_size = (float)(int)(31 * ex.scale[l]);  // :837 (PATCH_SIZE*mvScaleFactor -> int)
+        L.ot_base = (long long)ot_off;
+        ot_off += align_up(octree_ws_bytes(L.cand_cap, L.node_cap), 256);
+    }
+    P.total_cells = cell_base;
+    P.total_cand_cap = cand_base;
+    P.total_sel_cap = sel_base;
+    P.ot_frame_bytes = (long long)ot_off;
+    P.kp_cap = sel_base;
+    G.pyr_bytes_per_frame = pyr_off / batch_cap;
+    return "";
+}
+
+int ensure_geometry(orbgpu_extractor* ex, int w, int h) {
+    if (ex->cur_w == w && ex->cur_h == h) return ORBGPU_OK;
+    if (w > ex->max_w || h > ex->max_h)
+        return fail(ORBGPU_ERR_ARG, "image " + std::to_string(w) + "x" + std::to_string(h) + " exceeds the extractor's max size");
+    Geometry G;
+    std::string err = build_geometry(*ex, w, h, ex->max_batch, G);
+    if (!err.empty()) return fail(ORBGPU_ERR_ARG, err);
+    const og::ExtractParams& P = G.P;
+    const size_t B = (size_t)ex->max_batch;
+    if ((size_t)P.lv[ex->nlevels - 1].base + (size_t)P.lv[ex->nlevels - 1].frame_stride * B > ex->cap_pyr ||
+        G.cells.size() > ex->cap_cells || G.taps.size() > ex->cap_taps || (size_t)P.total_cand_cap > ex->cap_cand ||
+        (size_t)P.total_sel_cap > ex->cap_sel || (size_t)P.ot_frame_bytes > ex->cap_ot)
+        return fail(ORBGPU_ERR_CAPACITY, "internal: workspace sized at creation is too small for this frame size");
+    OG_CUDA(cudaMemcpyAsync(ex->d_cells, G.cells.data(), G.cells.size() * sizeof(og::Cell), cudaMemcpyHostToDevice, ex->stream));
+    if (!G.taps.empty())
+        OG_CUDA(cudaMemcpyAsync(ex->d_taps, G.taps.data(), G.taps.size() * sizeof(og::Tap), cudaMemcpyHostToDevice, ex->stream));
+    OG_CUDA(cudaStreamSynchronize(ex->stream));
+    ex->P = P;
+    for (int l = 1; l < ex->nlevels; ++l) {
+        ex->P.lv[l].xt = ex->d_taps + G.xt_off[l];
+        ex->P.lv[l].yt = ex->d_taps + G.yt_off[l];
+    }
+    ex->P.pyr = ex->d_pyr;
+    ex->P.blur = ex->d_blur;
+    ex->P.cells = ex->d_cells;
+    ex->P.cell_count = ex->d_cell_count;
+    ex->P.cand_xy = ex->d_cand_xy;
+    ex->P.cand_resp = ex->d_cand_resp;
+    ex->P.ot_ws = ex->d_ot;
+    ex->P.sel_xy = ex->d_sel_xy;
+    ex->P.sel_resp = ex->d_sel_resp;
+    ex->P.sel_count = ex->d_sel_count;
+    ex->cells = G.cells;
+    ex->cur_w = w;
+    ex->cur_h = h;
+    return ORBGPU_OK;
+}
+
+// The launch sequence of one batch (device pointers in, device pointers out), all on ex->stream.
+int launch_extract(orbgpu_extractor* ex, const uint8_t* d_images, int batch, size_t row_stride, size_t frame_stride,
+                   og::KeyPoint* d_kp, uint8_t* d_desc, int kp_capacity, int32_t* d_counts) {
+    og::ExtractParams P = ex->P;
+    P.batch = batch;
+    P.kp_cap = kp_capacity;
+    cudaStream_t st = ex->stream;
+    int launches = 0;
+    {
+        const og::Level& L = P.lv[0];
+        dim3 grid((L.pitch / 4 + 127) / 128, L.rows, batch);
+        og::k_level0<<<grid, 128, 0, st>>>(P, d_images, (long long)row_stride, (long long)frame_stride);
+        ++launches;
+    }
+    for (int l = 1; l < P.n_levels; ++l) {
+        const og::Level& L = P.lv[l];
+        dim3 grid((L.pitch / 4 + 127) / 128, L.rows, batch);
+        og::k_resize<<<grid, 128, 0, st>>>(P, l);
+        ++launches;
+    }
+    og::k_fast_cells<<<dim3(P.total_cells, batch), og::kFastThreads, 0, st>>>(P);
+    ++launches;
+    og::k_octree<<<dim3(P.n_levels, batch), og::kOctThreads, 0, st>>>(P);
+    ++launches;
+    for (int l = 0; l < P.n_levels; ++l) {
+        const og::Level& L = P.lv[l];
+        dim3 grid((L.w + og::kBlurTW - 1) / og::kBlurTW, (L.h + og::kBlurTH - 1) / og::kBlurTH, batch);
+        og::k_blur<<<grid, og::kBlurThreads, 0, st>>>(P, l);
+        ++launches;
+    }
+    og::k_orient_desc<<<dim3((ex->kp_cap + og::kDescWarps - 1) / og::kDescWarps, batch), og::kDescWarps * 32, 0, st>>>(
+        P, d_kp, d_desc, d_counts);
+    ++launches;
+    OG_CUDA(cudaGetLastError());
+    ex->last_batch = batch;
+    ex->last_launches = launches;
+    return ORBGPU_OK;
+}
+
+int check_call(orbgpu_extractor* ex, int batch, int width, int height, size_t row_stride, int kp_capacity) {
+    if (!ex) return fail(ORBGPU_ERR_ARG, "null extractor");
+    if (batch < 1 || batch > ex->max_batch)
+        return fail(ORBGPU_ERR_ARG, "batch " + std::to_string(batch) + " outside [1, max_batch=" + std::to_string(ex->max_batch) + "]");
+    if (row_stride < (size_t)width) return fail(ORBGPU_ERR_ARG, "row_stride smaller than width");
+    if (kp_capacity < ex->kp_cap)
+        return fail(ORBGPU_ERR_CAPACITY, "kp_capacity " + std::to_string(kp_capacity) + " < orbgpu_extractor_max_keypoints() = " + std::to_string(ex->kp_cap));
+    OG_CUDA(cudaSetDevice(ex->device));
+    return ensure_geometry(ex, width, height);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* orbgpu_last_error(void) { return g_err.c_str(); }
+int orbgpu_abi_version(void) { return 1; }
+
+int orbgpu_device_count(int* count) {
+    if (!count) return fail(ORBGPU_ERR_ARG, "null count");
+    *count = 0;
+    OG_CUDA(cudaGetDeviceCount(count));
+    return ORBGPU_OK;
+}
+
+int orbgpu_extractor_create(orbgpu_extractor** out, int device, int nfeatures, float scale_factor, int nlevels,
+                            int ini_th_fast, int min_th_fast, int max_width, int max_height, int max_batch) {
+    if (!out) return fail(ORBGPU_ERR_ARG, "null out");
+    *out = nullptr;
+    if (nfeatures < 1 || nlevels < 1 || nlevels > og::kMaxLevels || !(scale_factor > 1.f) || max_batch < 1 ||
+        ini_th_fast < 1 || min_th_fast < 1 || min_th_fast > ini_th_fast || ini_th_fast > 254)
+        return fail(ORBGPU_ERR_ARG, "bad extractor parameters (need nfeatures>=1, 1<=nlevels<=12, scaleFactor>1, 1<=minTh<=iniTh<=254)");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(ORBGPU_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) + " (there is no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(ORBGPU_ERR_ARG, "device index out of range");
+    OG_CUDA(cudaSetDevice(device));
+
+    orbgpu_extractor* ex = new orbgpu_extractor();
+    ex->device = device;
+    ex->nfeatures = nfeatures;
+    ex->nlevels = nlevels;
+    ex->ini_th = ini_th_fast;
+    ex->min_th = min_th_fast;
+    ex->scale_factor = scale_factor;
+    ex->max_w = max_width;
+    ex->max_h = max_height;
+    ex->max_batch = max_batch;
+    // ORBextractor.cc:413-431
+    ex->scale.resize(nlevels); ex->sigma2.resize(nlevels); ex->inv_scale.resize(nlevels); ex->inv_sigma2.resize(nlevels);
+    ex->scale[0] = 1.0f; ex->sigma2[0] = 1.0f;
+    for (int i = 1; i < nlevels; i++) {
+        ex->scale[i] = (float)(ex->scale[i - 1] * ex->scale_factor);
+        ex->sigma2[i] = ex->scale[i] * ex->scale[i];
+    }
+    for (int i = 0; i < nlevels; i++) { ex->inv_scale[i] = 1.0f / ex->scale[i]; ex->inv_sigma2[i] = 1.0f / ex->sigma2[i]; }
+    // :435-446
+    ex->quota.resize(nlevels);
+    float factor = (float)(1.0f / ex->scale_factor);
+    float nDesired = nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)nlevels));
+    int sum = 0;
+    for (int l = 0; l < nlevels - 1; l++) {
+        ex->quota[l] = cv_round_f(nDesired);
+        sum += ex->quota[l];
+        nDesired *= factor;
+    }
+    ex->quota[nlevels - 1] = std::max(nfeatures - sum, 0);
+    // :454-469
+    ex->umax.assign(16, 0);
+    {
+        const int HP = og::kHalfPatch;
+        int v, v0, vmax = (int)floor(HP * sqrt(2.f) / 2 + 1);
+        int vmin = (int)ceil(HP * sqrt(2.f) / 2);
+        const double hp2 = HP * HP;
+        for (v = 0; v <= vmax; ++v) ex->umax[v] = cv_round_d(sqrt(hp2 - v * v));
+        for (v = HP, v0 = 0; v >= vmin; --v) {
+            while (ex->umax[v0] == ex->umax[v0 + 1]) ++v0;
+            ex->umax[v] = v0;
+            ++v0;
+        }
+    }
+
+    Geometry G;
+    std::string err = build_geometry(*ex, max_width, max_height, max_batch, G);
+    if (!err.empty()) { delete ex; return fail(ORBGPU_ERR_ARG, err); }
+    ex->kp_cap = G.P.total_sel_cap;
+    const size_t B = (size_t)max_batch;
+    // capacities with slack: a smaller frame can need marginally more cells per pixel than the maximum one
+    ex->cap_pyr = (size_t)G.pyr_bytes_per_frame * B + 4096;
+    ex->cap_cells = G.cells.size() * 2 + 64;
+    ex->cap_taps = G.taps.size() + 64;
+    ex->cap_cand = (size_t)G.P.total_cand_cap * 5 / 4 + 1024;
+    ex->cap_sel = (size_t)G.P.total_sel_cap + 64;
+    ex->cap_ot = (size_t)G.P.ot_frame_bytes * 5 / 4 + 65536;
+    ex->cap_cellcount = ex->cap_cells;
+    cudaError_t ce = cudaSuccess;
+    auto alloc = [&](void** p, size_t bytes) { if (ce == cudaSuccess) ce = cudaMalloc(p, std::max<size_t>(bytes, 16)); };
+    alloc((void**)&ex->d_pyr, ex->cap_pyr);
+    alloc((void**)&ex->d_blur, ex->cap_pyr);
+    alloc((void**)&ex->d_images, (size_t)max_width * max_height * B);
+    alloc((void**)&ex->d_cells, ex->cap_cells * sizeof(og::Cell));
+    alloc((void**)&ex->d_taps, ex->cap_taps * sizeof(og::Tap));
+    alloc((void**)&ex->d_cell_count, ex->cap_cellcount * B * 4);
+    alloc((void**)&ex->d_cand_xy, ex->cap_cand * B * 4);
+    alloc((void**)&ex->d_cand_resp, ex->cap_cand * B);
+    alloc((void**)&ex->d_ot, ex->cap_ot * B);
+    alloc((void**)&ex->d_sel_xy, ex->cap_sel * B * 4);
+    alloc((void**)&ex->d_sel_resp, ex->cap_sel * B);
+    alloc((void**)&ex->d_sel_count, (size_t)og::kMaxLevels * B * 4);
+    alloc((void**)&ex->d_counts, B * 4);
+    alloc((void**)&ex->d_kp, (size_t)ex->kp_cap * B * sizeof(og::KeyPoint));
+    alloc((void**)&ex->d_desc, (size_t)ex->kp_cap * B * 32);
+    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&ex->stream, cudaStreamNonBlocking);
+    if (ce != cudaSuccess) {
+        std::string m = std::string("workspace allocation failed: ") + cudaGetErrorString(ce);
+        orbgpu_extractor_destroy(ex);
+        return fail(ORBGPU_ERR_CUDA, m);
+    }
+    *out = ex;
+    return ORBGPU_OK;
+}
+
+int orbgpu_extractor_destroy(orbgpu_extractor* ex) {
+    if (!ex) return ORBGPU_OK;
+    cudaSetDevice(ex->device);
+    if (ex->stream) { cudaStreamSynchronize(ex->stream); cudaStreamDestroy(ex->stream); }
+    void* ptrs[] = {ex->d_pyr, ex->d_blur, ex->d_images, ex->d_cells, ex->d_taps, ex->d_cell_count, ex->d_cand_xy,
+                    ex->d_cand_resp, ex->d_ot, ex->d_sel_xy, ex->d_sel_resp, ex->d_sel_count, ex->d_counts, ex->d_kp, ex->d_desc};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    delete ex;
+    return ORBGPU_OK;
+}
+
+int orbgpu_extractor_tables(const orbgpu_extractor* ex, float* scales, int32_t* features_per_level, int32_t* umax) {
+    if (!ex) return fail(ORBGPU_ERR_ARG, "null extractor");
+    const int n = ex->nlevels;
+    for (int i = 0; i < n; ++i) {
+        if (scales) {
+            scales[i] = ex->scale[i]; scales[n + i] = ex->inv_scale[i];
+            scales[2 * n + i] = ex->sigma2[i]; scales[3 * n + i] = ex->inv_sigma2[i];
+        }
+        if (features_per_level) features_per_level[i] = ex->quota[i];
+    }
+    if (umax) for (int i = 0; i < 16; ++i) umax[i] = ex->umax[i];
+    return ORBGPU_OK;
+}
+
+int orbgpu_extractor_max_keypoints(const orbgpu_extractor* ex) { return ex ? ex->kp_cap : 0; }
+
+int orbgpu_extract_batch_dev(orbgpu_extractor* ex, const uint8_t* images_dev, int batch, int width, int height,
+                             size_t row_stride, size_t frame_stride, orbgpu_keypoint* kp_out_dev, uint8_t* desc_out_dev,
+                             int kp_capacity, int32_t* counts_dev) {
+    int rc = check_call(ex, batch, width, height, row_stride, kp_capacity);
+    if (rc) return rc;
+    if (!images_dev || !kp_out_dev || !desc_out_dev || !counts_dev) return fail(ORBGPU_ERR_ARG, "null device pointer");
+    return launch_extract(ex, images_dev, batch, row_stride, frame_stride, (og::KeyPoint*)kp_out_dev, desc_out_dev, kp_capacity, counts_dev);
+}
+
+int orbgpu_extract_batch(orbgpu_extractor* ex, const uint8_t* images, int batch, int width, int height, size_t row_stride,
+                         size_t frame_stride, orbgpu_keypoint* kp_out, uint8_t* desc_out, int kp_capacity, int32_t* counts) {
+    int rc = check_call(ex, batch, width, height, row_stride, kp_capacity);
+    if (rc) return rc;
+    if (!images || !kp_out || !desc_out || !counts) return fail(ORBGPU_ERR_ARG, "null pointer");
+    cudaStream_t st = ex->stream;
+    // H2D: tightly packed device copy of the frames
+    if (row_stride == (size_t)width && frame_stride == (size_t)width * height) {
+        OG_CUDA(cudaMemcpyAsync(ex->d_images, images, (size_t)width * height * batch, cudaMemcpyHostToDevice, st));
+    } else {
+        for (int f = 0; f < batch; ++f)
+            OG_CUDA(cudaMemcpy2DAsync(ex->d_images + (size_t)f * width * height, width, images + (size_t)f * frame_stride,
+                                      row_stride, width, height, cudaMemcpyHostToDevice, st));
+    }
+    rc = launch_extract(ex, ex->d_images, batch, width, (size_t)width * height, ex->d_kp, ex->d_desc, ex->kp_cap, ex->d_counts);
+    if (rc) return rc;
+    // D2H: counts first, then only the used prefix of every frame's slots
+    OG_CUDA(cudaMemcpyAsync(counts, ex->d_counts, (size_t)batch * 4, cudaMemcpyDeviceToHost, st));
+    if (kp_capacity == ex->kp_cap) {
+        OG_CUDA(cudaMemcpyAsync(kp_out, ex->d_kp, (size_t)batch * ex->kp_cap * sizeof(og::KeyPoint), cudaMemcpyDeviceToHost, st));
+        OG_CUDA(cudaMemcpyAsync(desc_out, ex->d_desc, (size_t)batch * ex->kp_cap * 32, cudaMemcpyDeviceToHost, st));
+    } else {
+        OG_CUDA(cudaMemcpy2DAsync(kp_out, (size_t)kp_capacity * sizeof(og::KeyPoint), ex->d_kp, (size_t)ex->kp_cap * sizeof(og::KeyPoint),
+                                  (size_t)ex->kp_cap * sizeof(og::KeyPoint), batch, cudaMemcpyDeviceToHost, st));
+        OG_CUDA(cudaMemcpy2DAsync(desc_out, (size_t)kp_capacity * 32, ex->d_desc, (size_t)ex->kp_cap * 32, (size_t)ex->kp_cap * 32, batch,
+                                  cudaMemcpyDeviceToHost, st));
+    }
+    OG_CUDA(cudaStreamSynchronize(st));
+    return ORBGPU_OK;
+}
+
+int orbgpu_extract(orbgpu_extractor* ex, const uint8_t* image, int width, int height, size_t row_stride,
+                   orbgpu_keypoint* kp_out, uint8_t* desc_out, int kp_capacity, int* n_out) {
+    if (!n_out) return fail(ORBGPU_ERR_ARG, "null n_out");
+    *n_out = 0;
+    if (!image || width <= 0 || height <= 0) return ORBGPU_OK;  // empty image: silent return (:1046-1047)
+    int32_t n = 0;
+    int rc = orbgpu_extract_batch(ex, image, 1, width, height, row_stride, row_stride * height, kp_out, desc_out, kp_capacity, &n);
+    if (rc) return rc;
+    *n_out = n;
+    return ORBGPU_OK;
+}
+
+int orbgpu_extractor_sync(orbgpu_extractor* ex) {
+    if (!ex) return fail(ORBGPU_ERR_ARG, "null extractor");
+    OG_CUDA(cudaSetDevice(ex->device));
+    OG_CUDA(cudaStreamSynchronize(ex->stream));
+    return ORBGPU_OK;
+}
+
+int orbgpu_extractor_stream(orbgpu_extractor* ex, void** stream_out) {
+    if (!ex || !stream_out) return fail(ORBGPU_ERR_ARG, "null argument");
+    *stream_out = (void*)ex->stream;
+    return ORBGPU_OK;
+}
+
+int orbgpu_extractor_last_launches(const orbgpu_extractor* ex) { return ex ? ex->last_launches : 0; }
+
+int orbgpu_extractor_level_dims(const orbgpu_extractor* ex, int level, int* width, int* height) {
+    if (!ex || level < 0 || level >= ex->nlevels || ex->cur_w == 0) return fail(ORBGPU_ERR_ARG, "bad level or no frame processed yet");
+    if (width) *width = ex->P.lv[level].w;
+    if (height) *height = ex->P.lv[level].h;
+    return ORBGPU_OK;
+}
+
+static int read_plane(orbgpu_extractor* ex, const uint8_t* base, int frame, int level, int bordered, uint8_t* out, size_t out_stride) {
+    if (!ex || !out || level < 0 || level >= ex->nlevels || frame < 0 || frame >= ex->last_batch)
+        return fail(ORBGPU_ERR_ARG, "bad frame/level");
+    OG_CUDA(cudaSetDevice(ex->device));
+    const og::Level& L = ex->P.lv[level];
+    const uint8_t* src = base + L.base + (long long)frame * L.frame_stride;
+    const int W = bordered ? L.w + 2 * og::kEdge : L.w, H = bordered ? L.rows : L.h;
+    src += bordered ? (og::kXPad - og::kEdge) : ((long long)og::kEdge * L.pitch + og::kXPad);
+    if (out_stride < (size_t)W) return fail(ORBGPU_ERR_ARG, "out_stride too small");
+    OG_CUDA(cudaMemcpy2DAsync(out, out_stride, src, L.pitch, W, H, cudaMemcpyDeviceToHost, ex->stream));
+    OG_CUDA(cudaStreamSynchronize(ex->stream));
+    return ORBGPU_OK;
+}
+
+int orbgpu_extractor_read_level(orbgpu_extractor* ex, int frame, int level, int bordered, uint8_t* out, size_t out_stride) {
+    if (!ex) return fail(ORBGPU_ERR_ARG, "null extractor");
+    return read_plane(ex, ex->d_pyr, frame, level, bordered, out, out_stride);
+}
+
+int orbgpu_extractor_read_blurred(orbgpu_extractor* ex, int frame, int level, uint8_t* out, size_t out_stride) {
+    if (!ex) return fail(ORBGPU_ERR_ARG, "null extractor");
+    return read_plane(ex, ex->d_blur, frame, level, 0, out, out_stride);
+}
+
+int orbgpu_extractor_read_points(orbgpu_extractor* ex, int frame, int level, int stage, orbgpu_keypoint* out, int capacity, int* n_out) {
+    if (!ex || !n_out || level < 0 || level >= ex->nlevels || frame < 0 || frame >= ex->last_batch || (stage != 0 && stage != 1))
+        return fail(ORBGPU_ERR_ARG, "bad argument");
+    OG_CUDA(cudaSetDevice(ex->device));
+    const og::ExtractParams& P = ex->P;
+    const og::Level& L = P.lv[level];
+    std::vector<uint32_t> xy;
+    std::vector<uint8_t> rr;
+    std::vector<float> angles;
+    if (stage == 0) {
+        std::vector<int32_t> cc(L.n_cells);
+        OG_CUDA(cudaMemcpy(cc.data(), P.cell_count + (size_t)frame * P.total_cells + L.cell_base, (size_t)L.n_cells * 4, cudaMemcpyDeviceToHost));
+        std::vector<uint32_t> sxy(L.cand_cap);
+        std::vector<uint8_t> srr(L.cand_cap);
+        OG_CUDA(cudaMemcpy(sxy.data(), P.cand_xy + (size_t)frame * P.total_cand_cap + L.cand_base, (size_t)L.cand_cap * 4, cudaMemcpyDeviceToHost));
+        OG_CUDA(cudaMemcpy(srr.data(), P.cand_resp + (size_t)frame * P.total_cand_cap + L.cand_base, (size_t)L.cand_cap, cudaMemcpyDeviceToHost));
+        for (int c = 0; c < L.n_cells; ++c)
+            for (int k = 0; k < cc[c]; ++k) {
+                xy.push_back(sxy[ex->cells[L.cell_base + c].slot + k]);
+                rr.push_back(srr[ex->cells[L.cell_base + c].slot + k]);
+            }
+    } else {
+        std::vector<int32_t> sc(ex->nlevels);
+        OG_CUDA(cudaMemcpy(sc.data(), P.sel_count + (size_t)frame * ex->nlevels, (size_t)ex->nlevels * 4, cudaMemcpyDeviceToHost));
+        const int n = sc[level];
+        int off = 0;
+        for (int l = 0; l < level; ++l) off += sc[l];
+        xy.resize(n); rr.resize(n);
+        if (n) {
+            OG_CUDA(cudaMemcpy(xy.data(), P.sel_xy + (size_t)frame * P.total_sel_cap + L.sel_base, (size_t)n * 4, cudaMemcpyDeviceToHost));
+            OG_CUDA(cudaMemcpy(rr.data(), P.sel_resp + (size_t)frame * P.total_sel_cap + L.sel_base, (size_t)n, cudaMemcpyDeviceToHost));
+            std::vector<og::KeyPoint> kp(n);
+            OG_CUDA(cudaMemcpy(kp.data(), ex->d_kp + (size_t)frame * ex->kp_cap + off, (size_t)n * sizeof(og::KeyPoint), cudaMemcpyDeviceToHost));
+            for (int i = 0; i < n; ++i) angles.push_back(kp[i].angle);
+        }
+    }
+    *n_out = (int)xy.size();
+    for (int i = 0; i < (int)xy.size() && i < capacity; ++i) {
+        orbgpu_keypoint k;
+        const int add = stage == 0 ? 0 : 16;
+        k.x = (float)((xy[i] & 0xffffu) + add);
+        k.y = (float)((xy[i] >> 16) + add);
+        k.size = stage == 0 ? 7.f : L.kp_size;
+        k.angle = stage == 0 ? -1.f : angles[i];
+        k.response = (float)rr[i];
+        k.octave = stage == 0 ? 0 : level;
+        k.class_id = -1;
+        out[i] = k;
+    }
+    return ORBGPU_OK;
+}
+
+int orbgpu_octree(orbgpu_extractor* ex, const orbgpu_keypoint* candidates, int n, int min_x, int max_x, int min_y, int max_y,
+                  int n_features, orbgpu_keypoint* out, int capacity, int* n_out) {
+    if (!ex || !n_out || n < 0 || n_features < 1) return fail(ORBGPU_ERR_ARG, "bad argument");
+    OG_CUDA(cudaSetDevice(ex->device));
+    const int width = max_x - min_x, height = max_y - min_y;
+    if (width <= 0 || height <= 0) return fail(ORBGPU_ERR_ARG, "empty rectangle");
+    const int n_ini = (int)roundf((float)width / (float)height);
+    if (n_ini < 1) return fail(ORBGPU_ERR_ARG, "rectangle taller than 2:1");
+    const float hx = (float)width / (float)n_ini;
+    const int cap = std::max(n, 1), sel_cap = std::max(n_features + 3, 4 * n_ini), node_cap = sel_cap + 8;
+    if (node_cap > 65535) return fail(ORBGPU_ERR_ARG, "n_features too large");
+    std::vector<uint32_t> xy(cap);
+    std::vector<uint8_t> rr(cap);
+    for (int i = 0; i < n; ++i) {
+        xy[i] = ((uint32_t)(int)candidates[i].y << 16) | (uint32_t)(int)candidates[i].x;
+        rr[i] = (uint8_t)(int)candidates[i].response;
+    }
+    uint8_t* ws = nullptr;
+    uint32_t *d_xy = nullptr, *d_oxy = nullptr;
+    uint8_t *d_rr = nullptr, *d_orr = nullptr;
+    int* d_n = nullptr;
+    OG_CUDA(cudaMalloc((void**)&ws, octree_ws_bytes(cap, node_cap)));
+    OG_CUDA(cudaMalloc((void**)&d_xy, (size_t)cap * 4));
+    OG_CUDA(cudaMalloc((void**)&d_rr, cap));
+    OG_CUDA(cudaMalloc((void**)&d_oxy, (size_t)sel_cap * 4));
+    OG_CUDA(cudaMalloc((void**)&d_orr, sel_cap));
+    OG_CUDA(cudaMalloc((void**)&d_n, 4));
+    OG_CUDA(cudaMemcpy(d_xy, xy.data(), (size_t)cap * 4, cudaMemcpyHostToDevice));
+    OG_CUDA(cudaMemcpy(d_rr, rr.data(), cap, cudaMemcpyHostToDevice));
+    og::k_octree_single<<<1, og::kOctThreads, 0, ex->stream>>>(ws, cap, node_cap, d_xy, d_rr, n, n_ini, hx, height, n_features, d_oxy, d_orr, sel_cap, d_n);
+    OG_CUDA(cudaGetLastError());
+    OG_CUDA(cudaStreamSynchronize(ex->stream));
+    int m = 0;
+    OG_CUDA(cudaMemcpy(&m, d_n, 4, cudaMemcpyDeviceToHost));
+    std::vector<uint32_t> oxy(std::max(m, 1));
+    std::vector<uint8_t> orr(std::max(m, 1));
+    if (m) {
+        OG_CUDA(cudaMemcpy(oxy.data(), d_oxy, (size_t)m * 4, cudaMemcpyDeviceToHost));
+        OG_CUDA(cudaMemcpy(orr.data(), d_orr, m, cudaMemcpyDeviceToHost));
+    }
+    cudaFree(ws); cudaFree(d_xy); cudaFree(d_rr); cudaFree(d_oxy); cudaFree(d_orr); cudaFree(d_n);
+    *n_out = m;
+    for (int i = 0; i < m && i < capacity; ++i) {
+        orbgpu_keypoint k;
+        memset(&k, 0, sizeof(k));
+        k.x = (float)(oxy[i] & 0xffffu);
+        k.y = (float)(oxy[i] >> 16);
+        k.response = (float)orr[i];
+        out[i] = k;
+    }
+    return ORBGPU_OK;
+}
+
+}  // extern "C"

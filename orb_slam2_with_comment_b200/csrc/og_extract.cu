@@ -1,0 +1,388 @@
+// og_extract.cu — CUDA kernels (sm_100a) of ORBextractor::operator() (ORBextractor.cc:1043-1132).
+//
+//   k_level0        copyMakeBorder of the input into level 0                         (:1127)
+//   k_resize        cv::resize INTER_LINEAR level l-1 -> l  + its reflect-101 border (:1120-1123)
+//   k_fast_cells    per-cell FAST-9/16 + 3x3 NMS + iniTh/minTh fallback              (:789-829)
+//   k_octree        DistributeOctTree, one CTA per (frame, level)                    (:539-763)
+//   k_blur          GaussianBlur 7x7 sigma 2                                         (:1085-1086)
+//   k_orient_desc   IC_Angle + rotated BRIEF + final KeyPoint fields                 (:77-147, :837-847, :1095-1103)
+//
+// Integer stencil / compaction / popcount work: no tensor cores.  All kernels are batched over frames.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/orbgpu_pattern.inc"
+#include "og_octree.cuh"
+#include "og_types.h"
+
+namespace og {
+
+__device__ __forceinline__ uint8_t* level_ptr(uint8_t* base, const Level& L, int frame) {
+    return base + L.base + (long long)frame * L.frame_stride;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Level 0: interior copy + BORDER_REFLECT_101 frame.  One thread writes 4 consecutive bytes of the padded row.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void k_level0(const __grid_constant__ ExtractParams P, const uint8_t* __restrict__ images, long long row_stride,
+                         long long frame_stride) {
+    const Level& L = P.lv[0];
+    const int frame = blockIdx.z;
+    const int Y = blockIdx.y;  // row of the bordered buffer
+    const int X4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (X4 >= L.pitch) return;
+    const int y = reflect101(Y - kEdge, L.h);
+    const uint8_t* src = images + (long long)frame * frame_stride + (long long)y * row_stride;
+    uint32_t out = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        int x = X4 + k - kXPad;
+        x = x < -kEdge ? -kEdge : (x > L.w + kEdge - 1 ? L.w + kEdge - 1 : x);
+        x = reflect101(x, L.w);
+        out |= (uint32_t)__ldg(src + x) << (8 * k);
+    }
+    *reinterpret_cast<uint32_t*>(level_ptr(P.pyr, L, frame) + (long long)Y * L.pitch + X4) = out;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Level l from level l-1 (chained, :1120) including the border of the new level (:1122-1123): a border pixel is
+// the resize output at its reflected interior coordinate, so one pass writes the whole padded row.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void k_resize(const __grid_constant__ ExtractParams P, int level) {
+    const Level& L = P.lv[level];
+    const Level& S = P.lv[level - 1];
+    const int frame = blockIdx.z;
+    const int Y = blockIdx.y;
+    const int X4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (X4 >= L.pitch) return;
+    const int y = reflect101(Y - kEdge, L.h);
+    const Tap ty = L.yt[y];
+    const uint8_t* src = level_ptr(P.pyr, S, frame) + (long long)kEdge * S.pitch + kXPad;
+    const uint8_t* r0 = src + (long long)ty.s0 * S.pitch;
+    const uint8_t* r1 = src + (long long)ty.s1 * S.pitch;
+    uint32_t out = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        int x = X4 + k - kXPad;
+        x = x < -kEdge ? -kEdge : (x > L.w + kEdge - 1 ? L.w + kEdge - 1 : x);
+        x = reflect101(x, L.w);
+        const Tap tx = L.xt[x];
+        const int h0 = resize_hpass(r0[tx.s0], r0[tx.s1], tx.w0, tx.w1);
+        const int h1 = resize_hpass(r1[tx.s0], r1[tx.s1], tx.w0, tx.w1);
+        out |= (uint32_t)resize_vpass(h0, h1, ty.w0, ty.w1) << (8 * k);
+    }
+    *reinterpret_cast<uint32_t*>(level_ptr(P.pyr, L, frame) + (long long)Y * L.pitch + X4) = out;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// FAST per cell.  One CTA per (cell, frame).  The score V is threshold-free, so one score map + one NMS pass +
+// a per-cell vote "any survivor with V >= iniTh?" reproduces FAST(iniTh) / fallback FAST(minTh) (:809-816).
+// Survivors are written in row-major order into the cell's private slot range (no atomics, deterministic).
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kFastThreads = 128;
+
+__global__ void __launch_bounds__(kFastThreads) k_fast_cells(const __grid_constant__ ExtractParams P) {
+    __shared__ uint8_t tile[(kCellMax + 6) * kTileStride];
+    __shared__ uint8_t score[(kCellMax + 2) * kTileStride];
+    __shared__ int warp_tot[kFastThreads / 32];
+    __shared__ int any_ini;
+
+    const Cell c = P.cells[blockIdx.x];
+    const int frame = blockIdx.y;
+    const Level& L = P.lv[c.level];
+    const int t = threadIdx.x;
+    const int tw = c.tw, th = c.th;
+    const int TW = tw + 6, TH = th + 6;
+
+    // tile: level pixels [x0-3, x0+tw+3) x [y0-3, y0+th+3)
+    const uint8_t* img = level_ptr(P.pyr, L, frame) + (long long)(kEdge + c.y0 - 3) * L.pitch + (kXPad + c.x0 - 3);
+    for (int i = t; i < TH * TW; i += kFastThreads) {
+        const int r = i / TW, q = i - r * TW;
+        tile[r * kTileStride + q] = __ldg(img + (long long)r * L.pitch + q);
+    }
+    for (int i = t; i < (th + 2) * kTileStride; i += kFastThreads) score[i] = 0;
+    if (t == 0) any_ini = 0;
+    __syncthreads();
+
+    const int min_th = P.min_th, ini_th = P.ini_th;
+    const int npx = tw * th;
+    for (int i = t; i < npx; i += kFastThreads) {
+        const int py = i / tw, px = i - py * tw;
+        const uint8_t* p = tile + (py + 3) * kTileStride + (px + 3);
+        const int v = p[0];
+        // necessary condition for 9 contiguous ring pixels beyond the threshold: at least two of the four
+        // compass pixels are (an arc of 9 always covers two of them)
+        const int d0 = v - p[3 * kTileStride], d4 = v - p[3], d8 = v - p[-3 * kTileStride], d12 = v - p[-3];
+        const int nb = (d0 > min_th) + (d4 > min_th) + (d8 > min_th) + (d12 > min_th);
+        const int nd = (d0 < -min_th) + (d4 < -min_th) + (d8 < -min_th) + (d12 < -min_th);
+        if (nb < 2 && nd < 2) continue;
+        int d[16];
+        d[0] = d0; d[4] = d4; d[8] = d8; d[12] = d12;
+        d[1] = v - p[3 * kTileStride + 1];  d[2] = v - p[2 * kTileStride + 2];  d[3] = v - p[kTileStride + 3];
+        d[5] = v - p[-kTileStride + 3];     d[6] = v - p[-2 * kTileStride + 2]; d[7] = v - p[-3 * kTileStride + 1];
+        d[9] = v - p[-3 * kTileStride - 1]; d[10] = v - p[-2 * kTileStride - 2]; d[11] = v - p[-kTileStride - 3];
+        d[13] = v - p[kTileStride - 3];     d[14] = v - p[2 * kTileStride - 2]; d[15] = v - p[3 * kTileStride - 1];
+        const int V = fast_score16(d);
+        if (V >= min_th) score[(py + 1) * kTileStride + (px + 1)] = (uint8_t)V;
+    }
+    __syncthreads();
+
+    // NMS (strict maximum over the 8 neighbours; pixels outside the cell's tested area count as 0) -> flag in
+    // `tile` (no longer needed): 0 = dropped, else the score
+    uint8_t* keep = tile;
+    int vote = 0;
+    for (int i = t; i < npx; i += kFastThreads) {
+        const int py = i / tw, px = i - py * tw;
+        const uint8_t* s = score + (py + 1) * kTileStride + (px + 1);
+        const int v = s[0];
+        bool k = v > 0 && v > s[-1] && v > s[1] && v > s[-kTileStride - 1] && v > s[-kTileStride] &&
+                 v > s[-kTileStride + 1] && v > s[kTileStride - 1] && v > s[kTileStride] && v > s[kTileStride + 1];
+        keep[i] = k ? (uint8_t)v : 0;
+        vote |= (k && v >= ini_th);
+    }
+    if (vote) any_ini = 1;   // benign race: every writer stores 1
+    __syncthreads();
+    const int th_eff = any_ini ? ini_th : min_th;
+
+    // ordered compaction: thread t owns pixels [t*chunk, (t+1)*chunk) in row-major order
+    const int chunk = (npx + kFastThreads - 1) / kFastThreads;
+    const int lo = min(t * chunk, npx), hi = min(lo + chunk, npx);
+    int cnt = 0;
+    for (int i = lo; i < hi; ++i) cnt += keep[i] >= th_eff && keep[i] > 0;
+    const int lane = t & 31, w = t >> 5;
+    int inc = cnt;
+#pragma unroll
+    for (int dlt = 1; dlt < 32; dlt <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, inc, dlt);
+        if (lane >= dlt) inc += u;
+    }
+    if (lane == 31) warp_tot[w] = inc;
+    __syncthreads();
+    int base = 0, total = 0;
+#pragma unroll
+    for (int k = 0; k < kFastThreads / 32; ++k) {
+        if (k < w) base += warp_tot[k];
+        total += warp_tot[k];
+    }
+    int pos = base + inc - cnt;
+    uint32_t* oxy = P.cand_xy + (long long)frame * P.total_cand_cap + L.cand_base + c.slot;
+    uint8_t* orr = P.cand_resp + (long long)frame * P.total_cand_cap + L.cand_base + c.slot;
+    for (int i = lo; i < hi; ++i) {
+        const int v = keep[i];
+        if (v > 0 && v >= th_eff) {
+            const int py = i / tw, px = i - py * tw;
+            // coordinates relative to (minBorderX, minBorderY) = (16,16) as the reference stores them (:822-823)
+            oxy[pos] = ((uint32_t)(c.y0 + py - 16) << 16) | (uint32_t)(c.x0 + px - 16);
+            orr[pos] = (uint8_t)v;
+            ++pos;
+        }
+    }
+    if (t == 0) P.cell_count[(long long)frame * P.total_cells + blockIdx.x] = total;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// DistributeOctTree: one CTA per (level, frame).  Gathers the level's candidates from the per-cell slots in
+// emission order (cell-row-major, row-major inside a cell), then runs the block-cooperative state machine.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kOctThreads = 256;
+
+__device__ __forceinline__ OtWork carve_work(uint8_t* ws, int cap, int node_cap) {
+    OtWork W;
+    auto take = [&](size_t bytes) { uint8_t* p = ws; ws += (bytes + 15) & ~size_t(15); return p; };
+    W.kxy[0] = (uint32_t*)take((size_t)cap * 4);
+    W.kxy[1] = (uint32_t*)take((size_t)cap * 4);
+    W.knode[0] = (uint16_t*)take((size_t)cap * 2);
+    W.knode[1] = (uint16_t*)take((size_t)cap * 2);
+    W.kresp[0] = (uint8_t*)take((size_t)cap);
+    W.kresp[1] = (uint8_t*)take((size_t)cap);
+    W.nodes[0] = (OtNode*)take((size_t)node_cap * sizeof(OtNode));
+    W.nodes[1] = (OtNode*)take((size_t)node_cap * sizeof(OtNode));
+    W.tmp = (OtTmp*)take((size_t)node_cap * sizeof(OtTmp));
+    W.R[0] = (int32_t*)take((size_t)node_cap * 4);
+    W.R[1] = (int32_t*)take((size_t)node_cap * 4);
+    W.ordv = (int32_t*)take((size_t)node_cap * 4);
+    W.ordv2 = (int32_t*)take((size_t)node_cap * 4);
+    W.surv = (int32_t*)take((size_t)node_cap * 4);
+    W.thr = (int32_t*)take((size_t)kOctThreads * 4 * 4);
+    W.cap = cap;
+    W.node_cap = node_cap;
+    return W;
+}
+
+__global__ void __launch_bounds__(kOctThreads) k_octree(const __grid_constant__ ExtractParams P) {
+    __shared__ OtShared sh;
+    const int level = blockIdx.x, frame = blockIdx.y;
+    const Level& L = P.lv[level];
+    OtWork W = carve_work(P.ot_ws + (long long)frame * P.ot_frame_bytes + L.ot_base, L.cand_cap, L.node_cap);
+
+    // exclusive scan of the per-cell counts -> emission-order offsets (stored in ordv2... cells may exceed
+    // node_cap, so the scan lives in kxy[0] which is free until the root partition)
+    int32_t* coff = (int32_t*)W.kxy[0];
+    const int32_t* ccount = P.cell_count + (long long)frame * P.total_cells + L.cell_base;
+    OG_FOR(i, L.n_cells) coff[i] = ccount[i];
+    OG_SYNC();
+    block_exscan(coff, L.n_cells, &sh);
+    const int M = sh.scan_total;
+    const uint32_t* cxy = P.cand_xy + (long long)frame * P.total_cand_cap + L.cand_base;
+    const uint8_t* crr = P.cand_resp + (long long)frame * P.total_cand_cap + L.cand_base;
+    const Cell* cells = P.cells + L.cell_base;
+    // one warp per cell copies the cell's run
+    for (int ci = threadIdx.x >> 5; ci < L.n_cells; ci += kOctThreads / 32) {
+        const int n = ccount[ci], dst = coff[ci], src = cells[ci].slot;
+        for (int k = threadIdx.x & 31; k < n; k += 32) {
+            W.kxy[1][dst + k] = cxy[src + k];
+            W.kresp[1][dst + k] = crr[src + k];
+        }
+    }
+    OG_SYNC();
+    uint32_t* oxy = P.sel_xy + (long long)frame * P.total_sel_cap + L.sel_base;
+    uint8_t* orr = P.sel_resp + (long long)frame * P.total_sel_cap + L.sel_base;
+    const int n = ot_run(W, &sh, M, L.n_ini, L.hx, L.det_h, L.quota, oxy, orr, L.sel_cap);
+    if (threadIdx.x == 0) P.sel_count[frame * P.n_levels + level] = n;
+}
+
+// Stand-alone octree on caller-provided candidates (stage-level parity tests, orbgpu_octree).
+__global__ void __launch_bounds__(kOctThreads) k_octree_single(uint8_t* ws, int cap, int node_cap, const uint32_t* xy,
+                                                               const uint8_t* resp, int M, int n_ini, float hx, int height,
+                                                               int N, uint32_t* out_xy, uint8_t* out_resp, int out_cap,
+                                                               int* out_n) {
+    __shared__ OtShared sh;
+    OtWork W = carve_work(ws, cap, node_cap);
+    OG_FOR(i, M) { W.kxy[1][i] = xy[i]; W.kresp[1][i] = resp[i]; }
+    OG_SYNC();
+    const int n = ot_run(W, &sh, M, n_ini, hx, height, N, out_xy, out_resp, out_cap);
+    if (threadIdx.x == 0) *out_n = n;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// GaussianBlur 7x7 (separable, fixed point).  The level buffers carry a 19-px reflect-101 frame, which is exactly
+// what BORDER_REFLECT_101 of the isolated clone needs for taps up to 3 px outside (:1085-1086), so the stencil
+// has no border logic.  CTA tile: 128 x 16 outputs, 256 threads.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kBlurTW = 128, kBlurTH = 16, kBlurThreads = 256;
+
+__global__ void __launch_bounds__(kBlurThreads) k_blur(const __grid_constant__ ExtractParams P, int level) {
+    __shared__ uint8_t in[(kBlurTH + 6)][kBlurTW + 8];
+    __shared__ uint16_t hp[(kBlurTH + 6)][kBlurTW];
+    const Level& L = P.lv[level];
+    const int frame = blockIdx.z;
+    const int x0 = blockIdx.x * kBlurTW, y0 = blockIdx.y * kBlurTH;
+    const uint8_t* src = level_ptr(P.pyr, L, frame);
+    const int t = threadIdx.x;
+    // input rows y0-3 .. y0+TH+2, columns x0-3 .. x0+TW+2 (+2 spare)
+    for (int i = t; i < (kBlurTH + 6) * (kBlurTW + 8); i += kBlurThreads) {
+        const int r = i / (kBlurTW + 8), q = i - r * (kBlurTW + 8);
+        const int Y = kEdge + y0 - 3 + r, X = kXPad + x0 - 3 + q;
+        in[r][q] = (Y < L.rows && X < L.pitch) ? src[(long long)Y * L.pitch + X] : 0;
+    }
+    __syncthreads();
+    for (int i = t; i < (kBlurTH + 6) * kBlurTW; i += kBlurThreads) {
+        const int r = i / kBlurTW, q = i - r * kBlurTW;
+        const uint8_t* p = &in[r][q];
+        hp[r][q] = (uint16_t)blur_tap7(p[0], p[1], p[2], p[3], p[4], p[5], p[6]);
+    }
+    __syncthreads();
+    uint8_t* dst = level_ptr(P.blur, L, frame);
+    for (int i = t; i < kBlurTH * kBlurTW; i += kBlurThreads) {
+        const int r = i / kBlurTW, q = i - r * kBlurTW;
+        const int x = x0 + q, y = y0 + r;
+        if (x < L.w && y < L.h) {
+            const uint32_t acc = (uint32_t)blur_tap7(hp[r][q], hp[r + 1][q], hp[r + 2][q], hp[r + 3][q], hp[r + 4][q],
+                                                    hp[r + 5][q], hp[r + 6][q]);
+            dst[(long long)(kEdge + y) * L.pitch + kXPad + x] = blur_finish(acc);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Orientation + descriptor + final KeyPoint record: one warp per keypoint.
+//   IC_Angle (:77-104): integer moments over the radius-15 disc of the UN-blurred level, then fastAtan2.
+//   computeOrbDescriptor (:108-147): lane i produces descriptor byte i from pattern points 16i .. 16i+15 sampled
+//   on the BLURRED level.  cos/sin of the float angle are evaluated in double and rounded to float.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kDescWarps = 8;
+__constant__ int8_t c_pat_x[512] = {ORB_PATTERN_X_INIT};
+__constant__ int8_t c_pat_y[512] = {ORB_PATTERN_Y_INIT};
+
+__global__ void __launch_bounds__(kDescWarps * 32) k_orient_desc(const __grid_constant__ ExtractParams P, KeyPoint* __restrict__ kp_out,
+                                                                 uint8_t* __restrict__ desc_out,
+                                                                 int32_t* __restrict__ counts) {
+    __shared__ int8_t spx[512], spy[512];
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) { spx[i] = c_pat_x[i]; spy[i] = c_pat_y[i]; }
+    __syncthreads();
+    const int frame = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int idx = blockIdx.x * kDescWarps + (threadIdx.x >> 5);   // index among the frame's keypoints
+    // locate (level, index in level): keypoints are concatenated in level order (:1076-1103)
+    const int32_t* sc = P.sel_count + frame * P.n_levels;
+    int level = 0, off = 0, total = 0;
+    {
+        int acc = 0;
+        bool found = false;
+        for (int l = 0; l < P.n_levels; ++l) {
+            const int c = sc[l];
+            if (!found && idx < acc + c) { level = l; off = idx - acc; found = true; }
+            acc += c;
+        }
+        total = acc;
+        if (blockIdx.x == 0 && threadIdx.x == 0) counts[frame] = total < P.kp_cap ? total : P.kp_cap;
+        if (!found || idx >= P.kp_cap) return;
+    }
+    const Level& L = P.lv[level];
+    const uint32_t xy = P.sel_xy[(long long)frame * P.total_sel_cap + L.sel_base + off];
+    const int resp = P.sel_resp[(long long)frame * P.total_sel_cap + L.sel_base + off];
+    const int cx = (int)(xy & 0xffffu) + 16, cy = (int)(xy >> 16) + 16;   // level coordinates (:840-841)
+
+    // ---- IC_Angle
+    const uint8_t* c0 = level_ptr(P.pyr, L, frame) + (long long)(kEdge + cy) * L.pitch + (kXPad + cx);
+    int m10 = 0, m01 = 0;
+    if (lane < 31) {
+        const int u = lane - kHalfPatch;
+        const int au = u < 0 ? -u : u;
+#pragma unroll 1
+        for (int v = -kHalfPatch; v <= kHalfPatch; ++v) {
+            const int av = v < 0 ? -v : v;
+            if (au <= P.umax[av]) {
+                const int val = c0[(long long)v * L.pitch + u];
+                m10 += u * val;
+                m01 += v * val;
+            }
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        m10 += __shfl_xor_sync(0xffffffffu, m10, d);
+        m01 += __shfl_xor_sync(0xffffffffu, m01, d);
+    }
+    const float angle = fast_atan2((float)m01, (float)m10, P.atan);
+
+    // ---- rotated BRIEF on the blurred level
+    const float ang = fmul(angle, P.factor_pi);
+    const float a = (float)cos((double)ang), b = (float)sin((double)ang);
+    const uint8_t* b0 = level_ptr(P.blur, L, frame) + (long long)(kEdge + cy) * L.pitch + (kXPad + cx);
+    int val = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int i0 = 16 * lane + 2 * k;
+        int r0, q0, r1, q1;
+        brief_offset(spx[i0], spy[i0], a, b, &r0, &q0);
+        brief_offset(spx[i0 + 1], spy[i0 + 1], a, b, &r1, &q1);
+        const int t0 = b0[(long long)r0 * L.pitch + q0], t1 = b0[(long long)r1 * L.pitch + q1];
+        val |= (t0 < t1) << k;
+    }
+    desc_out[((long long)frame * P.kp_cap + idx) * 32 + lane] = (uint8_t)val;
+    if (lane == 0) {
+        KeyPoint kp;
+        const float fx = (float)cx, fy = (float)cy;
+        kp.x = level ? fmul(fx, L.scale) : fx;   // keypoint->pt *= scale for level != 0 (:1095-1101)
+        kp.y = level ? fmul(fy, L.scale) : fy;
+        kp.size = L.kp_size;
+        kp.angle = angle;
+        kp.response = (float)resp;
+        kp.octave = level;
+        kp.class_id = -1;
+        kp_out[(long long)frame * P.kp_cap + idx] = kp;
+    }
+}
+
+}  // namespace og

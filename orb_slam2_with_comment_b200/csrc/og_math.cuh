@@ -1,0 +1,146 @@
+// og_math.cuh — per-element arithmetic of the ORB front-end, shared by every kernel.
+// Each routine states the reference / OpenCV semantics it reproduces bit for bit.
+// Functions are __host__ __device__ so that tests/host_model can run the very same code on the CPU;
+// on the host the translation unit must be built with -ffp-contract=off.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define OGM_HD __host__ __device__ __forceinline__
+#else
+#define OGM_HD inline
+#endif
+
+namespace og {
+
+// Separately rounded float ops: nvcc contracts a*b+c into an FMA by default, the reference's arithmetic
+// (OpenCV fastAtan2, the rounded rotation at ORBextractor.cc:118-120) is plain IEEE mul/add.
+OGM_HD float fmul(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+OGM_HD float fadd(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+OGM_HD float fsub(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fsub_rn(a, b);
+#else
+    return a - b;
+#endif
+}
+OGM_HD float fdiv(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fdiv_rn(a, b);
+#else
+    return a / b;
+#endif
+}
+// cvRound(float): round half to even
+OGM_HD int round_rn(float v) {
+#if defined(__CUDA_ARCH__)
+    return __float2int_rn(v);
+#else
+    return (int)__builtin_lrintf(v);
+#endif
+}
+
+// BORDER_REFLECT_101 for an index at most one period out of range (|overshoot| < n-1).
+OGM_HD int reflect101(int p, int n) {
+    if (p < 0) p = -p;
+    if (p >= n) p = 2 * n - 2 - p;
+    return p;
+}
+
+// ---- cv::resize INTER_LINEAR, 8UC1 (Appendix A.1) ------------------------------------------------------
+// h0/h1: horizontal interpolations of the two source rows (S[sx]*w0 + S[sx+1]*w1, 11-bit weights);
+// b0/b1: vertical weights.
+OGM_HD int resize_hpass(int s0, int s1, int w0, int w1) { return s0 * w0 + s1 * w1; }
+OGM_HD uint8_t resize_vpass(int h0, int h1, int b0, int b1) {
+    return (uint8_t)((((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2);
+}
+
+// ---- cv::GaussianBlur 7x7 sigma 2, 8UC1 (Appendix A.2): Q8.8 taps, Q16.16 accumulate, round -----------
+#define OG_G0 18
+#define OG_G1 34
+#define OG_G2 48
+#define OG_G3 56
+OGM_HD int blur_tap7(int a, int b, int c, int d, int e, int f, int g) {
+    return OG_G0 * (a + g) + OG_G1 * (b + f) + OG_G2 * (c + e) + OG_G3 * d;
+}
+OGM_HD uint8_t blur_finish(uint32_t acc) { return (uint8_t)((acc + 32768u) >> 16); }
+
+// ---- FAST-9/16 corner score (Appendix A.3) ------------------------------------------------------------
+// d[k] = I(p) - I(ring_k), k = 0..15 in ring order.  Returns V = max(A,B)-1 where A = max over the 16 arcs
+// of 9 contiguous ring pixels of min d, B the same for -d.  corner at threshold t <=> V >= t.
+OGM_HD int imin(int a, int b) { return a < b ? a : b; }
+OGM_HD int imax(int a, int b) { return a > b ? a : b; }
+OGM_HD int fast_score16(const int d[16]) {
+    int lo2[16], hi2[16], lo4[16], hi4[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        lo2[k] = imin(d[k], d[(k + 1) & 15]);
+        hi2[k] = imax(d[k], d[(k + 1) & 15]);
+    }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        lo4[k] = imin(lo2[k], lo2[(k + 2) & 15]);
+        hi4[k] = imax(hi2[k], hi2[(k + 2) & 15]);
+    }
+    int A = -256, Bn = 256;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const int lo9 = imin(imin(lo4[k], lo4[(k + 4) & 15]), d[(k + 8) & 15]);
+        const int hi9 = imax(imax(hi4[k], hi4[(k + 4) & 15]), d[(k + 8) & 15]);
+        A = imax(A, lo9);
+        Bn = imin(Bn, hi9);
+    }
+    return imax(A, -Bn) - 1;
+}
+
+// ---- cv::fastAtan2 (Appendix A.4); p1..p7 are the float products computed once on the host ---------------
+struct AtanCoef {
+    float p1, p3, p5, p7, eps;
+};
+OGM_HD float fast_atan2(float y, float x, const AtanCoef& k) {
+    const float ax = x < 0 ? -x : x, ay = y < 0 ? -y : y;
+    float a, c, c2;
+    if (ax >= ay) {
+        c = fdiv(ay, fadd(ax, k.eps));
+        c2 = fmul(c, c);
+        a = fmul(fadd(fmul(fadd(fmul(fadd(fmul(k.p7, c2), k.p5), c2), k.p3), c2), k.p1), c);
+    } else {
+        c = fdiv(ax, fadd(ay, k.eps));
+        c2 = fmul(c, c);
+        a = fsub(90.f, fmul(fadd(fmul(fadd(fmul(fadd(fmul(k.p7, c2), k.p5), c2), k.p3), c2), k.p1), c));
+    }
+    if (x < 0) a = fsub(180.f, a);
+    if (y < 0) a = fsub(360.f, a);
+    return a;
+}
+
+// ---- rotated BRIEF sample offset (ORBextractor.cc:118-120) ---------------------------------------------
+// row = cvRound(x*b + y*a), col = cvRound(x*a - y*b) with a = cos, b = sin of the keypoint angle.
+OGM_HD void brief_offset(int px, int py, float a, float b, int* row, int* col) {
+    const float fx = (float)px, fy = (float)py;
+    *row = round_rn(fadd(fmul(fx, b), fmul(fy, a)));
+    *col = round_rn(fsub(fmul(fx, a), fmul(fy, b)));
+}
+
+// ---- ORBmatcher::DescriptorDistance (ORBmatcher.cc:1901-1917): 256-bit Hamming distance ----------------
+OGM_HD int popc32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return __popc(v);
+#else
+    return __builtin_popcount(v);
+#endif
+}
+
+}  // namespace og

@@ -1,0 +1,133 @@
+"""Host-side mirror of ORB_SLAM2::ORBextractor (/root/reference/include/ORBextractor.h:45-111) over the C ABI.
+
+Same constructor arguments, same getters, `__call__(image)` plays operator() and returns the keypoints (a
+structured array with cv::KeyPoint's seven fields) and the N x 32 descriptor matrix; `mvImagePyramid` is read
+back from the device on demand.  `extract_batch` is the frame-batched entry the benchmark drives.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import KP_DTYPE
+
+
+class ORBextractor:
+    HARRIS_SCORE, FAST_SCORE = 0, 1
+
+    def __init__(self, nfeatures: int, scaleFactor: float, nlevels: int, iniThFAST: int, minThFAST: int, *,
+                 device: int = 0, max_width: int = 1241, max_height: int = 480, max_batch: int = 1):
+        self._lib = capi.lib()
+        self._h = C.c_void_p()
+        self.nlevels, self.scaleFactor = nlevels, float(np.float32(scaleFactor))
+        self.max_batch, self.device = max_batch, device
+        capi.check(self._lib.orbgpu_extractor_create(C.byref(self._h), device, nfeatures, scaleFactor, nlevels, iniThFAST,
+                                                     minThFAST, max_width, max_height, max_batch))
+        self.kp_cap = self._lib.orbgpu_extractor_max_keypoints(self._h)
+        s = np.zeros(4 * nlevels, np.float32)
+        q = np.zeros(nlevels, np.int32)
+        u = np.zeros(16, np.int32)
+        capi.check(self._lib.orbgpu_extractor_tables(self._h, s.ctypes.data, q.ctypes.data, u.ctypes.data))
+        self._tables = s.reshape(4, nlevels)
+        self.mnFeaturesPerLevel, self.umax = q, u
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.orbgpu_extractor_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- ORBextractor.h:63-83
+    def GetLevels(self): return self.nlevels
+    def GetScaleFactor(self): return self.scaleFactor
+    def GetScaleFactors(self): return self._tables[0].copy()
+    def GetInverseScaleFactors(self): return self._tables[1].copy()
+    def GetScaleSigmaSquares(self): return self._tables[2].copy()
+    def GetInverseScaleSigmaSquares(self): return self._tables[3].copy()
+
+    # ---- operator() (ORBextractor.cc:1043)
+    def __call__(self, image: np.ndarray, mask=None):
+        if image is None or image.size == 0:
+            return np.zeros(0, KP_DTYPE), np.zeros((0, 32), np.uint8)
+        assert image.dtype == np.uint8 and image.ndim == 2, "CV_8UC1 image expected (ORBextractor.cc:1050)"
+        if image.strides[1] != 1:
+            image = np.ascontiguousarray(image)
+        kp = np.zeros(self.kp_cap, KP_DTYPE)
+        desc = np.zeros((self.kp_cap, 32), np.uint8)
+        n = C.c_int(0)
+        capi.check(self._lib.orbgpu_extract(self._h, image.ctypes.data, image.shape[1], image.shape[0], image.strides[0],
+                                            kp.ctypes.data, desc.ctypes.data, self.kp_cap, C.byref(n)))
+        return kp[:n.value].copy(), desc[:n.value].copy()
+
+    def extract_batch(self, images: np.ndarray, kp_out=None, desc_out=None, counts=None):
+        """images: (B, H, W) uint8, C-contiguous.  Returns (kp (B,cap), desc (B,cap,32), counts (B,))."""
+        assert images.dtype == np.uint8 and images.ndim == 3 and images.flags.c_contiguous
+        B, H, W = images.shape
+        kp = np.zeros((B, self.kp_cap), KP_DTYPE) if kp_out is None else kp_out
+        desc = np.zeros((B, self.kp_cap, 32), np.uint8) if desc_out is None else desc_out
+        cnt = np.zeros(B, np.int32) if counts is None else counts
+        capi.check(self._lib.orbgpu_extract_batch(self._h, images.ctypes.data, B, W, H, W, W * H, kp.ctypes.data,
+                                                  desc.ctypes.data, self.kp_cap, cnt.ctypes.data))
+        return kp, desc, cnt
+
+    def extract_batch_dev(self, images_ptr: int, B: int, W: int, H: int, kp_ptr: int, desc_ptr: int, counts_ptr: int):
+        """Device-resident variant: raw device pointers (e.g. torch tensors' data_ptr()); asynchronous."""
+        capi.check(self._lib.orbgpu_extract_batch_dev(self._h, images_ptr, B, W, H, W, W * H, kp_ptr, desc_ptr, self.kp_cap,
+                                                      counts_ptr))
+
+    def sync(self):
+        capi.check(self._lib.orbgpu_extractor_sync(self._h))
+
+    def stream(self) -> int:
+        s = C.c_void_p()
+        capi.check(self._lib.orbgpu_extractor_stream(self._h, C.byref(s)))
+        return s.value or 0
+
+    def last_launches(self) -> int:
+        return self._lib.orbgpu_extractor_last_launches(self._h)
+
+    # ---- mvImagePyramid (ORBextractor.h:86) and stage taps
+    def level_dims(self, level):
+        w, h = C.c_int(), C.c_int()
+        capi.check(self._lib.orbgpu_extractor_level_dims(self._h, level, C.byref(w), C.byref(h)))
+        return w.value, h.value
+
+    def level(self, level, frame=0, bordered=False):
+        w, h = self.level_dims(level)
+        shape = (h + 38, w + 38) if bordered else (h, w)
+        out = np.zeros(shape, np.uint8)
+        capi.check(self._lib.orbgpu_extractor_read_level(self._h, frame, level, int(bordered), out.ctypes.data, shape[1]))
+        return out
+
+    @property
+    def mvImagePyramid(self):
+        return [self.level(l) for l in range(self.nlevels)]
+
+    def blurred(self, level, frame=0):
+        w, h = self.level_dims(level)
+        out = np.zeros((h, w), np.uint8)
+        capi.check(self._lib.orbgpu_extractor_read_blurred(self._h, frame, level, out.ctypes.data, w))
+        return out
+
+    def level_points(self, level, stage, frame=0):
+        cap = 1 << 18
+        out = np.zeros(cap, KP_DTYPE)
+        n = C.c_int(0)
+        capi.check(self._lib.orbgpu_extractor_read_points(self._h, frame, level, stage, out.ctypes.data, cap, C.byref(n)))
+        assert n.value <= cap
+        return out[:n.value].copy()
+
+    def octree(self, cand: np.ndarray, min_x, max_x, min_y, max_y, n_features):
+        cand = np.ascontiguousarray(cand)
+        out = np.zeros(n_features + 1024, KP_DTYPE)
+        n = C.c_int(0)
+        capi.check(self._lib.orbgpu_octree(self._h, cand.ctypes.data, len(cand), min_x, max_x, min_y, max_y, n_features,
+                                           out.ctypes.data, len(out), C.byref(n)))
+        return out[:n.value].copy()

@@ -1,0 +1,37 @@
+// TEST INFRASTRUCTURE: host compile of the block-cooperative octree state machine (og_octree.cuh) with
+// OG_FOR = plain loop.  Lets the CPU test-suite check the list-order logic of the CUDA kernel's algorithm
+// against the oracle without a GPU.  Never linked into liborbgpu.so.
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "../../orb_slam2_with_comment_b200/csrc/og_octree.cuh"
+
+extern "C" int ogm_octree(const uint32_t* xy, const uint8_t* resp, int M, int width, int height, int N,
+                          uint32_t* out_xy, uint8_t* out_resp, int out_cap) {
+    using namespace og;
+    const int nIni = (int)roundf((float)width / (float)height);
+    if (nIni < 1) return -1;
+    const float hX = (float)width / (float)nIni;
+    const int node_cap = std::max(N + 3, 4 * nIni) + 8;
+    const int cap = M > 0 ? M : 1;
+    std::vector<uint32_t> kxy0(cap), kxy1(cap);
+    std::vector<uint8_t> kr0(cap), kr1(cap);
+    std::vector<uint16_t> kn0(cap), kn1(cap);
+    std::vector<OtNode> n0(node_cap), n1(node_cap);
+    std::vector<OtTmp> tmp(node_cap);
+    std::vector<int32_t> R0(node_cap), R1(node_cap), ordv(node_cap), ordv2(node_cap), surv(node_cap), thr(4 * 64);
+    OtWork W;
+    W.kxy[0] = kxy0.data(); W.kxy[1] = kxy1.data();
+    W.kresp[0] = kr0.data(); W.kresp[1] = kr1.data();
+    W.knode[0] = kn0.data(); W.knode[1] = kn1.data();
+    W.nodes[0] = n0.data(); W.nodes[1] = n1.data();
+    W.tmp = tmp.data();
+    W.R[0] = R0.data(); W.R[1] = R1.data();
+    W.ordv = ordv.data(); W.ordv2 = ordv2.data(); W.surv = surv.data(); W.thr = thr.data();
+    W.cap = cap; W.node_cap = node_cap;
+    if (M) { memcpy(kxy1.data(), xy, (size_t)M * 4); memcpy(kr1.data(), resp, M); }
+    OtShared sh;
+    memset(&sh, 0, sizeof(sh));
+    return ot_run(W, &sh, M, nIni, hX, height, N, out_xy, out_resp, out_cap);
+}

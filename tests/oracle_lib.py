@@ -166,7 +166,7 @@ class Extractor:
 
 def octree(lib, prefix, cand, minX, maxX, minY, maxY, N):
     cand = np.ascontiguousarray(cand)
-    out = np.zeros(N + 16, KP_DTYPE)
+    out = np.zeros(N + 1024, KP_DTYPE)
     n = getattr(lib, prefix + "_octree")(cand.ctypes.data_as(C.c_void_p), len(cand), minX, maxX, minY, maxY, N,
                                          out.ctypes.data_as(C.c_void_p), len(out))
     return out[:n]

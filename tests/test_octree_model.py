@@ -1,0 +1,86 @@
+"""The block-cooperative octree state machine of the CUDA path (csrc/og_octree.cuh), compiled for the host,
+against the oracle's DistributeOctTree restatement and the compiled reference — no GPU needed.  This checks
+the array/prefix-sum formulation of the list algorithm (ordering, careful phase cut-off, tie-breaks)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from orb_slam2_with_comment_b200 import synth
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def model():
+    src = os.path.join(HERE, "host_model", "octree_model.cc")
+    out = os.path.join(HERE, "host_model", "libogmodel.so")
+    hdr = os.path.join(HERE, "..", "orb_slam2_with_comment_b200", "csrc", "og_octree.cuh")
+    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(["g++", "-std=c++14", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-x", "c++", src, "-o", out])
+    lib = C.CDLL(out)
+    lib.ogm_octree.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    return lib
+
+
+def run_model(lib, cand, width, height, N):
+    xy = (cand["y"].astype(np.uint32) << 16) | cand["x"].astype(np.uint32)
+    resp = cand["response"].astype(np.uint8)
+    cap = N + 1024
+    oxy = np.zeros(cap, np.uint32)
+    orr = np.zeros(cap, np.uint8)
+    n = lib.ogm_octree(xy.ctypes.data, resp.ctypes.data, len(cand), width, height, N, oxy.ctypes.data, orr.ctypes.data, cap)
+    assert n >= 0
+    return (oxy[:n] & 0xffff).astype(np.float32), (oxy[:n] >> 16).astype(np.float32), orr[:n].astype(np.float32)
+
+
+def check(lib, oracle, cand, width, height, N):
+    exp = ol.octree(oracle, "orbo", cand, 16, 16 + width, 16, 16 + height, N)
+    x, y, r = run_model(lib, cand, width, height, N)
+    assert len(x) == len(exp)
+    assert np.array_equal(x, exp["x"]) and np.array_equal(y, exp["y"]) and np.array_equal(r, exp["response"])
+    return len(exp)
+
+
+@pytest.mark.parametrize("shape", [(1241, 376, 2000), (640, 480, 1000), (752, 480, 1200), (320, 240, 4000)])
+def test_model_on_real_candidates(model, oracle, shape):
+    w, h, nf = shape
+    ex = ol.Extractor(oracle, "orbo", nf, 1.2, 8, 20, 7)
+    _, quota, _ = ex.tables()
+    for gen, seed in ((synth.g_rects, 21), (synth.g_blurnoise, 22), (synth.g_uniform, 23)):
+        ex.extract(gen(w, h, seed))
+        for l in range(8):
+            cand = ex.level_points(l, 0)
+            lw, lh = ex.level(l).shape[1], ex.level(l).shape[0]
+            n = check(model, oracle, cand, lw - 32, lh - 32, int(quota[l]))
+            assert n <= max(int(quota[l]) + 3, 4 * round((lw - 32) / (lh - 32)))
+
+
+def test_model_random_stress(model, oracle, refso):
+    rs = np.random.RandomState(5)
+    for it in range(300):
+        width, height = int(rs.randint(30, 400)), int(rs.randint(30, 200))
+        if round(width / height) < 1:
+            continue
+        M = int(rs.randint(0, 600))
+        N = int(rs.randint(1, 200))
+        # distinct integer positions (FAST never yields two keypoints on one pixel), clustered sometimes
+        if it % 3 == 0:
+            xs = np.clip(rs.normal(width / 2, width / 12, M * 2), 3, width - 4).astype(int)
+            ys = np.clip(rs.normal(height / 2, height / 12, M * 2), 3, height - 4).astype(int)
+        else:
+            xs = rs.randint(3, width - 3, M * 2)
+            ys = rs.randint(3, height - 3, M * 2)
+        pts = np.unique(np.stack([ys, xs], 1), axis=0)
+        pts = pts[rs.permutation(len(pts))][:M]
+        cand = np.zeros(len(pts), ol.KP_DTYPE)
+        cand["x"], cand["y"] = pts[:, 1], pts[:, 0]
+        cand["response"] = rs.randint(7, 60 if it % 2 else 255, len(pts))
+        check(model, oracle, cand, width, height, N)
+        # the restated octree is itself pinned to the compiled reference on the same inputs
+        a = ol.octree(oracle, "orbo", cand, 16, 16 + width, 16, 16 + height, N)
+        b = ol.octree(refso, "orbref", cand, 16, 16 + width, 16, 16 + height, N)
+        assert a.tobytes() == b.tobytes()
