@@ -90,6 +90,11 @@ int orbgpu_extractor_stream(orbgpu_extractor* ex, void** stream_out);
 /* Number of kernels the last extract call launched (for bench.py's gpu_launches). */
 int orbgpu_extractor_last_launches(const orbgpu_extractor* ex);
 
+/* Per-stage device time of the last extract call, measured with CUDA events on the extractor's stream:
+ * ms5 = { pyramid (level 0 + 7 resizes), FAST cells, octree, blur (8 levels), orientation+descriptors }. */
+int orbgpu_extractor_set_profiling(orbgpu_extractor* ex, int enable);
+int orbgpu_extractor_stage_ms(orbgpu_extractor* ex, float* ms5);
+
 /* mvImagePyramid (ORBextractor.h:86, filled by ComputePyramid :1107-1132) of frame `frame` of the last call.
  * bordered != 0 copies the (w+38) x (h+38) buffer with its 19-px BORDER_REFLECT_101 frame, else the w x h level. */
 int orbgpu_extractor_level_dims(const orbgpu_extractor* ex, int level, int* width, int* height);

@@ -60,6 +60,9 @@ struct orbgpu_extractor {
     uint8_t* d_desc = nullptr;
     size_t cap_pyr = 0, cap_cells = 0, cap_taps = 0, cap_cand = 0, cap_sel = 0, cap_ot = 0, cap_cellcount = 0;
     int last_batch = 0, last_launches = 0;
+    // optional per-stage timing (cudaEvents on the launching stream)
+    bool profiling = false;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 namespace {
@@ -262,6 +265,8 @@ int launch_extract(orbgpu_extractor* ex, const uint8_t* d_images, int batch, siz
     P.kp_cap = kp_capacity;
     cudaStream_t st = ex->stream;
     int launches = 0;
+    auto mark = [&](int i) { if (ex->profiling) cudaEventRecord(ex->ev[i], st); };
+    mark(0);
     {
         const og::Level& L = P.lv[0];
         dim3 grid((L.pitch / 4 + 127) / 128, L.rows, batch);
@@ -274,19 +279,24 @@ int launch_extract(orbgpu_extractor* ex, const uint8_t* d_images, int batch, siz
         og::k_resize<<<grid, 128, 0, st>>>(P, l);
         ++launches;
     }
+    mark(1);
     og::k_fast_cells<<<dim3(P.total_cells, batch), og::kFastThreads, 0, st>>>(P);
     ++launches;
+    mark(2);
     og::k_octree<<<dim3(P.n_levels, batch), og::kOctThreads, 0, st>>>(P);
     ++launches;
+    mark(3);
     for (int l = 0; l < P.n_levels; ++l) {
         const og::Level& L = P.lv[l];
         dim3 grid((L.w + og::kBlurTW - 1) / og::kBlurTW, (L.h + og::kBlurTH - 1) / og::kBlurTH, batch);
         og::k_blur<<<grid, og::kBlurThreads, 0, st>>>(P, l);
         ++launches;
     }
+    mark(4);
     og::k_orient_desc<<<dim3((ex->kp_cap + og::kDescWarps - 1) / og::kDescWarps, batch), og::kDescWarps * 32, 0, st>>>(
         P, d_kp, d_desc, d_counts);
     ++launches;
+    mark(5);
     OG_CUDA(cudaGetLastError());
     ex->last_batch = batch;
     ex->last_launches = launches;
@@ -420,6 +430,7 @@ int orbgpu_extractor_destroy(orbgpu_extractor* ex) {
     if (!ex) return ORBGPU_OK;
     cudaSetDevice(ex->device);
     if (ex->stream) { cudaStreamSynchronize(ex->stream); cudaStreamDestroy(ex->stream); }
+    for (int i = 0; i < 6; ++i) if (ex->ev[i]) cudaEventDestroy(ex->ev[i]);
     void* ptrs[] = {ex->d_pyr, ex->d_blur, ex->d_images, ex->d_cells, ex->d_taps, ex->d_cell_count, ex->d_cand_xy,
                     ex->d_cand_resp, ex->d_ot, ex->d_sel_xy, ex->d_sel_resp, ex->d_sel_count, ex->d_counts, ex->d_kp, ex->d_desc};
     for (void* p : ptrs) if (p) cudaFree(p);
@@ -509,6 +520,23 @@ int orbgpu_extractor_stream(orbgpu_extractor* ex, void** stream_out) {
 }
 
 int orbgpu_extractor_last_launches(const orbgpu_extractor* ex) { return ex ? ex->last_launches : 0; }
+
+int orbgpu_extractor_set_profiling(orbgpu_extractor* ex, int enable) {
+    if (!ex) return fail(ORBGPU_ERR_ARG, "null extractor");
+    OG_CUDA(cudaSetDevice(ex->device));
+    if (enable && !ex->ev[0])
+        for (int i = 0; i < 6; ++i) OG_CUDA(cudaEventCreate(&ex->ev[i]));
+    ex->profiling = enable != 0;
+    return ORBGPU_OK;
+}
+
+int orbgpu_extractor_stage_ms(orbgpu_extractor* ex, float* ms5) {
+    if (!ex || !ms5 || !ex->ev[0]) return fail(ORBGPU_ERR_ARG, "profiling was not enabled");
+    OG_CUDA(cudaSetDevice(ex->device));
+    OG_CUDA(cudaEventSynchronize(ex->ev[5]));
+    for (int i = 0; i < 5; ++i) OG_CUDA(cudaEventElapsedTime(&ms5[i], ex->ev[i], ex->ev[i + 1]));
+    return ORBGPU_OK;
+}
 
 int orbgpu_extractor_level_dims(const orbgpu_extractor* ex, int level, int* width, int* height) {
     if (!ex || level < 0 || level >= ex->nlevels || ex->cur_w == 0) return fail(ORBGPU_ERR_ARG, "bad level or no frame processed yet");

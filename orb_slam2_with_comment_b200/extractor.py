@@ -93,6 +93,16 @@ class ORBextractor:
     def last_launches(self) -> int:
         return self._lib.orbgpu_extractor_last_launches(self._h)
 
+    STAGES = ("pyramid", "fast_cells", "octree", "blur", "orient_desc")
+
+    def set_profiling(self, on: bool):
+        capi.check(self._lib.orbgpu_extractor_set_profiling(self._h, int(on)))
+
+    def stage_ms(self):
+        ms = np.zeros(5, np.float32)
+        capi.check(self._lib.orbgpu_extractor_stage_ms(self._h, ms.ctypes.data))
+        return dict(zip(self.STAGES, (float(v) for v in ms)))
+
     # ---- mvImagePyramid (ORBextractor.h:86) and stage taps
     def level_dims(self, level):
         w, h = C.c_int(), C.c_int()
