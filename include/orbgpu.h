@@ -115,6 +115,137 @@ int orbgpu_extractor_read_blurred(orbgpu_extractor* ex, int frame, int level, ui
 int orbgpu_octree(orbgpu_extractor* ex, const orbgpu_keypoint* candidates, int n, int min_x, int max_x, int min_y,
                   int max_y, int n_features, orbgpu_keypoint* out, int capacity, int* n_out);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * Matching — replaces the Hamming path of ORBmatcher (ORBmatcher.h:37-102)
+ *
+ * ORBmatcher's search functions read Frame / KeyFrame / MapPoint members; the C ABI takes flat, read-only views of
+ * exactly those members, concatenated over a batch of frames, so one call matches many independent frame pairs
+ * (the unit the path shards by).  The C++ shell (csrc/host/ORBmatcher.cc) packs one frame per call.
+ * ---------------------------------------------------------------------------------------------- */
+#define ORBGPU_GRID_COLS 64 /* FRAME_GRID_COLS, Frame.h:38 */
+#define ORBGPU_GRID_ROWS 48 /* FRAME_GRID_ROWS, Frame.h:37 */
+#define ORBGPU_TH_LOW 50    /* ORBmatcher.cc:38 */
+#define ORBGPU_TH_HIGH 100  /* ORBmatcher.cc:37 */
+#define ORBGPU_HISTO_LENGTH 30 /* ORBmatcher.cc:39 */
+
+typedef struct orbgpu_matcher orbgpu_matcher;
+
+/* A set of frames (Frame or KeyFrame objects).  Frame f owns keypoints [kp_off[f], kp_off[f+1]). */
+typedef struct orbgpu_frame_set {
+    int32_t n_frames;
+    const int32_t* kp_off;          /* [n_frames+1]                                                              */
+    const orbgpu_keypoint* keys_un; /* mvKeysUn: pt, octave, angle are read                                      */
+    const uint8_t* desc;            /* mDescriptors rows, 32 contiguous bytes each (ORBmatcher.cc:1903-1904)     */
+    const float* u_right;           /* mvuRight; NULL means -1 everywhere (monocular)                            */
+    const uint8_t* kp_flags;        /* per keypoint; meaning is stated per search function; NULL means 0         */
+    const float* grid;              /* [n_frames][4] mnMinX, mnMinY, mfGridElementWidthInv, mfGridElementHeightInv
+                                       (Frame.cc:101-102; projection search only, else NULL)                      */
+    /* DBoW2::FeatureVector of every frame (std::map<NodeId, vector<unsigned>>, FeatureVector.h:21-22), BoW searches
+       only: frame f owns nodes [fv_node_off[f], fv_node_off[f+1]), ascending ids; node k owns the feature indices
+       fv_feat[fv_feat_off[k] .. fv_feat_off[k+1]) (frame-local keypoint indices, in vector order).  As in DBoW2
+       (FeatureVector::addFeature is called once per feature, TemplatedVocabulary.h:1195) a keypoint index appears
+       at most once among a frame's nodes. */
+    const int32_t* fv_node_off;     /* [n_frames+1]     */
+    const int32_t* fv_node_id;      /* [total nodes]    */
+    const int32_t* fv_feat_off;     /* [total nodes+1]  */
+    const int32_t* fv_feat;         /* [total features] */
+} orbgpu_frame_set;
+
+/* The local map points handed to SearchByProjection(Frame&, vector<MapPoint*>&, th) (ORBmatcher.cc:59), per frame:
+ * frame f is matched against map points [mp_off[f], mp_off[f+1]) in vector order. */
+typedef struct orbgpu_mappoint_set {
+    const int32_t* mp_off;     /* [n_frames+1]                                                */
+    const float* proj_x;       /* mTrackProjX                                                 */
+    const float* proj_y;       /* mTrackProjY                                                 */
+    const float* proj_xr;      /* mTrackProjXR (read only where the frame has mvuRight > 0)   */
+    const float* view_cos;     /* mTrackViewCos                                               */
+    const int32_t* level;      /* mnTrackScaleLevel                                           */
+    const uint8_t* flags;      /* bit0 mbTrackInView, bit1 isBad(), bit2 Observations() > 0   */
+    const uint8_t* desc;       /* GetDescriptor(), 32 B each                                  */
+} orbgpu_mappoint_set;
+
+int orbgpu_matcher_create(orbgpu_matcher** out, int device);
+int orbgpu_matcher_destroy(orbgpu_matcher* m);
+int orbgpu_matcher_sync(orbgpu_matcher* m);
+int orbgpu_matcher_stream(orbgpu_matcher* m, void** stream_out);
+int orbgpu_matcher_last_launches(const orbgpu_matcher* m);
+/* Device time of the last search call (kernels only, CUDA events on the matcher's stream; synchronises) and the
+ * number of 256-bit distance evaluations its kernels performed. */
+int orbgpu_matcher_last_stats(orbgpu_matcher* m, float* kernel_ms, int64_t* distance_evals);
+/* Kernel selection of the BoW-node scans: a node pair with at least min_queries x min_candidates descriptors is
+ * scanned by the register-tiled kernel (one thread owns several queries, candidates are staged in shared memory),
+ * smaller ones by the warp-per-query kernel.  Defaults 512 / 256; min_queries <= 0 disables the tiled kernel.
+ * queries_per_thread (4 or 8, 0 = keep) is the register tile of the tiled kernel.  Results do not depend on any
+ * of these. */
+int orbgpu_matcher_configure(orbgpu_matcher* m, int min_queries, int min_candidates, int queries_per_thread);
+
+/* Device-resident copies of the views above (key frames live for many searches: upload once, match often).
+ * The small per-frame offset arrays are also kept on the host side of the handle. */
+typedef struct orbgpu_frame_set_dev orbgpu_frame_set_dev;
+typedef struct orbgpu_mappoint_set_dev orbgpu_mappoint_set_dev;
+int orbgpu_frame_set_upload(orbgpu_matcher* m, const orbgpu_frame_set* host, orbgpu_frame_set_dev** out);
+int orbgpu_frame_set_release(orbgpu_frame_set_dev* fs);
+int orbgpu_mappoint_set_upload(orbgpu_matcher* m, const orbgpu_mappoint_set* host, int n_frames, orbgpu_mappoint_set_dev** out);
+int orbgpu_mappoint_set_release(orbgpu_mappoint_set_dev* mps);
+
+/* ORBmatcher::DescriptorDistance (ORBmatcher.cc:1901-1917) for n independent descriptor pairs, on the device. */
+int orbgpu_hamming_pairs(orbgpu_matcher* m, const uint8_t* a, const uint8_t* b, int n, int32_t* dist_out);
+
+/* ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th) (ORBmatcher.cc:59-155) for every frame of
+ * `frames` against its slice of `mps`.  frames->kp_flags: 0 = mvpMapPoints[idx] is NULL, 1 = it holds a MapPoint
+ * with Observations() > 0 (candidate skipped, :108-110), 2 = it holds one with no observations.
+ * Outputs (any may be NULL):
+ *   kp_match[total keypoints]  index (within the frame's map-point slice) of the map point written into
+ *                              F.mvpMapPoints[idx] by this call, -1 where the call wrote nothing
+ *   mp_best_idx / mp_best_dist / mp_second_dist [total map points]  bestIdx, bestDist, bestDist2 of every map point
+ *                              that reached the selection (:127-139); -1 / 256 / 256 otherwise
+ *   nmatches[n_frames]         the function's return value per frame */
+int orbgpu_search_by_projection(orbgpu_matcher* m, const orbgpu_frame_set* frames, const orbgpu_mappoint_set* mps,
+                                const float* scale_factors, int n_levels, float th, float nnratio, int32_t* kp_match,
+                                int32_t* mp_best_idx, int32_t* mp_best_dist, int32_t* mp_second_dist, int32_t* nmatches);
+
+/* ORBmatcher::SearchForTriangulation (ORBmatcher.cc:783-975) for n_pairs keyframe pairs; pair p matches frame
+ * idx1[p] of set1 against frame idx2[p] of set2.  kp_flags bit0 = the keypoint already has a MapPoint (skipped,
+ * :846,:868).  f12[p] = the 3x3 fundamental matrix, row major; epipole[p] = (ex, ey) as computed at :790-799.
+ * match12[match_off[p] + i] receives the index matched to keypoint i of frame idx1[p] or -1 (vMatches12, :964-972);
+ * match_dist (may be NULL) the Hamming distance of that match. */
+int orbgpu_search_for_triangulation(orbgpu_matcher* m, const orbgpu_frame_set* set1, const orbgpu_frame_set* set2,
+                                    int n_pairs, const int32_t* idx1, const int32_t* idx2, const float* f12,
+                                    const float* epipole, const float* scale_factors, const float* level_sigma2,
+                                    int n_levels, int only_stereo, int check_orientation, const int64_t* match_off,
+                                    int32_t* match12, int32_t* match_dist, int32_t* nmatches);
+
+/* The BoW-node scans ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, ...) (ORBmatcher.cc:635-768; th_inclusive = 0,
+ * `bestDist1 < TH_LOW` at :711) and SearchByBoW(KeyFrame*, Frame&, ...) (:211-344; th_inclusive = 1, `<=` at :284).
+ * A brute-force scan is the same call with one node holding every index.  kp_flags bit0 = the keypoint has a valid
+ * (non-NULL, !isBad) MapPoint: required of the queries of set1, and of the candidates of set2 when
+ * require_mp2 != 0 (the KeyFrame-KeyFrame variant, :681-688).  match12 as above (the index in frame 2 whose MapPoint
+ * the reference stores in vpMatches12[idx1]); for the KeyFrame-Frame variant the reference indexes its output by the
+ * frame-2 keypoint instead — the shell transposes. */
+int orbgpu_search_by_bow(orbgpu_matcher* m, const orbgpu_frame_set* set1, const orbgpu_frame_set* set2, int n_pairs,
+                         const int32_t* idx1, const int32_t* idx2, float nnratio, int check_orientation, int th_low,
+                         int th_inclusive, int require_mp2, const int64_t* match_off, int32_t* match12,
+                         int32_t* match_dist, int32_t* nmatches);
+
+/* Device-resident variants: the frame / map-point sets are uploaded handles, every OUTPUT pointer is a device
+ * pointer on the matcher's device (NULL allowed where the host variant allows it), the per-pair control arrays
+ * (idx1, idx2, match_off, f12, epipole, scale tables) stay host pointers.  The work is enqueued on the matcher's
+ * stream and the call returns without synchronising (orbgpu_matcher_sync waits). */
+int orbgpu_search_by_projection_dev(orbgpu_matcher* m, const orbgpu_frame_set_dev* frames, const orbgpu_mappoint_set_dev* mps,
+                                    const float* scale_factors, int n_levels, float th, float nnratio, int32_t* kp_match_dev,
+                                    int32_t* mp_best_idx_dev, int32_t* mp_best_dist_dev, int32_t* mp_second_dist_dev,
+                                    int32_t* nmatches_dev);
+int orbgpu_search_for_triangulation_dev(orbgpu_matcher* m, const orbgpu_frame_set_dev* set1, const orbgpu_frame_set_dev* set2,
+                                        int n_pairs, const int32_t* idx1, const int32_t* idx2, const float* f12,
+                                        const float* epipole, const float* scale_factors, const float* level_sigma2,
+                                        int n_levels, int only_stereo, int check_orientation, const int64_t* match_off,
+                                        int32_t* match12_dev, int32_t* match_dist_dev, int32_t* nmatches_dev);
+int orbgpu_search_by_bow_dev(orbgpu_matcher* m, const orbgpu_frame_set_dev* set1, const orbgpu_frame_set_dev* set2, int n_pairs,
+                             const int32_t* idx1, const int32_t* idx2, float nnratio, int check_orientation, int th_low,
+                             int th_inclusive, int require_mp2, const int64_t* match_off, int32_t* match12_dev,
+                             int32_t* match_dist_dev, int32_t* nmatches_dev);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,1 +1,337 @@
-extern "C" int orbm_placeholder(){return 0;}
+// match_oracle — TEST INFRASTRUCTURE: CPU restatement ("port") of the Hamming path of the reference ORBmatcher,
+// over the same flat views the C ABI takes (include/orbgpu.h is included for the struct layouts only).
+//
+// Follows /root/reference/src/ORBmatcher.cc function by function (lines cited), plus the two Frame members the
+// projection search calls: Frame::AssignFeaturesToGrid / PosInGrid (Frame.cc:232-247, :412-422) and
+// Frame::GetFeaturesInArea (Frame.cc:353-410).  ORBmatcher.cc cannot be compiled here (it needs OpenCV, DBoW2 and
+// the Frame/KeyFrame/MapPoint classes), and the reference ships no tests or golden vectors for it, so this
+// restatement is pinned only by (a) DescriptorDistance against an independent popcount, (b) hand-checkable
+// micro-cases in tests/test_oracle_matcher.py and (c) an independent Python restatement of the same functions
+// (tests/golden/gen_matcher_golden.py -> committed fixtures).  Parity of these functions is therefore "unpinned by
+// the reference" (DESIGN.md §Oracle).  Build with -ffp-contract=off.
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../include/orbgpu.h"
+
+namespace {
+
+const int TH_HIGH = 100, TH_LOW = 50, HISTO_LENGTH = 30;  // ORBmatcher.cc:37-39
+
+// ORBmatcher::DescriptorDistance, ORBmatcher.cc:1901-1917 (SWAR bit count over eight 32-bit words)
+int descriptor_distance(const uint8_t* a, const uint8_t* b) {
+    int32_t pa[8], pb[8];
+    memcpy(pa, a, 32);
+    memcpy(pb, b, 32);
+    int dist = 0;
+    for (int i = 0; i < 8; i++) {
+        unsigned int v = pa[i] ^ pb[i];
+        v = v - ((v >> 1) & 0x55555555);
+        v = (v & 0x33333333) + ((v >> 2) & 0x33333333);
+        dist += (((v + (v >> 4)) & 0xF0F0F0F) * 0x1010101) >> 24;
+    }
+    return dist;
+}
+
+// ORBmatcher::ComputeThreeMaxima, ORBmatcher.cc:1854-1895
+void three_maxima(const std::vector<int>* histo, int L, int& ind1, int& ind2, int& ind3) {
+    int max1 = 0, max2 = 0, max3 = 0;
+    for (int i = 0; i < L; i++) {
+        const int s = (int)histo[i].size();
+        if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+        else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+        else if (s > max3) { max3 = s; ind3 = i; }
+    }
+    if (max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+    else if (max3 < 0.1f * (float)max1) { ind3 = -1; }
+}
+
+// the rotation-histogram idiom shared by the BoW and triangulation searches (e.g. :718-728)
+int rot_bin(float a1, float a2) {
+    const float factor = 1.0f / HISTO_LENGTH;
+    float rot = a1 - a2;
+    if (rot < 0.0) rot += 360.0f;
+    int bin = (int)round(rot * factor);
+    if (bin == HISTO_LENGTH) bin = 0;
+    return bin;
+}
+
+struct Grid {  // Frame::mGrid, Frame.h:161
+    std::vector<int> cell[ORBGPU_GRID_COLS][ORBGPU_GRID_ROWS];
+};
+
+// Frame::AssignFeaturesToGrid + PosInGrid, Frame.cc:232-247, :412-422
+void assign_grid(const orbgpu_keypoint* k, int n, const float* g, Grid& G) {
+    for (int i = 0; i < n; i++) {
+        const int px = (int)round((k[i].x - g[0]) * g[2]);
+        const int py = (int)round((k[i].y - g[1]) * g[3]);
+        if (px < 0 || px >= ORBGPU_GRID_COLS || py < 0 || py >= ORBGPU_GRID_ROWS) continue;
+        G.cell[px][py].push_back(i);
+    }
+}
+
+// Frame::GetFeaturesInArea, Frame.cc:353-410
+void features_in_area(const Grid& G, const orbgpu_keypoint* k, const float* g, float x, float y, float r, int minLevel,
+                      int maxLevel, std::vector<int>& out) {
+    out.clear();
+    const int nMinCellX = std::max(0, (int)floor((x - g[0] - r) * g[2]));
+    if (nMinCellX >= ORBGPU_GRID_COLS) return;
+    const int nMaxCellX = std::min((int)ORBGPU_GRID_COLS - 1, (int)ceil((x - g[0] + r) * g[2]));
+    if (nMaxCellX < 0) return;
+    const int nMinCellY = std::max(0, (int)floor((y - g[1] - r) * g[3]));
+    if (nMinCellY >= ORBGPU_GRID_ROWS) return;
+    const int nMaxCellY = std::min((int)ORBGPU_GRID_ROWS - 1, (int)ceil((y - g[1] + r) * g[3]));
+    if (nMaxCellY < 0) return;
+    const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+    for (int ix = nMinCellX; ix <= nMaxCellX; ix++)
+        for (int iy = nMinCellY; iy <= nMaxCellY; iy++) {
+            const std::vector<int>& vCell = G.cell[ix][iy];
+            for (size_t j = 0; j < vCell.size(); j++) {
+                const orbgpu_keypoint& kp = k[vCell[j]];
+                if (bCheckLevels) {
+                    if (kp.octave < minLevel) continue;
+                    if (maxLevel >= 0 && kp.octave > maxLevel) continue;
+                }
+                const float distx = kp.x - x, disty = kp.y - y;
+                if (fabs(distx) < r && fabs(disty) < r) out.push_back(vCell[j]);
+            }
+        }
+}
+
+// ORBmatcher::CheckDistEpipolarLine, ORBmatcher.cc:173-196 (F12 row major)
+bool check_epipolar(const orbgpu_keypoint& kp1, const orbgpu_keypoint& kp2, const float* F, const float* sigma2) {
+    const float a = kp1.x * F[0] + kp1.y * F[3] + F[6];
+    const float b = kp1.x * F[1] + kp1.y * F[4] + F[7];
+    const float c = kp1.x * F[2] + kp1.y * F[5] + F[8];
+    const float num = a * kp2.x + b * kp2.y + c;
+    const float den = a * a + b * b;
+    if (den == 0) return false;
+    const float dsqr = num * num / den;
+    return dsqr < 3.84 * sigma2[kp2.octave];
+}
+
+}  // namespace
+
+extern "C" {
+
+int orbm_hamming(const uint8_t* a, const uint8_t* b) { return descriptor_distance(a, b); }
+
+// ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th), ORBmatcher.cc:59-155
+void orbm_search_by_projection(const orbgpu_frame_set* fs, const orbgpu_mappoint_set* mp, const float* scale, int n_levels,
+                               float th, float nnratio, int32_t* kp_match, int32_t* mp_best_idx, int32_t* mp_best_dist,
+                               int32_t* mp_second_dist, int32_t* nmatches_out) {
+    for (int f = 0; f < fs->n_frames; ++f) {
+        const int k0 = fs->kp_off[f], n = fs->kp_off[f + 1] - k0;
+        const orbgpu_keypoint* keys = fs->keys_un + k0;
+        const float* g = fs->grid + 4 * f;
+        Grid G;
+        assign_grid(keys, n, g, G);
+        std::vector<uint8_t> state(n, 0);
+        if (fs->kp_flags) for (int i = 0; i < n; ++i) state[i] = fs->kp_flags[k0 + i];
+        for (int i = 0; i < n; ++i) if (kp_match) kp_match[k0 + i] = -1;
+        int nmatches = 0;
+        const bool bFactor = th != 1.0;
+        std::vector<int> vIndices;
+        for (int q = mp->mp_off[f]; q < mp->mp_off[f + 1]; ++q) {
+            if (mp_best_idx) mp_best_idx[q] = -1;
+            if (mp_best_dist) mp_best_dist[q] = 256;
+            if (mp_second_dist) mp_second_dist[q] = 256;
+            if (!(mp->flags[q] & 1)) continue;   // mbTrackInView
+            if (mp->flags[q] & 2) continue;      // isBad()
+            const int lvl = mp->level[q];
+            float r = mp->view_cos[q] > 0.998 ? 2.5f : 4.0f;  // RadiusByViewingCos, :157-163
+            if (bFactor) r *= th;
+            features_in_area(G, keys, g, mp->proj_x[q], mp->proj_y[q], r * scale[lvl], lvl - 1, lvl, vIndices);
+            if (vIndices.empty()) continue;
+            const uint8_t* d = mp->desc + (size_t)q * 32;
+            int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+            for (size_t j = 0; j < vIndices.size(); ++j) {
+                const int idx = vIndices[j];
+                if (state[idx] == 1) continue;  // mvpMapPoints[idx] with Observations()>0, :108-110
+                if (fs->u_right && fs->u_right[k0 + idx] > 0) {
+                    const float er = fabs(mp->proj_xr[q] - fs->u_right[k0 + idx]);
+                    if (er > r * scale[lvl]) continue;
+                }
+                const int dist = descriptor_distance(d, fs->desc + (size_t)(k0 + idx) * 32);
+                if (dist < bestDist) {
+                    bestDist2 = bestDist; bestDist = dist;
+                    bestLevel2 = bestLevel; bestLevel = keys[idx].octave;
+                    bestIdx = idx;
+                } else if (dist < bestDist2) {
+                    bestLevel2 = keys[idx].octave;
+                    bestDist2 = dist;
+                }
+            }
+            if (mp_best_idx) mp_best_idx[q] = bestIdx;
+            if (mp_best_dist) mp_best_dist[q] = bestDist;
+            if (mp_second_dist) mp_second_dist[q] = bestDist2;
+            if (bestDist <= TH_HIGH) {
+                if (bestLevel == bestLevel2 && bestDist > nnratio * bestDist2) continue;
+                state[bestIdx] = (mp->flags[q] & 4) ? 1 : 2;   // F.mvpMapPoints[bestIdx] = pMP
+                if (kp_match) kp_match[k0 + bestIdx] = q - mp->mp_off[f];
+                nmatches++;
+            }
+        }
+        if (nmatches_out) nmatches_out[f] = nmatches;
+    }
+}
+
+// ORBmatcher::SearchForTriangulation, ORBmatcher.cc:783-975
+void orbm_search_for_triangulation(const orbgpu_frame_set* s1, const orbgpu_frame_set* s2, int n_pairs, const int32_t* idx1v,
+                                   const int32_t* idx2v, const float* f12, const float* epipole, const float* scale,
+                                   const float* sigma2, int n_levels, int only_stereo, int check_orientation,
+                                   const int64_t* match_off, int32_t* match12, int32_t* match_dist, int32_t* nmatches_out) {
+    for (int p = 0; p < n_pairs; ++p) {
+        const int fa = idx1v[p], fb = idx2v[p];
+        const int ka = s1->kp_off[fa], na = s1->kp_off[fa + 1] - ka;
+        const int kb = s2->kp_off[fb];
+        const orbgpu_keypoint* K1 = s1->keys_un + ka;
+        const orbgpu_keypoint* K2 = s2->keys_un + kb;
+        const float ex = epipole[2 * p], ey = epipole[2 * p + 1];
+        const float* F = f12 + 9 * p;
+        int nmatches = 0;
+        std::vector<int> vMatches12(na, -1), vDist(na, -1);
+        std::vector<int> rotHist[HISTO_LENGTH];
+        int a = s1->fv_node_off[fa], aend = s1->fv_node_off[fa + 1];
+        int b = s2->fv_node_off[fb], bend = s2->fv_node_off[fb + 1];
+        while (a != aend && b != bend) {
+            if (s1->fv_node_id[a] == s2->fv_node_id[b]) {
+                for (int i1 = s1->fv_feat_off[a]; i1 < s1->fv_feat_off[a + 1]; i1++) {
+                    const int idx1 = s1->fv_feat[i1];
+                    if (s1->kp_flags && (s1->kp_flags[ka + idx1] & 1)) continue;   // pMP1 set, :846
+                    const bool bStereo1 = s1->u_right && s1->u_right[ka + idx1] >= 0;
+                    if (only_stereo && !bStereo1) continue;
+                    const orbgpu_keypoint& kp1 = K1[idx1];
+                    const uint8_t* d1 = s1->desc + (size_t)(ka + idx1) * 32;
+                    int bestDist = TH_LOW, bestIdx2 = -1;
+                    for (int i2 = s2->fv_feat_off[b]; i2 < s2->fv_feat_off[b + 1]; i2++) {
+                        const int idx2 = s2->fv_feat[i2];
+                        if (s2->kp_flags && (s2->kp_flags[kb + idx2] & 1)) continue;  // vbMatched2 is never set, :868
+                        const bool bStereo2 = s2->u_right && s2->u_right[kb + idx2] >= 0;
+                        if (only_stereo && !bStereo2) continue;
+                        const int dist = descriptor_distance(d1, s2->desc + (size_t)(kb + idx2) * 32);
+                        if (dist > TH_LOW || dist > bestDist) continue;
+                        const orbgpu_keypoint& kp2 = K2[idx2];
+                        if (!bStereo1 && !bStereo2) {
+                            const float distex = ex - kp2.x, distey = ey - kp2.y;
+                            if (distex * distex + distey * distey < 100 * scale[kp2.octave]) continue;
+                        }
+                        if (check_epipolar(kp1, kp2, F, sigma2)) { bestIdx2 = idx2; bestDist = dist; }
+                    }
+                    if (bestIdx2 >= 0) {
+                        vMatches12[idx1] = bestIdx2;
+                        vDist[idx1] = bestDist;
+                        nmatches++;
+                        if (check_orientation) rotHist[rot_bin(kp1.angle, K2[bestIdx2].angle)].push_back(idx1);
+                    }
+                }
+                a++; b++;
+            } else if (s1->fv_node_id[a] < s2->fv_node_id[b]) {
+                while (a != aend && s1->fv_node_id[a] < s2->fv_node_id[b]) a++;   // lower_bound, :932
+            } else {
+                while (b != bend && s2->fv_node_id[b] < s1->fv_node_id[a]) b++;
+            }
+        }
+        if (check_orientation) {
+            int ind1 = -1, ind2 = -1, ind3 = -1;
+            three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+            for (int i = 0; i < HISTO_LENGTH; i++) {
+                if (i == ind1 || i == ind2 || i == ind3) continue;
+                for (size_t j = 0; j < rotHist[i].size(); j++) { vMatches12[rotHist[i][j]] = -1; vDist[rotHist[i][j]] = -1; nmatches--; }
+            }
+        }
+        for (int i = 0; i < na; ++i) {
+            match12[match_off[p] + i] = vMatches12[i];
+            if (match_dist) match_dist[match_off[p] + i] = vDist[i];
+        }
+        if (nmatches_out) nmatches_out[p] = nmatches;
+    }
+}
+
+// ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, ...) :635-768 and SearchByBoW(KeyFrame*, Frame&, ...) :211-344
+void orbm_search_by_bow(const orbgpu_frame_set* s1, const orbgpu_frame_set* s2, int n_pairs, const int32_t* idx1v,
+                        const int32_t* idx2v, float nnratio, int check_orientation, int th_low, int th_inclusive,
+                        int require_mp2, const int64_t* match_off, int32_t* match12, int32_t* match_dist,
+                        int32_t* nmatches_out) {
+    for (int p = 0; p < n_pairs; ++p) {
+        const int fa = idx1v[p], fb = idx2v[p];
+        const int ka = s1->kp_off[fa], na = s1->kp_off[fa + 1] - ka;
+        const int kb = s2->kp_off[fb], nb = s2->kp_off[fb + 1] - kb;
+        const orbgpu_keypoint* K1 = s1->keys_un + ka;
+        const orbgpu_keypoint* K2 = s2->keys_un + kb;
+        std::vector<int> vMatches12(na, -1), vDist(na, -1);
+        std::vector<bool> vbMatched2(nb, false);
+        std::vector<int> rotHist[HISTO_LENGTH];
+        int nmatches = 0;
+        int a = s1->fv_node_off[fa], aend = s1->fv_node_off[fa + 1];
+        int b = s2->fv_node_off[fb], bend = s2->fv_node_off[fb + 1];
+        while (a != aend && b != bend) {
+            if (s1->fv_node_id[a] == s2->fv_node_id[b]) {
+                for (int i1 = s1->fv_feat_off[a]; i1 < s1->fv_feat_off[a + 1]; i1++) {
+                    const int idx1 = s1->fv_feat[i1];
+                    if (!(s1->kp_flags && (s1->kp_flags[ka + idx1] & 1))) continue;   // !pMP1 || isBad, :673-677
+                    const uint8_t* d1 = s1->desc + (size_t)(ka + idx1) * 32;
+                    int bestDist1 = 256, bestIdx2 = -1, bestDist2 = 256;
+                    for (int i2 = s2->fv_feat_off[b]; i2 < s2->fv_feat_off[b + 1]; i2++) {
+                        const int idx2 = s2->fv_feat[i2];
+                        if (vbMatched2[idx2]) continue;
+                        if (require_mp2 && !(s2->kp_flags && (s2->kp_flags[kb + idx2] & 1))) continue;
+                        const int dist = descriptor_distance(d1, s2->desc + (size_t)(kb + idx2) * 32);
+                        if (dist < bestDist1) { bestDist2 = bestDist1; bestDist1 = dist; bestIdx2 = idx2; }
+                        else if (dist < bestDist2) { bestDist2 = dist; }
+                    }
+                    const bool pass = th_inclusive ? (bestDist1 <= th_low) : (bestDist1 < th_low);
+                    if (pass && static_cast<float>(bestDist1) < nnratio * static_cast<float>(bestDist2)) {
+                        vMatches12[idx1] = bestIdx2;
+                        vDist[idx1] = bestDist1;
+                        vbMatched2[bestIdx2] = true;
+                        if (check_orientation) rotHist[rot_bin(K1[idx1].angle, K2[bestIdx2].angle)].push_back(idx1);
+                        nmatches++;
+                    }
+                }
+                a++; b++;
+            } else if (s1->fv_node_id[a] < s2->fv_node_id[b]) {
+                while (a != aend && s1->fv_node_id[a] < s2->fv_node_id[b]) a++;
+            } else {
+                while (b != bend && s2->fv_node_id[b] < s1->fv_node_id[a]) b++;
+            }
+        }
+        if (check_orientation) {
+            int ind1 = -1, ind2 = -1, ind3 = -1;
+            three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+            for (int i = 0; i < HISTO_LENGTH; i++) {
+                if (i == ind1 || i == ind2 || i == ind3) continue;
+                for (size_t j = 0; j < rotHist[i].size(); j++) { vMatches12[rotHist[i][j]] = -1; vDist[rotHist[i][j]] = -1; nmatches--; }
+            }
+        }
+        for (int i = 0; i < na; ++i) {
+            match12[match_off[p] + i] = vMatches12[i];
+            if (match_dist) match_dist[match_off[p] + i] = vDist[i];
+        }
+        if (nmatches_out) nmatches_out[p] = nmatches;
+    }
+}
+
+// CPU baseline driver: the pairs are split over nthreads std::threads (one pair at a time per thread).
+}  // extern "C"
+
+#include <chrono>
+#include <thread>
+extern "C" double orbm_bench_bow(const orbgpu_frame_set* s1, const orbgpu_frame_set* s2, int n_pairs, const int32_t* idx1v,
+                                 const int32_t* idx2v, float nnratio, int check_orientation, int th_low, int th_inclusive,
+                                 int require_mp2, const int64_t* match_off, int32_t* match12, int32_t* nmatches, int nthreads) {
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; ++t)
+        th.emplace_back([=]() {
+            for (int p = t; p < n_pairs; p += nthreads) {
+                // a one-pair view: same sets, shifted pair arrays
+                orbm_search_by_bow(s1, s2, 1, idx1v + p, idx2v + p, nnratio, check_orientation, th_low, th_inclusive, require_mp2,
+                                   match_off + p, match12, nullptr, nmatches + p);
+            }
+        });
+    for (auto& x : th) x.join();
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}

@@ -35,6 +35,8 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace
 
+int og_fail(int code, const std::string& msg) { return fail(code, msg); }  // shared with og_match.cu
+
 struct orbgpu_extractor {
     int device = 0;
     int nfeatures = 0, nlevels = 0, ini_th = 0, min_th = 0;

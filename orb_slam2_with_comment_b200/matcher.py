@@ -1,0 +1,251 @@
+"""Host-side mirror of ORB_SLAM2::ORBmatcher (/root/reference/include/ORBmatcher.h:37-102) over the C ABI.
+
+The reference's search functions read Frame / KeyFrame / MapPoint members; here those members arrive as flat
+numpy arrays (`FrameSet`, `MapPointSet` = orbgpu_frame_set / orbgpu_mappoint_set of include/orbgpu.h), batched
+over many frames so that one call matches many independent frame pairs.  Same constructor arguments
+(nnratio, checkOri), same constants, same function names and return values (number of matches); the match
+vectors come back as integer index arrays.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import KP_DTYPE
+
+_f32p, _i32p, _u8p, _i64p = C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_uint8), C.POINTER(C.c_int64)
+
+
+class CFrameSet(C.Structure):  # orbgpu_frame_set
+    _fields_ = [("n_frames", C.c_int32), ("kp_off", _i32p), ("keys_un", C.c_void_p), ("desc", _u8p), ("u_right", _f32p),
+                ("kp_flags", _u8p), ("grid", _f32p), ("fv_node_off", _i32p), ("fv_node_id", _i32p), ("fv_feat_off", _i32p),
+                ("fv_feat", _i32p)]
+
+
+class CMapPointSet(C.Structure):  # orbgpu_mappoint_set
+    _fields_ = [("mp_off", _i32p), ("proj_x", _f32p), ("proj_y", _f32p), ("proj_xr", _f32p), ("view_cos", _f32p),
+                ("level", _i32p), ("flags", _u8p), ("desc", _u8p)]
+
+
+def _arr(a, dtype):
+    return None if a is None else np.ascontiguousarray(a, dtype=dtype)
+
+
+def _ptr(a, t):
+    return None if a is None else a.ctypes.data_as(t)
+
+
+class FrameSet:
+    """A batch of Frame / KeyFrame views.  kp_off[f]..kp_off[f+1] are frame f's keypoints."""
+
+    def __init__(self, kp_off, keys_un, desc, u_right=None, kp_flags=None, grid=None, fv_node_off=None, fv_node_id=None,
+                 fv_feat_off=None, fv_feat=None):
+        self.kp_off = _arr(kp_off, np.int32)
+        self.n_frames = len(self.kp_off) - 1
+        self.keys_un = np.ascontiguousarray(keys_un, dtype=KP_DTYPE)
+        self.desc = _arr(desc, np.uint8).reshape(-1, 32)
+        assert len(self.keys_un) == len(self.desc) == self.kp_off[-1]
+        self.u_right = _arr(u_right, np.float32)
+        self.kp_flags = _arr(kp_flags, np.uint8)
+        self.grid = _arr(grid, np.float32)
+        self.fv_node_off, self.fv_node_id = _arr(fv_node_off, np.int32), _arr(fv_node_id, np.int32)
+        self.fv_feat_off, self.fv_feat = _arr(fv_feat_off, np.int32), _arr(fv_feat, np.int32)
+        self.c = CFrameSet(self.n_frames, _ptr(self.kp_off, _i32p), self.keys_un.ctypes.data, _ptr(self.desc, _u8p),
+                           _ptr(self.u_right, _f32p), _ptr(self.kp_flags, _u8p), _ptr(self.grid, _f32p),
+                           _ptr(self.fv_node_off, _i32p), _ptr(self.fv_node_id, _i32p), _ptr(self.fv_feat_off, _i32p),
+                           _ptr(self.fv_feat, _i32p))
+
+    def n_kp(self, f):
+        return int(self.kp_off[f + 1] - self.kp_off[f])
+
+    @staticmethod
+    def single_node(kp_off, keys_un, desc, **kw):
+        """Brute-force view: every frame has one node (id 0) holding all of its keypoint indices in order."""
+        kp_off = np.asarray(kp_off, np.int32)
+        n = len(kp_off) - 1
+        feat = np.concatenate([np.arange(kp_off[f + 1] - kp_off[f], dtype=np.int32) for f in range(n)]) if n else np.zeros(0, np.int32)
+        return FrameSet(kp_off, keys_un, desc, fv_node_off=np.arange(n + 1, dtype=np.int32), fv_node_id=np.zeros(n, np.int32),
+                        fv_feat_off=kp_off.copy(), fv_feat=feat, **kw)
+
+
+class MapPointSet:
+    """The local map points handed to SearchByProjection, per frame (mp_off[f]..mp_off[f+1])."""
+
+    def __init__(self, mp_off, proj_x, proj_y, view_cos, level, flags, desc, proj_xr=None):
+        self.mp_off = _arr(mp_off, np.int32)
+        self.proj_x, self.proj_y = _arr(proj_x, np.float32), _arr(proj_y, np.float32)
+        self.proj_xr = _arr(proj_xr, np.float32)
+        self.view_cos, self.level = _arr(view_cos, np.float32), _arr(level, np.int32)
+        self.flags, self.desc = _arr(flags, np.uint8), _arr(desc, np.uint8).reshape(-1, 32)
+        self.n = int(self.mp_off[-1])
+        self.c = CMapPointSet(_ptr(self.mp_off, _i32p), _ptr(self.proj_x, _f32p), _ptr(self.proj_y, _f32p),
+                              _ptr(self.proj_xr, _f32p), _ptr(self.view_cos, _f32p), _ptr(self.level, _i32p),
+                              _ptr(self.flags, _u8p), _ptr(self.desc, _u8p))
+
+
+def match_offsets(fs1: FrameSet, idx1) -> np.ndarray:
+    """Packed output layout: pair p writes keypoints-of-frame-idx1[p] entries at match_off[p]."""
+    n = np.array([fs1.n_kp(int(f)) for f in idx1], np.int64)
+    off = np.zeros(len(idx1), np.int64)
+    if len(idx1) > 1:
+        off[1:] = np.cumsum(n)[:-1]
+    return off, int(n.sum())
+
+
+def _bind(L):
+    if getattr(L, "_matcher_bound", False):
+        return
+    vp, i, f = C.c_void_p, C.c_int, C.c_float
+    L.orbgpu_matcher_create.argtypes = [C.POINTER(vp), i]
+    L.orbgpu_matcher_destroy.argtypes = [vp]
+    L.orbgpu_matcher_sync.argtypes = [vp]
+    L.orbgpu_matcher_stream.argtypes = [vp, C.POINTER(vp)]
+    L.orbgpu_matcher_last_launches.argtypes = [vp]
+    L.orbgpu_matcher_last_stats.argtypes = [vp, C.POINTER(f), C.POINTER(C.c_int64)]
+    L.orbgpu_matcher_configure.argtypes = [vp, i, i, i]
+    L.orbgpu_frame_set_upload.argtypes = [vp, C.POINTER(CFrameSet), C.POINTER(vp)]
+    L.orbgpu_frame_set_release.argtypes = [vp]
+    L.orbgpu_mappoint_set_upload.argtypes = [vp, C.POINTER(CMapPointSet), i, C.POINTER(vp)]
+    L.orbgpu_mappoint_set_release.argtypes = [vp]
+    L.orbgpu_hamming_pairs.argtypes = [vp, vp, vp, i, vp]
+    L.orbgpu_search_by_projection.argtypes = [vp, C.POINTER(CFrameSet), C.POINTER(CMapPointSet), vp, i, f, f, vp, vp, vp, vp, vp]
+    L.orbgpu_search_by_projection_dev.argtypes = [vp, vp, vp, vp, i, f, f, vp, vp, vp, vp, vp]
+    L.orbgpu_search_for_triangulation.argtypes = [vp, C.POINTER(CFrameSet), C.POINTER(CFrameSet), i, vp, vp, vp, vp, vp, vp, i, i, i,
+                                                  vp, vp, vp, vp]
+    L.orbgpu_search_for_triangulation_dev.argtypes = [vp, vp, vp, i, vp, vp, vp, vp, vp, vp, i, i, i, vp, vp, vp, vp]
+    L.orbgpu_search_by_bow.argtypes = [vp, C.POINTER(CFrameSet), C.POINTER(CFrameSet), i, vp, vp, f, i, i, i, i, vp, vp, vp, vp]
+    L.orbgpu_search_by_bow_dev.argtypes = [vp, vp, vp, i, vp, vp, f, i, i, i, i, vp, vp, vp, vp]
+    L._matcher_bound = True
+
+
+class ORBmatcher:
+    TH_LOW, TH_HIGH, HISTO_LENGTH = 50, 100, 30   # ORBmatcher.cc:37-39
+
+    def __init__(self, nnratio: float = 0.6, checkOri: bool = True, *, device: int = 0):
+        self._lib = capi.lib()
+        _bind(self._lib)
+        self.mfNNratio, self.mbCheckOrientation, self.device = float(nnratio), bool(checkOri), device
+        self._h = C.c_void_p()
+        capi.check(self._lib.orbgpu_matcher_create(C.byref(self._h), device))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.orbgpu_matcher_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def configure(self, min_queries=512, min_candidates=256, queries_per_thread=0):
+        capi.check(self._lib.orbgpu_matcher_configure(self._h, min_queries, min_candidates, queries_per_thread))
+
+    def sync(self):
+        capi.check(self._lib.orbgpu_matcher_sync(self._h))
+
+    def stream(self) -> int:
+        s = C.c_void_p()
+        capi.check(self._lib.orbgpu_matcher_stream(self._h, C.byref(s)))
+        return s.value or 0
+
+    def last_launches(self) -> int:
+        return self._lib.orbgpu_matcher_last_launches(self._h)
+
+    def last_stats(self):
+        ms, ev = C.c_float(0), C.c_int64(0)
+        capi.check(self._lib.orbgpu_matcher_last_stats(self._h, C.byref(ms), C.byref(ev)))
+        return ms.value, ev.value
+
+    # ---- DescriptorDistance (ORBmatcher.cc:1901-1917)
+    def hamming_pairs(self, a: np.ndarray, b: np.ndarray) -> np.ndarray:
+        a = np.ascontiguousarray(a, np.uint8).reshape(-1, 32)
+        b = np.ascontiguousarray(b, np.uint8).reshape(-1, 32)
+        assert a.shape == b.shape
+        out = np.zeros(len(a), np.int32)
+        capi.check(self._lib.orbgpu_hamming_pairs(self._h, a.ctypes.data, b.ctypes.data, len(a), out.ctypes.data))
+        return out
+
+    def DescriptorDistance(self, a, b) -> int:
+        return int(self.hamming_pairs(np.asarray(a).reshape(1, 32), np.asarray(b).reshape(1, 32))[0])
+
+    # ---- SearchByProjection(Frame&, const vector<MapPoint*>&, th) (ORBmatcher.cc:59-155), batched over frames
+    def SearchByProjection(self, frames: FrameSet, mps: MapPointSet, scale_factors, th: float = 3.0):
+        sf = np.ascontiguousarray(scale_factors, np.float32)
+        kp_match = np.full(int(frames.kp_off[-1]), -1, np.int32)
+        best_idx = np.full(mps.n, -1, np.int32)
+        best_dist = np.full(mps.n, 256, np.int32)
+        second = np.full(mps.n, 256, np.int32)
+        nm = np.zeros(frames.n_frames, np.int32)
+        capi.check(self._lib.orbgpu_search_by_projection(self._h, C.byref(frames.c), C.byref(mps.c), sf.ctypes.data, len(sf), th,
+                                                         self.mfNNratio, kp_match.ctypes.data, best_idx.ctypes.data,
+                                                         best_dist.ctypes.data, second.ctypes.data, nm.ctypes.data))
+        return {"nmatches": nm, "kp_match": kp_match, "mp_best_idx": best_idx, "mp_best_dist": best_dist, "mp_second_dist": second}
+
+    # ---- SearchForTriangulation (ORBmatcher.cc:783-975), batched over keyframe pairs
+    def SearchForTriangulation(self, set1: FrameSet, set2: FrameSet, idx1, idx2, F12, epipole, scale_factors, level_sigma2,
+                               bOnlyStereo: bool = False):
+        idx1, idx2 = _arr(idx1, np.int32), _arr(idx2, np.int32)
+        F12 = np.ascontiguousarray(F12, np.float32).reshape(len(idx1), 9)
+        ep = np.ascontiguousarray(epipole, np.float32).reshape(len(idx1), 2)
+        sf, s2 = np.ascontiguousarray(scale_factors, np.float32), np.ascontiguousarray(level_sigma2, np.float32)
+        off, total = match_offsets(set1, idx1)
+        m12 = np.full(total, -1, np.int32)
+        md = np.full(total, -1, np.int32)
+        nm = np.zeros(len(idx1), np.int32)
+        capi.check(self._lib.orbgpu_search_for_triangulation(self._h, C.byref(set1.c), C.byref(set2.c), len(idx1), idx1.ctypes.data,
+                                                             idx2.ctypes.data, F12.ctypes.data, ep.ctypes.data, sf.ctypes.data,
+                                                             s2.ctypes.data, len(sf), int(bOnlyStereo), int(self.mbCheckOrientation),
+                                                             off.ctypes.data, m12.ctypes.data, md.ctypes.data, nm.ctypes.data))
+        return {"nmatches": nm, "match12": m12, "match_dist": md, "match_off": off}
+
+    # ---- SearchByBoW (KeyFrame-KeyFrame :635-768 by default; kf_frame=True gives the KeyFrame-Frame rule :211-344)
+    def SearchByBoW(self, set1: FrameSet, set2: FrameSet, idx1, idx2, kf_frame: bool = False):
+        idx1, idx2 = _arr(idx1, np.int32), _arr(idx2, np.int32)
+        off, total = match_offsets(set1, idx1)
+        m12 = np.full(total, -1, np.int32)
+        md = np.full(total, -1, np.int32)
+        nm = np.zeros(len(idx1), np.int32)
+        capi.check(self._lib.orbgpu_search_by_bow(self._h, C.byref(set1.c), C.byref(set2.c), len(idx1), idx1.ctypes.data,
+                                                  idx2.ctypes.data, self.mfNNratio, int(self.mbCheckOrientation), self.TH_LOW,
+                                                  int(kf_frame), int(not kf_frame), off.ctypes.data, m12.ctypes.data,
+                                                  md.ctypes.data, nm.ctypes.data))
+        return {"nmatches": nm, "match12": m12, "match_dist": md, "match_off": off}
+
+    # ---- device-resident handles (bench path)
+    def upload(self, fs: FrameSet) -> C.c_void_p:
+        h = C.c_void_p()
+        capi.check(self._lib.orbgpu_frame_set_upload(self._h, C.byref(fs.c), C.byref(h)))
+        return h
+
+    def release(self, h):
+        self._lib.orbgpu_frame_set_release(h)
+
+    def upload_mappoints(self, mps: MapPointSet, n_frames: int) -> C.c_void_p:
+        h = C.c_void_p()
+        capi.check(self._lib.orbgpu_mappoint_set_upload(self._h, C.byref(mps.c), n_frames, C.byref(h)))
+        return h
+
+    def release_mappoints(self, h):
+        self._lib.orbgpu_mappoint_set_release(h)
+
+    def search_by_bow_dev(self, h1, h2, idx1, idx2, match_off, d_match12: int, d_match_dist: int, d_nmatches: int,
+                          kf_frame: bool = False):
+        capi.check(self._lib.orbgpu_search_by_bow_dev(self._h, h1, h2, len(idx1), idx1.ctypes.data, idx2.ctypes.data, self.mfNNratio,
+                                                      int(self.mbCheckOrientation), self.TH_LOW, int(kf_frame), int(not kf_frame),
+                                                      match_off.ctypes.data, d_match12, d_match_dist, d_nmatches))
+
+    def search_for_triangulation_dev(self, h1, h2, idx1, idx2, F12, epipole, sf, s2, match_off, d_match12: int, d_match_dist: int,
+                                     d_nmatches: int, bOnlyStereo: bool = False):
+        capi.check(self._lib.orbgpu_search_for_triangulation_dev(self._h, h1, h2, len(idx1), idx1.ctypes.data, idx2.ctypes.data,
+                                                                 F12.ctypes.data, epipole.ctypes.data, sf.ctypes.data, s2.ctypes.data,
+                                                                 len(sf), int(bOnlyStereo), int(self.mbCheckOrientation),
+                                                                 match_off.ctypes.data, d_match12, d_match_dist, d_nmatches))
+
+    def search_by_projection_dev(self, hf, hm, sf, th, d_kp_match: int, d_best_idx: int, d_best_dist: int, d_second: int,
+                                 d_nmatches: int):
+        capi.check(self._lib.orbgpu_search_by_projection_dev(self._h, hf, hm, sf.ctypes.data, len(sf), th, self.mfNNratio, d_kp_match,
+                                                             d_best_idx, d_best_dist, d_second, d_nmatches))

@@ -85,3 +85,156 @@ def perturbed_descriptors(a: np.ndarray, seed: int, p_flip: float = 0.08, frac_m
     fresh = rs.randint(0, 256, (n, 32)).astype(np.uint8)
     b[~keep] = fresh[~keep]
     return b
+
+
+# ---- matching workloads ---------------------------------------------------
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                     ("octave", "<i4"), ("class_id", "<i4")])
+
+
+def scale_tables(n_levels: int = 8, scale: float = 1.2):
+    """mvScaleFactor / mvLevelSigma2 as the reference constructor computes them (ORBextractor.cc:413-431)."""
+    sf = np.zeros(n_levels, np.float32)
+    sf[0] = 1.0
+    for i in range(1, n_levels):
+        sf[i] = np.float32(float(sf[i - 1]) * float(np.float32(scale)))
+    return sf, (sf * sf).astype(np.float32)
+
+
+def synth_keypoints(n: int, w: int, h: int, seed: int, n_levels: int = 8) -> np.ndarray:
+    """Keypoints shaped like an extractor's output: level-space integer coordinates times the level scale,
+    geometric level quotas, angles U[0,360)."""
+    rs = np.random.RandomState(seed)
+    sf, _ = scale_tables(n_levels)
+    p = (1 / 1.2) ** np.arange(n_levels)
+    octv = np.sort(rs.choice(n_levels, n, p=p / p.sum())).astype(np.int32)
+    kp = np.zeros(n, KP_DTYPE)
+    lw, lh = np.rint(w / sf[octv]), np.rint(h / sf[octv])
+    kp["x"] = (np.floor(rs.uniform(19, np.maximum(lw - 19, 20))).astype(np.float32) * sf[octv]).astype(np.float32)
+    kp["y"] = (np.floor(rs.uniform(19, np.maximum(lh - 19, 20))).astype(np.float32) * sf[octv]).astype(np.float32)
+    kp["size"] = np.floor(31 * sf[octv])
+    kp["angle"] = rs.uniform(0, 360, n).astype(np.float32)
+    kp["response"] = rs.randint(7, 120, n)
+    kp["octave"] = octv
+    kp["class_id"] = -1
+    return kp
+
+
+def flip_bits(desc: np.ndarray, rs, p_flip: float) -> np.ndarray:
+    fl = np.packbits(rs.uniform(size=(len(desc), 256)) < p_flip, axis=1, bitorder="little")
+    return desc ^ fl
+
+
+def synth_vocabulary(seed: int = 12345, k: int = 10):
+    """Stand-in for the missing ORBvoc blob: a 2-level tree of k x k random 256-bit centroids."""
+    rs = np.random.RandomState(seed)
+    return rs.randint(0, 256, (k, 32)).astype(np.uint8), rs.randint(0, 256, (k, k, 32)).astype(np.uint8)
+
+
+_POP8 = np.array([bin(i).count("1") for i in range(256)], np.int32)
+
+
+def hamming_matrix(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    return _POP8[a[:, None, :] ^ b[None, :, :]].sum(-1)
+
+
+def feature_vector(desc: np.ndarray, vocab):
+    """DBoW2-style FeatureVector of one frame: node id = argmin Hamming at each tree level (first minimum wins);
+    returns (node ids ascending, per-node feature index lists in feature order)."""
+    l1, l2 = vocab
+    k = len(l1)
+    if len(desc) == 0:
+        return np.zeros(0, np.int32), []
+    a = hamming_matrix(desc, l1).argmin(1)
+    node = np.zeros(len(desc), np.int32)
+    for c in range(k):
+        m = np.nonzero(a == c)[0]
+        if len(m):
+            node[m] = c * k + hamming_matrix(desc[m], l2[c]).argmin(1)
+    ids = np.unique(node)
+    return ids.astype(np.int32), [np.nonzero(node == i)[0].astype(np.int32) for i in ids]
+
+
+def pack_feature_vectors(kp_off, desc, vocab):
+    """FeatureVector arrays of a frame set in the C-ABI layout (fv_node_off, fv_node_id, fv_feat_off, fv_feat)."""
+    node_off, node_id, feat_off, feat = [0], [], [0], []
+    for f in range(len(kp_off) - 1):
+        ids, lists = feature_vector(desc[kp_off[f]:kp_off[f + 1]], vocab)
+        for i, l in zip(ids, lists):
+            node_id.append(int(i))
+            feat.append(l)
+            feat_off.append(feat_off[-1] + len(l))
+        node_off.append(len(node_id))
+    feat = np.concatenate(feat).astype(np.int32) if feat else np.zeros(0, np.int32)
+    return (np.array(node_off, np.int32), np.array(node_id, np.int32), np.array(feat_off, np.int32), feat)
+
+
+def bruteforce_sets(n_sets: int, n: int, seed: int):
+    """Config #5: set A_i = n uniform random descriptors; B_i = permutation of A_i, half the rows with
+    Binomial(256, 0.08) bit flips, the rest fresh random.  Returns (descA [n_sets,n,32], descB, anglesA, anglesB)."""
+    A = np.stack([random_descriptors(n, seed + i) for i in range(n_sets)])
+    B = np.stack([perturbed_descriptors(A[i], seed + 7919 + i) for i in range(n_sets)])
+    rs = np.random.RandomState(seed + 13)
+    return A, B, rs.uniform(0, 360, (n_sets, n)).astype(np.float32), rs.uniform(0, 360, (n_sets, n)).astype(np.float32)
+
+
+def local_map(keys_prev: np.ndarray, desc_prev: np.ndarray, n_mp: int, w: int, h: int, seed: int, n_levels: int = 8):
+    """Config #2: n_mp synthetic map points for one frame.  60 % re-observe a keypoint of the previous frame
+    (descriptor with Binomial(256,0.05) flips, projection = its position + N(0,2) px, level = its octave), 40 % are
+    random.  Returns dict of arrays (proj_x, proj_y, view_cos, level, flags, desc)."""
+    rs = np.random.RandomState(seed)
+    real = (rs.uniform(size=n_mp) < 0.6) & (len(keys_prev) > 0)
+    src = rs.randint(0, max(len(keys_prev), 1), n_mp)
+    desc = rs.randint(0, 256, (n_mp, 32)).astype(np.uint8)
+    px = rs.uniform(0, w, n_mp).astype(np.float32)
+    py = rs.uniform(0, h, n_mp).astype(np.float32)
+    lvl = rs.randint(0, n_levels, n_mp).astype(np.int32)
+    if real.any():
+        k = keys_prev[src[real]]
+        desc[real] = flip_bits(desc_prev[src[real]], rs, 0.05)
+        px[real] = k["x"] + rs.normal(0, 2, real.sum()).astype(np.float32)
+        py[real] = k["y"] + rs.normal(0, 2, real.sum()).astype(np.float32)
+        lvl[real] = k["octave"]
+    return {"proj_x": px, "proj_y": py, "view_cos": rs.uniform(0.99, 1.0, n_mp).astype(np.float32), "level": lvl,
+            "flags": np.full(n_mp, 1 | 4, np.uint8), "desc": desc}
+
+
+def frame_grid(w: int, h: int):
+    """mnMinX, mnMinY, mfGridElementWidthInv, mfGridElementHeightInv of an undistorted w x h image (Frame.cc:96-102)."""
+    return np.array([0.0, 0.0, np.float32(64) / np.float32(w), np.float32(48) / np.float32(h)], np.float32)
+
+
+def skew(t):
+    return np.array([[0, -t[2], t[1]], [t[2], 0, -t[0]], [-t[1], t[0], 0]], np.float64)
+
+
+def fundamental_and_epipole(K: np.ndarray, R12: np.ndarray, t12: np.ndarray):
+    """F12 = K^-T [t12]x R12 K^-1 (LocalMapping::ComputeF12, LocalMapping.cc:676-693) in float32 row-major, and the
+    epipole of camera 1 in image 2 (ORBmatcher.cc:790-799) for the same relative pose."""
+    Ki = np.linalg.inv(K)
+    F = Ki.T @ skew(t12) @ R12 @ Ki
+    F = (F / np.abs(F).max()).astype(np.float32)
+    # camera-1 centre in camera-2 coordinates: x1 = R12 x2 + t12  ->  C2 = -R12^T t12
+    C2 = -R12.T @ t12
+    ex = np.float32(K[0, 0] * C2[0] / C2[2] + K[0, 2])
+    ey = np.float32(K[1, 1] * C2[1] / C2[2] + K[1, 2])
+    return F.reshape(9), np.array([ex, ey], np.float32)
+
+
+def epipolar_partner(kp1: np.ndarray, F: np.ndarray, rs, w: int, h: int, noise: float = 0.7) -> np.ndarray:
+    """For every keypoint of image 1 a point of image 2 near its epipolar line x1^T F12 (so that the chi-square
+    test of CheckDistEpipolarLine passes for most and fails for some)."""
+    F = F.reshape(3, 3).astype(np.float64)
+    x1 = np.stack([kp1["x"], kp1["y"], np.ones(len(kp1))], 1).astype(np.float64)
+    l = x1 @ F   # (a, b, c)
+    a, b, c = l[:, 0], l[:, 1], l[:, 2]
+    nrm = np.sqrt(a * a + b * b) + 1e-30
+    # foot of kp1 on the line, then slide along the line and jitter across it
+    d = (a * kp1["x"] + b * kp1["y"] + c) / nrm
+    fx, fy = kp1["x"] - d * a / nrm, kp1["y"] - d * b / nrm
+    s = rs.uniform(-40, 40, len(kp1))
+    e = rs.normal(0, noise, len(kp1)) * (1 + 2 * (rs.uniform(size=len(kp1)) < 0.15))
+    out = kp1.copy()
+    out["x"] = np.clip(fx - s * b / nrm + e * a / nrm, 0, w - 1).astype(np.float32)
+    out["y"] = np.clip(fy + s * a / nrm + e * b / nrm, 0, h - 1).astype(np.float32)
+    return out

@@ -1,0 +1,329 @@
+#!/usr/bin/env python3
+"""Golden fixtures for the matcher path, from an INDEPENDENT restatement of the reference (TEST INFRASTRUCTURE).
+
+The reference ships no tests or golden vectors for ORBmatcher and ORBmatcher.cc cannot be compiled here (OpenCV,
+DBoW2, Frame/KeyFrame/MapPoint), so the C++ port in oracle/match_oracle.cc is pinned by a second restatement written
+separately, in plain Python, straight from the reference source:
+
+    py_search_by_projection   ORBmatcher.cc:59-163 + Frame.cc:232-247, :353-422
+    py_search_by_bow          ORBmatcher.cc:211-344 (kf_frame=True) / :635-768
+    py_search_for_triangulation  ORBmatcher.cc:173-196, :783-975
+    py_three_maxima           ORBmatcher.cc:1854-1895
+
+FeatureVectors are Python dicts (std::map<NodeId, vector<unsigned>>), the grid is a dict of lists, float arithmetic
+uses numpy.float32 scalars so every product/sum rounds like the C++ float expressions.
+
+    python tests/golden/gen_matcher_golden.py      # rewrites tests/golden/matcher_golden.npz
+"""
+from __future__ import annotations
+
+import math
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+import match_cases as mc  # noqa: E402
+
+f32 = np.float32
+TH_HIGH, TH_LOW, HISTO_LENGTH = 100, 50, 30
+
+
+def popcount_distance(a, b) -> int:
+    return sum(bin(int(x) ^ int(y)).count("1") for x, y in zip(a, b))
+
+
+def c_round(v: float) -> int:  # C round(): half away from zero
+    return int(math.floor(abs(v) + 0.5)) * (1 if v >= 0 else -1)
+
+
+def rot_bin(a1, a2) -> int:
+    rot = f32(a1) - f32(a2)
+    if rot < 0.0:
+        rot = rot + f32(360.0)
+    b = c_round(float(f32(rot) * f32(f32(1.0) / f32(HISTO_LENGTH))))
+    return 0 if b == HISTO_LENGTH else b
+
+
+def py_three_maxima(histo):
+    max1 = max2 = max3 = 0
+    ind1 = ind2 = ind3 = -1
+    for i, h in enumerate(histo):
+        s = len(h)
+        if s > max1:
+            max3, max2, max1 = max2, max1, s
+            ind3, ind2, ind1 = ind2, ind1, i
+        elif s > max2:
+            max3, max2 = max2, s
+            ind3, ind2 = ind2, i
+        elif s > max3:
+            max3, ind3 = s, i
+    if f32(max2) < f32(0.1) * f32(max1):
+        ind2 = ind3 = -1
+    elif f32(max3) < f32(0.1) * f32(max1):
+        ind3 = -1
+    return ind1, ind2, ind3
+
+
+def fv_maps(fs, f):
+    """{node id: [feature indices]} of frame f, like DBoW2::FeatureVector."""
+    out = {}
+    for k in range(fs.fv_node_off[f], fs.fv_node_off[f + 1]):
+        out[int(fs.fv_node_id[k])] = [int(v) for v in fs.fv_feat[fs.fv_feat_off[k]:fs.fv_feat_off[k + 1]]]
+    return out
+
+
+def frame_view(fs, f):
+    a, b = int(fs.kp_off[f]), int(fs.kp_off[f + 1])
+    return (fs.keys_un[a:b], fs.desc[a:b], None if fs.kp_flags is None else fs.kp_flags[a:b],
+            None if fs.u_right is None else fs.u_right[a:b])
+
+
+def py_search_by_bow(fs1, fs2, idx1, idx2, nnratio, check_ori, kf_frame):
+    nm_out, m_out, d_out = [], [], []
+    for fa, fb in zip(idx1, idx2):
+        K1, D1, FL1, _ = frame_view(fs1, fa)
+        K2, D2, FL2, _ = frame_view(fs2, fb)
+        v1, v2 = fv_maps(fs1, fa), fv_maps(fs2, fb)
+        matches12 = [-1] * len(K1)
+        dist12 = [-1] * len(K1)
+        matched2 = [False] * len(K2)
+        hist = [[] for _ in range(HISTO_LENGTH)]
+        n = 0
+        for node in sorted(set(v1) & set(v2)):      # the merge walk visits exactly the common ids, ascending
+            for i1 in v1[node]:
+                if FL1 is None or not (FL1[i1] & 1):
+                    continue
+                best1, best2, besti = 256, 256, -1
+                for i2 in v2[node]:
+                    if matched2[i2]:
+                        continue
+                    if not kf_frame and (FL2 is None or not (FL2[i2] & 1)):
+                        continue
+                    d = popcount_distance(D1[i1], D2[i2])
+                    if d < best1:
+                        best2, best1, besti = best1, d, i2
+                    elif d < best2:
+                        best2 = d
+                ok = best1 <= TH_LOW if kf_frame else best1 < TH_LOW
+                if ok and f32(best1) < f32(nnratio) * f32(best2):
+                    matches12[i1], dist12[i1] = besti, best1
+                    matched2[besti] = True
+                    if check_ori:
+                        hist[rot_bin(K1[i1]["angle"], K2[besti]["angle"])].append(i1)
+                    n += 1
+        if check_ori:
+            keep = py_three_maxima(hist)
+            for i in range(HISTO_LENGTH):
+                if i in keep:
+                    continue
+                for i1 in hist[i]:
+                    matches12[i1], dist12[i1] = -1, -1
+                    n -= 1
+        nm_out.append(n)
+        m_out += matches12
+        d_out += dist12
+    return np.array(nm_out, np.int32), np.array(m_out, np.int32), np.array(d_out, np.int32)
+
+
+def epipolar_ok(k1, k2, F, sigma2):
+    x1, y1, x2, y2 = f32(k1["x"]), f32(k1["y"]), f32(k2["x"]), f32(k2["y"])
+    a = x1 * F[0] + y1 * F[3] + F[6]
+    b = x1 * F[1] + y1 * F[4] + F[7]
+    c = x1 * F[2] + y1 * F[5] + F[8]
+    num = a * x2 + b * y2 + c
+    den = a * a + b * b
+    if den == 0:
+        return False
+    dsqr = num * num / den
+    return float(dsqr) < 3.84 * float(sigma2[int(k2["octave"])])
+
+
+def py_search_for_triangulation(fs1, fs2, idx1, idx2, F12, epi, sf, s2, only_stereo, check_ori):
+    nm_out, m_out, d_out = [], [], []
+    for p, (fa, fb) in enumerate(zip(idx1, idx2)):
+        K1, D1, FL1, U1 = frame_view(fs1, fa)
+        K2, D2, FL2, U2 = frame_view(fs2, fb)
+        F = [f32(v) for v in F12[p]]
+        ex, ey = f32(epi[p][0]), f32(epi[p][1])
+        v1, v2 = fv_maps(fs1, fa), fv_maps(fs2, fb)
+        matches12 = [-1] * len(K1)
+        dist12 = [-1] * len(K1)
+        hist = [[] for _ in range(HISTO_LENGTH)]
+        n = 0
+        for node in sorted(set(v1) & set(v2)):
+            for i1 in v1[node]:
+                if FL1 is not None and (FL1[i1] & 1):
+                    continue
+                st1 = U1 is not None and U1[i1] >= 0
+                if only_stereo and not st1:
+                    continue
+                best, besti = TH_LOW, -1
+                for i2 in v2[node]:
+                    if FL2 is not None and (FL2[i2] & 1):
+                        continue
+                    st2 = U2 is not None and U2[i2] >= 0
+                    if only_stereo and not st2:
+                        continue
+                    d = popcount_distance(D1[i1], D2[i2])
+                    if d > TH_LOW or d > best:
+                        continue
+                    if not st1 and not st2:
+                        dx, dy = ex - f32(K2[i2]["x"]), ey - f32(K2[i2]["y"])
+                        if dx * dx + dy * dy < f32(100) * f32(sf[int(K2[i2]["octave"])]):
+                            continue
+                    if epipolar_ok(K1[i1], K2[i2], F, s2):
+                        besti, best = i2, d
+                if besti >= 0:
+                    matches12[i1], dist12[i1] = besti, best
+                    n += 1
+                    if check_ori:
+                        hist[rot_bin(K1[i1]["angle"], K2[besti]["angle"])].append(i1)
+        if check_ori:
+            keep = py_three_maxima(hist)
+            for i in range(HISTO_LENGTH):
+                if i in keep:
+                    continue
+                for i1 in hist[i]:
+                    matches12[i1], dist12[i1] = -1, -1
+                    n -= 1
+        nm_out.append(n)
+        m_out += matches12
+        d_out += dist12
+    return np.array(nm_out, np.int32), np.array(m_out, np.int32), np.array(d_out, np.int32)
+
+
+def py_search_by_projection(fs, mps, sf, th, nnratio):
+    COLS, ROWS = 64, 48
+    kp_match = np.full(int(fs.kp_off[-1]), -1, np.int32)
+    bi = np.full(mps.n, -1, np.int32)
+    bd = np.full(mps.n, 256, np.int32)
+    sd = np.full(mps.n, 256, np.int32)
+    nm_out = []
+    for f in range(fs.n_frames):
+        K, D, FL, UR = frame_view(fs, f)
+        k0 = int(fs.kp_off[f])
+        minx, miny, iw, ih = [f32(v) for v in fs.grid[f]]
+        grid = {}
+        for i in range(len(K)):
+            px = c_round(float((f32(K[i]["x"]) - minx) * iw))
+            py = c_round(float((f32(K[i]["y"]) - miny) * ih))
+            if 0 <= px < COLS and 0 <= py < ROWS:
+                grid.setdefault((px, py), []).append(i)
+        state = [0] * len(K) if FL is None else [int(v) for v in FL]
+        n = 0
+        for q in range(int(mps.mp_off[f]), int(mps.mp_off[f + 1])):
+            fl = int(mps.flags[q])
+            if not (fl & 1) or (fl & 2):
+                continue
+            lvl = int(mps.level[q])
+            r = f32(2.5) if float(mps.view_cos[q]) > 0.998 else f32(4.0)
+            if th != 1.0:
+                r = r * f32(th)
+            rs = r * f32(sf[lvl])
+            x, y = f32(mps.proj_x[q]), f32(mps.proj_y[q])
+            cx0 = max(0, int(math.floor(float((x - minx - rs) * iw))))
+            cx1 = min(COLS - 1, int(math.ceil(float((x - minx + rs) * iw))))
+            cy0 = max(0, int(math.floor(float((y - miny - rs) * ih))))
+            cy1 = min(ROWS - 1, int(math.ceil(float((y - miny + rs) * ih))))
+            if cx0 >= COLS or cx1 < 0 or cy0 >= ROWS or cy1 < 0:
+                continue
+            cand = []
+            for ix in range(cx0, cx1 + 1):
+                for iy in range(cy0, cy1 + 1):
+                    for i in grid.get((ix, iy), []):
+                        o = int(K[i]["octave"])
+                        if o < lvl - 1 or o > lvl:
+                            continue
+                        if abs(f32(K[i]["x"]) - x) < rs and abs(f32(K[i]["y"]) - y) < rs:
+                            cand.append(i)
+            if not cand:
+                continue
+            best, best2, lev, lev2, besti = 256, 256, -1, -1, -1
+            for i in cand:
+                if state[i] == 1:
+                    continue
+                if UR is not None and UR[i] > 0:
+                    if abs(f32(mps.proj_xr[q]) - f32(UR[i])) > rs:
+                        continue
+                d = popcount_distance(mps.desc[q], D[i])
+                if d < best:
+                    best2, best, lev2, lev, besti = best, d, lev, int(K[i]["octave"]), i
+                elif d < best2:
+                    lev2, best2 = int(K[i]["octave"]), d
+            bi[q], bd[q], sd[q] = besti, best, best2
+            if best <= TH_HIGH:
+                if lev == lev2 and f32(best) > f32(nnratio) * f32(best2):
+                    continue
+                state[besti] = 1 if (fl & 4) else 2
+                kp_match[k0 + besti] = q - int(mps.mp_off[f])
+                n += 1
+        nm_out.append(n)
+    return np.array(nm_out, np.int32), kp_match, bi, bd, sd
+
+
+def checksum(*arrays) -> np.ndarray:
+    import zlib
+    c = 0
+    for a in arrays:
+        if a is not None:
+            c = zlib.crc32(np.ascontiguousarray(a).tobytes(), c)
+    return np.array([c], np.uint32)
+
+
+def fs_checksum(fs):
+    return checksum(fs.kp_off, fs.keys_un, fs.desc, fs.kp_flags, fs.u_right, fs.grid, fs.fv_node_off, fs.fv_node_id, fs.fv_feat_off,
+                    fs.fv_feat)
+
+
+# case name -> (kind, generator kwargs, matcher kwargs)
+CASES = {
+    "bow_kfkf_nodes": ("bow", dict(seed=11, n_frames=4, n_lo=100, n_hi=160), dict(nnratio=0.75, check_ori=True, kf_frame=False)),
+    "bow_kff_nodes": ("bow", dict(seed=12, n_frames=4, n_lo=100, n_hi=160), dict(nnratio=0.7, check_ori=True, kf_frame=True)),
+    "bow_brute": ("bow", dict(seed=13, n_frames=3, n_lo=120, n_hi=150, single_node=True, flag_density=1.0),
+                  dict(nnratio=0.75, check_ori=True, kf_frame=False)),
+    "bow_brute_noori": ("bow", dict(seed=14, n_frames=3, n_lo=100, n_hi=130, single_node=True), dict(nnratio=0.9, check_ori=False, kf_frame=False)),
+    "tri_mono": ("tri", dict(seed=21, n_frames=4, n_lo=120, n_hi=200), dict(only_stereo=False, check_ori=False)),
+    "tri_ori_stereo": ("tri", dict(seed=22, n_frames=4, n_lo=120, n_hi=200, stereo_frac=0.5), dict(only_stereo=False, check_ori=True)),
+    "tri_only_stereo": ("tri", dict(seed=23, n_frames=3, n_lo=120, n_hi=200, stereo_frac=0.6), dict(only_stereo=True, check_ori=False)),
+    "sbp_mono_th1": ("sbp", dict(seed=31, n_frames=2, n_lo=250, n_hi=400, n_mp=500, th=1.0), dict(nnratio=0.8)),
+    "sbp_stereo_th3": ("sbp", dict(seed=32, n_frames=2, n_lo=250, n_hi=400, n_mp=500, stereo_frac=0.5, th=3.0), dict(nnratio=0.8)),
+    "sbp_wide_th15": ("sbp", dict(seed=33, n_frames=1, n_lo=300, n_hi=300, n_mp=300, th=15.0), dict(nnratio=0.9)),
+}
+
+
+def run_case(name):
+    kind, gen, mk = CASES[name]
+    out = {}
+    if kind == "bow":
+        s1, s2, i1, i2 = mc.bow_case(**gen)
+        nm, m12, md = py_search_by_bow(s1, s2, i1, i2, mk["nnratio"], mk["check_ori"], mk["kf_frame"])
+        out = {"nmatches": nm, "match12": m12, "match_dist": md, "input_crc": fs_checksum(s1)}
+    elif kind == "tri":
+        s1, s2, i1, i2, F12, epi, sf, s2t = mc.tri_case(**gen)
+        nm, m12, md = py_search_for_triangulation(s1, s2, i1, i2, F12, epi, sf, s2t, mk["only_stereo"], mk["check_ori"])
+        out = {"nmatches": nm, "match12": m12, "match_dist": md, "input_crc": fs_checksum(s1)}
+    else:
+        fs, mps, sf, th = mc.sbp_case(**gen)
+        nm, kpm, bi, bd, sd = py_search_by_projection(fs, mps, sf, th, mk["nnratio"])
+        out = {"nmatches": nm, "kp_match": kpm, "mp_best_idx": bi, "mp_best_dist": bd, "mp_second_dist": sd,
+               "input_crc": checksum(fs_checksum(fs), mps.proj_x, mps.proj_y, mps.desc, mps.flags)}
+    return out
+
+
+def main():
+    blob = {"cases": np.array(list(CASES))}
+    for name in CASES:
+        res = run_case(name)
+        for k, v in res.items():
+            blob[f"{name}__{k}"] = v
+        print(name, "nmatches", res["nmatches"].tolist())
+    np.savez_compressed(os.path.join(HERE, "matcher_golden.npz"), **blob)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,114 @@
+"""Seeded matcher workloads shared by the CPU-oracle tests, the golden-fixture generator and the GPU parity tests."""
+from __future__ import annotations
+
+import numpy as np
+
+from orb_slam2_with_comment_b200 import synth
+from orb_slam2_with_comment_b200.matcher import FrameSet, MapPointSet
+
+W, H = 640, 480
+K_TUM = np.array([[517.3, 0, 318.6], [0, 516.5, 255.3], [0, 0, 1]], np.float64)
+
+
+def _frames(seed, n_frames, n_lo, n_hi, p_flip=0.06, frac_rel=0.6, partner=None):
+    """n_frames frames; frame f>0 re-observes a fraction of frame f-1's keypoints (flipped descriptors)."""
+    rs = np.random.RandomState(seed)
+    keys, descs = [], []
+    for f in range(n_frames):
+        n = int(rs.randint(n_lo, n_hi + 1))
+        k = synth.synth_keypoints(n, W, H, seed * 1000 + f)
+        d = rs.randint(0, 256, (n, 32)).astype(np.uint8)
+        if f > 0 and n and len(keys[-1]):
+            m = min(n, len(keys[-1]))
+            take = rs.permutation(len(keys[-1]))[:int(frac_rel * m)]
+            slot = rs.permutation(n)[:len(take)]
+            src = keys[-1][take]
+            if partner is not None:
+                src = partner(src, rs)
+            k[slot] = src
+            k["angle"][slot] = (keys[-1]["angle"][take] + rs.normal(0, 8, len(take))).astype(np.float32) % np.float32(360)
+            d[slot] = synth.flip_bits(descs[-1][take], rs, p_flip)
+        keys.append(k)
+        descs.append(d)
+    kp_off = np.concatenate([[0], np.cumsum([len(k) for k in keys])]).astype(np.int32)
+    return rs, kp_off, np.concatenate(keys), np.concatenate(descs)
+
+
+def bow_case(seed, n_frames=6, n_lo=150, n_hi=400, single_node=False, flag_density=0.85, all_pairs=False):
+    rs, kp_off, keys, desc = _frames(seed, n_frames, n_lo, n_hi)
+    flags = (rs.uniform(size=len(keys)) < flag_density).astype(np.uint8)
+    if single_node:
+        fs = FrameSet.single_node(kp_off, keys, desc, kp_flags=flags)
+    else:
+        fv = synth.pack_feature_vectors(kp_off, desc, synth.synth_vocabulary())
+        fs = FrameSet(kp_off, keys, desc, kp_flags=flags, fv_node_off=fv[0], fv_node_id=fv[1], fv_feat_off=fv[2], fv_feat=fv[3])
+    if all_pairs:
+        idx1, idx2 = np.meshgrid(np.arange(n_frames), np.arange(n_frames), indexing="ij")
+        idx1, idx2 = idx1.ravel().astype(np.int32), idx2.ravel().astype(np.int32)
+    else:
+        idx1 = np.arange(1, n_frames, dtype=np.int32)
+        idx2 = np.arange(0, n_frames - 1, dtype=np.int32)
+    return fs, fs, idx1, idx2
+
+
+def tri_case(seed, n_frames=6, n_lo=200, n_hi=500, stereo_frac=0.0, flag_density=0.3):
+    R = np.eye(3)
+    ang = 0.02
+    R = np.array([[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]])
+    t = np.array([0.5, 0.02, 0.05])
+    F, ep = synth.fundamental_and_epipole(K_TUM, R, t)
+
+    # frame f = image "1" of pair (f, f-1): its re-observed keypoints sit near the epipolar line of the partner in f-1
+    def partner(src, rs):
+        # src are keypoints of frame f-1 (image 2); produce image-1 points whose line passes near them: use F^T
+        return synth.epipolar_partner(src, F.reshape(3, 3).T.copy().reshape(9), rs, W, H)
+    rs, kp_off, keys, desc = _frames(seed, n_frames, n_lo, n_hi, partner=partner)
+    flags = (rs.uniform(size=len(keys)) < flag_density).astype(np.uint8)
+    u_right = np.where(rs.uniform(size=len(keys)) < stereo_frac, keys["x"] - rs.uniform(1, 30, len(keys)), -1).astype(np.float32)
+    fv = synth.pack_feature_vectors(kp_off, desc, synth.synth_vocabulary())
+    fs = FrameSet(kp_off, keys, desc, kp_flags=flags, u_right=u_right, fv_node_off=fv[0], fv_node_id=fv[1], fv_feat_off=fv[2],
+                  fv_feat=fv[3])
+    idx1 = np.arange(1, n_frames, dtype=np.int32)
+    idx2 = np.arange(0, n_frames - 1, dtype=np.int32)
+    F12 = np.tile(F, (len(idx1), 1))
+    epi = np.tile(ep, (len(idx1), 1))
+    # put the epipole of one pair inside the image so the epipole-distance rule (:889-898) fires
+    if len(idx1) > 1:
+        epi[1] = (W / 2, H / 2)
+    sf, s2 = synth.scale_tables()
+    return fs, fs, idx1, idx2, F12, epi, sf, s2
+
+
+def sbp_case(seed, n_frames=4, n_lo=300, n_hi=700, n_mp=1500, stereo_frac=0.0, occupied=0.1, th=3.0):
+    rs, kp_off, keys, desc = _frames(seed, n_frames + 1, n_lo, n_hi)
+    # the searched frames are 1..n_frames; their local maps are built from the frame before
+    ko = kp_off[1:] - kp_off[1]
+    sel = slice(kp_off[1], kp_off[-1])
+    fkeys, fdesc = keys[sel], desc[sel]
+    flags = np.zeros(len(fkeys), np.uint8)
+    r = rs.uniform(size=len(fkeys))
+    flags[r < occupied] = 1           # holds a MapPoint with observations: skipped
+    flags[(r >= occupied) & (r < occupied + 0.05)] = 2
+    u_right = np.where(rs.uniform(size=len(fkeys)) < stereo_frac, fkeys["x"] - rs.uniform(1, 30, len(fkeys)), -1).astype(np.float32)
+    grid = np.tile(synth.frame_grid(W, H), (n_frames, 1))
+    fs = FrameSet(ko.astype(np.int32), fkeys, fdesc, kp_flags=flags, u_right=u_right if stereo_frac > 0 else None, grid=grid)
+    parts, mp_off = [], [0]
+    for f in range(n_frames):
+        nm = int(n_mp * rs.uniform(0.7, 1.0))
+        m = synth.local_map(keys[kp_off[f]:kp_off[f + 1]], desc[kp_off[f]:kp_off[f + 1]], nm, W, H, seed * 77 + f)
+        # the re-observed keypoints of frame f+1 were copied from frame f, so projecting frame f's keypoints lands on them
+        fl = m["flags"]
+        u = rs.uniform(size=nm)
+        fl[u < 0.05] &= ~np.uint8(1)          # not in view
+        fl[(u >= 0.05) & (u < 0.08)] |= 2     # bad
+        fl[(u >= 0.08) & (u < 0.2)] &= ~np.uint8(4)   # no observations: does not block its keypoint
+        m["flags"] = fl
+        m["view_cos"][rs.uniform(size=nm) < 0.5] = np.float32(0.9995)
+        m["proj_xr"] = (m["proj_x"] - rs.uniform(1, 30, nm)).astype(np.float32)
+        parts.append(m)
+        mp_off.append(mp_off[-1] + nm)
+    cat = {k: np.concatenate([p[k] for p in parts]) for k in parts[0]}
+    mps = MapPointSet(np.array(mp_off, np.int32), cat["proj_x"], cat["proj_y"], cat["view_cos"], cat["level"], cat["flags"],
+                      cat["desc"], proj_xr=cat["proj_xr"])
+    sf, _ = synth.scale_tables()
+    return fs, mps, sf, th

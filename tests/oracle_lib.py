@@ -170,3 +170,79 @@ def octree(lib, prefix, cand, minX, maxX, minY, maxY, N):
     n = getattr(lib, prefix + "_octree")(cand.ctypes.data_as(C.c_void_p), len(cand), minX, maxX, minY, maxY, N,
                                          out.ctypes.data_as(C.c_void_p), len(out))
     return out[:n]
+
+
+# ---- matcher oracle (oracle/match_oracle.cc) --------------------------------------------------------------
+def bind_match(lib):
+    from orb_slam2_with_comment_b200.matcher import CFrameSet, CMapPointSet
+    if getattr(lib, "_match_bound", False):
+        return lib
+    vp, i, f = C.c_void_p, C.c_int, C.c_float
+    lib.orbm_hamming.argtypes = [u8p, u8p]
+    lib.orbm_search_by_projection.restype = None
+    lib.orbm_search_by_projection.argtypes = [C.POINTER(CFrameSet), C.POINTER(CMapPointSet), vp, i, f, f, vp, vp, vp, vp, vp]
+    lib.orbm_search_for_triangulation.restype = None
+    lib.orbm_search_for_triangulation.argtypes = [C.POINTER(CFrameSet), C.POINTER(CFrameSet), i, vp, vp, vp, vp, vp, vp, i, i, i, vp,
+                                                  vp, vp, vp]
+    lib.orbm_search_by_bow.restype = None
+    lib.orbm_search_by_bow.argtypes = [C.POINTER(CFrameSet), C.POINTER(CFrameSet), i, vp, vp, f, i, i, i, i, vp, vp, vp, vp]
+    lib.orbm_bench_bow.restype = C.c_double
+    lib.orbm_bench_bow.argtypes = [C.POINTER(CFrameSet), C.POINTER(CFrameSet), i, vp, vp, f, i, i, i, i, vp, vp, vp, i]
+    lib._match_bound = True
+    return lib
+
+
+class MatcherOracle:
+    """Same method names / return dicts as orb_slam2_with_comment_b200.matcher.ORBmatcher, computed by the CPU port."""
+    TH_LOW, TH_HIGH, HISTO_LENGTH = 50, 100, 30
+
+    def __init__(self, lib, nnratio=0.6, checkOri=True):
+        self.lib, self.mfNNratio, self.mbCheckOrientation = bind_match(lib), float(nnratio), bool(checkOri)
+
+    def hamming_pairs(self, a, b):
+        a = np.ascontiguousarray(a, np.uint8).reshape(-1, 32)
+        b = np.ascontiguousarray(b, np.uint8).reshape(-1, 32)
+        return np.array([self.lib.orbm_hamming(_p(a[i]), _p(b[i])) for i in range(len(a))], np.int32)
+
+    def SearchByProjection(self, frames, mps, scale_factors, th=3.0):
+        sf = np.ascontiguousarray(scale_factors, np.float32)
+        kp_match = np.full(int(frames.kp_off[-1]), -1, np.int32)
+        bi, bd, sd = np.full(mps.n, -1, np.int32), np.full(mps.n, 256, np.int32), np.full(mps.n, 256, np.int32)
+        nm = np.zeros(frames.n_frames, np.int32)
+        self.lib.orbm_search_by_projection(C.byref(frames.c), C.byref(mps.c), sf.ctypes.data, len(sf), th, self.mfNNratio,
+                                           kp_match.ctypes.data, bi.ctypes.data, bd.ctypes.data, sd.ctypes.data, nm.ctypes.data)
+        return {"nmatches": nm, "kp_match": kp_match, "mp_best_idx": bi, "mp_best_dist": bd, "mp_second_dist": sd}
+
+    def SearchForTriangulation(self, set1, set2, idx1, idx2, F12, epipole, scale_factors, level_sigma2, bOnlyStereo=False):
+        from orb_slam2_with_comment_b200.matcher import match_offsets
+        idx1, idx2 = np.ascontiguousarray(idx1, np.int32), np.ascontiguousarray(idx2, np.int32)
+        F12 = np.ascontiguousarray(F12, np.float32).reshape(len(idx1), 9)
+        ep = np.ascontiguousarray(epipole, np.float32).reshape(len(idx1), 2)
+        sf, s2 = np.ascontiguousarray(scale_factors, np.float32), np.ascontiguousarray(level_sigma2, np.float32)
+        off, total = match_offsets(set1, idx1)
+        m12, md, nm = np.full(total, -1, np.int32), np.full(total, -1, np.int32), np.zeros(len(idx1), np.int32)
+        self.lib.orbm_search_for_triangulation(C.byref(set1.c), C.byref(set2.c), len(idx1), idx1.ctypes.data, idx2.ctypes.data,
+                                               F12.ctypes.data, ep.ctypes.data, sf.ctypes.data, s2.ctypes.data, len(sf),
+                                               int(bOnlyStereo), int(self.mbCheckOrientation), off.ctypes.data, m12.ctypes.data,
+                                               md.ctypes.data, nm.ctypes.data)
+        return {"nmatches": nm, "match12": m12, "match_dist": md, "match_off": off}
+
+    def SearchByBoW(self, set1, set2, idx1, idx2, kf_frame=False):
+        from orb_slam2_with_comment_b200.matcher import match_offsets
+        idx1, idx2 = np.ascontiguousarray(idx1, np.int32), np.ascontiguousarray(idx2, np.int32)
+        off, total = match_offsets(set1, idx1)
+        m12, md, nm = np.full(total, -1, np.int32), np.full(total, -1, np.int32), np.zeros(len(idx1), np.int32)
+        self.lib.orbm_search_by_bow(C.byref(set1.c), C.byref(set2.c), len(idx1), idx1.ctypes.data, idx2.ctypes.data, self.mfNNratio,
+                                    int(self.mbCheckOrientation), self.TH_LOW, int(kf_frame), int(not kf_frame), off.ctypes.data,
+                                    m12.ctypes.data, md.ctypes.data, nm.ctypes.data)
+        return {"nmatches": nm, "match12": m12, "match_dist": md, "match_off": off}
+
+    def bench_bow(self, set1, set2, idx1, idx2, threads, kf_frame=False):
+        from orb_slam2_with_comment_b200.matcher import match_offsets
+        idx1, idx2 = np.ascontiguousarray(idx1, np.int32), np.ascontiguousarray(idx2, np.int32)
+        off, total = match_offsets(set1, idx1)
+        m12, nm = np.full(total, -1, np.int32), np.zeros(len(idx1), np.int32)
+        sec = self.lib.orbm_bench_bow(C.byref(set1.c), C.byref(set2.c), len(idx1), idx1.ctypes.data, idx2.ctypes.data, self.mfNNratio,
+                                      int(self.mbCheckOrientation), self.TH_LOW, int(kf_frame), int(not kf_frame), off.ctypes.data,
+                                      m12.ctypes.data, nm.ctypes.data, threads)
+        return sec, int(nm.sum())

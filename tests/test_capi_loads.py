@@ -36,6 +36,9 @@ def test_no_cpu_fallback_without_device():
     from orb_slam2_with_comment_b200.capi import OrbGpuError
     with pytest.raises(OrbGpuError, match="no CUDA device"):
         ORBextractor(2000, 1.2, 8, 20, 7)
+    from orb_slam2_with_comment_b200.matcher import ORBmatcher
+    with pytest.raises(OrbGpuError, match="no CUDA device"):
+        ORBmatcher(0.6, True)
 
 
 def test_keypoint_layout_is_cv_keypoint():
