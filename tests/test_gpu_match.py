@@ -109,7 +109,7 @@ def test_bow_heavy_contention_forces_rescans(gm, mo):
         got = gm(0.99, False, **cfg).SearchByBoW(s1, s2, [0], [0], kf_frame=True)
         exp = mo(0.99, False).SearchByBoW(s1, s2, [0], [0], kf_frame=True)
         same(got, exp, BOW_KEYS, f"contention cfg {cfg}")
-    assert exp["nmatches"][0] > 50
+    assert exp["nmatches"][0] > 20
 
 
 def test_bow_edge_cases(gm, mo):
