@@ -65,6 +65,136 @@ def algorithmic_bytes():
     return per_stage, b_alg
 
 
+# ---- matching leg (BASELINE.json metric part 2: "Hamming matches/s") -------------------------
+MATCH_N, MATCH_SETS = 2000, 256
+
+
+def make_match_workload(pairs: int):
+    """Brute-force 2000 x 2000 keyframe pairs: SearchByBoW(KF1,KF2) semantics with one node holding all indices,
+    nnratio 0.75, checkOri on.  `pairs` pairs are formed from MATCH_SETS distinct descriptor-set pairs (A_i, B_i)."""
+    from orb_slam2_with_comment_b200 import synth
+    from orb_slam2_with_comment_b200.matcher import FrameSet, match_offsets
+    n_sets = min(MATCH_SETS, pairs)
+    A, B, angA, angB = synth.bruteforce_sets(n_sets, MATCH_N, 900)
+    kp_off = np.arange(n_sets + 1, dtype=np.int32) * MATCH_N
+    kA = np.zeros(n_sets * MATCH_N, synth.KP_DTYPE); kA["angle"] = angA.ravel()
+    kB = np.zeros(n_sets * MATCH_N, synth.KP_DTYPE); kB["angle"] = angB.ravel()
+    fl = np.ones(n_sets * MATCH_N, np.uint8)
+    sA = FrameSet.single_node(kp_off, kA, A.reshape(-1, 32), kp_flags=fl)
+    sB = FrameSet.single_node(kp_off, kB, B.reshape(-1, 32), kp_flags=fl)
+    i1 = (np.arange(pairs) % n_sets).astype(np.int32)
+    off, total = match_offsets(sA, i1)
+    return sA, sB, i1, i1.copy(), off, total
+
+
+def cpu_match_run(pairs: int, threads: int):
+    """The CPU port of SearchByBoW (oracle/match_oracle.cc; ORBmatcher.cc cannot be compiled here) on `pairs` pairs."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ol
+    sA, sB, i1, i2, off, total = make_match_workload(pairs)
+    mo = ol.MatcherOracle(ol.load_port(), 0.75, True)
+    sec, nm = mo.bench_bow(sA, sB, i1, i2, threads)
+    return {"matches_per_s": nm / sec, "evals_per_s": pairs * MATCH_N * MATCH_N / sec, "pairs_per_s": pairs / sec, "sec": sec}
+
+
+def popc_peak():
+    path = os.path.join(ROOT, "profiles", "popc_peak.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["popc_per_s"]), "measured (profiles/popc_peak.json: tools/popc_peak.cu on this pool's B200)"
+        except Exception:
+            pass
+    return 148 * 16 * 1.965e9, "nominal 16 POPC/clk/SM x 148 SMs x 1.965 GHz"
+
+
+def run_matching(args, torch, dist, rank, world, local, barrier):
+    from orb_slam2_with_comment_b200.matcher import ORBmatcher
+    from orb_slam2_with_comment_b200 import capi
+    import ctypes as C
+    dev = torch.device("cuda", local)
+    P = args.match_pairs
+    sA, sB, i1, i2, off, total = make_match_workload(P)
+    m = ORBmatcher(0.75, True, device=local)
+    hA, hB = m.upload(sA), m.upload(sB)
+    d12 = torch.empty(total, dtype=torch.int32, device=dev)
+    dd = torch.empty(total, dtype=torch.int32, device=dev)
+    dn = torch.empty(P, dtype=torch.int32, device=dev)
+    stream = torch.cuda.ExternalStream(m.stream(), device=dev)
+
+    def step_dev():
+        m.search_by_bow_dev(hA, hB, i1, i2, off, d12.data_ptr(), dd.data_ptr(), dn.data_ptr())
+
+    for _ in range(max(args.warmup, 3)):
+        step_dev()
+    m.sync()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_dev()
+    e1.record(stream)
+    m.sync()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    kernel_ms, evals = m.last_stats()
+    launches = m.last_launches() * args.steps
+    matches = int(dn.sum().item())
+
+    # end to end: host frame sets in, host match vectors out, through orbgpu_search_by_bow
+    h12 = torch.empty(total, dtype=torch.int32).pin_memory()
+    hd = torch.empty(total, dtype=torch.int32).pin_memory()
+    hn = torch.empty(P, dtype=torch.int32).pin_memory()
+    lib = m._lib
+
+    def step_host():
+        capi.check(lib.orbgpu_search_by_bow(m._h, C.byref(sA.c), C.byref(sB.c), P, i1.ctypes.data, i2.ctypes.data, 0.75, 1, 50, 0, 1,
+                                            off.ctypes.data, h12.data_ptr(), hd.data_ptr(), hn.data_ptr()))
+
+    step_host()
+    barrier()
+    t0 = time.time()
+    for _ in range(args.steps):
+        step_host()
+    wall_ms = (time.time() - t0) * 1e3
+    barrier()
+    assert int(hn.sum()) == matches, "host and device matching paths disagree"
+    if world > 1:
+        t = torch.tensor([ms, wall_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, wall_ms = float(t[0].item()), float(t[1].item())
+    m.release(hA); m.release(hB)
+    if rank != 0:
+        return None
+    peak, peak_src = popc_peak()
+    sec = ms / 1e3
+    n_in = (sA.desc.nbytes + sA.keys_un.nbytes) * 2
+    out = {
+        "metric": "Hamming matches/s", "value": world * matches * args.steps / sec, "unit": "matches/s",
+        "distance_evals_per_s": world * evals * args.steps / sec, "pairs_per_s": world * P * args.steps / sec,
+        "ms_per_step": ms / args.steps, "gpu_launches": launches,
+        "config": {"workload": f"config #5: brute-force 2000x2000 256-bit keyframe pairs, SearchByBoW(KF,KF) rule (TH_LOW 50 exclusive, "
+                               f"nnratio 0.75, rotation histogram), {P} pairs per GPU per step from {min(MATCH_SETS, P)} distinct set pairs",
+                   "pairs_per_gpu": P, "matches_per_pair": matches / P},
+        "e2e": {"value": world * matches * args.steps / (wall_ms / 1e3), "unit": "matches/s", "ms_per_step": wall_ms / args.steps,
+                "h2d_bytes_per_step": int(n_in), "d2h_bytes_per_step": int(total * 8 + P * 4)},
+        "roofline": {"bound": "int-popc", "kernel": "k_bow_topk_tile", "achieved": 8 * evals / (kernel_ms / 1e3) / 1e12, "peak": peak / 1e12,
+                     "unit": "T popc/s", "frac": 8 * evals / (kernel_ms / 1e3) / peak, "peak_source": peak_src,
+                     "note": "8 POPC per 256-bit distance evaluation (SURVEY 8d); achieved = 8 x evaluations / device time of the whole "
+                             "search (plan + tiled scan + greedy select kernels), last step"},
+    }
+    if world == 1:
+        cores = os.cpu_count() or 1
+        sample = max(8, cores)
+        try:
+            c = cpu_match_run(sample, cores)
+            out["cpu_baseline"] = {"value": c["matches_per_s"], "unit": "matches/s", "distance_evals_per_s": c["evals_per_s"], "cores": cores,
+                                   "kind": "port", "sample": f"{sample} pairs of the same workload, one pair per std::thread, {cores} threads "
+                                   "(oracle/match_oracle.cc, -O2; the reference's ORBmatcher.cc cannot be compiled without OpenCV/DBoW2)"}
+        except Exception as e:
+            out["cpu_baseline"] = {"value": None, "unit": "matches/s", "cores": cores, "kind": "port", "sample": f"unavailable: {e}"}
+    return out
+
+
 class ClockSampler:
     FIELDS = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
@@ -150,6 +280,13 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if not args.no_matching:
+        pairs = max(8, cores)
+        c = cpu_match_run(pairs, cores)
+        line["matching"] = {"metric": "Hamming matches/s", "value": c["matches_per_s"], "unit": "matches/s",
+                            "distance_evals_per_s": c["evals_per_s"], "pairs_per_s": c["pairs_per_s"],
+                            "cpu_baseline": {"value": c["matches_per_s"], "unit": "matches/s", "cores": cores, "kind": "port",
+                                             "sample": f"{pairs} brute-force 2000x2000 pairs, one pair per std::thread, {cores} threads"}}
     print(json.dumps(line))
 
 
@@ -248,6 +385,8 @@ def run_ours(args):
         ms_e2e = float(t.item())
     e2e_value = world * B * args.steps / (ms_e2e / 1e3)
     assert int(h_cnt.sum()) == int(d_cnt.sum().item()), "host and device paths disagree"
+    ex_launches_total = launches
+    matching = None if args.no_matching else run_matching(args, torch, dist, rank, world, local, barrier)
 
     if rank != 0:
         if world > 1:
@@ -289,9 +428,11 @@ def run_ours(args):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(B * W * H),
                 "d2h_bytes_per_step": int(B * (ex.kp_cap * 60 + 4)), "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": launches,
+        "gpu_launches": ex_launches_total + (matching["gpu_launches"] if matching else 0),
         "roofline": roofline,
     }
+    if matching:
+        line["matching"] = matching
     if world == 1:
         cores = os.cpu_count() or 1
         sample = max(64, 2 * cores)
@@ -313,6 +454,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=512)
+    ap.add_argument("--match-pairs", type=int, default=4096, help="brute-force keyframe pairs per GPU per step (matching leg)")
+    ap.add_argument("--no-matching", action="store_true")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
