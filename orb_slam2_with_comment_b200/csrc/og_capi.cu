@@ -1,12 +1,14 @@
 // og_capi.cu — the extern "C" layer of liborbgpu.so (include/orbgpu.h): extractor handle, workspace layout in
 // HBM, launch sequence.  Host-side geometry follows the reference constructor and ComputePyramid /
 // ComputeKeyPointsOctTree line by line (cited inline); no pixel is ever touched on the host.
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -54,6 +56,10 @@ struct orbgpu_extractor {
     // device buffers (capacity fixed at creation)
     uint8_t *d_pyr = nullptr, *d_blur = nullptr, *d_images = nullptr, *d_ot = nullptr;
     og::Cell* d_cells = nullptr;
+    og::Segment* d_segs = nullptr;
+    bool fast_v1 = false;             // ORBGPU_FAST_V1=1: first-generation per-cell kernel (kept for A/B timing)
+    CUtensorMap* d_tmaps = nullptr;   // [2][kMaxLevels]: FAST tile boxes over pyr, then (reserved) over blur
+    int fast_smem = 0;
     og::Tap* d_taps = nullptr;
     int32_t *d_cell_count = nullptr, *d_sel_count = nullptr, *d_counts = nullptr;
     uint32_t *d_cand_xy = nullptr, *d_sel_xy = nullptr;
@@ -72,6 +78,7 @@ namespace {
 struct Geometry {
     og::ExtractParams P;
     std::vector<og::Cell> cells;
+    std::vector<og::Segment> segs;
     std::vector<og::Tap> taps;            // all levels' x then y tables, concatenated
     std::vector<size_t> xt_off, yt_off;   // offsets into taps
     size_t pyr_bytes_per_frame = 0;
@@ -112,6 +119,35 @@ size_t octree_ws_bytes(int cap, int node_cap) {
     for (int i = 0; i < 5; ++i) take((size_t)node_cap * 4);
     take((size_t)og::kOctThreads * 16);
     return b;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// u8 tensor [batch][rows][pitch] at `base`, box = box_w x box_h x 1 (zero fill outside the tensor)
+std::string make_level_tmap(CUtensorMap* out, uint8_t* base, int pitch, int rows, long long frame_stride, int batch, int box_w, int box_h) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return "cuTensorMapEncodeTiled is not available from this driver";
+    const cuuint64_t gdim[3] = {(cuuint64_t)pitch, (cuuint64_t)rows, (cuuint64_t)batch};
+    const cuuint64_t gstr[2] = {(cuuint64_t)pitch, (cuuint64_t)frame_stride};
+    const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+    const cuuint32_t est[3] = {1, 1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r);
+    return "";
 }
 
 // Everything that depends on the frame size.  Returns an error string or "".
@@ -192,6 +228,36 @@ std::string build_geometry(const orbgpu_extractor& ex, int w, int h, int batch_c
             }
         }
         L.n_cells = ncell;
+        L.wcell = wCell;
+        // segments: runs of consecutive cells of one cell row that fit one 256-byte tile (k_fast_seg)
+        {
+            int th_max = 0;
+            for (int k = 0; k < ncell;) {
+                const og::Cell& c0 = G.cells[cell_base + k];
+                og::Segment sg;
+                sg.level = (int16_t)l;
+                sg.first_cell = cell_base + k;
+                sg.x0 = c0.x0; sg.y0 = c0.y0; sg.th = c0.th;
+                int tw = 0, n = 0;
+                while (k + n < ncell) {
+                    const og::Cell& c = G.cells[cell_base + k + n];
+                    if (c.y0 != c0.y0 || c.x0 != c0.x0 + n * wCell || tw + c.tw > og::kSegMaxTw) break;
+                    // every cell but the last of a row is exactly wCell wide, which the kernel's column table relies on
+                    if (n > 0 && G.cells[cell_base + k + n - 1].tw != wCell) break;
+                    tw += c.tw;
+                    ++n;
+                }
+                sg.ncells = (int16_t)n;
+                sg.tw = (int16_t)tw;
+                const int gx = (og::kXPad + sg.x0 - 3) & ~15, ox = og::kXPad + sg.x0 - gx;   // as in k_fast_seg
+                const uint32_t nw = (uint32_t)(((ox + tw + 3) >> 2) - (ox >> 2));
+                sg.nw_magic = (uint32_t)((0x100000000ull + nw - 1) / nw);
+                G.segs.push_back(sg);
+                th_max = std::max(th_max, (int)c0.th);
+                k += n;
+            }
+            L.hbox = th_max + 6;
+        }
         L.cand_cap = std::max(slot, 1);
         cell_base += ncell;
         cand_base += L.cand_cap;
@@ -235,6 +301,25 @@ int ensure_geometry(orbgpu_extractor* ex, int w, int h) {
         (size_t)P.total_sel_cap > ex->cap_sel || (size_t)P.ot_frame_bytes > ex->cap_ot)
         return fail(ORBGPU_ERR_CAPACITY, "internal: workspace sized at creation is too small for this frame size");
     OG_CUDA(cudaMemcpyAsync(ex->d_cells, G.cells.data(), G.cells.size() * sizeof(og::Cell), cudaMemcpyHostToDevice, ex->stream));
+    OG_CUDA(cudaMemcpyAsync(ex->d_segs, G.segs.data(), G.segs.size() * sizeof(og::Segment), cudaMemcpyHostToDevice, ex->stream));
+    {
+        std::vector<CUtensorMap> maps(2 * og::kMaxLevels);
+        memset(maps.data(), 0, maps.size() * sizeof(CUtensorMap));
+        int smem = 0;
+        for (int l = 0; l < ex->nlevels; ++l) {
+            const og::Level& L = P.lv[l];
+            std::string e = make_level_tmap(&maps[l], ex->d_pyr + L.base, L.pitch, L.rows, L.frame_stride, ex->max_batch, og::kSegPitch, L.hbox);
+            if (!e.empty()) return fail(ORBGPU_ERR_CUDA, e);
+            smem = std::max(smem, og::fast_seg_smem_bytes(L.hbox, L.hbox - 6));
+        }
+        OG_CUDA(cudaMemcpyAsync(ex->d_tmaps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, ex->stream));
+        OG_CUDA(cudaStreamSynchronize(ex->stream));   // `maps` is a local
+        if (smem > 200 * 1024) return fail(ORBGPU_ERR_ARG, "internal: FAST tile does not fit shared memory");
+        // the attribute is per function, not per handle: always allow the largest tile any geometry can ask for
+        OG_CUDA(cudaFuncSetAttribute(og::k_fast_seg, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     og::fast_seg_smem_bytes(og::kCellMax + 6, og::kCellMax)));
+        ex->fast_smem = smem;
+    }
     if (!G.taps.empty())
         OG_CUDA(cudaMemcpyAsync(ex->d_taps, G.taps.data(), G.taps.size() * sizeof(og::Tap), cudaMemcpyHostToDevice, ex->stream));
     OG_CUDA(cudaStreamSynchronize(ex->stream));
@@ -246,6 +331,8 @@ int ensure_geometry(orbgpu_extractor* ex, int w, int h) {
     ex->P.pyr = ex->d_pyr;
     ex->P.blur = ex->d_blur;
     ex->P.cells = ex->d_cells;
+    ex->P.segs = ex->d_segs;
+    ex->P.n_segs = (int)G.segs.size();
     ex->P.cell_count = ex->d_cell_count;
     ex->P.cand_xy = ex->d_cand_xy;
     ex->P.cand_resp = ex->d_cand_resp;
@@ -282,7 +369,10 @@ int launch_extract(orbgpu_extractor* ex, const uint8_t* d_images, int batch, siz
         ++launches;
     }
     mark(1);
-    og::k_fast_cells<<<dim3(P.total_cells, batch), og::kFastThreads, 0, st>>>(P);
+    if (ex->fast_v1)
+        og::k_fast_cells<<<dim3(P.total_cells, batch), og::kFastThreads, 0, st>>>(P);
+    else
+        og::k_fast_seg<<<dim3(P.n_segs, batch), og::kSegThreads, ex->fast_smem, st>>>(P, ex->d_tmaps);
     ++launches;
     mark(2);
     og::k_octree<<<dim3(P.n_levels, batch), og::kOctThreads, 0, st>>>(P);
@@ -407,6 +497,9 @@ int orbgpu_extractor_create(orbgpu_extractor** out, int device, int nfeatures, f
     alloc((void**)&ex->d_blur, ex->cap_pyr);
     alloc((void**)&ex->d_images, (size_t)max_width * max_height * B);
     alloc((void**)&ex->d_cells, ex->cap_cells * sizeof(og::Cell));
+    alloc((void**)&ex->d_segs, ex->cap_cells * sizeof(og::Segment));
+    alloc((void**)&ex->d_tmaps, 2 * og::kMaxLevels * sizeof(CUtensorMap));
+    { const char* e = getenv("ORBGPU_FAST_V1"); ex->fast_v1 = e && e[0] == '1'; }
     alloc((void**)&ex->d_taps, ex->cap_taps * sizeof(og::Tap));
     alloc((void**)&ex->d_cell_count, ex->cap_cellcount * B * 4);
     alloc((void**)&ex->d_cand_xy, ex->cap_cand * B * 4);
@@ -433,7 +526,7 @@ int orbgpu_extractor_destroy(orbgpu_extractor* ex) {
     cudaSetDevice(ex->device);
     if (ex->stream) { cudaStreamSynchronize(ex->stream); cudaStreamDestroy(ex->stream); }
     for (int i = 0; i < 6; ++i) if (ex->ev[i]) cudaEventDestroy(ex->ev[i]);
-    void* ptrs[] = {ex->d_pyr, ex->d_blur, ex->d_images, ex->d_cells, ex->d_taps, ex->d_cell_count, ex->d_cand_xy,
+    void* ptrs[] = {ex->d_segs, ex->d_tmaps, ex->d_pyr, ex->d_blur, ex->d_images, ex->d_cells, ex->d_taps, ex->d_cell_count, ex->d_cand_xy,
                     ex->d_cand_resp, ex->d_ot, ex->d_sel_xy, ex->d_sel_resp, ex->d_sel_count, ex->d_counts, ex->d_kp, ex->d_desc};
     for (void* p : ptrs) if (p) cudaFree(p);
     delete ex;

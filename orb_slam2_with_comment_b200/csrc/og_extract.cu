@@ -13,6 +13,7 @@
 
 #include "../../include/orbgpu_pattern.inc"
 #include "og_octree.cuh"
+#include "og_tma.cuh"
 #include "og_types.h"
 
 namespace og {
@@ -178,6 +179,235 @@ __global__ void __launch_bounds__(kFastThreads) k_fast_cells(const __grid_consta
         }
     }
     if (t == 0) P.cell_count[(long long)frame * P.total_cells + blockIdx.x] = total;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// FAST per cell, second generation: one CTA per (segment, frame), a segment being up to 8 consecutive cells of one
+// cell row.  The tile arrives by TMA.  The work is organised so that only the cheap rejection test touches every
+// pixel and everything expensive runs over a compacted queue:
+//   1. SWAR rejection test, 4 pixels per 32-bit word: a FAST-9 arc always covers two of the four compass ring
+//      pixels, so a corner has at least two compass pixels with |I - Ic| > minTh.  VABSDIFF4 + a carry-trick
+//      compare; 4-bit result per word -> mask bytes.
+//   2. ordered-free compaction of the surviving pixels into a shared-memory queue (warp scan + one atomic).
+//   3. per queued pixel: sign-aware compass test, then the exact score.  V = max(A,B)-1 with A/B the max over the
+//      16 arcs of the min of d / -d: both halves are evaluated at once on packed 16-bit pairs
+//      (256+d | 256-d << 16) with the 3-input VIMNMX3.U16x2 (two levels of min3 give the 9-wide arc minimum).
+//   4. 3x3 NMS over the queue only (cell borders count as 0, :809 runs FAST per cell) -> survivor bitmaps, one for
+//      V >= minTh and one for V >= iniTh.
+//   5. one warp per cell: if the iniTh bitmap has any bit in the cell it is used, else the minTh one (:809-816);
+//      row-major emission order comes from popcount prefix sums over the bitmap rows.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kSegThreads = 256;
+constexpr int kBmWords = 10;   // 256-bit bitmap row + 2 words so a 64-bit window can be read at any offset
+
+__host__ __device__ inline int fast_seg_smem_bytes(int hbox, int th_max) {
+    return hbox * kSegPitch + (th_max + 2) * kSegPitch + th_max * 64 + 2 * th_max * kBmWords * 4 + kSegMaxTw * th_max * 2 + 256 + 128;
+}
+
+__device__ __forceinline__ uint32_t gt_bytes(uint32_t x, uint32_t kadd, bool big) {
+    // 0x80 in every byte of x that is > t.  t < 127: kadd = (0x7f - t) per byte, carry from the low 7 bits or bit 7 itself;
+    // t >= 127: needs bit 7 and the low 7 bits > t - 128: kadd = (0xff - t) per byte.
+    const uint32_t s = (x & 0x7f7f7f7fu) + kadd;
+    return big ? (s & x & 0x80808080u) : ((s | x) & 0x80808080u);
+}
+
+__global__ void __launch_bounds__(kSegThreads) k_fast_seg(const __grid_constant__ ExtractParams P, const CUtensorMap* __restrict__ tmaps) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t mbar;
+    __shared__ int qn;
+
+    const Segment sg = P.segs[blockIdx.x];
+    const int frame = blockIdx.y;
+    const Level& L = P.lv[sg.level];
+    const int t = threadIdx.x, lane = t & 31, wi = t >> 5;
+    const int th = sg.th, tw = sg.tw, hbox = L.hbox;
+    // TMA needs a 16-byte aligned start column: the tile begins at gx, tested pixel px sits at tile column ox + px
+    const int gx = (kXPad + sg.x0 - 3) & ~15, ox = kXPad + sg.x0 - gx;   // 3 <= ox <= 18
+
+    uint8_t* tile = smem;                                                   // [hbox][256]
+    uint8_t* score = tile + hbox * kSegPitch;                               // [th+2][256], pixel (px,py) at [py+1][px+4]
+    uint8_t* mk = score + (th + 2) * kSegPitch;                             // [th][64] 4-bit rejection results per word
+    uint32_t* bm_min = reinterpret_cast<uint32_t*>(mk + th * 64);           // [th][kBmWords]
+    uint32_t* bm_ini = bm_min + th * kBmWords;
+    uint16_t* queue = reinterpret_cast<uint16_t*>(bm_ini + th * kBmWords);  // [tw*th] py << 8 | px
+    uint8_t* lut = reinterpret_cast<uint8_t*>(queue + tw * th);             // [256] bit0: first column of its cell, bit1: last
+
+    if (t == 0) {
+        mbar_init(&mbar, 1);
+        qn = 0;
+    }
+    __syncthreads();
+    if (t == 0) {
+        mbar_expect_tx(&mbar, (uint32_t)(hbox * kSegPitch));
+        tma_load_3d(tile, tmaps + sg.level, gx, kEdge + sg.y0 - 3, frame, &mbar);
+    }
+    // while the tile is in flight: clear score map, masks, bitmaps; build the cell-column table
+    {
+        uint4* z = reinterpret_cast<uint4*>(score);
+        const int nz = ((th + 2) * kSegPitch + th * 64 + 2 * th * kBmWords * 4) / 16;
+        for (int i = t; i < nz; i += kSegThreads) z[i] = make_uint4(0, 0, 0, 0);
+        const int wc = L.wcell;
+        for (int px = t; px < 256; px += kSegThreads) {
+            const int j = px / wc, lo = j * wc, hi = min(lo + wc, tw) - 1;
+            lut[px] = (uint8_t)((px == lo ? 1 : 0) | (px == hi ? 2 : 0));
+        }
+    }
+    __syncthreads();
+    mbar_wait(&mbar, 0);
+
+    const int min_th = P.min_th, ini_th = P.ini_th;
+    // ---- 1. rejection test on words -----------------------------------------------------------------------
+    {
+        const uint32_t* T = reinterpret_cast<const uint32_t*>(tile);
+        const int w0 = ox >> 2, nw = ((ox + tw + 3) >> 2) - w0, total = th * nw;
+        const bool big = min_th >= 127;
+        const uint32_t kadd = (uint32_t)(big ? 0xff - min_th : 0x7f - min_th) * 0x01010101u;
+        const uint32_t head = 0xffffffffu << (8 * (ox & 3));                                            // tested bytes of the first word
+        const uint32_t tail = ((ox + tw) & 3) ? (0xffffffffu >> (8 * (4 - ((ox + tw) & 3)))) : 0xffffffffu;   // ... of the last word
+        for (int u = t; u < total; u += kSegThreads) {
+            const int r = (int)__umulhi((uint32_t)u, sg.nw_magic);
+            const int wr = u - r * nw, w = w0 + wr;
+            const uint32_t* row = T + (r + 3) * 64 + w;
+            const uint32_t c = row[0], lw = row[-1], rw = row[1], up = row[-3 * 64], dn = row[3 * 64];
+            const uint32_t lf = __funnelshift_r(lw, c, 8), rt = __funnelshift_r(c, rw, 24);   // pixels x-3 / x+3
+            const uint32_t ma = gt_bytes(__vabsdiffu4(c, up), kadd, big), mb = gt_bytes(__vabsdiffu4(c, dn), kadd, big);
+            const uint32_t mc = gt_bytes(__vabsdiffu4(c, lf), kadd, big), md = gt_bytes(__vabsdiffu4(c, rt), kadd, big);
+            uint32_t ge2 = (ma & mb) | (mc & md) | ((ma ^ mb) & (mc ^ md));
+            if (wr == 0) ge2 &= head;
+            if (wr == nw - 1) ge2 &= tail;
+            // bits 7,15,23,31 -> 4-bit value
+            mk[r * 64 + w] = (uint8_t)((((ge2 >> 7) * 0x01020408u) >> 24) & 0xf);
+        }
+    }
+    __syncthreads();
+    // ---- 2. compaction of the surviving pixels into the queue ---------------------------------------------
+    {
+        const uint32_t* M = reinterpret_cast<const uint32_t*>(mk);
+        const int nwords = th * 16;
+        for (int i0 = 0; i0 < nwords; i0 += kSegThreads) {
+            const int i = i0 + t;
+            uint32_t v = i < nwords ? M[i] : 0u;
+            const int cnt = __popc(v);
+            int inc = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int o = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += o;
+            }
+            int base = 0;
+            if (lane == 31 && inc) base = atomicAdd(&qn, inc);
+            base = __shfl_sync(0xffffffffu, base, 31) + inc - cnt;
+            const int r = i >> 4, w0 = (i & 15) * 4;
+            while (v) {
+                const int b = __ffs(v) - 1;
+                v &= v - 1;
+                const int px = 4 * (w0 + (b >> 3)) + (b & 7) - ox;
+                queue[base++] = (uint16_t)((r << 8) | px);
+            }
+        }
+    }
+    __syncthreads();
+    const int nq = qn;
+    // ---- 3. exact score of the queued pixels ------------------------------------------------------------------
+    for (int q = t; q < nq; q += kSegThreads) {
+        const int e = queue[q], r = e >> 8, px = e & 255;
+        const uint8_t* p = tile + (r + 3) * kSegPitch + px + ox;
+        const int v = p[0];
+        uint32_t rg[16];
+        rg[0] = p[3 * kSegPitch]; rg[4] = p[3]; rg[8] = p[-3 * kSegPitch]; rg[12] = p[-3];
+        {
+            const int d0 = v - (int)rg[0], d4 = v - (int)rg[4], d8 = v - (int)rg[8], d12 = v - (int)rg[12];
+            const int nb = (d0 > min_th) + (d4 > min_th) + (d8 > min_th) + (d12 > min_th);
+            const int nd = (d0 < -min_th) + (d4 < -min_th) + (d8 < -min_th) + (d12 < -min_th);
+            if (nb < 2 && nd < 2) continue;
+        }
+        rg[1] = p[3 * kSegPitch + 1];   rg[2] = p[2 * kSegPitch + 2];   rg[3] = p[kSegPitch + 3];
+        rg[5] = p[-kSegPitch + 3];      rg[6] = p[-2 * kSegPitch + 2];  rg[7] = p[-3 * kSegPitch + 1];
+        rg[9] = p[-3 * kSegPitch - 1];  rg[10] = p[-2 * kSegPitch - 2]; rg[11] = p[-kSegPitch - 3];
+        rg[13] = p[kSegPitch - 3];      rg[14] = p[2 * kSegPitch - 2];  rg[15] = p[3 * kSegPitch - 1];
+        const uint32_t bias = ((uint32_t)(256 - v) << 16) | (uint32_t)(256 + v);
+        uint32_t E[16], m3[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) E[k] = rg[k] * 0xFFFFu + bias;     // lo: 256 + d_k, hi: 256 - d_k
+#pragma unroll
+        for (int k = 0; k < 16; ++k) m3[k] = __vimin3_u16x2(E[k], E[(k + 1) & 15], E[(k + 2) & 15]);
+        uint32_t m9[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) m9[k] = __vimin3_u16x2(m3[k], m3[(k + 3) & 15], m3[(k + 6) & 15]);
+        uint32_t a = __vimax3_u16x2(m9[0], m9[1], m9[2]), b = __vimax3_u16x2(m9[3], m9[4], m9[5]);
+        uint32_t c = __vimax3_u16x2(m9[6], m9[7], m9[8]), d = __vimax3_u16x2(m9[9], m9[10], m9[11]);
+        uint32_t f = __vimax3_u16x2(m9[12], m9[13], m9[14]);
+        a = __vimax3_u16x2(a, b, c);
+        d = __vimax3_u16x2(d, f, m9[15]);
+        a = __vmaxu2(a, d);
+        const int V = max((int)(a & 0xffffu), (int)(a >> 16)) - 257;
+        if (V >= min_th) score[(r + 1) * kSegPitch + px + 4] = (uint8_t)V;
+    }
+    __syncthreads();
+    // ---- 4. NMS over the queue ---------------------------------------------------------------------------------
+    for (int q = t; q < nq; q += kSegThreads) {
+        const int e = queue[q], r = e >> 8, px = e & 255;
+        const uint8_t* s = score + (r + 1) * kSegPitch + px + 4;
+        const int v = s[0];
+        if (v == 0) continue;
+        const int fl = lut[px];
+        bool k = v > s[-kSegPitch] && v > s[kSegPitch];
+        if (!(fl & 1)) k = k && v > s[-1] && v > s[-kSegPitch - 1] && v > s[kSegPitch - 1];
+        if (!(fl & 2)) k = k && v > s[1] && v > s[-kSegPitch + 1] && v > s[kSegPitch + 1];
+        if (k) {
+            atomicOr(&bm_min[r * kBmWords + (px >> 5)], 1u << (px & 31));
+            if (v >= ini_th) atomicOr(&bm_ini[r * kBmWords + (px >> 5)], 1u << (px & 31));
+        }
+    }
+    __syncthreads();
+    // ---- 5. per-cell threshold vote and ordered emission ------------------------------------------------------
+    const int wc = L.wcell;
+    for (int j = wi; j < sg.ncells; j += kSegThreads / 32) {
+        const int ci = sg.first_cell + j;
+        const Cell c = P.cells[ci];
+        const int cx = j * wc, cw = c.tw;
+        const uint64_t wmask = cw >= 64 ? ~0ull : ((1ull << cw) - 1);
+        uint64_t mm[2], mi[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int row = lane + 32 * h;
+            mm[h] = 0; mi[h] = 0;
+            if (row < th) {
+                const uint32_t* a = bm_min + row * kBmWords + (cx >> 5);
+                const uint32_t* b = bm_ini + row * kBmWords + (cx >> 5);
+                const int sh = cx & 31;
+                mm[h] = (((uint64_t)__funnelshift_r(a[1], a[2], sh) << 32) | __funnelshift_r(a[0], a[1], sh)) & wmask;
+                mi[h] = (((uint64_t)__funnelshift_r(b[1], b[2], sh) << 32) | __funnelshift_r(b[0], b[1], sh)) & wmask;
+            }
+        }
+        const bool any_ini = __any_sync(0xffffffffu, (mi[0] | mi[1]) != 0);
+        if (any_ini) { mm[0] = mi[0]; mm[1] = mi[1]; }
+        const int c0 = __popcll(mm[0]), c1 = __popcll(mm[1]);
+        int i0 = c0, i1 = c1;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o0 = __shfl_up_sync(0xffffffffu, i0, d), o1 = __shfl_up_sync(0xffffffffu, i1, d);
+            if (lane >= d) { i0 += o0; i1 += o1; }
+        }
+        const int tot0 = __shfl_sync(0xffffffffu, i0, 31), tot1 = __shfl_sync(0xffffffffu, i1, 31);
+        uint32_t* oxy = P.cand_xy + (long long)frame * P.total_cand_cap + L.cand_base + c.slot;
+        uint8_t* orr = P.cand_resp + (long long)frame * P.total_cand_cap + L.cand_base + c.slot;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int row = lane + 32 * h;
+            int pos = h == 0 ? i0 - c0 : tot0 + i1 - c1;
+            uint64_t m = mm[h];
+            while (m) {
+                const int b = __ffsll((long long)m) - 1;
+                m &= m - 1;
+                // coordinates relative to (minBorderX, minBorderY) = (16,16) as the reference stores them (:822-823)
+                oxy[pos] = ((uint32_t)(c.y0 + row - 16) << 16) | (uint32_t)(c.x0 + b - 16);
+                orr[pos] = score[(row + 1) * kSegPitch + cx + b + 4];
+                ++pos;
+            }
+        }
+        if (lane == 0) P.cell_count[(long long)frame * P.total_cells + ci] = tot0 + tot1;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------

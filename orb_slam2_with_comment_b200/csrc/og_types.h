@@ -42,6 +42,7 @@ struct Level {
     float scale;             // mvScaleFactor[l]
     float kp_size;           // (float)(int)(31 * scale) (:837)
     long long ot_base;       // byte offset of this level's octree workspace inside a frame's workspace
+    int wcell, hbox;         // cell pitch in x (:785); rows of the FAST tile box (tallest cell + 6)
 };
 
 // One FAST cell (:789-806): the reference runs cv::FAST on the sub-image [ini, max) and FAST itself never tests
@@ -52,6 +53,17 @@ struct Cell {
     int16_t tw, th;   // tested width / height (> 0)
     int16_t pad;
     int32_t slot;     // first candidate slot of this cell inside the level's slice
+};
+
+// A run of consecutive cells of one cell row whose tested pixels fit one 256-byte-wide shared-memory tile
+// (k_fast_seg): first tested pixel (x0, y0) in level coordinates, tested extent tw x th.
+constexpr int kSegPitch = 256;   // tile row pitch in bytes = TMA box width
+constexpr int kSegMaxTw = 232;   // TMA starts at a 16-byte aligned column: up to 18 bytes before the first tested pixel, 3 after the last
+struct Segment {
+    int16_t level, ncells;
+    int32_t first_cell;          // index into the frame's cell table
+    int16_t x0, y0, tw, th;
+    uint32_t nw_magic;           // ceil(2^32 / nw), nw = 32-bit words covering the tested columns: row = (unit * nw_magic) >> 32
 };
 
 struct ExtractParams {
@@ -71,6 +83,8 @@ struct ExtractParams {
     uint8_t* pyr;
     uint8_t* blur;
     const Cell* cells;
+    const Segment* segs;
+    int n_segs;
     int32_t* cell_count;      // [batch][total_cells]
     uint32_t* cand_xy;        // [batch][total_cand_cap]   y<<16 | x, relative to (minBorderX, minBorderY)
     uint8_t* cand_resp;       // [batch][total_cand_cap]
