@@ -57,6 +57,8 @@ struct orbgpu_extractor {
     uint8_t *d_pyr = nullptr, *d_blur = nullptr, *d_images = nullptr, *d_ot = nullptr;
     og::Cell* d_cells = nullptr;
     og::Segment* d_segs = nullptr;
+    og::BlurTile* d_btiles = nullptr;
+    int n_btiles = 0;
     bool fast_v1 = false;             // ORBGPU_FAST_V1=1: first-generation per-cell kernel (kept for A/B timing)
     CUtensorMap* d_tmaps = nullptr;   // [2][kMaxLevels]: FAST tile boxes over pyr, then (reserved) over blur
     int fast_smem = 0;
@@ -79,6 +81,7 @@ struct Geometry {
     og::ExtractParams P;
     std::vector<og::Cell> cells;
     std::vector<og::Segment> segs;
+    std::vector<og::BlurTile> btiles;
     std::vector<og::Tap> taps;            // all levels' x then y tables, concatenated
     std::vector<size_t> xt_off, yt_off;   // offsets into taps
     size_t pyr_bytes_per_frame = 0;
@@ -275,6 +278,8 @@ std::string build_geometry(const orbgpu_extractor& ex, int w, int h, int batch_c
         sel_base += L.sel_cap;
         L.scale = ex.scale[l];
         L.kp_size = (float)(int)(31 * ex.scale[l]);  // :837 (PATCH_SIZE*mvScaleFactor -> int)
+        for (int ty = 0; ty < (L.h + og::kBlurH - 1) / og::kBlurH; ++ty)
+            for (int tx = 0; tx < (L.w + og::kBlurW - 1) / og::kBlurW; ++tx) G.btiles.push_back({(int16_t)l, (int16_t)tx, (int16_t)ty, 0});
         L.ot_base = (long long)ot_off;
         ot_off += align_up(octree_ws_bytes(L.cand_cap, L.node_cap), 256);
     }
@@ -302,6 +307,9 @@ int ensure_geometry(orbgpu_extractor* ex, int w, int h) {
         return fail(ORBGPU_ERR_CAPACITY, "internal: workspace sized at creation is too small for this frame size");
     OG_CUDA(cudaMemcpyAsync(ex->d_cells, G.cells.data(), G.cells.size() * sizeof(og::Cell), cudaMemcpyHostToDevice, ex->stream));
     OG_CUDA(cudaMemcpyAsync(ex->d_segs, G.segs.data(), G.segs.size() * sizeof(og::Segment), cudaMemcpyHostToDevice, ex->stream));
+    if (G.btiles.size() > ex->cap_cells) return fail(ORBGPU_ERR_CAPACITY, "internal: blur tile table too small");
+    OG_CUDA(cudaMemcpyAsync(ex->d_btiles, G.btiles.data(), G.btiles.size() * sizeof(og::BlurTile), cudaMemcpyHostToDevice, ex->stream));
+    ex->n_btiles = (int)G.btiles.size();
     {
         std::vector<CUtensorMap> maps(2 * og::kMaxLevels);
         memset(maps.data(), 0, maps.size() * sizeof(CUtensorMap));
@@ -309,6 +317,8 @@ int ensure_geometry(orbgpu_extractor* ex, int w, int h) {
         for (int l = 0; l < ex->nlevels; ++l) {
             const og::Level& L = P.lv[l];
             std::string e = make_level_tmap(&maps[l], ex->d_pyr + L.base, L.pitch, L.rows, L.frame_stride, ex->max_batch, og::kSegPitch, L.hbox);
+            if (e.empty())
+                e = make_level_tmap(&maps[og::kMaxLevels + l], ex->d_pyr + L.base, L.pitch, L.rows, L.frame_stride, ex->max_batch, 256, og::kBlurBox);
             if (!e.empty()) return fail(ORBGPU_ERR_CUDA, e);
             smem = std::max(smem, og::fast_seg_smem_bytes(L.hbox, L.hbox - 6));
         }
@@ -378,12 +388,8 @@ int launch_extract(orbgpu_extractor* ex, const uint8_t* d_images, int batch, siz
     og::k_octree<<<dim3(P.n_levels, batch), og::kOctThreads, 0, st>>>(P);
     ++launches;
     mark(3);
-    for (int l = 0; l < P.n_levels; ++l) {
-        const og::Level& L = P.lv[l];
-        dim3 grid((L.w + og::kBlurTW - 1) / og::kBlurTW, (L.h + og::kBlurTH - 1) / og::kBlurTH, batch);
-        og::k_blur<<<grid, og::kBlurThreads, 0, st>>>(P, l);
-        ++launches;
-    }
+    og::k_blur_tma<<<dim3(ex->n_btiles, batch), og::kBlurThreads, 0, st>>>(P, ex->d_btiles, ex->d_tmaps);
+    ++launches;
     mark(4);
     og::k_orient_desc<<<dim3((ex->kp_cap + og::kDescWarps - 1) / og::kDescWarps, batch), og::kDescWarps * 32, 0, st>>>(
         P, d_kp, d_desc, d_counts);
@@ -498,6 +504,7 @@ int orbgpu_extractor_create(orbgpu_extractor** out, int device, int nfeatures, f
     alloc((void**)&ex->d_images, (size_t)max_width * max_height * B);
     alloc((void**)&ex->d_cells, ex->cap_cells * sizeof(og::Cell));
     alloc((void**)&ex->d_segs, ex->cap_cells * sizeof(og::Segment));
+    alloc((void**)&ex->d_btiles, ex->cap_cells * sizeof(og::BlurTile));
     alloc((void**)&ex->d_tmaps, 2 * og::kMaxLevels * sizeof(CUtensorMap));
     { const char* e = getenv("ORBGPU_FAST_V1"); ex->fast_v1 = e && e[0] == '1'; }
     alloc((void**)&ex->d_taps, ex->cap_taps * sizeof(og::Tap));
@@ -526,7 +533,7 @@ int orbgpu_extractor_destroy(orbgpu_extractor* ex) {
     cudaSetDevice(ex->device);
     if (ex->stream) { cudaStreamSynchronize(ex->stream); cudaStreamDestroy(ex->stream); }
     for (int i = 0; i < 6; ++i) if (ex->ev[i]) cudaEventDestroy(ex->ev[i]);
-    void* ptrs[] = {ex->d_segs, ex->d_tmaps, ex->d_pyr, ex->d_blur, ex->d_images, ex->d_cells, ex->d_taps, ex->d_cell_count, ex->d_cand_xy,
+    void* ptrs[] = {ex->d_btiles, ex->d_segs, ex->d_tmaps, ex->d_pyr, ex->d_blur, ex->d_images, ex->d_cells, ex->d_taps, ex->d_cell_count, ex->d_cand_xy,
                     ex->d_cand_resp, ex->d_ot, ex->d_sel_xy, ex->d_sel_resp, ex->d_sel_count, ex->d_counts, ex->d_kp, ex->d_desc};
     for (void* p : ptrs) if (p) cudaFree(p);
     delete ex;

@@ -485,41 +485,67 @@ __global__ void __launch_bounds__(kOctThreads) k_octree_single(uint8_t* ws, int 
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// GaussianBlur 7x7 (separable, fixed point).  The level buffers carry a 19-px reflect-101 frame, which is exactly
-// what BORDER_REFLECT_101 of the isolated clone needs for taps up to 3 px outside (:1085-1086), so the stencil
-// has no border logic.  CTA tile: 128 x 16 outputs, 256 threads.
+// GaussianBlur 7x7 (separable, fixed point, Appendix A.2).  The level buffers carry a 19-px reflect-101 frame, which
+// is exactly what BORDER_REFLECT_101 of the isolated clone needs for taps up to 3 px outside (:1085-1086), so the
+// stencil has no border logic.  One CTA = 224 x 64 outputs of one (level, frame); the 256 x 70 input tile arrives by
+// TMA (16-byte aligned origin: 16 spare columns on each side).  A thread owns one 32-bit word (4 columns) and walks
+// down 32 rows: the horizontal pass is two DP4A per pixel on byte windows cut with funnel shifts, the vertical pass
+// runs on a 7-row register window (fully unrolled, so the window rotates by renaming).
 // ------------------------------------------------------------------------------------------------------------
-constexpr int kBlurTW = 128, kBlurTH = 16, kBlurThreads = 256;
+constexpr int kBlurW = 224, kBlurH = 64, kBlurBox = kBlurH + 6, kBlurThreads = 128;
 
-__global__ void __launch_bounds__(kBlurThreads) k_blur(const __grid_constant__ ExtractParams P, int level) {
-    __shared__ uint8_t in[(kBlurTH + 6)][kBlurTW + 8];
-    __shared__ uint16_t hp[(kBlurTH + 6)][kBlurTW];
-    const Level& L = P.lv[level];
-    const int frame = blockIdx.z;
-    const int x0 = blockIdx.x * kBlurTW, y0 = blockIdx.y * kBlurTH;
-    const uint8_t* src = level_ptr(P.pyr, L, frame);
-    const int t = threadIdx.x;
-    // input rows y0-3 .. y0+TH+2, columns x0-3 .. x0+TW+2 (+2 spare)
-    for (int i = t; i < (kBlurTH + 6) * (kBlurTW + 8); i += kBlurThreads) {
-        const int r = i / (kBlurTW + 8), q = i - r * (kBlurTW + 8);
-        const int Y = kEdge + y0 - 3 + r, X = kXPad + x0 - 3 + q;
-        in[r][q] = (Y < L.rows && X < L.pitch) ? src[(long long)Y * L.pitch + X] : 0;
-    }
+struct BlurTile {
+    int16_t level, tx, ty, pad;
+};
+
+__global__ void __launch_bounds__(kBlurThreads) k_blur_tma(const __grid_constant__ ExtractParams P, const BlurTile* __restrict__ tiles,
+                                                           const CUtensorMap* __restrict__ tmaps) {
+    __shared__ __align__(1024) uint8_t tile[kBlurBox * 256];
+    __shared__ uint64_t mbar;
+    const BlurTile bt = tiles[blockIdx.x];
+    const Level& L = P.lv[bt.level];
+    const int frame = blockIdx.y, t = threadIdx.x;
+    if (t == 0) mbar_init(&mbar, 1);
     __syncthreads();
-    for (int i = t; i < (kBlurTH + 6) * kBlurTW; i += kBlurThreads) {
-        const int r = i / kBlurTW, q = i - r * kBlurTW;
-        const uint8_t* p = &in[r][q];
-        hp[r][q] = (uint16_t)blur_tap7(p[0], p[1], p[2], p[3], p[4], p[5], p[6]);
+    if (t == 0) {
+        mbar_expect_tx(&mbar, kBlurBox * 256);
+        // tile column 16 = interior column 224*tx (global column kXPad + 224*tx), tile row 3 = interior row 64*ty
+        tma_load_3d(tile, tmaps + kMaxLevels + bt.level, kXPad - 16 + kBlurW * bt.tx, kEdge - 3 + kBlurH * bt.ty, frame, &mbar);
     }
-    __syncthreads();
-    uint8_t* dst = level_ptr(P.blur, L, frame);
-    for (int i = t; i < kBlurTH * kBlurTW; i += kBlurThreads) {
-        const int r = i / kBlurTW, q = i - r * kBlurTW;
-        const int x = x0 + q, y = y0 + r;
-        if (x < L.w && y < L.h) {
-            const uint32_t acc = (uint32_t)blur_tap7(hp[r][q], hp[r + 1][q], hp[r + 2][q], hp[r + 3][q], hp[r + 4][q],
-                                                    hp[r + 5][q], hp[r + 6][q]);
-            dst[(long long)(kEdge + y) * L.pitch + kXPad + x] = blur_finish(acc);
+    const int c = t & 63, band = t >> 6;
+    const int x = kBlurW * bt.tx + 4 * c;          // first of this thread's 4 interior columns
+    const int ybase = kBlurH * bt.ty + 32 * band;  // first output row of this band
+    mbar_wait(&mbar, 0);
+    if (c >= kBlurW / 4 || x >= L.w || ybase >= L.h) return;
+    const uint32_t* T = reinterpret_cast<const uint32_t*>(tile) + (32 * band) * 64 + 4 + c;
+    const uint32_t KLO = OG_G0 | (OG_G1 << 8) | (OG_G2 << 16) | (OG_G3 << 24), KHI = OG_G2 | (OG_G1 << 8) | (OG_G0 << 16);
+    uint8_t* dst = level_ptr(P.blur, L, frame) + (long long)(kEdge + ybase) * L.pitch + kXPad + x;
+    const int nrows = min(32, L.h - ybase);
+    uint32_t a[7][4];
+#pragma unroll
+    for (int i = 0; i < 38; ++i) {
+        // horizontal pass of tile row 32*band + i
+        const uint32_t pw = T[i * 64 - 1], cw = T[i * 64], nw = T[i * 64 + 1];
+        const uint32_t m3 = __funnelshift_r(pw, cw, 8), m2 = __funnelshift_r(pw, cw, 16), m1 = __funnelshift_r(pw, cw, 24);
+        const uint32_t p1 = __funnelshift_r(cw, nw, 8), p2 = __funnelshift_r(cw, nw, 16), p3 = __funnelshift_r(cw, nw, 24);
+        uint32_t* h = a[i % 7];
+        h[0] = __dp4a(m3, KLO, __dp4a(p1, KHI, 0u));
+        h[1] = __dp4a(m2, KLO, __dp4a(p2, KHI, 0u));
+        h[2] = __dp4a(m1, KLO, __dp4a(p3, KHI, 0u));
+        h[3] = __dp4a(cw, KLO, __dp4a(nw, KHI, 0u));
+        if (i >= 6) {
+            const int r = i - 6;   // output row of the band; window rows r..r+6 live in a[(r+k) % 7]
+            if (r < nrows) {
+                uint32_t o[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t acc = OG_G0 * (a[(r + 0) % 7][j] + a[(r + 6) % 7][j]) + OG_G1 * (a[(r + 1) % 7][j] + a[(r + 5) % 7][j]) +
+                                         OG_G2 * (a[(r + 2) % 7][j] + a[(r + 4) % 7][j]) + OG_G3 * a[(r + 3) % 7][j] + 32768u;
+                    o[j] = acc;   // result byte = bits 16..23
+                }
+                const uint32_t lo = __byte_perm(o[0], o[1], 0x0062), hi = __byte_perm(o[2], o[3], 0x0062);
+                *reinterpret_cast<uint32_t*>(dst + (long long)r * L.pitch) = __byte_perm(lo, hi, 0x5410);
+            }
         }
     }
 }
