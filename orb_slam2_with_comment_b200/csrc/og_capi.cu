@@ -186,8 +186,10 @@ std::string build_geometry(const orbgpu_extractor& ex, int w, int h, int batch_c
         L.base = (long long)pyr_off;
         pyr_off += (size_t)L.frame_stride * batch_cap;
         if (l > 0) {
+            while (G.taps.size() % 4) G.taps.push_back(og::Tap{0, 0, 0, 0});   // 32-byte aligned: k_resize4 loads 4 taps as 2 x uint4
             G.xt_off.push_back(G.taps.size());
             make_taps(P.lv[l - 1].w, L.w, true, G.taps);
+            while (G.taps.size() % 4) G.taps.push_back(G.taps.back());          // padded outputs repeat the last column
             G.yt_off.push_back(G.taps.size());
             make_taps(P.lv[l - 1].h, L.h, false, G.taps);
         } else {
@@ -372,10 +374,25 @@ int launch_extract(orbgpu_extractor* ex, const uint8_t* d_images, int batch, siz
         og::k_level0<<<grid, 128, 0, st>>>(P, d_images, (long long)row_stride, (long long)frame_stride);
         ++launches;
     }
+    bool generic = false;
     for (int l = 1; l < P.n_levels; ++l) {
         const og::Level& L = P.lv[l];
-        dim3 grid((L.pitch / 4 + 127) / 128, L.rows, batch);
-        og::k_resize<<<grid, 128, 0, st>>>(P, l);
+        // the vectorised kernel needs the 4 outputs of a thread inside 12 source bytes: scale <= 2
+        if ((double)P.lv[l - 1].w / L.w <= 2.0) {
+            const int nwx = (L.w + 3) / 4, bands = (L.h + og::kResizeRows - 1) / og::kResizeRows, n_items = nwx * bands;
+            const uint32_t magic = (uint32_t)((0x100000000ull + nwx - 1) / nwx);
+            og::k_resize4<<<dim3((n_items + og::kResizeThreads - 1) / og::kResizeThreads, batch), og::kResizeThreads, 0, st>>>(P, l, nwx, magic, n_items);
+        } else {
+            dim3 grid((L.pitch / 4 + 127) / 128, L.rows, batch);
+            og::k_resize<<<grid, 128, 0, st>>>(P, l);
+            generic = true;
+        }
+        ++launches;
+    }
+    if (P.n_levels > 1 && !generic) {
+        int nblk = 0;
+        for (int l = 1; l < P.n_levels; ++l) nblk += (P.lv[l].rows + og::kBorderRows - 1) / og::kBorderRows;
+        og::k_borders<<<dim3(nblk, batch), og::kBorderThreads, 0, st>>>(P);
         ++launches;
     }
     mark(1);

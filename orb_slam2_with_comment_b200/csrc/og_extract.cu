@@ -76,6 +76,107 @@ __global__ void k_resize(const __grid_constant__ ExtractParams P, int level) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Level l from level l-1, interior only, vectorised: a thread produces 4 consecutive pixels (one 32-bit store) of
+// kResizeRows consecutive rows.  The 4 outputs read at most 12 consecutive source bytes (scale <= 2), fetched as
+// three aligned words per source row; the byte pair of every output is cut out with a funnel shift whose word
+// choice and shift depend only on x and are computed once.  Consecutive output rows share a source row about
+// every other step (scale 1.2): the horizontal pass of the shared row is reused.
+// The 19-px frames of all levels are written afterwards by k_borders.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kResizeRows = 8, kResizeThreads = 128;
+
+__global__ void __launch_bounds__(kResizeThreads) k_resize4(const __grid_constant__ ExtractParams P, int level, int nwx, uint32_t nwx_magic,
+                                                            int n_items) {
+    const Level& L = P.lv[level];
+    const Level& S = P.lv[level - 1];
+    const int frame = blockIdx.y;
+    const int id = blockIdx.x * kResizeThreads + threadIdx.x;
+    if (id >= n_items) return;
+    const int band = (int)__umulhi((uint32_t)id, nwx_magic), wx = id - band * nwx;
+    const int x = 4 * wx, y0 = band * kResizeRows;
+    // x taps of the 4 outputs (the table is padded to a multiple of 4 entries)
+    const uint4 ta = __ldg(reinterpret_cast<const uint4*>(L.xt + x)), tb = __ldg(reinterpret_cast<const uint4*>(L.xt + x) + 1);
+    const uint32_t tw[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};   // per output: (s0 | s1 << 16), (w0 | w1 << 16)
+    const int base = (int)(tw[0] & 0xffffu) & ~3;
+    int sel[4], sh[4], w0[4], w1[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int o = (int)(tw[2 * j] & 0xffffu) - base;   // 0..9
+        sel[j] = o >> 2;
+        sh[j] = 8 * (o & 3);
+        w0[j] = (int)(tw[2 * j + 1] & 0xffffu);
+        w1[j] = (int)(tw[2 * j + 1] >> 16);
+    }
+    const uint8_t* src = level_ptr(P.pyr, S, frame) + (long long)kEdge * S.pitch + kXPad + base;
+    uint8_t* dst = level_ptr(P.pyr, L, frame) + (long long)kEdge * L.pitch + kXPad + x;
+    auto hrow = [&](int sy, int (&h)[4]) {
+        const uint32_t* r = reinterpret_cast<const uint32_t*>(src + (long long)sy * S.pitch);
+        const uint32_t W0 = __ldg(r), W1 = __ldg(r + 1), W2 = __ldg(r + 2);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t lo = sel[j] == 0 ? W0 : (sel[j] == 1 ? W1 : W2), hi = sel[j] == 0 ? W1 : W2;
+            const uint32_t pr = __funnelshift_r(lo, hi, sh[j]);
+            const int p0 = (int)(pr & 0xffu), p1 = (int)((pr >> 8) & 0xffu);
+            h[j] = resize_hpass(p0, p1, w0[j], w1[j]);
+        }
+    };
+    int h0[4], h1[4], prev_s1 = -1;
+#pragma unroll 1
+    for (int r = 0; r < kResizeRows; ++r) {
+        const int y = y0 + r;
+        if (y >= L.h) break;
+        const Tap ty = L.yt[y];
+        if (ty.s0 == prev_s1) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) h0[j] = h1[j];
+        } else {
+            hrow(ty.s0, h0);
+        }
+        if (ty.s1 == ty.s0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) h1[j] = h0[j];
+        } else {
+            hrow(ty.s1, h1);
+        }
+        prev_s1 = ty.s1;
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = resize_vpass(h0[j], h1[j], ty.w0, ty.w1);
+        *reinterpret_cast<uint32_t*>(dst + (long long)y * L.pitch) = o[0] | (o[1] << 8) | (o[2] << 16) | (o[3] << 24);
+    }
+}
+
+// The BORDER_REFLECT_101 frame of levels 1.. (:1122-1123; level 0 gets its frame in k_level0).  One CTA per 8 padded rows.
+constexpr int kBorderRows = 8, kBorderThreads = 128;
+__global__ void __launch_bounds__(kBorderThreads) k_borders(const __grid_constant__ ExtractParams P) {
+    const int frame = blockIdx.y;
+    int level = 1, blk = blockIdx.x;
+    while (level < P.n_levels) {
+        const int nb = (P.lv[level].rows + kBorderRows - 1) / kBorderRows;
+        if (blk < nb) break;
+        blk -= nb;
+        ++level;
+    }
+    if (level >= P.n_levels) return;
+    const Level& L = P.lv[level];
+    uint8_t* img = level_ptr(P.pyr, L, frame);
+    const int W = L.w + 2 * kEdge;
+    for (int rr = 0; rr < kBorderRows; ++rr) {
+        const int Y = blk * kBorderRows + rr;
+        if (Y >= L.rows) break;
+        const int y = reflect101(Y - kEdge, L.h);
+        const uint8_t* srow = img + (long long)(kEdge + y) * L.pitch + kXPad;
+        uint8_t* drow = img + (long long)Y * L.pitch + kXPad - kEdge;
+        if (Y < kEdge || Y >= kEdge + L.h) {
+            for (int X = threadIdx.x; X < W; X += kBorderThreads) drow[X] = srow[reflect101(X - kEdge, L.w)];
+        } else if (threadIdx.x < 2 * kEdge) {
+            const int X = threadIdx.x < kEdge ? threadIdx.x : L.w + threadIdx.x;
+            drow[X] = srow[reflect101(X - kEdge, L.w)];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // FAST per cell.  One CTA per (cell, frame).  The score V is threshold-free, so one score map + one NMS pass +
 // a per-cell vote "any survivor with V >= iniTh?" reproduces FAST(iniTh) / fallback FAST(minTh) (:809-816).
 // Survivors are written in row-major order into the cell's private slot range (no atomics, deterministic).
