@@ -64,6 +64,11 @@ int orbgpu_extractor_destroy(orbgpu_extractor* ex);
  * = mnFeaturesPerLevel; umax[16].  Any pointer may be NULL. */
 int orbgpu_extractor_tables(const orbgpu_extractor* ex, float* scales, int32_t* features_per_level, int32_t* umax);
 
+/* The same tables without a handle or a device (pure host arithmetic of the constructor, ORBextractor.cc:413-469):
+ * the C++ shell needs them at construction, before the first image fixes the workspace size. */
+int orbgpu_extractor_static_tables(int nfeatures, float scale_factor, int nlevels, float* scales, int32_t* features_per_level,
+                                   int32_t* umax);
+
 /* Upper bound on the keypoints one frame can yield (nfeatures + 3*nlevels): size kp/desc buffers with it. */
 int orbgpu_extractor_max_keypoints(const orbgpu_extractor* ex);
 

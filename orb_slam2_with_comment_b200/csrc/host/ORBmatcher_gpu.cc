@@ -1,0 +1,234 @@
+// ORBmatcher_gpu.cc — the four Hamming-path search functions of ORB_SLAM2::ORBmatcher as members of the reference's own
+// class (declared in the reference's include/ORBmatcher.h), implemented on the GPU through the C ABI of include/orbgpu.h:
+//
+//   SearchByProjection(Frame&, const vector<MapPoint*>&, th)      replaces src/ORBmatcher.cc:59-155
+//   SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&)            replaces :211-344
+//   SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&)         replaces :635-768
+//   SearchForTriangulation(KeyFrame*, KeyFrame*, F12, pairs, ..)  replaces :783-975
+//
+// Integration: compile this file into the ORB_SLAM2 library and remove (or #ifdef out) those four bodies from the
+// reference's ORBmatcher.cc; everything else of that file — the constructor, DescriptorDistance, the other search
+// functions — stays the reference's CPU code.  Each function flattens the Frame / KeyFrame / MapPoint
+// members the reference body reads into the views of orbgpu.h, makes ONE call, and writes the result back into the
+// caller's containers exactly where the reference does.  No distance is computed on the host.
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "ORBmatcher.h"
+#include "orbgpu.h"
+
+namespace ORB_SLAM2 {
+
+static_assert(sizeof(cv::KeyPoint) == sizeof(orbgpu_keypoint), "cv::KeyPoint must be the 28-byte record the C ABI reads");
+
+namespace {
+
+void check(int rc, const char* what) {
+    if (rc != 0) throw std::runtime_error(std::string("ORBmatcher (GPU): ") + what + ": " + orbgpu_last_error());
+}
+
+// ORBmatcher objects are short-lived stack objects (one per call site invocation); the device handle (stream, scratch)
+// is kept per host thread instead — Tracking, LocalMapping and LoopClosing each get their own.
+struct ThreadMatcher {
+    orbgpu_matcher* m;
+    ThreadMatcher() : m(nullptr) {}
+    ~ThreadMatcher() { if (m) orbgpu_matcher_destroy(m); }
+};
+orbgpu_matcher* matcher() {
+    thread_local ThreadMatcher t;
+    if (!t.m) check(orbgpu_matcher_create(&t.m, 0), "cannot create the device matcher");
+    return t.m;
+}
+
+// N x 32 descriptor rows as one contiguous block (DescriptorDistance reads rows as 8 int32, ORBmatcher.cc:1903-1904)
+const uint8_t* rows32(const cv::Mat& d, std::vector<uint8_t>& tmp) {
+    if (d.rows == 0) return tmp.data();
+    if (d.isContinuous()) return d.ptr(0);
+    tmp.resize((size_t)d.rows * 32);
+    for (int i = 0; i < d.rows; ++i) std::memcpy(tmp.data() + (size_t)i * 32, d.ptr(i), 32);
+    return tmp.data();
+}
+
+// std::map<NodeId, vector<unsigned>> -> CSR (ascending node ids, features in vector order)
+struct FlatFeatVec {
+    int32_t node_off[2];
+    std::vector<int32_t> node_id, feat_off, feat;
+    explicit FlatFeatVec(const DBoW2::FeatureVector& fv) {
+        node_off[0] = 0;
+        feat_off.push_back(0);
+        for (DBoW2::FeatureVector::const_iterator it = fv.begin(); it != fv.end(); ++it) {
+            node_id.push_back((int32_t)it->first);
+            for (size_t k = 0; k < it->second.size(); ++k) feat.push_back((int32_t)it->second[k]);
+            feat_off.push_back((int32_t)feat.size());
+        }
+        node_off[1] = (int32_t)node_id.size();
+    }
+    void attach(orbgpu_frame_set& s) const {
+        s.fv_node_off = node_off;
+        s.fv_node_id = node_id.data();
+        s.fv_feat_off = feat_off.data();
+        s.fv_feat = feat.data();
+    }
+};
+
+orbgpu_frame_set one_frame(const int32_t* kp_off, const std::vector<cv::KeyPoint>& keys, const uint8_t* desc) {
+    orbgpu_frame_set s;
+    std::memset(&s, 0, sizeof(s));
+    s.n_frames = 1;
+    s.kp_off = kp_off;
+    s.keys_un = reinterpret_cast<const orbgpu_keypoint*>(keys.data());
+    s.desc = desc;
+    return s;
+}
+
+const int32_t kZero = 0;
+const int64_t kZero64 = 0;
+
+}  // namespace
+
+int ORBmatcher::SearchByProjection(Frame& F, const std::vector<MapPoint*>& vpMapPoints, const float th) {
+    const int N = (int)F.mvKeysUn.size(), M = (int)vpMapPoints.size();
+    if (N == 0 || M == 0) return 0;
+    const int32_t kp_off[2] = {0, N}, mp_off[2] = {0, M};
+    std::vector<uint8_t> tmp, kflags(N, 0);
+    orbgpu_frame_set fs = one_frame(kp_off, F.mvKeysUn, rows32(F.mDescriptors, tmp));
+    for (int i = 0; i < N; ++i)   // :108-110: a keypoint holding a MapPoint with observations is skipped
+        if (F.mvpMapPoints[i]) kflags[i] = F.mvpMapPoints[i]->Observations() > 0 ? 1 : 2;
+    fs.kp_flags = kflags.data();
+    fs.u_right = F.mvuRight.empty() ? nullptr : F.mvuRight.data();
+    const float grid[4] = {Frame::mnMinX, Frame::mnMinY, Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv};
+    fs.grid = grid;
+
+    std::vector<float> px(M), py(M), pxr(M), vc(M);
+    std::vector<int32_t> lvl(M);
+    std::vector<uint8_t> mflags(M, 0), mdesc((size_t)M * 32, 0);
+    for (int q = 0; q < M; ++q) {
+        MapPoint* p = vpMapPoints[q];
+        if (!p->mbTrackInView) continue;                       // :70-71
+        if (p->isBad()) { mflags[q] = 1 | 2; continue; }       // :73-74
+        mflags[q] = (uint8_t)(1 | (p->Observations() > 0 ? 4 : 0));
+        px[q] = p->mTrackProjX; py[q] = p->mTrackProjY; pxr[q] = p->mTrackProjXR;
+        vc[q] = p->mTrackViewCos; lvl[q] = p->mnTrackScaleLevel;
+        const cv::Mat d = p->GetDescriptor();                  // :93
+        std::memcpy(&mdesc[(size_t)q * 32], d.ptr(0), 32);
+    }
+    orbgpu_mappoint_set ms;
+    ms.mp_off = mp_off; ms.proj_x = px.data(); ms.proj_y = py.data(); ms.proj_xr = pxr.data(); ms.view_cos = vc.data();
+    ms.level = lvl.data(); ms.flags = mflags.data(); ms.desc = mdesc.data();
+
+    std::vector<int32_t> kp_match(N, -1);
+    int32_t nmatches = 0;
+    check(orbgpu_search_by_projection(matcher(), &fs, &ms, F.mvScaleFactors.data(), (int)F.mvScaleFactors.size(), th, mfNNratio,
+                                      kp_match.data(), nullptr, nullptr, nullptr, &nmatches),
+          "SearchByProjection");
+    for (int i = 0; i < N; ++i)
+        if (kp_match[i] >= 0) F.mvpMapPoints[i] = vpMapPoints[kp_match[i]];   // :149
+    return nmatches;
+}
+
+int ORBmatcher::SearchByBoW(KeyFrame* pKF, Frame& F, std::vector<MapPoint*>& vpMapPointMatches) {
+    const std::vector<MapPoint*> vpMapPointsKF = pKF->GetMapPointMatches();
+    vpMapPointMatches = std::vector<MapPoint*>(F.N, static_cast<MapPoint*>(NULL));
+    const int N1 = (int)pKF->mvKeysUn.size(), N2 = (int)F.mvKeys.size();
+    if (N1 == 0 || N2 == 0) return 0;
+    const int32_t off1[2] = {0, N1}, off2[2] = {0, N2};
+    std::vector<uint8_t> t1, t2, flags1(N1, 0);
+    for (int i = 0; i < N1; ++i) flags1[i] = (vpMapPointsKF[i] && !vpMapPointsKF[i]->isBad()) ? 1 : 0;   // :233-238
+    orbgpu_frame_set s1 = one_frame(off1, pKF->mvKeysUn, rows32(pKF->mDescriptors, t1));
+    orbgpu_frame_set s2 = one_frame(off2, F.mvKeys, rows32(F.mDescriptors, t2));   // the rotation check reads F.mvKeys (:294)
+    s1.kp_flags = flags1.data();
+    const FlatFeatVec fv1(pKF->mFeatVec), fv2(F.mFeatVec);
+    fv1.attach(s1);
+    fv2.attach(s2);
+    std::vector<int32_t> match12(N1, -1);
+    int32_t nmatches = 0;
+    check(orbgpu_search_by_bow(matcher(), &s1, &s2, 1, &kZero, &kZero, mfNNratio, mbCheckOrientation ? 1 : 0, TH_LOW, /*<=*/1,
+                               /*require_mp2*/ 0, &kZero64, match12.data(), nullptr, &nmatches),
+          "SearchByBoW(KeyFrame, Frame)");
+    for (int i = 0; i < N1; ++i)
+        if (match12[i] >= 0) vpMapPointMatches[match12[i]] = vpMapPointsKF[i];   // :288
+    return nmatches;
+}
+
+int ORBmatcher::SearchByBoW(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint*>& vpMatches12) {
+    const std::vector<MapPoint*> vpMapPoints1 = pKF1->GetMapPointMatches();
+    const std::vector<MapPoint*> vpMapPoints2 = pKF2->GetMapPointMatches();
+    vpMatches12 = std::vector<MapPoint*>(vpMapPoints1.size(), static_cast<MapPoint*>(NULL));
+    const int N1 = (int)pKF1->mvKeysUn.size(), N2 = (int)pKF2->mvKeysUn.size();
+    if (N1 == 0 || N2 == 0) return 0;
+    const int32_t off1[2] = {0, N1}, off2[2] = {0, N2};
+    std::vector<uint8_t> t1, t2, flags1(N1, 0), flags2(N2, 0);
+    for (int i = 0; i < N1; ++i) flags1[i] = (vpMapPoints1[i] && !vpMapPoints1[i]->isBad()) ? 1 : 0;   // :673-677
+    for (int i = 0; i < N2; ++i) flags2[i] = (vpMapPoints2[i] && !vpMapPoints2[i]->isBad()) ? 1 : 0;   // :688-694
+    orbgpu_frame_set s1 = one_frame(off1, pKF1->mvKeysUn, rows32(pKF1->mDescriptors, t1));
+    orbgpu_frame_set s2 = one_frame(off2, pKF2->mvKeysUn, rows32(pKF2->mDescriptors, t2));
+    s1.kp_flags = flags1.data();
+    s2.kp_flags = flags2.data();
+    const FlatFeatVec fv1(pKF1->mFeatVec), fv2(pKF2->mFeatVec);
+    fv1.attach(s1);
+    fv2.attach(s2);
+    std::vector<int32_t> match12(N1, -1);
+    int32_t nmatches = 0;
+    check(orbgpu_search_by_bow(matcher(), &s1, &s2, 1, &kZero, &kZero, mfNNratio, mbCheckOrientation ? 1 : 0, TH_LOW, /*<*/0,
+                               /*require_mp2*/ 1, &kZero64, match12.data(), nullptr, &nmatches),
+          "SearchByBoW(KeyFrame, KeyFrame)");
+    for (int i = 0; i < N1; ++i)
+        if (match12[i] >= 0) vpMatches12[i] = vpMapPoints2[match12[i]];   // :715
+    return nmatches;
+}
+
+int ORBmatcher::SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, cv::Mat F12,
+                                       std::vector<std::pair<size_t, size_t> >& vMatchedPairs, const bool bOnlyStereo) {
+    vMatchedPairs.clear();
+    const int N1 = (int)pKF1->mvKeysUn.size(), N2 = (int)pKF2->mvKeysUn.size();
+    if (N1 == 0 || N2 == 0) return 0;
+    // epipole of camera 1 in image 2 (:790-799): C2 = R2w * Cw + t2w, accumulated in double like cv::gemm's small-matrix path
+    const cv::Mat Cw = pKF1->GetCameraCenter(), R2w = pKF2->GetRotation(), t2w = pKF2->GetTranslation();
+    float C2[3];
+    for (int i = 0; i < 3; ++i) {
+        double acc = 0.0;
+        for (int j = 0; j < 3; ++j) acc += (double)R2w.at<float>(i, j) * (double)Cw.at<float>(j, 0);
+        C2[i] = (float)(acc + (double)t2w.at<float>(i, 0));
+    }
+    const float invz = 1.0f / C2[2];
+    const float epipole[2] = {pKF2->fx * C2[0] * invz + pKF2->cx, pKF2->fy * C2[1] * invz + pKF2->cy};
+    float f12[9];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) f12[3 * i + j] = F12.at<float>(i, j);
+
+    const int32_t off1[2] = {0, N1}, off2[2] = {0, N2};
+    std::vector<uint8_t> t1, t2, flags1(N1, 0), flags2(N2, 0);
+    for (int i = 0; i < N1; ++i) flags1[i] = pKF1->GetMapPoint(i) ? 1 : 0;   // :846
+    for (int i = 0; i < N2; ++i) flags2[i] = pKF2->GetMapPoint(i) ? 1 : 0;   // :868
+    orbgpu_frame_set s1 = one_frame(off1, pKF1->mvKeysUn, rows32(pKF1->mDescriptors, t1));
+    orbgpu_frame_set s2 = one_frame(off2, pKF2->mvKeysUn, rows32(pKF2->mDescriptors, t2));
+    s1.kp_flags = flags1.data();
+    s2.kp_flags = flags2.data();
+    s1.u_right = pKF1->mvuRight.empty() ? nullptr : pKF1->mvuRight.data();
+    s2.u_right = pKF2->mvuRight.empty() ? nullptr : pKF2->mvuRight.data();
+    const FlatFeatVec fv1(pKF1->mFeatVec), fv2(pKF2->mFeatVec);
+    fv1.attach(s1);
+    fv2.attach(s2);
+    std::vector<int32_t> match12(N1, -1);
+    int32_t nmatches = 0;
+    check(orbgpu_search_for_triangulation(matcher(), &s1, &s2, 1, &kZero, &kZero, f12, epipole, pKF2->mvScaleFactors.data(),
+                                          pKF2->mvLevelSigma2.data(), (int)pKF2->mvScaleFactors.size(), bOnlyStereo ? 1 : 0,
+                                          mbCheckOrientation ? 1 : 0, &kZero64, match12.data(), nullptr, &nmatches),
+          "SearchForTriangulation");
+    vMatchedPairs.reserve(nmatches);
+    for (int i = 0; i < N1; ++i)
+        if (match12[i] >= 0) vMatchedPairs.push_back(std::make_pair((size_t)i, (size_t)match12[i]));   // :964-972
+    return nmatches;
+}
+
+#ifdef ORBGPU_SHELL_STANDALONE
+// Builds without the reference's ORBmatcher.cc (tests): the members that file would provide.
+const int ORBmatcher::TH_HIGH = ORBGPU_TH_HIGH;
+const int ORBmatcher::TH_LOW = ORBGPU_TH_LOW;
+const int ORBmatcher::HISTO_LENGTH = ORBGPU_HISTO_LENGTH;
+ORBmatcher::ORBmatcher(float nnratio, bool checkOri) : mfNNratio(nnratio), mbCheckOrientation(checkOri) {}
+#endif
+
+}  // namespace ORB_SLAM2

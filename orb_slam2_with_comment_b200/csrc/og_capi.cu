@@ -124,6 +124,43 @@ size_t octree_ws_bytes(int cap, int node_cap) {
     return b;
 }
 
+// The constructor's tables (ORBextractor.cc:413-469), pure host arithmetic in the reference's own types: the float
+// scale argument lives in a double member (ORBextractor.h:98), every table entry is a float.
+void compute_tables(int nfeatures, float scale_factor_f, int nlevels, std::vector<float>& scale, std::vector<float>& inv_scale,
+                    std::vector<float>& sigma2, std::vector<float>& inv_sigma2, std::vector<int>& quota, std::vector<int>& umax) {
+    const double scale_factor = scale_factor_f;
+    scale.resize(nlevels); sigma2.resize(nlevels); inv_scale.resize(nlevels); inv_sigma2.resize(nlevels);
+    scale[0] = 1.0f; sigma2[0] = 1.0f;
+    for (int i = 1; i < nlevels; i++) {
+        scale[i] = (float)(scale[i - 1] * scale_factor);
+        sigma2[i] = scale[i] * scale[i];
+    }
+    for (int i = 0; i < nlevels; i++) { inv_scale[i] = 1.0f / scale[i]; inv_sigma2[i] = 1.0f / sigma2[i]; }
+    // :435-446
+    quota.resize(nlevels);
+    float factor = (float)(1.0f / scale_factor);
+    float nDesired = nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)nlevels));
+    int sum = 0;
+    for (int l = 0; l < nlevels - 1; l++) {
+        quota[l] = cv_round_f(nDesired);
+        sum += quota[l];
+        nDesired *= factor;
+    }
+    quota[nlevels - 1] = std::max(nfeatures - sum, 0);
+    // :454-469
+    umax.assign(16, 0);
+    const int HP = og::kHalfPatch;
+    int v, v0, vmax = (int)floor(HP * sqrt(2.f) / 2 + 1);
+    int vmin = (int)ceil(HP * sqrt(2.f) / 2);
+    const double hp2 = HP * HP;
+    for (v = 0; v <= vmax; ++v) umax[v] = cv_round_d(sqrt(hp2 - v * v));
+    for (v = HP, v0 = 0; v >= vmin; --v) {
+        while (umax[v0] == umax[v0 + 1]) ++v0;
+        umax[v] = v0;
+        ++v0;
+    }
+}
+
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda).
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -467,39 +504,7 @@ int orbgpu_extractor_create(orbgpu_extractor** out, int device, int nfeatures, f
     ex->max_w = max_width;
     ex->max_h = max_height;
     ex->max_batch = max_batch;
-    // ORBextractor.cc:413-431
-    ex->scale.resize(nlevels); ex->sigma2.resize(nlevels); ex->inv_scale.resize(nlevels); ex->inv_sigma2.resize(nlevels);
-    ex->scale[0] = 1.0f; ex->sigma2[0] = 1.0f;
-    for (int i = 1; i < nlevels; i++) {
-        ex->scale[i] = (float)(ex->scale[i - 1] * ex->scale_factor);
-        ex->sigma2[i] = ex->scale[i] * ex->scale[i];
-    }
-    for (int i = 0; i < nlevels; i++) { ex->inv_scale[i] = 1.0f / ex->scale[i]; ex->inv_sigma2[i] = 1.0f / ex->sigma2[i]; }
-    // :435-446
-    ex->quota.resize(nlevels);
-    float factor = (float)(1.0f / ex->scale_factor);
-    float nDesired = nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)nlevels));
-    int sum = 0;
-    for (int l = 0; l < nlevels - 1; l++) {
-        ex->quota[l] = cv_round_f(nDesired);
-        sum += ex->quota[l];
-        nDesired *= factor;
-    }
-    ex->quota[nlevels - 1] = std::max(nfeatures - sum, 0);
-    // :454-469
-    ex->umax.assign(16, 0);
-    {
-        const int HP = og::kHalfPatch;
-        int v, v0, vmax = (int)floor(HP * sqrt(2.f) / 2 + 1);
-        int vmin = (int)ceil(HP * sqrt(2.f) / 2);
-        const double hp2 = HP * HP;
-        for (v = 0; v <= vmax; ++v) ex->umax[v] = cv_round_d(sqrt(hp2 - v * v));
-        for (v = HP, v0 = 0; v >= vmin; --v) {
-            while (ex->umax[v0] == ex->umax[v0 + 1]) ++v0;
-            ex->umax[v] = v0;
-            ++v0;
-        }
-    }
+    compute_tables(nfeatures, scale_factor, nlevels, ex->scale, ex->inv_scale, ex->sigma2, ex->inv_sigma2, ex->quota, ex->umax);
 
     Geometry G;
     std::string err = build_geometry(*ex, max_width, max_height, max_batch, G);
@@ -572,6 +577,19 @@ int orbgpu_extractor_tables(const orbgpu_extractor* ex, float* scales, int32_t* 
 }
 
 int orbgpu_extractor_max_keypoints(const orbgpu_extractor* ex) { return ex ? ex->kp_cap : 0; }
+
+int orbgpu_extractor_static_tables(int nfeatures, float scale_factor, int nlevels, float* scales, int32_t* features_per_level, int32_t* umax) {
+    if (nfeatures < 1 || nlevels < 1 || nlevels > og::kMaxLevels || !(scale_factor > 1.f)) return fail(ORBGPU_ERR_ARG, "bad extractor parameters");
+    std::vector<float> sc, isc, s2, is2;
+    std::vector<int> q, um;
+    compute_tables(nfeatures, scale_factor, nlevels, sc, isc, s2, is2, q, um);
+    for (int i = 0; i < nlevels; ++i) {
+        if (scales) { scales[i] = sc[i]; scales[nlevels + i] = isc[i]; scales[2 * nlevels + i] = s2[i]; scales[3 * nlevels + i] = is2[i]; }
+        if (features_per_level) features_per_level[i] = q[i];
+    }
+    if (umax) for (int i = 0; i < 16; ++i) umax[i] = um[i];
+    return ORBGPU_OK;
+}
 
 int orbgpu_extract_batch_dev(orbgpu_extractor* ex, const uint8_t* images_dev, int batch, int width, int height,
                              size_t row_stride, size_t frame_stride, orbgpu_keypoint* kp_out_dev, uint8_t* desc_out_dev,

@@ -1,0 +1,83 @@
+// Stand-ins for the ORB-SLAM2 classes the matcher shell (csrc/host/ORBmatcher_gpu.cc) reads, declaring ONLY the members
+// the four GPU-backed search functions touch, with the reference's names and types
+// (/root/reference/include/Frame.h:113-188, KeyFrame.h:52-184, MapPoint.h:52-97, Thirdparty/DBoW2/DBoW2/FeatureVector.h:21).
+// They exist so the shell can be compiled and exercised where neither OpenCV nor the reference's sources are
+// available; in a real build the reference's own headers come first on the include path and these are never seen.
+#ifndef ORBGPU_STUB_FRAME_H
+#define ORBGPU_STUB_FRAME_H
+
+#include <map>
+#include <set>
+#include <vector>
+
+#include <opencv2/core/core.hpp>
+
+namespace DBoW2 {
+typedef unsigned int NodeId;
+class FeatureVector : public std::map<NodeId, std::vector<unsigned int> > {};
+}  // namespace DBoW2
+
+namespace ORB_SLAM2 {
+
+class KeyFrame;
+
+class MapPoint {
+public:
+    MapPoint() : mTrackProjX(0), mTrackProjY(0), mTrackProjXR(0), mbTrackInView(false), mnTrackScaleLevel(0), mTrackViewCos(0),
+                 mbBad(false), nObs(0) {}
+    int Observations() { return nObs; }
+    bool isBad() { return mbBad; }
+    cv::Mat GetDescriptor() { return mDescriptor.clone(); }
+
+    float mTrackProjX, mTrackProjY, mTrackProjXR;
+    bool mbTrackInView;
+    int mnTrackScaleLevel;
+    float mTrackViewCos;
+
+    // stub state
+    bool mbBad;
+    int nObs;
+    cv::Mat mDescriptor;
+};
+
+class Frame {
+public:
+    int N;
+    std::vector<cv::KeyPoint> mvKeys, mvKeysUn;
+    std::vector<float> mvuRight;
+    DBoW2::FeatureVector mFeatVec;
+    cv::Mat mDescriptors;
+    std::vector<MapPoint*> mvpMapPoints;
+    std::vector<float> mvScaleFactors;
+    static float mfGridElementWidthInv, mfGridElementHeightInv;
+    static float mnMinX, mnMaxX, mnMinY, mnMaxY;
+};
+
+class KeyFrame {
+public:
+    KeyFrame(const std::vector<cv::KeyPoint>& keys, const std::vector<float>& uright, const cv::Mat& desc,
+             const std::vector<float>& sf, const std::vector<float>& s2, float _fx, float _fy, float _cx, float _cy)
+        : fx(_fx), fy(_fy), cx(_cx), cy(_cy), N((int)keys.size()), mvKeysUn(keys), mvuRight(uright), mDescriptors(desc),
+          mvScaleFactors(sf), mvLevelSigma2(s2), mvpMapPoints(keys.size(), (MapPoint*)0) {}
+    cv::Mat GetCameraCenter() { return Ow.clone(); }
+    cv::Mat GetRotation() { return Rcw.clone(); }
+    cv::Mat GetTranslation() { return tcw.clone(); }
+    std::vector<MapPoint*> GetMapPointMatches() { return mvpMapPoints; }
+    MapPoint* GetMapPoint(const size_t& idx) { return mvpMapPoints[idx]; }
+
+    const float fx, fy, cx, cy;
+    const int N;
+    const std::vector<cv::KeyPoint> mvKeysUn;
+    const std::vector<float> mvuRight;
+    const cv::Mat mDescriptors;
+    DBoW2::FeatureVector mFeatVec;
+    const std::vector<float> mvScaleFactors;
+    const std::vector<float> mvLevelSigma2;
+
+    // stub state
+    std::vector<MapPoint*> mvpMapPoints;
+    cv::Mat Ow, Rcw, tcw;   // 3x1, 3x3, 3x1 CV_32F
+};
+
+}  // namespace ORB_SLAM2
+#endif

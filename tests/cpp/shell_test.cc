@@ -1,0 +1,302 @@
+// shell_test.cc — exercises the C++ drop-in shells (csrc/host) the way the reference's callers do, and checks every
+// result against the CPU oracle (oracle/_build/liborboracle.so).  TEST INFRASTRUCTURE.
+//   exit 0: all comparisons passed on the GPU        exit 3: no CUDA device, the shells failed loudly (no CPU fallback)
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+#include <vector>
+
+#include "ORBextractor.h"
+#include "ORBmatcher.h"
+#include "orbgpu.h"
+
+using namespace ORB_SLAM2;
+
+// ---- oracle entry points (oracle/orb_oracle.cc, oracle/match_oracle.cc) ----
+extern "C" {
+void* orbo_create(int, float, int, int, int);
+void orbo_destroy(void*);
+int orbo_extract(void*, const uint8_t*, int, int, int, void*, int, uint8_t*);
+int orbo_get_level(void*, int, int, uint8_t*);
+void orbm_search_by_projection(const orbgpu_frame_set*, const orbgpu_mappoint_set*, const float*, int, float, float, int32_t*, int32_t*,
+                               int32_t*, int32_t*, int32_t*);
+void orbm_search_for_triangulation(const orbgpu_frame_set*, const orbgpu_frame_set*, int, const int32_t*, const int32_t*, const float*,
+                                   const float*, const float*, const float*, int, int, int, const int64_t*, int32_t*, int32_t*, int32_t*);
+void orbm_search_by_bow(const orbgpu_frame_set*, const orbgpu_frame_set*, int, const int32_t*, const int32_t*, float, int, int, int, int,
+                        const int64_t*, int32_t*, int32_t*, int32_t*);
+}
+
+float Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv, Frame::mnMinX, Frame::mnMaxX, Frame::mnMinY, Frame::mnMaxY;
+
+static uint32_t g_seed = 12345;
+static uint32_t rnd() { g_seed = g_seed * 1664525u + 1013904223u; return g_seed >> 8; }
+static float frand(float a, float b) { return a + (b - a) * (rnd() % 100000) / 100000.0f; }
+
+static int fails = 0;
+#define EXPECT(c, ...) do { if (!(c)) { ++fails; printf("FAIL %s:%d: ", __FILE__, __LINE__); printf(__VA_ARGS__); printf("\n"); } } while (0)
+
+static cv::Mat synth_image(int w, int h) {
+    cv::Mat im(h, w, CV_8UC1);
+    for (int y = 0; y < h; ++y) for (int x = 0; x < w; ++x) im.at<uchar>(y, x) = 128;
+    for (int k = 0; k < w * h / 700; ++k) {
+        const int x0 = rnd() % w, y0 = rnd() % h, rw = 4 + rnd() % 50, rh = 4 + rnd() % 50, g = rnd() % 256;
+        for (int y = y0; y < y0 + rh && y < h; ++y) for (int x = x0; x < x0 + rw && x < w; ++x) im.at<uchar>(y, x) = (uchar)g;
+    }
+    for (int y = 0; y < h; ++y) for (int x = 0; x < w; ++x) {
+        int v = im.at<uchar>(y, x) + (int)(rnd() % 7) - 3;
+        im.at<uchar>(y, x) = (uchar)(v < 0 ? 0 : v > 255 ? 255 : v);
+    }
+    return im;
+}
+
+// what Frame::ExtractORB does (Frame.cc:249-255)
+struct MiniFrame {
+    std::vector<cv::KeyPoint> mvKeys;
+    cv::Mat mDescriptors;
+    void ExtractORB(ORBextractor* ex, const cv::Mat& im) { (*ex)(im, cv::Mat(), mvKeys, mDescriptors); }
+};
+
+static void test_extractor() {
+    const int W = 752, H = 480;
+    ORBextractor ex(1200, 1.2f, 8, 20, 7);   // Tracking.cc:120-126 style construction
+    EXPECT(ex.GetLevels() == 8 && std::fabs(ex.GetScaleFactor() - 1.2f) < 1e-6f, "getters");
+    EXPECT(ex.GetScaleFactors().size() == 8 && ex.GetInverseScaleSigmaSquares().size() == 8, "tables");
+    void* o = orbo_create(1200, 1.2f, 8, 20, 7);
+    for (int it = 0; it < 3; ++it) {
+        cv::Mat im = synth_image(W, H);
+        MiniFrame f;
+        f.ExtractORB(&ex, im);
+        std::vector<cv::KeyPoint> ok(1200 + 100);
+        std::vector<uint8_t> od(ok.size() * 32);
+        const int n = orbo_extract(o, im.ptr(0), W, H, (int)im.step, ok.data(), (int)ok.size(), od.data());
+        EXPECT(n == (int)f.mvKeys.size() && f.mDescriptors.rows == n, "keypoint count %d vs oracle %d", (int)f.mvKeys.size(), n);
+        int bad_desc = 0;
+        for (int i = 0; i < n && i < (int)f.mvKeys.size(); ++i) {
+            const cv::KeyPoint &a = f.mvKeys[i], &b = ok[i];
+            EXPECT(a.pt.x == b.pt.x && a.pt.y == b.pt.y && a.octave == b.octave && a.response == b.response && a.size == b.size &&
+                   a.class_id == b.class_id && std::fabs(a.angle - b.angle) <= 1e-3f, "keypoint %d differs", i);
+            bad_desc += std::memcmp(f.mDescriptors.ptr(i), &od[(size_t)i * 32], 32) != 0;
+        }
+        EXPECT(bad_desc <= 1, "%d descriptor rows differ", bad_desc);
+        // mvImagePyramid: interior views of bordered buffers, as ComputePyramid leaves them
+        for (int l = 0; l < 8; ++l) {
+            const cv::Mat& lv = ex.mvImagePyramid[l];
+            std::vector<uint8_t> ol((size_t)lv.rows * lv.cols);
+            orbo_get_level(o, l, 0, ol.data());
+            int diff = 0;
+            for (int y = 0; y < lv.rows; ++y) diff += std::memcmp(lv.ptr(y), &ol[(size_t)y * lv.cols], lv.cols) != 0;
+            EXPECT(diff == 0, "pyramid level %d: %d rows differ", l, diff);
+        }
+    }
+    // empty image: silent return, outputs untouched (reference :1046-1047)
+    MiniFrame e;
+    e.mvKeys.resize(3);
+    e.ExtractORB(&ex, cv::Mat());
+    EXPECT(e.mvKeys.size() == 3, "empty image must leave the outputs alone");
+    orbo_destroy(o);
+}
+
+// ---- matcher fixtures ----
+static std::vector<float> g_sf, g_s2;
+static cv::Mat random_desc(int n) {
+    cv::Mat d(n, 32, CV_8UC1);
+    for (int i = 0; i < n; ++i) for (int b = 0; b < 32; ++b) d.at<uchar>(i, b) = (uchar)(rnd() & 255);
+    return d;
+}
+static void flip(uchar* row, int nbits) { for (int k = 0; k < nbits; ++k) { int b = rnd() % 256; row[b >> 3] ^= (uchar)(1 << (b & 7)); } }
+static std::vector<cv::KeyPoint> random_keys(int n, int W, int H) {
+    std::vector<cv::KeyPoint> k(n);
+    for (int i = 0; i < n; ++i) {
+        const int o = rnd() % 8;
+        k[i] = cv::KeyPoint(std::floor(frand(20, W / g_sf[o] - 20)) * g_sf[o], std::floor(frand(20, H / g_sf[o] - 20)) * g_sf[o],
+                            31 * g_sf[o], frand(0, 360), (float)(rnd() % 100), o, -1);
+    }
+    return k;
+}
+struct Flat {   // independent flattening for the oracle
+    int32_t kp_off[2], node_off[2];
+    std::vector<int32_t> node_id, feat_off, feat;
+    std::vector<uint8_t> desc, flags;
+    orbgpu_frame_set s;
+    Flat(const std::vector<cv::KeyPoint>& keys, const cv::Mat& d, const DBoW2::FeatureVector* fv) {
+        std::memset(&s, 0, sizeof(s));
+        kp_off[0] = 0; kp_off[1] = (int)keys.size();
+        s.n_frames = 1; s.kp_off = kp_off; s.keys_un = (const orbgpu_keypoint*)keys.data();
+        desc.resize(keys.size() * 32);
+        for (size_t i = 0; i < keys.size(); ++i) std::memcpy(&desc[i * 32], d.ptr((int)i), 32);
+        s.desc = desc.data();
+        flags.assign(keys.size(), 0);
+        s.kp_flags = flags.data();
+        if (fv) {
+            node_off[0] = 0; feat_off.push_back(0);
+            for (auto& kv : *fv) { node_id.push_back((int)kv.first); for (unsigned v : kv.second) feat.push_back((int)v); feat_off.push_back((int)feat.size()); }
+            node_off[1] = (int)node_id.size();
+            s.fv_node_off = node_off; s.fv_node_id = node_id.data(); s.fv_feat_off = feat_off.data(); s.fv_feat = feat.data();
+        }
+    }
+};
+
+static void test_matcher() {
+    const int W = 640, H = 480, N = 900;
+    g_sf.assign(8, 1.f); g_s2.assign(8, 1.f);
+    for (int i = 1; i < 8; ++i) { g_sf[i] = (float)(g_sf[i - 1] * (double)1.2f); g_s2[i] = g_sf[i] * g_sf[i]; }
+    Frame::mnMinX = 0; Frame::mnMinY = 0; Frame::mnMaxX = W; Frame::mnMaxY = H;
+    Frame::mfGridElementWidthInv = 64.0f / W; Frame::mfGridElementHeightInv = 48.0f / H;
+
+    // two key frames; the second re-observes ~60 % of the first
+    std::vector<cv::KeyPoint> k1 = random_keys(N, W, H), k2 = random_keys(N, W, H);
+    cv::Mat d1 = random_desc(N), d2 = random_desc(N);
+    DBoW2::FeatureVector fv1, fv2;
+    std::vector<int> node1(N), node2(N);
+    for (int i = 0; i < N; ++i) node1[i] = rnd() % 40, node2[i] = rnd() % 40;
+    for (int j = 0; j < N; ++j)
+        if (rnd() % 10 < 6) {
+            const int i = rnd() % N;
+            std::memcpy(d2.ptr(j), d1.ptr(i), 32);
+            flip(d2.ptr(j), 12);
+            k2[j] = k1[i];
+            k2[j].pt.x += frand(-1.5f, 1.5f);
+            k2[j].angle = std::fmod(k1[i].angle + frand(-10, 10) + 360.f, 360.f);
+            node2[j] = node1[i];
+        }
+    for (int i = 0; i < N; ++i) { fv1[node1[i]].push_back(i); fv2[node2[i]].push_back(i); }
+    std::vector<float> ur1(N, -1.f), ur2(N, -1.f);
+    for (int i = 0; i < N; ++i) { if (rnd() % 4 == 0) ur1[i] = k1[i].pt.x - 5; if (rnd() % 4 == 0) ur2[i] = k2[i].pt.x - 5; }
+    KeyFrame kf1(k1, ur1, d1, g_sf, g_s2, 517.3f, 516.5f, 318.6f, 255.3f), kf2(k2, ur2, d2, g_sf, g_s2, 517.3f, 516.5f, 318.6f, 255.3f);
+    kf1.mFeatVec = fv1; kf2.mFeatVec = fv2;
+    std::vector<MapPoint> pool(2 * N);
+    for (int i = 0; i < N; ++i) {
+        if (rnd() % 10 < 7) { kf1.mvpMapPoints[i] = &pool[i]; pool[i].mbBad = rnd() % 20 == 0; pool[i].nObs = 1 + rnd() % 3; }
+        if (rnd() % 10 < 7) { kf2.mvpMapPoints[i] = &pool[N + i]; pool[N + i].mbBad = rnd() % 20 == 0; pool[N + i].nObs = 1; }
+    }
+
+    // --- SearchByBoW(KF, KF) ---
+    {
+        ORBmatcher m(0.8f, true);
+        std::vector<MapPoint*> got;
+        const int n = m.SearchByBoW(&kf1, &kf2, got);
+        Flat a(k1, d1, &fv1), b(k2, d2, &fv2);
+        for (int i = 0; i < N; ++i) { a.flags[i] = kf1.mvpMapPoints[i] && !kf1.mvpMapPoints[i]->mbBad; b.flags[i] = kf2.mvpMapPoints[i] && !kf2.mvpMapPoints[i]->mbBad; }
+        std::vector<int32_t> m12(N, -1); int32_t nm = 0; const int32_t z = 0; const int64_t z64 = 0;
+        orbm_search_by_bow(&a.s, &b.s, 1, &z, &z, 0.8f, 1, 50, 0, 1, &z64, m12.data(), nullptr, &nm);
+        EXPECT(n == nm && nm > 20, "SearchByBoW(KF,KF): %d matches vs oracle %d", n, nm);
+        for (int i = 0; i < N; ++i) EXPECT(got[i] == (m12[i] >= 0 ? kf2.mvpMapPoints[m12[i]] : nullptr), "SearchByBoW(KF,KF) entry %d", i);
+    }
+    // --- SearchByBoW(KF, Frame) ---
+    Frame F;
+    F.N = N; F.mvKeys = k2; F.mvKeysUn = k2; F.mvuRight = ur2; F.mFeatVec = fv2; F.mDescriptors = d2; F.mvScaleFactors = g_sf;
+    F.mvpMapPoints.assign(N, nullptr);
+    {
+        ORBmatcher m(0.7f, true);
+        std::vector<MapPoint*> got;
+        const int n = m.SearchByBoW(&kf1, F, got);
+        Flat a(k1, d1, &fv1), b(k2, d2, &fv2);
+        for (int i = 0; i < N; ++i) a.flags[i] = kf1.mvpMapPoints[i] && !kf1.mvpMapPoints[i]->mbBad;
+        std::vector<int32_t> m12(N, -1); int32_t nm = 0; const int32_t z = 0; const int64_t z64 = 0;
+        orbm_search_by_bow(&a.s, &b.s, 1, &z, &z, 0.7f, 1, 50, 1, 0, &z64, m12.data(), nullptr, &nm);
+        std::vector<MapPoint*> exp(N, nullptr);
+        for (int i = 0; i < N; ++i) if (m12[i] >= 0) exp[m12[i]] = kf1.mvpMapPoints[i];
+        EXPECT(n == nm && nm > 20, "SearchByBoW(KF,F): %d matches vs oracle %d", n, nm);
+        EXPECT(got == exp, "SearchByBoW(KF,F) vpMapPointMatches differ");
+    }
+    // --- SearchForTriangulation ---
+    {
+        kf1.Ow = cv::Mat(3, 1, CV_32FC1); kf2.Rcw = cv::Mat(3, 3, CV_32FC1); kf2.tcw = cv::Mat(3, 1, CV_32FC1);
+        const float ow[3] = {0.4f, 0.03f, 0.2f}, tc[3] = {-0.5f, 0.01f, 0.9f};
+        const float R[9] = {0.9998f, 0.f, 0.02f, 0.f, 1.f, 0.f, -0.02f, 0.f, 0.9998f};
+        for (int i = 0; i < 3; ++i) { kf1.Ow.at<float>(i, 0) = ow[i]; kf2.tcw.at<float>(i, 0) = tc[i]; for (int j = 0; j < 3; ++j) kf2.Rcw.at<float>(i, j) = R[3 * i + j]; }
+        cv::Mat F12(3, 3, CV_32FC1);
+        const float f[9] = {0.f, -1e-4f, 0.02f, 1e-4f, 0.f, -0.6f, -0.02f, 0.6f, 0.f};   // mostly horizontal epipolar lines
+        for (int i = 0; i < 9; ++i) F12.at<float>(i / 3, i % 3) = f[i];
+        for (int only = 0; only < 2; ++only) {
+            ORBmatcher m(0.6f, only == 0);
+            std::vector<std::pair<size_t, size_t> > pairs;
+            const int n = m.SearchForTriangulation(&kf1, &kf2, F12, pairs, only != 0);
+            Flat a(k1, d1, &fv1), b(k2, d2, &fv2);
+            for (int i = 0; i < N; ++i) { a.flags[i] = kf1.mvpMapPoints[i] != nullptr; b.flags[i] = kf2.mvpMapPoints[i] != nullptr; }
+            a.s.u_right = ur1.data(); b.s.u_right = ur2.data();
+            float C2[3];
+            for (int i = 0; i < 3; ++i) { double acc = 0; for (int j = 0; j < 3; ++j) acc += (double)R[3 * i + j] * ow[j]; C2[i] = (float)(acc + tc[i]); }
+            const float invz = 1.0f / C2[2];
+            const float ep[2] = {517.3f * C2[0] * invz + 318.6f, 516.5f * C2[1] * invz + 255.3f};
+            std::vector<int32_t> m12(N, -1); int32_t nm = 0; const int32_t z = 0; const int64_t z64 = 0;
+            orbm_search_for_triangulation(&a.s, &b.s, 1, &z, &z, f, ep, g_sf.data(), g_s2.data(), 8, only, only == 0, &z64, m12.data(), nullptr, &nm);
+            std::vector<std::pair<size_t, size_t> > exp;
+            for (int i = 0; i < N; ++i) if (m12[i] >= 0) exp.push_back(std::make_pair((size_t)i, (size_t)m12[i]));
+            EXPECT(n == nm && pairs == exp, "SearchForTriangulation(onlyStereo=%d): %d pairs vs oracle %d", only, n, nm);
+            if (!only) EXPECT(nm > 5, "SearchForTriangulation: degenerate fixture (%d)", nm);
+        }
+    }
+    // --- SearchByProjection(Frame, local map) ---
+    {
+        const int M = 3000;
+        std::vector<MapPoint> mps(M);
+        std::vector<MapPoint*> vp(M);
+        for (int q = 0; q < M; ++q) {
+            MapPoint& p = mps[q];
+            vp[q] = &p;
+            p.mDescriptor = cv::Mat(1, 32, CV_8UC1);
+            if (rnd() % 10 < 6) {
+                const int i = rnd() % N;
+                std::memcpy(p.mDescriptor.ptr(0), d2.ptr(i), 32);
+                flip(p.mDescriptor.ptr(0), 10);
+                p.mTrackProjX = k2[i].pt.x + frand(-2, 2); p.mTrackProjY = k2[i].pt.y + frand(-2, 2); p.mnTrackScaleLevel = k2[i].octave;
+            } else {
+                for (int b = 0; b < 32; ++b) p.mDescriptor.at<uchar>(0, b) = (uchar)(rnd() & 255);
+                p.mTrackProjX = frand(0, W); p.mTrackProjY = frand(0, H); p.mnTrackScaleLevel = rnd() % 8;
+            }
+            p.mTrackProjXR = p.mTrackProjX - 5; p.mTrackViewCos = rnd() % 2 ? 0.9999f : 0.99f;
+            p.mbTrackInView = rnd() % 20 != 0; p.mbBad = rnd() % 25 == 0; p.nObs = rnd() % 5 == 0 ? 0 : 2;
+        }
+        for (int i = 0; i < N; ++i) F.mvpMapPoints[i] = (rnd() % 10 == 0) ? &pool[i] : nullptr;   // some keypoints are taken already
+        for (int i = 0; i < N; ++i) if (rnd() % 7 == 0) pool[i].nObs = 0;
+        // oracle first (the shell mutates F.mvpMapPoints)
+        Flat a(k2, d2, nullptr);
+        for (int i = 0; i < N; ++i) a.flags[i] = F.mvpMapPoints[i] ? (F.mvpMapPoints[i]->nObs > 0 ? 1 : 2) : 0;
+        a.s.u_right = ur2.data();
+        const float grid[4] = {0, 0, Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv};
+        a.s.grid = grid;
+        int32_t mp_off[2] = {0, M};
+        std::vector<float> px(M), py(M), pxr(M), vc(M);
+        std::vector<int32_t> lv(M);
+        std::vector<uint8_t> fl(M), dd((size_t)M * 32);
+        for (int q = 0; q < M; ++q) {
+            px[q] = mps[q].mTrackProjX; py[q] = mps[q].mTrackProjY; pxr[q] = mps[q].mTrackProjXR; vc[q] = mps[q].mTrackViewCos;
+            lv[q] = mps[q].mnTrackScaleLevel;
+            fl[q] = (uint8_t)((mps[q].mbTrackInView ? 1 : 0) | (mps[q].mbBad ? 2 : 0) | (mps[q].nObs > 0 ? 4 : 0));
+            std::memcpy(&dd[(size_t)q * 32], mps[q].mDescriptor.ptr(0), 32);
+        }
+        orbgpu_mappoint_set ms = {mp_off, px.data(), py.data(), pxr.data(), vc.data(), lv.data(), fl.data(), dd.data()};
+        std::vector<int32_t> kpm(N, -1); int32_t nm = 0;
+        orbm_search_by_projection(&a.s, &ms, g_sf.data(), 8, 3.0f, 0.8f, kpm.data(), nullptr, nullptr, nullptr, &nm);
+        std::vector<MapPoint*> exp = F.mvpMapPoints;
+        for (int i = 0; i < N; ++i) if (kpm[i] >= 0) exp[i] = vp[kpm[i]];
+        ORBmatcher m(0.8f, true);
+        const int n = m.SearchByProjection(F, vp, 3.0f);
+        EXPECT(n == nm && nm > 50, "SearchByProjection: %d matches vs oracle %d", n, nm);
+        EXPECT(F.mvpMapPoints == exp, "SearchByProjection: F.mvpMapPoints differ");
+    }
+}
+
+int main() {
+    int ndev = 0;
+    if (orbgpu_device_count(&ndev) != 0 || ndev == 0) {
+        // no GPU: every shell must fail loudly, never fall back
+        int thrown = 0;
+        try { ORBextractor ex(1000, 1.2f, 8, 20, 7); MiniFrame f; f.ExtractORB(&ex, synth_image(640, 480)); } catch (const std::runtime_error& e) { ++thrown; printf("extractor: %s\n", e.what()); }
+        try {
+            g_sf.assign(8, 1.f); g_s2.assign(8, 1.f);
+            std::vector<cv::KeyPoint> k = random_keys(10, 640, 480);
+            cv::Mat d = random_desc(10);
+            KeyFrame a(k, std::vector<float>(10, -1.f), d, g_sf, g_s2, 1, 1, 0, 0), b(k, std::vector<float>(10, -1.f), d, g_sf, g_s2, 1, 1, 0, 0);
+            ORBmatcher m; std::vector<MapPoint*> out; m.SearchByBoW(&a, &b, out);
+        } catch (const std::runtime_error& e) { ++thrown; printf("matcher: %s\n", e.what()); }
+        return thrown == 2 ? 3 : 1;
+    }
+    test_extractor();
+    test_matcher();
+    printf(fails ? "shell_test: %d FAILURES\n" : "shell_test: all shell results equal the oracle (%d failures)\n", fails);
+    return fails ? 1 : 0;
+}
