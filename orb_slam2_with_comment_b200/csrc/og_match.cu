@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -45,10 +46,12 @@ struct BowArgs {
     const long long* entry_off;   // [n_pairs+1] scan entries (queries) before pair p
     const long long* match_off;   // [n_pairs]
     int require_mp2;
+    int dmax;                     // distances above it cannot change any accept decision (see bow_dev): phase A drops them
     int dense_q, dense_c;         // a node pair with n1 >= dense_q && n2 >= dense_c goes to the tiled kernel (dense_q<=0: never)
     uint32_t* topk;               // [total entries][kTopK]
     int4* items;                  // tiled-kernel work list
     int* n_items;
+    int* n_sparse;                // node pairs left to the warp kernel (null: unknown, scan everything)
     int items_cap;
     unsigned long long* evals;
 };
@@ -68,9 +71,14 @@ __global__ void k_bow_plan(const __grid_constant__ BowArgs A) {
     if (a >= c.a1) return;
     const int id = A.S1.node_id[a];
     const int j = lower_bound_i32(A.S2.node_id, c.b0, c.b1, id);
-    if (j >= c.b1 || A.S2.node_id[j] != id) return;
-    const int n1 = A.S1.feat_off[a + 1] - A.S1.feat_off[a], n2 = A.S2.feat_off[j + 1] - A.S2.feat_off[j];
-    if (!is_dense(A, n1, n2)) return;
+    const int n1 = A.S1.feat_off[a + 1] - A.S1.feat_off[a];
+    const bool matched = j < c.b1 && A.S2.node_id[j] == id;
+    const int n2 = matched ? A.S2.feat_off[j + 1] - A.S2.feat_off[j] : 0;
+    if (!matched || !is_dense(A, n1, n2)) {
+        // the warp kernel owns this node's queries (it also writes the empty lists of nodes frame 2 does not have)
+        if (n1 > 0) atomicAdd(A.n_sparse, 1);
+        return;
+    }
     const int QT = kTileThreads * RQ;
     const int nt = (n1 + QT - 1) / QT;
     const int base = atomicAdd(A.n_items, nt);
@@ -83,6 +91,7 @@ __global__ void __launch_bounds__(kTileThreads) k_bow_topk_tile(const __grid_con
     __shared__ int cpos[kTileChunk];
     __shared__ int s_nv, s_ne;
     const int tid = threadIdx.x;
+    const int dmax = A.dmax;
     const int n_items = min(*A.n_items, A.items_cap);
     for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
         const int4 it = A.items[w];
@@ -139,8 +148,11 @@ __global__ void __launch_bounds__(kTileThreads) k_bow_topk_tile(const __grid_con
                 d.hi = cd[2 * jj + 1];
 #pragma unroll
                 for (int r = 0; r < RQ; ++r) {
-                    const uint32_t key = ((uint32_t)hamming256(q[r], d) << kPosBits) | (uint32_t)pos;
-                    if (key < t[r][kTopK - 1]) topk_insert(t[r], key);
+                    const int dist = hamming256_csa(q[r], d);
+                    if (dist <= dmax) {
+                        const uint32_t key = ((uint32_t)dist << kPosBits) | (uint32_t)pos;
+                        if (key < t[r][kTopK - 1]) topk_insert(t[r], key);
+                    }
                 }
             }
         }
@@ -167,7 +179,7 @@ __global__ void __launch_bounds__(kTileThreads) k_bow_topk_tile(const __grid_con
 // One warp scans the candidates of node b for one query; `taken` (bitmask over frame fb's keypoints, may be null)
 // removes candidates already matched.  Returns the K smallest keys, identical in every lane.
 __device__ __forceinline__ int bow_scan_warp(const FrameSetView& S2, int kb, int b, const Desc& dq, int require_mp2,
-                                             const uint32_t* taken, uint32_t (&out)[kTopK]) {
+                                             const uint32_t* taken, int dmax, uint32_t (&out)[kTopK]) {
     const int lane = threadIdx.x & 31;
     const int b_off = S2.feat_off[b], n2 = S2.feat_off[b + 1] - b_off;
     uint32_t t[kTopK];
@@ -178,8 +190,10 @@ __device__ __forceinline__ int bow_scan_warp(const FrameSetView& S2, int kb, int
         const int i2 = S2.feat[b_off + j];
         if (require_mp2 && !(S2.flags && (S2.flags[kb + i2] & 1))) continue;
         if (taken && ((taken[i2 >> 5] >> (i2 & 31)) & 1u)) continue;
-        const uint32_t key = ((uint32_t)hamming256(dq, load_desc(S2.desc, kb + i2)) << kPosBits) | (uint32_t)j;
+        const int dist = hamming256(dq, load_desc(S2.desc, kb + i2));
         ++evals;
+        if (dist > dmax) continue;
+        const uint32_t key = ((uint32_t)dist << kPosBits) | (uint32_t)j;
         if (key < t[kTopK - 1]) topk_insert(t, key);
     }
     warp_topk_merge(t, out);
@@ -190,6 +204,7 @@ constexpr int kWarpsPerBlock = 8;
 
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_bow_topk_warp(const __grid_constant__ BowArgs A, long long total_entries) {
     __shared__ int s_evals;
+    if (A.n_sparse && *A.n_sparse == 0) return;   // every matched node pair went to the tiled kernel (which also wrote the empty lists)
     if (threadIdx.x == 0) s_evals = 0;
     __syncthreads();
     const long long g = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
@@ -206,7 +221,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_bow_topk_warp(const __g
             uint32_t out[kTopK] = {kEmptyKey, kEmptyKey, kEmptyKey, kEmptyKey};
             const int i1 = A.S1.feat[c.fbase + e];
             const bool ok = b >= 0 && A.S1.flags && (A.S1.flags[c.ka + i1] & 1);
-            if (ok) evals = bow_scan_warp(A.S2, c.kb, b, load_desc(A.S1.desc, c.ka + i1), A.require_mp2, nullptr, out);
+            if (ok) evals = bow_scan_warp(A.S2, c.kb, b, load_desc(A.S1.desc, c.ka + i1), A.require_mp2, nullptr, A.dmax, out);
             if ((threadIdx.x & 31) == 0) *reinterpret_cast<uint4*>(A.topk + g * kTopK) = make_uint4(out[0], out[1], out[2], out[3]);
         }
     }
@@ -249,6 +264,7 @@ __global__ void __launch_bounds__(32) k_bow_select(const __grid_constant__ BowAr
         const int e = base + lane;
         uint32_t k[kTopK] = {kEmptyKey, kEmptyKey, kEmptyKey, kEmptyKey};
         int c2[kTopK] = {-1, -1, -1, -1};
+        float ang2[kTopK] = {0.f, 0.f, 0.f, 0.f}, ang1 = 0.f;   // angles for the rotation histogram, fetched lane-parallel
         int i1 = -1, nb_node = -1;
         if (e < E) {
             const uint4 v = *reinterpret_cast<const uint4*>(A.topk + (g0 + e) * kTopK);
@@ -262,6 +278,12 @@ __global__ void __launch_bounds__(32) k_bow_select(const __grid_constant__ BowAr
 #pragma unroll
                 for (int j = 0; j < kTopK; ++j)
                     if (k[j] != kEmptyKey) c2[j] = A.S2.feat[b_off + (int)(k[j] & kPosMask)];
+                if (Z.check_orientation) {
+                    ang1 = A.S1.keys[c.ka + i1].angle;
+#pragma unroll
+                    for (int j = 0; j < kTopK; ++j)
+                        if (c2[j] >= 0) ang2[j] = A.S2.keys[c.kb + c2[j]].angle;
+                }
             }
         }
         unsigned act = __ballot_sync(0xffffffffu, i1 >= 0);
@@ -271,30 +293,35 @@ __global__ void __launch_bounds__(32) k_bow_select(const __grid_constant__ BowAr
             // everything below is warp-uniform
             uint32_t kk[kTopK];
             int cc[kTopK];
+            float aa[kTopK];
 #pragma unroll
             for (int j = 0; j < kTopK; ++j) {
                 kk[j] = __shfl_sync(0xffffffffu, k[j], l);
                 cc[j] = __shfl_sync(0xffffffffu, c2[j], l);
+                aa[j] = __shfl_sync(0xffffffffu, ang2[j], l);
             }
             const int qi1 = __shfl_sync(0xffffffffu, i1, l);
             const int qb = __shfl_sync(0xffffffffu, nb_node, l);
+            const float qa1 = __shfl_sync(0xffffffffu, ang1, l);
             int cnt = 0, best_c = -1, d1 = 256, d2 = 256;
-            bool complete = false;
+            float best_a = 0.f;
+            bool complete = false, rescanned = false;
 #pragma unroll
             for (int j = 0; j < kTopK; ++j) {
                 if (cnt == 2 || complete) break;
                 if (kk[j] == kEmptyKey) { complete = true; break; }
                 const int i2 = cc[j];
                 if ((taken[i2 >> 5] >> (i2 & 31)) & 1u) continue;
-                if (cnt == 0) { best_c = i2; d1 = (int)(kk[j] >> kPosBits); cnt = 1; }
+                if (cnt == 0) { best_c = i2; best_a = aa[j]; d1 = (int)(kk[j] >> kPosBits); cnt = 1; }
                 else { d2 = (int)(kk[j] >> kPosBits); cnt = 2; }
             }
             if (cnt == 2) complete = true;
             if (!complete && (cnt == 0 || pass_th(d1))) {
                 // the truncated list ran out: exact rescan of this query's node with the taken mask
                 uint32_t out[kTopK];
-                evals += bow_scan_warp(A.S2, c.kb, qb, load_desc(A.S1.desc, c.ka + qi1), A.require_mp2, taken, out);
+                evals += bow_scan_warp(A.S2, c.kb, qb, load_desc(A.S1.desc, c.ka + qi1), A.require_mp2, taken, 256, out);
                 best_c = -1; d1 = 256; d2 = 256;
+                rescanned = true;
                 if (out[0] != kEmptyKey) {
                     best_c = A.S2.feat[A.S2.feat_off[qb] + (int)(out[0] & kPosMask)];
                     d1 = (int)(out[0] >> kPosBits);
@@ -303,7 +330,7 @@ __global__ void __launch_bounds__(32) k_bow_select(const __grid_constant__ BowAr
             }
             if (best_c >= 0 && pass_th(d1) && (float)d1 < __fmul_rn(Z.nnratio, (float)d2)) {
                 int bin = 0;
-                if (Z.check_orientation) bin = rot_bin(A.S1.keys[c.ka + qi1].angle, A.S2.keys[c.kb + best_c].angle);
+                if (Z.check_orientation) bin = rot_bin(qa1, rescanned ? A.S2.keys[c.kb + best_c].angle : best_a);
                 if (lane == 0) {
                     taken[best_c >> 5] |= 1u << (best_c & 31);
                     Z.match12[mo + qi1] = best_c;
@@ -990,6 +1017,13 @@ int bow_dev(orbgpu_matcher* m, const orbgpu_frame_set_dev* s1, const orbgpu_fram
     A.entry_off = (const long long*)(dc + oe); A.match_off = (const long long*)(dc + om);
     A.require_mp2 = require_mp2;
     A.dense_q = m->dense_q; A.dense_c = m->dense_c;
+    // A best above th_low is rejected whatever follows, and a second best s > th_low / nnratio passes the ratio test
+    // (best < nnratio * s) for every admissible best, exactly like "no second best" (256): such candidates need not be
+    // listed.  +2 keeps the bound clear of float rounding in nnratio * s.
+    {
+        const double bound = nnratio > 0.f ? std::floor((double)th_low / (double)nnratio) + 2.0 : 256.0;
+        A.dmax = (int)std::min(256.0, std::max((double)th_low, bound));
+    }
     void* ptr = nullptr;
     OGM_CUDA(m->s_topk.grab((size_t)std::max<long long>(P.total_entries, 1) * kTopK * 4, &ptr));
     A.topk = (uint32_t*)ptr;
@@ -997,6 +1031,7 @@ int bow_dev(orbgpu_matcher* m, const orbgpu_frame_set_dev* s1, const orbgpu_fram
     A.items = (int4*)ptr;
     A.items_cap = (int)P.items_cap;
     A.n_items = m->d_nitems;
+    A.n_sparse = m->dense_q > 0 ? m->d_nitems + 1 : nullptr;
     A.evals = m->d_evals;
     SelectArgs Z;
     Z.nnratio = nnratio; Z.check_orientation = check_orientation; Z.th_low = th_low; Z.th_inclusive = th_inclusive;
@@ -1010,7 +1045,7 @@ int bow_dev(orbgpu_matcher* m, const orbgpu_frame_set_dev* s1, const orbgpu_fram
     cudaStream_t st = m->stream;
     OGM_CUDA(cudaEventRecord(m->ev0, st));
     OGM_CUDA(cudaMemsetAsync(m->d_evals, 0, 8, st));
-    OGM_CUDA(cudaMemsetAsync(m->d_nitems, 0, 4, st));
+    OGM_CUDA(cudaMemsetAsync(m->d_nitems, 0, 8, st));
     if (P.total_entries > 0) {
         if (m->dense_q > 0) {
             dim3 pg(n_pairs, (P.max_nodes1 + 127) / 128);
@@ -1160,7 +1195,7 @@ int orbgpu_matcher_create(orbgpu_matcher** out, int device) {
     if (ce == cudaSuccess) ce = cudaEventCreate(&m->ev1);
     if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&m->ev_stage, cudaEventDisableTiming);
     if (ce == cudaSuccess) ce = cudaMalloc((void**)&m->d_evals, 8);
-    if (ce == cudaSuccess) ce = cudaMalloc((void**)&m->d_nitems, 4);
+    if (ce == cudaSuccess) ce = cudaMalloc((void**)&m->d_nitems, 8);   // [0] tiled work items, [1] node pairs left to the warp kernel
     if (ce == cudaSuccess) ce = cudaMemset(m->d_evals, 0, 8);
     if (ce == cudaSuccess) ce = cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (ce != cudaSuccess) {

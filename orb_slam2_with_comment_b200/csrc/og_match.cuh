@@ -69,6 +69,29 @@ __device__ __forceinline__ int hamming256(const Desc& a, const Desc& b) {
            __popc(a.hi.x ^ b.hi.x) + __popc(a.hi.y ^ b.hi.y) + __popc(a.hi.z ^ b.hi.z) + __popc(a.hi.w ^ b.hi.w);
 }
 
+// The same distance with half the POPCs: POPC issues on the XU pipe at 16 lanes/clk/SM and binds the brute-force scan, the
+// LOP3 pipe has room.  Carry-save adders (sum = a^b^c, carry = maj(a,b,c), one LOP3 each) compress the eight XOR words
+// into one word of weight 1 twice (s2, x7), one of weight 2 (s3) and one of weight 4 (c3): 4 POPC + 16 LOP3 instead of 8 + 8.
+__device__ __forceinline__ uint32_t lop3_xor3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+__device__ __forceinline__ uint32_t lop3_maj(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+__device__ __forceinline__ int hamming256_csa(const Desc& a, const Desc& b) {
+    const uint32_t x0 = a.lo.x ^ b.lo.x, x1 = a.lo.y ^ b.lo.y, x2 = a.lo.z ^ b.lo.z, x3 = a.lo.w ^ b.lo.w;
+    const uint32_t x4 = a.hi.x ^ b.hi.x, x5 = a.hi.y ^ b.hi.y, x6 = a.hi.z ^ b.hi.z, x7 = a.hi.w ^ b.hi.w;
+    const uint32_t s0 = lop3_xor3(x0, x1, x2), c0 = lop3_maj(x0, x1, x2);
+    const uint32_t s1 = lop3_xor3(x3, x4, x5), c1 = lop3_maj(x3, x4, x5);
+    const uint32_t s2 = lop3_xor3(s0, s1, x6), c2 = lop3_maj(s0, s1, x6);
+    const uint32_t s3 = lop3_xor3(c0, c1, c2), c3 = lop3_maj(c0, c1, c2);
+    return __popc(s2) + __popc(x7) + 2 * __popc(s3) + 4 * __popc(c3);
+}
+
 // sorted insertion into t[0] <= t[1] <= t[2] <= t[3]; precondition key < t[3]
 __device__ __forceinline__ void topk_insert(uint32_t (&t)[kTopK], uint32_t key) {
     t[3] = key;
