@@ -58,6 +58,7 @@ struct orbgpu_extractor {
     og::Cell* d_cells = nullptr;
     og::Segment* d_segs = nullptr;
     og::BlurTile* d_btiles = nullptr;
+    uint32_t* d_ic_tab = nullptr;
     int n_btiles = 0;
     bool fast_v1 = false;             // ORBGPU_FAST_V1=1: first-generation per-cell kernel (kept for A/B timing)
     CUtensorMap* d_tmaps = nullptr;   // [2][kMaxLevels]: FAST tile boxes over pyr, then (reserved) over blur
@@ -380,6 +381,7 @@ int ensure_geometry(orbgpu_extractor* ex, int w, int h) {
     ex->P.pyr = ex->d_pyr;
     ex->P.blur = ex->d_blur;
     ex->P.cells = ex->d_cells;
+    ex->P.ic_tab = ex->d_ic_tab;
     ex->P.segs = ex->d_segs;
     ex->P.n_segs = (int)G.segs.size();
     ex->P.cell_count = ex->d_cell_count;
@@ -445,7 +447,7 @@ int launch_extract(orbgpu_extractor* ex, const uint8_t* d_images, int batch, siz
     og::k_blur_tma<<<dim3(ex->n_btiles, batch), og::kBlurThreads, 0, st>>>(P, ex->d_btiles, ex->d_tmaps);
     ++launches;
     mark(4);
-    og::k_orient_desc<<<dim3((ex->kp_cap + og::kDescWarps - 1) / og::kDescWarps, batch), og::kDescWarps * 32, 0, st>>>(
+    og::k_orient_desc<<<dim3((ex->kp_cap + og::kDescWarps * og::kDescPerWarp - 1) / (og::kDescWarps * og::kDescPerWarp), batch), og::kDescWarps * 32, 0, st>>>(
         P, d_kp, d_desc, d_counts);
     ++launches;
     mark(5);
@@ -540,6 +542,29 @@ int orbgpu_extractor_create(orbgpu_extractor** out, int device, int nfeatures, f
     alloc((void**)&ex->d_counts, B * 4);
     alloc((void**)&ex->d_kp, (size_t)ex->kp_cap * B * sizeof(og::KeyPoint));
     alloc((void**)&ex->d_desc, (size_t)ex->kp_cap * B * 32);
+    alloc((void**)&ex->d_ic_tab, 4 * og::kIcRows * og::kIcWords * 2 * sizeof(uint32_t));
+    if (ce == cudaSuccess) {
+        // IC_Angle weights: word j of disc row v (alignment A) covers columns u = -15 - A + 4j + k, k = 0..3; a column inside the
+        // disc (|u| <= umax[|v|], :85-99) weighs u for m_10 and v for m_01, everything else 0
+        std::vector<uint32_t> tab((size_t)4 * og::kIcRows * og::kIcWords * 2, 0u);
+        for (int A = 0; A < 4; ++A)
+            for (int r = 0; r < og::kIcRows; ++r)
+                for (int j = 0; j < og::kIcWords; ++j) {
+                    const int v = r - og::kHalfPatch;
+                    uint32_t wu = 0, wv = 0;
+                    for (int k = 0; k < 4; ++k) {
+                        const int u = -og::kHalfPatch - A + 4 * j + k;
+                        if (std::abs(u) <= ex->umax[std::abs(v)]) {
+                            wu |= (uint32_t)(uint8_t)(int8_t)u << (8 * k);
+                            wv |= (uint32_t)(uint8_t)(int8_t)v << (8 * k);
+                        }
+                    }
+                    const size_t o = (((size_t)A * og::kIcRows + r) * og::kIcWords + j) * 2;
+                    tab[o] = wu;
+                    tab[o + 1] = wv;
+                }
+        ce = cudaMemcpy(ex->d_ic_tab, tab.data(), tab.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
+    }
     if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&ex->stream, cudaStreamNonBlocking);
     if (ce != cudaSuccess) {
         std::string m = std::string("workspace allocation failed: ") + cudaGetErrorString(ce);
@@ -555,7 +580,7 @@ int orbgpu_extractor_destroy(orbgpu_extractor* ex) {
     cudaSetDevice(ex->device);
     if (ex->stream) { cudaStreamSynchronize(ex->stream); cudaStreamDestroy(ex->stream); }
     for (int i = 0; i < 6; ++i) if (ex->ev[i]) cudaEventDestroy(ex->ev[i]);
-    void* ptrs[] = {ex->d_btiles, ex->d_segs, ex->d_tmaps, ex->d_pyr, ex->d_blur, ex->d_images, ex->d_cells, ex->d_taps, ex->d_cell_count, ex->d_cand_xy,
+    void* ptrs[] = {ex->d_ic_tab, ex->d_btiles, ex->d_segs, ex->d_tmaps, ex->d_pyr, ex->d_blur, ex->d_images, ex->d_cells, ex->d_taps, ex->d_cell_count, ex->d_cand_xy,
                     ex->d_cand_resp, ex->d_ot, ex->d_sel_xy, ex->d_sel_resp, ex->d_sel_count, ex->d_counts, ex->d_kp, ex->d_desc};
     for (void* p : ptrs) if (p) cudaFree(p);
     delete ex;

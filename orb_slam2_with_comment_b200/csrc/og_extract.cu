@@ -652,93 +652,130 @@ __global__ void __launch_bounds__(kBlurThreads) k_blur_tma(const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Orientation + descriptor + final KeyPoint record: one warp per keypoint.
-//   IC_Angle (:77-104): integer moments over the radius-15 disc of the UN-blurred level, then fastAtan2.
-//   computeOrbDescriptor (:108-147): lane i produces descriptor byte i from pattern points 16i .. 16i+15 sampled
-//   on the BLURRED level.  cos/sin of the float angle are evaluated in double and rounded to float.
+// Orientation + descriptor + final KeyPoint record: one warp per keypoint, kDescPerWarp keypoints per warp.
+//   IC_Angle (:77-104): integer moments over the radius-15 disc of the UN-blurred level.  The disc rows are read as
+//   aligned 32-bit words (9 per row); a host-built table gives, per (alignment, row, word), the four signed column
+//   weights u (0 outside the disc) and the four row weights v, so one word contributes with two DP4A:
+//   m10 += dp4a(pixels, u weights), m01 += dp4a(pixels, v weights).  Then cv::fastAtan2's polynomial.
+//   computeOrbDescriptor (:108-147): the 37 x 37 neighbourhood of the BLURRED level is staged in shared memory with
+//   coalesced word loads; lane i produces descriptor byte i from pattern points 16i .. 16i+15.  cos/sin of the float
+//   angle are evaluated in double and rounded to float.
 // ------------------------------------------------------------------------------------------------------------
-constexpr int kDescWarps = 8;
+constexpr int kDescWarps = 8, kDescPerWarp = 4;
+constexpr int kIcWords = 9, kIcRows = 31;           // table [4 alignments][31 rows][9 words][2]
+constexpr int kPatchRows = 37, kPatchPitch = 40;    // 37 x 37 window + up to 3 bytes of alignment
 __constant__ int8_t c_pat_x[512] = {ORB_PATTERN_X_INIT};
 __constant__ int8_t c_pat_y[512] = {ORB_PATTERN_Y_INIT};
+
+__device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c) {   // unsigned bytes of a times signed bytes of b
+    int r;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
 
 __global__ void __launch_bounds__(kDescWarps * 32) k_orient_desc(const __grid_constant__ ExtractParams P, KeyPoint* __restrict__ kp_out,
                                                                  uint8_t* __restrict__ desc_out,
                                                                  int32_t* __restrict__ counts) {
     __shared__ int8_t spx[512], spy[512];
+    __shared__ __align__(16) uint8_t patch[kDescWarps][kPatchRows * kPatchPitch];
     for (int i = threadIdx.x; i < 512; i += blockDim.x) { spx[i] = c_pat_x[i]; spy[i] = c_pat_y[i]; }
     __syncthreads();
     const int frame = blockIdx.y;
-    const int lane = threadIdx.x & 31;
-    const int idx = blockIdx.x * kDescWarps + (threadIdx.x >> 5);   // index among the frame's keypoints
-    // locate (level, index in level): keypoints are concatenated in level order (:1076-1103)
+    const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+    // keypoints are concatenated in level order (:1076-1103): level starts from the per-level counts
     const int32_t* sc = P.sel_count + frame * P.n_levels;
-    int level = 0, off = 0, total = 0;
-    {
-        int acc = 0;
-        bool found = false;
-        for (int l = 0; l < P.n_levels; ++l) {
-            const int c = sc[l];
-            if (!found && idx < acc + c) { level = l; off = idx - acc; found = true; }
-            acc += c;
-        }
-        total = acc;
-        if (blockIdx.x == 0 && threadIdx.x == 0) counts[frame] = total < P.kp_cap ? total : P.kp_cap;
-        if (!found || idx >= P.kp_cap) return;
-    }
-    const Level& L = P.lv[level];
-    const uint32_t xy = P.sel_xy[(long long)frame * P.total_sel_cap + L.sel_base + off];
-    const int resp = P.sel_resp[(long long)frame * P.total_sel_cap + L.sel_base + off];
-    const int cx = (int)(xy & 0xffffu) + 16, cy = (int)(xy >> 16) + 16;   // level coordinates (:840-841)
+    int lstart[kMaxLevels + 1];
+    lstart[0] = 0;
+#pragma unroll
+    for (int l = 0; l < kMaxLevels; ++l) lstart[l + 1] = lstart[l] + (l < P.n_levels ? sc[l] : 0);
+    const int total = min(lstart[kMaxLevels], P.kp_cap);
+    if (blockIdx.x == 0 && threadIdx.x == 0) counts[frame] = total;
+    uint8_t* pw = patch[wi];
+    const int ic_r = lane / kIcWords, ic_j = lane - ic_r * kIcWords;     // lanes 0..26: 3 disc rows x 9 words per step
+    const int pt_r = lane / 10, pt_j = lane - pt_r * 10;                 // lanes 0..29: 3 patch rows x 10 words per step
 
-    // ---- IC_Angle
-    const uint8_t* c0 = level_ptr(P.pyr, L, frame) + (long long)(kEdge + cy) * L.pitch + (kXPad + cx);
-    int m10 = 0, m01 = 0;
-    if (lane < 31) {
-        const int u = lane - kHalfPatch;
-        const int au = u < 0 ? -u : u;
-#pragma unroll 1
-        for (int v = -kHalfPatch; v <= kHalfPatch; ++v) {
-            const int av = v < 0 ? -v : v;
-            if (au <= P.umax[av]) {
-                const int val = c0[(long long)v * L.pitch + u];
-                m10 += u * val;
-                m01 += v * val;
+    for (int n = 0; n < kDescPerWarp; ++n) {
+        const int idx = (blockIdx.x * kDescPerWarp + n) * kDescWarps + wi;   // index among the frame's keypoints
+        if (idx >= total) break;
+        int level = 0, first = 0;
+#pragma unroll
+        for (int l = 1; l < kMaxLevels; ++l)
+            if (idx >= lstart[l]) { level = l; first = lstart[l]; }
+        const int off = idx - first;
+        const Level& L = P.lv[level];
+        const uint32_t xy = P.sel_xy[(long long)frame * P.total_sel_cap + L.sel_base + off];
+        const int resp = P.sel_resp[(long long)frame * P.total_sel_cap + L.sel_base + off];
+        const int cx = (int)(xy & 0xffffu) + 16, cy = (int)(xy >> 16) + 16;   // level coordinates (:840-841)
+
+        // ---- IC_Angle
+        int m10 = 0, m01 = 0;
+        {
+            const int A = (kXPad + cx - kHalfPatch) & 3;
+            const uint8_t* base = level_ptr(P.pyr, L, frame) + (long long)(kEdge + cy - kHalfPatch) * L.pitch + (kXPad + cx - kHalfPatch - A);
+            const uint2* tab = reinterpret_cast<const uint2*>(P.ic_tab) + (A * kIcRows) * kIcWords + ic_j;
+            if (lane < 3 * kIcWords) {
+#pragma unroll
+                for (int it = 0; it < (kIcRows + 2) / 3; ++it) {
+                    const int row = 3 * it + ic_r;
+                    if (row < kIcRows) {
+                        const uint32_t px = __ldg(reinterpret_cast<const uint32_t*>(base + (long long)row * L.pitch) + ic_j);
+                        const uint2 w = __ldg(tab + row * kIcWords);
+                        m10 = dp4a_us(px, w.x, m10);
+                        m01 = dp4a_us(px, w.y, m01);
+                    }
+                }
             }
         }
-    }
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        m10 += __shfl_xor_sync(0xffffffffu, m10, d);
-        m01 += __shfl_xor_sync(0xffffffffu, m01, d);
-    }
-    const float angle = fast_atan2((float)m01, (float)m10, P.atan);
+        for (int d = 16; d > 0; d >>= 1) {
+            m10 += __shfl_xor_sync(0xffffffffu, m10, d);
+            m01 += __shfl_xor_sync(0xffffffffu, m01, d);
+        }
+        const float angle = fast_atan2((float)m01, (float)m10, P.atan);
 
-    // ---- rotated BRIEF on the blurred level
-    const float ang = fmul(angle, P.factor_pi);
-    const float a = (float)cos((double)ang), b = (float)sin((double)ang);
-    const uint8_t* b0 = level_ptr(P.blur, L, frame) + (long long)(kEdge + cy) * L.pitch + (kXPad + cx);
-    int val = 0;
+        // ---- stage the blurred 37 x 37 neighbourhood
+        const int A2 = (kXPad + cx - 18) & 3;
+        {
+            const uint8_t* bsrc = level_ptr(P.blur, L, frame) + (long long)(kEdge + cy - 18) * L.pitch + (kXPad + cx - 18 - A2);
+            __syncwarp();
+            if (lane < 30) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const int i0 = 16 * lane + 2 * k;
-        int r0, q0, r1, q1;
-        brief_offset(spx[i0], spy[i0], a, b, &r0, &q0);
-        brief_offset(spx[i0 + 1], spy[i0 + 1], a, b, &r1, &q1);
-        const int t0 = b0[(long long)r0 * L.pitch + q0], t1 = b0[(long long)r1 * L.pitch + q1];
-        val |= (t0 < t1) << k;
-    }
-    desc_out[((long long)frame * P.kp_cap + idx) * 32 + lane] = (uint8_t)val;
-    if (lane == 0) {
-        KeyPoint kp;
-        const float fx = (float)cx, fy = (float)cy;
-        kp.x = level ? fmul(fx, L.scale) : fx;   // keypoint->pt *= scale for level != 0 (:1095-1101)
-        kp.y = level ? fmul(fy, L.scale) : fy;
-        kp.size = L.kp_size;
-        kp.angle = angle;
-        kp.response = (float)resp;
-        kp.octave = level;
-        kp.class_id = -1;
-        kp_out[(long long)frame * P.kp_cap + idx] = kp;
+                for (int it = 0; it < (kPatchRows + 2) / 3; ++it) {
+                    const int row = 3 * it + pt_r;
+                    if (row < kPatchRows)
+                        reinterpret_cast<uint32_t*>(pw + row * kPatchPitch)[pt_j] =
+                            __ldg(reinterpret_cast<const uint32_t*>(bsrc + (long long)row * L.pitch) + pt_j);
+                }
+            }
+            __syncwarp();
+        }
+        // ---- rotated BRIEF
+        const float ang = fmul(angle, P.factor_pi);
+        const float a = (float)cos((double)ang), b = (float)sin((double)ang);
+        const uint8_t* b0 = pw + 18 * kPatchPitch + 18 + A2;
+        int val = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int i0 = 16 * lane + 2 * k;
+            int r0, q0, r1, q1;
+            brief_offset(spx[i0], spy[i0], a, b, &r0, &q0);
+            brief_offset(spx[i0 + 1], spy[i0 + 1], a, b, &r1, &q1);
+            const int t0 = b0[r0 * kPatchPitch + q0], t1 = b0[r1 * kPatchPitch + q1];
+            val |= (t0 < t1) << k;
+        }
+        desc_out[((long long)frame * P.kp_cap + idx) * 32 + lane] = (uint8_t)val;
+        if (lane == 0) {
+            KeyPoint kp;
+            const float fx = (float)cx, fy = (float)cy;
+            kp.x = level ? fmul(fx, L.scale) : fx;   // keypoint->pt *= scale for level != 0 (:1095-1101)
+            kp.y = level ? fmul(fy, L.scale) : fy;
+            kp.size = L.kp_size;
+            kp.angle = angle;
+            kp.response = (float)resp;
+            kp.octave = level;
+            kp.class_id = -1;
+            kp_out[(long long)frame * P.kp_cap + idx] = kp;
+        }
     }
 }
 

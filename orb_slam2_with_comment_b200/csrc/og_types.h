@@ -79,6 +79,7 @@ struct ExtractParams {
     AtanCoef atan;
     float factor_pi;          // (float)(CV_PI/180.f) (:107)
     int umax[16];             // (:454-469)
+    const uint32_t* ic_tab;   // IC_Angle DP4A weights [4 alignments][31 rows][9 words][2] (k_orient_desc)
     // device buffers
     uint8_t* pyr;
     uint8_t* blur;
