@@ -49,6 +49,11 @@ struct orbgpu_extractor {
     int kp_cap = 0;
 
     cudaStream_t stream = nullptr;
+    // host-pointer batch path: copies run on their own streams so that H2D of chunk k+1 and D2H of chunk k-1 overlap
+    // the kernels of chunk k
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr, stream2 = nullptr;   // stream2: odd chunks, so neighbouring chunks' kernels interleave
+    std::vector<cudaEvent_t> ev_in, ev_out;
+    cudaEvent_t ev_begin = nullptr;
     // geometry is rebuilt whenever the frame size changes (buffers are sized for max_w x max_h)
     int cur_w = 0, cur_h = 0;
     og::ExtractParams P;
@@ -399,11 +404,12 @@ int ensure_geometry(orbgpu_extractor* ex, int w, int h) {
 
 // The launch sequence of one batch (device pointers in, device pointers out), all on ex->stream.
 int launch_extract(orbgpu_extractor* ex, const uint8_t* d_images, int batch, size_t row_stride, size_t frame_stride,
-                   og::KeyPoint* d_kp, uint8_t* d_desc, int kp_capacity, int32_t* d_counts) {
+                   og::KeyPoint* d_kp, uint8_t* d_desc, int kp_capacity, int32_t* d_counts, int frame0 = 0, cudaStream_t on = nullptr) {
     og::ExtractParams P = ex->P;
     P.batch = batch;
+    P.frame0 = frame0;
     P.kp_cap = kp_capacity;
-    cudaStream_t st = ex->stream;
+    cudaStream_t st = on ? on : ex->stream;
     int launches = 0;
     auto mark = [&](int i) { if (ex->profiling) cudaEventRecord(ex->ev[i], st); };
     mark(0);
@@ -566,6 +572,10 @@ int orbgpu_extractor_create(orbgpu_extractor** out, int device, int nfeatures, f
         ce = cudaMemcpy(ex->d_ic_tab, tab.data(), tab.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
     }
     if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&ex->stream, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&ex->s_h2d, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&ex->s_d2h, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&ex->stream2, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&ex->ev_begin, cudaEventDisableTiming);
     if (ce != cudaSuccess) {
         std::string m = std::string("workspace allocation failed: ") + cudaGetErrorString(ce);
         orbgpu_extractor_destroy(ex);
@@ -579,6 +589,12 @@ int orbgpu_extractor_destroy(orbgpu_extractor* ex) {
     if (!ex) return ORBGPU_OK;
     cudaSetDevice(ex->device);
     if (ex->stream) { cudaStreamSynchronize(ex->stream); cudaStreamDestroy(ex->stream); }
+    if (ex->s_h2d) { cudaStreamSynchronize(ex->s_h2d); cudaStreamDestroy(ex->s_h2d); }
+    if (ex->s_d2h) { cudaStreamSynchronize(ex->s_d2h); cudaStreamDestroy(ex->s_d2h); }
+    if (ex->stream2) { cudaStreamSynchronize(ex->stream2); cudaStreamDestroy(ex->stream2); }
+    for (cudaEvent_t e : ex->ev_in) cudaEventDestroy(e);
+    for (cudaEvent_t e : ex->ev_out) cudaEventDestroy(e);
+    if (ex->ev_begin) cudaEventDestroy(ex->ev_begin);
     for (int i = 0; i < 6; ++i) if (ex->ev[i]) cudaEventDestroy(ex->ev[i]);
     void* ptrs[] = {ex->d_ic_tab, ex->d_btiles, ex->d_segs, ex->d_tmaps, ex->d_pyr, ex->d_blur, ex->d_images, ex->d_cells, ex->d_taps, ex->d_cell_count, ex->d_cand_xy,
                     ex->d_cand_resp, ex->d_ot, ex->d_sel_xy, ex->d_sel_resp, ex->d_sel_count, ex->d_counts, ex->d_kp, ex->d_desc};
@@ -631,27 +647,56 @@ int orbgpu_extract_batch(orbgpu_extractor* ex, const uint8_t* images, int batch,
     if (rc) return rc;
     if (!images || !kp_out || !desc_out || !counts) return fail(ORBGPU_ERR_ARG, "null pointer");
     cudaStream_t st = ex->stream;
-    // H2D: tightly packed device copy of the frames
-    if (row_stride == (size_t)width && frame_stride == (size_t)width * height) {
-        OG_CUDA(cudaMemcpyAsync(ex->d_images, images, (size_t)width * height * batch, cudaMemcpyHostToDevice, st));
-    } else {
-        for (int f = 0; f < batch; ++f)
-            OG_CUDA(cudaMemcpy2DAsync(ex->d_images + (size_t)f * width * height, width, images + (size_t)f * frame_stride,
-                                      row_stride, width, height, cudaMemcpyHostToDevice, st));
+    // Chunked pipeline: H2D (s_h2d) -> kernels (stream) -> D2H (s_d2h), chained by events per chunk.
+    const int chunk = batch <= 96 ? batch : 64;
+    const int nchunks = (batch + chunk - 1) / chunk;
+    while ((int)ex->ev_in.size() < nchunks) {
+        cudaEvent_t a, b;
+        OG_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        ex->ev_in.push_back(a);
+        OG_CUDA(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        ex->ev_out.push_back(b);
     }
-    rc = launch_extract(ex, ex->d_images, batch, width, (size_t)width * height, ex->d_kp, ex->d_desc, ex->kp_cap, ex->d_counts);
-    if (rc) return rc;
-    // D2H: counts first, then only the used prefix of every frame's slots
-    OG_CUDA(cudaMemcpyAsync(counts, ex->d_counts, (size_t)batch * 4, cudaMemcpyDeviceToHost, st));
-    if (kp_capacity == ex->kp_cap) {
-        OG_CUDA(cudaMemcpyAsync(kp_out, ex->d_kp, (size_t)batch * ex->kp_cap * sizeof(og::KeyPoint), cudaMemcpyDeviceToHost, st));
-        OG_CUDA(cudaMemcpyAsync(desc_out, ex->d_desc, (size_t)batch * ex->kp_cap * 32, cudaMemcpyDeviceToHost, st));
-    } else {
-        OG_CUDA(cudaMemcpy2DAsync(kp_out, (size_t)kp_capacity * sizeof(og::KeyPoint), ex->d_kp, (size_t)ex->kp_cap * sizeof(og::KeyPoint),
-                                  (size_t)ex->kp_cap * sizeof(og::KeyPoint), batch, cudaMemcpyDeviceToHost, st));
-        OG_CUDA(cudaMemcpy2DAsync(desc_out, (size_t)kp_capacity * 32, ex->d_desc, (size_t)ex->kp_cap * 32, (size_t)ex->kp_cap * 32, batch,
-                                  cudaMemcpyDeviceToHost, st));
+    // work queued earlier on the compute stream (device-resident calls) must not be overtaken by the copies
+    OG_CUDA(cudaEventRecord(ex->ev_begin, st));
+    OG_CUDA(cudaStreamWaitEvent(ex->s_h2d, ex->ev_begin, 0));
+    OG_CUDA(cudaStreamWaitEvent(ex->s_d2h, ex->ev_begin, 0));
+    OG_CUDA(cudaStreamWaitEvent(ex->stream2, ex->ev_begin, 0));
+    const size_t fbytes = (size_t)width * height;
+    const bool packed = row_stride == (size_t)width && frame_stride == fbytes;
+    for (int c = 0; c < nchunks; ++c) {
+        const int f0 = c * chunk, nb = std::min(chunk, batch - f0);
+        if (packed) {
+            OG_CUDA(cudaMemcpyAsync(ex->d_images + f0 * fbytes, images + f0 * fbytes, fbytes * nb, cudaMemcpyHostToDevice, ex->s_h2d));
+        } else {
+            for (int f = f0; f < f0 + nb; ++f)
+                OG_CUDA(cudaMemcpy2DAsync(ex->d_images + f * fbytes, width, images + (size_t)f * frame_stride, row_stride, width, height,
+                                          cudaMemcpyHostToDevice, ex->s_h2d));
+        }
+        cudaStream_t cs = (c & 1) ? ex->stream2 : st;
+        OG_CUDA(cudaEventRecord(ex->ev_in[c], ex->s_h2d));
+        OG_CUDA(cudaStreamWaitEvent(cs, ex->ev_in[c], 0));
+        rc = launch_extract(ex, ex->d_images, nb, width, fbytes, ex->d_kp, ex->d_desc, ex->kp_cap, ex->d_counts, f0, cs);
+        if (rc) return rc;
+        OG_CUDA(cudaEventRecord(ex->ev_out[c], cs));
+        OG_CUDA(cudaStreamWaitEvent(ex->s_d2h, ex->ev_out[c], 0));
+        // D2H of this chunk's slots
+        OG_CUDA(cudaMemcpyAsync(counts + f0, ex->d_counts + f0, (size_t)nb * 4, cudaMemcpyDeviceToHost, ex->s_d2h));
+        const size_t kb = (size_t)ex->kp_cap * sizeof(og::KeyPoint), db = (size_t)ex->kp_cap * 32;
+        if (kp_capacity == ex->kp_cap) {
+            OG_CUDA(cudaMemcpyAsync(kp_out + (size_t)f0 * kp_capacity, ex->d_kp + (size_t)f0 * ex->kp_cap, kb * nb, cudaMemcpyDeviceToHost, ex->s_d2h));
+            OG_CUDA(cudaMemcpyAsync(desc_out + (size_t)f0 * kp_capacity * 32, ex->d_desc + (size_t)f0 * ex->kp_cap * 32, db * nb, cudaMemcpyDeviceToHost, ex->s_d2h));
+        } else {
+            OG_CUDA(cudaMemcpy2DAsync(kp_out + (size_t)f0 * kp_capacity, (size_t)kp_capacity * sizeof(og::KeyPoint), ex->d_kp + (size_t)f0 * ex->kp_cap, kb, kb, nb,
+                                      cudaMemcpyDeviceToHost, ex->s_d2h));
+            OG_CUDA(cudaMemcpy2DAsync(desc_out + (size_t)f0 * kp_capacity * 32, (size_t)kp_capacity * 32, ex->d_desc + (size_t)f0 * ex->kp_cap * 32, db, db, nb,
+                                      cudaMemcpyDeviceToHost, ex->s_d2h));
+        }
     }
+    ex->last_batch = batch;
+    ex->last_launches *= nchunks;
+    OG_CUDA(cudaStreamSynchronize(ex->s_d2h));
+    OG_CUDA(cudaStreamSynchronize(ex->stream2));
     OG_CUDA(cudaStreamSynchronize(st));
     return ORBGPU_OK;
 }

@@ -28,7 +28,7 @@ __device__ __forceinline__ uint8_t* level_ptr(uint8_t* base, const Level& L, int
 __global__ void k_level0(const __grid_constant__ ExtractParams P, const uint8_t* __restrict__ images, long long row_stride,
                          long long frame_stride) {
     const Level& L = P.lv[0];
-    const int frame = blockIdx.z;
+    const int frame = P.frame0 + blockIdx.z;
     const int Y = blockIdx.y;  // row of the bordered buffer
     const int X4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (X4 >= L.pitch) return;
@@ -52,7 +52,7 @@ __global__ void k_level0(const __grid_constant__ ExtractParams P, const uint8_t*
 __global__ void k_resize(const __grid_constant__ ExtractParams P, int level) {
     const Level& L = P.lv[level];
     const Level& S = P.lv[level - 1];
-    const int frame = blockIdx.z;
+    const int frame = P.frame0 + blockIdx.z;
     const int Y = blockIdx.y;
     const int X4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (X4 >= L.pitch) return;
@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(kResizeThreads) k_resize4(const __grid_constan
                                                             int n_items) {
     const Level& L = P.lv[level];
     const Level& S = P.lv[level - 1];
-    const int frame = blockIdx.y;
+    const int frame = P.frame0 + blockIdx.y;
     const int id = blockIdx.x * kResizeThreads + threadIdx.x;
     if (id >= n_items) return;
     const int band = (int)__umulhi((uint32_t)id, nwx_magic), wx = id - band * nwx;
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(kResizeThreads) k_resize4(const __grid_constan
 // The BORDER_REFLECT_101 frame of levels 1.. (:1122-1123; level 0 gets its frame in k_level0).  One CTA per 8 padded rows.
 constexpr int kBorderRows = 8, kBorderThreads = 128;
 __global__ void __launch_bounds__(kBorderThreads) k_borders(const __grid_constant__ ExtractParams P) {
-    const int frame = blockIdx.y;
+    const int frame = P.frame0 + blockIdx.y;
     int level = 1, blk = blockIdx.x;
     while (level < P.n_levels) {
         const int nb = (P.lv[level].rows + kBorderRows - 1) / kBorderRows;
@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(kFastThreads) k_fast_cells(const __grid_consta
     __shared__ int any_ini;
 
     const Cell c = P.cells[blockIdx.x];
-    const int frame = blockIdx.y;
+    const int frame = P.frame0 + blockIdx.y;
     const Level& L = P.lv[c.level];
     const int t = threadIdx.x;
     const int tw = c.tw, th = c.th;
@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(kSegThreads) k_fast_seg(const __grid_constant_
     __shared__ int qn;
 
     const Segment sg = P.segs[blockIdx.x];
-    const int frame = blockIdx.y;
+    const int frame = P.frame0 + blockIdx.y;
     const Level& L = P.lv[sg.level];
     const int t = threadIdx.x, lane = t & 31, wi = t >> 5;
     const int th = sg.th, tw = sg.tw, hbox = L.hbox;
@@ -515,7 +515,10 @@ __global__ void __launch_bounds__(kSegThreads) k_fast_seg(const __grid_constant_
 // DistributeOctTree: one CTA per (level, frame).  Gathers the level's candidates from the per-cell slots in
 // emission order (cell-row-major, row-major inside a cell), then runs the block-cooperative state machine.
 // ------------------------------------------------------------------------------------------------------------
-constexpr int kOctThreads = 256;
+#ifndef OG_OCT_THREADS
+#define OG_OCT_THREADS 128
+#endif
+constexpr int kOctThreads = OG_OCT_THREADS;
 
 __device__ __forceinline__ OtWork carve_work(uint8_t* ws, int cap, int node_cap) {
     OtWork W;
@@ -542,7 +545,7 @@ __device__ __forceinline__ OtWork carve_work(uint8_t* ws, int cap, int node_cap)
 
 __global__ void __launch_bounds__(kOctThreads) k_octree(const __grid_constant__ ExtractParams P) {
     __shared__ OtShared sh;
-    const int level = blockIdx.x, frame = blockIdx.y;
+    const int level = blockIdx.x, frame = P.frame0 + blockIdx.y;
     const Level& L = P.lv[level];
     OtWork W = carve_work(P.ot_ws + (long long)frame * P.ot_frame_bytes + L.ot_base, L.cand_cap, L.node_cap);
 
@@ -557,10 +560,11 @@ __global__ void __launch_bounds__(kOctThreads) k_octree(const __grid_constant__ 
     const uint32_t* cxy = P.cand_xy + (long long)frame * P.total_cand_cap + L.cand_base;
     const uint8_t* crr = P.cand_resp + (long long)frame * P.total_cand_cap + L.cand_base;
     const Cell* cells = P.cells + L.cell_base;
-    // one warp per cell copies the cell's run
-    for (int ci = threadIdx.x >> 5; ci < L.n_cells; ci += kOctThreads / 32) {
+    // one thread per cell copies the cell's run (a handful of candidates): all lanes busy, the loads of different
+    // cells overlap
+    for (int ci = threadIdx.x; ci < L.n_cells; ci += kOctThreads) {
         const int n = ccount[ci], dst = coff[ci], src = cells[ci].slot;
-        for (int k = threadIdx.x & 31; k < n; k += 32) {
+        for (int k = 0; k < n; ++k) {
             W.kxy[1][dst + k] = cxy[src + k];
             W.kresp[1][dst + k] = crr[src + k];
         }
@@ -605,7 +609,7 @@ __global__ void __launch_bounds__(kBlurThreads) k_blur_tma(const __grid_constant
     __shared__ uint64_t mbar;
     const BlurTile bt = tiles[blockIdx.x];
     const Level& L = P.lv[bt.level];
-    const int frame = blockIdx.y, t = threadIdx.x;
+    const int frame = P.frame0 + blockIdx.y, t = threadIdx.x;
     if (t == 0) mbar_init(&mbar, 1);
     __syncthreads();
     if (t == 0) {
@@ -680,7 +684,7 @@ __global__ void __launch_bounds__(kDescWarps * 32) k_orient_desc(const __grid_co
     __shared__ __align__(16) uint8_t patch[kDescWarps][kPatchRows * kPatchPitch];
     for (int i = threadIdx.x; i < 512; i += blockDim.x) { spx[i] = c_pat_x[i]; spy[i] = c_pat_y[i]; }
     __syncthreads();
-    const int frame = blockIdx.y;
+    const int frame = P.frame0 + blockIdx.y;
     const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
     // keypoints are concatenated in level order (:1076-1103): level starts from the per-level counts
     const int32_t* sc = P.sel_count + frame * P.n_levels;

@@ -82,6 +82,7 @@ struct OtShared {
     int m;        // candidates in the current pass
     int scan_total;
     int warp_sums[32];
+    int warp_sums4[32][4];
     int finish;
     int mode;
 };
@@ -195,8 +196,34 @@ OG_HD void ot_pass(const OtWork& W, OtShared* sh, int cur, int rcur, int M, int 
         W.thr[tt * 4 + 0] = c0; W.thr[tt * 4 + 1] = c1; W.thr[tt * 4 + 2] = c2; W.thr[tt * 4 + 3] = c3;
     OG_THREADS_END
     OG_SYNC();
-    // exclusive scan over threads of each of the 4 counters: threads 0..3 scan one counter each, serially
-    // (blockDim <= 1024 entries)
+    // exclusive scan over threads of each of the 4 counters
+#if OG_DEVICE_PASS
+    {
+        const int tt = threadIdx.x, lane = tt & 31, w = tt >> 5, nwarp = (blockDim.x + 31) >> 5;
+        int v[4], own[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { own[k] = W.thr[tt * 4 + k]; v[k] = own[k]; }
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int u = __shfl_up_sync(0xffffffffu, v[k], d);
+                if (lane >= d) v[k] += u;
+            }
+        }
+        if (lane == 31) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) sh->warp_sums4[w][k] = v[k];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            int off = 0;
+            for (int w2 = 0; w2 < nwarp; ++w2) off += (w2 < w) ? sh->warp_sums4[w2][k] : 0;
+            W.thr[tt * 4 + k] = off + v[k] - own[k];
+        }
+    }
+#else
     OG_FOR(k, 4) {
         const int TTn = OG_NTHREADS();
         int run = 0;
@@ -206,6 +233,7 @@ OG_HD void ot_pass(const OtWork& W, OtShared* sh, int cur, int rcur, int M, int 
             run += x;
         }
     }
+#endif
     OG_SYNC();
     OG_THREADS_BEGIN(tt, TT)
         OG_CHUNK(M, tt, TT, lo, hi)

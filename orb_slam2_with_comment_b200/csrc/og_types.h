@@ -69,7 +69,8 @@ struct Segment {
 struct ExtractParams {
     Level lv[kMaxLevels];
     int n_levels;
-    int batch;
+    int batch;                // frames of this launch
+    int frame0;               // first frame of this launch inside the workspace / output arrays (chunked host path)
     int ini_th, min_th;
     int total_cells;          // cells per frame (all levels)
     int total_cand_cap;       // candidate slots per frame

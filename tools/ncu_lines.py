@@ -71,5 +71,6 @@ def src(ln):
             L = src_cache[p]
             return L[ln[1] - 1].strip()[:90] if ln[1] - 1 < len(L) else ""
     return ""
-for ln, (i, s, n) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+key = (lambda kv: -kv[1][1]) if os.environ.get("SORT") == "stall" else (lambda kv: -kv[1][0])
+for ln, (i, s, n) in sorted(agg.items(), key=key)[:top]:
     print(f"{100.0*i/tot_i:5.1f}% inst {100.0*s/max(tot_s,1):5.1f}% stall  {n:4d} sass  {ln[0] if ln else '?'}:{ln[1] if ln else 0:<4d} {src(ln)}")
