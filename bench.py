@@ -35,11 +35,11 @@ METRIC = "ORB frames/s @1241x376 2k feats"
 N_DISTINCT = 16  # distinct synthetic frames; the batch tiles them (every copy has its own HBM address)
 
 
-def make_frames(batch: int) -> np.ndarray:
+def make_frames(batch: int, first: int = 0) -> np.ndarray:
+    """Frames first .. first+batch of the global work list (frame i is G_rects seed i mod N_DISTINCT)."""
     from orb_slam2_with_comment_b200 import synth
-    base = np.stack([synth.g_rects(W, H, s) for s in range(min(N_DISTINCT, batch))])
-    reps = (batch + len(base) - 1) // len(base)
-    return np.ascontiguousarray(np.concatenate([base] * reps)[:batch])
+    base = [synth.g_rects(W, H, s) for s in range(min(N_DISTINCT, max(batch, 1)))]
+    return np.ascontiguousarray(np.stack([base[(first + i) % len(base)] for i in range(batch)]))
 
 
 def level_sizes():
@@ -301,8 +301,10 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from orb_slam2_with_comment_b200 import sharding
     B = args.batch
-    frames = make_frames(B)
+    lo, hi = sharding.shard_range(world * B, rank, world)   # weak scaling: B frames per rank, contiguous ranges of the global list
+    frames = make_frames(hi - lo, lo)
     ex = ORBextractor(NFEATURES, SCALE, NLEVELS, INI_TH, MIN_TH, device=local, max_width=W, max_height=H, max_batch=B)
     dev = torch.device("cuda", local)
     d_img = torch.from_numpy(frames).to(dev)
@@ -337,7 +339,6 @@ def run_ours(args):
     barrier()
     ms = e0.elapsed_time(e1)
     launches = ex.last_launches() * args.steps
-    clocks = sampler.stop()
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -387,6 +388,7 @@ def run_ours(args):
     assert int(h_cnt.sum()) == int(d_cnt.sum().item()), "host and device paths disagree"
     ex_launches_total = launches
     matching = None if args.no_matching else run_matching(args, torch, dist, rank, world, local, barrier)
+    clocks = sampler.stop()   # sampled over the extraction and matching timed regions
 
     if rank != 0:
         if world > 1:
@@ -405,8 +407,8 @@ def run_ours(args):
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
-        try:
-            traffic = json.load(open(tpath)).get(dominant)
+        try:   # DRAM bytes per frame of the stage's kernels from the committed ncu --set full capture, scaled to this launch
+            traffic = float(json.load(open(tpath))["dram_bytes_per_frame"][dominant]) * B
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
