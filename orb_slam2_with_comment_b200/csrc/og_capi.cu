@@ -298,7 +298,7 @@ std::string build_geometry(const orbgpu_extractor& ex, int w, int h, int batch_c
                 sg.ncells = (int16_t)n;
                 sg.tw = (int16_t)tw;
                 const int gx = (og::kXPad + sg.x0 - 3) & ~15, ox = og::kXPad + sg.x0 - gx;   // as in k_fast_seg
-                const uint32_t nw = (uint32_t)(((ox + tw + 3) >> 2) - (ox >> 2));
+                const uint32_t nw = (uint32_t)(((ox + tw - 1) >> 3) - (ox >> 3) + 1);   // 8-pixel steps covering the tested columns
                 sg.nw_magic = (uint32_t)((0x100000000ull + nw - 1) / nw);
                 G.segs.push_back(sg);
                 th_max = std::max(th_max, (int)c0.th);

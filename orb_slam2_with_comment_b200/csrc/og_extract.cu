@@ -357,37 +357,39 @@ __global__ void __launch_bounds__(kSegThreads) k_fast_seg(const __grid_constant_
     mbar_wait(&mbar, 0);
 
     const int min_th = P.min_th, ini_th = P.ini_th;
-    // ---- 1. rejection test on words -----------------------------------------------------------------------
+    // ---- 1. rejection test, 8 pixels (two words) per step -> one byte of the row's 256-bit candidate bitmap ---------
     {
         const uint32_t* T = reinterpret_cast<const uint32_t*>(tile);
-        const int w0 = ox >> 2, nw = ((ox + tw + 3) >> 2) - w0, total = th * nw;
+        const int b0 = ox >> 3, nb = ((ox + tw - 1) >> 3) - b0 + 1, total = th * nb;
         const bool big = min_th >= 127;
         const uint32_t kadd = (uint32_t)(big ? 0xff - min_th : 0x7f - min_th) * 0x01010101u;
-        const uint32_t head = 0xffffffffu << (8 * (ox & 3));                                            // tested bytes of the first word
-        const uint32_t tail = ((ox + tw) & 3) ? (0xffffffffu >> (8 * (4 - ((ox + tw) & 3)))) : 0xffffffffu;   // ... of the last word
-        for (int u = t; u < total; u += kSegThreads) {
-            const int r = (int)__umulhi((uint32_t)u, sg.nw_magic);
-            const int wr = u - r * nw, w = w0 + wr;
-            const uint32_t* row = T + (r + 3) * 64 + w;
-            const uint32_t c = row[0], lw = row[-1], rw = row[1], up = row[-3 * 64], dn = row[3 * 64];
-            const uint32_t lf = __funnelshift_r(lw, c, 8), rt = __funnelshift_r(c, rw, 24);   // pixels x-3 / x+3
+        auto ge2 = [&](uint32_t c, uint32_t up, uint32_t dn, uint32_t lf, uint32_t rt) {
             const uint32_t ma = gt_bytes(__vabsdiffu4(c, up), kadd, big), mb = gt_bytes(__vabsdiffu4(c, dn), kadd, big);
             const uint32_t mc = gt_bytes(__vabsdiffu4(c, lf), kadd, big), md = gt_bytes(__vabsdiffu4(c, rt), kadd, big);
-            uint32_t ge2 = (ma & mb) | (mc & md) | ((ma ^ mb) & (mc ^ md));
-            if (wr == 0) ge2 &= head;
-            if (wr == nw - 1) ge2 &= tail;
-            // bits 7,15,23,31 -> 4-bit value
-            mk[r * 64 + w] = (uint8_t)((((ge2 >> 7) * 0x01020408u) >> 24) & 0xf);
+            const uint32_t g = (ma & mb) | (mc & md) | ((ma ^ mb) & (mc ^ md));
+            return (((g >> 7) * 0x01020408u) >> 24) & 0xfu;   // bits 7,15,23,31 -> 4-bit value
+        };
+        for (int u = t; u < total; u += kSegThreads) {
+            const int r = (int)__umulhi((uint32_t)u, sg.nw_magic);
+            const int br = u - r * nb, B = b0 + br;
+            const uint32_t* row = T + (r + 3) * 64 + 2 * B;
+            const uint32_t c0 = row[0], c1 = row[1], lw = row[-1], rw = row[2];
+            const uint32_t n0 = ge2(c0, row[-3 * 64], row[3 * 64], __funnelshift_r(lw, c0, 8), __funnelshift_r(c0, c1, 24));
+            const uint32_t n1 = ge2(c1, row[-3 * 64 + 1], row[3 * 64 + 1], __funnelshift_r(c0, c1, 8), __funnelshift_r(c1, rw, 24));
+            uint32_t m = n0 | (n1 << 4);
+            if (br == 0) m &= 0xffu << (ox & 7);                                  // columns before the first tested pixel
+            if (br == nb - 1) m &= 0xffu >> (7 - ((ox + tw - 1) & 7));            // ... and after the last
+            mk[r * 32 + B] = (uint8_t)m;
         }
     }
     __syncthreads();
-    // ---- 2. compaction of the surviving pixels into the queue ---------------------------------------------
+    // ---- 2. compaction of the surviving pixels into the queue (entry = tile row << 8 | tile column) --------------
     {
-        const uint32_t* M = reinterpret_cast<const uint32_t*>(mk);
-        const int nwords = th * 16;
-        for (int i0 = 0; i0 < nwords; i0 += kSegThreads) {
+        const uint16_t* M = reinterpret_cast<const uint16_t*>(mk);
+        const int nhalf = th * 16;
+        for (int i0 = 0; i0 < nhalf; i0 += kSegThreads) {
             const int i = i0 + t;
-            uint32_t v = i < nwords ? M[i] : 0u;
+            uint32_t v = i < nhalf ? M[i] : 0u;
             const int cnt = __popc(v);
             int inc = cnt;
 #pragma unroll
@@ -398,41 +400,39 @@ __global__ void __launch_bounds__(kSegThreads) k_fast_seg(const __grid_constant_
             int base = 0;
             if (lane == 31 && inc) base = atomicAdd(&qn, inc);
             base = __shfl_sync(0xffffffffu, base, 31) + inc - cnt;
-            const int r = i >> 4, w0 = (i & 15) * 4;
+            const int e0 = i << 4;   // 16 rows-of-16 per tile row: row * 256 + 16 * (i & 15)
             while (v) {
                 const int b = __ffs(v) - 1;
                 v &= v - 1;
-                const int px = 4 * (w0 + (b >> 3)) + (b & 7) - ox;
-                queue[base++] = (uint16_t)((r << 8) | px);
+                queue[base++] = (uint16_t)(e0 + b);
             }
         }
     }
     __syncthreads();
     const int nq = qn;
     // ---- 3. exact score of the queued pixels ------------------------------------------------------------------
+    const uint32_t thr2 = (uint32_t)(256 + min_th);
     for (int q = t; q < nq; q += kSegThreads) {
-        const int e = queue[q], r = e >> 8, px = e & 255;
-        const uint8_t* p = tile + (r + 3) * kSegPitch + px + ox;
-        const int v = p[0];
-        uint32_t rg[16];
-        rg[0] = p[3 * kSegPitch]; rg[4] = p[3]; rg[8] = p[-3 * kSegPitch]; rg[12] = p[-3];
+        const int e = queue[q];
+        const uint8_t* p = tile + 3 * kSegPitch + e;
+        const uint32_t v = p[0];
+        const uint32_t bias = ((256u - v) << 16) | (256u + v);
+        uint32_t E[16];
+        E[0] = p[3 * kSegPitch] * 0xFFFFu + bias;  E[4] = p[3] * 0xFFFFu + bias;   // lo: 256 + d_k, hi: 256 - d_k
+        E[8] = p[-3 * kSegPitch] * 0xFFFFu + bias; E[12] = p[-3] * 0xFFFFu + bias;
         {
-            const int d0 = v - (int)rg[0], d4 = v - (int)rg[4], d8 = v - (int)rg[8], d12 = v - (int)rg[12];
-            const int nb = (d0 > min_th) + (d4 > min_th) + (d8 > min_th) + (d12 > min_th);
-            const int nd = (d0 < -min_th) + (d4 < -min_th) + (d8 < -min_th) + (d12 < -min_th);
-            if (nb < 2 && nd < 2) continue;
+            // an arc of 9 covers two of the four compass pixels: the second largest of the four (per half) must pass
+            const uint32_t a = __vmaxu2(E[0], E[4]), b = __vminu2(E[0], E[4]), c = __vmaxu2(E[8], E[12]), d = __vminu2(E[8], E[12]);
+            const uint32_t s2 = __vmaxu2(__vminu2(a, c), __vmaxu2(b, d));
+            if ((s2 & 0xffffu) <= thr2 && (s2 >> 16) <= thr2) continue;
         }
-        rg[1] = p[3 * kSegPitch + 1];   rg[2] = p[2 * kSegPitch + 2];   rg[3] = p[kSegPitch + 3];
-        rg[5] = p[-kSegPitch + 3];      rg[6] = p[-2 * kSegPitch + 2];  rg[7] = p[-3 * kSegPitch + 1];
-        rg[9] = p[-3 * kSegPitch - 1];  rg[10] = p[-2 * kSegPitch - 2]; rg[11] = p[-kSegPitch - 3];
-        rg[13] = p[kSegPitch - 3];      rg[14] = p[2 * kSegPitch - 2];  rg[15] = p[3 * kSegPitch - 1];
-        const uint32_t bias = ((uint32_t)(256 - v) << 16) | (uint32_t)(256 + v);
-        uint32_t E[16], m3[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) E[k] = rg[k] * 0xFFFFu + bias;     // lo: 256 + d_k, hi: 256 - d_k
+        E[1] = p[3 * kSegPitch + 1] * 0xFFFFu + bias;   E[2] = p[2 * kSegPitch + 2] * 0xFFFFu + bias;   E[3] = p[kSegPitch + 3] * 0xFFFFu + bias;
+        E[5] = p[-kSegPitch + 3] * 0xFFFFu + bias;      E[6] = p[-2 * kSegPitch + 2] * 0xFFFFu + bias;  E[7] = p[-3 * kSegPitch + 1] * 0xFFFFu + bias;
+        E[9] = p[-3 * kSegPitch - 1] * 0xFFFFu + bias;  E[10] = p[-2 * kSegPitch - 2] * 0xFFFFu + bias; E[11] = p[-kSegPitch - 3] * 0xFFFFu + bias;
+        E[13] = p[kSegPitch - 3] * 0xFFFFu + bias;      E[14] = p[2 * kSegPitch - 2] * 0xFFFFu + bias;  E[15] = p[3 * kSegPitch - 1] * 0xFFFFu + bias;
+        uint32_t m3[16], m9[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) m3[k] = __vimin3_u16x2(E[k], E[(k + 1) & 15], E[(k + 2) & 15]);
-        uint32_t m9[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) m9[k] = __vimin3_u16x2(m3[k], m3[(k + 3) & 15], m3[(k + 6) & 15]);
         uint32_t a = __vimax3_u16x2(m9[0], m9[1], m9[2]), b = __vimax3_u16x2(m9[3], m9[4], m9[5]);
@@ -442,13 +442,32 @@ __global__ void __launch_bounds__(kSegThreads) k_fast_seg(const __grid_constant_
         d = __vimax3_u16x2(d, f, m9[15]);
         a = __vmaxu2(a, d);
         const int V = max((int)(a & 0xffffu), (int)(a >> 16)) - 257;
-        if (V >= min_th) score[(r + 1) * kSegPitch + px + 4] = (uint8_t)V;
+        if (V >= min_th) score[e + kSegPitch + 4 - ox] = (uint8_t)V;   // (row + 1) * 256 + px + 4
     }
     __syncthreads();
-    // ---- 4. NMS over the queue ---------------------------------------------------------------------------------
-    for (int q = t; q < nq; q += kSegThreads) {
-        const int e = queue[q], r = e >> 8, px = e & 255;
-        const uint8_t* s = score + (r + 1) * kSegPitch + px + 4;
+    // ---- 4a. the corners among the queued pixels, compacted into the (now dead) tile ---------------------------
+    uint16_t* cq = reinterpret_cast<uint16_t*>(tile);
+    const int cq_cap = hbox * kSegPitch / 2;
+    if (t == 0) qn = 0;
+    __syncthreads();
+    for (int q0 = 0; q0 < nq; q0 += kSegThreads) {
+        const int q = q0 + t;
+        const int e = q < nq ? queue[q] : 0;
+        const bool corner = q < nq && score[e + kSegPitch + 4 - ox] != 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, corner);
+        int base = 0;
+        if (lane == 0 && bal) base = atomicAdd(&qn, __popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0) + __popc(bal & ((1u << lane) - 1));
+        if (corner && base < cq_cap) cq[base] = (uint16_t)e;
+    }
+    __syncthreads();
+    // ---- 4b. NMS over the corners (all queued pixels if the corner list overflowed its buffer) -------------------
+    const bool use_cq = qn <= cq_cap;
+    const uint16_t* nms_q = use_cq ? cq : queue;
+    const int nms_n = use_cq ? qn : nq;
+    for (int q = t; q < nms_n; q += kSegThreads) {
+        const int e = nms_q[q], r = e >> 8, px = (e & 255) - ox;
+        const uint8_t* s = score + e + kSegPitch + 4 - ox;
         const int v = s[0];
         if (v == 0) continue;
         const int fl = lut[px];

@@ -63,7 +63,7 @@ struct Segment {
     int16_t level, ncells;
     int32_t first_cell;          // index into the frame's cell table
     int16_t x0, y0, tw, th;
-    uint32_t nw_magic;           // ceil(2^32 / nw), nw = 32-bit words covering the tested columns: row = (unit * nw_magic) >> 32
+    uint32_t nw_magic;           // ceil(2^32 / nb), nb = 8-pixel steps covering the tested columns: row = (unit * nw_magic) >> 32
 };
 
 struct ExtractParams {
