@@ -435,9 +435,15 @@ int launch_extract(orbgpu_extractor* ex, const uint8_t* d_images, int batch, siz
         ++launches;
     }
     if (P.n_levels > 1 && !generic) {
-        int nblk = 0;
-        for (int l = 1; l < P.n_levels; ++l) nblk += (P.lv[l].rows + og::kBorderRows - 1) / og::kBorderRows;
-        og::k_borders<<<dim3(nblk, batch), og::kBorderThreads, 0, st>>>(P);
+        og::BorderPlan bp;
+        int acc = 0;
+        bp.first[0] = 0;
+        for (int l = 1; l < P.n_levels; ++l) {
+            bp.first[l] = acc;
+            acc += 2 * og::kEdge * P.lv[l].h + 2 * og::kEdge * ((P.lv[l].w + 2 * og::kEdge + 3) / 4);
+        }
+        for (int l = P.n_levels; l <= og::kMaxLevels; ++l) bp.first[l] = acc;
+        og::k_borders<<<dim3((acc + og::kBorderThreads - 1) / og::kBorderThreads, batch), og::kBorderThreads, 0, st>>>(P, bp);
         ++launches;
     }
     mark(1);

@@ -146,32 +146,40 @@ __global__ void __launch_bounds__(kResizeThreads) k_resize4(const __grid_constan
     }
 }
 
-// The BORDER_REFLECT_101 frame of levels 1.. (:1122-1123; level 0 gets its frame in k_level0).  One CTA per 8 padded rows.
-constexpr int kBorderRows = 8, kBorderThreads = 128;
-__global__ void __launch_bounds__(kBorderThreads) k_borders(const __grid_constant__ ExtractParams P) {
+// The BORDER_REFLECT_101 frame of levels 1.. (:1122-1123; level 0 gets its frame in k_level0).  Work items per level:
+// 38*h "side" items (one byte of the frame left or right of an interior row) and 38 * ceil((w+38)/4) "cap"
+// items (one thread writes 4 bytes of a top/bottom row).  Item -> (level, kind) through the per-level prefix in `B`.
+constexpr int kBorderThreads = 128;
+struct BorderPlan {
+    int first[kMaxLevels + 1];   // first item of level l (levels 1..n-1), total at [n_levels]
+};
+__global__ void __launch_bounds__(kBorderThreads) k_borders(const __grid_constant__ ExtractParams P, const __grid_constant__ BorderPlan B) {
     const int frame = P.frame0 + blockIdx.y;
-    int level = 1, blk = blockIdx.x;
-    while (level < P.n_levels) {
-        const int nb = (P.lv[level].rows + kBorderRows - 1) / kBorderRows;
-        if (blk < nb) break;
-        blk -= nb;
-        ++level;
-    }
-    if (level >= P.n_levels) return;
+    int it = blockIdx.x * kBorderThreads + threadIdx.x;
+    if (it >= B.first[P.n_levels]) return;
+    int level = 1;
+    while (it >= B.first[level + 1]) ++level;
+    it -= B.first[level];
     const Level& L = P.lv[level];
     uint8_t* img = level_ptr(P.pyr, L, frame);
-    const int W = L.w + 2 * kEdge;
-    for (int rr = 0; rr < kBorderRows; ++rr) {
-        const int Y = blk * kBorderRows + rr;
-        if (Y >= L.rows) break;
+    if (it < 2 * kEdge * L.h) {
+        // one byte of the left / right frame of an interior row: consecutive threads write consecutive bytes
+        const int y = it / (2 * kEdge), k = it - y * 2 * kEdge;
+        const int X = k < kEdge ? k : L.w + k;                         // padded column
+        uint8_t* row = img + (long long)(kEdge + y) * L.pitch + kXPad;
+        row[X - kEdge] = row[reflect101(X - kEdge, L.w)];
+    } else {
+        it -= 2 * kEdge * L.h;
+        const int W = L.w + 2 * kEdge, nwx = (W + 3) >> 2;
+        const int rr = it / nwx, X0 = (it - rr * nwx) * 4;            // rr: 0..18 top rows, 19..37 bottom rows
+        const int Y = rr < kEdge ? rr : L.h + rr;                      // padded row index
         const int y = reflect101(Y - kEdge, L.h);
         const uint8_t* srow = img + (long long)(kEdge + y) * L.pitch + kXPad;
         uint8_t* drow = img + (long long)Y * L.pitch + kXPad - kEdge;
-        if (Y < kEdge || Y >= kEdge + L.h) {
-            for (int X = threadIdx.x; X < W; X += kBorderThreads) drow[X] = srow[reflect101(X - kEdge, L.w)];
-        } else if (threadIdx.x < 2 * kEdge) {
-            const int X = threadIdx.x < kEdge ? threadIdx.x : L.w + threadIdx.x;
-            drow[X] = srow[reflect101(X - kEdge, L.w)];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int X = X0 + k;
+            if (X < W) drow[X] = srow[reflect101(X - kEdge, L.w)];
         }
     }
 }
@@ -475,8 +483,10 @@ __global__ void __launch_bounds__(kSegThreads) k_fast_seg(const __grid_constant_
         if (!(fl & 1)) k = k && v > s[-1] && v > s[-kSegPitch - 1] && v > s[kSegPitch - 1];
         if (!(fl & 2)) k = k && v > s[1] && v > s[-kSegPitch + 1] && v > s[kSegPitch + 1];
         if (k) {
-            atomicOr(&bm_min[r * kBmWords + (px >> 5)], 1u << (px & 31));
-            if (v >= ini_th) atomicOr(&bm_ini[r * kBmWords + (px >> 5)], 1u << (px & 31));
+            // plain shared-memory reductions (atomicOr makes ptxas build a warp-aggregation loop that costs more than it saves here)
+            const uint32_t bit = 1u << (px & 31);
+            asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(smem_u32(&bm_min[r * kBmWords + (px >> 5)])), "r"(bit) : "memory");
+            if (v >= ini_th) asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(smem_u32(&bm_ini[r * kBmWords + (px >> 5)])), "r"(bit) : "memory");
         }
     }
     __syncthreads();
