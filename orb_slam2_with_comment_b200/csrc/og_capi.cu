@@ -415,11 +415,12 @@ int launch_extract(orbgpu_extractor* ex, const uint8_t* d_images, int batch, siz
     mark(0);
     {
         const og::Level& L = P.lv[0];
-        dim3 grid((L.pitch / 4 + 127) / 128, L.rows, batch);
-        og::k_level0<<<grid, 128, 0, st>>>(P, d_images, (long long)row_stride, (long long)frame_stride);
+        dim3 grid(((L.w + 15) / 16 + 63) / 64, L.h, batch);
+        og::k_level0<<<grid, 64, 0, st>>>(P, d_images, (long long)row_stride, (long long)frame_stride);
         ++launches;
     }
     bool generic = false;
+    (void)generic;
     for (int l = 1; l < P.n_levels; ++l) {
         const og::Level& L = P.lv[l];
         // the vectorised kernel needs the 4 outputs of a thread inside 12 source bytes: scale <= 2
@@ -434,11 +435,11 @@ int launch_extract(orbgpu_extractor* ex, const uint8_t* d_images, int batch, siz
         }
         ++launches;
     }
-    if (P.n_levels > 1 && !generic) {
+    {
+        // the generic resize writes its own frame; k_borders then only repeats it (and does level 0)
         og::BorderPlan bp;
         int acc = 0;
-        bp.first[0] = 0;
-        for (int l = 1; l < P.n_levels; ++l) {
+        for (int l = 0; l < P.n_levels; ++l) {
             bp.first[l] = acc;
             acc += 2 * og::kEdge * P.lv[l].h + 2 * og::kEdge * ((P.lv[l].w + 2 * og::kEdge + 3) / 4);
         }

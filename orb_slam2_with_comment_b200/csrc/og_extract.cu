@@ -23,26 +23,30 @@ __device__ __forceinline__ uint8_t* level_ptr(uint8_t* base, const Level& L, int
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Level 0: interior copy + BORDER_REFLECT_101 frame.  One thread writes 4 consecutive bytes of the padded row.
+// Level 0: copy of the input image into the interior of the level-0 buffer (the frame is written by k_borders).
+// One thread moves 16 pixels: the source row may start at any byte address, so it is read as five aligned words
+// realigned with funnel shifts, and stored as one 16-byte vector (the interior starts 16-byte aligned).
+// The last vector of a row is copied byte-wise so that nothing past the row's end is ever read.
 // ------------------------------------------------------------------------------------------------------------
 __global__ void k_level0(const __grid_constant__ ExtractParams P, const uint8_t* __restrict__ images, long long row_stride,
                          long long frame_stride) {
     const Level& L = P.lv[0];
     const int frame = P.frame0 + blockIdx.z;
-    const int Y = blockIdx.y;  // row of the bordered buffer
-    const int X4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (X4 >= L.pitch) return;
-    const int y = reflect101(Y - kEdge, L.h);
-    const uint8_t* src = images + (long long)frame * frame_stride + (long long)y * row_stride;
-    uint32_t out = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        int x = X4 + k - kXPad;
-        x = x < -kEdge ? -kEdge : (x > L.w + kEdge - 1 ? L.w + kEdge - 1 : x);
-        x = reflect101(x, L.w);
-        out |= (uint32_t)__ldg(src + x) << (8 * k);
+    const int y = blockIdx.y;
+    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    if (x >= L.w) return;
+    const uint8_t* src = images + (long long)frame * frame_stride + (long long)y * row_stride + x;
+    uint8_t* dst = level_ptr(P.pyr, L, frame) + (long long)(kEdge + y) * L.pitch + kXPad + x;
+    if (x + 20 <= L.w) {   // the five words reach at most byte x + 19 of the row
+        const int a = (int)(reinterpret_cast<uintptr_t>(src) & 3);
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(src - a);
+        const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2), w3 = __ldg(w + 3), w4 = __ldg(w + 4);
+        const int sh = 8 * a;
+        *reinterpret_cast<uint4*>(dst) = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh),
+                                                    __funnelshift_r(w3, w4, sh));
+    } else {
+        for (int k = 0; k < 16 && x + k < L.w; ++k) dst[k] = __ldg(src + k);
     }
-    *reinterpret_cast<uint32_t*>(level_ptr(P.pyr, L, frame) + (long long)Y * L.pitch + X4) = out;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -146,18 +150,18 @@ __global__ void __launch_bounds__(kResizeThreads) k_resize4(const __grid_constan
     }
 }
 
-// The BORDER_REFLECT_101 frame of levels 1.. (:1122-1123; level 0 gets its frame in k_level0).  Work items per level:
+// The BORDER_REFLECT_101 frame of every level (:1122-1123, :1127).  Work items per level:
 // 38*h "side" items (one byte of the frame left or right of an interior row) and 38 * ceil((w+38)/4) "cap"
 // items (one thread writes 4 bytes of a top/bottom row).  Item -> (level, kind) through the per-level prefix in `B`.
 constexpr int kBorderThreads = 128;
 struct BorderPlan {
-    int first[kMaxLevels + 1];   // first item of level l (levels 1..n-1), total at [n_levels]
+    int first[kMaxLevels + 1];   // first item of level l, total at [n_levels]
 };
 __global__ void __launch_bounds__(kBorderThreads) k_borders(const __grid_constant__ ExtractParams P, const __grid_constant__ BorderPlan B) {
     const int frame = P.frame0 + blockIdx.y;
     int it = blockIdx.x * kBorderThreads + threadIdx.x;
     if (it >= B.first[P.n_levels]) return;
-    int level = 1;
+    int level = 0;
     while (it >= B.first[level + 1]) ++level;
     it -= B.first[level];
     const Level& L = P.lv[level];
