@@ -848,19 +848,27 @@ struct orbgpu_matcher {
     int* d_nitems = nullptr;
     // grow-only scratch
     Scratch s_ctrl, s_topk, s_topk2, s_bin, s_items, s_grid_start, s_grid_items, s_res1, s_res2, s_out[5], s_in[2];
+    Scratch s_tmp[32];            // device copies of the caller's arrays in the host-pointer variants (grow-only, reused)
+    int tmp_next = 0;
     uint8_t* h_stage = nullptr;   // pinned staging for the per-call control arrays
     size_t h_stage_cap = 0;
 };
 
 namespace {
 
+// `pool` = the matcher whose scratch slots back the copy (temporary sets of the host-pointer variants), or null for an
+// allocation owned by the set (uploaded handles).
 template <class T>
-int upload_array(const T* host, size_t n, std::vector<void*>& owned, const T** out, cudaStream_t st) {
+int upload_array(const T* host, size_t n, std::vector<void*>& owned, const T** out, cudaStream_t st, orbgpu_matcher* pool = nullptr) {
     *out = nullptr;
     if (!host || n == 0) return ORBGPU_OK;
     void* d = nullptr;
-    OGM_CUDA(cudaMalloc(&d, n * sizeof(T)));
-    owned.push_back(d);
+    if (pool && pool->tmp_next < 32) {
+        OGM_CUDA(pool->s_tmp[pool->tmp_next++].grab(n * sizeof(T), &d));
+    } else {
+        OGM_CUDA(cudaMalloc(&d, n * sizeof(T)));
+        owned.push_back(d);
+    }
     OGM_CUDA(cudaMemcpyAsync(d, host, n * sizeof(T), cudaMemcpyHostToDevice, st));
     *out = (const T*)d;
     return ORBGPU_OK;
@@ -914,7 +922,7 @@ int check_matcher(orbgpu_matcher* m) {
     return ORBGPU_OK;
 }
 
-int build_frame_set(orbgpu_matcher* m, const orbgpu_frame_set* h, orbgpu_frame_set_dev* fs) {
+int build_frame_set(orbgpu_matcher* m, const orbgpu_frame_set* h, orbgpu_frame_set_dev* fs, orbgpu_matcher* pool = nullptr) {
     if (!h || h->n_frames < 0 || !h->kp_off || !h->desc) return og_fail(ORBGPU_ERR_ARG, "frame set: null kp_off/desc");
     fs->device = m->device;
     fs->n_frames = h->n_frames;
@@ -928,14 +936,14 @@ int build_frame_set(orbgpu_matcher* m, const orbgpu_frame_set* h, orbgpu_frame_s
     if (fs->max_kp > (int)og::kPosMask) return og_fail(ORBGPU_ERR_ARG, "frame set: more than 2^20-1 keypoints in one frame");
     cudaStream_t st = m->stream;
     int rc;
-    if ((rc = upload_array(h->kp_off, (size_t)h->n_frames + 1, fs->owned, &fs->v.kp_off, st))) return rc;
-    if ((rc = upload_array((const og::KeyPoint*)h->keys_un, (size_t)fs->nkp, fs->owned, &fs->v.keys, st))) return rc;
-    if ((rc = upload_array(h->desc, (size_t)fs->nkp * 32, fs->owned, &fs->v.desc, st))) return rc;
-    if ((rc = upload_array(h->u_right, (size_t)fs->nkp, fs->owned, &fs->v.u_right, st))) return rc;
-    if ((rc = upload_array(h->kp_flags, (size_t)fs->nkp, fs->owned, &fs->v.flags, st))) return rc;
+    if ((rc = upload_array(h->kp_off, (size_t)h->n_frames + 1, fs->owned, &fs->v.kp_off, st, pool))) return rc;
+    if ((rc = upload_array((const og::KeyPoint*)h->keys_un, (size_t)fs->nkp, fs->owned, &fs->v.keys, st, pool))) return rc;
+    if ((rc = upload_array(h->desc, (size_t)fs->nkp * 32, fs->owned, &fs->v.desc, st, pool))) return rc;
+    if ((rc = upload_array(h->u_right, (size_t)fs->nkp, fs->owned, &fs->v.u_right, st, pool))) return rc;
+    if ((rc = upload_array(h->kp_flags, (size_t)fs->nkp, fs->owned, &fs->v.flags, st, pool))) return rc;
     if (h->grid) {
         fs->has_grid = true;
-        if ((rc = upload_array(h->grid, (size_t)h->n_frames * 4, fs->owned, &fs->v.grid, st))) return rc;
+        if ((rc = upload_array(h->grid, (size_t)h->n_frames * 4, fs->owned, &fs->v.grid, st, pool))) return rc;
     }
     if (h->fv_node_off) {
         if (!h->fv_node_id || !h->fv_feat_off || !h->fv_feat) return og_fail(ORBGPU_ERR_ARG, "frame set: incomplete FeatureVector arrays");
@@ -951,10 +959,10 @@ int build_frame_set(orbgpu_matcher* m, const orbgpu_frame_set* h, orbgpu_frame_s
             fs->max_nodes = std::max(fs->max_nodes, a1 - a0);
             if (a1 < a0 || fs->h_ent_cnt[f] < 0) return og_fail(ORBGPU_ERR_ARG, "frame set: FeatureVector offsets not ascending");
         }
-        if ((rc = upload_array(h->fv_node_off, (size_t)h->n_frames + 1, fs->owned, &fs->v.node_off, st))) return rc;
-        if ((rc = upload_array(h->fv_node_id, (size_t)fs->nnodes, fs->owned, &fs->v.node_id, st))) return rc;
-        if ((rc = upload_array(h->fv_feat_off, (size_t)fs->nnodes + 1, fs->owned, &fs->v.feat_off, st))) return rc;
-        if ((rc = upload_array(h->fv_feat, (size_t)fs->nfeat, fs->owned, &fs->v.feat, st))) return rc;
+        if ((rc = upload_array(h->fv_node_off, (size_t)h->n_frames + 1, fs->owned, &fs->v.node_off, st, pool))) return rc;
+        if ((rc = upload_array(h->fv_node_id, (size_t)fs->nnodes, fs->owned, &fs->v.node_id, st, pool))) return rc;
+        if ((rc = upload_array(h->fv_feat_off, (size_t)fs->nnodes + 1, fs->owned, &fs->v.feat_off, st, pool))) return rc;
+        if ((rc = upload_array(h->fv_feat, (size_t)fs->nfeat, fs->owned, &fs->v.feat, st, pool))) return rc;
     }
     return ORBGPU_OK;
 }
@@ -1290,27 +1298,33 @@ int orbgpu_frame_set_release(orbgpu_frame_set_dev* fs) {
     return ORBGPU_OK;
 }
 
-int orbgpu_mappoint_set_upload(orbgpu_matcher* m, const orbgpu_mappoint_set* h, int n_frames, orbgpu_mappoint_set_dev** out) {
-    int rc = check_matcher(m);
-    if (rc) return rc;
-    if (!out || !h || n_frames < 0 || !h->mp_off) return og_fail(ORBGPU_ERR_ARG, "null argument");
-    *out = nullptr;
+static int build_mappoint_set(orbgpu_matcher* m, const orbgpu_mappoint_set* h, int n_frames, orbgpu_mappoint_set_dev* mp, orbgpu_matcher* pool) {
+    if (!h || n_frames < 0 || !h->mp_off) return og_fail(ORBGPU_ERR_ARG, "null argument");
     const int n = h->mp_off[n_frames];
     if (n && (!h->proj_x || !h->proj_y || !h->view_cos || !h->level || !h->flags || !h->desc))
         return og_fail(ORBGPU_ERR_ARG, "map-point set: null array");
-    orbgpu_mappoint_set_dev* mp = new orbgpu_mappoint_set_dev();
     mp->device = m->device; mp->n_frames = n_frames; mp->nmp = n;
     cudaStream_t st = m->stream;
-    rc = upload_array(h->mp_off, (size_t)n_frames + 1, mp->owned, &mp->v.mp_off, st);
-    if (!rc) rc = upload_array(h->proj_x, (size_t)n, mp->owned, &mp->v.proj_x, st);
-    if (!rc) rc = upload_array(h->proj_y, (size_t)n, mp->owned, &mp->v.proj_y, st);
-    if (!rc) rc = upload_array(h->proj_xr, (size_t)n, mp->owned, &mp->v.proj_xr, st);
-    if (!rc) rc = upload_array(h->view_cos, (size_t)n, mp->owned, &mp->v.view_cos, st);
-    if (!rc) rc = upload_array(h->level, (size_t)n, mp->owned, &mp->v.level, st);
-    if (!rc) rc = upload_array(h->flags, (size_t)n, mp->owned, &mp->v.flags, st);
-    if (!rc) rc = upload_array(h->desc, (size_t)n * 32, mp->owned, &mp->v.desc, st);
+    int rc = upload_array(h->mp_off, (size_t)n_frames + 1, mp->owned, &mp->v.mp_off, st, pool);
+    if (!rc) rc = upload_array(h->proj_x, (size_t)n, mp->owned, &mp->v.proj_x, st, pool);
+    if (!rc) rc = upload_array(h->proj_y, (size_t)n, mp->owned, &mp->v.proj_y, st, pool);
+    if (!rc) rc = upload_array(h->proj_xr, (size_t)n, mp->owned, &mp->v.proj_xr, st, pool);
+    if (!rc) rc = upload_array(h->view_cos, (size_t)n, mp->owned, &mp->v.view_cos, st, pool);
+    if (!rc) rc = upload_array(h->level, (size_t)n, mp->owned, &mp->v.level, st, pool);
+    if (!rc) rc = upload_array(h->flags, (size_t)n, mp->owned, &mp->v.flags, st, pool);
+    if (!rc) rc = upload_array(h->desc, (size_t)n * 32, mp->owned, &mp->v.desc, st, pool);
+    return rc;
+}
+
+int orbgpu_mappoint_set_upload(orbgpu_matcher* m, const orbgpu_mappoint_set* h, int n_frames, orbgpu_mappoint_set_dev** out) {
+    int rc = check_matcher(m);
+    if (rc) return rc;
+    if (!out) return og_fail(ORBGPU_ERR_ARG, "null out");
+    *out = nullptr;
+    orbgpu_mappoint_set_dev* mp = new orbgpu_mappoint_set_dev();
+    rc = build_mappoint_set(m, h, n_frames, mp, nullptr);
     if (!rc) {
-        cudaError_t e = cudaStreamSynchronize(st);
+        cudaError_t e = cudaStreamSynchronize(m->stream);
         if (e != cudaSuccess) rc = og_fail(ORBGPU_ERR_CUDA, std::string("upload: ") + cudaGetErrorString(e));
     }
     if (rc) { free_owned(mp->owned); delete mp; return rc; }
@@ -1392,9 +1406,10 @@ static int node_scan_host(orbgpu_matcher* m, const orbgpu_frame_set* set1, const
     if (n_pairs == 0) return ORBGPU_OK;
     if (!match_off || !match12 || !idx1) return og_fail(ORBGPU_ERR_ARG, "null match_off/match12/idx1");
     orbgpu_frame_set_dev A, B;
-    rc = build_frame_set(m, set1, &A);
+    m->tmp_next = 0;
+    rc = build_frame_set(m, set1, &A, m);
     const bool same = set1 == set2;
-    if (!rc && !same) rc = build_frame_set(m, set2, &B);
+    if (!rc && !same) rc = build_frame_set(m, set2, &B, m);
     // output extent: pair p writes match12[match_off[p] .. + keypoints of frame idx1[p])
     long long out_n = 0;
     if (!rc)
@@ -1464,9 +1479,11 @@ int orbgpu_search_by_projection(orbgpu_matcher* m, const orbgpu_frame_set* frame
     if (rc) return rc;
     if (!frames || !mps) return og_fail(ORBGPU_ERR_ARG, "null argument");
     orbgpu_frame_set_dev F;
-    orbgpu_mappoint_set_dev* M = nullptr;
-    rc = build_frame_set(m, frames, &F);
-    if (!rc) rc = orbgpu_mappoint_set_upload(m, mps, frames->n_frames, &M);
+    orbgpu_mappoint_set_dev Mset;
+    orbgpu_mappoint_set_dev* M = &Mset;
+    m->tmp_next = 0;
+    rc = build_frame_set(m, frames, &F, m);
+    if (!rc) rc = build_mappoint_set(m, mps, frames->n_frames, M, m);
     void* d[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     if (!rc) {
         const size_t sz[5] = {(size_t)std::max(F.nkp, 1) * 4, (size_t)std::max(M->nmp, 1) * 4, (size_t)std::max(M->nmp, 1) * 4,
@@ -1487,7 +1504,7 @@ int orbgpu_search_by_projection(orbgpu_matcher* m, const orbgpu_frame_set* frame
     cudaError_t se = cudaStreamSynchronize(m->stream);
     if (!rc && se != cudaSuccess) rc = og_fail(ORBGPU_ERR_CUDA, std::string("search: ") + cudaGetErrorString(se));
     free_owned(F.owned);
-    if (M) orbgpu_mappoint_set_release(M);
+    free_owned(Mset.owned);
     return rc;
 }
 
