@@ -713,9 +713,11 @@ __device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c) {   // uns
 __global__ void __launch_bounds__(kDescWarps * 32) k_orient_desc(const __grid_constant__ ExtractParams P, KeyPoint* __restrict__ kp_out,
                                                                  uint8_t* __restrict__ desc_out,
                                                                  int32_t* __restrict__ counts) {
-    __shared__ int8_t spx[512], spy[512];
+    // pattern point j of lane i (= bit_pattern_31_ point 16 i + j) at spat[j * 32 + i]: the 32 lanes of a load hit 32
+    // consecutive 8-byte slots (no bank conflicts), and the coordinates are already floats (no I2F in the sample loop)
+    __shared__ float2 spat[512];
     __shared__ __align__(16) uint8_t patch[kDescWarps][kPatchRows * kPatchPitch];
-    for (int i = threadIdx.x; i < 512; i += blockDim.x) { spx[i] = c_pat_x[i]; spy[i] = c_pat_y[i]; }
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) spat[(i & 15) * 32 + (i >> 4)] = make_float2((float)c_pat_x[i], (float)c_pat_y[i]);
     __syncthreads();
     const int frame = P.frame0 + blockIdx.y;
     const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
@@ -793,10 +795,10 @@ __global__ void __launch_bounds__(kDescWarps * 32) k_orient_desc(const __grid_co
         int val = 0;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            const int i0 = 16 * lane + 2 * k;
+            const float2 p0 = spat[(2 * k) * 32 + lane], p1 = spat[(2 * k + 1) * 32 + lane];
             int r0, q0, r1, q1;
-            brief_offset(spx[i0], spy[i0], a, b, &r0, &q0);
-            brief_offset(spx[i0 + 1], spy[i0 + 1], a, b, &r1, &q1);
+            brief_offset_f(p0.x, p0.y, a, b, &r0, &q0);
+            brief_offset_f(p1.x, p1.y, a, b, &r1, &q1);
             const int t0 = b0[r0 * kPatchPitch + q0], t1 = b0[r1 * kPatchPitch + q1];
             val |= (t0 < t1) << k;
         }

@@ -134,6 +134,20 @@ OGM_HD void brief_offset(int px, int py, float a, float b, int* row, int* col) {
     *col = round_rn(fsub(fmul(fx, a), fmul(fy, b)));
 }
 
+// The same with float pattern coordinates and cvRound done on the FMA pipe: for |v| < 2^22, v + 1.5 * 2^23 rounds v to
+// an integer (round-half-even, the FADD's own rounding = cvRound's) in the low mantissa bits.
+OGM_HD int round_rn_small(float v) {
+#if defined(__CUDA_ARCH__)
+    return __float_as_int(__fadd_rn(v, 12582912.f)) - 0x4B400000;
+#else
+    return (int)__builtin_lrintf(v);
+#endif
+}
+OGM_HD void brief_offset_f(float fx, float fy, float a, float b, int* row, int* col) {
+    *row = round_rn_small(fadd(fmul(fx, b), fmul(fy, a)));
+    *col = round_rn_small(fsub(fmul(fx, a), fmul(fy, b)));
+}
+
 // ---- ORBmatcher::DescriptorDistance (ORBmatcher.cc:1901-1917): 256-bit Hamming distance ----------------
 OGM_HD int popc32(uint32_t v) {
 #if defined(__CUDA_ARCH__)
