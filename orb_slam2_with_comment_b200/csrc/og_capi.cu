@@ -65,7 +65,6 @@ struct orbgpu_extractor {
     og::BlurTile* d_btiles = nullptr;
     uint32_t* d_ic_tab = nullptr;
     int n_btiles = 0;
-    bool fast_v1 = false;             // ORBGPU_FAST_V1=1: first-generation per-cell kernel (kept for A/B timing)
     CUtensorMap* d_tmaps = nullptr;   // [2][kMaxLevels]: FAST tile boxes over pyr, then (reserved) over blur
     int fast_smem = 0;
     og::Tap* d_taps = nullptr;
@@ -448,10 +447,7 @@ int launch_extract(orbgpu_extractor* ex, const uint8_t* d_images, int batch, siz
         ++launches;
     }
     mark(1);
-    if (ex->fast_v1)
-        og::k_fast_cells<<<dim3(P.total_cells, batch), og::kFastThreads, 0, st>>>(P);
-    else
-        og::k_fast_seg<<<dim3(P.n_segs, batch), og::kSegThreads, ex->fast_smem, st>>>(P, ex->d_tmaps);
+    og::k_fast_seg<<<dim3(P.n_segs, batch), og::kSegThreads, ex->fast_smem, st>>>(P, ex->d_tmaps);
     ++launches;
     mark(2);
     og::k_octree<<<dim3(P.n_levels, batch), og::kOctThreads, 0, st>>>(P);
@@ -543,7 +539,6 @@ int orbgpu_extractor_create(orbgpu_extractor** out, int device, int nfeatures, f
     alloc((void**)&ex->d_segs, ex->cap_cells * sizeof(og::Segment));
     alloc((void**)&ex->d_btiles, ex->cap_cells * sizeof(og::BlurTile));
     alloc((void**)&ex->d_tmaps, 2 * og::kMaxLevels * sizeof(CUtensorMap));
-    { const char* e = getenv("ORBGPU_FAST_V1"); ex->fast_v1 = e && e[0] == '1'; }
     alloc((void**)&ex->d_taps, ex->cap_taps * sizeof(og::Tap));
     alloc((void**)&ex->d_cell_count, ex->cap_cellcount * B * 4);
     alloc((void**)&ex->d_cand_xy, ex->cap_cand * B * 4);

@@ -1,10 +1,12 @@
 // og_extract.cu — CUDA kernels (sm_100a) of ORBextractor::operator() (ORBextractor.cc:1043-1132).
 //
-//   k_level0        copyMakeBorder of the input into level 0                         (:1127)
-//   k_resize        cv::resize INTER_LINEAR level l-1 -> l  + its reflect-101 border (:1120-1123)
-//   k_fast_cells    per-cell FAST-9/16 + 3x3 NMS + iniTh/minTh fallback              (:789-829)
+//   k_level0        the input image into the interior of level 0                     (:1127)
+//   k_resize4       cv::resize INTER_LINEAR level l-1 -> l, 4 pixels per thread       (:1120)
+//   k_resize        the same, any scale, one pass incl. frame (fallback for scale > 2)
+//   k_borders       BORDER_REFLECT_101 frame of every level                          (:1122-1128)
+//   k_fast_seg      per-cell FAST-9/16 + 3x3 NMS + iniTh/minTh fallback (TMA tiles)  (:789-829)
 //   k_octree        DistributeOctTree, one CTA per (frame, level)                    (:539-763)
-//   k_blur          GaussianBlur 7x7 sigma 2                                         (:1085-1086)
+//   k_blur_tma      GaussianBlur 7x7 sigma 2 (TMA tiles, DP4A)                       (:1085-1086)
 //   k_orient_desc   IC_Angle + rotated BRIEF + final KeyPoint fields                 (:77-147, :837-847, :1095-1103)
 //
 // Integer stencil / compaction / popcount work: no tensor cores.  All kernels are batched over frames.
@@ -189,113 +191,7 @@ __global__ void __launch_bounds__(kBorderThreads) k_borders(const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// FAST per cell.  One CTA per (cell, frame).  The score V is threshold-free, so one score map + one NMS pass +
-// a per-cell vote "any survivor with V >= iniTh?" reproduces FAST(iniTh) / fallback FAST(minTh) (:809-816).
-// Survivors are written in row-major order into the cell's private slot range (no atomics, deterministic).
-// ------------------------------------------------------------------------------------------------------------
-constexpr int kFastThreads = 128;
-
-__global__ void __launch_bounds__(kFastThreads) k_fast_cells(const __grid_constant__ ExtractParams P) {
-    __shared__ uint8_t tile[(kCellMax + 6) * kTileStride];
-    __shared__ uint8_t score[(kCellMax + 2) * kTileStride];
-    __shared__ int warp_tot[kFastThreads / 32];
-    __shared__ int any_ini;
-
-    const Cell c = P.cells[blockIdx.x];
-    const int frame = P.frame0 + blockIdx.y;
-    const Level& L = P.lv[c.level];
-    const int t = threadIdx.x;
-    const int tw = c.tw, th = c.th;
-    const int TW = tw + 6, TH = th + 6;
-
-    // tile: level pixels [x0-3, x0+tw+3) x [y0-3, y0+th+3)
-    const uint8_t* img = level_ptr(P.pyr, L, frame) + (long long)(kEdge + c.y0 - 3) * L.pitch + (kXPad + c.x0 - 3);
-    for (int i = t; i < TH * TW; i += kFastThreads) {
-        const int r = i / TW, q = i - r * TW;
-        tile[r * kTileStride + q] = __ldg(img + (long long)r * L.pitch + q);
-    }
-    for (int i = t; i < (th + 2) * kTileStride; i += kFastThreads) score[i] = 0;
-    if (t == 0) any_ini = 0;
-    __syncthreads();
-
-    const int min_th = P.min_th, ini_th = P.ini_th;
-    const int npx = tw * th;
-    for (int i = t; i < npx; i += kFastThreads) {
-        const int py = i / tw, px = i - py * tw;
-        const uint8_t* p = tile + (py + 3) * kTileStride + (px + 3);
-        const int v = p[0];
-        // necessary condition for 9 contiguous ring pixels beyond the threshold: at least two of the four
-        // compass pixels are (an arc of 9 always covers two of them)
-        const int d0 = v - p[3 * kTileStride], d4 = v - p[3], d8 = v - p[-3 * kTileStride], d12 = v - p[-3];
-        const int nb = (d0 > min_th) + (d4 > min_th) + (d8 > min_th) + (d12 > min_th);
-        const int nd = (d0 < -min_th) + (d4 < -min_th) + (d8 < -min_th) + (d12 < -min_th);
-        if (nb < 2 && nd < 2) continue;
-        int d[16];
-        d[0] = d0; d[4] = d4; d[8] = d8; d[12] = d12;
-        d[1] = v - p[3 * kTileStride + 1];  d[2] = v - p[2 * kTileStride + 2];  d[3] = v - p[kTileStride + 3];
-        d[5] = v - p[-kTileStride + 3];     d[6] = v - p[-2 * kTileStride + 2]; d[7] = v - p[-3 * kTileStride + 1];
-        d[9] = v - p[-3 * kTileStride - 1]; d[10] = v - p[-2 * kTileStride - 2]; d[11] = v - p[-kTileStride - 3];
-        d[13] = v - p[kTileStride - 3];     d[14] = v - p[2 * kTileStride - 2]; d[15] = v - p[3 * kTileStride - 1];
-        const int V = fast_score16(d);
-        if (V >= min_th) score[(py + 1) * kTileStride + (px + 1)] = (uint8_t)V;
-    }
-    __syncthreads();
-
-    // NMS (strict maximum over the 8 neighbours; pixels outside the cell's tested area count as 0) -> flag in
-    // `tile` (no longer needed): 0 = dropped, else the score
-    uint8_t* keep = tile;
-    int vote = 0;
-    for (int i = t; i < npx; i += kFastThreads) {
-        const int py = i / tw, px = i - py * tw;
-        const uint8_t* s = score + (py + 1) * kTileStride + (px + 1);
-        const int v = s[0];
-        bool k = v > 0 && v > s[-1] && v > s[1] && v > s[-kTileStride - 1] && v > s[-kTileStride] &&
-                 v > s[-kTileStride + 1] && v > s[kTileStride - 1] && v > s[kTileStride] && v > s[kTileStride + 1];
-        keep[i] = k ? (uint8_t)v : 0;
-        vote |= (k && v >= ini_th);
-    }
-    if (vote) any_ini = 1;   // benign race: every writer stores 1
-    __syncthreads();
-    const int th_eff = any_ini ? ini_th : min_th;
-
-    // ordered compaction: thread t owns pixels [t*chunk, (t+1)*chunk) in row-major order
-    const int chunk = (npx + kFastThreads - 1) / kFastThreads;
-    const int lo = min(t * chunk, npx), hi = min(lo + chunk, npx);
-    int cnt = 0;
-    for (int i = lo; i < hi; ++i) cnt += keep[i] >= th_eff && keep[i] > 0;
-    const int lane = t & 31, w = t >> 5;
-    int inc = cnt;
-#pragma unroll
-    for (int dlt = 1; dlt < 32; dlt <<= 1) {
-        const int u = __shfl_up_sync(0xffffffffu, inc, dlt);
-        if (lane >= dlt) inc += u;
-    }
-    if (lane == 31) warp_tot[w] = inc;
-    __syncthreads();
-    int base = 0, total = 0;
-#pragma unroll
-    for (int k = 0; k < kFastThreads / 32; ++k) {
-        if (k < w) base += warp_tot[k];
-        total += warp_tot[k];
-    }
-    int pos = base + inc - cnt;
-    uint32_t* oxy = P.cand_xy + (long long)frame * P.total_cand_cap + L.cand_base + c.slot;
-    uint8_t* orr = P.cand_resp + (long long)frame * P.total_cand_cap + L.cand_base + c.slot;
-    for (int i = lo; i < hi; ++i) {
-        const int v = keep[i];
-        if (v > 0 && v >= th_eff) {
-            const int py = i / tw, px = i - py * tw;
-            // coordinates relative to (minBorderX, minBorderY) = (16,16) as the reference stores them (:822-823)
-            oxy[pos] = ((uint32_t)(c.y0 + py - 16) << 16) | (uint32_t)(c.x0 + px - 16);
-            orr[pos] = (uint8_t)v;
-            ++pos;
-        }
-    }
-    if (t == 0) P.cell_count[(long long)frame * P.total_cells + blockIdx.x] = total;
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// FAST per cell, second generation: one CTA per (segment, frame), a segment being up to 8 consecutive cells of one
+// FAST per cell (:789-829): one CTA per (segment, frame), a segment being up to 8 consecutive cells of one
 // cell row.  The tile arrives by TMA.  The work is organised so that only the cheap rejection test touches every
 // pixel and everything expensive runs over a compacted queue:
 //   1. SWAR rejection test, 4 pixels per 32-bit word: a FAST-9 arc always covers two of the four compass ring

@@ -77,33 +77,8 @@ OGM_HD int blur_tap7(int a, int b, int c, int d, int e, int f, int g) {
 }
 OGM_HD uint8_t blur_finish(uint32_t acc) { return (uint8_t)((acc + 32768u) >> 16); }
 
-// ---- FAST-9/16 corner score (Appendix A.3) ------------------------------------------------------------
-// d[k] = I(p) - I(ring_k), k = 0..15 in ring order.  Returns V = max(A,B)-1 where A = max over the 16 arcs
-// of 9 contiguous ring pixels of min d, B the same for -d.  corner at threshold t <=> V >= t.
 OGM_HD int imin(int a, int b) { return a < b ? a : b; }
 OGM_HD int imax(int a, int b) { return a > b ? a : b; }
-OGM_HD int fast_score16(const int d[16]) {
-    int lo2[16], hi2[16], lo4[16], hi4[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        lo2[k] = imin(d[k], d[(k + 1) & 15]);
-        hi2[k] = imax(d[k], d[(k + 1) & 15]);
-    }
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        lo4[k] = imin(lo2[k], lo2[(k + 2) & 15]);
-        hi4[k] = imax(hi2[k], hi2[(k + 2) & 15]);
-    }
-    int A = -256, Bn = 256;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        const int lo9 = imin(imin(lo4[k], lo4[(k + 4) & 15]), d[(k + 8) & 15]);
-        const int hi9 = imax(imax(hi4[k], hi4[(k + 4) & 15]), d[(k + 8) & 15]);
-        A = imax(A, lo9);
-        Bn = imin(Bn, hi9);
-    }
-    return imax(A, -Bn) - 1;
-}
 
 // ---- cv::fastAtan2 (Appendix A.4); p1..p7 are the float products computed once on the host ---------------
 struct AtanCoef {

@@ -13,7 +13,6 @@ constexpr int kEdge = 19;        // EDGE_THRESHOLD (ORBextractor.cc:74): border 
 constexpr int kXPad = 32;        // the level interior starts at byte column kXPad (>= kEdge, keeps rows 32-B aligned)
 constexpr int kHalfPatch = 15;   // HALF_PATCH_SIZE (:73)
 constexpr int kCellMax = 64;     // upper bound of a cell's tested width/height (wCell < 60 by construction)
-constexpr int kTileStride = 72;  // shared-memory row stride of a FAST cell tile (>= kCellMax + 6, multiple of 8)
 
 // HBM layout of the pyramid: pyr[level][frame][rows][pitch] bytes, interior pixel (x,y) of a level at
 // row kEdge + y, column kXPad + x.  The 19-px BORDER_REFLECT_101 frame of the reference's level buffers

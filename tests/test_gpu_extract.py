@@ -172,3 +172,36 @@ def test_octree_stage_against_oracle(gpu, oracle):
         assert len(got) == len(exp)
         for f in ("x", "y", "response"):
             assert np.array_equal(got[f], exp[f]), f"iteration {it} field {f}"
+
+
+def test_full_size_batch_properties(oracle):
+    """BASELINE size (KITTI 1241x376, 2000 features) at a full 512-frame batch: size-independent properties instead of
+    512 oracle runs — every copy of a frame inside the batch gives byte-identical results wherever it sits (chunk and
+    stream boundaries of the pipelined host path included), the device-resident and host-pointer paths agree, and a
+    sample of frames equals the oracle."""
+    import torch
+    from orb_slam2_with_comment_b200 import ORBextractor
+    w, h, nf, B, D = 1241, 376, 2000, 512, 8
+    base = np.stack([synth.g_rects(w, h, 300 + i) for i in range(D)])
+    imgs = np.ascontiguousarray(base[np.arange(B) % D])
+    ex = ORBextractor(nf, 1.2, 8, 20, 7, max_width=w, max_height=h, max_batch=B)
+    kp, desc, cnt = ex.extract_batch(imgs)
+    for f in range(D, B):
+        r = f % D
+        assert cnt[f] == cnt[r] and kp[f, :cnt[f]].tobytes() == kp[r, :cnt[r]].tobytes() and np.array_equal(desc[f, :cnt[f]], desc[r, :cnt[r]]), f
+    dev = torch.device("cuda", 0)
+    d_img = torch.from_numpy(imgs).to(dev)
+    d_kp = torch.zeros(B * ex.kp_cap * 28, dtype=torch.uint8, device=dev)
+    d_desc = torch.zeros(B * ex.kp_cap * 32, dtype=torch.uint8, device=dev)
+    d_cnt = torch.zeros(B, dtype=torch.int32, device=dev)
+    ex.extract_batch_dev(d_img.data_ptr(), B, w, h, d_kp.data_ptr(), d_desc.data_ptr(), d_cnt.data_ptr())
+    ex.sync()
+    assert np.array_equal(d_cnt.cpu().numpy(), cnt)
+    dk = d_kp.cpu().numpy().reshape(B, ex.kp_cap, 28)
+    for f in (0, 77, 511):
+        assert dk[f, :cnt[f]].tobytes() == kp[f, :cnt[f]].tobytes()
+    o = ol.Extractor(oracle, "orbo", nf, 1.2, 8, 20, 7)
+    for f in (3, 6):
+        ekp, edesc = o.extract(base[f])
+        compare_final(kp[f, :cnt[f]], desc[f, :cnt[f]], ekp, edesc, f"full batch frame {f}")
+    ex.close()
