@@ -120,6 +120,17 @@ int orbgpu_extractor_read_blurred(orbgpu_extractor* ex, int frame, int level, ui
 int orbgpu_octree(orbgpu_extractor* ex, const orbgpu_keypoint* candidates, int n, int min_x, int max_x, int min_y,
                   int max_y, int n_features, orbgpu_keypoint* out, int capacity, int* n_out);
 
+/* Frame::ComputeStereoMatches (Frame.cc:501-675) for every stereo pair of the last call: `left` and `right` are two
+ * extractors on the same device that have just processed the left and the right images of the same batch (same image size,
+ * same parameters); their key points, descriptors and pyramids are consumed where they lie in HBM — no pyramid download.
+ * u_right / depth receive mvuRight / mvDepth: entry f*out_stride + i belongs to key point i of left frame f, -1 = no match
+ * (entries beyond the frame's key-point count are not written).  mb / mbf are Frame::mb / Frame::mbf. */
+int orbgpu_stereo_matches(orbgpu_extractor* left, orbgpu_extractor* right, float mb, float mbf, float* u_right, float* depth,
+                          int out_stride);
+/* The same with device output pointers, enqueued on the left extractor's stream (orbgpu_extractor_sync(left) waits). */
+int orbgpu_stereo_matches_dev(orbgpu_extractor* left, orbgpu_extractor* right, float mb, float mbf, float* u_right_dev,
+                              float* depth_dev, int out_stride);
+
 
 /* ------------------------------------------------------------------------------------------------
  * Matching — replaces the Hamming path of ORBmatcher (ORBmatcher.h:37-102)

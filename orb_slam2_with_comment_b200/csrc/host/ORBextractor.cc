@@ -93,4 +93,15 @@ void ORBextractor::operator()(cv::InputArray _image, cv::InputArray /*_mask*/, s
     }
 }
 
+void ORBextractor::ComputeStereoMatches(ORBextractor* pLeft, ORBextractor* pRight, int N, float mb, float mbf,
+                                        std::vector<float>& mvuRight, std::vector<float>& mvDepth) {
+    mvuRight = std::vector<float>(N, -1.0f);   // Frame.cc:503-504
+    mvDepth = std::vector<float>(N, -1.0f);
+    if (N == 0 || !pLeft->mpHandle || !pRight->mpHandle) return;
+    const int cap = orbgpu_extractor_max_keypoints(pLeft->mpHandle);
+    std::vector<float> u(cap, -1.0f), d(cap, -1.0f);
+    check(orbgpu_stereo_matches(pLeft->mpHandle, pRight->mpHandle, mb, mbf, u.data(), d.data(), cap), "stereo matching failed");
+    for (int i = 0; i < N && i < cap; ++i) { mvuRight[i] = u[i]; mvDepth[i] = d[i]; }
+}
+
 }  // namespace ORB_SLAM2

@@ -50,6 +50,14 @@ public:
     std::vector<cv::Mat> mvImagePyramid;
     void SetPyramidDownload(bool on) { mbDownloadPyramid = on; }
 
+    // Frame::ComputeStereoMatches (Frame.cc:501-675) on the device: pLeft / pRight are the two extractors that have just
+    // processed the left and right image of the frame (Frame.cc:78-83); fills mvuRight / mvDepth for the N left key points.
+    // In Frame.cc the body of ComputeStereoMatches() becomes
+    //     ORBextractor::ComputeStereoMatches(mpORBextractorLeft, mpORBextractorRight, N, mb, mbf, mvuRight, mvDepth);
+    // and the pyramids never leave the GPU (SetPyramidDownload(false) on both).
+    static void ComputeStereoMatches(ORBextractor* pLeft, ORBextractor* pRight, int N, float mb, float mbf,
+                                     std::vector<float>& mvuRight, std::vector<float>& mvDepth);
+
     // Device placement of instances created afterwards (default: device 0).
     static void SetDevice(int device);
 

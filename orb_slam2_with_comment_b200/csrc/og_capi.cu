@@ -15,6 +15,7 @@
 
 #include "../../include/orbgpu.h"
 #include "og_extract.cu"
+#include "og_stereo.cuh"
 
 namespace {
 
@@ -75,6 +76,16 @@ struct orbgpu_extractor {
     uint8_t* d_desc = nullptr;
     size_t cap_pyr = 0, cap_cells = 0, cap_taps = 0, cap_cand = 0, cap_sel = 0, cap_ot = 0, cap_cellcount = 0;
     int last_batch = 0, last_launches = 0;
+    // results of the last call as they sit on the device (consumed by orbgpu_stereo_matches)
+    const og::KeyPoint* last_kp = nullptr;
+    const uint8_t* last_desc = nullptr;
+    const int32_t* last_counts = nullptr;
+    int last_stride = 0;
+    // stereo scratch (grow-only) and the event that orders the partner extractor's stream before ours
+    int32_t *d_st_rows = nullptr, *d_st_items = nullptr, *d_st_sad = nullptr;
+    float *d_st_u = nullptr, *d_st_d = nullptr;
+    size_t st_cap_rows = 0, st_cap_items = 0, st_cap_kp = 0;
+    cudaEvent_t ev_peer = nullptr;
     // optional per-stage timing (cudaEvents on the launching stream)
     bool profiling = false;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -463,6 +474,10 @@ int launch_extract(orbgpu_extractor* ex, const uint8_t* d_images, int batch, siz
     OG_CUDA(cudaGetLastError());
     ex->last_batch = batch;
     ex->last_launches = launches;
+    ex->last_kp = d_kp;
+    ex->last_desc = d_desc;
+    ex->last_counts = d_counts;
+    ex->last_stride = kp_capacity;
     return ORBGPU_OK;
 }
 
@@ -598,7 +613,8 @@ int orbgpu_extractor_destroy(orbgpu_extractor* ex) {
     for (cudaEvent_t e : ex->ev_out) cudaEventDestroy(e);
     if (ex->ev_begin) cudaEventDestroy(ex->ev_begin);
     for (int i = 0; i < 6; ++i) if (ex->ev[i]) cudaEventDestroy(ex->ev[i]);
-    void* ptrs[] = {ex->d_ic_tab, ex->d_btiles, ex->d_segs, ex->d_tmaps, ex->d_pyr, ex->d_blur, ex->d_images, ex->d_cells, ex->d_taps, ex->d_cell_count, ex->d_cand_xy,
+    if (ex->ev_peer) cudaEventDestroy(ex->ev_peer);
+    void* ptrs[] = {ex->d_st_rows, ex->d_st_items, ex->d_st_sad, ex->d_st_u, ex->d_st_d, ex->d_ic_tab, ex->d_btiles, ex->d_segs, ex->d_tmaps, ex->d_pyr, ex->d_blur, ex->d_images, ex->d_cells, ex->d_taps, ex->d_cell_count, ex->d_cand_xy,
                     ex->d_cand_resp, ex->d_ot, ex->d_sel_xy, ex->d_sel_resp, ex->d_sel_count, ex->d_counts, ex->d_kp, ex->d_desc};
     for (void* p : ptrs) if (p) cudaFree(p);
     delete ex;
@@ -880,6 +896,90 @@ int orbgpu_octree(orbgpu_extractor* ex, const orbgpu_keypoint* candidates, int n
         k.response = (float)orr[i];
         out[i] = k;
     }
+    return ORBGPU_OK;
+}
+
+// ---- Frame::ComputeStereoMatches (Frame.cc:501-675) ---------------------------------------------------------------
+static int stereo_launch(orbgpu_extractor* L, orbgpu_extractor* R, float mb, float mbf, float* d_u, float* d_d, int out_stride) {
+    if (!L || !R) return fail(ORBGPU_ERR_ARG, "null extractor");
+    if (L->device != R->device) return fail(ORBGPU_ERR_ARG, "left and right extractor live on different devices");
+    if (L->last_batch < 1 || L->last_batch != R->last_batch || L->cur_w != R->cur_w || L->cur_h != R->cur_h || L->nlevels != R->nlevels ||
+        L->last_stride != R->last_stride || !L->last_kp || !R->last_kp)
+        return fail(ORBGPU_ERR_ARG, "stereo matching needs the left and right extractor to have just processed equally sized batches of equally sized images");
+    if (!(mb > 0.f) || out_stride < L->last_stride) return fail(ORBGPU_ERR_ARG, "bad mb or output stride");
+    if (L->last_stride > (int)og::kPosMask) return fail(ORBGPU_ERR_ARG, "too many key points per frame");
+    OG_CUDA(cudaSetDevice(L->device));
+    const int B = L->last_batch, n_rows = L->P.lv[0].h;
+    const int band = 2 * (int)std::ceil(2.0 * R->scale[R->nlevels - 1]) + 3;
+    const size_t items_cap = (size_t)R->last_stride * band;
+    auto grow = [&](void** p, size_t& cap, size_t want, size_t elt) -> cudaError_t {
+        if (want <= cap) return cudaSuccess;
+        if (*p) cudaFree(*p);
+        *p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(p, want * elt);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    };
+    OG_CUDA(cudaStreamSynchronize(L->stream));   // scratch may still be in use by an earlier stereo call
+    OG_CUDA(grow((void**)&L->d_st_rows, L->st_cap_rows, (size_t)B * (n_rows + 1), 4));
+    OG_CUDA(grow((void**)&L->d_st_items, L->st_cap_items, (size_t)B * items_cap, 4));
+    if ((size_t)B * L->last_stride > L->st_cap_kp) {
+        if (L->d_st_sad) cudaFree(L->d_st_sad);
+        if (L->d_st_u) cudaFree(L->d_st_u);
+        if (L->d_st_d) cudaFree(L->d_st_d);
+        L->d_st_sad = nullptr; L->d_st_u = nullptr; L->d_st_d = nullptr; L->st_cap_kp = 0;
+        OG_CUDA(cudaMalloc((void**)&L->d_st_sad, (size_t)B * L->last_stride * 4));
+        OG_CUDA(cudaMalloc((void**)&L->d_st_u, (size_t)B * L->last_stride * 4));
+        OG_CUDA(cudaMalloc((void**)&L->d_st_d, (size_t)B * L->last_stride * 4));
+        L->st_cap_kp = (size_t)B * L->last_stride;
+    }
+    if (!L->ev_peer) OG_CUDA(cudaEventCreateWithFlags(&L->ev_peer, cudaEventDisableTiming));
+    OG_CUDA(cudaEventRecord(L->ev_peer, R->stream));
+    OG_CUDA(cudaStreamWaitEvent(L->stream, L->ev_peer, 0));
+
+    og::StereoArgs A;
+    A.PL = L->P; A.PR = R->P;
+    A.PL.frame0 = 0; A.PR.frame0 = 0;
+    A.kpL = L->last_kp; A.kpR = R->last_kp;
+    A.descL = L->last_desc; A.descR = R->last_desc;
+    A.cntL = L->last_counts; A.cntR = R->last_counts;
+    A.kp_stride = L->last_stride;
+    A.n_rows = n_rows;
+    A.max_d = mbf / mb;   // :527-528
+    A.mbf = mbf;
+    for (int l = 0; l < og::kMaxLevels; ++l) A.inv_scale[l] = l < L->nlevels ? L->inv_scale[l] : 0.f;
+    A.row_start = L->d_st_rows;
+    A.row_items = L->d_st_items;
+    A.items_cap = (int)items_cap;
+    A.u_right = d_u ? d_u : L->d_st_u;
+    A.depth = d_d ? d_d : L->d_st_d;
+    A.sad = L->d_st_sad;
+    A.out_stride = d_u ? out_stride : L->last_stride;
+    cudaStream_t st = L->stream;
+    const size_t smem = (size_t)(n_rows + 1) * 4;
+    if (smem > 48 * 1024) return fail(ORBGPU_ERR_ARG, "image too tall for the row index");
+    og::k_stereo_rows<<<B, og::kStereoThreads, smem, st>>>(A);
+    og::k_stereo_match<<<dim3((L->last_stride + og::kStereoThreads / 32 - 1) / (og::kStereoThreads / 32), B), og::kStereoThreads, 0, st>>>(A);
+    og::k_stereo_filter<<<B, og::kStereoThreads, 0, st>>>(A);
+    OG_CUDA(cudaGetLastError());
+    L->last_launches = 3;
+    return ORBGPU_OK;
+}
+
+int orbgpu_stereo_matches_dev(orbgpu_extractor* left, orbgpu_extractor* right, float mb, float mbf, float* u_right_dev, float* depth_dev,
+                              int out_stride) {
+    if (!u_right_dev || !depth_dev) return fail(ORBGPU_ERR_ARG, "null output");
+    return stereo_launch(left, right, mb, mbf, u_right_dev, depth_dev, out_stride);
+}
+
+int orbgpu_stereo_matches(orbgpu_extractor* left, orbgpu_extractor* right, float mb, float mbf, float* u_right, float* depth, int out_stride) {
+    if (!u_right || !depth) return fail(ORBGPU_ERR_ARG, "null output");
+    int rc = stereo_launch(left, right, mb, mbf, nullptr, nullptr, out_stride);
+    if (rc) return rc;
+    const int B = left->last_batch, s = left->last_stride;
+    OG_CUDA(cudaMemcpy2DAsync(u_right, (size_t)out_stride * 4, left->d_st_u, (size_t)s * 4, (size_t)s * 4, B, cudaMemcpyDeviceToHost, left->stream));
+    OG_CUDA(cudaMemcpy2DAsync(depth, (size_t)out_stride * 4, left->d_st_d, (size_t)s * 4, (size_t)s * 4, B, cudaMemcpyDeviceToHost, left->stream));
+    OG_CUDA(cudaStreamSynchronize(left->stream));
     return ORBGPU_OK;
 }
 

@@ -82,6 +82,17 @@ class ORBextractor:
         capi.check(self._lib.orbgpu_extract_batch_dev(self._h, images_ptr, B, W, H, W, W * H, kp_ptr, desc_ptr, self.kp_cap,
                                                       counts_ptr))
 
+    # ---- Frame::ComputeStereoMatches (Frame.cc:501-675): self = left extractor, both have just processed the same batch
+    def stereo_matches(self, right: "ORBextractor", mb: float, mbf: float, batch: int = 1):
+        """Returns (mvuRight, mvDepth) as (batch, kp_cap) float32 arrays (-1 = no stereo match)."""
+        ur = np.full((batch, self.kp_cap), -1, np.float32)
+        dp = np.full((batch, self.kp_cap), -1, np.float32)
+        capi.check(self._lib.orbgpu_stereo_matches(self._h, right._h, mb, mbf, ur.ctypes.data, dp.ctypes.data, self.kp_cap))
+        return ur, dp
+
+    def stereo_matches_dev(self, right: "ORBextractor", mb: float, mbf: float, u_right_ptr: int, depth_ptr: int):
+        capi.check(self._lib.orbgpu_stereo_matches_dev(self._h, right._h, mb, mbf, u_right_ptr, depth_ptr, self.kp_cap))
+
     def sync(self):
         capi.check(self._lib.orbgpu_extractor_sync(self._h))
 

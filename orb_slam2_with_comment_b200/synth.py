@@ -238,3 +238,15 @@ def epipolar_partner(kp1: np.ndarray, F: np.ndarray, rs, w: int, h: int, noise: 
     out["x"] = np.clip(fx - s * b / nrm + e * a / nrm, 0, w - 1).astype(np.float32)
     out["y"] = np.clip(fy + s * a / nrm + e * b / nrm, 0, h - 1).astype(np.float32)
     return out
+
+
+def stereo_pair(w: int, h: int, seed: int, d0: int = 6, bands: int = 9):
+    """A rectified stereo pair: left = G_rects(seed); right = left shifted left by a disparity that is constant inside each of
+    `bands` horizontal bands (d0 .. d0 + bands - 1 px), so a point at uL appears at uR = uL - d in the same row."""
+    left = g_rects(w, h, seed)
+    right = np.empty_like(left)
+    bh = (h + bands - 1) // bands
+    for b in range(bands):
+        y0, y1 = b * bh, min((b + 1) * bh, h)
+        right[y0:y1] = np.roll(left[y0:y1], -(d0 + b), axis=1)
+    return left, right

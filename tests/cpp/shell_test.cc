@@ -20,6 +20,9 @@ void* orbo_create(int, float, int, int, int);
 void orbo_destroy(void*);
 int orbo_extract(void*, const uint8_t*, int, int, int, void*, int, uint8_t*);
 int orbo_get_level(void*, int, int, uint8_t*);
+void orbs_stereo_matches(const orbgpu_keypoint*, const uint8_t*, int, const orbgpu_keypoint*, const uint8_t*, int, const uint8_t* const*,
+                         const uint8_t* const*, const int32_t*, const int32_t*, const float*, const float*, int, float, float, float*, float*,
+                         int32_t*);
 void orbm_search_by_projection(const orbgpu_frame_set*, const orbgpu_mappoint_set*, const float*, int, float, float, int32_t*, int32_t*,
                                int32_t*, int32_t*, int32_t*);
 void orbm_search_for_triangulation(const orbgpu_frame_set*, const orbgpu_frame_set*, int, const int32_t*, const int32_t*, const float*,
@@ -96,6 +99,45 @@ static void test_extractor() {
     e.ExtractORB(&ex, cv::Mat());
     EXPECT(e.mvKeys.size() == 3, "empty image must leave the outputs alone");
     orbo_destroy(o);
+}
+
+// what the stereo Frame constructor does (Frame.cc:78-100): both extractors, then ComputeStereoMatches
+static void test_stereo() {
+    const int W = 752, H = 480;
+    ORBextractor exL(1200, 1.2f, 8, 20, 7), exR(1200, 1.2f, 8, 20, 7);
+    cv::Mat left = synth_image(W, H), right(H, W, CV_8UC1);
+    for (int y = 0; y < H; ++y) {
+        const int d = 6 + (y / 60) % 9;
+        for (int x = 0; x < W; ++x) right.at<uchar>(y, x) = left.at<uchar>(y, (x + d) % W);
+    }
+    MiniFrame fl, fr;
+    fl.ExtractORB(&exL, left);
+    fr.ExtractORB(&exR, right);
+    const int N = (int)fl.mvKeys.size(), Nr = (int)fr.mvKeys.size();
+    std::vector<float> mvuRight, mvDepth;
+    const float mb = 0.11f, mbf = 47.9f;
+    ORBextractor::ComputeStereoMatches(&exL, &exR, N, mb, mbf, mvuRight, mvDepth);
+    // oracle on the same key points / descriptors / pyramids (copied out of the ROI views into packed buffers)
+    std::vector<std::vector<uint8_t> > pl(8), pr(8);
+    const uint8_t *ppl[8], *ppr[8];
+    int32_t lw[8], lh[8];
+    for (int l = 0; l < 8; ++l) {
+        const cv::Mat &a = exL.mvImagePyramid[l], &b = exR.mvImagePyramid[l];
+        lw[l] = a.cols; lh[l] = a.rows;
+        pl[l].resize((size_t)a.rows * a.cols); pr[l].resize((size_t)a.rows * a.cols);
+        for (int y = 0; y < a.rows; ++y) { std::memcpy(&pl[l][(size_t)y * a.cols], a.ptr(y), a.cols); std::memcpy(&pr[l][(size_t)y * a.cols], b.ptr(y), a.cols); }
+        ppl[l] = pl[l].data(); ppr[l] = pr[l].data();
+    }
+    std::vector<uint8_t> dl((size_t)N * 32), dr((size_t)Nr * 32);
+    for (int i = 0; i < N; ++i) std::memcpy(&dl[(size_t)i * 32], fl.mDescriptors.ptr(i), 32);
+    for (int i = 0; i < Nr; ++i) std::memcpy(&dr[(size_t)i * 32], fr.mDescriptors.ptr(i), 32);
+    std::vector<float> sc = exL.GetScaleFactors(), isc = exL.GetInverseScaleFactors(), eu(N), ed(N);
+    orbs_stereo_matches((const orbgpu_keypoint*)fl.mvKeys.data(), dl.data(), N, (const orbgpu_keypoint*)fr.mvKeys.data(), dr.data(), Nr, ppl, ppr, lw,
+                        lh, sc.data(), isc.data(), 8, mb, mbf, eu.data(), ed.data(), nullptr);
+    int matched = 0;
+    for (int i = 0; i < N; ++i) matched += eu[i] >= 0;
+    EXPECT(mvuRight == eu && mvDepth == ed && matched > N / 4, "ComputeStereoMatches: %d of %d matched, vectors %s", matched, N,
+           mvuRight == eu ? "equal" : "differ");
 }
 
 // ---- matcher fixtures ----
@@ -296,6 +338,7 @@ int main() {
         return thrown == 2 ? 3 : 1;
     }
     test_extractor();
+    test_stereo();
     test_matcher();
     printf(fails ? "shell_test: %d FAILURES\n" : "shell_test: all shell results equal the oracle (%d failures)\n", fails);
     return fails ? 1 : 0;

@@ -246,3 +246,34 @@ class MatcherOracle:
                                       int(self.mbCheckOrientation), self.TH_LOW, int(kf_frame), int(not kf_frame), off.ctypes.data,
                                       m12.ctypes.data, nm.ctypes.data, threads)
         return sec, int(nm.sum())
+
+
+# ---- stereo oracle (oracle/stereo_oracle.cc) ----------------------------------------------------------------
+def stereo_inputs(lib, img_l, img_r, nfeatures, nlevels=8):
+    """Extracts both images with the extractor port and returns everything Frame::ComputeStereoMatches reads."""
+    out = {}
+    for side, img in (("L", img_l), ("R", img_r)):
+        ex = Extractor(lib, "orbo", nfeatures, 1.2, nlevels, 20, 7)
+        kp, desc = ex.extract(img)
+        out["kp" + side], out["desc" + side] = kp, desc
+        out["pyr" + side] = [np.ascontiguousarray(ex.level(l)) for l in range(nlevels)]
+        out["tables"] = ex.tables()[0]
+    return out
+
+
+def stereo_matches(lib, S, mb, mbf):
+    kpL, kpR = np.ascontiguousarray(S["kpL"]), np.ascontiguousarray(S["kpR"])
+    dL, dR = np.ascontiguousarray(S["descL"]), np.ascontiguousarray(S["descR"])
+    nl = len(S["pyrL"])
+    PL = (C.c_void_p * nl)(*[p.ctypes.data for p in S["pyrL"]])
+    PR = (C.c_void_p * nl)(*[p.ctypes.data for p in S["pyrR"]])
+    lw = np.array([p.shape[1] for p in S["pyrL"]], np.int32)
+    lh = np.array([p.shape[0] for p in S["pyrL"]], np.int32)
+    sc, isc = np.ascontiguousarray(S["tables"][0]), np.ascontiguousarray(S["tables"][1])
+    ur, dp, sad = np.zeros(len(kpL), np.float32), np.zeros(len(kpL), np.float32), np.zeros(len(kpL), np.int32)
+    lib.orbs_stereo_matches.restype = None
+    lib.orbs_stereo_matches.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.orbs_stereo_matches(kpL.ctypes.data, dL.ctypes.data, len(kpL), kpR.ctypes.data, dR.ctypes.data, len(kpR), PL, PR, lw.ctypes.data,
+                            lh.ctypes.data, sc.ctypes.data, isc.ctypes.data, nl, mb, mbf, ur.ctypes.data, dp.ctypes.data, sad.ctypes.data)
+    return ur, dp, sad
