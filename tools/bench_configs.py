@@ -132,6 +132,19 @@ out({"config": 3, "what": f"{P} KITTI stereo pairs: extraction of {2 * (P + 1)} 
      "(synthetic 10x10 vocabulary, no MapPoints, mono, checkOri off)", "extract_images_per_s": 2 * (P + 1) / ms_ex * 1e3, "pairs_per_s": P / ms_m * 1e3,
      "match_ms": ms_m, "distance_evals": int(evals), "matches_per_pair": float(dn.float().mean().item())})
 m.release(h); m.close(); ex.close()
+# stereo matching of the same pairs (Frame::ComputeStereoMatches), two extractor instances as in the stereo Frame constructor
+exL = ORBextractor(NF, 1.2, 8, 20, 7, max_width=W, max_height=H, max_batch=P)
+exR = ORBextractor(NF, 1.2, 8, 20, 7, max_width=W, max_height=H, max_batch=P)
+fnL, *_ = extract_dev(exL, left[:P], W, H)
+fnR, *_ = extract_dev(exR, right[:P], W, H)
+fnL(); fnR(); exL.sync(); exR.sync()
+d_u = torch.zeros(P * exL.kp_cap, dtype=torch.float32, device=dev)
+d_d = torch.zeros(P * exL.kp_cap, dtype=torch.float32, device=dev)
+fn = lambda: exL.stereo_matches_dev(exR, 0.537, 386.1448, d_u.data_ptr(), d_d.data_ptr())
+ms_s = ev_time(exL.stream(), fn, args.reps, exL.sync)
+out({"config": "3-stereo", "what": f"Frame::ComputeStereoMatches for {P} KITTI stereo pairs (device-resident key points, descriptors, pyramids)",
+     "pairs_per_s": P / ms_s * 1e3, "ms": ms_s, "stereo_matches_per_pair": float((d_u >= 0).sum().item()) / P})
+exL.close(); exR.close()
 
 # ---- #4 -------------------------------------------------------------------------------------------------------------
 W, H, NF = 752, 480, 1200
