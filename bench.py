@@ -69,6 +69,19 @@ def algorithmic_bytes():
 MATCH_N, MATCH_SETS = 2000, 256
 
 
+def _pinned(a: np.ndarray) -> np.ndarray:
+    """The same array in page-locked host memory (numpy view of a pinned torch tensor), so H2D copies run at PCIe speed."""
+    import torch
+    if not torch.cuda.is_available():
+        return a
+    t = torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).pin_memory()
+    _PIN_KEEP.append(t)   # the numpy view does not own the memory
+    return t.numpy().view(a.dtype).reshape(a.shape)
+
+
+_PIN_KEEP = []
+
+
 def make_match_workload(pairs: int):
     """Brute-force 2000 x 2000 keyframe pairs: SearchByBoW(KF1,KF2) semantics with one node holding all indices,
     nnratio 0.75, checkOri on.  `pairs` pairs are formed from MATCH_SETS distinct descriptor-set pairs (A_i, B_i)."""
@@ -80,8 +93,8 @@ def make_match_workload(pairs: int):
     kA = np.zeros(n_sets * MATCH_N, synth.KP_DTYPE); kA["angle"] = angA.ravel()
     kB = np.zeros(n_sets * MATCH_N, synth.KP_DTYPE); kB["angle"] = angB.ravel()
     fl = np.ones(n_sets * MATCH_N, np.uint8)
-    sA = FrameSet.single_node(kp_off, kA, A.reshape(-1, 32), kp_flags=fl)
-    sB = FrameSet.single_node(kp_off, kB, B.reshape(-1, 32), kp_flags=fl)
+    sA = FrameSet.single_node(kp_off, _pinned(kA), _pinned(A.reshape(-1, 32)), kp_flags=fl)
+    sB = FrameSet.single_node(kp_off, _pinned(kB), _pinned(B.reshape(-1, 32)), kp_flags=fl)
     i1 = (np.arange(pairs) % n_sets).astype(np.int32)
     off, total = match_offsets(sA, i1)
     return sA, sB, i1, i1.copy(), off, total

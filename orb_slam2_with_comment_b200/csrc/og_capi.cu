@@ -666,7 +666,9 @@ int orbgpu_extract_batch(orbgpu_extractor* ex, const uint8_t* images, int batch,
     if (!images || !kp_out || !desc_out || !counts) return fail(ORBGPU_ERR_ARG, "null pointer");
     cudaStream_t st = ex->stream;
     // Chunked pipeline: H2D (s_h2d) -> kernels (stream) -> D2H (s_d2h), chained by events per chunk.
-    const int chunk = batch <= 96 ? batch : 64;
+    static const int chunk_env = []() { const char* e = getenv("ORBGPU_CHUNK"); return e ? atoi(e) : 0; }();
+    const int chunk_pref = chunk_env > 0 ? chunk_env : 64;
+    const int chunk = batch <= chunk_pref + chunk_pref / 2 ? batch : chunk_pref;
     const int nchunks = (batch + chunk - 1) / chunk;
     while ((int)ex->ev_in.size() < nchunks) {
         cudaEvent_t a, b;
