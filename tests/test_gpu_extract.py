@@ -205,3 +205,24 @@ def test_full_size_batch_properties(oracle):
         ekp, edesc = o.extract(base[f])
         compare_final(kp[f, :cnt[f]], desc[f, :cnt[f]], ekp, edesc, f"full batch frame {f}")
     ex.close()
+
+
+@pytest.mark.parametrize("w,h,nf,nlevels,scale,ini,mn", [
+    (1920, 1080, 5000, 8, 1.2, 20, 7),     # full-HD, larger quota: wider cell rows, more segments per row, more blur tiles
+    (801, 601, 1500, 5, 1.5, 30, 10),      # odd sizes, fewer levels, other thresholds
+    (1000, 700, 1200, 3, 2.5, 20, 7),      # scale > 2: the generic resize kernel (the vectorised one needs scale <= 2)
+    (500, 700, 600, 4, 1.3, 12, 5),        # portrait: nIni = round(w/h) = 1 (taller than 2:1 is rejected, the reference divides by zero there)
+])
+def test_other_geometries_vs_oracle(oracle, w, h, nf, nlevels, scale, ini, mn):
+    from orb_slam2_with_comment_b200 import ORBextractor
+    g = ORBextractor(nf, scale, nlevels, ini, mn, max_width=w, max_height=h)
+    o = ol.Extractor(oracle, "orbo", nf, scale, nlevels, ini, mn)
+    for seed, gen in ((11, synth.g_rects), (12, synth.g_blurnoise)):
+        img = gen(w, h, seed)
+        kp, desc = g(img)
+        ekp, edesc = o.extract(img)
+        for l in range(nlevels):
+            assert np.array_equal(g.level(l, bordered=True), o.level(l, True)), f"pyramid level {l}"
+        compare_final(kp, desc, ekp, edesc, f"{w}x{h} seed {seed}")
+        assert len(kp) > nf // 2
+    g.close()
