@@ -468,7 +468,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=512)
+    ap.add_argument("--batch", type=int, default=1024)
     ap.add_argument("--match-pairs", type=int, default=4096, help="brute-force keyframe pairs per GPU per step (matching leg)")
     ap.add_argument("--no-matching", action="store_true")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
