@@ -181,6 +181,21 @@ typedef struct orbgpu_mappoint_set {
     const uint8_t* desc;       /* GetDescriptor(), 32 B each                                  */
 } orbgpu_mappoint_set;
 
+/* Queries of the generic windowed search: one per projected map point, already reduced to what the search loop reads.
+ * Frame f owns queries [q_off[f], q_off[f+1]) in the reference's loop order. */
+typedef struct orbgpu_window_query_set {
+    const int32_t* q_off;      /* [n_frames+1]                                                                              */
+    const float* u;            /* projection, the x / y arguments of Frame::GetFeaturesInArea (Frame.cc:353)                */
+    const float* v;
+    const float* radius;       /* its r argument (th * mvScaleFactors[level], ORBmatcher.cc:1598, :1760)                    */
+    const int32_t* min_level;  /* its minLevel / maxLevel arguments (-1 = unbounded above)                                  */
+    const int32_t* max_level;
+    const float* ur;           /* u - mbf * invzc, checked against mvuRight of the candidate (:1624-1630); NULL = no check   */
+    const uint8_t* flags;      /* bit0: the query is live (passed the projection tests), bit2: its MapPoint has observations */
+    const uint8_t* desc;       /* pMP->GetDescriptor(), 32 B each                                                           */
+    const float* angle;        /* angle of the query's key point in its own frame (rotation histogram); NULL if unused       */
+} orbgpu_window_query_set;
+
 int orbgpu_matcher_create(orbgpu_matcher** out, int device);
 int orbgpu_matcher_destroy(orbgpu_matcher* m);
 int orbgpu_matcher_sync(orbgpu_matcher* m);
@@ -220,6 +235,20 @@ int orbgpu_hamming_pairs(orbgpu_matcher* m, const uint8_t* a, const uint8_t* b, 
 int orbgpu_search_by_projection(orbgpu_matcher* m, const orbgpu_frame_set* frames, const orbgpu_mappoint_set* mps,
                                 const float* scale_factors, int n_levels, float th, float nnratio, int32_t* kp_match,
                                 int32_t* mp_best_idx, int32_t* mp_best_dist, int32_t* mp_second_dist, int32_t* nmatches);
+
+/* The search loop shared by ORBmatcher::SearchByProjection(Frame&, const Frame&, th, bMono) (ORBmatcher.cc:1540-1685) and
+ * SearchByProjection(Frame&, KeyFrame*, const set<MapPoint*>&, th, ORBdist) (:1711-1833), for every frame of `frames`
+ * (the CurrentFrame side) against its slice of `queries` (the projected map points; the pose arithmetic that produces them
+ * stays in the C++ shell).  Per query: candidates = Frame::GetFeaturesInArea(u, v, radius, min_level, max_level); skip key
+ * points holding a MapPoint with observations (kp_flags == 1; with skip_any_mappoint != 0 any MapPoint, kp_flags != 0) and the
+ * stereo-inconsistent ones; best = smallest distance, first encountered; accept when best <= th_dist; the key point then
+ * holds the query's MapPoint (later queries see that); optional rotation histogram with removal outside the three main bins.
+ *   kp_match[total key points]  -1 untouched, >= 0 index (within the frame's query slice) of the MapPoint assigned last,
+ *                               -2 reset to NULL by the rotation check (:1676, :1825)
+ *   q_best_idx / q_best_dist [total queries] (may be NULL), nmatches[n_frames] the functions' return values */
+int orbgpu_search_windowed(orbgpu_matcher* m, const orbgpu_frame_set* frames, const orbgpu_window_query_set* queries, int th_dist,
+                           int skip_any_mappoint, int check_orientation, int32_t* kp_match, int32_t* q_best_idx, int32_t* q_best_dist,
+                           int32_t* nmatches);
 
 /* ORBmatcher::SearchForTriangulation (ORBmatcher.cc:783-975) for n_pairs keyframe pairs; pair p matches frame
  * idx1[p] of set1 against frame idx2[p] of set2.  kp_flags bit0 = the keypoint already has a MapPoint (skipped,

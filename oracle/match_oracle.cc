@@ -178,6 +178,65 @@ void orbm_search_by_projection(const orbgpu_frame_set* fs, const orbgpu_mappoint
     }
 }
 
+// The search loop of SearchByProjection(Frame&, const Frame&, th, bMono) (ORBmatcher.cc:1581-1684) and of
+// SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist) (:1760-1832) over already projected queries.
+void orbm_search_windowed(const orbgpu_frame_set* fs, const orbgpu_window_query_set* qs, int th_dist, int skip_any, int check_orientation,
+                          int32_t* kp_match, int32_t* q_best_idx, int32_t* q_best_dist, int32_t* nmatches_out) {
+    for (int f = 0; f < fs->n_frames; ++f) {
+        const int k0 = fs->kp_off[f], n = fs->kp_off[f + 1] - k0;
+        const orbgpu_keypoint* keys = fs->keys_un + k0;
+        const float* g = fs->grid + 4 * f;
+        Grid G;
+        assign_grid(keys, n, g, G);
+        std::vector<uint8_t> state(n, 0);   // 0: NULL, 1: MapPoint with observations, 2: MapPoint without
+        if (fs->kp_flags) for (int i = 0; i < n; ++i) state[i] = fs->kp_flags[k0 + i];
+        for (int i = 0; i < n; ++i) if (kp_match) kp_match[k0 + i] = -1;
+        int nmatches = 0;
+        std::vector<int> rotHist[HISTO_LENGTH];
+        std::vector<int> vIndices2;
+        for (int q = qs->q_off[f]; q < qs->q_off[f + 1]; ++q) {
+            if (q_best_idx) q_best_idx[q] = -1;
+            if (q_best_dist) q_best_dist[q] = 256;
+            if (!(qs->flags[q] & 1)) continue;
+            const float u = qs->u[q], v = qs->v[q], radius = qs->radius[q];
+            features_in_area(G, keys, g, u, v, radius, qs->min_level[q], qs->max_level[q], vIndices2);
+            if (vIndices2.empty()) continue;
+            const uint8_t* dMP = qs->desc + (size_t)q * 32;
+            int bestDist = 256, bestIdx2 = -1;
+            for (size_t j = 0; j < vIndices2.size(); ++j) {
+                const int i2 = vIndices2[j];
+                if (state[i2] == 1 || (skip_any && state[i2] != 0)) continue;   // :1619-1621 / :1776-1777
+                if (qs->ur && fs->u_right && fs->u_right[k0 + i2] > 0) {         // :1624-1630
+                    const float er = fabs(qs->ur[q] - fs->u_right[k0 + i2]);
+                    if (er > radius) continue;
+                }
+                const int dist = descriptor_distance(dMP, fs->desc + (size_t)(k0 + i2) * 32);
+                if (dist < bestDist) { bestDist = dist; bestIdx2 = i2; }
+            }
+            if (q_best_idx) q_best_idx[q] = bestIdx2;
+            if (q_best_dist) q_best_dist[q] = bestDist;
+            if (bestDist <= th_dist) {
+                state[bestIdx2] = (qs->flags[q] & 4) ? 1 : 2;                   // CurrentFrame.mvpMapPoints[bestIdx2] = pMP
+                if (kp_match) kp_match[k0 + bestIdx2] = q - qs->q_off[f];
+                nmatches++;
+                if (check_orientation) rotHist[rot_bin(qs->angle[q], keys[bestIdx2].angle)].push_back(bestIdx2);
+            }
+        }
+        if (check_orientation) {
+            int ind1 = -1, ind2 = -1, ind3 = -1;
+            three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+            for (int i = 0; i < HISTO_LENGTH; i++) {
+                if (i == ind1 || i == ind2 || i == ind3) continue;
+                for (size_t j = 0; j < rotHist[i].size(); j++) {
+                    if (kp_match) kp_match[k0 + rotHist[i][j]] = -2;            // reset to NULL
+                    nmatches--;
+                }
+            }
+        }
+        if (nmatches_out) nmatches_out[f] = nmatches;
+    }
+}
+
 // ORBmatcher::SearchForTriangulation, ORBmatcher.cc:783-975
 void orbm_search_for_triangulation(const orbgpu_frame_set* s1, const orbgpu_frame_set* s2, int n_pairs, const int32_t* idx1v,
                                    const int32_t* idx2v, const float* f12, const float* epipole, const float* scale,

@@ -509,9 +509,24 @@ __global__ void __launch_bounds__(32) k_tri_finalize(const __grid_constant__ Tri
 constexpr int kGridCells = kGridCols * kGridRows;
 constexpr int kGridThreads = 256;
 
+// Queries of the generic windowed search (orbgpu_window_query_set): explicit window and level range per query.
+struct WindowQueryView {
+    const int32_t* q_off;
+    const float *u, *v, *radius, *ur, *angle;
+    const int32_t *min_level, *max_level;
+    const uint8_t* flags;
+    const uint8_t* desc;
+};
+
 struct SbpArgs {
     FrameSetView F;
     MapPointView M;
+    WindowQueryView W;
+    int generic;           // 0: SearchByProjection(Frame&, vector<MapPoint*>&, th) queries from M; 1: queries from W
+    int skip_any;          // generic: candidates holding ANY MapPoint are skipped (:1776), else only those with observations (:1619-1621)
+    int th_dist;           // generic: accept when best <= th_dist
+    int check_orientation; // generic: rotation histogram
+    int8_t* q_bin;         // generic: [total queries] histogram bin of the accepted query, -1 otherwise
     int n_frames;
     const float* scale;
     float th, nnratio;
@@ -591,8 +606,8 @@ __global__ void __launch_bounds__(kGridThreads) k_grid_build(const __grid_consta
 }
 
 struct SbpQuery {
-    bool live;
-    int f, k0, lvl;
+    bool live, use_xr;
+    int f, k0, lvl, min_level, max_level;
     float x, y, rs, xr;
     int minx, maxx, miny, maxy;
 };
@@ -603,15 +618,30 @@ __device__ __forceinline__ SbpQuery sbp_query(const SbpArgs& A, int q, int f) {
     Q.live = false;
     Q.f = f;
     Q.k0 = A.F.kp_off[f];
-    const int fl = A.M.flags[q];
-    if (!(fl & 1) || (fl & 2)) return Q;   // !mbTrackInView || isBad()
-    Q.lvl = A.M.level[q];
-    float r = ((double)A.M.view_cos[q] > 0.998) ? 2.5f : 4.0f;   // RadiusByViewingCos (:157-163)
-    if (A.th != 1.0f) r = __fmul_rn(r, A.th);
-    Q.rs = __fmul_rn(r, A.scale[Q.lvl]);
-    Q.x = A.M.proj_x[q];
-    Q.y = A.M.proj_y[q];
-    Q.xr = A.M.proj_xr ? A.M.proj_xr[q] : 0.f;
+    if (A.generic) {
+        if (!(A.W.flags[q] & 1)) return Q;
+        Q.lvl = 0;
+        Q.min_level = A.W.min_level[q];
+        Q.max_level = A.W.max_level[q];
+        Q.rs = A.W.radius[q];
+        Q.x = A.W.u[q];
+        Q.y = A.W.v[q];
+        Q.use_xr = A.W.ur != nullptr;
+        Q.xr = Q.use_xr ? A.W.ur[q] : 0.f;
+    } else {
+        const int fl = A.M.flags[q];
+        if (!(fl & 1) || (fl & 2)) return Q;   // !mbTrackInView || isBad()
+        Q.lvl = A.M.level[q];
+        Q.min_level = Q.lvl - 1;
+        Q.max_level = Q.lvl;
+        float r = ((double)A.M.view_cos[q] > 0.998) ? 2.5f : 4.0f;   // RadiusByViewingCos (:157-163)
+        if (A.th != 1.0f) r = __fmul_rn(r, A.th);
+        Q.rs = __fmul_rn(r, A.scale[Q.lvl]);
+        Q.x = A.M.proj_x[q];
+        Q.y = A.M.proj_y[q];
+        Q.use_xr = true;
+        Q.xr = A.M.proj_xr ? A.M.proj_xr[q] : 0.f;
+    }
     const float* g = A.F.grid + 4 * f;
     Q.minx = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(Q.x, g[0]), Q.rs), g[2])));
     if (Q.minx >= kGridCols) return Q;
@@ -637,7 +667,7 @@ __device__ __forceinline__ int sbp_scan_warp(const SbpArgs& A, const SbpQuery& Q
     const int ny = Q.maxy - Q.miny + 1, ncell = (Q.maxx - Q.minx + 1) * ny;
     const int32_t* cs = A.cell_start + (long long)Q.f * (kGridCells + 1);
     const int32_t* items = A.cell_items + Q.k0;
-    const int minLevel = Q.lvl - 1, maxLevel = Q.lvl;
+    const int minLevel = Q.min_level, maxLevel = Q.max_level;
     const bool check_levels = (minLevel > 0) || (maxLevel >= 0);
     int base = 0, evals = 0;
     for (int c0 = 0; c0 < ncell; c0 += 32) {
@@ -664,9 +694,12 @@ __device__ __forceinline__ int sbp_scan_warp(const SbpArgs& A, const SbpQuery& Q
                 if (maxLevel >= 0 && kp.octave > maxLevel) continue;
             }
             if (!(fabsf(__fsub_rn(kp.x, Q.x)) < Q.rs && fabsf(__fsub_rn(kp.y, Q.y)) < Q.rs)) continue;
-            if (A.F.flags && A.F.flags[Q.k0 + idx] == 1) continue;        // holds a MapPoint with observations (:108-110)
+            if (A.F.flags) {   // holds a MapPoint with observations (:108-110, :1619-1621) / any MapPoint (:1776)
+                const int st = A.F.flags[Q.k0 + idx];
+                if (st == 1 || (A.skip_any && st != 0)) continue;
+            }
             if (blocked && ((blocked[idx >> 5] >> (idx & 31)) & 1u)) continue;
-            if (A.F.u_right && A.F.u_right[Q.k0 + idx] > 0.f) {            // (:113-118)
+            if (Q.use_xr && A.F.u_right && A.F.u_right[Q.k0 + idx] > 0.f) {   // (:113-118, :1624-1630)
                 const float er = fabsf(__fsub_rn(Q.xr, A.F.u_right[Q.k0 + idx]));
                 if (er > Q.rs) continue;
             }
@@ -686,11 +719,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_sbp_topk(const __grid_c
     const int q = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     int evals = 0;
     if (q < total_mp) {
-        const int f = upper_slot_i32(A.M.mp_off, 0, A.n_frames, q);
+        const int f = upper_slot_i32(A.generic ? A.W.q_off : A.M.mp_off, 0, A.n_frames, q);
         const SbpQuery Q = sbp_query(A, q, f);
         uint32_t out[kTopK] = {kEmptyKey, kEmptyKey, kEmptyKey, kEmptyKey};
         int32_t outi[kTopK] = {-1, -1, -1, -1};
-        if (Q.live) evals = sbp_scan_warp(A, Q, load_desc(A.M.desc, q), nullptr, out, outi);
+        if (Q.live) evals = sbp_scan_warp(A, Q, load_desc(A.generic ? A.W.desc : A.M.desc, q), nullptr, out, outi);
         if ((threadIdx.x & 31) == 0) {
             *reinterpret_cast<uint4*>(A.topk_key + (long long)q * kTopK) = make_uint4(out[0], out[1], out[2], out[3]);
             *reinterpret_cast<int4*>(A.topk_idx + (long long)q * kTopK) = make_int4(outi[0], outi[1], outi[2], outi[3]);
@@ -778,6 +811,115 @@ __global__ void __launch_bounds__(32) k_sbp_select(const __grid_constant__ SbpAr
     }
     if (lane == 0) {
         if (A.nmatches) A.nmatches[f] = nacc;
+        if (evals) atomicAdd(A.evals, (unsigned long long)evals);
+    }
+}
+
+// Phase B of the generic windowed search, one warp per frame: queries in order, best candidate only, accept when
+// best <= th_dist, CurrentFrame.mvpMapPoints[bestIdx2] = pMP (:1644, :1789), rotation histogram over the accepted queries and
+// removal of the matches outside the three main bins (:1663-1682: the key point is reset to NULL -> kp_match = -2).
+__global__ void __launch_bounds__(32) k_win_select(const __grid_constant__ SbpArgs A) {
+    extern __shared__ uint32_t smem_b[];
+    uint32_t* blocked = smem_b;
+    int* hist = (int*)(smem_b + A.blocked_words);
+    const int lane = threadIdx.x, f = blockIdx.x;
+    const int k0 = A.F.kp_off[f], n = A.F.kp_off[f + 1] - k0;
+    for (int i = lane; i < (n + 31) / 32; i += 32) blocked[i] = 0;
+    hist[lane] = 0;
+    if (A.kp_match) for (int i = lane; i < n; i += 32) A.kp_match[k0 + i] = -1;
+    __syncwarp();
+    const int q0 = A.W.q_off[f], q1 = A.W.q_off[f + 1];
+    int nacc = 0, evals = 0;
+    for (int base = q0; base < q1; base += 32) {
+        const int q = base + lane;
+        uint32_t k[kTopK] = {kEmptyKey, kEmptyKey, kEmptyKey, kEmptyKey};
+        int ci[kTopK] = {-1, -1, -1, -1};
+        float ca[kTopK] = {0.f, 0.f, 0.f, 0.f}, qa = 0.f;
+        int fl = 0;
+        if (q < q1) {
+            const uint4 v = *reinterpret_cast<const uint4*>(A.topk_key + (long long)q * kTopK);
+            const int4 vi = *reinterpret_cast<const int4*>(A.topk_idx + (long long)q * kTopK);
+            k[0] = v.x; k[1] = v.y; k[2] = v.z; k[3] = v.w;
+            ci[0] = vi.x; ci[1] = vi.y; ci[2] = vi.z; ci[3] = vi.w;
+            fl = A.W.flags[q];
+            A.q_bin[q] = -1;
+            if (A.check_orientation) {
+                qa = A.W.angle[q];
+#pragma unroll
+                for (int j = 0; j < kTopK; ++j)
+                    if (ci[j] >= 0) ca[j] = A.F.keys[k0 + ci[j]].angle;
+            }
+        }
+        const int cnt_chunk = min(32, q1 - base);
+        for (int l = 0; l < cnt_chunk; ++l) {
+            uint32_t kk[kTopK];
+            int cc[kTopK];
+            float aa[kTopK];
+#pragma unroll
+            for (int j = 0; j < kTopK; ++j) {
+                kk[j] = __shfl_sync(0xffffffffu, k[j], l);
+                cc[j] = __shfl_sync(0xffffffffu, ci[j], l);
+                aa[j] = __shfl_sync(0xffffffffu, ca[j], l);
+            }
+            const int qfl = __shfl_sync(0xffffffffu, fl, l);
+            const float qang = __shfl_sync(0xffffffffu, qa, l);
+            const int qq = base + l;
+            int bestIdx = -1, d1 = 256;
+            float bang = 0.f;
+            bool complete = false, rescanned = false;
+#pragma unroll
+            for (int j = 0; j < kTopK; ++j) {
+                if (bestIdx >= 0 || complete) break;
+                if (kk[j] == kEmptyKey) { complete = true; break; }
+                const int idx = cc[j];
+                if ((blocked[idx >> 5] >> (idx & 31)) & 1u) continue;
+                bestIdx = idx; d1 = (int)(kk[j] >> kPosBits); bang = aa[j];
+            }
+            if (bestIdx < 0 && !complete) {
+                const SbpQuery Q = sbp_query(A, qq, f);
+                uint32_t out[kTopK];
+                int32_t outi[kTopK];
+                evals += sbp_scan_warp(A, Q, load_desc(A.W.desc, qq), blocked, out, outi);
+                rescanned = true;
+                if (out[0] != kEmptyKey) { bestIdx = outi[0]; d1 = (int)(out[0] >> kPosBits); }
+            }
+            const bool accept = bestIdx >= 0 && d1 <= A.th_dist;
+            if (accept) {
+                int bin = 0;
+                if (A.check_orientation) bin = rot_bin(qang, rescanned ? A.F.keys[k0 + bestIdx].angle : bang);
+                if (lane == 0) {
+                    // the key point now holds pMP: later candidates skip it if pMP has observations, or always under skip_any
+                    if ((qfl & 4) || A.skip_any) blocked[bestIdx >> 5] |= 1u << (bestIdx & 31);
+                    if (A.kp_match) A.kp_match[k0 + bestIdx] = qq - q0;
+                    A.q_bin[qq] = (int8_t)bin;
+                    hist[bin] += 1;
+                }
+            }
+            if (lane == 0) {
+                if (A.mp_best_idx) A.mp_best_idx[qq] = bestIdx;
+                if (A.mp_best_dist) A.mp_best_dist[qq] = d1;
+            }
+            nacc += accept;
+            __syncwarp();
+        }
+    }
+    __syncwarp();
+    int removed = 0;
+    if (A.check_orientation) {
+        int ind1, ind2, ind3;
+        three_maxima(hist, kHisto, ind1, ind2, ind3);
+        for (int q = q0 + lane; q < q1; q += 32) {
+            const int bin = A.q_bin[q];
+            if (bin >= 0 && bin != ind1 && bin != ind2 && bin != ind3) {
+                if (A.kp_match && A.mp_best_idx) A.kp_match[k0 + A.mp_best_idx[q]] = -2;
+                ++removed;
+            }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) removed += __shfl_xor_sync(0xffffffffu, removed, d);
+    }
+    if (lane == 0) {
+        if (A.nmatches) A.nmatches[f] = nacc - removed;
         if (evals) atomicAdd(A.evals, (unsigned long long)evals);
     }
 }
@@ -1140,6 +1282,7 @@ int sbp_dev(orbgpu_matcher* m, const orbgpu_frame_set_dev* fs, const orbgpu_mapp
     int rc = C.upload(&dc);
     if (rc) return rc;
     SbpArgs A;
+    memset(&A, 0, sizeof(A));
     A.F = fs->v; A.M = mp->v;
     A.n_frames = fs->n_frames;
     A.scale = (const float*)(dc + os);
@@ -1174,6 +1317,97 @@ int sbp_dev(orbgpu_matcher* m, const orbgpu_frame_set_dev* fs, const orbgpu_mapp
     OGM_CUDA(cudaEventRecord(m->ev1, st));
     OGM_CUDA(cudaGetLastError());
     return ORBGPU_OK;
+}
+
+// Generic windowed search (host pointers): the query arrays are uploaded into pooled scratch, the frame set likewise.
+int win_host(orbgpu_matcher* m, const orbgpu_frame_set* frames, const orbgpu_window_query_set* qs, int th_dist, int skip_any,
+             int check_orientation, int32_t* kp_match, int32_t* q_best_idx, int32_t* q_best_dist, int32_t* nmatches) {
+    using namespace og;
+    m->last_launches = 0;
+    if (!frames || !qs || !qs->q_off) return og_fail(ORBGPU_ERR_ARG, "null argument");
+    if (!frames->grid) return og_fail(ORBGPU_ERR_ARG, "windowed search needs the frame set's grid parameters");
+    const int nf = frames->n_frames;
+    if (nf == 0) return ORBGPU_OK;
+    const int nq = qs->q_off[nf];
+    if (nq && (!qs->u || !qs->v || !qs->radius || !qs->min_level || !qs->max_level || !qs->flags || !qs->desc || (check_orientation && !qs->angle)))
+        return og_fail(ORBGPU_ERR_ARG, "window query set: null array");
+    orbgpu_frame_set_dev F;
+    std::vector<void*> owned;
+    m->tmp_next = 0;
+    int rc = build_frame_set(m, frames, &F, m);
+    SbpArgs A;
+    memset(&A, 0, sizeof(A));
+    cudaStream_t st = m->stream;
+    if (!rc) rc = upload_array(qs->q_off, (size_t)nf + 1, owned, &A.W.q_off, st, m);
+    if (!rc) rc = upload_array(qs->u, (size_t)nq, owned, &A.W.u, st, m);
+    if (!rc) rc = upload_array(qs->v, (size_t)nq, owned, &A.W.v, st, m);
+    if (!rc) rc = upload_array(qs->radius, (size_t)nq, owned, &A.W.radius, st, m);
+    if (!rc) rc = upload_array(qs->ur, (size_t)nq, owned, &A.W.ur, st, m);
+    if (!rc) rc = upload_array(qs->angle, (size_t)nq, owned, &A.W.angle, st, m);
+    if (!rc) rc = upload_array(qs->min_level, (size_t)nq, owned, &A.W.min_level, st, m);
+    if (!rc) rc = upload_array(qs->max_level, (size_t)nq, owned, &A.W.max_level, st, m);
+    if (!rc) rc = upload_array(qs->flags, (size_t)nq, owned, &A.W.flags, st, m);
+    if (!rc) rc = upload_array(qs->desc, (size_t)nq * 32, owned, &A.W.desc, st, m);
+    void* d[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    void* ptr = nullptr;
+    cudaError_t ce = cudaSuccess;
+    if (!rc) {
+        const size_t sz[5] = {(size_t)std::max(F.nkp, 1) * 4, (size_t)std::max(nq, 1) * 4, (size_t)std::max(nq, 1) * 4, (size_t)std::max(nq, 1), (size_t)nf * 4};
+        for (int i = 0; i < 5 && ce == cudaSuccess; ++i) ce = m->s_out[i].grab(sz[i], &d[i]);
+        if (ce == cudaSuccess) ce = m->s_grid_start.grab((size_t)nf * (kGridCells + 1) * 4, &ptr);
+        A.cell_start = (int32_t*)ptr;
+        if (ce == cudaSuccess) ce = m->s_grid_items.grab((size_t)std::max(F.nkp, 1) * 4, &ptr);
+        A.cell_items = (int32_t*)ptr;
+        if (ce == cudaSuccess) ce = m->s_topk.grab((size_t)std::max(nq, 1) * kTopK * 4, &ptr);
+        A.topk_key = (uint32_t*)ptr;
+        if (ce == cudaSuccess) ce = m->s_topk2.grab((size_t)std::max(nq, 1) * kTopK * 4, &ptr);
+        A.topk_idx = (int32_t*)ptr;
+        if (ce != cudaSuccess) rc = og_fail(ORBGPU_ERR_CUDA, std::string("scratch: ") + cudaGetErrorString(ce));
+    }
+    if (!rc) {
+        A.F = F.v;
+        A.n_frames = nf;
+        A.generic = 1;
+        A.skip_any = skip_any;
+        A.th_dist = th_dist;
+        A.check_orientation = check_orientation;
+        A.kp_match = (int32_t*)d[0];
+        A.mp_best_idx = (int32_t*)d[1];
+        A.mp_best_dist = (int32_t*)d[2];
+        A.q_bin = (int8_t*)d[3];
+        A.nmatches = (int32_t*)d[4];
+        A.blocked_words = (F.max_kp + 31) / 32 + 1;
+        A.evals = m->d_evals;
+        const size_t smem = ((size_t)A.blocked_words + 32) * 4;
+        if (smem > 200 * 1024) rc = og_fail(ORBGPU_ERR_CAPACITY, "frame too large for the shared-memory blocked mask");
+        if (!rc) {
+            cudaEventRecord(m->ev0, st);
+            cudaMemsetAsync(m->d_evals, 0, 8, st);
+            k_grid_build<<<nf, kGridThreads, 0, st>>>(A);
+            if (nq > 0) k_sbp_topk<<<(nq + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock * 32, 0, st>>>(A, nq);
+            if (smem > 48 * 1024) cudaFuncSetAttribute(k_win_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            k_win_select<<<nf, 32, smem, st>>>(A);
+            cudaEventRecord(m->ev1, st);
+            m->last_launches = 3;
+            ce = cudaGetLastError();
+            if (ce != cudaSuccess) rc = og_fail(ORBGPU_ERR_CUDA, std::string("windowed search: ") + cudaGetErrorString(ce));
+        }
+    }
+    auto get = [&](void* host, const void* dev, size_t bytes) {
+        if (!rc && host && bytes) {
+            cudaError_t e = cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, st);
+            if (e != cudaSuccess) rc = og_fail(ORBGPU_ERR_CUDA, std::string("download: ") + cudaGetErrorString(e));
+        }
+    };
+    get(kp_match, d[0], (size_t)F.nkp * 4);
+    get(q_best_idx, d[1], (size_t)nq * 4);
+    get(q_best_dist, d[2], (size_t)nq * 4);
+    get(nmatches, d[4], (size_t)nf * 4);
+    cudaError_t se = cudaStreamSynchronize(st);
+    if (!rc && se != cudaSuccess) rc = og_fail(ORBGPU_ERR_CUDA, std::string("windowed search: ") + cudaGetErrorString(se));
+    free_owned(F.owned);
+    free_owned(owned);
+    return rc;
 }
 
 // D2H helper of the host-pointer variants
@@ -1506,6 +1740,14 @@ int orbgpu_search_by_projection(orbgpu_matcher* m, const orbgpu_frame_set* frame
     free_owned(F.owned);
     free_owned(Mset.owned);
     return rc;
+}
+
+int orbgpu_search_windowed(orbgpu_matcher* m, const orbgpu_frame_set* frames, const orbgpu_window_query_set* queries, int th_dist,
+                           int skip_any_mappoint, int check_orientation, int32_t* kp_match, int32_t* q_best_idx, int32_t* q_best_dist,
+                           int32_t* nmatches) {
+    int rc = check_matcher(m);
+    if (rc) return rc;
+    return win_host(m, frames, queries, th_dist, skip_any_mappoint, check_orientation, kp_match, q_best_idx, q_best_dist, nmatches);
 }
 
 }  // extern "C"

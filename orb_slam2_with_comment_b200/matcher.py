@@ -29,6 +29,11 @@ class CMapPointSet(C.Structure):  # orbgpu_mappoint_set
                 ("level", _i32p), ("flags", _u8p), ("desc", _u8p)]
 
 
+class CWindowQuerySet(C.Structure):  # orbgpu_window_query_set
+    _fields_ = [("q_off", _i32p), ("u", _f32p), ("v", _f32p), ("radius", _f32p), ("min_level", _i32p), ("max_level", _i32p),
+                ("ur", _f32p), ("flags", _u8p), ("desc", _u8p), ("angle", _f32p)]
+
+
 def _arr(a, dtype):
     return None if a is None else np.ascontiguousarray(a, dtype=dtype)
 
@@ -85,6 +90,21 @@ class MapPointSet:
                               _ptr(self.flags, _u8p), _ptr(self.desc, _u8p))
 
 
+class WindowQuerySet:
+    """Projected map points for the generic windowed search (orbgpu_search_windowed), per frame."""
+
+    def __init__(self, q_off, u, v, radius, min_level, max_level, flags, desc, ur=None, angle=None):
+        self.q_off = _arr(q_off, np.int32)
+        self.u, self.v, self.radius = _arr(u, np.float32), _arr(v, np.float32), _arr(radius, np.float32)
+        self.min_level, self.max_level = _arr(min_level, np.int32), _arr(max_level, np.int32)
+        self.ur, self.angle = _arr(ur, np.float32), _arr(angle, np.float32)
+        self.flags, self.desc = _arr(flags, np.uint8), _arr(desc, np.uint8).reshape(-1, 32)
+        self.n = int(self.q_off[-1])
+        self.c = CWindowQuerySet(_ptr(self.q_off, _i32p), _ptr(self.u, _f32p), _ptr(self.v, _f32p), _ptr(self.radius, _f32p),
+                                 _ptr(self.min_level, _i32p), _ptr(self.max_level, _i32p), _ptr(self.ur, _f32p),
+                                 _ptr(self.flags, _u8p), _ptr(self.desc, _u8p), _ptr(self.angle, _f32p))
+
+
 def match_offsets(fs1: FrameSet, idx1) -> np.ndarray:
     """Packed output layout: pair p writes keypoints-of-frame-idx1[p] entries at match_off[p]."""
     n = np.array([fs1.n_kp(int(f)) for f in idx1], np.int64)
@@ -112,6 +132,7 @@ def _bind(L):
     L.orbgpu_hamming_pairs.argtypes = [vp, vp, vp, i, vp]
     L.orbgpu_search_by_projection.argtypes = [vp, C.POINTER(CFrameSet), C.POINTER(CMapPointSet), vp, i, f, f, vp, vp, vp, vp, vp]
     L.orbgpu_search_by_projection_dev.argtypes = [vp, vp, vp, vp, i, f, f, vp, vp, vp, vp, vp]
+    L.orbgpu_search_windowed.argtypes = [vp, C.POINTER(CFrameSet), C.POINTER(CWindowQuerySet), i, i, i, vp, vp, vp, vp]
     L.orbgpu_search_for_triangulation.argtypes = [vp, C.POINTER(CFrameSet), C.POINTER(CFrameSet), i, vp, vp, vp, vp, vp, vp, i, i, i,
                                                   vp, vp, vp, vp]
     L.orbgpu_search_for_triangulation_dev.argtypes = [vp, vp, vp, i, vp, vp, vp, vp, vp, vp, i, i, i, vp, vp, vp, vp]
@@ -184,6 +205,16 @@ class ORBmatcher:
                                                          self.mfNNratio, kp_match.ctypes.data, best_idx.ctypes.data,
                                                          best_dist.ctypes.data, second.ctypes.data, nm.ctypes.data))
         return {"nmatches": nm, "kp_match": kp_match, "mp_best_idx": best_idx, "mp_best_dist": best_dist, "mp_second_dist": second}
+
+    # ---- the search loop of SearchByProjection(Frame&, const Frame&, th, bMono) (:1540) and (Frame&, KeyFrame*, ...) (:1711)
+    def SearchWindowed(self, frames: FrameSet, queries: "WindowQuerySet", th_dist: int = 100, skip_any_mappoint: bool = False):
+        kp_match = np.full(int(frames.kp_off[-1]), -1, np.int32)
+        bi, bd = np.full(queries.n, -1, np.int32), np.full(queries.n, 256, np.int32)
+        nm = np.zeros(frames.n_frames, np.int32)
+        capi.check(self._lib.orbgpu_search_windowed(self._h, C.byref(frames.c), C.byref(queries.c), th_dist, int(skip_any_mappoint),
+                                                    int(self.mbCheckOrientation), kp_match.ctypes.data, bi.ctypes.data, bd.ctypes.data,
+                                                    nm.ctypes.data))
+        return {"nmatches": nm, "kp_match": kp_match, "q_best_idx": bi, "q_best_dist": bd}
 
     # ---- SearchForTriangulation (ORBmatcher.cc:783-975), batched over keyframe pairs
     def SearchForTriangulation(self, set1: FrameSet, set2: FrameSet, idx1, idx2, F12, epipole, scale_factors, level_sigma2,

@@ -266,6 +266,72 @@ def py_search_by_projection(fs, mps, sf, th, nnratio):
     return np.array(nm_out, np.int32), kp_match, bi, bd, sd
 
 
+def py_search_windowed(fs, qs, th_dist, skip_any, check_ori):
+    """ORBmatcher.cc:1581-1684 / :1760-1832 over projected queries."""
+    COLS, ROWS = 64, 48
+    kp_match = np.full(int(fs.kp_off[-1]), -1, np.int32)
+    bi, bd = np.full(qs.n, -1, np.int32), np.full(qs.n, 256, np.int32)
+    nm_out = []
+    for f in range(fs.n_frames):
+        K, D, FL, UR = frame_view(fs, f)
+        k0 = int(fs.kp_off[f])
+        minx, miny, iw, ih = [f32(v) for v in fs.grid[f]]
+        grid = {}
+        for i in range(len(K)):
+            px = c_round(float((f32(K[i]["x"]) - minx) * iw))
+            py = c_round(float((f32(K[i]["y"]) - miny) * ih))
+            if 0 <= px < COLS and 0 <= py < ROWS:
+                grid.setdefault((px, py), []).append(i)
+        state = [0] * len(K) if FL is None else [int(v) for v in FL]
+        hist = [[] for _ in range(HISTO_LENGTH)]
+        n = 0
+        for q in range(int(qs.q_off[f]), int(qs.q_off[f + 1])):
+            if not (int(qs.flags[q]) & 1):
+                continue
+            x, y, r = f32(qs.u[q]), f32(qs.v[q]), f32(qs.radius[q])
+            lo, hi = int(qs.min_level[q]), int(qs.max_level[q])
+            cx0 = max(0, int(math.floor(float((x - minx - r) * iw))))
+            cx1 = min(COLS - 1, int(math.ceil(float((x - minx + r) * iw))))
+            cy0 = max(0, int(math.floor(float((y - miny - r) * ih))))
+            cy1 = min(ROWS - 1, int(math.ceil(float((y - miny + r) * ih))))
+            if cx0 >= COLS or cx1 < 0 or cy0 >= ROWS or cy1 < 0:
+                continue
+            check_levels = lo > 0 or hi >= 0
+            best, besti = 256, -1
+            for ix in range(cx0, cx1 + 1):
+                for iy in range(cy0, cy1 + 1):
+                    for i in grid.get((ix, iy), []):
+                        o = int(K[i]["octave"])
+                        if check_levels and (o < lo or (hi >= 0 and o > hi)):
+                            continue
+                        if not (abs(f32(K[i]["x"]) - x) < r and abs(f32(K[i]["y"]) - y) < r):
+                            continue
+                        if state[i] == 1 or (skip_any and state[i] != 0):
+                            continue
+                        if qs.ur is not None and UR is not None and UR[i] > 0 and abs(f32(qs.ur[q]) - f32(UR[i])) > r:
+                            continue
+                        d = popcount_distance(qs.desc[q], D[i])
+                        if d < best:
+                            best, besti = d, i
+            bi[q], bd[q] = besti, best
+            if best <= th_dist:
+                state[besti] = 1 if (int(qs.flags[q]) & 4) else 2
+                kp_match[k0 + besti] = q - int(qs.q_off[f])
+                n += 1
+                if check_ori:
+                    hist[rot_bin(qs.angle[q], K[besti]["angle"])].append(besti)
+        if check_ori:
+            keep = py_three_maxima(hist)
+            for b in range(HISTO_LENGTH):
+                if b in keep:
+                    continue
+                for i in hist[b]:
+                    kp_match[k0 + i] = -2
+                    n -= 1
+        nm_out.append(n)
+    return np.array(nm_out, np.int32), kp_match, bi, bd
+
+
 def checksum(*arrays) -> np.ndarray:
     import zlib
     c = 0
@@ -293,6 +359,9 @@ CASES = {
     "sbp_mono_th1": ("sbp", dict(seed=31, n_frames=2, n_lo=250, n_hi=400, n_mp=500, th=1.0), dict(nnratio=0.8)),
     "sbp_stereo_th3": ("sbp", dict(seed=32, n_frames=2, n_lo=250, n_hi=400, n_mp=500, stereo_frac=0.5, th=3.0), dict(nnratio=0.8)),
     "sbp_wide_th15": ("sbp", dict(seed=33, n_frames=1, n_lo=300, n_hi=300, n_mp=300, th=15.0), dict(nnratio=0.9)),
+    "win_frame_mono": ("win", dict(seed=41, n_frames=3, n_lo=250, n_hi=400, n_q=300, mode="frame", th=15.0), dict(th_dist=100, skip_any=False, check_ori=True)),
+    "win_frame_stereo": ("win", dict(seed=42, n_frames=3, n_lo=250, n_hi=400, n_q=300, mode="frame", th=7.0, stereo_frac=0.5), dict(th_dist=100, skip_any=False, check_ori=True)),
+    "win_keyframe": ("win", dict(seed=43, n_frames=2, n_lo=250, n_hi=400, n_q=300, mode="keyframe", th=10.0), dict(th_dist=64, skip_any=True, check_ori=False)),
 }
 
 
@@ -307,6 +376,10 @@ def run_case(name):
         s1, s2, i1, i2, F12, epi, sf, s2t = mc.tri_case(**gen)
         nm, m12, md = py_search_for_triangulation(s1, s2, i1, i2, F12, epi, sf, s2t, mk["only_stereo"], mk["check_ori"])
         out = {"nmatches": nm, "match12": m12, "match_dist": md, "input_crc": fs_checksum(s1)}
+    elif kind == "win":
+        fs, qs = mc.win_case(**gen)
+        nm, kpm, bi, bd = py_search_windowed(fs, qs, mk["th_dist"], mk["skip_any"], mk["check_ori"])
+        out = {"nmatches": nm, "kp_match": kpm, "q_best_idx": bi, "q_best_dist": bd, "input_crc": checksum(fs_checksum(fs), qs.u, qs.v, qs.desc)}
     else:
         fs, mps, sf, th = mc.sbp_case(**gen)
         nm, kpm, bi, bd, sd = py_search_by_projection(fs, mps, sf, th, mk["nnratio"])

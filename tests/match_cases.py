@@ -112,3 +112,48 @@ def sbp_case(seed, n_frames=4, n_lo=300, n_hi=700, n_mp=1500, stereo_frac=0.0, o
                       cat["desc"], proj_xr=cat["proj_xr"])
     sf, _ = synth.scale_tables()
     return fs, mps, sf, th
+
+
+def win_case(seed, n_frames=3, n_lo=400, n_hi=800, n_q=700, stereo_frac=0.0, mode="frame", th=15.0):
+    """Queries for the generic windowed search: the map points of a 'last frame' projected into the current frame
+    (mode 'frame': level range l-1..l+1 or, for a third of the frames each, the forward [l, inf) / backward [0, l] ranges
+    of ORBmatcher.cc:1604-1611; mode 'keyframe': always l-1..l+1)."""
+    from orb_slam2_with_comment_b200.matcher import WindowQuerySet
+    rs, kp_off, keys, desc = _frames(seed, n_frames + 1, n_lo, n_hi)
+    ko = kp_off[1:] - kp_off[1]
+    sel = slice(kp_off[1], kp_off[-1])
+    fkeys, fdesc = keys[sel], desc[sel]
+    flags = np.zeros(len(fkeys), np.uint8)
+    r = rs.uniform(size=len(fkeys))
+    flags[r < 0.08] = 1
+    flags[(r >= 0.08) & (r < 0.14)] = 2
+    u_right = np.where(rs.uniform(size=len(fkeys)) < stereo_frac, fkeys["x"] - rs.uniform(1, 30, len(fkeys)), -1).astype(np.float32)
+    grid = np.tile(synth.frame_grid(W, H), (n_frames, 1))
+    fs = FrameSet(ko.astype(np.int32), fkeys, fdesc, kp_flags=flags, u_right=u_right if stereo_frac > 0 else None, grid=grid)
+    sf, _ = synth.scale_tables()
+    q_off, parts = [0], []
+    for f in range(n_frames):
+        prev_k, prev_d = keys[kp_off[f]:kp_off[f + 1]], desc[kp_off[f]:kp_off[f + 1]]
+        nq = min(int(n_q * rs.uniform(0.7, 1.0)), len(prev_k))
+        src = rs.permutation(len(prev_k))[:nq]
+        k = prev_k[src]
+        lvl = k["octave"].astype(np.int32)
+        if mode == "frame" and f % 3 == 1:
+            lo, hi = lvl, np.full(nq, -1, np.int32)          # forward
+        elif mode == "frame" and f % 3 == 2:
+            lo, hi = np.zeros(nq, np.int32), lvl              # backward
+        else:
+            lo, hi = lvl - 1, lvl + 1
+        u = (k["x"] + rs.normal(0, 3, nq)).astype(np.float32)
+        fl = np.full(nq, 1 | 4, np.uint8)
+        z = rs.uniform(size=nq)
+        fl[z < 0.05] = 0                                      # projection failed
+        fl[(z >= 0.05) & (z < 0.25)] &= ~np.uint8(4)          # temporal MapPoint without observations
+        parts.append({"u": u, "v": (k["y"] + rs.normal(0, 3, nq)).astype(np.float32), "radius": (np.float32(th) * sf[lvl]).astype(np.float32),
+                      "lo": lo.astype(np.int32), "hi": hi.astype(np.int32), "ur": (u - rs.uniform(1, 30, nq)).astype(np.float32), "flags": fl,
+                      "desc": synth.flip_bits(prev_d[src], rs, 0.05), "angle": k["angle"]})
+        q_off.append(q_off[-1] + nq)
+    cat = {k2: np.concatenate([p[k2] for p in parts]) for k2 in parts[0]}
+    qs = WindowQuerySet(np.array(q_off, np.int32), cat["u"], cat["v"], cat["radius"], cat["lo"], cat["hi"], cat["flags"], cat["desc"],
+                        ur=cat["ur"] if stereo_frac > 0 else None, angle=cat["angle"])
+    return fs, qs

@@ -181,6 +181,9 @@ def bind_match(lib):
     lib.orbm_hamming.argtypes = [u8p, u8p]
     lib.orbm_search_by_projection.restype = None
     lib.orbm_search_by_projection.argtypes = [C.POINTER(CFrameSet), C.POINTER(CMapPointSet), vp, i, f, f, vp, vp, vp, vp, vp]
+    from orb_slam2_with_comment_b200.matcher import CWindowQuerySet
+    lib.orbm_search_windowed.restype = None
+    lib.orbm_search_windowed.argtypes = [C.POINTER(CFrameSet), C.POINTER(CWindowQuerySet), i, i, i, vp, vp, vp, vp]
     lib.orbm_search_for_triangulation.restype = None
     lib.orbm_search_for_triangulation.argtypes = [C.POINTER(CFrameSet), C.POINTER(CFrameSet), i, vp, vp, vp, vp, vp, vp, i, i, i, vp,
                                                   vp, vp, vp]
@@ -212,6 +215,14 @@ class MatcherOracle:
         self.lib.orbm_search_by_projection(C.byref(frames.c), C.byref(mps.c), sf.ctypes.data, len(sf), th, self.mfNNratio,
                                            kp_match.ctypes.data, bi.ctypes.data, bd.ctypes.data, sd.ctypes.data, nm.ctypes.data)
         return {"nmatches": nm, "kp_match": kp_match, "mp_best_idx": bi, "mp_best_dist": bd, "mp_second_dist": sd}
+
+    def SearchWindowed(self, frames, queries, th_dist=100, skip_any_mappoint=False):
+        kp_match = np.full(int(frames.kp_off[-1]), -1, np.int32)
+        bi, bd = np.full(queries.n, -1, np.int32), np.full(queries.n, 256, np.int32)
+        nm = np.zeros(frames.n_frames, np.int32)
+        self.lib.orbm_search_windowed(C.byref(frames.c), C.byref(queries.c), th_dist, int(skip_any_mappoint), int(self.mbCheckOrientation),
+                                      kp_match.ctypes.data, bi.ctypes.data, bd.ctypes.data, nm.ctypes.data)
+        return {"nmatches": nm, "kp_match": kp_match, "q_best_idx": bi, "q_best_dist": bd}
 
     def SearchForTriangulation(self, set1, set2, idx1, idx2, F12, epipole, scale_factors, level_sigma2, bOnlyStereo=False):
         from orb_slam2_with_comment_b200.matcher import match_offsets

@@ -230,3 +230,15 @@ def test_full_size_bruteforce_properties(gm):
     for cfg in (dict(min_queries=0), dict(queries_per_thread=8)):
         r2 = gm(0.75, False, **cfg).SearchByBoW(sA, sB, idx, idx)
         same(r, r2, BOW_KEYS, f"cfg {cfg}")
+
+
+@pytest.mark.parametrize("mode,stereo,th,th_dist,skip_any,ori", [("frame", 0.0, 15.0, 100, False, True), ("frame", 0.5, 7.0, 100, False, True),
+                                                                 ("keyframe", 0.0, 10.0, 64, True, True), ("frame", 0.3, 40.0, 100, False, False)])
+def test_windowed_search_vs_oracle(gm, mo, mode, stereo, th, th_dist, skip_any, ori):
+    """The search loop of SearchByProjection(CurrentFrame, LastFrame) / (CurrentFrame, KeyFrame) (ORBmatcher.cc:1540, :1711)."""
+    for seed in (701, 702):
+        fs, qs = mc.win_case(seed, n_frames=6, n_lo=700, n_hi=1500, n_q=1200, stereo_frac=stereo, mode=mode, th=th)
+        got = gm(0.9, ori).SearchWindowed(fs, qs, th_dist, skip_any)
+        exp = mo(0.9, ori).SearchWindowed(fs, qs, th_dist, skip_any)
+        same(got, exp, ("nmatches", "kp_match", "q_best_idx", "q_best_dist"), f"windowed seed {seed} {mode}")
+        assert exp["nmatches"].sum() > 500

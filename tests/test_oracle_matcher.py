@@ -190,6 +190,12 @@ def test_port_reproduces_golden_fixtures(mo):
             assert np.array_equal(gen.fs_checksum(s1), G[f"{name}__input_crc"])
             res = mo(0.6, mk["check_ori"]).SearchForTriangulation(s1, s2, i1, i2, F12, epi, sf, s2t, bOnlyStereo=mk["only_stereo"])
             _check(res, G, name, ("nmatches", "match12", "match_dist"))
+        elif kind == "win":
+            fs, qs = mc.win_case(**g)
+            res = mo(0.6, mk["check_ori"]).SearchWindowed(fs, qs, mk["th_dist"], mk["skip_any"])
+            _check(res, G, name, ("nmatches", "kp_match", "q_best_idx", "q_best_dist"))
+            if mk["check_ori"]:
+                assert (res["kp_match"] == -2).any(), f"{name}: the rotation check removed nothing"
         else:
             fs, mps, sf, th = mc.sbp_case(**g)
             res = mo(mk["nnratio"], True).SearchByProjection(fs, mps, sf, th)
