@@ -5,6 +5,7 @@
 //   SearchByBoW(KeyFrame*, Frame&, vector<MapPoint*>&)            replaces :211-344
 //   SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&)         replaces :635-768
 //   SearchForTriangulation(KeyFrame*, KeyFrame*, F12, pairs, ..)  replaces :783-975
+//   SearchByProjection(Frame&, const Frame&, th, bMono)           replaces :1540-1685 (pose arithmetic here, search on the GPU)
 //
 // Integration: compile this file into the ORB_SLAM2 library and remove (or #ifdef out) those four bodies from the
 // reference's ORBmatcher.cc; everything else of that file — the constructor, DescriptorDistance, the other search
@@ -220,6 +221,83 @@ int ORBmatcher::SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, cv::Mat F
     vMatchedPairs.reserve(nmatches);
     for (int i = 0; i < N1; ++i)
         if (match12[i] >= 0) vMatchedPairs.push_back(std::make_pair((size_t)i, (size_t)match12[i]));   // :964-972
+    return nmatches;
+}
+
+// 3x3 (rows 0-2, cols 0-2 of a 4x4 pose) times a 3-vector plus a 3-vector, accumulated in double and rounded to float like
+// cv::gemm's small-matrix path (the reference writes these as cv::Mat expressions, ORBmatcher.cc:1556-1563, :1579).
+static void rt_apply(const cv::Mat& T, const float* x, float* out) {
+    for (int i = 0; i < 3; ++i) {
+        double acc = 0.0;
+        for (int j = 0; j < 3; ++j) acc += (double)T.at<float>(i, j) * (double)x[j];
+        out[i] = (float)(acc + (double)T.at<float>(i, 3));
+    }
+}
+
+int ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono) {
+    const int N = (int)CurrentFrame.mvKeysUn.size(), NL = LastFrame.N;
+    if (N == 0 || NL == 0) return 0;
+    // twc = -Rcw^T * tcw, tlc = Rlw * twc + tlw (:1556-1563)
+    float twc[3], tlc[3];
+    for (int i = 0; i < 3; ++i) {
+        double acc = 0.0;
+        for (int j = 0; j < 3; ++j) acc += (double)CurrentFrame.mTcw.at<float>(j, i) * (double)CurrentFrame.mTcw.at<float>(j, 3);
+        twc[i] = (float)(-acc);
+    }
+    rt_apply(LastFrame.mTcw, twc, tlc);
+    const bool bForward = tlc[2] > CurrentFrame.mb && !bMono;     // :1566-1567
+    const bool bBackward = -tlc[2] > CurrentFrame.mb && !bMono;
+
+    const int32_t kp_off[2] = {0, N}, q_off[2] = {0, NL};
+    std::vector<uint8_t> tmp, kflags(N, 0);
+    orbgpu_frame_set fs = one_frame(kp_off, CurrentFrame.mvKeysUn, rows32(CurrentFrame.mDescriptors, tmp));
+    for (int i = 0; i < N; ++i)
+        if (CurrentFrame.mvpMapPoints[i]) kflags[i] = CurrentFrame.mvpMapPoints[i]->Observations() > 0 ? 1 : 2;   // :1619-1621
+    fs.kp_flags = kflags.data();
+    fs.u_right = CurrentFrame.mvuRight.empty() ? nullptr : CurrentFrame.mvuRight.data();
+    const float grid[4] = {Frame::mnMinX, Frame::mnMinY, Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv};
+    fs.grid = grid;
+
+    std::vector<float> qu(NL), qv(NL), qr(NL), qur(NL), qang(NL);
+    std::vector<int32_t> qlo(NL), qhi(NL);
+    std::vector<uint8_t> qfl(NL, 0), qdesc((size_t)NL * 32, 0);
+    for (int i = 0; i < NL; ++i) {
+        MapPoint* pMP = LastFrame.mvpMapPoints[i];
+        if (!pMP || LastFrame.mvbOutlier[i]) continue;            // :1572-1575
+        const cv::Mat x3Dw = pMP->GetWorldPos();
+        const float xw[3] = {x3Dw.at<float>(0, 0), x3Dw.at<float>(1, 0), x3Dw.at<float>(2, 0)};
+        float xc[3];
+        rt_apply(CurrentFrame.mTcw, xw, xc);                      // :1579
+        const float invzc = 1.0 / xc[2];
+        if (invzc < 0) continue;
+        const float u = Frame::fx * xc[0] * invzc + Frame::cx;
+        const float v = Frame::fy * xc[1] * invzc + Frame::cy;
+        if (u < Frame::mnMinX || u > Frame::mnMaxX) continue;
+        if (v < Frame::mnMinY || v > Frame::mnMaxY) continue;
+        const int nLastOctave = LastFrame.mvKeys[i].octave;
+        qu[i] = u; qv[i] = v;
+        qr[i] = th * CurrentFrame.mvScaleFactors[nLastOctave];   // :1598
+        if (bForward) { qlo[i] = nLastOctave; qhi[i] = -1; }      // GetFeaturesInArea(u, v, radius, nLastOctave)
+        else if (bBackward) { qlo[i] = 0; qhi[i] = nLastOctave; }
+        else { qlo[i] = nLastOctave - 1; qhi[i] = nLastOctave + 1; }
+        qur[i] = u - CurrentFrame.mbf * invzc;                    // :1626
+        qang[i] = LastFrame.mvKeysUn[i].angle;
+        qfl[i] = (uint8_t)(1 | (pMP->Observations() > 0 ? 4 : 0));
+        const cv::Mat d = pMP->GetDescriptor();
+        std::memcpy(&qdesc[(size_t)i * 32], d.ptr(0), 32);
+    }
+    orbgpu_window_query_set qs;
+    qs.q_off = q_off; qs.u = qu.data(); qs.v = qv.data(); qs.radius = qr.data(); qs.min_level = qlo.data(); qs.max_level = qhi.data();
+    qs.ur = qur.data(); qs.flags = qfl.data(); qs.desc = qdesc.data(); qs.angle = qang.data();
+    std::vector<int32_t> kp_match(N, -1);
+    int32_t nmatches = 0;
+    check(orbgpu_search_windowed(matcher(), &fs, &qs, TH_HIGH, /*skip_any_mappoint*/ 0, mbCheckOrientation ? 1 : 0, kp_match.data(), nullptr,
+                                 nullptr, &nmatches),
+          "SearchByProjection(Frame, Frame)");
+    for (int i = 0; i < N; ++i) {
+        if (kp_match[i] >= 0) CurrentFrame.mvpMapPoints[i] = LastFrame.mvpMapPoints[kp_match[i]];   // :1644
+        else if (kp_match[i] == -2) CurrentFrame.mvpMapPoints[i] = static_cast<MapPoint*>(NULL);    // :1676
+    }
     return nmatches;
 }
 

@@ -28,6 +28,7 @@ public:
     int Observations() { return nObs; }
     bool isBad() { return mbBad; }
     cv::Mat GetDescriptor() { return mDescriptor.clone(); }
+    cv::Mat GetWorldPos() { return mWorldPos.clone(); }
 
     float mTrackProjX, mTrackProjY, mTrackProjXR;
     bool mbTrackInView;
@@ -38,6 +39,7 @@ public:
     bool mbBad;
     int nObs;
     cv::Mat mDescriptor;
+    cv::Mat mWorldPos;   // 3x1 CV_32F
 };
 
 class Frame {
@@ -48,7 +50,11 @@ public:
     DBoW2::FeatureVector mFeatVec;
     cv::Mat mDescriptors;
     std::vector<MapPoint*> mvpMapPoints;
+    std::vector<bool> mvbOutlier;
     std::vector<float> mvScaleFactors;
+    cv::Mat mTcw;        // 4x4 CV_32F
+    float mb, mbf;
+    static float fx, fy, cx, cy;
     static float mfGridElementWidthInv, mfGridElementHeightInv;
     static float mnMinX, mnMaxX, mnMinY, mnMaxY;
 };

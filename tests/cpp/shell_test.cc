@@ -25,6 +25,7 @@ void orbs_stereo_matches(const orbgpu_keypoint*, const uint8_t*, int, const orbg
                          int32_t*);
 void orbm_search_by_projection(const orbgpu_frame_set*, const orbgpu_mappoint_set*, const float*, int, float, float, int32_t*, int32_t*,
                                int32_t*, int32_t*, int32_t*);
+void orbm_search_windowed(const orbgpu_frame_set*, const orbgpu_window_query_set*, int, int, int, int32_t*, int32_t*, int32_t*, int32_t*);
 void orbm_search_for_triangulation(const orbgpu_frame_set*, const orbgpu_frame_set*, int, const int32_t*, const int32_t*, const float*,
                                    const float*, const float*, const float*, int, int, int, const int64_t*, int32_t*, int32_t*, int32_t*);
 void orbm_search_by_bow(const orbgpu_frame_set*, const orbgpu_frame_set*, int, const int32_t*, const int32_t*, float, int, int, int, int,
@@ -32,6 +33,7 @@ void orbm_search_by_bow(const orbgpu_frame_set*, const orbgpu_frame_set*, int, c
 }
 
 float Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv, Frame::mnMinX, Frame::mnMaxX, Frame::mnMinY, Frame::mnMaxY;
+float Frame::fx, Frame::fy, Frame::cx, Frame::cy;
 
 static uint32_t g_seed = 12345;
 static uint32_t rnd() { g_seed = g_seed * 1664525u + 1013904223u; return g_seed >> 8; }
@@ -322,6 +324,111 @@ static void test_matcher() {
     }
 }
 
+// --- SearchByProjection(CurrentFrame, LastFrame, th, bMono): TrackWithMotionModel's matcher ---
+static void test_track_last_frame() {
+    const int W = 640, H = 480, N = 1000;
+    Frame::fx = 517.3f; Frame::fy = 516.5f; Frame::cx = 318.6f; Frame::cy = 255.3f;
+    Frame::mnMinX = 0; Frame::mnMinY = 0; Frame::mnMaxX = W; Frame::mnMaxY = H;
+    Frame::mfGridElementWidthInv = 64.0f / W; Frame::mfGridElementHeightInv = 48.0f / H;
+    for (int variant = 0; variant < 3; ++variant) {   // 0: mono, 1: stereo forward motion, 2: stereo backward motion
+        Frame last, cur;
+        last.N = N; cur.N = N;
+        last.mvKeys = random_keys(N, W, H); last.mvKeysUn = last.mvKeys;
+        last.mDescriptors = random_desc(N);
+        last.mvScaleFactors = g_sf; cur.mvScaleFactors = g_sf;
+        last.mTcw = cv::Mat(4, 4, CV_32FC1); cur.mTcw = cv::Mat(4, 4, CV_32FC1);
+        for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) { last.mTcw.at<float>(i, j) = i == j; cur.mTcw.at<float>(i, j) = i == j; }
+        const float ang = 0.01f;
+        cur.mTcw.at<float>(0, 0) = std::cos(ang); cur.mTcw.at<float>(0, 2) = std::sin(ang); cur.mTcw.at<float>(2, 0) = -std::sin(ang); cur.mTcw.at<float>(2, 2) = std::cos(ang);
+        cur.mTcw.at<float>(0, 3) = 0.02f; cur.mTcw.at<float>(2, 3) = variant == 1 ? -0.3f : (variant == 2 ? 0.3f : 0.01f);
+        cur.mb = 0.08f; cur.mbf = 40.f; last.mb = 0.08f; last.mbf = 40.f;
+        // map points: back-projection of the last frame's key points at random depths
+        std::vector<MapPoint> pool(N);
+        last.mvpMapPoints.assign(N, nullptr); last.mvbOutlier.assign(N, false);
+        for (int i = 0; i < N; ++i) {
+            if (rnd() % 10 < 8) {
+                MapPoint& p = pool[i];
+                const float z = frand(2.f, 12.f);
+                p.mWorldPos = cv::Mat(3, 1, CV_32FC1);
+                p.mWorldPos.at<float>(0, 0) = (last.mvKeys[i].pt.x - Frame::cx) / Frame::fx * z;
+                p.mWorldPos.at<float>(1, 0) = (last.mvKeys[i].pt.y - Frame::cy) / Frame::fy * z;
+                p.mWorldPos.at<float>(2, 0) = rnd() % 50 == 0 ? -z : z;
+                p.mDescriptor = cv::Mat(1, 32, CV_8UC1);
+                std::memcpy(p.mDescriptor.ptr(0), last.mDescriptors.ptr(i), 32);
+                p.nObs = rnd() % 4 == 0 ? 0 : 2;
+                last.mvpMapPoints[i] = &p;
+                last.mvbOutlier[i] = rnd() % 15 == 0;
+            }
+        }
+        // current frame: the same scene seen from the new pose (+ noise), plus unrelated key points
+        cur.mvKeys = random_keys(N, W, H);
+        cur.mDescriptors = random_desc(N);
+        for (int i = 0; i < N; ++i) {
+            MapPoint* p = last.mvpMapPoints[i];
+            if (!p || rnd() % 10 >= 7) continue;
+            float xc[3];
+            for (int r = 0; r < 3; ++r) { double a = 0; for (int c = 0; c < 3; ++c) a += (double)cur.mTcw.at<float>(r, c) * p->mWorldPos.at<float>(c, 0); xc[r] = (float)(a + cur.mTcw.at<float>(r, 3)); }
+            if (xc[2] <= 0.1f) continue;
+            const int j = rnd() % N;
+            cur.mvKeys[j] = last.mvKeys[i];
+            cur.mvKeys[j].pt.x = Frame::fx * xc[0] / xc[2] + Frame::cx + frand(-2, 2);
+            cur.mvKeys[j].pt.y = Frame::fy * xc[1] / xc[2] + Frame::cy + frand(-2, 2);
+            cur.mvKeys[j].angle = std::fmod(last.mvKeys[i].angle + frand(-12, 12) + 360.f, 360.f);
+            std::memcpy(cur.mDescriptors.ptr(j), last.mDescriptors.ptr(i), 32);
+            flip(cur.mDescriptors.ptr(j), 10);
+        }
+        cur.mvKeysUn = cur.mvKeys;
+        cur.mvuRight.assign(N, -1.f);
+        if (variant) for (int i = 0; i < N; ++i) if (rnd() % 2) cur.mvuRight[i] = cur.mvKeys[i].pt.x - frand(2, 18);
+        std::vector<MapPoint> held(N);
+        cur.mvpMapPoints.assign(N, nullptr);
+        for (int i = 0; i < N; ++i) if (rnd() % 12 == 0) { cur.mvpMapPoints[i] = &held[i]; held[i].nObs = rnd() % 2; }
+        const bool bMono = variant == 0;
+        const float th = bMono ? 15.f : 7.f;
+
+        // ---- oracle: the same projection arithmetic, then the windowed search port
+        Flat a(cur.mvKeysUn, cur.mDescriptors, nullptr);
+        for (int i = 0; i < N; ++i) a.flags[i] = cur.mvpMapPoints[i] ? (cur.mvpMapPoints[i]->nObs > 0 ? 1 : 2) : 0;
+        a.s.u_right = cur.mvuRight.data();
+        const float grid[4] = {0, 0, Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv};
+        a.s.grid = grid;
+        float twc[3], tlc[3];
+        for (int i = 0; i < 3; ++i) { double acc = 0; for (int j = 0; j < 3; ++j) acc += (double)cur.mTcw.at<float>(j, i) * cur.mTcw.at<float>(j, 3); twc[i] = (float)(-acc); }
+        for (int i = 0; i < 3; ++i) { double acc = 0; for (int j = 0; j < 3; ++j) acc += (double)last.mTcw.at<float>(i, j) * twc[j]; tlc[i] = (float)(acc + last.mTcw.at<float>(i, 3)); }
+        const bool fwd = tlc[2] > cur.mb && !bMono, bwd = -tlc[2] > cur.mb && !bMono;
+        EXPECT(variant == 0 || (variant == 1) == fwd, "variant %d: forward=%d backward=%d", variant, fwd, bwd);
+        int32_t q_off[2] = {0, N};
+        std::vector<float> qu(N), qv(N), qr(N), qur(N), qa(N);
+        std::vector<int32_t> lo(N), hi(N);
+        std::vector<uint8_t> qf(N, 0), qd((size_t)N * 32, 0);
+        for (int i = 0; i < N; ++i) {
+            MapPoint* p = last.mvpMapPoints[i];
+            if (!p || last.mvbOutlier[i]) continue;
+            float xc[3];
+            for (int r = 0; r < 3; ++r) { double acc = 0; for (int c = 0; c < 3; ++c) acc += (double)cur.mTcw.at<float>(r, c) * p->mWorldPos.at<float>(c, 0); xc[r] = (float)(acc + cur.mTcw.at<float>(r, 3)); }
+            const float invzc = 1.0 / xc[2];
+            if (invzc < 0) continue;
+            const float u = Frame::fx * xc[0] * invzc + Frame::cx, v = Frame::fy * xc[1] * invzc + Frame::cy;
+            if (u < 0 || u > W || v < 0 || v > H) continue;
+            const int o = last.mvKeys[i].octave;
+            qu[i] = u; qv[i] = v; qr[i] = th * g_sf[o]; qur[i] = u - cur.mbf * invzc; qa[i] = last.mvKeysUn[i].angle;
+            if (fwd) { lo[i] = o; hi[i] = -1; } else if (bwd) { lo[i] = 0; hi[i] = o; } else { lo[i] = o - 1; hi[i] = o + 1; }
+            qf[i] = (uint8_t)(1 | (p->nObs > 0 ? 4 : 0));
+            std::memcpy(&qd[(size_t)i * 32], p->mDescriptor.ptr(0), 32);
+        }
+        orbgpu_window_query_set qs = {q_off, qu.data(), qv.data(), qr.data(), lo.data(), hi.data(), qur.data(), qf.data(), qd.data(), qa.data()};
+        std::vector<int32_t> kpm(N, -1); int32_t nm = 0;
+        orbm_search_windowed(&a.s, &qs, 100, 0, 1, kpm.data(), nullptr, nullptr, &nm);
+        std::vector<MapPoint*> exp = cur.mvpMapPoints;
+        for (int i = 0; i < N; ++i) { if (kpm[i] >= 0) exp[i] = last.mvpMapPoints[kpm[i]]; else if (kpm[i] == -2) exp[i] = nullptr; }
+
+        ORBmatcher m(0.9f, true);
+        const int n = m.SearchByProjection(cur, last, th, bMono);
+        EXPECT(n == nm && nm > 100, "SearchByProjection(Frame,Frame) variant %d: %d matches vs oracle %d", variant, n, nm);
+        EXPECT(cur.mvpMapPoints == exp, "SearchByProjection(Frame,Frame) variant %d: mvpMapPoints differ", variant);
+    }
+}
+
 int main() {
     int ndev = 0;
     if (orbgpu_device_count(&ndev) != 0 || ndev == 0) {
@@ -340,6 +447,7 @@ int main() {
     test_extractor();
     test_stereo();
     test_matcher();
+    test_track_last_frame();
     printf(fails ? "shell_test: %d FAILURES\n" : "shell_test: all shell results equal the oracle (%d failures)\n", fails);
     return fails ? 1 : 0;
 }
