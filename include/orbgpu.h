@@ -124,7 +124,7 @@ int orbgpu_octree(orbgpu_extractor* ex, const orbgpu_keypoint* candidates, int n
  * extractors on the same device that have just processed the left and the right images of the same batch (same image size,
  * same parameters); their key points, descriptors and pyramids are consumed where they lie in HBM — no pyramid download.
  * u_right / depth receive mvuRight / mvDepth: entry f*out_stride + i belongs to key point i of left frame f, -1 = no match
- * (entries beyond the frame's key-point count are not written).  mb / mbf are Frame::mb / Frame::mbf. */
+ * (slots beyond the frame's key-point count, up to orbgpu_extractor_max_keypoints(), are set to -1 too).  mb / mbf are Frame::mb / Frame::mbf. */
 int orbgpu_stereo_matches(orbgpu_extractor* left, orbgpu_extractor* right, float mb, float mbf, float* u_right, float* depth,
                           int out_stride);
 /* The same with device output pointers, enqueued on the left extractor's stream (orbgpu_extractor_sync(left) waits). */

@@ -94,7 +94,14 @@ __global__ void __launch_bounds__(kStereoThreads) k_stereo_match(const __grid_co
     const int f = blockIdx.y, lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
     const int iL = blockIdx.x * (kStereoThreads / 32) + wi;
     const int nl = A.cntL[f];
-    if (iL >= nl) return;
+    if (iL >= nl) {
+        // slots beyond the frame's key points read -1 as well (the host variant copies whole rows)
+        if (lane == 0 && iL < A.kp_stride) {
+            A.u_right[(long long)f * A.out_stride + iL] = -1.0f;
+            A.depth[(long long)f * A.out_stride + iL] = -1.0f;
+        }
+        return;
+    }
     const KeyPoint kL = A.kpL[(long long)f * A.kp_stride + iL];
     float out_u = -1.0f, out_d = -1.0f;
     int out_sad = -1;
