@@ -140,7 +140,7 @@ size_t octree_ws_bytes(int cap, int node_cap) {
     take((size_t)node_cap * sizeof(og::OtNode)); take((size_t)node_cap * sizeof(og::OtNode));
     take((size_t)node_cap * sizeof(og::OtTmp));
     for (int i = 0; i < 5; ++i) take((size_t)node_cap * 4);
-    take((size_t)og::kOctThreads * 16);
+    take((size_t)og::kOctMaxThreads * 16);
     return b;
 }
 
@@ -385,6 +385,7 @@ int ensure_geometry(orbgpu_extractor* ex, int w, int h) {
         OG_CUDA(cudaStreamSynchronize(ex->stream));   // `maps` is a local
         if (smem > 200 * 1024) return fail(ORBGPU_ERR_ARG, "internal: FAST tile does not fit shared memory");
         // the attribute is per function, not per handle: always allow the largest tile any geometry can ask for
+        OG_CUDA(cudaFuncSetAttribute(og::k_octree<og::kOctLatThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, og::kOctSmem));
         OG_CUDA(cudaFuncSetAttribute(og::k_fast_seg, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      og::fast_seg_smem_bytes(og::kCellMax + 6, og::kCellMax)));
         ex->fast_smem = smem;
@@ -476,7 +477,12 @@ int launch_extract(orbgpu_extractor* ex, const uint8_t* d_images, int batch, siz
     og::k_fast_seg<<<dim3(P.n_segs, batch), og::kSegThreads, ex->fast_smem, st>>>(P, ex->d_tmaps);
     ++launches;
     mark(2);
-    og::k_octree<<<dim3(P.n_levels, batch), og::kOctThreads, 0, st>>>(P);
+    {
+        if (batch <= og::kOctSmemMaxBatch)
+            og::k_octree<og::kOctLatThreads><<<dim3(P.n_levels, batch), og::kOctLatThreads, og::kOctSmem, st>>>(P, og::kOctSmem);
+        else
+            og::k_octree<og::kOctThreads><<<dim3(P.n_levels, batch), og::kOctThreads, 0, st>>>(P, 0);
+    }
     ++launches;
     mark(3);
     if (overlap_blur) {

@@ -448,6 +448,10 @@ __global__ void __launch_bounds__(kSegThreads) k_fast_seg(const __grid_constant_
 #define OG_OCT_THREADS 128
 #endif
 constexpr int kOctThreads = OG_OCT_THREADS;
+constexpr int kOctSmem = 160 * 1024;   // shared-memory workspace budget of one octree CTA in latency mode (small batches)
+constexpr int kOctSmemMaxBatch = 16;
+constexpr int kOctLatThreads = 512;      // CTA size in latency mode (per-thread key chunks shrink 4x; occupancy is irrelevant there)
+constexpr int kOctMaxThreads = 1024;     // sizes the per-thread scan scratch
 
 __device__ __forceinline__ OtWork carve_work(uint8_t* ws, int cap, int node_cap) {
     OtWork W;
@@ -466,22 +470,59 @@ __device__ __forceinline__ OtWork carve_work(uint8_t* ws, int cap, int node_cap)
     W.ordv = (int32_t*)take((size_t)node_cap * 4);
     W.ordv2 = (int32_t*)take((size_t)node_cap * 4);
     W.surv = (int32_t*)take((size_t)node_cap * 4);
-    W.thr = (int32_t*)take((size_t)kOctThreads * 4 * 4);
+    W.thr = (int32_t*)take((size_t)kOctMaxThreads * 4 * 4);
     W.cap = cap;
     W.node_cap = node_cap;
     return W;
 }
 
-__global__ void __launch_bounds__(kOctThreads) k_octree(const __grid_constant__ ExtractParams P) {
+// Workspace bytes of one (level, frame) for `cap` keys and `node_cap` nodes (same carving as carve_work).
+__host__ __device__ inline size_t octree_ws_bytes_dev(int cap, int node_cap) {
+    size_t b = 0;
+    auto take = [&](size_t bytes) { b += (bytes + 15) & ~size_t(15); };
+    take((size_t)cap * 4); take((size_t)cap * 4);
+    take((size_t)cap * 2); take((size_t)cap * 2);
+    take((size_t)cap); take((size_t)cap);
+    take((size_t)node_cap * sizeof(OtNode)); take((size_t)node_cap * sizeof(OtNode));
+    take((size_t)node_cap * sizeof(OtTmp));
+    for (int i = 0; i < 5; ++i) take((size_t)node_cap * 4);
+    take((size_t)kOctMaxThreads * 16);
+    return b;
+}
+
+// smem_budget > 0 (small batches, where the kernel's own latency is what counts): the workspace of a (level, frame) lives
+// in shared memory when it fits — data written in one phase is read in the next, which from global memory is an L2 round
+// trip (stores do not allocate in L1).  Large batches keep the workspace in HBM: there occupancy hides the latency and
+// shared memory would cut the resident CTAs per SM.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_octree(const __grid_constant__ ExtractParams P, int smem_budget) {
+    extern __shared__ __align__(16) uint8_t oct_smem[];
     __shared__ OtShared sh;
     const int level = blockIdx.x, frame = P.frame0 + blockIdx.y;
     const Level& L = P.lv[level];
-    OtWork W = carve_work(P.ot_ws + (long long)frame * P.ot_frame_bytes + L.ot_base, L.cand_cap, L.node_cap);
+    const int32_t* ccount = P.cell_count + (long long)frame * P.total_cells + L.cell_base;
+    bool in_smem = false;
+    int cap_s = 0;
+    if (smem_budget > 0) {
+        // number of candidates of this level = sum of the per-cell counts
+        int part = 0;
+        for (int i = threadIdx.x; i < L.n_cells; i += THREADS) part += ccount[i];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+        if ((threadIdx.x & 31) == 0) sh.warp_sums[threadIdx.x >> 5] = part;
+        __syncthreads();
+        int Mtot = 0;
+        for (int w = 0; w < THREADS / 32; ++w) Mtot += sh.warp_sums[w];
+        __syncthreads();
+        cap_s = max(max(Mtot, L.n_cells), 1);   // kxy[0] doubles as the cell-offset scan buffer
+        in_smem = octree_ws_bytes_dev(cap_s, L.node_cap) <= (size_t)smem_budget;
+    }
+    OtWork W = in_smem ? carve_work(oct_smem, cap_s, L.node_cap)
+                       : carve_work(P.ot_ws + (long long)frame * P.ot_frame_bytes + L.ot_base, L.cand_cap, L.node_cap);
 
     // exclusive scan of the per-cell counts -> emission-order offsets (stored in ordv2... cells may exceed
     // node_cap, so the scan lives in kxy[0] which is free until the root partition)
     int32_t* coff = (int32_t*)W.kxy[0];
-    const int32_t* ccount = P.cell_count + (long long)frame * P.total_cells + L.cell_base;
     OG_FOR(i, L.n_cells) coff[i] = ccount[i];
     OG_SYNC();
     block_exscan(coff, L.n_cells, &sh);
@@ -491,7 +532,7 @@ __global__ void __launch_bounds__(kOctThreads) k_octree(const __grid_constant__ 
     const Cell* cells = P.cells + L.cell_base;
     // one thread per cell copies the cell's run (a handful of candidates): all lanes busy, the loads of different
     // cells overlap
-    for (int ci = threadIdx.x; ci < L.n_cells; ci += kOctThreads) {
+    for (int ci = threadIdx.x; ci < L.n_cells; ci += THREADS) {
         const int n = ccount[ci], dst = coff[ci], src = cells[ci].slot;
         for (int k = 0; k < n; ++k) {
             W.kxy[1][dst + k] = cxy[src + k];
