@@ -863,7 +863,8 @@ int orbgpu_extractor_read_points(orbgpu_extractor* ex, int frame, int level, int
             OG_CUDA(cudaMemcpy(xy.data(), P.sel_xy + (size_t)frame * P.total_sel_cap + L.sel_base, (size_t)n * 4, cudaMemcpyDeviceToHost));
             OG_CUDA(cudaMemcpy(rr.data(), P.sel_resp + (size_t)frame * P.total_sel_cap + L.sel_base, (size_t)n, cudaMemcpyDeviceToHost));
             std::vector<og::KeyPoint> kp(n);
-            OG_CUDA(cudaMemcpy(kp.data(), ex->d_kp + (size_t)frame * ex->kp_cap + off, (size_t)n * sizeof(og::KeyPoint), cudaMemcpyDeviceToHost));
+            // the final records of the last call, wherever that call wrote them (own buffers or the caller's device buffers)
+            OG_CUDA(cudaMemcpy(kp.data(), ex->last_kp + (size_t)frame * ex->last_stride + off, (size_t)n * sizeof(og::KeyPoint), cudaMemcpyDeviceToHost));
             for (int i = 0; i < n; ++i) angles.push_back(kp[i].angle);
         }
     }
