@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <stdexcept>
+#include <thread>
 #include <vector>
 
 #include "ORBextractor.h"
@@ -140,6 +141,31 @@ static void test_stereo() {
     for (int i = 0; i < N; ++i) matched += eu[i] >= 0;
     EXPECT(mvuRight == eu && mvDepth == ed && matched > N / 4, "ComputeStereoMatches: %d of %d matched, vectors %s", matched, N,
            mvuRight == eu ? "equal" : "differ");
+}
+
+// The stereo Frame constructor runs the left and right extractor on two threads (Frame.cc:78-81), and matchers run on the
+// Tracking / LocalMapping / LoopClosing threads: concurrent use of distinct handles must give the serial results.
+static void test_two_threads() {
+    const int W = 640, H = 480;
+    cv::Mat imA = synth_image(W, H), imB = synth_image(W, H);
+    ORBextractor exA(1000, 1.2f, 8, 20, 7), exB(1000, 1.2f, 8, 20, 7);
+    MiniFrame refA, refB;
+    refA.ExtractORB(&exA, imA);
+    refB.ExtractORB(&exB, imB);
+    int bad = 0;
+    for (int round = 0; round < 20; ++round) {
+        MiniFrame a, b;
+        std::thread tl(&MiniFrame::ExtractORB, &a, &exA, imA);
+        std::thread tr(&MiniFrame::ExtractORB, &b, &exB, imB);
+        tl.join();
+        tr.join();
+        bad += a.mvKeys.size() != refA.mvKeys.size() || b.mvKeys.size() != refB.mvKeys.size();
+        for (size_t i = 0; i < a.mvKeys.size() && i < refA.mvKeys.size(); ++i)
+            bad += std::memcmp(&a.mvKeys[i], &refA.mvKeys[i], sizeof(cv::KeyPoint)) != 0 || std::memcmp(a.mDescriptors.ptr((int)i), refA.mDescriptors.ptr((int)i), 32) != 0;
+        for (size_t i = 0; i < b.mvKeys.size() && i < refB.mvKeys.size(); ++i)
+            bad += std::memcmp(&b.mvKeys[i], &refB.mvKeys[i], sizeof(cv::KeyPoint)) != 0 || std::memcmp(b.mDescriptors.ptr((int)i), refB.mDescriptors.ptr((int)i), 32) != 0;
+    }
+    EXPECT(bad == 0 && refA.mvKeys.size() > 500, "two extractor threads: %d differences from the serial results", bad);
 }
 
 // ---- matcher fixtures ----
@@ -446,6 +472,7 @@ int main() {
     }
     test_extractor();
     test_stereo();
+    test_two_threads();
     test_matcher();
     test_track_last_frame();
     printf(fails ? "shell_test: %d FAILURES\n" : "shell_test: all shell results equal the oracle (%d failures)\n", fails);

@@ -23,7 +23,7 @@ def build_exe():
         return EXE
     subprocess.check_call(["g++", "-std=c++14", "-O1", "-Wall", "-Wno-unused-function", f"-I{ROOT}/include", f"-I{ROOT}/shim",
                            f"-I{ROOT}/shim/orbslam2", f"-I{PKG}/csrc/host", "-o", EXE, src, f"-L{PKG}", "-lorbslam2_shell", "-lorbgpu",
-                           f"-L{ROOT}/oracle/_build", "-lorboracle", f"-Wl,-rpath,{PKG}", f"-Wl,-rpath,{ROOT}/oracle/_build"])
+                           f"-L{ROOT}/oracle/_build", "-lorboracle", "-pthread", f"-Wl,-rpath,{PKG}", f"-Wl,-rpath,{ROOT}/oracle/_build"])
     return EXE
 
 
