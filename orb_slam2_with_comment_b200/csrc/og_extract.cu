@@ -265,131 +265,178 @@ __global__ void __launch_bounds__(kSegThreads) k_fast_seg(const __grid_constant_
     mbar_wait(&mbar, 0);
 
     const int min_th = P.min_th, ini_th = P.ini_th;
-    // ---- 1. rejection test, 8 pixels (two words) per step -> one byte of the row's 256-bit candidate bitmap ---------
-    {
-        const uint32_t* T = reinterpret_cast<const uint32_t*>(tile);
-        const int b0 = ox >> 3, nb = ((ox + tw - 1) >> 3) - b0 + 1, total = th * nb;
-        const bool big = min_th >= 127;
-        const uint32_t kadd = (uint32_t)(big ? 0xff - min_th : 0x7f - min_th) * 0x01010101u;
-        auto ge2 = [&](uint32_t c, uint32_t up, uint32_t dn, uint32_t lf, uint32_t rt) {
-            const uint32_t ma = gt_bytes(__vabsdiffu4(c, up), kadd, big), mb = gt_bytes(__vabsdiffu4(c, dn), kadd, big);
-            const uint32_t mc = gt_bytes(__vabsdiffu4(c, lf), kadd, big), md = gt_bytes(__vabsdiffu4(c, rt), kadd, big);
-            const uint32_t g = (ma & mb) | (mc & md) | ((ma ^ mb) & (mc ^ md));
-            return (((g >> 7) * 0x01020408u) >> 24) & 0xfu;   // bits 7,15,23,31 -> 4-bit value
-        };
-        for (int u = t; u < total; u += kSegThreads) {
-            const int r = (int)__umulhi((uint32_t)u, sg.nw_magic);
-            const int br = u - r * nb, B = b0 + br;
-            const uint32_t* row = T + (r + 3) * 64 + 2 * B;
-            const uint32_t c0 = row[0], c1 = row[1], lw = row[-1], rw = row[2];
-            const uint32_t n0 = ge2(c0, row[-3 * 64], row[3 * 64], __funnelshift_r(lw, c0, 8), __funnelshift_r(c0, c1, 24));
-            const uint32_t n1 = ge2(c1, row[-3 * 64 + 1], row[3 * 64 + 1], __funnelshift_r(c0, c1, 8), __funnelshift_r(c1, rw, 24));
-            uint32_t m = n0 | (n1 << 4);
-            if (br == 0) m &= 0xffu << (ox & 7);                                  // columns before the first tested pixel
-            if (br == nb - 1) m &= 0xffu >> (7 - ((ox + tw - 1) & 7));            // ... and after the last
-            mk[r * 32 + B] = (uint8_t)m;
-        }
-    }
-    __syncthreads();
-    // ---- 2. compaction of the surviving pixels into the queue (entry = tile row << 8 | tile column) --------------
-    {
-        const uint16_t* M = reinterpret_cast<const uint16_t*>(mk);
-        const int nhalf = th * 16;
-        for (int i0 = 0; i0 < nhalf; i0 += kSegThreads) {
-            const int i = i0 + t;
-            uint32_t v = i < nhalf ? M[i] : 0u;
-            const int cnt = __popc(v);
-            int inc = cnt;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int o = __shfl_up_sync(0xffffffffu, inc, d);
-                if (lane >= d) inc += o;
-            }
-            int base = 0;
-            if (lane == 31 && inc) base = atomicAdd(&qn, inc);
-            base = __shfl_sync(0xffffffffu, base, 31) + inc - cnt;
-            const int e0 = i << 4;   // 16 rows-of-16 per tile row: row * 256 + 16 * (i & 15)
-            while (v) {
-                const int b = __ffs(v) - 1;
-                v &= v - 1;
-                queue[base++] = (uint16_t)(e0 + b);
-            }
-        }
-    }
-    __syncthreads();
-    const int nq = qn;
-    // ---- 3. exact score of the queued pixels ------------------------------------------------------------------
-    const uint32_t thr2 = (uint32_t)(256 + min_th);
-    for (int q = t; q < nq; q += kSegThreads) {
-        const int e = queue[q];
-        const uint8_t* p = tile + 3 * kSegPitch + e;
-        const uint32_t v = p[0];
-        const uint32_t bias = ((256u - v) << 16) | (256u + v);
-        uint32_t E[16];
-        E[0] = p[3 * kSegPitch] * 0xFFFFu + bias;  E[4] = p[3] * 0xFFFFu + bias;   // lo: 256 + d_k, hi: 256 - d_k
-        E[8] = p[-3 * kSegPitch] * 0xFFFFu + bias; E[12] = p[-3] * 0xFFFFu + bias;
+    __shared__ uint32_t colmask[8];   // pass 1: tile columns of the cells that need the minTh pass (256 bits)
+    __shared__ int need[8], nneed;
+    const int wcell = L.wcell;
+    // Pass 0 works at iniTh for the whole segment: FAST(cell, iniTh) only involves pixels with V >= iniTh (a corner's
+    // neighbours below the threshold cannot beat it), and far fewer pixels pass the rejection test at 20 than at 7.
+    // Only cells left without a survivor (:812) are redone at minTh in pass 1 (a few percent of the cells).
+    for (int pass = 0; pass < 2; ++pass) {
+        const int tcur = pass == 0 ? ini_th : min_th;
+        uint32_t* bm_out = pass == 0 ? bm_ini : bm_min;
+        // ---- 1. rejection test, 8 pixels (two words) per step -> one byte of the row's 256-bit candidate bitmap -----
         {
-            // an arc of 9 covers two of the four compass pixels: the second largest of the four (per half) must pass
-            const uint32_t a = __vmaxu2(E[0], E[4]), b = __vminu2(E[0], E[4]), c = __vmaxu2(E[8], E[12]), d = __vminu2(E[8], E[12]);
-            const uint32_t s2 = __vmaxu2(__vminu2(a, c), __vmaxu2(b, d));
-            if ((s2 & 0xffffu) <= thr2 && (s2 >> 16) <= thr2) continue;
+            const uint32_t* T = reinterpret_cast<const uint32_t*>(tile);
+            const int b0 = ox >> 3, nb = ((ox + tw - 1) >> 3) - b0 + 1, total = th * nb;
+            const bool big = tcur >= 127;
+            const uint32_t kadd = (uint32_t)(big ? 0xff - tcur : 0x7f - tcur) * 0x01010101u;
+            auto ge2 = [&](uint32_t c, uint32_t up, uint32_t dn, uint32_t lf, uint32_t rt) {
+                const uint32_t ma = gt_bytes(__vabsdiffu4(c, up), kadd, big), mb = gt_bytes(__vabsdiffu4(c, dn), kadd, big);
+                const uint32_t mc = gt_bytes(__vabsdiffu4(c, lf), kadd, big), md = gt_bytes(__vabsdiffu4(c, rt), kadd, big);
+                const uint32_t g = (ma & mb) | (mc & md) | ((ma ^ mb) & (mc ^ md));
+                return (((g >> 7) * 0x01020408u) >> 24) & 0xfu;   // bits 7,15,23,31 -> 4-bit value
+            };
+            const uint8_t* cmb = reinterpret_cast<const uint8_t*>(colmask);
+            for (int u = t; u < total; u += kSegThreads) {
+                const int r = (int)__umulhi((uint32_t)u, sg.nw_magic);
+                const int br = u - r * nb, B = b0 + br;
+                uint32_t m = 0;
+                if (pass == 0 || cmb[B]) {
+                    const uint32_t* row = T + (r + 3) * 64 + 2 * B;
+                    const uint32_t c0 = row[0], c1 = row[1], lw = row[-1], rw = row[2];
+                    const uint32_t n0 = ge2(c0, row[-3 * 64], row[3 * 64], __funnelshift_r(lw, c0, 8), __funnelshift_r(c0, c1, 24));
+                    const uint32_t n1 = ge2(c1, row[-3 * 64 + 1], row[3 * 64 + 1], __funnelshift_r(c0, c1, 8), __funnelshift_r(c1, rw, 24));
+                    m = n0 | (n1 << 4);
+                    if (br == 0) m &= 0xffu << (ox & 7);                                  // columns before the first tested pixel
+                    if (br == nb - 1) m &= 0xffu >> (7 - ((ox + tw - 1) & 7));            // ... and after the last
+                    if (pass) m &= cmb[B];
+                }
+                mk[r * 32 + B] = (uint8_t)m;
+            }
         }
-        E[1] = p[3 * kSegPitch + 1] * 0xFFFFu + bias;   E[2] = p[2 * kSegPitch + 2] * 0xFFFFu + bias;   E[3] = p[kSegPitch + 3] * 0xFFFFu + bias;
-        E[5] = p[-kSegPitch + 3] * 0xFFFFu + bias;      E[6] = p[-2 * kSegPitch + 2] * 0xFFFFu + bias;  E[7] = p[-3 * kSegPitch + 1] * 0xFFFFu + bias;
-        E[9] = p[-3 * kSegPitch - 1] * 0xFFFFu + bias;  E[10] = p[-2 * kSegPitch - 2] * 0xFFFFu + bias; E[11] = p[-kSegPitch - 3] * 0xFFFFu + bias;
-        E[13] = p[kSegPitch - 3] * 0xFFFFu + bias;      E[14] = p[2 * kSegPitch - 2] * 0xFFFFu + bias;  E[15] = p[3 * kSegPitch - 1] * 0xFFFFu + bias;
-        uint32_t m3[16], m9[16];
+        __syncthreads();
+        // ---- 2. compaction of the surviving pixels into the queue (entry = tile row << 8 | tile column) ----------
+        {
+            const uint16_t* M = reinterpret_cast<const uint16_t*>(mk);
+            const int nhalf = th * 16;
+            for (int i0 = 0; i0 < nhalf; i0 += kSegThreads) {
+                const int i = i0 + t;
+                uint32_t v = i < nhalf ? M[i] : 0u;
+                const int cnt = __popc(v);
+                int inc = cnt;
 #pragma unroll
-        for (int k = 0; k < 16; ++k) m3[k] = __vimin3_u16x2(E[k], E[(k + 1) & 15], E[(k + 2) & 15]);
-#pragma unroll
-        for (int k = 0; k < 16; ++k) m9[k] = __vimin3_u16x2(m3[k], m3[(k + 3) & 15], m3[(k + 6) & 15]);
-        uint32_t a = __vimax3_u16x2(m9[0], m9[1], m9[2]), b = __vimax3_u16x2(m9[3], m9[4], m9[5]);
-        uint32_t c = __vimax3_u16x2(m9[6], m9[7], m9[8]), d = __vimax3_u16x2(m9[9], m9[10], m9[11]);
-        uint32_t f = __vimax3_u16x2(m9[12], m9[13], m9[14]);
-        a = __vimax3_u16x2(a, b, c);
-        d = __vimax3_u16x2(d, f, m9[15]);
-        a = __vmaxu2(a, d);
-        const int V = max((int)(a & 0xffffu), (int)(a >> 16)) - 257;
-        if (V >= min_th) score[e + kSegPitch + 4 - ox] = (uint8_t)V;   // (row + 1) * 256 + px + 4
-    }
-    __syncthreads();
-    // ---- 4a. the corners among the queued pixels, compacted into the (now dead) tile ---------------------------
-    uint16_t* cq = reinterpret_cast<uint16_t*>(tile);
-    const int cq_cap = hbox * kSegPitch / 2;
-    if (t == 0) qn = 0;
-    __syncthreads();
-    for (int q0 = 0; q0 < nq; q0 += kSegThreads) {
-        const int q = q0 + t;
-        const int e = q < nq ? queue[q] : 0;
-        const bool corner = q < nq && score[e + kSegPitch + 4 - ox] != 0;
-        const unsigned bal = __ballot_sync(0xffffffffu, corner);
-        int base = 0;
-        if (lane == 0 && bal) base = atomicAdd(&qn, __popc(bal));
-        base = __shfl_sync(0xffffffffu, base, 0) + __popc(bal & ((1u << lane) - 1));
-        if (corner && base < cq_cap) cq[base] = (uint16_t)e;
-    }
-    __syncthreads();
-    // ---- 4b. NMS over the corners (all queued pixels if the corner list overflowed its buffer) -------------------
-    const bool use_cq = qn <= cq_cap;
-    const uint16_t* nms_q = use_cq ? cq : queue;
-    const int nms_n = use_cq ? qn : nq;
-    for (int q = t; q < nms_n; q += kSegThreads) {
-        const int e = nms_q[q], r = e >> 8, px = (e & 255) - ox;
-        const uint8_t* s = score + e + kSegPitch + 4 - ox;
-        const int v = s[0];
-        if (v == 0) continue;
-        const int fl = lut[px];
-        bool k = v > s[-kSegPitch] && v > s[kSegPitch];
-        if (!(fl & 1)) k = k && v > s[-1] && v > s[-kSegPitch - 1] && v > s[kSegPitch - 1];
-        if (!(fl & 2)) k = k && v > s[1] && v > s[-kSegPitch + 1] && v > s[kSegPitch + 1];
-        if (k) {
-            // plain shared-memory reductions (atomicOr makes ptxas build a warp-aggregation loop that costs more than it saves here)
-            const uint32_t bit = 1u << (px & 31);
-            asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(smem_u32(&bm_min[r * kBmWords + (px >> 5)])), "r"(bit) : "memory");
-            if (v >= ini_th) asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(smem_u32(&bm_ini[r * kBmWords + (px >> 5)])), "r"(bit) : "memory");
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int o = __shfl_up_sync(0xffffffffu, inc, d);
+                    if (lane >= d) inc += o;
+                }
+                int base = 0;
+                if (lane == 31 && inc) base = atomicAdd(&qn, inc);
+                base = __shfl_sync(0xffffffffu, base, 31) + inc - cnt;
+                const int e0 = i << 4;   // 16 rows-of-16 per tile row: row * 256 + 16 * (i & 15)
+                while (v) {
+                    const int b = __ffs(v) - 1;
+                    v &= v - 1;
+                    queue[base++] = (uint16_t)(e0 + b);
+                }
+            }
         }
+        __syncthreads();
+        const int nq = qn;
+        // ---- 3. exact score of the queued pixels --------------------------------------------------------------
+        const uint32_t thr2 = (uint32_t)(256 + tcur);
+        for (int q = t; q < nq; q += kSegThreads) {
+            const int e = queue[q];
+            const uint8_t* p = tile + 3 * kSegPitch + e;
+            const uint32_t v = p[0];
+            const uint32_t bias = ((256u - v) << 16) | (256u + v);
+            uint32_t E[16];
+            E[0] = p[3 * kSegPitch] * 0xFFFFu + bias;  E[4] = p[3] * 0xFFFFu + bias;   // lo: 256 + d_k, hi: 256 - d_k
+            E[8] = p[-3 * kSegPitch] * 0xFFFFu + bias; E[12] = p[-3] * 0xFFFFu + bias;
+            {
+                // an arc of 9 covers two of the four compass pixels: the second largest of the four (per half) must pass
+                const uint32_t a = __vmaxu2(E[0], E[4]), b = __vminu2(E[0], E[4]), c = __vmaxu2(E[8], E[12]), d = __vminu2(E[8], E[12]);
+                const uint32_t s2 = __vmaxu2(__vminu2(a, c), __vmaxu2(b, d));
+                if ((s2 & 0xffffu) <= thr2 && (s2 >> 16) <= thr2) continue;
+            }
+            E[1] = p[3 * kSegPitch + 1] * 0xFFFFu + bias;   E[2] = p[2 * kSegPitch + 2] * 0xFFFFu + bias;   E[3] = p[kSegPitch + 3] * 0xFFFFu + bias;
+            E[5] = p[-kSegPitch + 3] * 0xFFFFu + bias;      E[6] = p[-2 * kSegPitch + 2] * 0xFFFFu + bias;  E[7] = p[-3 * kSegPitch + 1] * 0xFFFFu + bias;
+            E[9] = p[-3 * kSegPitch - 1] * 0xFFFFu + bias;  E[10] = p[-2 * kSegPitch - 2] * 0xFFFFu + bias; E[11] = p[-kSegPitch - 3] * 0xFFFFu + bias;
+            E[13] = p[kSegPitch - 3] * 0xFFFFu + bias;      E[14] = p[2 * kSegPitch - 2] * 0xFFFFu + bias;  E[15] = p[3 * kSegPitch - 1] * 0xFFFFu + bias;
+            uint32_t m3[16], m9[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) m3[k] = __vimin3_u16x2(E[k], E[(k + 1) & 15], E[(k + 2) & 15]);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) m9[k] = __vimin3_u16x2(m3[k], m3[(k + 3) & 15], m3[(k + 6) & 15]);
+            uint32_t a = __vimax3_u16x2(m9[0], m9[1], m9[2]), b = __vimax3_u16x2(m9[3], m9[4], m9[5]);
+            uint32_t c = __vimax3_u16x2(m9[6], m9[7], m9[8]), d = __vimax3_u16x2(m9[9], m9[10], m9[11]);
+            uint32_t f = __vimax3_u16x2(m9[12], m9[13], m9[14]);
+            a = __vimax3_u16x2(a, b, c);
+            d = __vimax3_u16x2(d, f, m9[15]);
+            a = __vmaxu2(a, d);
+            const int V = max((int)(a & 0xffffu), (int)(a >> 16)) - 257;
+            if (V >= tcur) score[e + kSegPitch + 4 - ox] = (uint8_t)V;   // (row + 1) * 256 + px + 4
+        }
+        __syncthreads();
+        // ---- 4a. the corners among the queued pixels, compacted into the (now dead) tile -----------------------
+        uint16_t* cq = reinterpret_cast<uint16_t*>(tile);
+        const int cq_cap = hbox * kSegPitch / 2;
+        if (t == 0) { qn = 0; nneed = 0; }
+        if (t < 8) need[t] = 0;
+        __syncthreads();
+        for (int q0 = 0; q0 < nq; q0 += kSegThreads) {
+            const int q = q0 + t;
+            const int e = q < nq ? queue[q] : 0;
+            const bool corner = q < nq && score[e + kSegPitch + 4 - ox] >= tcur;
+            const unsigned bal = __ballot_sync(0xffffffffu, corner);
+            int base = 0;
+            if (lane == 0 && bal) base = atomicAdd(&qn, __popc(bal));
+            base = __shfl_sync(0xffffffffu, base, 0) + __popc(bal & ((1u << lane) - 1));
+            if (corner && base < cq_cap) cq[base] = (uint16_t)e;
+        }
+        __syncthreads();
+        // ---- 4b. NMS over the corners (all queued pixels if the corner list overflowed its buffer) ---------------
+        {
+            const bool use_cq = qn <= cq_cap;
+            const uint16_t* nms_q = use_cq ? cq : queue;
+            const int nms_n = use_cq ? qn : nq;
+            for (int q = t; q < nms_n; q += kSegThreads) {
+                const int e = nms_q[q], r = e >> 8, px = (e & 255) - ox;
+                const uint8_t* s = score + e + kSegPitch + 4 - ox;
+                const int v = s[0];
+                if (v < tcur) continue;
+                const int fl = lut[px];
+                // in pass 0 the score map only holds V >= iniTh; in pass 1 a cell's map holds everything >= minTh
+                bool k = v > s[-kSegPitch] && v > s[kSegPitch];
+                if (!(fl & 1)) k = k && v > s[-1] && v > s[-kSegPitch - 1] && v > s[kSegPitch - 1];
+                if (!(fl & 2)) k = k && v > s[1] && v > s[-kSegPitch + 1] && v > s[kSegPitch + 1];
+                if (k) {
+                    // plain shared-memory reduction (atomicOr makes ptxas build a warp-aggregation loop that costs more than it saves)
+                    asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(smem_u32(&bm_out[r * kBmWords + (px >> 5)])), "r"(1u << (px & 31)) : "memory");
+                }
+            }
+        }
+        __syncthreads();
+        if (pass == 1) break;
+        // ---- which cells have no iniTh survivor? (one warp per cell) ----------------------------------------------
+        for (int j = wi; j < sg.ncells; j += kSegThreads / 32) {
+            const int cx = j * wcell, cw = P.cells[sg.first_cell + j].tw;
+            const uint64_t wmask = cw >= 64 ? ~0ull : ((1ull << cw) - 1);
+            uint64_t any = 0;
+            for (int row = lane; row < th; row += 32) {
+                const uint32_t* bw = bm_ini + row * kBmWords + (cx >> 5);
+                const int sh = cx & 31;
+                any |= (((uint64_t)__funnelshift_r(bw[1], bw[2], sh) << 32) | __funnelshift_r(bw[0], bw[1], sh)) & wmask;
+            }
+            if (!__any_sync(0xffffffffu, any != 0) && lane == 0) { need[j] = 1; atomicAdd(&nneed, 1); }
+        }
+        fence_async_smem();   // generic-proxy accesses to the tile region (corner list) are ordered before the TMA reload
+        __syncthreads();
+        if (nneed == 0) break;
+        // ---- prepare pass 1: column mask of the needy cells, fresh tile (the corner list overwrote it), empty queue
+        {
+            const int px = t - ox;
+            const bool on = px >= 0 && px < tw && need[px / wcell];
+            const unsigned bal = __ballot_sync(0xffffffffu, on);
+            if (lane == 0) colmask[wi] = bal;
+            if (t == 0) {
+                qn = 0;
+                mbar_expect_tx(&mbar, (uint32_t)(hbox * kSegPitch));
+                tma_load_3d(tile, tmaps + sg.level, gx, kEdge + sg.y0 - 3, frame, &mbar);
+            }
+        }
+        __syncthreads();
+        mbar_wait(&mbar, 1);
     }
-    __syncthreads();
     // ---- 5. per-cell threshold vote and ordered emission ------------------------------------------------------
     const int wc = L.wcell;
     for (int j = wi; j < sg.ncells; j += kSegThreads / 32) {
