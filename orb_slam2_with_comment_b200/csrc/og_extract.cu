@@ -104,29 +104,30 @@ __global__ void __launch_bounds__(kResizeThreads) k_resize4(const __grid_constan
     const uint4 ta = __ldg(reinterpret_cast<const uint4*>(L.xt + x)), tb = __ldg(reinterpret_cast<const uint4*>(L.xt + x) + 1);
     const uint32_t tw[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};   // per output: (s0 | s1 << 16), (w0 | w1 << 16)
     const int base = (int)(tw[0] & 0xffffu) & ~3;
-    int sel[4], sh[4], w0[4], w1[4];
+    int sel[4], sh[4];
+    uint32_t wq[4];   // (w0 | w1 << 16): the two 11-bit weights as DP2A's 16-bit operand pair
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const int o = (int)(tw[2 * j] & 0xffffu) - base;   // 0..9
         sel[j] = o >> 2;
         sh[j] = 8 * (o & 3);
-        w0[j] = (int)(tw[2 * j + 1] & 0xffffu);
-        w1[j] = (int)(tw[2 * j + 1] >> 16);
+        wq[j] = tw[2 * j + 1];
     }
     const uint8_t* src = level_ptr(P.pyr, S, frame) + (long long)kEdge * S.pitch + kXPad + base;
     uint8_t* dst = level_ptr(P.pyr, L, frame) + (long long)kEdge * L.pitch + kXPad + x;
-    auto hrow = [&](int sy, int (&h)[4]) {
+    // horizontal pass of one source row for the 4 outputs: g = (S[sx]*w0 + S[sx+1]*w1) >> 4, one DP2A per output
+    auto hrow = [&](int sy, uint32_t (&g)[4]) {
         const uint32_t* r = reinterpret_cast<const uint32_t*>(src + (long long)sy * S.pitch);
         const uint32_t W0 = __ldg(r), W1 = __ldg(r + 1), W2 = __ldg(r + 2);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const uint32_t lo = sel[j] == 0 ? W0 : (sel[j] == 1 ? W1 : W2), hi = sel[j] == 0 ? W1 : W2;
-            const uint32_t pr = __funnelshift_r(lo, hi, sh[j]);
-            const int p0 = (int)(pr & 0xffu), p1 = (int)((pr >> 8) & 0xffu);
-            h[j] = resize_hpass(p0, p1, w0[j], w1[j]);
+            const uint32_t pr = __funnelshift_r(lo, hi, sh[j]);   // bytes 0,1 = the two source pixels
+            g[j] = __dp2a_lo(wq[j], pr, 0u) >> 4;
         }
     };
-    int h0[4], h1[4], prev_s1 = -1;
+    uint32_t g0[4], g1[4];
+    int prev_s1 = -1;
 #pragma unroll 1
     for (int r = 0; r < kResizeRows; ++r) {
         const int y = y0 + r;
@@ -134,20 +135,22 @@ __global__ void __launch_bounds__(kResizeThreads) k_resize4(const __grid_constan
         const Tap ty = L.yt[y];
         if (ty.s0 == prev_s1) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) h0[j] = h1[j];
+            for (int j = 0; j < 4; ++j) g0[j] = g1[j];
         } else {
-            hrow(ty.s0, h0);
+            hrow(ty.s0, g0);
         }
         if (ty.s1 == ty.s0) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) h1[j] = h0[j];
+            for (int j = 0; j < 4; ++j) g1[j] = g0[j];
         } else {
-            hrow(ty.s1, h1);
+            hrow(ty.s1, g1);
         }
         prev_s1 = ty.s1;
+        // vertical pass: ((b0 * g0) >> 16) + ((b1 * g1) >> 16) + 2 >> 2, the products' high halves taken with one IMAD.HI each
+        const uint32_t b0 = (uint32_t)ty.w0 << 16, b1 = (uint32_t)ty.w1 << 16;
         uint32_t o[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) o[j] = resize_vpass(h0[j], h1[j], ty.w0, ty.w1);
+        for (int j = 0; j < 4; ++j) o[j] = (__umulhi(b0, g0[j]) + __umulhi(b1, g1[j]) + 2u) >> 2;
         *reinterpret_cast<uint32_t*>(dst + (long long)y * L.pitch) = o[0] | (o[1] << 8) | (o[2] << 16) | (o[3] << 24);
     }
 }
