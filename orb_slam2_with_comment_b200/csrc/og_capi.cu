@@ -67,6 +67,7 @@ struct orbgpu_extractor {
     uint8_t *d_pyr = nullptr, *d_blur = nullptr, *d_images = nullptr, *d_ot = nullptr;
     og::Cell* d_cells = nullptr;
     og::Segment* d_segs = nullptr;
+    bool resize_mlp[og::kMaxLevels] = {};   // per level: every band of 8 output rows reads <= kResizeSpan source rows
     og::BlurTile* d_btiles = nullptr;
     uint32_t* d_ic_tab = nullptr;
     int n_btiles = 0;
@@ -397,6 +398,13 @@ int ensure_geometry(orbgpu_extractor* ex, int w, int h) {
     for (int l = 1; l < ex->nlevels; ++l) {
         ex->P.lv[l].xt = ex->d_taps + G.xt_off[l];
         ex->P.lv[l].yt = ex->d_taps + G.yt_off[l];
+        const og::Tap* yt = G.taps.data() + G.yt_off[l];
+        bool ok = true;
+        for (int y0 = 0; y0 < P.lv[l].h && ok; y0 += og::kResizeRows) {
+            const int y1 = std::min(y0 + og::kResizeRows, P.lv[l].h) - 1;
+            ok = yt[y1].s1 - yt[y0].s0 + 1 <= og::kResizeSpan;
+        }
+        ex->resize_mlp[l] = ok;
     }
     ex->P.pyr = ex->d_pyr;
     ex->P.blur = ex->d_blur;
@@ -442,7 +450,10 @@ int launch_extract(orbgpu_extractor* ex, const uint8_t* d_images, int batch, siz
         if ((double)P.lv[l - 1].w / L.w <= 2.0) {
             const int nwx = (L.w + 3) / 4, bands = (L.h + og::kResizeRows - 1) / og::kResizeRows, n_items = nwx * bands;
             const uint32_t magic = (uint32_t)((0x100000000ull + nwx - 1) / nwx);
-            og::k_resize4<<<dim3((n_items + og::kResizeThreads - 1) / og::kResizeThreads, batch), og::kResizeThreads, 0, st>>>(P, l, nwx, magic, n_items);
+            if (ex->resize_mlp[l])
+                og::k_resize4_mlp<<<dim3((n_items + og::kResizeThreads - 1) / og::kResizeThreads, batch), og::kResizeThreads, 0, st>>>(P, l, nwx, magic, n_items);
+            else
+                og::k_resize4<<<dim3((n_items + og::kResizeThreads - 1) / og::kResizeThreads, batch), og::kResizeThreads, 0, st>>>(P, l, nwx, magic, n_items);
         } else {
             dim3 grid((L.pitch / 4 + 127) / 128, L.rows, batch);
             og::k_resize<<<grid, 128, 0, st>>>(P, l);

@@ -155,6 +155,66 @@ __global__ void __launch_bounds__(kResizeThreads) k_resize4(const __grid_constan
     }
 }
 
+// The same with all loads up front: the 8 output rows of a thread read at most kResizeSpan consecutive source rows (true for
+// scale <= 1.25, checked on the host per level).  All 3 x kResizeSpan word loads are issued back to back (the row loop above
+// waits for every row's three loads before it can start the next), their horizontal passes are parked in shared memory, and
+// the vertical pass picks its two rows from there.
+constexpr int kResizeSpan = 11;
+__global__ void __launch_bounds__(kResizeThreads) k_resize4_mlp(const __grid_constant__ ExtractParams P, int level, int nwx, uint32_t nwx_magic,
+                                                                int n_items) {
+    __shared__ uint4 sg[kResizeSpan][kResizeThreads];
+    const Level& L = P.lv[level];
+    const Level& S = P.lv[level - 1];
+    const int frame = P.frame0 + blockIdx.y;
+    const int id = blockIdx.x * kResizeThreads + threadIdx.x;
+    if (id >= n_items) return;
+    const int band = (int)__umulhi((uint32_t)id, nwx_magic), wx = id - band * nwx;
+    const int x = 4 * wx, y0 = band * kResizeRows;
+    const uint4 ta = __ldg(reinterpret_cast<const uint4*>(L.xt + x)), tb = __ldg(reinterpret_cast<const uint4*>(L.xt + x) + 1);
+    const uint32_t tw[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
+    const int base = (int)(tw[0] & 0xffffu) & ~3;
+    int sel[4], sh[4];
+    uint32_t wq[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int o = (int)(tw[2 * j] & 0xffffu) - base;
+        sel[j] = o >> 2;
+        sh[j] = 8 * (o & 3);
+        wq[j] = tw[2 * j + 1];
+    }
+    const int sfirst = L.yt[y0].s0;
+    const uint8_t* src = level_ptr(P.pyr, S, frame) + (long long)(kEdge + sfirst) * S.pitch + kXPad + base;
+    uint32_t W[kResizeSpan][3];
+#pragma unroll
+    for (int k = 0; k < kResizeSpan; ++k) {
+        const int dy = min(k, S.h - 1 - sfirst);   // rows past the image are never selected; keep the address valid
+        const uint32_t* r = reinterpret_cast<const uint32_t*>(src + (long long)dy * S.pitch);
+        W[k][0] = __ldg(r); W[k][1] = __ldg(r + 1); W[k][2] = __ldg(r + 2);
+    }
+#pragma unroll
+    for (int k = 0; k < kResizeSpan; ++k) {
+        uint32_t g[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t lo = sel[j] == 0 ? W[k][0] : (sel[j] == 1 ? W[k][1] : W[k][2]), hi = sel[j] == 0 ? W[k][1] : W[k][2];
+            g[j] = __dp2a_lo(wq[j], __funnelshift_r(lo, hi, sh[j]), 0u) >> 4;
+        }
+        sg[k][threadIdx.x] = make_uint4(g[0], g[1], g[2], g[3]);
+    }
+    uint8_t* dst = level_ptr(P.pyr, L, frame) + (long long)kEdge * L.pitch + kXPad + x;
+    const int nrows = min(kResizeRows, L.h - y0);
+#pragma unroll 2
+    for (int r = 0; r < nrows; ++r) {
+        const int y = y0 + r;
+        const Tap ty = L.yt[y];
+        const uint4 a = sg[ty.s0 - sfirst][threadIdx.x], b = sg[ty.s1 - sfirst][threadIdx.x];   // own slots only: no barrier needed
+        const uint32_t b0 = (uint32_t)ty.w0 << 16, b1 = (uint32_t)ty.w1 << 16;
+        const uint32_t o0 = (__umulhi(b0, a.x) + __umulhi(b1, b.x) + 2u) >> 2, o1 = (__umulhi(b0, a.y) + __umulhi(b1, b.y) + 2u) >> 2;
+        const uint32_t o2 = (__umulhi(b0, a.z) + __umulhi(b1, b.z) + 2u) >> 2, o3 = (__umulhi(b0, a.w) + __umulhi(b1, b.w) + 2u) >> 2;
+        *reinterpret_cast<uint32_t*>(dst + (long long)y * L.pitch) = o0 | (o1 << 8) | (o2 << 16) | (o3 << 24);
+    }
+}
+
 // The BORDER_REFLECT_101 frame of every level (:1122-1123, :1127).  Work items per level:
 // 38*h "side" items (one byte of the frame left or right of an interior row) and 38 * ceil((w+38)/4) "cap"
 // items (one thread writes 4 bytes of a top/bottom row).  Item -> (level, kind) through the per-level prefix in `B`.
