@@ -291,6 +291,50 @@ int orbgpu_search_by_bow_dev(orbgpu_matcher* m, const orbgpu_frame_set_dev* set1
                              int th_inclusive, int require_mp2, const int64_t* match_off, int32_t* match12_dev,
                              int32_t* match_dist_dev, int32_t* nmatches_dev);
 
+/* ------------------------------------------------------------------------------------------------
+ * Vocabulary — replaces ORBVocabulary::transform (DBoW2 TemplatedVocabulary<FORB::TDescriptor, FORB>,
+ * include/ORBVocabulary.h:31-32) as called by Frame::ComputeBoW (Frame.cc:425-432) and KeyFrame::ComputeBoW
+ * (KeyFrame.cc:59-70): every descriptor descends the vocabulary tree by FORB::distance (FORB.cpp:81-101, first minimum
+ * wins, TemplatedVocabulary.h:1237-1247); the words reached form the BowVector, the nodes passed `levelsup` levels above
+ * the leaves group the feature indices into the FeatureVector the BoW searches consume.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct orbgpu_vocabulary orbgpu_vocabulary;
+
+/* The vocabulary as TemplatedVocabulary::loadFromTextFile reads it (TemplatedVocabulary.h:1338-1423): k, L, scoring
+ * (ScoringType, BowVector.h:45-53: 0 L1_NORM .. 5 DOT_PRODUCT) and weighting (WeightingType, BowVector.h:36-42: 0 TF_IDF,
+ * 1 TF, 2 IDF, 3 BINARY) from the header line, then one record per line: record r describes node r + 1 (node 0 is the
+ * root) — parent[r] (< r + 1), is_leaf[r], desc[r][32], weight[r].  Word ids are handed out to the leaves in record
+ * order (:1407-1414).  At most 32 children per node. */
+int orbgpu_vocabulary_create(orbgpu_vocabulary** out, int device, int k, int L, int scoring, int weighting, int n_records,
+                             const int32_t* parent, const uint8_t* is_leaf, const uint8_t* desc, const double* weight);
+int orbgpu_vocabulary_destroy(orbgpu_vocabulary* v);
+int orbgpu_vocabulary_info(const orbgpu_vocabulary* v, int* n_nodes, int* n_words);
+int orbgpu_vocabulary_sync(orbgpu_vocabulary* v);
+int orbgpu_vocabulary_last_launches(const orbgpu_vocabulary* v);
+
+/* transform(features, BowVector&, FeatureVector&, levelsup) (TemplatedVocabulary.h:1127-1197) for every frame of a batch:
+ * frame f owns descriptor rows [kp_off[f], kp_off[f+1]) of `desc` (at most 8192 per frame).  All outputs are sized by the
+ * caller for n = kp_off[n_frames] entries (the +1 arrays for n + 1) and may be NULL when not wanted:
+ *   BowVector     (std::map<WordId, WordValue>, BowVector.h:58-60): frame f owns entries [bv_off[f], bv_off[f+1]) of
+ *                 bv_word (ascending) / bv_value (after addWeight / addIfNotExist and normalisation, BowVector.cpp:36-90,
+ *                 bit-exact doubles: the sums run in the reference's order);
+ *   FeatureVector (std::map<NodeId, vector<unsigned>>, FeatureVector.h:21-22) in the orbgpu_frame_set layout: frame f owns
+ *                 nodes [fv_node_off[f], fv_node_off[f+1]); node j has id fv_node_id[j] (ascending within the frame) and the
+ *                 frame-local feature indices fv_feat[fv_feat_off[j] .. fv_feat_off[j+1]) in ascending order;
+ *   word_of_feature / node_of_feature: the WordId and the level-(L - levelsup) NodeId of every descriptor
+ *                 (transform(feature, id, weight, &nid, levelsup), :1214-1259).
+ * Features whose word has weight 0 (stopped words, :1185) appear in neither vector.  A leaf shallower than level
+ * L - levelsup (where the reference leaves nid uninitialised) reports its own node id. */
+int orbgpu_bow_transform(orbgpu_vocabulary* v, int n_frames, const int32_t* kp_off, const uint8_t* desc, int levelsup,
+                         int32_t* bv_off, uint32_t* bv_word, double* bv_value, int32_t* fv_node_off, int32_t* fv_node_id,
+                         int32_t* fv_feat_off, int32_t* fv_feat, uint32_t* word_of_feature, uint32_t* node_of_feature);
+/* The same with `kp_off_dev`, `desc_dev` and every output a device pointer on the vocabulary's device (n_features = the host's
+ * copy of kp_off[n_frames], max_per_frame = an upper bound of the rows per frame); enqueued on the vocabulary's stream. */
+int orbgpu_bow_transform_dev(orbgpu_vocabulary* v, int n_frames, const int32_t* kp_off_dev, int n_features, int max_per_frame,
+                             const uint8_t* desc_dev, int levelsup, int32_t* bv_off, uint32_t* bv_word, double* bv_value,
+                             int32_t* fv_node_off, int32_t* fv_node_id, int32_t* fv_feat_off, int32_t* fv_feat,
+                             uint32_t* word_of_feature, uint32_t* node_of_feature);
+
 #ifdef __cplusplus
 }
 #endif

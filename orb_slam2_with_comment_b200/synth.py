@@ -250,3 +250,75 @@ def stereo_pair(w: int, h: int, seed: int, d0: int = 6, bands: int = 9):
         y0, y1 = b * bh, min((b + 1) * bh, h)
         right[y0:y1] = np.roll(left[y0:y1], -(d0 + b), axis=1)
     return left, right
+
+
+def vocabulary_tree(k: int = 10, L: int = 3, seed: int = 7, p_flip: float = 0.12, ragged: bool = False, stop_frac: float = 0.0):
+    """Synthetic DBoW2 vocabulary (stand-in for the missing ORBvoc.txt) as the records of its text file, in file order
+    (TemplatedVocabulary.h:1338-1423: node id = 1 + record index; ids are handed out the way HKmeansStep does — all
+    children of a node first, then each child's subtree, :560-636).  A child's descriptor is its parent's with a fraction
+    of bits flipped, so descents are decisive near the top and full of near-ties at the bottom.  Weights mimic idf values
+    (ln(N/Ni)); `stop_frac` of the words get weight 0 (stopped words, :1185).  `ragged`: some nodes have fewer than k
+    children (k-means clusters can come out empty); every leaf stays at depth L.
+    Returns dict(k, L, parent[int32], is_leaf[u8], desc[n,32 u8], weight[f64])."""
+    rs = np.random.RandomState(seed)
+    parent, is_leaf, desc, weight = [], [], [], []
+
+    def expand(pid, pdesc, level):
+        nch = k if not ragged else int(rs.randint(max(1, k // 2), k + 1))
+        ids = []
+        for _ in range(nch):
+            d = flip_bits(pdesc[None, :], rs, p_flip)[0] if level > 1 else rs.randint(0, 256, 32).astype(np.uint8)
+            parent.append(pid)
+            leaf = level == L
+            is_leaf.append(1 if leaf else 0)
+            desc.append(d)
+            w = float(np.log(rs.uniform(1.5, 400.0))) if leaf else 0.0
+            if leaf and rs.uniform() < stop_frac:
+                w = 0.0
+            weight.append(w)
+            ids.append(len(parent))       # node id of the record just appended
+        if level < L:
+            for i in ids:
+                expand(i, desc[i - 1], level + 1)
+
+    expand(0, np.zeros(32, np.uint8), 1)
+    return {"k": k, "L": L, "parent": np.array(parent, np.int32), "is_leaf": np.array(is_leaf, np.uint8),
+            "desc": np.stack(desc).astype(np.uint8), "weight": np.array(weight, np.float64)}
+
+
+def vocabulary_tree_full(k: int = 10, L: int = 6, seed: int = 7, p_flip: float = 0.10):
+    """The same at ORBvoc size (k=10, L=6: 1,111,110 nodes), vectorised, level by level (breadth-first ids: a valid file
+    order too, since every parent precedes its children)."""
+    rs = np.random.RandomState(seed)
+    parent, is_leaf, desc, weight = [], [], [], []
+    prev_ids = np.zeros(1, np.int64)
+    prev_desc = np.zeros((1, 32), np.uint8)
+    next_id = 1
+    for level in range(1, L + 1):
+        n = len(prev_ids) * k
+        par = np.repeat(prev_ids, k)
+        if level == 1:
+            d = rs.randint(0, 256, (n, 32)).astype(np.uint8)
+        else:
+            flips = np.packbits(rs.uniform(size=(n, 256)) < p_flip, axis=1)
+            d = np.repeat(prev_desc, k, axis=0) ^ flips
+        parent.append(par)
+        is_leaf.append(np.full(n, 1 if level == L else 0, np.uint8))
+        desc.append(d)
+        weight.append(np.log(rs.uniform(1.5, 400.0, n)) if level == L else np.zeros(n))
+        prev_ids = np.arange(next_id, next_id + n, dtype=np.int64)
+        prev_desc = d
+        next_id += n
+    return {"k": k, "L": L, "parent": np.concatenate(parent).astype(np.int32), "is_leaf": np.concatenate(is_leaf),
+            "desc": np.concatenate(desc), "weight": np.concatenate(weight).astype(np.float64)}
+
+
+def vocabulary_descriptors(voc, n: int, seed: int, p_flip: float = 0.06):
+    """n descriptors near random words of the vocabulary (plus 20 % uniform random rows)."""
+    rs = np.random.RandomState(seed)
+    leaves = np.nonzero(voc["is_leaf"])[0]
+    pick = leaves[rs.randint(0, len(leaves), n)]
+    d = flip_bits(voc["desc"][pick], rs, p_flip)
+    r = rs.uniform(size=n) < 0.2
+    d[r] = rs.randint(0, 256, (int(r.sum()), 32)).astype(np.uint8)
+    return d

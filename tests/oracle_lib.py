@@ -288,3 +288,97 @@ def stereo_matches(lib, S, mb, mbf):
     lib.orbs_stereo_matches(kpL.ctypes.data, dL.ctypes.data, len(kpL), kpR.ctypes.data, dR.ctypes.data, len(kpR), PL, PR, lw.ctypes.data,
                             lh.ctypes.data, sc.ctypes.data, isc.ctypes.data, nl, mb, mbf, ur.ctypes.data, dp.ctypes.data, sad.ctypes.data)
     return ur, dp, sad
+
+
+# ---- vocabulary (DBoW2 transform) -------------------------------------------------------------------
+def _bind_voc(lib, prefix):
+    vp, i = C.c_void_p, C.c_int
+    if prefix == "orbo_voc":
+        lib.orbo_voc_create.restype = vp
+        lib.orbo_voc_create.argtypes = [i, i, i, i, i, vp, vp, vp, vp]
+        lib.orbo_voc_free.argtypes = [vp]
+        lib.orbo_voc_words.argtypes = [vp]
+        lib.orbo_voc_transform.argtypes = [vp, vp, i, i, C.POINTER(i), vp, vp, C.POINTER(i), vp, vp, vp, vp, vp]
+        lib.orbo_voc_bench.argtypes = [vp, vp, i, i, i, i]
+    else:
+        lib.dbowref_load.restype = vp
+        lib.dbowref_load.argtypes = [C.c_char_p]
+        lib.dbowref_free.argtypes = [vp]
+        lib.dbowref_words.argtypes = [vp]
+        lib.dbowref_transform.argtypes = [vp, vp, i, i, C.POINTER(i), vp, vp, C.POINTER(i), vp, vp, vp]
+        lib.dbowref_score.restype = C.c_double
+        lib.dbowref_score.argtypes = [vp, i, vp, vp, i, vp, vp]
+    return lib
+
+
+def load_dbow_ref():
+    """The reference's own DBoW2 (oracle/_ref/libdbowref.so); None where it cannot be built and was not shipped."""
+    path = os.path.join(ORACLE_DIR, "_ref", "libdbowref.so")
+    if not os.path.exists(path):
+        if os.path.isdir("/root/reference"):
+            subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "ref"])
+        else:
+            return None
+    return _bind_voc(C.CDLL(path), "dbowref")
+
+
+class _VocBase:
+    def _run(self, fn, desc, levelsup, extra):
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        n = len(desc)
+        bw, bv = np.zeros(max(n, 1), np.uint32), np.zeros(max(n, 1), np.float64)
+        fn_, fo, ff = np.zeros(max(n, 1), np.uint32), np.zeros(n + 1, np.int32), np.zeros(max(n, 1), np.uint32)
+        nb, nf = C.c_int(0), C.c_int(0)
+        vp = C.c_void_p
+        fn(self.h, _p(desc, vp), n, levelsup, C.byref(nb), _p(bw, vp), _p(bv, vp), C.byref(nf), _p(fn_, vp), _p(fo, vp), _p(ff, vp), *extra)
+        return {"bv_word": bw[:nb.value].copy(), "bv_value": bv[:nb.value].copy(), "fv_node_id": fn_[:nf.value].astype(np.int32),
+                "fv_feat_off": fo[:nf.value + 1].copy(), "fv_feat": ff[:fo[nf.value]].astype(np.int32)}
+
+
+class VocabularyOracle(_VocBase):
+    """oracle/bow_oracle.cc (the port)."""
+
+    def __init__(self, lib, rec, scoring=0, weighting=0):
+        self.lib = _bind_voc(lib, "orbo_voc")
+        vp = C.c_void_p
+        self._keep = [np.ascontiguousarray(rec["parent"], np.int32), np.ascontiguousarray(rec["is_leaf"], np.uint8),
+                      np.ascontiguousarray(rec["desc"], np.uint8), np.ascontiguousarray(rec["weight"], np.float64)]
+        self.h = self.lib.orbo_voc_create(int(rec["k"]), int(rec["L"]), scoring, weighting, len(self._keep[0]), *[_p(a, vp) for a in self._keep])
+        assert self.h
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.orbo_voc_free(self.h)
+
+    def words(self):
+        return self.lib.orbo_voc_words(self.h)
+
+    def transform(self, desc, levelsup=4):
+        n = len(np.asarray(desc).reshape(-1, 32))
+        fw, fnode = np.zeros(max(n, 1), np.uint32), np.zeros(max(n, 1), np.uint32)
+        out = self._run(self.lib.orbo_voc_transform, desc, levelsup, (_p(fw, C.c_void_p), _p(fnode, C.c_void_p)))
+        out["word_of_feature"], out["node_of_feature"] = fw[:n], fnode[:n]
+        return out
+
+    def bench(self, desc, n_frames, per, levelsup, threads):
+        desc = np.ascontiguousarray(desc, np.uint8)
+        self.lib.orbo_voc_bench(self.h, _p(desc, C.c_void_p), n_frames, per, levelsup, threads)
+
+
+class VocabularyRef(_VocBase):
+    """The reference's TemplatedVocabulary, loaded from a text file."""
+
+    def __init__(self, lib, text_path):
+        self.lib = lib
+        self.h = lib.dbowref_load(text_path.encode())
+        assert self.h, "reference DBoW2 failed to load the vocabulary text file"
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.dbowref_free(self.h)
+
+    def words(self):
+        return self.lib.dbowref_words(self.h)
+
+    def transform(self, desc, levelsup=4):
+        return self._run(self.lib.dbowref_transform, desc, levelsup, ())
