@@ -208,6 +208,111 @@ def run_matching(args, torch, dist, rank, world, local, barrier):
     return out
 
 
+# ---- vocabulary leg (ORBVocabulary::transform of Frame::ComputeBoW, ORBvoc-shaped tree) ----------------
+VOC_PER_FRAME = 2000
+
+
+def make_voc_workload(frames: int):
+    from orb_slam2_with_comment_b200 import synth
+    voc = synth.vocabulary_tree_full(10, 6, seed=7)
+    desc = synth.vocabulary_descriptors_fast(voc, frames * VOC_PER_FRAME, seed=31)
+    kp_off = (np.arange(frames + 1, dtype=np.int64) * VOC_PER_FRAME).astype(np.int32)
+    return voc, kp_off, desc
+
+
+def cpu_voc_run(voc, desc, frames: int, threads: int):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ol
+    o = ol.VocabularyOracle(ol.load_port(), voc)
+    t0 = time.time()
+    o.bench(desc[:frames * VOC_PER_FRAME], frames, VOC_PER_FRAME, 4, threads)
+    return frames / (time.time() - t0)
+
+
+def run_vocabulary(args, torch, dist, rank, world, local, barrier):
+    """BowVector + FeatureVector of `voc_frames` frames x 2000 descriptors per step (k=10, L=6 synthetic vocabulary, levelsup 4)."""
+    import ctypes as C
+    from orb_slam2_with_comment_b200 import capi, vocabulary
+    dev = torch.device("cuda", local)
+    F = args.voc_frames
+    voc, kp_off, desc = make_voc_workload(F)
+    v = vocabulary.ORBVocabulary(device=local).from_records(voc)
+    L = vocabulary._lib()
+    n = int(kp_off[-1])
+    d_off = torch.from_numpy(kp_off).to(dev)
+    d_desc = torch.from_numpy(desc).to(dev)
+    i32, f64 = torch.int32, torch.float64
+    outs = [torch.empty(F + 1, dtype=i32, device=dev), torch.empty(n, dtype=i32, device=dev), torch.empty(n, dtype=f64, device=dev),
+            torch.empty(F + 1, dtype=i32, device=dev), torch.empty(n, dtype=i32, device=dev), torch.empty(n + 1, dtype=i32, device=dev),
+            torch.empty(n, dtype=i32, device=dev)]
+    torch.cuda.synchronize()
+    sp = C.c_void_p()
+    capi.check(L.orbgpu_vocabulary_stream(v._h, C.byref(sp)))
+    stream = torch.cuda.ExternalStream(sp.value, device=dev)
+
+    def step_dev():
+        capi.check(L.orbgpu_bow_transform_dev(v._h, F, d_off.data_ptr(), n, VOC_PER_FRAME, d_desc.data_ptr(), 4,
+                                              *[C.c_void_p(t.data_ptr()) for t in outs], None, None))
+
+    for _ in range(max(args.warmup, 3)):
+        step_dev()
+    capi.check(L.orbgpu_vocabulary_sync(v._h))
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_dev()
+    e1.record(stream)
+    capi.check(L.orbgpu_vocabulary_sync(v._h))
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = v.last_launches * args.steps
+    n_words = int(outs[0][-1].item())
+
+    # end to end: host descriptors in, host BowVector / FeatureVector arrays out, through orbgpu_bow_transform
+    h_desc = _pinned(desc)
+    h = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in outs]
+
+    def step_host():
+        capi.check(L.orbgpu_bow_transform(v._h, F, kp_off.ctypes.data, h_desc.ctypes.data, 4, *[C.c_void_p(t.data_ptr()) for t in h], None, None))
+
+    step_host()
+    barrier()
+    t0 = time.time()
+    for _ in range(args.steps):
+        step_host()
+    wall_ms = (time.time() - t0) * 1e3
+    barrier()
+    assert int(h[0][-1]) == n_words and torch.equal(h[1][:n_words], outs[1][:n_words].cpu()), "host and device vocabulary paths disagree"
+    if world > 1:
+        t = torch.tensor([ms, wall_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, wall_ms = float(t[0].item()), float(t[1].item())
+    if rank != 0:
+        return None
+    sec = ms / 1e3
+    evals = n * 60   # k x L node distances per descriptor
+    out = {
+        "metric": "BoW frames/s (BowVector + FeatureVector of 2000 descriptors)", "value": world * F * args.steps / sec, "unit": "frames/s",
+        "distance_evals_per_s": world * evals * args.steps / sec, "ms_per_step": ms / args.steps, "gpu_launches": launches,
+        "config": {"workload": f"ORBVocabulary::transform(levelsup 4) of {F} frames x {VOC_PER_FRAME} descriptors per GPU per step; synthetic "
+                               "vocabulary of ORBvoc's shape (k=10, L=6, 1,111,110 nodes, TF_IDF / L1_NORM)", "words_per_frame": n_words / F},
+        "e2e": {"value": world * F * args.steps / (wall_ms / 1e3), "unit": "frames/s", "ms_per_step": wall_ms / args.steps,
+                "h2d_bytes_per_step": int(desc.nbytes + kp_off.nbytes), "d2h_bytes_per_step": int(sum(t.numel() * t.element_size() for t in h))},
+    }
+    if world == 1:
+        cores = os.cpu_count() or 1
+        sample = max(64, 4 * cores)
+        try:
+            c = cpu_voc_run(voc, desc, min(sample, F), cores)
+            out["cpu_baseline"] = {"value": c, "unit": "frames/s", "cores": cores, "kind": "port",
+                                   "sample": f"{min(sample, F)} of the same frames, one frame per std::thread, {cores} threads (oracle/bow_oracle.cc, "
+                                             "restatement of DBoW2's transform, -O2)"}
+        except Exception as e:
+            out["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": cores, "kind": "port", "sample": f"unavailable: {e}"}
+    return out
+
+
 class ClockSampler:
     FIELDS = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
@@ -300,6 +405,14 @@ def run_reference(args):
                             "distance_evals_per_s": c["evals_per_s"], "pairs_per_s": c["pairs_per_s"],
                             "cpu_baseline": {"value": c["matches_per_s"], "unit": "matches/s", "cores": cores, "kind": "port",
                                              "sample": f"{pairs} brute-force 2000x2000 pairs, one pair per std::thread, {cores} threads"}}
+    if not args.no_vocabulary:
+        nfr = max(64, 4 * cores)
+        voc, _, desc = make_voc_workload(nfr)
+        c = cpu_voc_run(voc, desc, nfr, cores)
+        line["vocabulary"] = {"metric": "BoW frames/s (BowVector + FeatureVector of 2000 descriptors)", "value": c, "unit": "frames/s",
+                              "cpu_baseline": {"value": c, "unit": "frames/s", "cores": cores, "kind": "port",
+                                               "sample": f"{nfr} frames x {VOC_PER_FRAME} descriptors, one frame per std::thread, {cores} threads "
+                                                         "(oracle/bow_oracle.cc; k=10, L=6 synthetic vocabulary)"}}
     print(json.dumps(line))
 
 
@@ -401,6 +514,7 @@ def run_ours(args):
     assert int(h_cnt.sum()) == int(d_cnt.sum().item()), "host and device paths disagree"
     ex_launches_total = launches
     matching = None if args.no_matching else run_matching(args, torch, dist, rank, world, local, barrier)
+    vocab = None if args.no_vocabulary else run_vocabulary(args, torch, dist, rank, world, local, barrier)
     clocks = sampler.stop()   # sampled over the extraction and matching timed regions
 
     if rank != 0:
@@ -443,11 +557,13 @@ def run_ours(args):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(B * W * H),
                 "d2h_bytes_per_step": int(B * (ex.kp_cap * 60 + 4)), "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": ex_launches_total + (matching["gpu_launches"] if matching else 0),
+        "gpu_launches": ex_launches_total + (matching["gpu_launches"] if matching else 0) + (vocab["gpu_launches"] if vocab else 0),
         "roofline": roofline,
     }
     if matching:
         line["matching"] = matching
+    if vocab:
+        line["vocabulary"] = vocab
     if world == 1:
         cores = os.cpu_count() or 1
         sample = max(64, 2 * cores)
@@ -471,6 +587,8 @@ def main():
     ap.add_argument("--batch", type=int, default=1024)
     ap.add_argument("--match-pairs", type=int, default=4096, help="brute-force keyframe pairs per GPU per step (matching leg)")
     ap.add_argument("--no-matching", action="store_true")
+    ap.add_argument("--voc-frames", type=int, default=1024, help="frames per GPU per step of the vocabulary (BoW transform) leg")
+    ap.add_argument("--no-vocabulary", action="store_true")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:

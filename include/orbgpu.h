@@ -311,6 +311,8 @@ int orbgpu_vocabulary_destroy(orbgpu_vocabulary* v);
 int orbgpu_vocabulary_info(const orbgpu_vocabulary* v, int* n_nodes, int* n_words);
 int orbgpu_vocabulary_sync(orbgpu_vocabulary* v);
 int orbgpu_vocabulary_last_launches(const orbgpu_vocabulary* v);
+/* The CUDA stream (cudaStream_t) the vocabulary's work is enqueued on, for callers that order their own work after it. */
+int orbgpu_vocabulary_stream(orbgpu_vocabulary* v, void** stream_out);
 
 /* transform(features, BowVector&, FeatureVector&, levelsup) (TemplatedVocabulary.h:1127-1197) for every frame of a batch:
  * frame f owns descriptor rows [kp_off[f], kp_off[f+1]) of `desc` (at most 8192 per frame).  All outputs are sized by the

@@ -452,6 +452,12 @@ int orbgpu_vocabulary_sync(orbgpu_vocabulary* v) {
 
 int orbgpu_vocabulary_last_launches(const orbgpu_vocabulary* v) { return v ? v->last_launches : 0; }
 
+int orbgpu_vocabulary_stream(orbgpu_vocabulary* v, void** stream_out) {
+    if (!v || !stream_out) return og_fail(ORBGPU_ERR_ARG, "null argument");
+    *stream_out = (void*)v->stream;
+    return ORBGPU_OK;
+}
+
 int orbgpu_bow_transform_dev(orbgpu_vocabulary* v, int n_frames, const int32_t* kp_off_dev, int n_features, int max_per_frame,
                              const uint8_t* desc_dev, int levelsup, int32_t* bv_off, uint32_t* bv_word, double* bv_value,
                              int32_t* fv_node_off, int32_t* fv_node_id, int32_t* fv_feat_off, int32_t* fv_feat,

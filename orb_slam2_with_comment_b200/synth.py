@@ -286,9 +286,10 @@ def vocabulary_tree(k: int = 10, L: int = 3, seed: int = 7, p_flip: float = 0.12
             "desc": np.stack(desc).astype(np.uint8), "weight": np.array(weight, np.float64)}
 
 
-def vocabulary_tree_full(k: int = 10, L: int = 6, seed: int = 7, p_flip: float = 0.10):
+def vocabulary_tree_full(k: int = 10, L: int = 6, seed: int = 7):
     """The same at ORBvoc size (k=10, L=6: 1,111,110 nodes), vectorised, level by level (breadth-first ids: a valid file
-    order too, since every parent precedes its children)."""
+    order too, since every parent precedes its children).  A child flips each bit of its parent with probability 1/8
+    (the AND of three random bytes)."""
     rs = np.random.RandomState(seed)
     parent, is_leaf, desc, weight = [], [], [], []
     prev_ids = np.zeros(1, np.int64)
@@ -300,8 +301,8 @@ def vocabulary_tree_full(k: int = 10, L: int = 6, seed: int = 7, p_flip: float =
         if level == 1:
             d = rs.randint(0, 256, (n, 32)).astype(np.uint8)
         else:
-            flips = np.packbits(rs.uniform(size=(n, 256)) < p_flip, axis=1)
-            d = np.repeat(prev_desc, k, axis=0) ^ flips
+            r = np.frombuffer(rs.bytes(3 * n * 32), np.uint8).reshape(3, n, 32)
+            d = np.repeat(prev_desc, k, axis=0) ^ (r[0] & r[1] & r[2])
         parent.append(par)
         is_leaf.append(np.full(n, 1 if level == L else 0, np.uint8))
         desc.append(d)
@@ -321,4 +322,16 @@ def vocabulary_descriptors(voc, n: int, seed: int, p_flip: float = 0.06):
     d = flip_bits(voc["desc"][pick], rs, p_flip)
     r = rs.uniform(size=n) < 0.2
     d[r] = rs.randint(0, 256, (int(r.sum()), 32)).astype(np.uint8)
+    return d
+
+
+def vocabulary_descriptors_fast(voc, n: int, seed: int):
+    """The same for millions of rows: bit flips with probability 1/16 (the AND of four random bytes), 20 % random rows."""
+    rs = np.random.RandomState(seed)
+    leaves = np.nonzero(voc["is_leaf"])[0]
+    pick = leaves[rs.randint(0, len(leaves), n)]
+    r = np.frombuffer(rs.bytes(4 * n * 32), np.uint8).reshape(4, n, 32)
+    d = voc["desc"][pick] ^ (r[0] & r[1] & r[2] & r[3])
+    rnd = rs.uniform(size=n) < 0.2
+    d[rnd] = np.frombuffer(rs.bytes(int(rnd.sum()) * 32), np.uint8).reshape(-1, 32)
     return d

@@ -23,6 +23,7 @@ def _lib():
         L.orbgpu_vocabulary_info.argtypes = [vp, C.POINTER(i), C.POINTER(i)]
         L.orbgpu_vocabulary_sync.argtypes = [vp]
         L.orbgpu_vocabulary_last_launches.argtypes = [vp]
+        L.orbgpu_vocabulary_stream.argtypes = [vp, C.POINTER(vp)]
         L.orbgpu_bow_transform.argtypes = [vp, i, vp, vp, i] + [vp] * 9
         L.orbgpu_bow_transform_dev.argtypes = [vp, i, vp, i, i, vp, i] + [vp] * 9
         _bound = True

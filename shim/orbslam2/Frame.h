@@ -14,7 +14,10 @@
 
 namespace DBoW2 {
 typedef unsigned int NodeId;
+typedef unsigned int WordId;    // BowVector.h:21
+typedef double WordValue;       // BowVector.h:24
 class FeatureVector : public std::map<NodeId, std::vector<unsigned int> > {};
+class BowVector : public std::map<WordId, WordValue> {};   // BowVector.h:58-60
 }  // namespace DBoW2
 
 namespace ORB_SLAM2 {
@@ -47,6 +50,7 @@ public:
     int N;
     std::vector<cv::KeyPoint> mvKeys, mvKeysUn;
     std::vector<float> mvuRight;
+    DBoW2::BowVector mBowVec;
     DBoW2::FeatureVector mFeatVec;
     cv::Mat mDescriptors;
     std::vector<MapPoint*> mvpMapPoints;

@@ -6,9 +6,11 @@
 #include <cstdlib>
 #include <cstring>
 #include <stdexcept>
+#include <string>
 #include <thread>
 #include <vector>
 
+#include "ORBVocabulary.h"
 #include "ORBextractor.h"
 #include "ORBmatcher.h"
 #include "orbgpu.h"
@@ -31,6 +33,9 @@ void orbm_search_for_triangulation(const orbgpu_frame_set*, const orbgpu_frame_s
                                    const float*, const float*, const float*, int, int, int, const int64_t*, int32_t*, int32_t*, int32_t*);
 void orbm_search_by_bow(const orbgpu_frame_set*, const orbgpu_frame_set*, int, const int32_t*, const int32_t*, float, int, int, int, int,
                         const int64_t*, int32_t*, int32_t*, int32_t*);
+void* orbo_voc_create(int, int, int, int, int, const int32_t*, const uint8_t*, const uint8_t*, const double*);
+void orbo_voc_free(void*);
+int orbo_voc_transform(void*, const uint8_t*, int, int, int*, uint32_t*, double*, int*, uint32_t*, int32_t*, uint32_t*, uint32_t*, uint32_t*);
 }
 
 float Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv, Frame::mnMinX, Frame::mnMaxX, Frame::mnMinY, Frame::mnMaxY;
@@ -455,6 +460,86 @@ static void test_track_last_frame() {
     }
 }
 
+// ---- ORBVocabulary::transform as Frame::ComputeBoW calls it (Frame.cc:425-432) -------------------------------------------
+struct VocRecords {
+    int k, L;
+    std::vector<int32_t> parent;
+    std::vector<uint8_t> is_leaf, desc;
+    std::vector<double> weight;
+};
+static void grow(VocRecords& V, int pid, const uint8_t* pdesc, int level) {
+    std::vector<int> ids;
+    const int nch = level == 2 ? V.k - 1 : V.k;   // one level with fewer children
+    for (int c = 0; c < nch; ++c) {
+        uint8_t d[32];
+        for (int b = 0; b < 32; ++b) d[b] = level == 1 ? (uint8_t)rnd() : (uint8_t)(pdesc[b] ^ ((rnd() % 5 == 0) ? (1u << (rnd() % 8)) : 0u));
+        V.parent.push_back(pid);
+        V.is_leaf.push_back(level == V.L);
+        V.desc.insert(V.desc.end(), d, d + 32);
+        V.weight.push_back(level == V.L ? (rnd() % 17 == 0 ? 0.0 : 0.25 + (rnd() % 100000) / 17000.0) : 0.0);
+        ids.push_back((int)V.parent.size());
+    }
+    if (level < V.L)
+        for (size_t i = 0; i < ids.size(); ++i) grow(V, ids[i], &V.desc[(size_t)(ids[i] - 1) * 32], level + 1);
+}
+static std::string write_voc(const VocRecords& V) {
+    char name[] = "/tmp/orbgpu_vocXXXXXX";
+    const int fd = mkstemp(name);
+    FILE* f = fdopen(fd, "w");
+    fprintf(f, "%d %d  0 0", V.k, V.L);
+    for (size_t r = 0; r < V.parent.size(); ++r) {
+        fprintf(f, "\n%d %d ", V.parent[r], (int)V.is_leaf[r]);
+        for (int b = 0; b < 32; ++b) fprintf(f, "%d ", (int)V.desc[r * 32 + b]);
+        fprintf(f, " %.17g", V.weight[r]);
+    }
+    fclose(f);
+    return name;
+}
+static std::vector<cv::Mat> toDescriptorVector(const cv::Mat& D) {   // Converter.cc:29-37
+    std::vector<cv::Mat> v;
+    v.reserve(D.rows);
+    for (int j = 0; j < D.rows; ++j) v.push_back(D.row(j));
+    return v;
+}
+static void test_vocabulary() {
+    VocRecords V;
+    V.k = 6; V.L = 4;
+    const uint8_t zero[32] = {0};
+    grow(V, 0, zero, 1);
+    const std::string path = write_voc(V);
+    ORBVocabulary voc;
+    EXPECT(voc.loadFromTextFile(path), "loadFromTextFile failed");
+    remove(path.c_str());
+    void* o = orbo_voc_create(V.k, V.L, 0, 0, (int)V.parent.size(), V.parent.data(), V.is_leaf.data(), V.desc.data(), V.weight.data());
+    for (int n : {0, 1, 1500}) {
+        Frame F;
+        F.mDescriptors = cv::Mat(n, 32, CV_8U);
+        for (int i = 0; i < n; ++i) {
+            const size_t leaf = rnd() % V.parent.size();
+            for (int b = 0; b < 32; ++b) F.mDescriptors.at<uchar>(i, b) = (uint8_t)(V.desc[leaf * 32 + b] ^ ((rnd() % 9 == 0) ? (1u << (rnd() % 8)) : 0u));
+        }
+        voc.transform(toDescriptorVector(F.mDescriptors), F.mBowVec, F.mFeatVec, 2);   // Frame::ComputeBoW with levelsup 2 of 4 levels
+        std::vector<uint32_t> bw(n + 1), fn(n + 1), ff(n + 1);
+        std::vector<double> bv(n + 1);
+        std::vector<int32_t> fo(n + 2);
+        int nb = 0, nf = 0;
+        orbo_voc_transform(o, n ? F.mDescriptors.ptr(0) : zero, n, 2, &nb, bw.data(), bv.data(), &nf, fn.data(), fo.data(), ff.data(), 0, 0);
+        EXPECT((int)F.mBowVec.size() == nb && (int)F.mFeatVec.size() == nf, "vocabulary n=%d: %zu words / %zu nodes, oracle %d / %d", n,
+               F.mBowVec.size(), F.mFeatVec.size(), nb, nf);
+        int i = 0, bad = 0;
+        for (DBoW2::BowVector::const_iterator it = F.mBowVec.begin(); it != F.mBowVec.end() && i < nb; ++it, ++i)
+            bad += it->first != bw[i] || it->second != bv[i];
+        int j = 0;
+        for (DBoW2::FeatureVector::const_iterator it = F.mFeatVec.begin(); it != F.mFeatVec.end() && j < nf; ++it, ++j) {
+            bad += it->first != fn[j] || (int)it->second.size() != fo[j + 1] - fo[j];
+            for (size_t q = 0; q < it->second.size() && (int)q < fo[j + 1] - fo[j]; ++q) bad += it->second[q] != ff[fo[j] + q];
+        }
+        EXPECT(bad == 0, "vocabulary n=%d: %d entries differ from the oracle", n, bad);
+        if (n == 1500) printf("vocabulary: %zu words, %zu nodes for %d features (oracle equal: %s)\n", F.mBowVec.size(), F.mFeatVec.size(), n, bad ? "no" : "yes");
+    }
+    orbo_voc_free(o);
+}
+
 int main() {
     int ndev = 0;
     if (orbgpu_device_count(&ndev) != 0 || ndev == 0) {
@@ -468,13 +553,21 @@ int main() {
             KeyFrame a(k, std::vector<float>(10, -1.f), d, g_sf, g_s2, 1, 1, 0, 0), b(k, std::vector<float>(10, -1.f), d, g_sf, g_s2, 1, 1, 0, 0);
             ORBmatcher m; std::vector<MapPoint*> out; m.SearchByBoW(&a, &b, out);
         } catch (const std::runtime_error& e) { ++thrown; printf("matcher: %s\n", e.what()); }
-        return thrown == 2 ? 3 : 1;
+        try {
+            VocRecords V; V.k = 3; V.L = 2; const uint8_t z[32] = {0}; grow(V, 0, z, 1);
+            const std::string path = write_voc(V);
+            ORBVocabulary voc;
+            struct Rm { std::string p; ~Rm() { remove(p.c_str()); } } rm = {path};
+            voc.loadFromTextFile(path);
+        } catch (const std::runtime_error& e) { ++thrown; printf("vocabulary: %s\n", e.what()); }
+        return thrown == 3 ? 3 : 1;
     }
     test_extractor();
     test_stereo();
     test_two_threads();
     test_matcher();
     test_track_last_frame();
+    test_vocabulary();
     printf(fails ? "shell_test: %d FAILURES\n" : "shell_test: all shell results equal the oracle (%d failures)\n", fails);
     return fails ? 1 : 0;
 }

@@ -21,7 +21,7 @@ def build_exe():
     deps = [src, os.path.join(PKG, "liborbslam2_shell.so"), os.path.join(ROOT, "oracle", "_build", "liborboracle.so")]
     if os.path.exists(EXE) and all(os.path.getmtime(EXE) > os.path.getmtime(d) for d in deps):
         return EXE
-    subprocess.check_call(["g++", "-std=c++14", "-O1", "-Wall", "-Wno-unused-function", f"-I{ROOT}/include", f"-I{ROOT}/shim",
+    subprocess.check_call(["g++", "-std=c++14", "-O1", "-Wall", "-Wno-unused-function", "-DORBGPU_SHELL_STANDALONE", f"-I{ROOT}/include", f"-I{ROOT}/shim",
                            f"-I{ROOT}/shim/orbslam2", f"-I{PKG}/csrc/host", "-o", EXE, src, f"-L{PKG}", "-lorbslam2_shell", "-lorbgpu",
                            f"-L{ROOT}/oracle/_build", "-lorboracle", "-pthread", f"-Wl,-rpath,{PKG}", f"-Wl,-rpath,{ROOT}/oracle/_build"])
     return EXE
@@ -34,7 +34,7 @@ def test_shells_compile_link_and_fail_loudly_without_a_device():
         pytest.skip("a GPU is present: covered by the gpu test")
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 3, r.stdout + r.stderr
-    assert r.stdout.count("no CUDA device") == 2
+    assert r.stdout.count("no CUDA device") == 3
 
 
 @pytest.mark.gpu
@@ -43,3 +43,51 @@ def test_shells_equal_oracle_on_gpu():
     r = subprocess.run([exe], capture_output=True, text=True)
     print(r.stdout[-2000:])
     assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
+
+
+DERIVED = os.path.join(ROOT, "oracle", "_ref", "vocab_derived_test")
+
+
+def _derived_inputs(tmp_path):
+    import numpy as np
+    from orb_slam2_with_comment_b200 import synth, vocabulary
+    voc = synth.vocabulary_tree(k=9, L=4, seed=21, ragged=True, stop_frac=0.1)
+    path = str(tmp_path / "voc.txt")
+    vocabulary.write_text_file(path, voc)
+    desc = synth.vocabulary_descriptors(voc, 1900, seed=5)
+    dpath = str(tmp_path / "desc.bin")
+    desc.tofile(dpath)
+    return path, dpath
+
+
+def _build_derived():
+    if os.path.isdir("/root/reference"):
+        from orb_slam2_with_comment_b200 import build
+        build.build()
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref"])
+    return os.path.exists(DERIVED)
+
+
+def test_derived_vocabulary_builds_against_reference_dbow2_and_fails_loudly(tmp_path):
+    """The deployment form of the ORBVocabulary shell (derived from the reference's TemplatedVocabulary) compiles and links
+    against the reference's DBoW2 sources; without a device it reports the missing device."""
+    import torch
+    if not _build_derived():
+        pytest.skip("needs /root/reference (or the prebuilt oracle/_ref/vocab_derived_test)")
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: covered by the gpu test")
+    path, dpath = _derived_inputs(tmp_path)
+    r = subprocess.run([DERIVED, path, dpath, "2"], capture_output=True, text=True)
+    assert r.returncode == 3 and "no CUDA device" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_derived_vocabulary_equals_reference_transform_on_gpu(tmp_path):
+    """GPU transform vs the reference's own CPU transform on the same object (maps compared exactly, doubles included)."""
+    if not _build_derived():
+        pytest.skip("oracle/_ref/vocab_derived_test was not shipped")
+    path, dpath = _derived_inputs(tmp_path)
+    for levelsup in ("2", "0", "4"):
+        r = subprocess.run([DERIVED, path, dpath, levelsup], capture_output=True, text=True)
+        print(r.stdout)
+        assert r.returncode == 0, r.stdout + r.stderr

@@ -58,7 +58,7 @@ def test_orbvoc_sized_vocabulary():
     rs = np.random.RandomState(5)
     per = rs.randint(1800, 2013, 64)
     kp_off = np.concatenate([[0], np.cumsum(per)]).astype(np.int32)
-    desc = synth.vocabulary_descriptors(voc, int(kp_off[-1]), seed=77)
+    desc = synth.vocabulary_descriptors_fast(voc, int(kp_off[-1]), seed=77)
     v = ORBVocabulary().from_records(voc)
     assert v.size() == 10 ** 6
     out = v.transform_batch(kp_off, desc, 4)
