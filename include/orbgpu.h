@@ -337,6 +337,24 @@ int orbgpu_bow_transform_dev(orbgpu_vocabulary* v, int n_frames, const int32_t* 
                              int32_t* fv_node_off, int32_t* fv_node_id, int32_t* fv_feat_off, int32_t* fv_feat,
                              uint32_t* word_of_feature, uint32_t* node_of_feature);
 
+/* ------------------------------------------------------------------------------------------------
+ * Chaining on the device: extraction -> vocabulary -> matching without a host round trip.
+ * Builds a device-resident frame set from the batch `ex` has just processed (its key points and descriptors are compacted
+ * where they lie in HBM; they serve as mvKeysUn, i.e. an undistorted / rectified camera as in the KITTI and EuRoC-rectified
+ * configurations — with distortion, undistort on the host and use orbgpu_frame_set_upload).  With `voc` != NULL every frame's
+ * FeatureVector is computed by orbgpu_bow_transform_dev (levelsup as in Frame::ComputeBoW) and attached.  kp_flag fills
+ * kp_flags (meaning per search function); u_right_dev (optional, device, [batch][u_right_stride], e.g. the output of
+ * orbgpu_stereo_matches_dev) becomes mvuRight; grid (optional, host, 4 floats: mnMinX, mnMinY, mfGridElementWidthInv,
+ * mfGridElementHeightInv) is shared by all frames.  Only the per-frame counts travel to the host.  Release with
+ * orbgpu_frame_set_release. */
+int orbgpu_frame_set_from_extraction(orbgpu_matcher* m, orbgpu_extractor* ex, orbgpu_vocabulary* voc, int levelsup, int kp_flag,
+                                     const float* u_right_dev, int u_right_stride, const float* grid, orbgpu_frame_set_dev** out);
+/* Sizes of a device-resident frame set; kp_off (may be NULL) receives n_frames + 1 offsets. */
+int orbgpu_frame_set_dev_info(const orbgpu_frame_set_dev* fs, int* n_frames, int32_t* kp_off, int* n_nodes, int* n_feat);
+/* Copies arrays of a device-resident frame set to the host (any pointer may be NULL; sizes from orbgpu_frame_set_dev_info). */
+int orbgpu_frame_set_download(orbgpu_matcher* m, const orbgpu_frame_set_dev* fs, orbgpu_keypoint* keys, uint8_t* desc,
+                              int32_t* fv_node_off, int32_t* fv_node_id, int32_t* fv_feat_off, int32_t* fv_feat);
+
 #ifdef __cplusplus
 }
 #endif

@@ -794,6 +794,21 @@ int orbgpu_extractor_stream(orbgpu_extractor* ex, void** stream_out) {
 
 int orbgpu_extractor_last_launches(const orbgpu_extractor* ex) { return ex ? ex->last_launches : 0; }
 
+}  // extern "C" (re-opened below)
+
+// Internal (not part of the C ABI): where the results of the extractor's last batch lie in HBM — consumed by
+// orbgpu_frame_set_from_extraction (og_match.cu).
+int og_extractor_last_results(orbgpu_extractor* ex, int* device, int* batch, int* stride, const og::KeyPoint** kp, const uint8_t** desc,
+                              const int32_t** counts, cudaStream_t* stream) {
+    if (!ex) return fail(ORBGPU_ERR_ARG, "null extractor");
+    if (ex->last_batch < 1 || !ex->last_kp) return fail(ORBGPU_ERR_ARG, "the extractor has not processed a batch yet");
+    *device = ex->device; *batch = ex->last_batch; *stride = ex->last_stride;
+    *kp = ex->last_kp; *desc = ex->last_desc; *counts = ex->last_counts; *stream = ex->stream;
+    return ORBGPU_OK;
+}
+
+extern "C" {
+
 int orbgpu_extractor_set_profiling(orbgpu_extractor* ex, int enable) {
     if (!ex) return fail(ORBGPU_ERR_ARG, "null extractor");
     OG_CUDA(cudaSetDevice(ex->device));

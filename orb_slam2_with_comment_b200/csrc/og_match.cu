@@ -1751,3 +1751,176 @@ int orbgpu_search_windowed(orbgpu_matcher* m, const orbgpu_frame_set* frames, co
 }
 
 }  // extern "C"
+
+// ---- frame set straight from an extractor's last batch (+ vocabulary transform), nothing leaves the device -------------
+int og_extractor_last_results(orbgpu_extractor* ex, int* device, int* batch, int* stride, const og::KeyPoint** kp, const uint8_t** desc,
+                              const int32_t** counts, cudaStream_t* stream);   // og_capi.cu
+
+namespace og {
+// one block per frame: strided extractor output -> the concatenated layout of a frame set
+__global__ void __launch_bounds__(256) k_compact_extraction(const KeyPoint* __restrict__ kp, const uint8_t* __restrict__ desc,
+                                                            const float* __restrict__ u_right, int stride, int ur_stride,
+                                                            const int32_t* __restrict__ kp_off, KeyPoint* __restrict__ kp_out,
+                                                            uint8_t* __restrict__ desc_out, float* __restrict__ ur_out) {
+    const int f = blockIdx.x, base = kp_off[f], n = kp_off[f + 1] - base;
+    const uint32_t* ks = reinterpret_cast<const uint32_t*>(kp + (size_t)f * stride);
+    uint32_t* kd = reinterpret_cast<uint32_t*>(kp_out + base);
+    for (int i = threadIdx.x; i < n * 7; i += 256) kd[i] = ks[i];
+    const uint4* ds = reinterpret_cast<const uint4*>(desc + (size_t)f * stride * 32);
+    uint4* dd = reinterpret_cast<uint4*>(desc_out + (size_t)base * 32);
+    for (int i = threadIdx.x; i < n * 2; i += 256) dd[i] = ds[i];
+    if (u_right)
+        for (int i = threadIdx.x; i < n; i += 256) ur_out[base + i] = u_right[(size_t)f * ur_stride + i];
+}
+__global__ void k_gather_i32(const int32_t* __restrict__ src, const int32_t* __restrict__ idx, int n, int32_t* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = src[idx[i]];
+}
+}  // namespace og
+
+extern "C" int orbgpu_frame_set_from_extraction(orbgpu_matcher* m, orbgpu_extractor* ex, orbgpu_vocabulary* voc, int levelsup, int kp_flag,
+                                                const float* u_right_dev, int u_right_stride, const float* grid,
+                                                orbgpu_frame_set_dev** out) {
+    int rc = check_matcher(m);
+    if (rc) return rc;
+    if (!out) return og_fail(ORBGPU_ERR_ARG, "null out");
+    *out = nullptr;
+    int dev = 0, batch = 0, stride = 0;
+    const og::KeyPoint* kp = nullptr;
+    const uint8_t* desc = nullptr;
+    const int32_t* counts = nullptr;
+    cudaStream_t ex_stream = nullptr;
+    if ((rc = og_extractor_last_results(ex, &dev, &batch, &stride, &kp, &desc, &counts, &ex_stream))) return rc;
+    if (dev != m->device) return og_fail(ORBGPU_ERR_ARG, "frame_set_from_extraction: extractor and matcher live on different devices");
+    if (u_right_dev && u_right_stride < stride) return og_fail(ORBGPU_ERR_ARG, "frame_set_from_extraction: u_right stride too small");
+    cudaStream_t st = m->stream;
+    // the per-frame key-point counts come to the host: the searches plan their launches from them
+    std::vector<int32_t> cnt(batch);
+    OGM_CUDA(cudaMemcpyAsync(cnt.data(), counts, (size_t)batch * 4, cudaMemcpyDeviceToHost, ex_stream));
+    OGM_CUDA(cudaStreamSynchronize(ex_stream));
+    orbgpu_frame_set_dev* fs = new orbgpu_frame_set_dev();
+    fs->device = m->device;
+    fs->n_frames = batch;
+    fs->h_kp_off.resize(batch + 1);
+    fs->h_kp_off[0] = 0;
+    for (int f = 0; f < batch; ++f) {
+        fs->h_kp_off[f + 1] = fs->h_kp_off[f] + cnt[f];
+        fs->max_kp = std::max(fs->max_kp, cnt[f]);
+    }
+    fs->nkp = fs->h_kp_off[batch];
+    auto bail = [&](int code) { free_owned(fs->owned); delete fs; return code; };
+    auto alloc = [&](size_t bytes, void** p) -> cudaError_t {
+        cudaError_t e = cudaMalloc(p, std::max<size_t>(bytes, 256));
+        if (e == cudaSuccess) fs->owned.push_back(*p);
+        return e;
+    };
+#define OGF_CUDA(expr)                                                                                             \
+    do {                                                                                                           \
+        cudaError_t e_ = (expr);                                                                                   \
+        if (e_ != cudaSuccess) return bail(og_fail(ORBGPU_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_))); \
+    } while (0)
+    const size_t nkp = (size_t)fs->nkp;
+    void *d_off, *d_keys, *d_desc, *d_flags, *d_ur = nullptr, *d_grid = nullptr;
+    OGF_CUDA(alloc((size_t)(batch + 1) * 4, &d_off));
+    OGF_CUDA(alloc(nkp * sizeof(og::KeyPoint), &d_keys));
+    OGF_CUDA(alloc(nkp * 32, &d_desc));
+    OGF_CUDA(alloc(nkp, &d_flags));
+    if (u_right_dev) OGF_CUDA(alloc(nkp * 4, &d_ur));
+    OGF_CUDA(cudaMemcpyAsync(d_off, fs->h_kp_off.data(), (size_t)(batch + 1) * 4, cudaMemcpyHostToDevice, st));
+    OGF_CUDA(cudaMemsetAsync(d_flags, kp_flag & 0xff, std::max<size_t>(nkp, 1), st));
+    og::k_compact_extraction<<<batch, 256, 0, st>>>(kp, desc, u_right_dev, stride, u_right_stride, (const int32_t*)d_off, (og::KeyPoint*)d_keys,
+                                                   (uint8_t*)d_desc, (float*)d_ur);
+    fs->v.kp_off = (const int32_t*)d_off;
+    fs->v.keys = (const og::KeyPoint*)d_keys;
+    fs->v.desc = (const uint8_t*)d_desc;
+    fs->v.flags = (const uint8_t*)d_flags;
+    fs->v.u_right = (const float*)d_ur;
+    if (grid) {
+        std::vector<float> g((size_t)batch * 4);
+        for (int f = 0; f < batch; ++f) std::copy(grid, grid + 4, g.begin() + (size_t)f * 4);
+        OGF_CUDA(alloc(g.size() * 4, &d_grid));
+        OGF_CUDA(cudaMemcpyAsync(d_grid, g.data(), g.size() * 4, cudaMemcpyHostToDevice, st));
+        OGF_CUDA(cudaStreamSynchronize(st));   // g is a local
+        fs->v.grid = (const float*)d_grid;
+        fs->has_grid = true;
+    }
+    if (voc) {
+        if (fs->max_kp > 8192) return bail(og_fail(ORBGPU_ERR_CAPACITY, "frame_set_from_extraction: more than 8192 key points in one frame"));
+        void *d_node_off, *d_node_id, *d_feat_off, *d_feat, *d_ent;
+        OGF_CUDA(alloc((size_t)(batch + 1) * 4, &d_node_off));
+        OGF_CUDA(alloc(nkp * 4, &d_node_id));
+        OGF_CUDA(alloc((nkp + 1) * 4, &d_feat_off));
+        OGF_CUDA(alloc(nkp * 4, &d_feat));
+        OGF_CUDA(alloc((size_t)(batch + 1) * 4, &d_ent));
+        void* vs = nullptr;
+        if (orbgpu_vocabulary_stream(voc, &vs) != ORBGPU_OK) return bail(ORBGPU_ERR_ARG);
+        cudaEvent_t ev;
+        OGF_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        cudaError_t ce = cudaEventRecord(ev, st);
+        if (ce == cudaSuccess) ce = cudaStreamWaitEvent((cudaStream_t)vs, ev, 0);
+        int vrc = ORBGPU_OK;
+        if (ce == cudaSuccess)
+            vrc = orbgpu_bow_transform_dev(voc, batch, (const int32_t*)d_off, fs->nkp, fs->max_kp, (const uint8_t*)d_desc, levelsup, nullptr, nullptr,
+                                           nullptr, (int32_t*)d_node_off, (int32_t*)d_node_id, (int32_t*)d_feat_off, (int32_t*)d_feat, nullptr, nullptr);
+        if (ce == cudaSuccess && vrc == ORBGPU_OK) ce = cudaEventRecord(ev, (cudaStream_t)vs);
+        if (ce == cudaSuccess && vrc == ORBGPU_OK) ce = cudaStreamWaitEvent(st, ev, 0);
+        cudaEventDestroy(ev);
+        if (vrc != ORBGPU_OK) return bail(vrc);
+        OGF_CUDA(ce);
+        // per-frame node / entry counts back to the host (the BoW searches size their work lists from them)
+        og::k_gather_i32<<<(batch + 1 + 255) / 256, 256, 0, st>>>((const int32_t*)d_feat_off, (const int32_t*)d_node_off, batch + 1, (int32_t*)d_ent);
+        std::vector<int32_t> node_off(batch + 1), ent_off(batch + 1);
+        OGF_CUDA(cudaMemcpyAsync(node_off.data(), d_node_off, (size_t)(batch + 1) * 4, cudaMemcpyDeviceToHost, st));
+        OGF_CUDA(cudaMemcpyAsync(ent_off.data(), d_ent, (size_t)(batch + 1) * 4, cudaMemcpyDeviceToHost, st));
+        OGF_CUDA(cudaStreamSynchronize(st));
+        fs->has_fv = true;
+        fs->nnodes = node_off[batch];
+        fs->nfeat = ent_off[batch];
+        fs->h_node_cnt.resize(batch);
+        fs->h_ent_cnt.resize(batch);
+        for (int f = 0; f < batch; ++f) {
+            fs->h_node_cnt[f] = node_off[f + 1] - node_off[f];
+            fs->h_ent_cnt[f] = ent_off[f + 1] - ent_off[f];
+            fs->max_nodes = std::max(fs->max_nodes, fs->h_node_cnt[f]);
+        }
+        fs->v.node_off = (const int32_t*)d_node_off;
+        fs->v.node_id = (const int32_t*)d_node_id;
+        fs->v.feat_off = (const int32_t*)d_feat_off;
+        fs->v.feat = (const int32_t*)d_feat;
+    } else {
+        OGF_CUDA(cudaStreamSynchronize(st));
+    }
+    OGF_CUDA(cudaGetLastError());
+#undef OGF_CUDA
+    *out = fs;
+    return ORBGPU_OK;
+}
+
+extern "C" int orbgpu_frame_set_dev_info(const orbgpu_frame_set_dev* fs, int* n_frames, int32_t* kp_off, int* n_nodes, int* n_feat) {
+    if (!fs) return og_fail(ORBGPU_ERR_ARG, "null frame set");
+    if (n_frames) *n_frames = fs->n_frames;
+    if (kp_off) std::copy(fs->h_kp_off.begin(), fs->h_kp_off.end(), kp_off);
+    if (n_nodes) *n_nodes = fs->nnodes;
+    if (n_feat) *n_feat = fs->nfeat;
+    return ORBGPU_OK;
+}
+
+/* Copies the arrays of a device-resident frame set back to the host (any pointer may be NULL); sizes as reported by
+ * orbgpu_frame_set_dev_info. */
+extern "C" int orbgpu_frame_set_download(orbgpu_matcher* m, const orbgpu_frame_set_dev* fs, orbgpu_keypoint* keys, uint8_t* desc, int32_t* fv_node_off,
+                                         int32_t* fv_node_id, int32_t* fv_feat_off, int32_t* fv_feat) {
+    int rc = check_matcher(m);
+    if (rc) return rc;
+    if (!fs) return og_fail(ORBGPU_ERR_ARG, "null frame set");
+    cudaStream_t st = m->stream;
+    if (keys && fs->nkp) OGM_CUDA(cudaMemcpyAsync(keys, fs->v.keys, (size_t)fs->nkp * sizeof(og::KeyPoint), cudaMemcpyDeviceToHost, st));
+    if (desc && fs->nkp) OGM_CUDA(cudaMemcpyAsync(desc, fs->v.desc, (size_t)fs->nkp * 32, cudaMemcpyDeviceToHost, st));
+    if (fs->has_fv) {
+        if (fv_node_off) OGM_CUDA(cudaMemcpyAsync(fv_node_off, fs->v.node_off, (size_t)(fs->n_frames + 1) * 4, cudaMemcpyDeviceToHost, st));
+        if (fv_node_id && fs->nnodes) OGM_CUDA(cudaMemcpyAsync(fv_node_id, fs->v.node_id, (size_t)fs->nnodes * 4, cudaMemcpyDeviceToHost, st));
+        if (fv_feat_off) OGM_CUDA(cudaMemcpyAsync(fv_feat_off, fs->v.feat_off, (size_t)(fs->nnodes + 1) * 4, cudaMemcpyDeviceToHost, st));
+        if (fv_feat && fs->nfeat) OGM_CUDA(cudaMemcpyAsync(fv_feat, fs->v.feat, (size_t)fs->nfeat * 4, cudaMemcpyDeviceToHost, st));
+    }
+    OGM_CUDA(cudaStreamSynchronize(st));
+    return ORBGPU_OK;
+}

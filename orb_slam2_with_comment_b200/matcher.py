@@ -138,6 +138,9 @@ def _bind(L):
     L.orbgpu_search_for_triangulation_dev.argtypes = [vp, vp, vp, i, vp, vp, vp, vp, vp, vp, i, i, i, vp, vp, vp, vp]
     L.orbgpu_search_by_bow.argtypes = [vp, C.POINTER(CFrameSet), C.POINTER(CFrameSet), i, vp, vp, f, i, i, i, i, vp, vp, vp, vp]
     L.orbgpu_search_by_bow_dev.argtypes = [vp, vp, vp, i, vp, vp, f, i, i, i, i, vp, vp, vp, vp]
+    L.orbgpu_frame_set_from_extraction.argtypes = [vp, vp, vp, i, i, vp, i, vp, C.POINTER(vp)]
+    L.orbgpu_frame_set_dev_info.argtypes = [vp, C.POINTER(i), vp, C.POINTER(i), C.POINTER(i)]
+    L.orbgpu_frame_set_download.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
     L._matcher_bound = True
 
 
@@ -254,6 +257,33 @@ class ORBmatcher:
 
     def release(self, h):
         self._lib.orbgpu_frame_set_release(h)
+
+    def frame_set_from_extraction(self, extractor, vocabulary=None, levelsup: int = 4, kp_flag: int = 0, u_right_ptr: int = 0,
+                                  u_right_stride: int = 0, grid=None) -> C.c_void_p:
+        """Device-resident frame set from the batch `extractor` has just processed (+ FeatureVectors from `vocabulary`):
+        extraction -> vocabulary -> matching without a host round trip (orbgpu_frame_set_from_extraction)."""
+        h = C.c_void_p()
+        g = None if grid is None else np.ascontiguousarray(grid, np.float32)
+        capi.check(self._lib.orbgpu_frame_set_from_extraction(self._h, extractor._h, vocabulary._h if vocabulary is not None else None, levelsup,
+                                                              kp_flag, u_right_ptr or None, u_right_stride, None if g is None else g.ctypes.data,
+                                                              C.byref(h)))
+        return h
+
+    def frame_set_info(self, h):
+        n, nn, nf = C.c_int(0), C.c_int(0), C.c_int(0)
+        capi.check(self._lib.orbgpu_frame_set_dev_info(h, C.byref(n), None, C.byref(nn), C.byref(nf)))
+        kp_off = np.zeros(n.value + 1, np.int32)
+        capi.check(self._lib.orbgpu_frame_set_dev_info(h, None, kp_off.ctypes.data, None, None))
+        return kp_off, nn.value, nf.value
+
+    def frame_set_download(self, h):
+        kp_off, nn, nf = self.frame_set_info(h)
+        out = {"kp_off": kp_off, "keys_un": np.zeros(int(kp_off[-1]), capi.KP_DTYPE), "desc": np.zeros((int(kp_off[-1]), 32), np.uint8),
+               "fv_node_off": np.zeros(len(kp_off), np.int32), "fv_node_id": np.zeros(nn, np.int32), "fv_feat_off": np.zeros(nn + 1, np.int32),
+               "fv_feat": np.zeros(nf, np.int32)}
+        capi.check(self._lib.orbgpu_frame_set_download(self._h, h, *[out[k].ctypes.data for k in
+                                                                    ("keys_un", "desc", "fv_node_off", "fv_node_id", "fv_feat_off", "fv_feat")]))
+        return out
 
     def upload_mappoints(self, mps: MapPointSet, n_frames: int) -> C.c_void_p:
         h = C.c_void_p()
