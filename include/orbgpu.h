@@ -346,7 +346,8 @@ int orbgpu_bow_transform_dev(orbgpu_vocabulary* v, int n_frames, const int32_t* 
  * kp_flags (meaning per search function); u_right_dev (optional, device, [batch][u_right_stride], e.g. the output of
  * orbgpu_stereo_matches_dev) becomes mvuRight; grid (optional, host, 4 floats: mnMinX, mnMinY, mfGridElementWidthInv,
  * mfGridElementHeightInv) is shared by all frames.  Only the per-frame counts travel to the host.  Release with
- * orbgpu_frame_set_release. */
+ * orbgpu_frame_set_release BEFORE destroying `m`: the set's memory is borrowed from the matcher and goes back to it, so a
+ * pipeline that builds one set per batch allocates nothing after the first step.  Use such a set only with `m`. */
 int orbgpu_frame_set_from_extraction(orbgpu_matcher* m, orbgpu_extractor* ex, orbgpu_vocabulary* voc, int levelsup, int kp_flag,
                                      const float* u_right_dev, int u_right_stride, const float* grid, orbgpu_frame_set_dev** out);
 /* Sizes of a device-resident frame set; kp_off (may be NULL) receives n_frames + 1 offsets. */

@@ -969,6 +969,9 @@ struct orbgpu_frame_set_dev {
     std::vector<int32_t> h_ent_cnt;     // [n_frames] fv_feat entries per frame
     og::FrameSetView v{};
     std::vector<void*> owned;
+    // blocks borrowed from the matcher's arena (orbgpu_frame_set_from_extraction): returned to it on release, not freed
+    orbgpu_matcher* arena_owner = nullptr;
+    std::vector<std::pair<void*, size_t>> borrowed;
 };
 
 struct orbgpu_mappoint_set_dev {
@@ -994,6 +997,25 @@ struct orbgpu_matcher {
     int tmp_next = 0;
     uint8_t* h_stage = nullptr;   // pinned staging for the per-call control arrays
     size_t h_stage_cap = 0;
+    // free blocks of released extraction-built frame sets: a pipeline that builds a frame set per batch reuses them instead
+    // of paying cudaMalloc / cudaFree (which synchronises the device) every step
+    std::vector<std::pair<void*, size_t>> arena_free;
+    cudaError_t arena_take(size_t bytes, void** out, size_t* cap) {
+        bytes = std::max<size_t>(bytes, 256);
+        int best = -1;
+        for (int i = 0; i < (int)arena_free.size(); ++i)
+            if (arena_free[i].second >= bytes && (best < 0 || arena_free[i].second < arena_free[best].second)) best = i;
+        if (best >= 0 && arena_free[best].second <= 4 * bytes + (1 << 20)) {
+            *out = arena_free[best].first;
+            *cap = arena_free[best].second;
+            arena_free.erase(arena_free.begin() + best);
+            return cudaSuccess;
+        }
+        const size_t want = bytes + bytes / 8;
+        cudaError_t e = cudaMalloc(out, want);
+        *cap = want;
+        return e;
+    }
 };
 
 namespace {
@@ -1456,6 +1478,8 @@ int orbgpu_matcher_destroy(orbgpu_matcher* m) {
     Scratch* all[] = {&m->s_ctrl, &m->s_topk, &m->s_topk2, &m->s_bin, &m->s_items, &m->s_grid_start, &m->s_grid_items, &m->s_res1,
                       &m->s_res2, &m->s_out[0], &m->s_out[1], &m->s_out[2], &m->s_out[3], &m->s_out[4], &m->s_in[0], &m->s_in[1]};
     for (Scratch* s : all) s->release();
+    for (Scratch& s : m->s_tmp) s.release();
+    for (auto& b : m->arena_free) cudaFree(b.first);
     if (m->h_stage) cudaFreeHost(m->h_stage);
     if (m->d_evals) cudaFree(m->d_evals);
     if (m->d_nitems) cudaFree(m->d_nitems);
@@ -1528,6 +1552,12 @@ int orbgpu_frame_set_release(orbgpu_frame_set_dev* fs) {
     if (!fs) return ORBGPU_OK;
     cudaSetDevice(fs->device);
     free_owned(fs->owned);
+    if (fs->arena_owner) {
+        // searches that read the set were enqueued on the owner's stream; later users of the blocks are ordered after them there
+        for (auto& b : fs->borrowed) fs->arena_owner->arena_free.push_back(b);
+    } else {
+        for (auto& b : fs->borrowed) cudaFree(b.first);
+    }
     delete fs;
     return ORBGPU_OK;
 }
@@ -1808,10 +1838,12 @@ extern "C" int orbgpu_frame_set_from_extraction(orbgpu_matcher* m, orbgpu_extrac
         fs->max_kp = std::max(fs->max_kp, cnt[f]);
     }
     fs->nkp = fs->h_kp_off[batch];
-    auto bail = [&](int code) { free_owned(fs->owned); delete fs; return code; };
+    fs->arena_owner = m;
+    auto bail = [&](int code) { orbgpu_frame_set_release(fs); return code; };
     auto alloc = [&](size_t bytes, void** p) -> cudaError_t {
-        cudaError_t e = cudaMalloc(p, std::max<size_t>(bytes, 256));
-        if (e == cudaSuccess) fs->owned.push_back(*p);
+        size_t cap = 0;
+        cudaError_t e = m->arena_take(bytes, p, &cap);
+        if (e == cudaSuccess) fs->borrowed.push_back(std::make_pair(*p, cap));
         return e;
     };
 #define OGF_CUDA(expr)                                                                                             \

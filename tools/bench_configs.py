@@ -103,7 +103,9 @@ m.release(hf); m.release_mappoints(hm); m.close(); ex.close()
 W, H, NF = 1241, 376, 2000
 P = max(8, int(1024 * args.scale))
 ex = ORBextractor(NF, 1.2, 8, 20, 7, max_width=W, max_height=H, max_batch=2 * (P + 1))
-left = frames(W, H, P + 1, distinct=32)
+# consecutive key frames see the same scene 8 px further along (16 frames per scene), so triangulation finds real matches
+wide = [synth.g_rects(W + 128, H, s) for s in range(8)]
+left = np.ascontiguousarray(np.stack([wide[(f // 16) % 8][:, 8 * (f % 16):8 * (f % 16) + W] for f in range(P + 1)]))
 right = np.ascontiguousarray(np.roll(left, -12, axis=2))      # constant-disparity right images
 both = np.ascontiguousarray(np.concatenate([left, right]))
 fn, *_ = extract_dev(ex, both, W, H)
@@ -144,6 +146,46 @@ fn = lambda: exL.stereo_matches_dev(exR, 0.537, 386.1448, d_u.data_ptr(), d_d.da
 ms_s = ev_time(exL.stream(), fn, args.reps, exL.sync)
 out({"config": "3-stereo", "what": f"Frame::ComputeStereoMatches for {P} KITTI stereo pairs (device-resident key points, descriptors, pyramids)",
      "pairs_per_s": P / ms_s * 1e3, "ms": ms_s, "stereo_matches_per_pair": float((d_u >= 0).sum().item()) / P})
+# the whole of config #3 chained on the device: extraction of both images of every key frame, ComputeStereoMatches, FeatureVectors by the
+# device vocabulary transform (10 x 10 two-level tree, levelsup 0), frame set built in HBM, SearchForTriangulation between consecutive
+# key frames with the stereo coordinates — the host sees only the per-frame counts
+from orb_slam2_with_comment_b200.vocabulary import ORBVocabulary
+voc = ORBVocabulary().from_records(synth.vocabulary_tree(k=10, L=2, seed=12345))
+fnL, *_ = extract_dev(exL, left[:P], W, H)
+fnR, *_ = extract_dev(exR, right[:P], W, H)
+m = ORBmatcher(0.6, False)
+i1c, i2c = np.arange(1, P, dtype=np.int32), np.arange(0, P - 1, dtype=np.int32)
+F12c, EPc = np.tile(F, (P - 1, 1)), np.tile(ep, (P - 1, 1))
+cap = exL.kp_cap
+d12c = torch.zeros((P - 1) * cap, dtype=torch.int32, device=dev)
+ddc = torch.zeros((P - 1) * cap, dtype=torch.int32, device=dev)
+dnc = torch.zeros(P - 1, dtype=torch.int32, device=dev)
+
+
+def chain():
+    fnL(); fnR()
+    exR.sync()   # the stereo kernels run on the left extractor's stream
+    exL.stereo_matches_dev(exR, 0.537, 386.1448, d_u.data_ptr(), d_d.data_ptr())
+    hc = m.frame_set_from_extraction(exL, voc, levelsup=0, kp_flag=0, u_right_ptr=d_u.data_ptr(), u_right_stride=cap)
+    kp_off_c, _, _ = m.frame_set_info(hc)
+    offc = kp_off_c[i1c].astype(np.int64) - kp_off_c[1]     # match slots of pair p start where frame i1[p]'s key points start
+    m.search_for_triangulation_dev(hc, hc, i1c, i2c, F12c, EPc, sf, s2, offc, d12c.data_ptr(), ddc.data_ptr(), dnc.data_ptr())
+    m.sync()
+    m.release(hc)
+
+
+chain(); chain()
+torch.cuda.synchronize()
+t0 = time.time()
+for _ in range(args.reps):
+    chain()
+torch.cuda.synchronize()
+ms_c = (time.time() - t0) / args.reps * 1e3
+out({"config": "3-chained", "what": f"{P} KITTI stereo key frames per step, everything on the device: extraction of {2 * P} images, ComputeStereoMatches, "
+     "vocabulary transform, frame set in HBM, SearchForTriangulation (stereo) between consecutive key frames; wall clock incl. the host's "
+     "count read-backs", "ms_per_step": ms_c, "keyframes_per_s": P / ms_c * 1e3, "images_per_s": 2 * P / ms_c * 1e3,
+     "matches_per_pair": float(dnc.float().mean().item())})
+m.close(); voc.close()
 exL.close(); exR.close()
 
 # ---- #4 -------------------------------------------------------------------------------------------------------------
