@@ -291,6 +291,27 @@ int orbgpu_search_by_bow_dev(orbgpu_matcher* m, const orbgpu_frame_set_dev* set1
                              int th_inclusive, int require_mp2, const int64_t* match_off, int32_t* match12_dev,
                              int32_t* match_dist_dev, int32_t* nmatches_dev);
 
+/* Frame::isInFrustum (Frame.cc:274-342) with MapPoint::PredictScale (MapPoint.cc:421-436) for all map points of a batch
+ * of frames — what Tracking::SearchLocalPoints runs per local map point before SearchByProjection; the outputs are the
+ * mTrack* fields, i.e. exactly the proj_x / proj_y / proj_xr / view_cos / level arrays and bit 0 of `flags` of an
+ * orbgpu_mappoint_set.  cam[f] holds 24 floats of frame f: mRcw (9, row-major), mtcw (3), mOw (3), fx, fy, cx, cy, mbf,
+ * mnMinX, mnMaxX, mnMinY, mnMaxY.  Frame f owns map points [mp_off[f], mp_off[f+1]): world_pos / normal are xyz triples
+ * (GetWorldPos / GetNormal), min_dist_inv / max_dist_inv are GetMinDistanceInvariance() / GetMaxDistanceInvariance(),
+ * max_distance is mfMaxDistance (PredictScale's numerator).  Points failing a test get in_view 0 and zeroed outputs.
+ * The cv::Mat arithmetic is evaluated as OpenCV 4.13 does (float dot product + double addend in cv::gemm, double norm and
+ * dot); the predicted level uses a correctly rounded logf — it can differ from glibc's logf by one level only when
+ * log(ratio)/log(scaleFactor) is within one ulp of an integer. */
+int orbgpu_is_in_frustum(orbgpu_matcher* m, int n_frames, const float* cam, float log_scale_factor, int n_levels,
+                         float viewing_cos_limit, const int32_t* mp_off, const float* world_pos, const float* normal,
+                         const float* min_dist_inv, const float* max_dist_inv, const float* max_distance, uint8_t* in_view,
+                         float* proj_x, float* proj_y, float* proj_xr, int32_t* level, float* view_cos);
+/* The same with every array but `mp_off` and `cam` (host) a device pointer; enqueued on the matcher's stream. */
+int orbgpu_is_in_frustum_dev(orbgpu_matcher* m, int n_frames, const float* cam, float log_scale_factor, int n_levels,
+                             float viewing_cos_limit, const int32_t* mp_off, const float* world_pos_dev, const float* normal_dev,
+                             const float* min_dist_inv_dev, const float* max_dist_inv_dev, const float* max_distance_dev,
+                             uint8_t* in_view_dev, float* proj_x_dev, float* proj_y_dev, float* proj_xr_dev, int32_t* level_dev,
+                             float* view_cos_dev);
+
 /* ------------------------------------------------------------------------------------------------
  * Vocabulary — replaces ORBVocabulary::transform (DBoW2 TemplatedVocabulary<FORB::TDescriptor, FORB>,
  * include/ORBVocabulary.h:31-32) as called by Frame::ComputeBoW (Frame.cc:425-432) and KeyFrame::ComputeBoW

@@ -275,4 +275,34 @@ float cvl_fast_atan2(float y, float x) {
     return a;
 }
 
+// ---- small float cv::Mat algebra as the reference's pose arithmetic uses it (pinned to cv2 4.13 by tests/golden/cvsmall_golden.npz) ----
+// d = A * x + c for a 3x3 and 3x1 CV_32F (cv::gemm, alpha = beta = 1, no transpose flags: the small-matrix path): the dot
+// products are accumulated in float, left to right; the addition of c happens in double and is rounded once.
+void cvl_gemm3_f32(const float* A, const float* x, const float* c, float* out) {
+    for (int i = 0; i < 3; ++i) {
+        const float t = A[3 * i] * x[0] + A[3 * i + 1] * x[1] + A[3 * i + 2] * x[2];
+        out[i] = (float)((double)t * 1.0 + (double)(c ? c[i] : 0.f) * 1.0);
+    }
+}
+// d = -A^T * x (cv::gemm with GEMM_1_T, alpha = -1: the general path): products and sums in double, rounded once.
+void cvl_gemm3t_neg_f32(const float* A, const float* x, float* out) {
+    for (int i = 0; i < 3; ++i) {
+        double acc = 0.0;
+        for (int j = 0; j < 3; ++j) acc += (double)A[3 * j + i] * (double)x[j];
+        out[i] = (float)(-acc);
+    }
+}
+// cv::norm(v) of a 3x1 CV_32F (NORM_L2): squares summed in double, sqrt in double.
+double cvl_norm3_f32(const float* v) {
+    double s = 0.0;
+    for (int i = 0; i < 3; ++i) s += (double)v[i] * (double)v[i];
+    return std::sqrt(s);
+}
+// a.dot(b) of 3x1 CV_32F: products and sum in double.
+double cvl_dot3_f32(const float* a, const float* b) {
+    double s = 0.0;
+    for (int i = 0; i < 3; ++i) s += (double)a[i] * (double)b[i];
+    return s;
+}
+
 }  // extern "C"

@@ -49,6 +49,11 @@ int cvl_fast9_16(const uint8_t* img, int w, int h, int stride, int threshold, in
 void cvl_fast_score_map(const uint8_t* img, int w, int h, int stride, uint8_t* score, int score_stride);
 
 float cvl_fast_atan2(float y, float x);
+/* small float cv::Mat algebra of the pose arithmetic (Frame.cc:285, :312-320; ORBmatcher.cc:790-799, :1556-1563) */
+void cvl_gemm3_f32(const float* A, const float* x, const float* c, float* out);
+void cvl_gemm3t_neg_f32(const float* A, const float* x, float* out);
+double cvl_norm3_f32(const float* v);
+double cvl_dot3_f32(const float* a, const float* b);
 
 #ifdef __cplusplus
 }

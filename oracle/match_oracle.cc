@@ -394,3 +394,49 @@ extern "C" double orbm_bench_bow(const orbgpu_frame_set* s1, const orbgpu_frame_
     for (auto& x : th) x.join();
     return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
+
+// Frame::isInFrustum (Frame.cc:274-342) + MapPoint::PredictScale (MapPoint.cc:421-436) for every map point of every frame.
+// cam[f] = Rcw[9], tcw[3], Ow[3], fx, fy, cx, cy, mbf, mnMinX, mnMaxX, mnMinY, mnMaxY (24 floats).  The cv::Mat expressions
+// follow cv2 4.13 (oracle/cvlite.cc cvl_gemm3_f32 / cvl_norm3_f32 / cvl_dot3_f32, pinned by tests/golden/cvsmall_golden.npz).
+extern "C" void cvl_gemm3_f32(const float*, const float*, const float*, float*);
+extern "C" double cvl_norm3_f32(const float*);
+extern "C" double cvl_dot3_f32(const float*, const float*);
+extern "C" void orbm_is_in_frustum(int n_frames, const float* cam, float log_scale_factor, int n_levels, float viewing_cos_limit,
+                                   const int32_t* mp_off, const float* world_pos, const float* normal, const float* min_dist_inv,
+                                   const float* max_dist_inv, const float* max_distance, uint8_t* in_view, float* proj_x, float* proj_y,
+                                   float* proj_xr, int32_t* level, float* view_cos) {
+    for (int f = 0; f < n_frames; ++f) {
+        const float* c = cam + 24 * f;
+        const float fx = c[15], fy = c[16], cx = c[17], cy = c[18], mbf = c[19], minX = c[20], maxX = c[21], minY = c[22], maxY = c[23];
+        for (int q = mp_off[f]; q < mp_off[f + 1]; ++q) {
+            in_view[q] = 0;                                   // pMP->mbTrackInView = false (:277)
+            proj_x[q] = proj_y[q] = proj_xr[q] = view_cos[q] = 0.f;
+            level[q] = 0;
+            const float* P = world_pos + 3 * q;
+            float Pc[3];
+            cvl_gemm3_f32(c, P, c + 9, Pc);                   // mRcw*P+mtcw (:285)
+            const float PcX = Pc[0], PcY = Pc[1], PcZ = Pc[2];
+            if (PcZ < 0.0f) continue;                         // :292
+            const float invz = 1.0f / PcZ;
+            const float u = fx * PcX * invz + cx;
+            const float v = fy * PcY * invz + cy;
+            if (u < minX || u > maxX) continue;               // :301-304
+            if (v < minY || v > maxY) continue;
+            const float PO[3] = {P[0] - c[12], P[1] - c[13], P[2] - c[14]};   // P-mOw (:312)
+            const float dist = (float)cvl_norm3_f32(PO);
+            if (dist < min_dist_inv[q] || dist > max_dist_inv[q]) continue;    // :315
+            const float viewCos = (float)(cvl_dot3_f32(PO, normal + 3 * q) / dist);   // :322
+            if (viewCos < viewing_cos_limit) continue;
+            const float ratio = max_distance[q] / dist;       // MapPoint.cc:426
+            int nScale = (int)std::ceil(std::log(ratio) / log_scale_factor);   // float overloads, as in the reference (:429)
+            if (nScale < 0) nScale = 0;
+            else if (nScale >= n_levels) nScale = n_levels - 1;
+            in_view[q] = 1;
+            proj_x[q] = u;
+            proj_xr[q] = u - mbf * invz;
+            proj_y[q] = v;
+            level[q] = nScale;
+            view_cos[q] = viewCos;
+        }
+    }
+}

@@ -185,13 +185,14 @@ int ORBmatcher::SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, cv::Mat F
     vMatchedPairs.clear();
     const int N1 = (int)pKF1->mvKeysUn.size(), N2 = (int)pKF2->mvKeysUn.size();
     if (N1 == 0 || N2 == 0) return 0;
-    // epipole of camera 1 in image 2 (:790-799): C2 = R2w * Cw + t2w, accumulated in double like cv::gemm's small-matrix path
+    // epipole of camera 1 in image 2 (:790-799): C2 = R2w * Cw + t2w.  A 3x3 * 3x1 + 3x1 cv::Mat expression is one cv::gemm call
+    // on its small-matrix path: the dot product is accumulated in float, left to right, the addend joins in double
+    // (pinned to cv2 4.13: tests/golden/cvsmall_golden.npz, oracle/cvlite.cc cvl_gemm3_f32).
     const cv::Mat Cw = pKF1->GetCameraCenter(), R2w = pKF2->GetRotation(), t2w = pKF2->GetTranslation();
     float C2[3];
     for (int i = 0; i < 3; ++i) {
-        double acc = 0.0;
-        for (int j = 0; j < 3; ++j) acc += (double)R2w.at<float>(i, j) * (double)Cw.at<float>(j, 0);
-        C2[i] = (float)(acc + (double)t2w.at<float>(i, 0));
+        const float t = R2w.at<float>(i, 0) * Cw.at<float>(0, 0) + R2w.at<float>(i, 1) * Cw.at<float>(1, 0) + R2w.at<float>(i, 2) * Cw.at<float>(2, 0);
+        C2[i] = (float)((double)t + (double)t2w.at<float>(i, 0));
     }
     const float invz = 1.0f / C2[2];
     const float epipole[2] = {pKF2->fx * C2[0] * invz + pKF2->cx, pKF2->fy * C2[1] * invz + pKF2->cy};
@@ -224,20 +225,19 @@ int ORBmatcher::SearchForTriangulation(KeyFrame* pKF1, KeyFrame* pKF2, cv::Mat F
     return nmatches;
 }
 
-// 3x3 (rows 0-2, cols 0-2 of a 4x4 pose) times a 3-vector plus a 3-vector, accumulated in double and rounded to float like
-// cv::gemm's small-matrix path (the reference writes these as cv::Mat expressions, ORBmatcher.cc:1556-1563, :1579).
+// 3x3 (rows 0-2, cols 0-2 of a 4x4 pose) times a 3-vector plus a 3-vector, the way cv::gemm evaluates the reference's
+// cv::Mat expressions Rcw*x3Dw+tcw (ORBmatcher.cc:1556-1563, :1579): float dot product left to right, addend joined in double.
 static void rt_apply(const cv::Mat& T, const float* x, float* out) {
     for (int i = 0; i < 3; ++i) {
-        double acc = 0.0;
-        for (int j = 0; j < 3; ++j) acc += (double)T.at<float>(i, j) * (double)x[j];
-        out[i] = (float)(acc + (double)T.at<float>(i, 3));
+        const float t = T.at<float>(i, 0) * x[0] + T.at<float>(i, 1) * x[1] + T.at<float>(i, 2) * x[2];
+        out[i] = (float)((double)t + (double)T.at<float>(i, 3));
     }
 }
 
 int ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, const float th, const bool bMono) {
     const int N = (int)CurrentFrame.mvKeysUn.size(), NL = LastFrame.N;
     if (N == 0 || NL == 0) return 0;
-    // twc = -Rcw^T * tcw, tlc = Rlw * twc + tlw (:1556-1563)
+    // twc = -Rcw^T * tcw (a transposed operand takes cv::gemm's general path: double accumulation), tlc = Rlw * twc + tlw (:1556-1563)
     float twc[3], tlc[3];
     for (int i = 0; i < 3; ++i) {
         double acc = 0.0;

@@ -1956,3 +1956,123 @@ extern "C" int orbgpu_frame_set_download(orbgpu_matcher* m, const orbgpu_frame_s
     OGM_CUDA(cudaStreamSynchronize(st));
     return ORBGPU_OK;
 }
+
+// ---- Frame::isInFrustum + MapPoint::PredictScale (Frame.cc:274-342, MapPoint.cc:421-436) ----------------------------------
+namespace og {
+struct FrustumArgs {
+    const float* cam;        // [n_frames][24]
+    const int32_t* mp_off;   // device copy
+    const float *world_pos, *normal, *min_d, *max_d, *max_distance;
+    uint8_t* in_view;
+    float *proj_x, *proj_y, *proj_xr, *view_cos;
+    int32_t* level;
+    float log_sf, cos_limit;
+    int n_levels;
+};
+// grid (chunks of 256 points, frames).  Plain IEEE single / double operations in the reference's order (the library is built
+// with --fmad=false); cv::gemm's 3x3 * 3x1 + 3x1: float dot product left to right, addend joined in double.
+__global__ void __launch_bounds__(256) k_frustum(FrustumArgs A) {
+    const int f = blockIdx.y;
+    const int q0 = A.mp_off[f], n = A.mp_off[f + 1] - q0;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const int q = q0 + i;
+    const float* c = A.cam + 24 * f;
+    const float Px = A.world_pos[3 * q], Py = A.world_pos[3 * q + 1], Pz = A.world_pos[3 * q + 2];
+    uint8_t ok = 0;
+    float u = 0.f, v = 0.f, ur = 0.f, vc = 0.f;
+    int lvl = 0;
+    do {
+        float Pc[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const float t = __ldg(c + 3 * r) * Px + __ldg(c + 3 * r + 1) * Py + __ldg(c + 3 * r + 2) * Pz;
+            Pc[r] = (float)((double)t + (double)__ldg(c + 9 + r));
+        }
+        if (Pc[2] < 0.0f) break;
+        const float invz = 1.0f / Pc[2];
+        const float uu = __ldg(c + 15) * Pc[0] * invz + __ldg(c + 17);
+        const float vv = __ldg(c + 16) * Pc[1] * invz + __ldg(c + 18);
+        if (uu < __ldg(c + 20) || uu > __ldg(c + 21)) break;
+        if (vv < __ldg(c + 22) || vv > __ldg(c + 23)) break;
+        const float PO0 = Px - __ldg(c + 12), PO1 = Py - __ldg(c + 13), PO2 = Pz - __ldg(c + 14);
+        const float dist = (float)sqrt((double)PO0 * (double)PO0 + (double)PO1 * (double)PO1 + (double)PO2 * (double)PO2);
+        if (dist < A.min_d[q] || dist > A.max_d[q]) break;
+        const double dot = (double)PO0 * (double)A.normal[3 * q] + (double)PO1 * (double)A.normal[3 * q + 1] + (double)PO2 * (double)A.normal[3 * q + 2];
+        const float viewCos = (float)(dot / (double)dist);
+        if (viewCos < A.cos_limit) break;
+        const float ratio = A.max_distance[q] / dist;
+        const float qf = ceilf((float)log((double)ratio) / A.log_sf);
+        lvl = qf >= (float)A.n_levels ? A.n_levels - 1 : (qf < 0.f ? 0 : (int)qf);
+        if (!(qf == qf)) lvl = 0;   // NaN: the reference's float -> int conversion is undefined here
+        ok = 1; u = uu; v = vv; ur = uu - __ldg(c + 19) * invz; vc = viewCos;
+    } while (0);
+    A.in_view[q] = ok;
+    A.proj_x[q] = u; A.proj_y[q] = v; A.proj_xr[q] = ur; A.view_cos[q] = vc;
+    A.level[q] = lvl;
+}
+}  // namespace og
+
+extern "C" int orbgpu_is_in_frustum_dev(orbgpu_matcher* m, int n_frames, const float* cam, float log_scale_factor, int n_levels,
+                                        float viewing_cos_limit, const int32_t* mp_off, const float* world_pos, const float* normal,
+                                        const float* min_d, const float* max_d, const float* max_distance, uint8_t* in_view, float* proj_x,
+                                        float* proj_y, float* proj_xr, int32_t* level, float* view_cos) {
+    int rc = check_matcher(m);
+    if (rc) return rc;
+    m->last_launches = 0;
+    if (n_frames < 0 || (n_frames && (!cam || !mp_off))) return og_fail(ORBGPU_ERR_ARG, "is_in_frustum: null cam / mp_off");
+    if (n_frames == 0) return ORBGPU_OK;
+    int max_n = 0;
+    for (int f = 0; f < n_frames; ++f) {
+        if (mp_off[f + 1] < mp_off[f]) return og_fail(ORBGPU_ERR_ARG, "is_in_frustum: mp_off must be non-decreasing");
+        max_n = std::max(max_n, mp_off[f + 1] - mp_off[f]);
+    }
+    if (max_n == 0) return ORBGPU_OK;
+    if (!world_pos || !normal || !min_d || !max_d || !max_distance || !in_view || !proj_x || !proj_y || !proj_xr || !level || !view_cos)
+        return og_fail(ORBGPU_ERR_ARG, "is_in_frustum: null array");
+    if (!(log_scale_factor > 0.f) || n_levels < 1) return og_fail(ORBGPU_ERR_ARG, "is_in_frustum: bad scale factor / level count");
+    void *d_cam, *d_off;
+    OGM_CUDA(m->s_grid_start.grab((size_t)n_frames * 24 * 4, &d_cam));
+    OGM_CUDA(m->s_grid_items.grab((size_t)(n_frames + 1) * 4, &d_off));
+    OGM_CUDA(cudaMemcpyAsync(d_cam, cam, (size_t)n_frames * 24 * 4, cudaMemcpyHostToDevice, m->stream));
+    OGM_CUDA(cudaMemcpyAsync(d_off, mp_off, (size_t)(n_frames + 1) * 4, cudaMemcpyHostToDevice, m->stream));
+    og::FrustumArgs A = {(const float*)d_cam, (const int32_t*)d_off, world_pos, normal, min_d, max_d, max_distance, in_view, proj_x, proj_y,
+                         proj_xr, view_cos, level, log_scale_factor, viewing_cos_limit, n_levels};
+    og::k_frustum<<<dim3((max_n + 255) / 256, n_frames), 256, 0, m->stream>>>(A);
+    m->last_launches = 1;
+    OGM_CUDA(cudaGetLastError());
+    return ORBGPU_OK;
+}
+
+extern "C" int orbgpu_is_in_frustum(orbgpu_matcher* m, int n_frames, const float* cam, float log_scale_factor, int n_levels,
+                                    float viewing_cos_limit, const int32_t* mp_off, const float* world_pos, const float* normal,
+                                    const float* min_d, const float* max_d, const float* max_distance, uint8_t* in_view, float* proj_x,
+                                    float* proj_y, float* proj_xr, int32_t* level, float* view_cos) {
+    int rc = check_matcher(m);
+    if (rc) return rc;
+    if (n_frames < 0 || (n_frames && !mp_off)) return og_fail(ORBGPU_ERR_ARG, "is_in_frustum: null mp_off");
+    const size_t n = n_frames ? (size_t)mp_off[n_frames] : 0;
+    if (n == 0) return ORBGPU_OK;
+    if (!world_pos || !normal || !min_d || !max_d || !max_distance || !in_view || !proj_x || !proj_y || !proj_xr || !level || !view_cos)
+        return og_fail(ORBGPU_ERR_ARG, "is_in_frustum: null array");
+    cudaStream_t st = m->stream;
+    m->tmp_next = 0;
+    const void* src[5] = {world_pos, normal, min_d, max_d, max_distance};
+    const size_t sb[5] = {n * 12, n * 12, n * 4, n * 4, n * 4};
+    void* din[5];
+    for (int i = 0; i < 5; ++i) {
+        OGM_CUDA(m->s_tmp[m->tmp_next++].grab(sb[i], &din[i]));
+        OGM_CUDA(cudaMemcpyAsync(din[i], src[i], sb[i], cudaMemcpyHostToDevice, st));
+    }
+    void* dout[6];
+    const size_t ob[6] = {n, n * 4, n * 4, n * 4, n * 4, n * 4};
+    for (int i = 0; i < 6; ++i) OGM_CUDA(m->s_tmp[m->tmp_next++].grab(ob[i], &dout[i]));
+    rc = orbgpu_is_in_frustum_dev(m, n_frames, cam, log_scale_factor, n_levels, viewing_cos_limit, mp_off, (const float*)din[0], (const float*)din[1],
+                                  (const float*)din[2], (const float*)din[3], (const float*)din[4], (uint8_t*)dout[0], (float*)dout[1], (float*)dout[2],
+                                  (float*)dout[3], (int32_t*)dout[4], (float*)dout[5]);
+    if (rc) return rc;
+    void* host[6] = {in_view, proj_x, proj_y, proj_xr, level, view_cos};
+    for (int i = 0; i < 6; ++i) OGM_CUDA(cudaMemcpyAsync(host[i], dout[i], ob[i], cudaMemcpyDeviceToHost, st));
+    OGM_CUDA(cudaStreamSynchronize(st));
+    return ORBGPU_OK;
+}

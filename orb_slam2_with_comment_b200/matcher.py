@@ -138,6 +138,8 @@ def _bind(L):
     L.orbgpu_search_for_triangulation_dev.argtypes = [vp, vp, vp, i, vp, vp, vp, vp, vp, vp, i, i, i, vp, vp, vp, vp]
     L.orbgpu_search_by_bow.argtypes = [vp, C.POINTER(CFrameSet), C.POINTER(CFrameSet), i, vp, vp, f, i, i, i, i, vp, vp, vp, vp]
     L.orbgpu_search_by_bow_dev.argtypes = [vp, vp, vp, i, vp, vp, f, i, i, i, i, vp, vp, vp, vp]
+    L.orbgpu_is_in_frustum.argtypes = [vp, i, vp, f, i, f] + [vp] * 12
+    L.orbgpu_is_in_frustum_dev.argtypes = [vp, i, vp, f, i, f] + [vp] * 12
     L.orbgpu_frame_set_from_extraction.argtypes = [vp, vp, vp, i, i, vp, i, vp, C.POINTER(vp)]
     L.orbgpu_frame_set_dev_info.argtypes = [vp, C.POINTER(i), vp, C.POINTER(i), C.POINTER(i)]
     L.orbgpu_frame_set_download.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
@@ -250,6 +252,21 @@ class ORBmatcher:
         return {"nmatches": nm, "match12": m12, "match_dist": md, "match_off": off}
 
     # ---- device-resident handles (bench path)
+    def isInFrustum(self, cam, log_scale_factor, n_levels, viewing_cos_limit, mp_off, world_pos, normal, min_dist_inv, max_dist_inv,
+                    max_distance):
+        """Frame::isInFrustum + MapPoint::PredictScale for every map point of a batch of frames (orbgpu_is_in_frustum).
+        cam: (n_frames, 24) float32 = Rcw(9) tcw(3) Ow(3) fx fy cx cy mbf minX maxX minY maxY."""
+        cam = np.ascontiguousarray(cam, np.float32).reshape(-1, 24)
+        mp_off = np.ascontiguousarray(mp_off, np.int32)
+        n = int(mp_off[-1])
+        ins = [np.ascontiguousarray(a, np.float32) for a in (world_pos, normal, min_dist_inv, max_dist_inv, max_distance)]
+        out = {"in_view": np.zeros(n, np.uint8), "proj_x": np.zeros(n, np.float32), "proj_y": np.zeros(n, np.float32),
+               "proj_xr": np.zeros(n, np.float32), "level": np.zeros(n, np.int32), "view_cos": np.zeros(n, np.float32)}
+        capi.check(self._lib.orbgpu_is_in_frustum(self._h, len(cam), cam.ctypes.data, float(log_scale_factor), n_levels, float(viewing_cos_limit),
+                                                  mp_off.ctypes.data, *[a.ctypes.data for a in ins], *[out[k].ctypes.data for k in
+                                                  ("in_view", "proj_x", "proj_y", "proj_xr", "level", "view_cos")]))
+        return out
+
     def upload(self, fs: FrameSet) -> C.c_void_p:
         h = C.c_void_p()
         capi.check(self._lib.orbgpu_frame_set_upload(self._h, C.byref(fs.c), C.byref(h)))

@@ -33,6 +33,8 @@ void orbm_search_for_triangulation(const orbgpu_frame_set*, const orbgpu_frame_s
                                    const float*, const float*, const float*, int, int, int, const int64_t*, int32_t*, int32_t*, int32_t*);
 void orbm_search_by_bow(const orbgpu_frame_set*, const orbgpu_frame_set*, int, const int32_t*, const int32_t*, float, int, int, int, int,
                         const int64_t*, int32_t*, int32_t*, int32_t*);
+void cvl_gemm3_f32(const float*, const float*, const float*, float*);
+void cvl_gemm3t_neg_f32(const float*, const float*, float*);
 void* orbo_voc_create(int, int, int, int, int, const int32_t*, const uint8_t*, const uint8_t*, const double*);
 void orbo_voc_free(void*);
 int orbo_voc_transform(void*, const uint8_t*, int, int, int*, uint32_t*, double*, int*, uint32_t*, int32_t*, uint32_t*, uint32_t*, uint32_t*);
@@ -293,7 +295,7 @@ static void test_matcher() {
             for (int i = 0; i < N; ++i) { a.flags[i] = kf1.mvpMapPoints[i] != nullptr; b.flags[i] = kf2.mvpMapPoints[i] != nullptr; }
             a.s.u_right = ur1.data(); b.s.u_right = ur2.data();
             float C2[3];
-            for (int i = 0; i < 3; ++i) { double acc = 0; for (int j = 0; j < 3; ++j) acc += (double)R[3 * i + j] * ow[j]; C2[i] = (float)(acc + tc[i]); }
+            cvl_gemm3_f32(R, ow, tc, C2);
             const float invz = 1.0f / C2[2];
             const float ep[2] = {517.3f * C2[0] * invz + 318.6f, 516.5f * C2[1] * invz + 255.3f};
             std::vector<int32_t> m12(N, -1); int32_t nm = 0; const int32_t z = 0; const int64_t z64 = 0;
@@ -424,8 +426,10 @@ static void test_track_last_frame() {
         const float grid[4] = {0, 0, Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv};
         a.s.grid = grid;
         float twc[3], tlc[3];
-        for (int i = 0; i < 3; ++i) { double acc = 0; for (int j = 0; j < 3; ++j) acc += (double)cur.mTcw.at<float>(j, i) * cur.mTcw.at<float>(j, 3); twc[i] = (float)(-acc); }
-        for (int i = 0; i < 3; ++i) { double acc = 0; for (int j = 0; j < 3; ++j) acc += (double)last.mTcw.at<float>(i, j) * twc[j]; tlc[i] = (float)(acc + last.mTcw.at<float>(i, 3)); }
+        float Rc[9], tcv[3], Rl[9], tl[3];
+        for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) { Rc[3 * i + j] = cur.mTcw.at<float>(i, j); Rl[3 * i + j] = last.mTcw.at<float>(i, j); } tcv[i] = cur.mTcw.at<float>(i, 3); tl[i] = last.mTcw.at<float>(i, 3); }
+        cvl_gemm3t_neg_f32(Rc, tcv, twc);
+        cvl_gemm3_f32(Rl, twc, tl, tlc);
         const bool fwd = tlc[2] > cur.mb && !bMono, bwd = -tlc[2] > cur.mb && !bMono;
         EXPECT(variant == 0 || (variant == 1) == fwd, "variant %d: forward=%d backward=%d", variant, fwd, bwd);
         int32_t q_off[2] = {0, N};
@@ -436,7 +440,7 @@ static void test_track_last_frame() {
             MapPoint* p = last.mvpMapPoints[i];
             if (!p || last.mvbOutlier[i]) continue;
             float xc[3];
-            for (int r = 0; r < 3; ++r) { double acc = 0; for (int c = 0; c < 3; ++c) acc += (double)cur.mTcw.at<float>(r, c) * p->mWorldPos.at<float>(c, 0); xc[r] = (float)(acc + cur.mTcw.at<float>(r, 3)); }
+            cvl_gemm3_f32(Rc, p->mWorldPos.ptr<float>(0), tcv, xc);
             const float invzc = 1.0 / xc[2];
             if (invzc < 0) continue;
             const float u = Frame::fx * xc[0] * invzc + Frame::cx, v = Frame::fy * xc[1] * invzc + Frame::cy;

@@ -157,3 +157,33 @@ def win_case(seed, n_frames=3, n_lo=400, n_hi=800, n_q=700, stereo_frac=0.0, mod
     qs = WindowQuerySet(np.array(q_off, np.int32), cat["u"], cat["v"], cat["radius"], cat["lo"], cat["hi"], cat["flags"], cat["desc"],
                         ur=cat["ur"] if stereo_frac > 0 else None, angle=cat["angle"])
     return fs, qs
+
+
+def frustum_case(seed, n_frames=4, n_mp=6000):
+    """Poses and local-map points for Frame::isInFrustum: a point cloud in front of (and partly behind / beside) slightly
+    rotated cameras, normals roughly facing them, distance-invariance ranges that cut some of the points."""
+    rs = np.random.RandomState(seed)
+    cams, offs, P, Nn, dmin, dmax, dref = [], [0], [], [], [], [], []
+    for f in range(n_frames):
+        a, b, c = rs.normal(0, 0.05, 3)
+        Rx = np.array([[1, 0, 0], [0, np.cos(a), -np.sin(a)], [0, np.sin(a), np.cos(a)]])
+        Ry = np.array([[np.cos(b), 0, np.sin(b)], [0, 1, 0], [-np.sin(b), 0, np.cos(b)]])
+        Rz = np.array([[np.cos(c), -np.sin(c), 0], [np.sin(c), np.cos(c), 0], [0, 0, 1]])
+        R = (Rx @ Ry @ Rz).astype(np.float32)
+        t = rs.normal(0, 0.5, 3).astype(np.float32)
+        Ow = (-(R.astype(np.float64).T @ t.astype(np.float64))).astype(np.float32)
+        cams.append(np.concatenate([R.ravel(), t, Ow, [517.3, 516.5, 318.6, 255.3, 40.0, 0.0, 640.0, 0.0, 480.0]]).astype(np.float32))
+        n = int(n_mp * rs.uniform(0.6, 1.0))
+        pc = np.stack([rs.uniform(-6, 6, n), rs.uniform(-5, 5, n), rs.uniform(-2, 25, n)], 1)          # camera coordinates
+        pw = ((pc - t.astype(np.float64)) @ R.astype(np.float64)).astype(np.float32)                     # R^T (pc - t)
+        d = np.linalg.norm(pw.astype(np.float64) - Ow, axis=1)
+        nrm = (pw.astype(np.float64) - Ow) / np.maximum(d, 1e-6)[:, None] + rs.normal(0, 0.6, (n, 3))
+        nrm /= np.linalg.norm(nrm, axis=1)[:, None]
+        ref = d * rs.uniform(0.3, 6.0, n)                                                               # mfMaxDistance
+        P.append(pw); Nn.append(nrm.astype(np.float32))
+        dref.append(ref.astype(np.float32))
+        dmax.append((np.float32(1.2) * ref.astype(np.float32)).astype(np.float32))
+        dmin.append((np.float32(0.8) * (ref / 1.2 ** 7).astype(np.float32)).astype(np.float32))
+        offs.append(offs[-1] + n)
+    return (np.stack(cams), np.float32(np.log(np.float32(1.2))), 8, 0.5, np.array(offs, np.int32), np.concatenate(P), np.concatenate(Nn),
+            np.concatenate(dmin), np.concatenate(dmax), np.concatenate(dref))

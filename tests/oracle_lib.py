@@ -382,3 +382,18 @@ class VocabularyRef(_VocBase):
 
     def transform(self, desc, levelsup=4):
         return self._run(self.lib.dbowref_transform, desc, levelsup, ())
+
+
+# ---- Frame::isInFrustum ---------------------------------------------------------------------------------
+def is_in_frustum(lib, cam, log_scale_factor, n_levels, viewing_cos_limit, mp_off, world_pos, normal, min_dist_inv, max_dist_inv, max_distance):
+    vp, f, i = C.c_void_p, C.c_float, C.c_int
+    lib.orbm_is_in_frustum.argtypes = [i, vp, f, i, f] + [vp] * 12
+    cam = np.ascontiguousarray(cam, np.float32).reshape(-1, 24)
+    mp_off = np.ascontiguousarray(mp_off, np.int32)
+    n = int(mp_off[-1])
+    ins = [np.ascontiguousarray(a, np.float32) for a in (world_pos, normal, min_dist_inv, max_dist_inv, max_distance)]
+    out = {"in_view": np.zeros(n, np.uint8), "proj_x": np.zeros(n, np.float32), "proj_y": np.zeros(n, np.float32),
+           "proj_xr": np.zeros(n, np.float32), "level": np.zeros(n, np.int32), "view_cos": np.zeros(n, np.float32)}
+    lib.orbm_is_in_frustum(len(cam), _p(cam, vp), float(log_scale_factor), n_levels, float(viewing_cos_limit), _p(mp_off, vp), *[_p(a, vp) for a in ins],
+                           *[_p(out[k], vp) for k in ("in_view", "proj_x", "proj_y", "proj_xr", "level", "view_cos")])
+    return out

@@ -242,3 +242,21 @@ def test_windowed_search_vs_oracle(gm, mo, mode, stereo, th, th_dist, skip_any, 
         exp = mo(0.9, ori).SearchWindowed(fs, qs, th_dist, skip_any)
         same(got, exp, ("nmatches", "kp_match", "q_best_idx", "q_best_dist"), f"windowed seed {seed} {mode}")
         assert exp["nmatches"].sum() > 500
+
+
+def test_is_in_frustum_matches_oracle():
+    """Frame::isInFrustum + PredictScale (Frame.cc:274-342): visibility and mTrack* fields, float results bit for bit."""
+    from orb_slam2_with_comment_b200.matcher import ORBmatcher
+    args = mc.frustum_case(3)
+    exp = ol.is_in_frustum(ol.load_port(), *args)
+    m = ORBmatcher()
+    got = m.isInFrustum(*args)
+    assert 0.15 < exp["in_view"].mean() < 0.85          # every exit of the function is exercised
+    assert np.array_equal(got["in_view"], exp["in_view"])
+    for k in ("proj_x", "proj_y", "proj_xr", "view_cos"):
+        assert got[k].tobytes() == exp[k].tobytes(), k
+    # predicted level: glibc's logf vs a correctly rounded logf can differ when the quotient sits on an integer
+    diff = np.nonzero(got["level"] != exp["level"])[0]
+    assert len(diff) <= 2 and np.all(np.abs(got["level"][diff] - exp["level"][diff]) == 1), diff
+    assert len(np.unique(exp["level"][exp["in_view"] == 1])) == 8
+    m.close()
