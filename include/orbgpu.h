@@ -312,6 +312,14 @@ int orbgpu_is_in_frustum_dev(orbgpu_matcher* m, int n_frames, const float* cam, 
                              uint8_t* in_view_dev, float* proj_x_dev, float* proj_y_dev, float* proj_xr_dev, int32_t* level_dev,
                              float* view_cos_dev);
 
+/* MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:247-316) for a batch of map points: point p owns the descriptors
+ * [obs_off[p], obs_off[p+1]) of `desc` (the rows of its observing, non-bad key frames in the reference's iteration order,
+ * 32 bytes each, at most 256 per point).  best_idx[p] = the row (relative to obs_off[p]) with the least median Hamming
+ * distance to all rows, its own included — the median is the element of rank (int)(0.5*(N-1)) of the sorted row, the first
+ * row wins ties; -1 for a point without descriptors.  best_median (may be NULL) receives that median. */
+int orbgpu_distinctive_descriptors(orbgpu_matcher* m, int n_points, const int32_t* obs_off, const uint8_t* desc, int32_t* best_idx,
+                                   int32_t* best_median);
+
 /* ------------------------------------------------------------------------------------------------
  * Vocabulary — replaces ORBVocabulary::transform (DBoW2 TemplatedVocabulary<FORB::TDescriptor, FORB>,
  * include/ORBVocabulary.h:31-32) as called by Frame::ComputeBoW (Frame.cc:425-432) and KeyFrame::ComputeBoW

@@ -9,6 +9,8 @@
 // micro-cases in tests/test_oracle_matcher.py and (c) an independent Python restatement of the same functions
 // (tests/golden/gen_matcher_golden.py -> committed fixtures).  Parity of these functions is therefore "unpinned by
 // the reference" (DESIGN.md §Oracle).  Build with -ffp-contract=off.
+#include <climits>
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -438,5 +440,36 @@ extern "C" void orbm_is_in_frustum(int n_frames, const float* cam, float log_sca
             level[q] = nScale;
             view_cos[q] = viewCos;
         }
+    }
+}
+
+// MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:247-316) for a batch of map points: point p owns the observed
+// descriptors [obs_off[p], obs_off[p+1]) (those of its non-bad key frames, in std::map<KeyFrame*, size_t> iteration order).
+// best_idx = the row with the least median distance to the others (first wins), -1 for a point without descriptors.
+extern "C" void orbm_distinctive_descriptors(int n_points, const int32_t* obs_off, const uint8_t* desc, int32_t* best_idx, int32_t* best_median) {
+    for (int p = 0; p < n_points; ++p) {
+        const int N = obs_off[p + 1] - obs_off[p];
+        best_idx[p] = -1;
+        best_median[p] = INT_MAX;
+        if (N <= 0) continue;
+        const uint8_t* D = desc + (size_t)obs_off[p] * 32;
+        std::vector<std::vector<float>> Distances(N, std::vector<float>(N, 0.f));
+        for (int i = 0; i < N; ++i) {
+            Distances[i][i] = 0;
+            for (int j = i + 1; j < N; ++j) {
+                const int d = descriptor_distance(D + (size_t)i * 32, D + (size_t)j * 32);
+                Distances[i][j] = d;
+                Distances[j][i] = d;
+            }
+        }
+        int BestMedian = INT_MAX, BestIdx = 0;
+        for (int i = 0; i < N; ++i) {
+            std::vector<int> vDists(Distances[i].begin(), Distances[i].end());
+            std::sort(vDists.begin(), vDists.end());
+            const int median = vDists[0.5 * (N - 1)];
+            if (median < BestMedian) { BestMedian = median; BestIdx = i; }
+        }
+        best_idx[p] = BestIdx;
+        best_median[p] = BestMedian;
     }
 }

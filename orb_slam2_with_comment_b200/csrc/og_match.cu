@@ -2076,3 +2076,92 @@ extern "C" int orbgpu_is_in_frustum(orbgpu_matcher* m, int n_frames, const float
     OGM_CUDA(cudaStreamSynchronize(st));
     return ORBGPU_OK;
 }
+
+// ---- MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:247-316) -------------------------------------------------------
+namespace og {
+// One block per map point.  Shared: N descriptors (uint4 pairs) | N x N distance matrix (u16).
+__global__ void __launch_bounds__(128) k_distinctive(const int32_t* __restrict__ obs_off, const uint8_t* __restrict__ desc, int n_max,
+                                                     int32_t* __restrict__ best_idx, int32_t* __restrict__ best_median) {
+    extern __shared__ __align__(16) unsigned char dd_smem[];
+    uint4* sd = reinterpret_cast<uint4*>(dd_smem);
+    uint16_t* dm = reinterpret_cast<uint16_t*>(dd_smem + (size_t)n_max * 32);
+    __shared__ uint32_t wbest[4];
+    const int p = blockIdx.x, t = threadIdx.x;
+    const int o = obs_off[p], N = obs_off[p + 1] - o;
+    if (N <= 0) {
+        if (t == 0) { best_idx[p] = -1; if (best_median) best_median[p] = 0x7fffffff; }
+        return;
+    }
+    const uint4* g = reinterpret_cast<const uint4*>(desc + (size_t)o * 32);
+    for (int i = t; i < 2 * N; i += 128) sd[i] = __ldg(g + i);
+    __syncthreads();
+    for (int e = t; e < N * N; e += 128) {
+        const int i = e / N, j = e - i * N;
+        Desc a, b;
+        a.lo = sd[2 * i]; a.hi = sd[2 * i + 1];
+        b.lo = sd[2 * j]; b.hi = sd[2 * j + 1];
+        dm[e] = (uint16_t)hamming256(a, b);
+    }
+    __syncthreads();
+    const int k = (int)(0.5 * (N - 1));   // vDists[0.5*(N-1)] (:301)
+    uint32_t best = 0xffffffffu;
+    for (int r = t; r < N; r += 128) {
+        const uint16_t* row = dm + (size_t)r * N;
+        int lo = 0, hi = 256;             // smallest v with #{d <= v} >= k + 1
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            int c = 0;
+            for (int j = 0; j < N; ++j) c += row[j] <= mid;
+            if (c >= k + 1) hi = mid; else lo = mid + 1;
+        }
+        best = min(best, ((uint32_t)lo << 16) | (uint32_t)r);
+    }
+    best = __reduce_min_sync(0xffffffffu, best);
+    if ((t & 31) == 0) wbest[t >> 5] = best;
+    __syncthreads();
+    if (t == 0) {
+        best = min(min(wbest[0], wbest[1]), min(wbest[2], wbest[3]));
+        best_idx[p] = (int32_t)(best & 0xffffu);
+        if (best_median) best_median[p] = (int32_t)(best >> 16);
+    }
+}
+}  // namespace og
+
+extern "C" int orbgpu_distinctive_descriptors(orbgpu_matcher* m, int n_points, const int32_t* obs_off, const uint8_t* desc, int32_t* best_idx,
+                                              int32_t* best_median) {
+    int rc = check_matcher(m);
+    if (rc) return rc;
+    m->last_launches = 0;
+    if (n_points < 0 || (n_points && (!obs_off || !best_idx))) return og_fail(ORBGPU_ERR_ARG, "distinctive_descriptors: null argument");
+    if (n_points == 0) return ORBGPU_OK;
+    int n_max = 0;
+    for (int p = 0; p < n_points; ++p) {
+        if (obs_off[p + 1] < obs_off[p]) return og_fail(ORBGPU_ERR_ARG, "distinctive_descriptors: obs_off must be non-decreasing");
+        n_max = std::max(n_max, obs_off[p + 1] - obs_off[p]);
+    }
+    if (n_max > 256) return og_fail(ORBGPU_ERR_CAPACITY, "distinctive_descriptors: more than 256 observations of one map point");
+    const size_t total = (size_t)obs_off[n_points];
+    if (total && !desc) return og_fail(ORBGPU_ERR_ARG, "distinctive_descriptors: null descriptors");
+    cudaStream_t st = m->stream;
+    m->tmp_next = 0;
+    void *d_off, *d_desc, *d_idx, *d_med;
+    OGM_CUDA(m->s_tmp[m->tmp_next++].grab((size_t)(n_points + 1) * 4, &d_off));
+    OGM_CUDA(m->s_tmp[m->tmp_next++].grab(std::max<size_t>(total, 1) * 32, &d_desc));
+    OGM_CUDA(m->s_tmp[m->tmp_next++].grab((size_t)n_points * 4, &d_idx));
+    OGM_CUDA(m->s_tmp[m->tmp_next++].grab((size_t)n_points * 4, &d_med));
+    OGM_CUDA(cudaMemcpyAsync(d_off, obs_off, (size_t)(n_points + 1) * 4, cudaMemcpyHostToDevice, st));
+    if (total) OGM_CUDA(cudaMemcpyAsync(d_desc, desc, total * 32, cudaMemcpyHostToDevice, st));
+    const size_t smem = (size_t)n_max * 32 + (size_t)n_max * n_max * 2;
+    static bool attr_set = false;
+    if (smem > 48 * 1024 && !attr_set) {
+        OGM_CUDA(cudaFuncSetAttribute(og::k_distinctive, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 32 + 256 * 256 * 2));
+        attr_set = true;
+    }
+    og::k_distinctive<<<n_points, 128, smem, st>>>((const int32_t*)d_off, (const uint8_t*)d_desc, n_max, (int32_t*)d_idx, (int32_t*)d_med);
+    m->last_launches = 1;
+    OGM_CUDA(cudaGetLastError());
+    OGM_CUDA(cudaMemcpyAsync(best_idx, d_idx, (size_t)n_points * 4, cudaMemcpyDeviceToHost, st));
+    if (best_median) OGM_CUDA(cudaMemcpyAsync(best_median, d_med, (size_t)n_points * 4, cudaMemcpyDeviceToHost, st));
+    OGM_CUDA(cudaStreamSynchronize(st));
+    return ORBGPU_OK;
+}

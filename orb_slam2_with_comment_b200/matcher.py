@@ -138,6 +138,7 @@ def _bind(L):
     L.orbgpu_search_for_triangulation_dev.argtypes = [vp, vp, vp, i, vp, vp, vp, vp, vp, vp, i, i, i, vp, vp, vp, vp]
     L.orbgpu_search_by_bow.argtypes = [vp, C.POINTER(CFrameSet), C.POINTER(CFrameSet), i, vp, vp, f, i, i, i, i, vp, vp, vp, vp]
     L.orbgpu_search_by_bow_dev.argtypes = [vp, vp, vp, i, vp, vp, f, i, i, i, i, vp, vp, vp, vp]
+    L.orbgpu_distinctive_descriptors.argtypes = [vp, i, vp, vp, vp, vp]
     L.orbgpu_is_in_frustum.argtypes = [vp, i, vp, f, i, f] + [vp] * 12
     L.orbgpu_is_in_frustum_dev.argtypes = [vp, i, vp, f, i, f] + [vp] * 12
     L.orbgpu_frame_set_from_extraction.argtypes = [vp, vp, vp, i, i, vp, i, vp, C.POINTER(vp)]
@@ -266,6 +267,15 @@ class ORBmatcher:
                                                   mp_off.ctypes.data, *[a.ctypes.data for a in ins], *[out[k].ctypes.data for k in
                                                   ("in_view", "proj_x", "proj_y", "proj_xr", "level", "view_cos")]))
         return out
+
+    def ComputeDistinctiveDescriptors(self, obs_off, desc):
+        """MapPoint::ComputeDistinctiveDescriptors for a batch of map points: (best row per point, its median distance)."""
+        obs_off = np.ascontiguousarray(obs_off, np.int32)
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        n = len(obs_off) - 1
+        idx, med = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        capi.check(self._lib.orbgpu_distinctive_descriptors(self._h, n, obs_off.ctypes.data, desc.ctypes.data, idx.ctypes.data, med.ctypes.data))
+        return idx, med
 
     def upload(self, fs: FrameSet) -> C.c_void_p:
         h = C.c_void_p()

@@ -187,3 +187,25 @@ def frustum_case(seed, n_frames=4, n_mp=6000):
         offs.append(offs[-1] + n)
     return (np.stack(cams), np.float32(np.log(np.float32(1.2))), 8, 0.5, np.array(offs, np.int32), np.concatenate(P), np.concatenate(Nn),
             np.concatenate(dmin), np.concatenate(dmax), np.concatenate(dref))
+
+
+def distinctive_case(seed, n_points=3000, n_max=60):
+    """Observation sets of map points: a true descriptor seen from 0..n_max key frames with a few bits flipped each time,
+    a share of outliers, exact duplicates (ties) and a few large sets."""
+    rs = np.random.RandomState(seed)
+    sizes = rs.randint(0, n_max + 1, n_points)
+    sizes[:6] = [0, 1, 2, 3, 255, 256]
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    desc = np.zeros((int(off[-1]), 32), np.uint8)
+    for p in range(n_points):
+        n = sizes[p]
+        if not n:
+            continue
+        base = rs.randint(0, 256, (1, 32)).astype(np.uint8)
+        d = synth.flip_bits(np.repeat(base, n, 0), rs, rs.uniform(0.0, 0.12))
+        out = rs.uniform(size=n) < 0.15
+        d[out] = rs.randint(0, 256, (int(out.sum()), 32)).astype(np.uint8)
+        if n > 3 and p % 3 == 0:
+            d[n // 2] = d[0]
+        desc[off[p]:off[p + 1]] = d
+    return off, desc

@@ -397,3 +397,14 @@ def is_in_frustum(lib, cam, log_scale_factor, n_levels, viewing_cos_limit, mp_of
     lib.orbm_is_in_frustum(len(cam), _p(cam, vp), float(log_scale_factor), n_levels, float(viewing_cos_limit), _p(mp_off, vp), *[_p(a, vp) for a in ins],
                            *[_p(out[k], vp) for k in ("in_view", "proj_x", "proj_y", "proj_xr", "level", "view_cos")])
     return out
+
+
+def distinctive_descriptors(lib, obs_off, desc):
+    vp = C.c_void_p
+    lib.orbm_distinctive_descriptors.argtypes = [C.c_int, vp, vp, vp, vp]
+    obs_off = np.ascontiguousarray(obs_off, np.int32)
+    desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+    n = len(obs_off) - 1
+    idx, med = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    lib.orbm_distinctive_descriptors(n, _p(obs_off, vp), _p(desc, vp), _p(idx, vp), _p(med, vp))
+    return idx, med

@@ -260,3 +260,18 @@ def test_is_in_frustum_matches_oracle():
     assert len(diff) <= 2 and np.all(np.abs(got["level"][diff] - exp["level"][diff]) == 1), diff
     assert len(np.unique(exp["level"][exp["in_view"] == 1])) == 8
     m.close()
+
+
+def test_distinctive_descriptors_match_oracle():
+    """MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:247-316): least-median row per map point, first wins."""
+    from orb_slam2_with_comment_b200 import capi
+    from orb_slam2_with_comment_b200.matcher import ORBmatcher
+    off, desc = mc.distinctive_case(11)
+    ei, em = ol.distinctive_descriptors(ol.load_port(), off, desc)
+    m = ORBmatcher()
+    gi, gm = m.ComputeDistinctiveDescriptors(off, desc)
+    assert np.array_equal(gi, ei) and np.array_equal(gm[ei >= 0], em[ei >= 0])
+    assert ei[0] == -1 and ei[1] == 0 and (ei > 0).mean() > 0.5
+    with pytest.raises(capi.OrbGpuError):
+        m.ComputeDistinctiveDescriptors(np.array([0, 257], np.int32), np.zeros((257, 32), np.uint8))
+    m.close()
