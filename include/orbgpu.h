@@ -312,6 +312,21 @@ int orbgpu_is_in_frustum_dev(orbgpu_matcher* m, int n_frames, const float* cam, 
                              uint8_t* in_view_dev, float* proj_x_dev, float* proj_y_dev, float* proj_xr_dev, int32_t* level_dev,
                              float* view_cos_dev);
 
+/* Best-only windowed search: the candidate loops of ORBmatcher::Fuse(KeyFrame*, const vector<MapPoint*>&, th)
+ * (ORBmatcher.cc:1051-1112), Fuse(KeyFrame*, Scw, ...) (:1211-1246) and both directions of SearchBySim3 (:1363-1401,
+ * :1443-1481).  Queries are independent — no key point is taken by an earlier query; the map updates that follow in the
+ * reference (Replace / AddObservation / the agreement check) stay with the caller.  For every live query (flags bit 0):
+ * candidates = key points of the frame inside the window (u, v, radius) with octave in [min_level, max_level]
+ * (KeyFrame::GetFeaturesInArea order, KeyFrame.cc:583-622), minus those with kp_flags != 0 when skip_flagged
+ * (vbAlreadyMatched2 / vbAlreadyMatched1 of SearchBySim3); with inv_level_sigma2 != NULL (mvInvLevelSigma2, n_levels entries)
+ * a candidate must also pass Fuse's chi-square gate: e2 * invSigma2[octave] <= 5.99 with e2 = ex^2 + ey^2 for a monocular
+ * key point (mvuRight < 0), <= 7.8 with e2 = ex^2 + ey^2 + er^2 for a stereo one (er from queries->ur, which must be given).
+ * Outputs: the candidate of least distance (first wins) and that distance; -1 / 256 if none.  The caller compares with
+ * TH_LOW (Fuse) or TH_HIGH (SearchBySim3). */
+int orbgpu_search_window_best(orbgpu_matcher* m, const orbgpu_frame_set* frames, const orbgpu_window_query_set* queries,
+                              const float* inv_level_sigma2, int n_levels, int skip_flagged, int32_t* q_best_idx,
+                              int32_t* q_best_dist);
+
 /* MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:247-316) for a batch of map points: point p owns the descriptors
  * [obs_off[p], obs_off[p+1]) of `desc` (the rows of its observing, non-bad key frames in the reference's iteration order,
  * 32 bytes each, at most 256 per point).  best_idx[p] = the row (relative to obs_off[p]) with the least median Hamming

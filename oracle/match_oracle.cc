@@ -473,3 +473,46 @@ extern "C" void orbm_distinctive_descriptors(int n_points, const int32_t* obs_of
         best_median[p] = BestMedian;
     }
 }
+
+// The candidate loops of Fuse (ORBmatcher.cc:1051-1112, :1211-1246) and SearchBySim3 (:1363-1401, :1443-1481): independent
+// queries, best candidate only; optional chi-square gate of Fuse(KF, vpMapPoints, th) (:1077-1102).
+extern "C" void orbm_search_window_best(const orbgpu_frame_set* fs, const orbgpu_window_query_set* qs, const float* inv_sigma2, int skip_flagged,
+                                        int32_t* q_best_idx, int32_t* q_best_dist) {
+    for (int f = 0; f < fs->n_frames; ++f) {
+        const int k0 = fs->kp_off[f], n = fs->kp_off[f + 1] - k0;
+        const orbgpu_keypoint* keys = fs->keys_un + k0;
+        const float* g = fs->grid + 4 * f;
+        Grid G;
+        assign_grid(keys, n, g, G);
+        std::vector<int> vIndices;
+        for (int q = qs->q_off[f]; q < qs->q_off[f + 1]; ++q) {
+            q_best_idx[q] = -1;
+            q_best_dist[q] = 256;
+            if (!(qs->flags[q] & 1)) continue;
+            const float u = qs->u[q], v = qs->v[q];
+            features_in_area(G, keys, g, u, v, qs->radius[q], qs->min_level[q], qs->max_level[q], vIndices);
+            int bestDist = 256, bestIdx = -1;
+            for (size_t j = 0; j < vIndices.size(); ++j) {
+                const int idx = vIndices[j];
+                if (skip_flagged && fs->kp_flags && fs->kp_flags[k0 + idx] != 0) continue;
+                if (inv_sigma2) {
+                    const orbgpu_keypoint& kp = keys[idx];
+                    const float kur = fs->u_right ? fs->u_right[k0 + idx] : -1.f;
+                    const float ex = u - kp.x, ey = v - kp.y;
+                    if (kur >= 0) {
+                        const float er = qs->ur[q] - kur;
+                        const float e2 = ex * ex + ey * ey + er * er;
+                        if (e2 * inv_sigma2[kp.octave] > 7.8) continue;
+                    } else {
+                        const float e2 = ex * ex + ey * ey;
+                        if (e2 * inv_sigma2[kp.octave] > 5.99) continue;
+                    }
+                }
+                const int dist = descriptor_distance(qs->desc + (size_t)q * 32, fs->desc + (size_t)(k0 + idx) * 32);
+                if (dist < bestDist) { bestDist = dist; bestIdx = idx; }
+            }
+            q_best_idx[q] = bestIdx;
+            q_best_dist[q] = bestDist;
+        }
+    }
+}

@@ -527,6 +527,8 @@ struct SbpArgs {
     int th_dist;           // generic: accept when best <= th_dist
     int check_orientation; // generic: rotation histogram
     int8_t* q_bin;         // generic: [total queries] histogram bin of the accepted query, -1 otherwise
+    const float* inv_sigma2;  // generic, best-only searches: mvInvLevelSigma2 for the chi-square gate of Fuse (:1077-1102); null = no gate
+    int no_xr_window;      // generic: the |ur - mvuRight| <= radius test (:1624-1630) is off (Fuse / SearchBySim3 have none)
     int n_frames;
     const float* scale;
     float th, nnratio;
@@ -699,7 +701,19 @@ __device__ __forceinline__ int sbp_scan_warp(const SbpArgs& A, const SbpQuery& Q
                 if (st == 1 || (A.skip_any && st != 0)) continue;
             }
             if (blocked && ((blocked[idx >> 5] >> (idx & 31)) & 1u)) continue;
-            if (Q.use_xr && A.F.u_right && A.F.u_right[Q.k0 + idx] > 0.f) {   // (:113-118, :1624-1630)
+            if (A.inv_sigma2) {   // reprojection error against the candidate's key point, chi-square at 95 % (ORBmatcher.cc:1077-1102)
+                const float kur = A.F.u_right ? A.F.u_right[Q.k0 + idx] : -1.f;
+                const float ex = __fsub_rn(Q.x, kp.x), ey = __fsub_rn(Q.y, kp.y);
+                float e2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+                double lim = 5.99;
+                if (kur >= 0.f) {
+                    const float er = __fsub_rn(Q.xr, kur);
+                    e2 = __fadd_rn(e2, __fmul_rn(er, er));
+                    lim = 7.8;
+                }
+                if ((double)__fmul_rn(e2, A.inv_sigma2[kp.octave]) > lim) continue;
+            }
+            if (Q.use_xr && !A.no_xr_window && A.F.u_right && A.F.u_right[Q.k0 + idx] > 0.f) {   // (:113-118, :1624-1630)
                 const float er = fabsf(__fsub_rn(Q.xr, A.F.u_right[Q.k0 + idx]));
                 if (er > Q.rs) continue;
             }
@@ -818,6 +832,15 @@ __global__ void __launch_bounds__(32) k_sbp_select(const __grid_constant__ SbpAr
 // Phase B of the generic windowed search, one warp per frame: queries in order, best candidate only, accept when
 // best <= th_dist, CurrentFrame.mvpMapPoints[bestIdx2] = pMP (:1644, :1789), rotation histogram over the accepted queries and
 // removal of the matches outside the three main bins (:1663-1682: the key point is reset to NULL -> kp_match = -2).
+// Best-only searches (Fuse, SearchBySim3): queries are independent, the winner is the head of the top-K list.
+__global__ void __launch_bounds__(256) k_win_best(const __grid_constant__ SbpArgs A, int nq) {
+    const int q = blockIdx.x * 256 + threadIdx.x;
+    if (q >= nq) return;
+    const uint32_t key = A.topk_key[(long long)q * kTopK];
+    A.mp_best_idx[q] = key == kEmptyKey ? -1 : A.topk_idx[(long long)q * kTopK];
+    A.mp_best_dist[q] = key == kEmptyKey ? 256 : (int)(key >> kPosBits);
+}
+
 __global__ void __launch_bounds__(32) k_win_select(const __grid_constant__ SbpArgs A) {
     extern __shared__ uint32_t smem_b[];
     uint32_t* blocked = smem_b;
@@ -1343,7 +1366,8 @@ int sbp_dev(orbgpu_matcher* m, const orbgpu_frame_set_dev* fs, const orbgpu_mapp
 
 // Generic windowed search (host pointers): the query arrays are uploaded into pooled scratch, the frame set likewise.
 int win_host(orbgpu_matcher* m, const orbgpu_frame_set* frames, const orbgpu_window_query_set* qs, int th_dist, int skip_any,
-             int check_orientation, int32_t* kp_match, int32_t* q_best_idx, int32_t* q_best_dist, int32_t* nmatches) {
+             int check_orientation, int32_t* kp_match, int32_t* q_best_idx, int32_t* q_best_dist, int32_t* nmatches, bool best_only = false,
+             const float* inv_sigma2 = nullptr, int n_levels = 0) {
     using namespace og;
     m->last_launches = 0;
     if (!frames || !qs || !qs->q_off) return og_fail(ORBGPU_ERR_ARG, "null argument");
@@ -1370,6 +1394,8 @@ int win_host(orbgpu_matcher* m, const orbgpu_frame_set* frames, const orbgpu_win
     if (!rc) rc = upload_array(qs->max_level, (size_t)nq, owned, &A.W.max_level, st, m);
     if (!rc) rc = upload_array(qs->flags, (size_t)nq, owned, &A.W.flags, st, m);
     if (!rc) rc = upload_array(qs->desc, (size_t)nq * 32, owned, &A.W.desc, st, m);
+    if (!rc && inv_sigma2) rc = upload_array(inv_sigma2, (size_t)n_levels, owned, &A.inv_sigma2, st, m);
+    A.no_xr_window = best_only ? 1 : 0;
     void* d[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     void* ptr = nullptr;
     cudaError_t ce = cudaSuccess;
@@ -1388,6 +1414,7 @@ int win_host(orbgpu_matcher* m, const orbgpu_frame_set* frames, const orbgpu_win
     }
     if (!rc) {
         A.F = F.v;
+        if (best_only && !skip_any) A.F.flags = nullptr;   // Fuse looks at every candidate, whatever MapPoint it holds
         A.n_frames = nf;
         A.generic = 1;
         A.skip_any = skip_any;
@@ -1407,8 +1434,12 @@ int win_host(orbgpu_matcher* m, const orbgpu_frame_set* frames, const orbgpu_win
             cudaMemsetAsync(m->d_evals, 0, 8, st);
             k_grid_build<<<nf, kGridThreads, 0, st>>>(A);
             if (nq > 0) k_sbp_topk<<<(nq + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock * 32, 0, st>>>(A, nq);
-            if (smem > 48 * 1024) cudaFuncSetAttribute(k_win_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            k_win_select<<<nf, 32, smem, st>>>(A);
+            if (best_only) {
+                if (nq > 0) k_win_best<<<(nq + 255) / 256, 256, 0, st>>>(A, nq);
+            } else {
+                if (smem > 48 * 1024) cudaFuncSetAttribute(k_win_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                k_win_select<<<nf, 32, smem, st>>>(A);
+            }
             cudaEventRecord(m->ev1, st);
             m->last_launches = 3;
             ce = cudaGetLastError();
@@ -2164,4 +2195,15 @@ extern "C" int orbgpu_distinctive_descriptors(orbgpu_matcher* m, int n_points, c
     if (best_median) OGM_CUDA(cudaMemcpyAsync(best_median, d_med, (size_t)n_points * 4, cudaMemcpyDeviceToHost, st));
     OGM_CUDA(cudaStreamSynchronize(st));
     return ORBGPU_OK;
+}
+
+// Best-only windowed search (the search loops of Fuse x2 and SearchBySim3): see include/orbgpu.h
+extern "C" int orbgpu_search_window_best(orbgpu_matcher* m, const orbgpu_frame_set* frames, const orbgpu_window_query_set* queries,
+                                         const float* inv_level_sigma2, int n_levels, int skip_flagged, int32_t* q_best_idx,
+                                         int32_t* q_best_dist) {
+    int rc = check_matcher(m);
+    if (rc) return rc;
+    if (inv_level_sigma2 && n_levels < 1) return og_fail(ORBGPU_ERR_ARG, "search_window_best: n_levels");
+    if (inv_level_sigma2 && queries && !queries->ur) return og_fail(ORBGPU_ERR_ARG, "search_window_best: the chi-square gate needs the queries' ur");
+    return win_host(m, frames, queries, 256, skip_flagged, 0, nullptr, q_best_idx, q_best_dist, nullptr, true, inv_level_sigma2, n_levels);
 }

@@ -138,6 +138,7 @@ def _bind(L):
     L.orbgpu_search_for_triangulation_dev.argtypes = [vp, vp, vp, i, vp, vp, vp, vp, vp, vp, i, i, i, vp, vp, vp, vp]
     L.orbgpu_search_by_bow.argtypes = [vp, C.POINTER(CFrameSet), C.POINTER(CFrameSet), i, vp, vp, f, i, i, i, i, vp, vp, vp, vp]
     L.orbgpu_search_by_bow_dev.argtypes = [vp, vp, vp, i, vp, vp, f, i, i, i, i, vp, vp, vp, vp]
+    L.orbgpu_search_window_best.argtypes = [vp, C.POINTER(CFrameSet), C.POINTER(CWindowQuerySet), vp, i, i, vp, vp]
     L.orbgpu_distinctive_descriptors.argtypes = [vp, i, vp, vp, vp, vp]
     L.orbgpu_is_in_frustum.argtypes = [vp, i, vp, f, i, f] + [vp] * 12
     L.orbgpu_is_in_frustum_dev.argtypes = [vp, i, vp, f, i, f] + [vp] * 12
@@ -267,6 +268,15 @@ class ORBmatcher:
                                                   mp_off.ctypes.data, *[a.ctypes.data for a in ins], *[out[k].ctypes.data for k in
                                                   ("in_view", "proj_x", "proj_y", "proj_xr", "level", "view_cos")]))
         return out
+
+    def SearchWindowBest(self, frames: FrameSet, queries: "WindowQuerySet", inv_level_sigma2=None, skip_flagged: bool = False):
+        """The candidate loops of Fuse / SearchBySim3: independent queries, best candidate only (orbgpu_search_window_best)."""
+        nq = int(queries.q_off[-1])
+        bi, bd = np.zeros(nq, np.int32), np.zeros(nq, np.int32)
+        s2 = None if inv_level_sigma2 is None else np.ascontiguousarray(inv_level_sigma2, np.float32)
+        capi.check(self._lib.orbgpu_search_window_best(self._h, C.byref(frames.c), C.byref(queries.c), None if s2 is None else s2.ctypes.data,
+                                                       0 if s2 is None else len(s2), int(skip_flagged), bi.ctypes.data, bd.ctypes.data))
+        return {"q_best_idx": bi, "q_best_dist": bd}
 
     def ComputeDistinctiveDescriptors(self, obs_off, desc):
         """MapPoint::ComputeDistinctiveDescriptors for a batch of map points: (best row per point, its median distance)."""

@@ -224,6 +224,14 @@ class MatcherOracle:
                                       kp_match.ctypes.data, bi.ctypes.data, bd.ctypes.data, nm.ctypes.data)
         return {"nmatches": nm, "kp_match": kp_match, "q_best_idx": bi, "q_best_dist": bd}
 
+    def SearchWindowBest(self, frames, queries, inv_level_sigma2=None, skip_flagged=False):
+        bi, bd = np.full(queries.n, -1, np.int32), np.full(queries.n, 256, np.int32)
+        s2 = None if inv_level_sigma2 is None else np.ascontiguousarray(inv_level_sigma2, np.float32)
+        self.lib.orbm_search_window_best.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        self.lib.orbm_search_window_best(C.byref(frames.c), C.byref(queries.c), None if s2 is None else s2.ctypes.data, int(skip_flagged),
+                                         bi.ctypes.data, bd.ctypes.data)
+        return {"q_best_idx": bi, "q_best_dist": bd}
+
     def SearchForTriangulation(self, set1, set2, idx1, idx2, F12, epipole, scale_factors, level_sigma2, bOnlyStereo=False):
         from orb_slam2_with_comment_b200.matcher import match_offsets
         idx1, idx2 = np.ascontiguousarray(idx1, np.int32), np.ascontiguousarray(idx2, np.int32)

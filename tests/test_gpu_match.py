@@ -275,3 +275,25 @@ def test_distinctive_descriptors_match_oracle():
     with pytest.raises(capi.OrbGpuError):
         m.ComputeDistinctiveDescriptors(np.array([0, 257], np.int32), np.zeros((257, 32), np.uint8))
     m.close()
+
+
+@pytest.mark.parametrize("stereo,gate,skip", [(0.0, True, False), (0.5, True, False), (0.5, False, False), (0.0, False, True)])
+def test_window_best_vs_oracle(gm, mo, stereo, gate, skip):
+    """The candidate loops of Fuse (ORBmatcher.cc:1051-1112 with the chi-square gate, :1211-1246 without) and SearchBySim3
+    (:1363-1401: candidates already matched are skipped): independent queries, best candidate only."""
+    from orb_slam2_with_comment_b200.matcher import WindowQuerySet
+    _, s2 = synth.scale_tables()
+    inv_s2 = (np.float32(1.0) / s2).astype(np.float32) if gate else None
+    for seed in (811, 812):
+        fs, qs = mc.win_case(seed, n_frames=5, n_lo=700, n_hi=1500, n_q=1200, stereo_frac=stereo, mode="keyframe", th=12.0)
+        # Fuse / SearchBySim3 search levels [l-1, l]
+        q2 = WindowQuerySet(qs.q_off, qs.u, qs.v, qs.radius, qs.min_level, qs.min_level + 1, qs.flags, qs.desc,
+                            ur=qs.ur if qs.ur is not None else (qs.u - 5.0).astype(np.float32), angle=qs.angle)
+        got = gm(0.9, False).SearchWindowBest(fs, q2, inv_s2, skip)
+        exp = mo(0.9, False).SearchWindowBest(fs, q2, inv_s2, skip)
+        same(got, exp, ("q_best_idx", "q_best_dist"), f"window best seed {seed}")
+        found = (exp["q_best_idx"] >= 0).sum()
+        assert found > 300
+        if gate:   # the gate must reject some candidates a plain search accepts
+            plain = mo(0.9, False).SearchWindowBest(fs, q2, None, skip)
+            assert (plain["q_best_idx"] != exp["q_best_idx"]).sum() > 50
