@@ -757,7 +757,7 @@ __device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c) {   // uns
     return r;
 }
 
-__global__ void __launch_bounds__(kDescWarps * 32) k_orient_desc(const __grid_constant__ ExtractParams P, KeyPoint* __restrict__ kp_out,
+__global__ void __launch_bounds__(kDescWarps * 32, 6) k_orient_desc(const __grid_constant__ ExtractParams P, KeyPoint* __restrict__ kp_out,
                                                                  uint8_t* __restrict__ desc_out,
                                                                  int32_t* __restrict__ counts) {
     // pattern point j of lane i (= bit_pattern_31_ point 16 i + j) at spat[j * 32 + i]: the 32 lanes of a load hit 32
