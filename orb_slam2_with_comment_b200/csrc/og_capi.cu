@@ -441,8 +441,10 @@ int launch_extract(orbgpu_extractor* ex, const uint8_t* d_images, int batch, siz
     mark(0);
     {
         const og::Level& L = P.lv[0];
-        dim3 grid(((L.w + 15) / 16 + 63) / 64, L.h, batch);
-        og::k_level0<<<grid, 64, 0, st>>>(P, d_images, (long long)row_stride, (long long)frame_stride);
+        const int nvec = (L.w + 15) / 16, n_items = nvec * L.h;
+        const uint32_t magic = (uint32_t)(((1ull << 32) + nvec - 1) / nvec);   // exact floor(id / nvec) for id < 2^32 / nvec
+        og::k_level0<<<dim3((n_items + 255) / 256, batch), 256, 0, st>>>(P, d_images, (long long)row_stride, (long long)frame_stride, nvec, magic,
+                                                                      n_items);
         ++launches;
     }
     bool generic = false;
@@ -465,15 +467,11 @@ int launch_extract(orbgpu_extractor* ex, const uint8_t* d_images, int batch, siz
         ++launches;
     }
     {
-        // the generic resize writes its own frame; k_borders then only repeats it (and does level 0)
-        og::BorderPlan bp;
-        int acc = 0;
-        for (int l = 0; l < P.n_levels; ++l) {
-            bp.first[l] = acc;
-            acc += 2 * og::kEdge * P.lv[l].h + 2 * og::kEdge * ((P.lv[l].w + 2 * og::kEdge + 3) / 4);
-        }
-        for (int l = P.n_levels; l <= og::kMaxLevels; ++l) bp.first[l] = acc;
-        og::k_borders<<<dim3((acc + og::kBorderThreads - 1) / og::kBorderThreads, batch), og::kBorderThreads, 0, st>>>(P, bp);
+        // the generic resize writes its own frame; the border kernels then only repeat it (and do level 0)
+        const int sides0 = 2 * P.lv[0].h;
+        og::k_border_sides<<<dim3((sides0 + og::kBorderThreads - 1) / og::kBorderThreads, P.n_levels, batch), og::kBorderThreads, 0, st>>>(P);
+        og::k_border_caps<<<dim3(2 * og::kEdge, P.n_levels, batch), og::kBorderThreads, 0, st>>>(P);
+        ++launches;
         ++launches;
     }
     mark(1);

@@ -3,7 +3,7 @@
 //   k_level0        the input image into the interior of level 0                     (:1127)
 //   k_resize4       cv::resize INTER_LINEAR level l-1 -> l, 4 pixels per thread       (:1120)
 //   k_resize        the same, any scale, one pass incl. frame (fallback for scale > 2)
-//   k_borders       BORDER_REFLECT_101 frame of every level                          (:1122-1128)
+//   k_border_sides / k_border_caps   BORDER_REFLECT_101 frame of every level         (:1122-1128)
 //   k_fast_seg      per-cell FAST-9/16 + 3x3 NMS + iniTh/minTh fallback (TMA tiles)  (:789-829)
 //   k_octree        DistributeOctTree, one CTA per (frame, level)                    (:539-763)
 //   k_blur_tma      GaussianBlur 7x7 sigma 2 (TMA tiles, DP4A)                       (:1085-1086)
@@ -25,18 +25,19 @@ __device__ __forceinline__ uint8_t* level_ptr(uint8_t* base, const Level& L, int
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Level 0: copy of the input image into the interior of the level-0 buffer (the frame is written by k_borders).
+// Level 0: copy of the input image into the interior of the level-0 buffer (the frame is written by the border kernels).
 // One thread moves 16 pixels: the source row may start at any byte address, so it is read as five aligned words
 // realigned with funnel shifts, and stored as one 16-byte vector (the interior starts 16-byte aligned).
 // The last vector of a row is copied byte-wise so that nothing past the row's end is ever read.
 // ------------------------------------------------------------------------------------------------------------
-__global__ void k_level0(const __grid_constant__ ExtractParams P, const uint8_t* __restrict__ images, long long row_stride,
-                         long long frame_stride) {
+__global__ void __launch_bounds__(256) k_level0(const __grid_constant__ ExtractParams P, const uint8_t* __restrict__ images, long long row_stride,
+                                                long long frame_stride, int nvec, uint32_t nvec_magic, int n_items) {
     const Level& L = P.lv[0];
-    const int frame = P.frame0 + blockIdx.z;
-    const int y = blockIdx.y;
-    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
-    if (x >= L.w) return;
+    const int frame = P.frame0 + blockIdx.y;
+    const int id = blockIdx.x * 256 + threadIdx.x;   // one item = 16 pixels; nvec items per row (no idle threads at row ends)
+    if (id >= n_items) return;
+    const int y = (int)__umulhi((uint32_t)id, nvec_magic);
+    const int x = (id - y * nvec) * 16;
     const uint8_t* src = images + (long long)frame * frame_stride + (long long)y * row_stride + x;
     uint8_t* dst = level_ptr(P.pyr, L, frame) + (long long)(kEdge + y) * L.pitch + kXPad + x;
     if (x + 20 <= L.w) {   // the five words reach at most byte x + 19 of the row
@@ -87,7 +88,7 @@ __global__ void k_resize(const __grid_constant__ ExtractParams P, int level) {
 // three aligned words per source row; the byte pair of every output is cut out with a funnel shift whose word
 // choice and shift depend only on x and are computed once.  Consecutive output rows share a source row about
 // every other step (scale 1.2): the horizontal pass of the shared row is reused.
-// The 19-px frames of all levels are written afterwards by k_borders.
+// The 19-px frames of all levels are written afterwards by the border kernels.
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kResizeRows = 8, kResizeThreads = 128;
 
@@ -215,42 +216,58 @@ __global__ void __launch_bounds__(kResizeThreads) k_resize4_mlp(const __grid_con
     }
 }
 
-// The BORDER_REFLECT_101 frame of every level (:1122-1123, :1127).  Work items per level:
-// 38*h "side" items (one byte of the frame left or right of an interior row) and 38 * ceil((w+38)/4) "cap"
-// items (one thread writes 4 bytes of a top/bottom row).  Item -> (level, kind) through the per-level prefix in `B`.
+// The BORDER_REFLECT_101 frame of every level (:1122-1123, :1127), in two kernels.
+//   k_border_sides  one thread per (row, side): the 19 frame bytes left or right of an interior row are the mirrored
+//                   interior bytes 1..19 (w-2..w-20).  They are read as aligned words and written as aligned words: a
+//                   frame word is four consecutive interior bytes in reverse order = funnel shift + PRMT.  The words that
+//                   straddle the frame's ends also cover padding bytes of the row (nobody reads those) or, on the right,
+//                   the last interior bytes (rewritten with their own values).
+//   k_border_caps   then the 19 rows above and below are whole-row copies of padded rows (the corners come along), moved as
+//                   16-byte vectors.
+// grid = (items, level, frame): blocks beyond a level's item count exit at once.
+// ------------------------------------------------------------------------------------------------------------
 constexpr int kBorderThreads = 128;
-struct BorderPlan {
-    int first[kMaxLevels + 1];   // first item of level l, total at [n_levels]
-};
-__global__ void __launch_bounds__(kBorderThreads) k_borders(const __grid_constant__ ExtractParams P, const __grid_constant__ BorderPlan B) {
-    const int frame = P.frame0 + blockIdx.y;
-    int it = blockIdx.x * kBorderThreads + threadIdx.x;
-    if (it >= B.first[P.n_levels]) return;
-    int level = 0;
-    while (it >= B.first[level + 1]) ++level;
-    it -= B.first[level];
-    const Level& L = P.lv[level];
-    uint8_t* img = level_ptr(P.pyr, L, frame);
-    if (it < 2 * kEdge * L.h) {
-        // one byte of the left / right frame of an interior row: consecutive threads write consecutive bytes
-        const int y = it / (2 * kEdge), k = it - y * 2 * kEdge;
-        const int X = k < kEdge ? k : L.w + k;                         // padded column
-        uint8_t* row = img + (long long)(kEdge + y) * L.pitch + kXPad;
-        row[X - kEdge] = row[reflect101(X - kEdge, L.w)];
+__global__ void __launch_bounds__(kBorderThreads) k_border_sides(const __grid_constant__ ExtractParams P) {
+    const Level& L = P.lv[blockIdx.y];
+    const int it = blockIdx.x * kBorderThreads + threadIdx.x;
+    if (it >= 2 * L.h) return;
+    const int frame = P.frame0 + blockIdx.z;
+    const int y = it >> 1;
+    uint8_t* row = level_ptr(P.pyr, L, frame) + (long long)(kEdge + y) * L.pitch;   // 128-byte aligned
+    uint32_t* rw = reinterpret_cast<uint32_t*>(row);
+    if ((it & 1) == 0) {
+        // left: frame byte 32 - k = interior byte 32 + k (k = 1..19); the word at byte a takes bytes 64-a, 63-a, 62-a, 61-a
+        const uint32_t w8 = rw[8], w9 = rw[9], w10 = rw[10], w11 = rw[11], w12 = rw[12], w13 = rw[13];
+        rw[3] = __byte_perm(w12, w13, 0x1234);   // bytes 12..15 (12 is padding)
+        *reinterpret_cast<uint4*>(row + 16) = make_uint4(__byte_perm(w11, w12, 0x1234), __byte_perm(w10, w11, 0x1234),
+                                                         __byte_perm(w9, w10, 0x1234), __byte_perm(w8, w9, 0x1234));
     } else {
-        it -= 2 * kEdge * L.h;
-        const int W = L.w + 2 * kEdge, nwx = (W + 3) >> 2;
-        const int rr = it / nwx, X0 = (it - rr * nwx) * 4;            // rr: 0..18 top rows, 19..37 bottom rows
-        const int Y = rr < kEdge ? rr : L.h + rr;                      // padded row index
-        const int y = reflect101(Y - kEdge, L.h);
-        const uint8_t* srow = img + (long long)(kEdge + y) * L.pitch + kXPad;
-        uint8_t* drow = img + (long long)Y * L.pitch + kXPad - kEdge;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int X = X0 + k;
-            if (X < W) drow[X] = srow[reflect101(X - kEdge, L.w)];
+        // right: frame byte E + j = byte E - 2 - j (j = 0..18), E = 32 + w.  The word at byte a takes bytes s, s-1, s-2, s-3
+        // with s = 2E - 2 - a; in the first word the bytes below E keep their interior values.
+        const int E = kXPad + L.w, a0 = E & ~3, nw = ((E + kEdge - 1) >> 2) - (E >> 2) + 1;
+        const uint32_t keep = (1u << (8 * (E & 3))) - 1u;   // 0 when E is word aligned
+        for (int k = 0; k < nw; ++k) {
+            const int a = a0 + 4 * k, lo = 2 * E - 5 - a;   // source bytes lo .. lo + 3
+            const uint32_t* sw = rw + (lo >> 2);
+            const uint32_t x = __funnelshift_r(sw[0], sw[1], 8 * (lo & 3));
+            uint32_t out = __byte_perm(x, 0u, 0x0123);
+            if (k == 0 && keep) out = (rw[a0 >> 2] & keep) | (out & ~keep);
+            rw[a >> 2] = out;
         }
     }
+}
+
+__global__ void __launch_bounds__(kBorderThreads) k_border_caps(const __grid_constant__ ExtractParams P) {
+    const Level& L = P.lv[blockIdx.y];
+    const int rr = blockIdx.x;                                   // 0..18 rows above, 19..37 rows below
+    const int frame = P.frame0 + blockIdx.z;
+    const int Y = rr < kEdge ? rr : L.h + rr;                    // padded row index
+    const int y = reflect101(Y - kEdge, L.h);
+    uint8_t* img = level_ptr(P.pyr, L, frame);
+    const uint4* srow = reinterpret_cast<const uint4*>(img + (long long)(kEdge + y) * L.pitch);
+    uint4* drow = reinterpret_cast<uint4*>(img + (long long)Y * L.pitch);
+    const int nvec = (kXPad + L.w + kEdge + 15) >> 4;            // through the last frame byte (<= pitch / 16)
+    for (int v = threadIdx.x; v < nvec; v += kBorderThreads) drow[v] = srow[v];
 }
 
 // ------------------------------------------------------------------------------------------------------------
