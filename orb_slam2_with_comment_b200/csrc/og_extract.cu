@@ -300,7 +300,7 @@ __device__ __forceinline__ uint32_t gt_bytes(uint32_t x, uint32_t kadd, bool big
     return big ? (s & x & 0x80808080u) : ((s | x) & 0x80808080u);
 }
 
-__global__ void __launch_bounds__(kSegThreads) k_fast_seg(const __grid_constant__ ExtractParams P, const CUtensorMap* __restrict__ tmaps) {
+__global__ void __launch_bounds__(kSegThreads, 5) k_fast_seg(const __grid_constant__ ExtractParams P, const CUtensorMap* __restrict__ tmaps) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t mbar;
     __shared__ int qn;
