@@ -74,14 +74,12 @@ __global__ void __launch_bounds__(kVocThreads) k_voc_descend(VocView V, const ui
 __device__ __forceinline__ void bitonic_sort_u64(unsigned long long* keys, int P) {
     for (int k = 2; k <= P; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < P; i += kVocThreads) {
-                const int ixj = i ^ j;
-                if (ixj > i) {
-                    const unsigned long long a = keys[i], b = keys[ixj];
-                    if ((a > b) == ((i & k) == 0)) {
-                        keys[i] = b;
-                        keys[ixj] = a;
-                    }
+            for (int h = threadIdx.x; h < (P >> 1); h += kVocThreads) {   // one compare-exchange per thread step
+                const int i = ((h & ~(j - 1)) << 1) | (h & (j - 1)), ixj = i | j;
+                const unsigned long long a = keys[i], b = keys[ixj];
+                if ((a > b) == ((i & k) == 0)) {
+                    keys[i] = b;
+                    keys[ixj] = a;
                 }
             }
             __syncthreads();
