@@ -84,6 +84,16 @@ int orbgpu_extract_batch(orbgpu_extractor* ex, const uint8_t* images, int batch,
                          size_t row_stride, size_t frame_stride, orbgpu_keypoint* kp_out, uint8_t* desc_out,
                          int kp_capacity, int32_t* counts);
 
+/* Colour input: what Tracking::GrabImageMonocular / GrabImageStereo / GrabImageRGBD do before the Frame constructor
+ * (Tracking.cc:173-198, :214-228) fused in front of the extraction — cvtColor(im, mImGray, CV_RGB2GRAY | CV_BGR2GRAY |
+ * CV_RGBA2GRAY | CV_BGRA2GRAY) with OpenCV's 8-bit fixed point (Y = (R*9798 + G*19235 + B*3735 + 2^14) >> 15, bit-exact with
+ * OpenCV 4.13).  `images` holds `channels` (3 or 4) interleaved bytes per pixel, row_stride / frame_stride in bytes;
+ * rgb_order != 0 means channel 0 is red (mbRGB), else blue.  gray_out (may be NULL) receives mImGray, width x height bytes
+ * per frame, packed.  This entry is not pipelined; the throughput path takes gray images. */
+int orbgpu_extract_batch_color(orbgpu_extractor* ex, const uint8_t* images, int batch, int width, int height, int channels,
+                               int rgb_order, size_t row_stride, size_t frame_stride, uint8_t* gray_out, orbgpu_keypoint* kp_out,
+                               uint8_t* desc_out, int kp_capacity, int32_t* counts);
+
 /* Device-resident variant: all pointers are device pointers on the extractor's device, the work is enqueued on
  * the extractor's stream and the call returns without synchronising (orbgpu_extractor_sync waits). */
 int orbgpu_extract_batch_dev(orbgpu_extractor* ex, const uint8_t* images_dev, int batch, int width, int height,

@@ -39,6 +39,7 @@ def lib() -> C.CDLL:
     L.orbgpu_extractor_max_keypoints.argtypes = [vp]
     L.orbgpu_extract.argtypes = [vp, vp, i, i, sz, vp, vp, i, C.POINTER(i)]
     L.orbgpu_extract_batch.argtypes = [vp, vp, i, i, i, sz, sz, vp, vp, i, vp]
+    L.orbgpu_extract_batch_color.argtypes = [vp, vp, i, i, i, i, i, sz, sz, vp, vp, vp, i, vp]
     L.orbgpu_extract_batch_dev.argtypes = [vp, vp, i, i, i, sz, sz, vp, vp, i, vp]
     L.orbgpu_extractor_sync.argtypes = [vp]
     L.orbgpu_extractor_stream.argtypes = [vp, C.POINTER(vp)]

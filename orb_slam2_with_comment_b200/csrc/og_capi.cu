@@ -68,6 +68,8 @@ struct orbgpu_extractor {
     std::vector<og::Cell> cells;
     // device buffers (capacity fixed at creation)
     uint8_t *d_pyr = nullptr, *d_blur = nullptr, *d_images = nullptr, *d_ot = nullptr;
+    uint8_t* d_color = nullptr;     // interleaved colour input of orbgpu_extract_batch_color (allocated on first use)
+    size_t color_cap = 0;
     og::Cell* d_cells = nullptr;
     og::Segment* d_segs = nullptr;
     bool resize_mlp[og::kMaxLevels] = {};   // per level: every band of 8 output rows reads <= kResizeSpan source rows
@@ -667,7 +669,7 @@ int orbgpu_extractor_destroy(orbgpu_extractor* ex) {
     }
     for (int i = 0; i < 6; ++i) if (ex->ev[i]) cudaEventDestroy(ex->ev[i]);
     if (ex->ev_peer) cudaEventDestroy(ex->ev_peer);
-    void* ptrs[] = {ex->d_st_rows, ex->d_st_items, ex->d_st_sad, ex->d_st_u, ex->d_st_d, ex->d_ic_tab, ex->d_btiles, ex->d_segs, ex->d_tmaps, ex->d_pyr, ex->d_blur, ex->d_images, ex->d_cells, ex->d_taps, ex->d_cell_count, ex->d_cand_xy,
+    void* ptrs[] = {ex->d_color, ex->d_st_rows, ex->d_st_items, ex->d_st_sad, ex->d_st_u, ex->d_st_d, ex->d_ic_tab, ex->d_btiles, ex->d_segs, ex->d_tmaps, ex->d_pyr, ex->d_blur, ex->d_images, ex->d_cells, ex->d_taps, ex->d_cell_count, ex->d_cand_xy,
                     ex->d_cand_resp, ex->d_ot, ex->d_sel_xy, ex->d_sel_resp, ex->d_sel_count, ex->d_counts, ex->d_kp, ex->d_desc};
     for (void* p : ptrs) if (p) cudaFree(p);
     delete ex;
@@ -777,6 +779,39 @@ int orbgpu_extract_batch(orbgpu_extractor* ex, const uint8_t* images, int batch,
     ex->last_launches *= nchunks;
     OG_CUDA(cudaStreamSynchronize(ex->s_d2h));
     for (int k = 1; k < n_streams; ++k) OG_CUDA(cudaStreamSynchronize(ex->compute_stream(k)));
+    OG_CUDA(cudaStreamSynchronize(st));
+    return ORBGPU_OK;
+}
+
+int orbgpu_extract_batch_color(orbgpu_extractor* ex, const uint8_t* images, int batch, int width, int height, int channels, int rgb_order,
+                               size_t row_stride, size_t frame_stride, uint8_t* gray_out, orbgpu_keypoint* kp_out, uint8_t* desc_out,
+                               int kp_capacity, int32_t* counts) {
+    if (channels != 3 && channels != 4) return fail(ORBGPU_ERR_ARG, "colour input must have 3 or 4 interleaved channels");
+    int rc = check_call(ex, batch, width, height, row_stride / (size_t)channels, kp_capacity);
+    if (rc) return rc;
+    if (row_stride < (size_t)width * channels) return fail(ORBGPU_ERR_ARG, "row_stride smaller than width * channels");
+    if (!images || !kp_out || !desc_out || !counts) return fail(ORBGPU_ERR_ARG, "null pointer");
+    cudaStream_t st = ex->stream;
+    const size_t in_bytes = (size_t)(batch - 1) * frame_stride + (size_t)(height - 1) * row_stride + (size_t)width * channels;
+    if (in_bytes > ex->color_cap) {
+        if (ex->d_color) cudaFree(ex->d_color);
+        ex->d_color = nullptr;
+        ex->color_cap = 0;
+        OG_CUDA(cudaMalloc((void**)&ex->d_color, in_bytes));
+        ex->color_cap = in_bytes;
+    }
+    OG_CUDA(cudaMemcpyAsync(ex->d_color, images, in_bytes, cudaMemcpyHostToDevice, st));
+    og::k_cvt_gray<<<dim3(((width + 3) / 4 + 255) / 256, height, batch), 256, 0, st>>>(ex->d_color, (long long)row_stride, (long long)frame_stride,
+                                                                                  channels, rgb_order ? 1 : 0, width, height, ex->d_images);
+    const size_t fbytes = (size_t)width * height;
+    if (gray_out) OG_CUDA(cudaMemcpyAsync(gray_out, ex->d_images, fbytes * batch, cudaMemcpyDeviceToHost, st));
+    rc = launch_extract(ex, ex->d_images, batch, width, fbytes, ex->d_kp, ex->d_desc, ex->kp_cap, ex->d_counts);
+    if (rc) return rc;
+    ++ex->last_launches;
+    OG_CUDA(cudaMemcpyAsync(counts, ex->d_counts, (size_t)batch * 4, cudaMemcpyDeviceToHost, st));
+    const size_t kb = (size_t)ex->kp_cap * sizeof(og::KeyPoint), db = (size_t)ex->kp_cap * 32;
+    OG_CUDA(cudaMemcpy2DAsync(kp_out, (size_t)kp_capacity * sizeof(og::KeyPoint), ex->d_kp, kb, kb, batch, cudaMemcpyDeviceToHost, st));
+    OG_CUDA(cudaMemcpy2DAsync(desc_out, (size_t)kp_capacity * 32, ex->d_desc, db, db, batch, cudaMemcpyDeviceToHost, st));
     OG_CUDA(cudaStreamSynchronize(st));
     return ORBGPU_OK;
 }

@@ -53,6 +53,32 @@ __global__ void __launch_bounds__(256) k_level0(const __grid_constant__ ExtractP
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// cvtColor(im, mImGray, CV_RGB2GRAY / CV_BGR2GRAY / CV_RGBA2GRAY / CV_BGRA2GRAY) of Tracking::GrabImage* (Tracking.cc:173-198,
+// :214-228): OpenCV's 8-bit fixed point, Y = (R*9798 + G*19235 + B*3735 + 2^14) >> 15 (pinned to cv2 4.13 by
+// tests/golden/cvtcolor_golden.npz).  One thread converts 4 pixels into one aligned word of the packed gray image.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_cvt_gray(const uint8_t* __restrict__ src, long long row_stride, long long frame_stride, int channels,
+                                                  int r_first, int width, int height, uint8_t* __restrict__ gray) {
+    const int frame = blockIdx.z, y = blockIdx.y;
+    const int x = (blockIdx.x * 256 + threadIdx.x) * 4;
+    if (x >= width) return;
+    const uint8_t* s = src + (long long)frame * frame_stride + (long long)y * row_stride + (long long)x * channels;
+    uint8_t* d = gray + ((long long)frame * height + y) * width + x;
+    const int cr = r_first ? 9798 : 3735, cb = r_first ? 3735 : 9798;   // weight of channel 0 / channel 2
+    uint32_t out = 0;
+    const int n = min(4, width - x);
+    for (int k = 0; k < n; ++k) {
+        const int c0 = __ldg(s + k * channels), c1 = __ldg(s + k * channels + 1), c2 = __ldg(s + k * channels + 2);
+        out |= (uint32_t)((c0 * cr + c1 * 19235 + c2 * cb + (1 << 14)) >> 15) << (8 * k);
+    }
+    if (n == 4 && ((width & 3) == 0)) {
+        *reinterpret_cast<uint32_t*>(d) = out;   // rows of a packed image whose width is a multiple of 4 stay word aligned
+    } else {
+        for (int k = 0; k < n; ++k) d[k] = (uint8_t)(out >> (8 * k));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // Level l from level l-1 (chained, :1120) including the border of the new level (:1122-1123): a border pixel is
 // the resize output at its reflected interior coordinate, so one pass writes the whole padded row.
 // ------------------------------------------------------------------------------------------------------------

@@ -77,6 +77,19 @@ class ORBextractor:
                                                   desc.ctypes.data, self.kp_cap, cnt.ctypes.data))
         return kp, desc, cnt
 
+    def extract_batch_color(self, images: np.ndarray, rgb: bool = True):
+        """images: (B, H, W, 3 or 4) uint8 — Tracking::GrabImage*'s cvtColor fused in front of the extraction.
+        Returns (gray (B,H,W), kp, desc, counts)."""
+        assert images.dtype == np.uint8 and images.ndim == 4 and images.shape[3] in (3, 4) and images.flags.c_contiguous
+        B, H, W, Cn = images.shape
+        gray = np.zeros((B, H, W), np.uint8)
+        kp = np.zeros((B, self.kp_cap), KP_DTYPE)
+        desc = np.zeros((B, self.kp_cap, 32), np.uint8)
+        cnt = np.zeros(B, np.int32)
+        capi.check(self._lib.orbgpu_extract_batch_color(self._h, images.ctypes.data, B, W, H, Cn, int(rgb), W * Cn, W * H * Cn, gray.ctypes.data,
+                                                        kp.ctypes.data, desc.ctypes.data, self.kp_cap, cnt.ctypes.data))
+        return gray, kp, desc, cnt
+
     def extract_batch_dev(self, images_ptr: int, B: int, W: int, H: int, kp_ptr: int, desc_ptr: int, counts_ptr: int):
         """Device-resident variant: raw device pointers (e.g. torch tensors' data_ptr()); asynchronous."""
         capi.check(self._lib.orbgpu_extract_batch_dev(self._h, images_ptr, B, W, H, W, W * H, kp_ptr, desc_ptr, self.kp_cap,

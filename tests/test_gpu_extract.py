@@ -226,3 +226,27 @@ def test_other_geometries_vs_oracle(oracle, w, h, nf, nlevels, scale, ini, mn):
         compare_final(kp, desc, ekp, edesc, f"{w}x{h} seed {seed}")
         assert len(kp) > nf // 2
     g.close()
+
+
+def test_colour_input_matches_cv2_golden_and_gray_path():
+    """orbgpu_extract_batch_color: the gray image equals cv2's cvtColor (golden vectors), and the extraction equals the
+    extraction of that gray image (Tracking::GrabImageMonocular, Tracking.cc:214-228)."""
+    import os
+    from orb_slam2_with_comment_b200 import ORBextractor
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "cvtcolor_golden.npz"))
+    ex = ORBextractor(300, 1.2, 4, 20, 7, max_width=203, max_height=120, max_batch=2)
+    for name in ("c3", "c4"):
+        for rgb in (True, False):
+            gray, *_ = ex.extract_batch_color(np.ascontiguousarray(g[name]), rgb=rgb)
+            assert np.array_equal(gray, g[name + ("_rgb" if rgb else "_bgr")]), (name, rgb)
+    ex.close()
+    # a real-sized colour frame: tint the synthetic gray scene, convert + extract in one call, compare with the gray path
+    W, H = 640, 480
+    base = synth.g_rects(W, H, 5).astype(np.int32)
+    rs = np.random.RandomState(1)
+    col = np.clip(np.stack([base + rs.randint(-20, 20, base.shape), base, base + rs.randint(-30, 30, base.shape)], -1), 0, 255).astype(np.uint8)
+    ex = ORBextractor(1000, 1.2, 8, 20, 7, max_width=W, max_height=H, max_batch=1)
+    gray, kp, desc, cnt = ex.extract_batch_color(col[None].copy(), rgb=True)
+    kp2, desc2 = ex(gray[0])
+    assert cnt[0] == len(kp2) > 500 and kp[0, :cnt[0]].tobytes() == kp2.tobytes() and np.array_equal(desc[0, :cnt[0]], desc2)
+    ex.close()
