@@ -337,6 +337,16 @@ int orbgpu_search_window_best(orbgpu_matcher* m, const orbgpu_frame_set* frames,
                               const float* inv_level_sigma2, int n_levels, int skip_flagged, int32_t* q_best_idx,
                               int32_t* q_best_dist);
 
+/* ORBmatcher::SearchForInitialization(Frame& F1, Frame& F2, vbPrevMatched, vnMatches12, windowSize) (ORBmatcher.cc:493-632),
+ * the monocular bootstrap search, for a batch of frame pairs.  frames2 = the F2 of every pair (with grid); queries1 = the key
+ * points of the matching F1 as window queries: u / v = vbPrevMatched[i1], radius = windowSize, min_level = max_level = 0,
+ * flags bit 0 = (octave == 0) (:512-514), desc / angle = F1's descriptor row / key-point angle.  match12[q] = vnMatches12
+ * (index in F2 or -1) after the distance test (<= TH_LOW), the ratio test (bestDist < bestDist2 * nnratio), the stealing rule
+ * (a better match takes a key point from its earlier owner, :546, :573-583) and the rotation histogram; nmatches per pair.
+ * The caller updates vbPrevMatched from match12 (:626-628). */
+int orbgpu_search_for_initialization(orbgpu_matcher* m, const orbgpu_frame_set* frames2, const orbgpu_window_query_set* queries1,
+                                     float nnratio, int check_orientation, int32_t* match12, int32_t* nmatches);
+
 /* MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:247-316) for a batch of map points: point p owns the descriptors
  * [obs_off[p], obs_off[p+1]) of `desc` (the rows of its observing, non-bad key frames in the reference's iteration order,
  * 32 bytes each, at most 256 per point).  best_idx[p] = the row (relative to obs_off[p]) with the least median Hamming

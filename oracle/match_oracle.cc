@@ -516,3 +516,58 @@ extern "C" void orbm_search_window_best(const orbgpu_frame_set* fs, const orbgpu
         }
     }
 }
+
+// ORBmatcher::SearchForInitialization, ORBmatcher.cc:493-632 (queries = key points of F1, frames = F2)
+extern "C" void orbm_search_for_initialization(const orbgpu_frame_set* fs, const orbgpu_window_query_set* qs, float nnratio, int check_orientation,
+                                               int32_t* match12, int32_t* nmatches_out) {
+    for (int f = 0; f < fs->n_frames; ++f) {
+        const int k0 = fs->kp_off[f], n = fs->kp_off[f + 1] - k0;
+        const orbgpu_keypoint* keys = fs->keys_un + k0;
+        const float* g = fs->grid + 4 * f;
+        Grid G;
+        assign_grid(keys, n, g, G);
+        const int q0 = qs->q_off[f], nq = qs->q_off[f + 1] - q0;
+        int nmatches = 0;
+        std::vector<int> vnMatches12(nq, -1), vMatchedDistance(n, INT_MAX), vnMatches21(n, -1);
+        std::vector<int> rotHist[HISTO_LENGTH];
+        std::vector<int> vIndices2;
+        for (int i1 = 0; i1 < nq; ++i1) {
+            const int q = q0 + i1;
+            if (!(qs->flags[q] & 1)) continue;   // level1 > 0
+            features_in_area(G, keys, g, qs->u[q], qs->v[q], qs->radius[q], qs->min_level[q], qs->max_level[q], vIndices2);
+            if (vIndices2.empty()) continue;
+            const uint8_t* d1 = qs->desc + (size_t)q * 32;
+            int bestDist = INT_MAX, bestDist2 = INT_MAX, bestIdx2 = -1;
+            for (size_t j = 0; j < vIndices2.size(); ++j) {
+                const int i2 = vIndices2[j];
+                const int dist = descriptor_distance(d1, fs->desc + (size_t)(k0 + i2) * 32);
+                if (vMatchedDistance[i2] <= dist) continue;
+                if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx2 = i2; }
+                else if (dist < bestDist2) bestDist2 = dist;
+            }
+            if (bestDist <= TH_LOW) {
+                if (bestDist < (float)bestDist2 * nnratio) {
+                    if (vnMatches21[bestIdx2] >= 0) { vnMatches12[vnMatches21[bestIdx2]] = -1; nmatches--; }
+                    vnMatches12[i1] = bestIdx2;
+                    vnMatches21[bestIdx2] = i1;
+                    vMatchedDistance[bestIdx2] = bestDist;
+                    nmatches++;
+                    if (check_orientation) rotHist[rot_bin(qs->angle[q], keys[bestIdx2].angle)].push_back(i1);
+                }
+            }
+        }
+        if (check_orientation) {
+            int ind1 = -1, ind2 = -1, ind3 = -1;
+            three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+            for (int i = 0; i < HISTO_LENGTH; i++) {
+                if (i == ind1 || i == ind2 || i == ind3) continue;
+                for (size_t j = 0; j < rotHist[i].size(); j++) {
+                    const int idx1 = rotHist[i][j];
+                    if (vnMatches12[idx1] >= 0) { vnMatches12[idx1] = -1; nmatches--; }
+                }
+            }
+        }
+        for (int i1 = 0; i1 < nq; ++i1) match12[q0 + i1] = vnMatches12[i1];
+        if (nmatches_out) nmatches_out[f] = nmatches;
+    }
+}

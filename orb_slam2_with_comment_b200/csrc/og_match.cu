@@ -660,7 +660,7 @@ __device__ __forceinline__ SbpQuery sbp_query(const SbpArgs& A, int q, int f) {
 // One warp enumerates the window's candidates in the reference's order (ix outer, iy inner, ascending index in a
 // cell) and keeps the K smallest (dist, position).  `blocked` = bitmask of keypoints taken during phase B.
 __device__ __forceinline__ int sbp_scan_warp(const SbpArgs& A, const SbpQuery& Q, const Desc& dq, const uint32_t* blocked,
-                                             uint32_t (&out)[kTopK], int32_t (&outi)[kTopK]) {
+                                             uint32_t (&out)[kTopK], int32_t (&outi)[kTopK], const uint16_t* mdist = nullptr) {
     const int lane = threadIdx.x & 31;
     uint32_t t[kTopK];
     int32_t v[kTopK];
@@ -717,8 +717,10 @@ __device__ __forceinline__ int sbp_scan_warp(const SbpArgs& A, const SbpQuery& Q
                 const float er = fabsf(__fsub_rn(Q.xr, A.F.u_right[Q.k0 + idx]));
                 if (er > Q.rs) continue;
             }
-            const uint32_t key = ((uint32_t)hamming256(dq, load_desc(A.F.desc, Q.k0 + idx)) << kPosBits) | (uint32_t)(pos0 + j);
+            const uint32_t dist = (uint32_t)hamming256(dq, load_desc(A.F.desc, Q.k0 + idx));
             ++evals;
+            if (mdist && (uint32_t)mdist[idx] <= dist) continue;   // SearchForInitialization: vMatchedDistance[i2] <= dist (:546)
+            const uint32_t key = (dist << kPosBits) | (uint32_t)(pos0 + j);
             if (key < t[kTopK - 1]) topk_insert2(t, v, key, idx);
         }
     }
@@ -943,6 +945,104 @@ __global__ void __launch_bounds__(32) k_win_select(const __grid_constant__ SbpAr
     }
     if (lane == 0) {
         if (A.nmatches) A.nmatches[f] = nacc - removed;
+        if (evals) atomicAdd(A.evals, (unsigned long long)evals);
+    }
+}
+
+// Phase B of SearchForInitialization (ORBmatcher.cc:493-632), one warp per frame pair, queries (key points of frame 1) in
+// index order.  The dynamic state is not a taken mask but vMatchedDistance: a candidate is skipped when it already holds a
+// match of the same or a smaller distance (:546) — for the best AND the second best; a better match steals the key point
+// from its earlier owner (:573-583).  rotHist keeps the stolen entries (:592-603), so the bin counts do too.
+// Shared: mdist[n2] (u16, 0xFFFF = INT_MAX) | owner[n2] (i32) | hist[32].
+__global__ void __launch_bounds__(32) k_init_select(const __grid_constant__ SbpArgs A, int32_t* __restrict__ match12) {
+    extern __shared__ uint32_t smem_i[];
+    const int lane = threadIdx.x, f = blockIdx.x;
+    const int k0 = A.F.kp_off[f], n = A.F.kp_off[f + 1] - k0;
+    int* owner = reinterpret_cast<int*>(smem_i);
+    int* hist = owner + A.blocked_words * 32;
+    uint16_t* mdist = reinterpret_cast<uint16_t*>(hist + 32);
+    for (int i = lane; i < n; i += 32) { owner[i] = -1; mdist[i] = 0xFFFFu; }
+    hist[lane] = 0;
+    const int q0 = A.W.q_off[f], q1 = A.W.q_off[f + 1];
+    for (int q = q0 + lane; q < q1; q += 32) { match12[q] = -1; A.q_bin[q] = -1; }
+    __syncwarp();
+    int nmatches = 0, evals = 0;
+    for (int base = q0; base < q1; base += 32) {
+        const int q = base + lane;
+        uint32_t k[kTopK] = {kEmptyKey, kEmptyKey, kEmptyKey, kEmptyKey};
+        int ci[kTopK] = {-1, -1, -1, -1};
+        if (q < q1) {
+            const uint4 v = *reinterpret_cast<const uint4*>(A.topk_key + (long long)q * kTopK);
+            const int4 vi = *reinterpret_cast<const int4*>(A.topk_idx + (long long)q * kTopK);
+            k[0] = v.x; k[1] = v.y; k[2] = v.z; k[3] = v.w;
+            ci[0] = vi.x; ci[1] = vi.y; ci[2] = vi.z; ci[3] = vi.w;
+        }
+        const int cnt_chunk = min(32, q1 - base);
+        for (int l = 0; l < cnt_chunk; ++l) {
+            uint32_t kk[kTopK];
+            int cc[kTopK];
+#pragma unroll
+            for (int j = 0; j < kTopK; ++j) {
+                kk[j] = __shfl_sync(0xffffffffu, k[j], l);
+                cc[j] = __shfl_sync(0xffffffffu, ci[j], l);
+            }
+            const int qq = base + l;
+            int cnt = 0, bestIdx = -1, d1 = 0x7fffffff, d2 = 0x7fffffff;
+            bool complete = false;
+#pragma unroll
+            for (int j = 0; j < kTopK; ++j) {
+                if (cnt == 2 || complete) break;
+                if (kk[j] == kEmptyKey) { complete = true; break; }
+                const int idx = cc[j], dist = (int)(kk[j] >> kPosBits);
+                if ((int)mdist[idx] <= dist) continue;
+                if (cnt == 0) { bestIdx = idx; d1 = dist; cnt = 1; }
+                else { d2 = dist; cnt = 2; }
+            }
+            if (cnt == 2) complete = true;
+            if (!complete) {   // truncated list ran dry: exact rescan under the current vMatchedDistance
+                const SbpQuery Q = sbp_query(A, qq, f);
+                uint32_t out[kTopK];
+                int32_t outi[kTopK];
+                evals += sbp_scan_warp(A, Q, load_desc(A.W.desc, qq), nullptr, out, outi, mdist);
+                bestIdx = -1; d1 = 0x7fffffff; d2 = 0x7fffffff;
+                if (out[0] != kEmptyKey) { bestIdx = outi[0]; d1 = (int)(out[0] >> kPosBits); }
+                if (out[1] != kEmptyKey) d2 = (int)(out[1] >> kPosBits);
+            }
+            // bestDist <= TH_LOW && bestDist < (float)bestDist2 * mfNNratio (:561-563)
+            const bool accept = bestIdx >= 0 && d1 <= A.th_dist && (float)d1 < __fmul_rn((float)d2, A.nnratio);
+            if (accept) {
+                const int prev = owner[bestIdx];
+                int bin = 0;
+                if (A.check_orientation) bin = rot_bin(A.W.angle[qq], A.F.keys[k0 + bestIdx].angle);
+                if (lane == 0) {
+                    if (prev >= 0) match12[q0 + prev] = -1;            // the earlier owner loses the key point (:573-577)
+                    match12[qq] = bestIdx;
+                    owner[bestIdx] = qq - q0;
+                    mdist[bestIdx] = (uint16_t)d1;
+                    if (A.check_orientation) { A.q_bin[qq] = (int8_t)bin; hist[bin] += 1; }
+                }
+                nmatches += prev >= 0 ? 0 : 1;
+            }
+            __syncwarp();
+        }
+    }
+    __syncwarp();
+    int removed = 0;
+    if (A.check_orientation) {
+        int ind1, ind2, ind3;
+        three_maxima(hist, kHisto, ind1, ind2, ind3);
+        for (int q = q0 + lane; q < q1; q += 32) {
+            const int bin = A.q_bin[q];
+            if (bin >= 0 && bin != ind1 && bin != ind2 && bin != ind3 && match12[q] >= 0) {   // stolen entries are already -1 (:617-621)
+                match12[q] = -1;
+                ++removed;
+            }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) removed += __shfl_xor_sync(0xffffffffu, removed, d);
+    }
+    if (lane == 0) {
+        if (A.nmatches) A.nmatches[f] = nmatches - removed;
         if (evals) atomicAdd(A.evals, (unsigned long long)evals);
     }
 }
@@ -1367,7 +1467,7 @@ int sbp_dev(orbgpu_matcher* m, const orbgpu_frame_set_dev* fs, const orbgpu_mapp
 // Generic windowed search (host pointers): the query arrays are uploaded into pooled scratch, the frame set likewise.
 int win_host(orbgpu_matcher* m, const orbgpu_frame_set* frames, const orbgpu_window_query_set* qs, int th_dist, int skip_any,
              int check_orientation, int32_t* kp_match, int32_t* q_best_idx, int32_t* q_best_dist, int32_t* nmatches, bool best_only = false,
-             const float* inv_sigma2 = nullptr, int n_levels = 0) {
+             const float* inv_sigma2 = nullptr, int n_levels = 0, bool init_mode = false, float nnratio = 0.f, int32_t* match12 = nullptr) {
     using namespace og;
     m->last_launches = 0;
     if (!frames || !qs || !qs->q_off) return og_fail(ORBGPU_ERR_ARG, "null argument");
@@ -1395,7 +1495,8 @@ int win_host(orbgpu_matcher* m, const orbgpu_frame_set* frames, const orbgpu_win
     if (!rc) rc = upload_array(qs->flags, (size_t)nq, owned, &A.W.flags, st, m);
     if (!rc) rc = upload_array(qs->desc, (size_t)nq * 32, owned, &A.W.desc, st, m);
     if (!rc && inv_sigma2) rc = upload_array(inv_sigma2, (size_t)n_levels, owned, &A.inv_sigma2, st, m);
-    A.no_xr_window = best_only ? 1 : 0;
+    A.no_xr_window = (best_only || init_mode) ? 1 : 0;
+    A.nnratio = nnratio;
     void* d[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     void* ptr = nullptr;
     cudaError_t ce = cudaSuccess;
@@ -1414,7 +1515,7 @@ int win_host(orbgpu_matcher* m, const orbgpu_frame_set* frames, const orbgpu_win
     }
     if (!rc) {
         A.F = F.v;
-        if (best_only && !skip_any) A.F.flags = nullptr;   // Fuse looks at every candidate, whatever MapPoint it holds
+        if ((best_only && !skip_any) || init_mode) A.F.flags = nullptr;   // Fuse / SearchForInitialization look at every candidate
         A.n_frames = nf;
         A.generic = 1;
         A.skip_any = skip_any;
@@ -1436,6 +1537,14 @@ int win_host(orbgpu_matcher* m, const orbgpu_frame_set* frames, const orbgpu_win
             if (nq > 0) k_sbp_topk<<<(nq + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock * 32, 0, st>>>(A, nq);
             if (best_only) {
                 if (nq > 0) k_win_best<<<(nq + 255) / 256, 256, 0, st>>>(A, nq);
+            } else if (init_mode) {
+                // per key point of frame 2: owner (4 B) + matched distance (2 B); A.mp_best_idx doubles as the match12 output
+                const size_t smem_i = (size_t)A.blocked_words * 32 * 4 + 32 * 4 + (size_t)A.blocked_words * 32 * 2;
+                if (smem_i > 200 * 1024) rc = og_fail(ORBGPU_ERR_CAPACITY, "frame too large for the shared-memory match state");
+                else {
+                    if (smem_i > 48 * 1024) cudaFuncSetAttribute(k_init_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_i);
+                    k_init_select<<<nf, 32, smem_i, st>>>(A, A.mp_best_idx);
+                }
             } else {
                 if (smem > 48 * 1024) cudaFuncSetAttribute(k_win_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 k_win_select<<<nf, 32, smem, st>>>(A);
@@ -1453,7 +1562,7 @@ int win_host(orbgpu_matcher* m, const orbgpu_frame_set* frames, const orbgpu_win
         }
     };
     get(kp_match, d[0], (size_t)F.nkp * 4);
-    get(q_best_idx, d[1], (size_t)nq * 4);
+    get(init_mode ? match12 : q_best_idx, d[1], (size_t)nq * 4);
     get(q_best_dist, d[2], (size_t)nq * 4);
     get(nmatches, d[4], (size_t)nf * 4);
     cudaError_t se = cudaStreamSynchronize(st);
@@ -2206,4 +2315,14 @@ extern "C" int orbgpu_search_window_best(orbgpu_matcher* m, const orbgpu_frame_s
     if (inv_level_sigma2 && n_levels < 1) return og_fail(ORBGPU_ERR_ARG, "search_window_best: n_levels");
     if (inv_level_sigma2 && queries && !queries->ur) return og_fail(ORBGPU_ERR_ARG, "search_window_best: the chi-square gate needs the queries' ur");
     return win_host(m, frames, queries, 256, skip_flagged, 0, nullptr, q_best_idx, q_best_dist, nullptr, true, inv_level_sigma2, n_levels);
+}
+
+// ORBmatcher::SearchForInitialization (ORBmatcher.cc:493-632): see include/orbgpu.h
+extern "C" int orbgpu_search_for_initialization(orbgpu_matcher* m, const orbgpu_frame_set* frames2, const orbgpu_window_query_set* queries1,
+                                                float nnratio, int check_orientation, int32_t* match12, int32_t* nmatches) {
+    int rc = check_matcher(m);
+    if (rc) return rc;
+    if (!match12) return og_fail(ORBGPU_ERR_ARG, "search_for_initialization: null match12");
+    return win_host(m, frames2, queries1, ORBGPU_TH_LOW, 0, check_orientation, nullptr, nullptr, nullptr, nmatches, false, nullptr, 0, true, nnratio,
+                    match12);
 }

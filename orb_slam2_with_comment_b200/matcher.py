@@ -138,6 +138,7 @@ def _bind(L):
     L.orbgpu_search_for_triangulation_dev.argtypes = [vp, vp, vp, i, vp, vp, vp, vp, vp, vp, i, i, i, vp, vp, vp, vp]
     L.orbgpu_search_by_bow.argtypes = [vp, C.POINTER(CFrameSet), C.POINTER(CFrameSet), i, vp, vp, f, i, i, i, i, vp, vp, vp, vp]
     L.orbgpu_search_by_bow_dev.argtypes = [vp, vp, vp, i, vp, vp, f, i, i, i, i, vp, vp, vp, vp]
+    L.orbgpu_search_for_initialization.argtypes = [vp, C.POINTER(CFrameSet), C.POINTER(CWindowQuerySet), f, i, vp, vp]
     L.orbgpu_search_window_best.argtypes = [vp, C.POINTER(CFrameSet), C.POINTER(CWindowQuerySet), vp, i, i, vp, vp]
     L.orbgpu_distinctive_descriptors.argtypes = [vp, i, vp, vp, vp, vp]
     L.orbgpu_is_in_frustum.argtypes = [vp, i, vp, f, i, f] + [vp] * 12
@@ -268,6 +269,14 @@ class ORBmatcher:
                                                   mp_off.ctypes.data, *[a.ctypes.data for a in ins], *[out[k].ctypes.data for k in
                                                   ("in_view", "proj_x", "proj_y", "proj_xr", "level", "view_cos")]))
         return out
+
+    def SearchForInitialization(self, frames2: FrameSet, queries1: "WindowQuerySet"):
+        """ORBmatcher::SearchForInitialization for a batch of (F1, F2) pairs: vnMatches12 and the match count per pair."""
+        nq = int(queries1.q_off[-1])
+        m12, nm = np.zeros(nq, np.int32), np.zeros(frames2.n_frames, np.int32)
+        capi.check(self._lib.orbgpu_search_for_initialization(self._h, C.byref(frames2.c), C.byref(queries1.c), self.mfNNratio,
+                                                              int(self.mbCheckOrientation), m12.ctypes.data, nm.ctypes.data))
+        return {"match12": m12, "nmatches": nm}
 
     def SearchWindowBest(self, frames: FrameSet, queries: "WindowQuerySet", inv_level_sigma2=None, skip_flagged: bool = False):
         """The candidate loops of Fuse / SearchBySim3: independent queries, best candidate only (orbgpu_search_window_best)."""

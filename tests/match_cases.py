@@ -209,3 +209,29 @@ def distinctive_case(seed, n_points=3000, n_max=60):
             d[n // 2] = d[0]
         desc[off[p]:off[p + 1]] = d
     return off, desc
+
+
+def init_case(seed, n_frames=3, n_lo=800, n_hi=1600, window=100.0, p_flip=0.08):
+    """SearchForInitialization: F2 = frame f+1, F1 = frame f; vbPrevMatched = F1's own key-point positions (as at the first call,
+    Tracking.cc:612-614), windowSize 100, only level-0 key points of F1 are live.  Heavy contention: repeated descriptors make
+    several F1 points want the same F2 point, so the stealing rule fires."""
+    from orb_slam2_with_comment_b200.matcher import WindowQuerySet
+    rs, kp_off, keys, desc = _frames(seed, n_frames + 1, n_lo, n_hi, p_flip=p_flip, frac_rel=0.7)
+    ko = kp_off[1:] - kp_off[1]
+    sel = slice(kp_off[1], kp_off[-1])
+    fkeys, fdesc = keys[sel].copy(), desc[sel].copy()
+    grid = np.tile(synth.frame_grid(W, H), (n_frames, 1))
+    fs2 = FrameSet(ko.astype(np.int32), fkeys, fdesc, grid=grid)
+    q_off, parts = [0], []
+    for f in range(n_frames):
+        k1, d1 = keys[kp_off[f]:kp_off[f + 1]], desc[kp_off[f]:kp_off[f + 1]].copy()
+        n1 = len(k1)
+        dup = rs.permutation(n1)[:n1 // 6]                      # near-duplicates of other F1 descriptors: rivals for one F2 point
+        d1[dup] = synth.flip_bits(d1[rs.randint(0, n1, len(dup))], rs, 0.01)
+        parts.append({"u": k1["x"].astype(np.float32), "v": k1["y"].astype(np.float32), "radius": np.full(n1, window, np.float32),
+                      "lo": np.zeros(n1, np.int32), "hi": np.zeros(n1, np.int32), "flags": (k1["octave"] == 0).astype(np.uint8),
+                      "desc": d1, "angle": k1["angle"].astype(np.float32)})
+        q_off.append(q_off[-1] + n1)
+    cat = {k2: np.concatenate([p[k2] for p in parts]) for k2 in parts[0]}
+    qs = WindowQuerySet(np.array(q_off, np.int32), cat["u"], cat["v"], cat["radius"], cat["lo"], cat["hi"], cat["flags"], cat["desc"], angle=cat["angle"])
+    return fs2, qs

@@ -224,6 +224,13 @@ class MatcherOracle:
                                       kp_match.ctypes.data, bi.ctypes.data, bd.ctypes.data, nm.ctypes.data)
         return {"nmatches": nm, "kp_match": kp_match, "q_best_idx": bi, "q_best_dist": bd}
 
+    def SearchForInitialization(self, frames2, queries1):
+        m12, nm = np.full(queries1.n, -1, np.int32), np.zeros(frames2.n_frames, np.int32)
+        self.lib.orbm_search_for_initialization.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p, C.c_void_p]
+        self.lib.orbm_search_for_initialization(C.byref(frames2.c), C.byref(queries1.c), self.mfNNratio, int(self.mbCheckOrientation),
+                                                m12.ctypes.data, nm.ctypes.data)
+        return {"match12": m12, "nmatches": nm}
+
     def SearchWindowBest(self, frames, queries, inv_level_sigma2=None, skip_flagged=False):
         bi, bd = np.full(queries.n, -1, np.int32), np.full(queries.n, 256, np.int32)
         s2 = None if inv_level_sigma2 is None else np.ascontiguousarray(inv_level_sigma2, np.float32)

@@ -297,3 +297,14 @@ def test_window_best_vs_oracle(gm, mo, stereo, gate, skip):
         if gate:   # the gate must reject some candidates a plain search accepts
             plain = mo(0.9, False).SearchWindowBest(fs, q2, None, skip)
             assert (plain["q_best_idx"] != exp["q_best_idx"]).sum() > 50
+
+
+@pytest.mark.parametrize("ratio,ori", [(0.9, True), (0.9, False), (0.6, True)])
+def test_search_for_initialization_vs_oracle(gm, mo, ratio, ori):
+    """ORBmatcher::SearchForInitialization (ORBmatcher.cc:493-632) incl. the stealing rule and the stale histogram entries."""
+    for seed in (901, 902):
+        fs2, qs = mc.init_case(seed)
+        got = gm(ratio, ori).SearchForInitialization(fs2, qs)
+        exp = mo(ratio, ori).SearchForInitialization(fs2, qs)
+        same(got, exp, ("nmatches", "match12"), f"init seed {seed}")
+        assert exp["nmatches"].sum() > 150
