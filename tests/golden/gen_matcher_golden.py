@@ -9,6 +9,10 @@ separately, in plain Python, straight from the reference source:
     py_search_by_bow          ORBmatcher.cc:211-344 (kf_frame=True) / :635-768
     py_search_for_triangulation  ORBmatcher.cc:173-196, :783-975
     py_three_maxima           ORBmatcher.cc:1854-1895
+    py_search_window_best     the candidate loops of Fuse (ORBmatcher.cc:1051-1112, :1211-1246) and SearchBySim3 (:1363-1401)
+    py_search_for_initialization  ORBmatcher.cc:493-632
+    py_distinctive_descriptors    MapPoint.cc:247-316
+    py_is_in_frustum          Frame.cc:274-342 + MapPoint.cc:421-436 (cv::Mat algebra as cv2 4.13 evaluates it)
 
 FeatureVectors are Python dicts (std::map<NodeId, vector<unsigned>>), the grid is a dict of lists, float arithmetic
 uses numpy.float32 scalars so every product/sum rounds like the C++ float expressions.
@@ -332,6 +336,173 @@ def py_search_windowed(fs, qs, th_dist, skip_any, check_ori):
     return np.array(nm_out, np.int32), kp_match, bi, bd
 
 
+def _frame_grid(fs, f):
+    """Frame::AssignFeaturesToGrid (Frame.cc:232-247): dict (cell x, cell y) -> key-point indices in ascending order."""
+    COLS, ROWS = 64, 48
+    K, D, FL, UR = frame_view(fs, f)
+    minx, miny, iw, ih = [f32(v) for v in fs.grid[f]]
+    grid = {}
+    for i in range(len(K)):
+        px = c_round(float((f32(K[i]["x"]) - minx) * iw))
+        py = c_round(float((f32(K[i]["y"]) - miny) * ih))
+        if 0 <= px < COLS and 0 <= py < ROWS:
+            grid.setdefault((px, py), []).append(i)
+    return K, D, FL, UR, (minx, miny, iw, ih), grid
+
+
+def _features_in_area(K, g, grid, x, y, r, lo, hi):
+    """GetFeaturesInArea (Frame.cc:353-410 / KeyFrame.cc:583-622) in its own order: cell columns, cell rows, index."""
+    COLS, ROWS = 64, 48
+    minx, miny, iw, ih = g
+    cx0 = max(0, int(math.floor(float((x - minx - r) * iw))))
+    cx1 = min(COLS - 1, int(math.ceil(float((x - minx + r) * iw))))
+    cy0 = max(0, int(math.floor(float((y - miny - r) * ih))))
+    cy1 = min(ROWS - 1, int(math.ceil(float((y - miny + r) * ih))))
+    if cx0 >= COLS or cx1 < 0 or cy0 >= ROWS or cy1 < 0:
+        return
+    check_levels = lo > 0 or hi >= 0
+    for ix in range(cx0, cx1 + 1):
+        for iy in range(cy0, cy1 + 1):
+            for i in grid.get((ix, iy), []):
+                o = int(K[i]["octave"])
+                if check_levels and (o < lo or (hi >= 0 and o > hi)):
+                    continue
+                if abs(f32(K[i]["x"]) - x) < r and abs(f32(K[i]["y"]) - y) < r:
+                    yield i
+
+
+def py_search_window_best(fs, qs, inv_s2, skip_flagged):
+    bi, bd = np.full(qs.n, -1, np.int32), np.full(qs.n, 256, np.int32)
+    for f in range(fs.n_frames):
+        K, D, FL, UR, g, grid = _frame_grid(fs, f)
+        for q in range(int(qs.q_off[f]), int(qs.q_off[f + 1])):
+            if not (int(qs.flags[q]) & 1):
+                continue
+            u, v = f32(qs.u[q]), f32(qs.v[q])
+            best, besti = 256, -1
+            for i in _features_in_area(K, g, grid, u, v, f32(qs.radius[q]), int(qs.min_level[q]), int(qs.max_level[q])):
+                if skip_flagged and FL is not None and int(FL[i]) != 0:
+                    continue
+                if inv_s2 is not None:
+                    ex, ey = u - f32(K[i]["x"]), v - f32(K[i]["y"])
+                    kur = f32(UR[i]) if UR is not None else f32(-1)
+                    if kur >= 0:
+                        er = f32(qs.ur[q]) - kur
+                        e2 = f32(f32(f32(ex * ex) + f32(ey * ey)) + f32(er * er))
+                        if float(f32(e2 * f32(inv_s2[int(K[i]["octave"])]))) > 7.8:
+                            continue
+                    else:
+                        e2 = f32(f32(ex * ex) + f32(ey * ey))
+                        if float(f32(e2 * f32(inv_s2[int(K[i]["octave"])]))) > 5.99:
+                            continue
+                d = popcount_distance(qs.desc[q], D[i])
+                if d < best:
+                    best, besti = d, i
+            bi[q], bd[q] = besti, best
+    return bi, bd
+
+
+def py_search_for_initialization(fs2, qs, nnratio, check_ori):
+    INT_MAX = 2 ** 31 - 1
+    m12_all = np.full(qs.n, -1, np.int32)
+    nm_out = []
+    for f in range(fs2.n_frames):
+        K, D, FL, UR, g, grid = _frame_grid(fs2, f)
+        q0, q1 = int(qs.q_off[f]), int(qs.q_off[f + 1])
+        m12 = [-1] * (q1 - q0)
+        mdist, m21 = [INT_MAX] * len(K), [-1] * len(K)
+        hist = [[] for _ in range(HISTO_LENGTH)]
+        n = 0
+        for i1 in range(q1 - q0):
+            q = q0 + i1
+            if not (int(qs.flags[q]) & 1):
+                continue
+            best, best2, besti = INT_MAX, INT_MAX, -1
+            for i2 in _features_in_area(K, g, grid, f32(qs.u[q]), f32(qs.v[q]), f32(qs.radius[q]), int(qs.min_level[q]), int(qs.max_level[q])):
+                d = popcount_distance(qs.desc[q], D[i2])
+                if mdist[i2] <= d:
+                    continue
+                if d < best:
+                    best2, best, besti = best, d, i2
+                elif d < best2:
+                    best2 = d
+            if best <= TH_LOW and f32(best) < f32(f32(best2) * f32(nnratio)):
+                if m21[besti] >= 0:
+                    m12[m21[besti]] = -1
+                    n -= 1
+                m12[i1], m21[besti], mdist[besti] = besti, i1, best
+                n += 1
+                if check_ori:
+                    hist[rot_bin(qs.angle[q], K[besti]["angle"])].append(i1)
+        if check_ori:
+            keep = py_three_maxima(hist)
+            for b in range(HISTO_LENGTH):
+                if b in keep:
+                    continue
+                for i1 in hist[b]:
+                    if m12[i1] >= 0:
+                        m12[i1] = -1
+                        n -= 1
+        m12_all[q0:q1] = m12
+        nm_out.append(n)
+    return np.array(nm_out, np.int32), m12_all
+
+
+def py_distinctive_descriptors(off, desc):
+    idx, med = np.full(len(off) - 1, -1, np.int32), np.full(len(off) - 1, 2 ** 31 - 1, np.int32)
+    for p in range(len(off) - 1):
+        D = desc[off[p]:off[p + 1]]
+        N = len(D)
+        if N == 0:
+            continue
+        best_med, best_i = 2 ** 31 - 1, 0
+        dist = [[popcount_distance(D[i], D[j]) if i != j else 0 for j in range(N)] for i in range(N)]
+        for i in range(N):
+            m = sorted(dist[i])[int(0.5 * (N - 1))]
+            if m < best_med:
+                best_med, best_i = m, i
+        idx[p], med[p] = best_i, best_med
+    return idx, med
+
+
+def py_is_in_frustum(cam, log_sf, n_levels, cos_limit, mp_off, P, Nn, dmin, dmax, dref):
+    n = int(mp_off[-1])
+    out = {"in_view": np.zeros(n, np.uint8), "proj_x": np.zeros(n, f32), "proj_y": np.zeros(n, f32), "proj_xr": np.zeros(n, f32),
+           "level": np.zeros(n, np.int32), "view_cos": np.zeros(n, f32)}
+    for f in range(len(mp_off) - 1):
+        c = cam[f].astype(f32)
+        fx, fy, cx, cy, mbf, minx, maxx, miny, maxy = c[15:24]
+        for q in range(int(mp_off[f]), int(mp_off[f + 1])):
+            p = P[q].astype(f32)
+            pc = []
+            for r in range(3):   # cv::gemm small-matrix path: float dot product left to right, addend joined in double
+                t = f32(f32(f32(c[3 * r] * p[0]) + f32(c[3 * r + 1] * p[1])) + f32(c[3 * r + 2] * p[2]))
+                pc.append(f32(float(t) + float(c[9 + r])))
+            if pc[2] < 0:
+                continue
+            with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+                invz = f32(1.0) / pc[2]
+                u = f32(f32(f32(fx * pc[0]) * invz) + cx)
+                v = f32(f32(f32(fy * pc[1]) * invz) + cy)
+            if u < minx or u > maxx or v < miny or v > maxy:
+                continue
+            po = [f32(p[k] - c[12 + k]) for k in range(3)]
+            dist = f32(math.sqrt(sum(float(x) * float(x) for x in po)))
+            if dist < dmin[q] or dist > dmax[q]:
+                continue
+            dot = float(po[0]) * float(Nn[q][0]) + float(po[1]) * float(Nn[q][1]) + float(po[2]) * float(Nn[q][2])
+            vc = f32(dot / float(dist))
+            if vc < f32(cos_limit):
+                continue
+            ratio = f32(f32(dref[q]) / dist)
+            lvl = int(math.ceil(float(f32(f32(math.log(float(ratio))) / f32(log_sf)))))
+            lvl = 0 if lvl < 0 else (n_levels - 1 if lvl >= n_levels else lvl)
+            out["in_view"][q], out["proj_x"][q], out["proj_y"][q] = 1, u, v
+            out["proj_xr"][q] = f32(u - f32(mbf * invz))
+            out["level"][q], out["view_cos"][q] = lvl, vc
+    return out
+
+
 def checksum(*arrays) -> np.ndarray:
     import zlib
     c = 0
@@ -362,7 +533,25 @@ CASES = {
     "win_frame_mono": ("win", dict(seed=41, n_frames=3, n_lo=250, n_hi=400, n_q=300, mode="frame", th=15.0), dict(th_dist=100, skip_any=False, check_ori=True)),
     "win_frame_stereo": ("win", dict(seed=42, n_frames=3, n_lo=250, n_hi=400, n_q=300, mode="frame", th=7.0, stereo_frac=0.5), dict(th_dist=100, skip_any=False, check_ori=True)),
     "win_keyframe": ("win", dict(seed=43, n_frames=2, n_lo=250, n_hi=400, n_q=300, mode="keyframe", th=10.0), dict(th_dist=64, skip_any=True, check_ori=False)),
+    "best_fuse_gate_stereo": ("best", dict(seed=51, n_frames=2, n_lo=250, n_hi=400, n_q=300, mode="keyframe", th=12.0, stereo_frac=0.5), dict(gate=True, skip=False)),
+    "best_fuse_gate_mono": ("best", dict(seed=52, n_frames=2, n_lo=250, n_hi=400, n_q=300, mode="keyframe", th=12.0), dict(gate=True, skip=False)),
+    "best_sim3_skip": ("best", dict(seed=53, n_frames=2, n_lo=250, n_hi=400, n_q=300, mode="keyframe", th=10.0), dict(gate=False, skip=True)),
+    "init_ori": ("init", dict(seed=61, n_frames=2, n_lo=300, n_hi=500), dict(nnratio=0.9, check_ori=True)),
+    "init_noori": ("init", dict(seed=62, n_frames=2, n_lo=300, n_hi=500), dict(nnratio=0.9, check_ori=False)),
+    "distinctive": ("distinctive", dict(seed=71, n_points=250, n_max=40), dict()),
+    "frustum": ("frustum", dict(seed=81, n_frames=2, n_mp=700), dict()),
 }
+
+
+def best_inputs(gen):
+    """win_case queries restricted to the level range [l-1, l] of Fuse / SearchBySim3, ur always present."""
+    from orb_slam2_with_comment_b200 import synth
+    from orb_slam2_with_comment_b200.matcher import WindowQuerySet
+    fs, qs = mc.win_case(**gen)
+    q2 = WindowQuerySet(qs.q_off, qs.u, qs.v, qs.radius, qs.min_level, qs.min_level + 1, qs.flags, qs.desc,
+                        ur=qs.ur if qs.ur is not None else (qs.u - 5.0).astype(np.float32), angle=qs.angle)
+    _, s2 = synth.scale_tables()
+    return fs, q2, (np.float32(1.0) / s2).astype(np.float32)
 
 
 def run_case(name):
@@ -376,6 +565,23 @@ def run_case(name):
         s1, s2, i1, i2, F12, epi, sf, s2t = mc.tri_case(**gen)
         nm, m12, md = py_search_for_triangulation(s1, s2, i1, i2, F12, epi, sf, s2t, mk["only_stereo"], mk["check_ori"])
         out = {"nmatches": nm, "match12": m12, "match_dist": md, "input_crc": fs_checksum(s1)}
+    elif kind == "best":
+        fs, qs, inv = best_inputs(gen)
+        bi, bd = py_search_window_best(fs, qs, inv if mk["gate"] else None, mk["skip"])
+        out = {"q_best_idx": bi, "q_best_dist": bd, "nmatches": np.array([(bi >= 0).sum()], np.int32), "input_crc": checksum(fs_checksum(fs), qs.u, qs.v, qs.desc)}
+    elif kind == "init":
+        fs2, qs = mc.init_case(**gen)
+        nm, m12 = py_search_for_initialization(fs2, qs, mk["nnratio"], mk["check_ori"])
+        out = {"nmatches": nm, "match12": m12, "input_crc": checksum(fs_checksum(fs2), qs.u, qs.v, qs.desc)}
+    elif kind == "distinctive":
+        off, desc = mc.distinctive_case(**gen)
+        idx, med = py_distinctive_descriptors(off, desc)
+        out = {"best_idx": idx, "best_median": med, "nmatches": np.array([(idx > 0).sum()], np.int32), "input_crc": checksum(off, desc)}
+    elif kind == "frustum":
+        args = mc.frustum_case(**gen)
+        out = py_is_in_frustum(*args)
+        out["nmatches"] = np.array([out["in_view"].sum()], np.int32)
+        out["input_crc"] = checksum(*args[4:])
     elif kind == "win":
         fs, qs = mc.win_case(**gen)
         nm, kpm, bi, bd = py_search_windowed(fs, qs, mk["th_dist"], mk["skip_any"], mk["check_ori"])

@@ -190,6 +190,29 @@ def test_port_reproduces_golden_fixtures(mo):
             assert np.array_equal(gen.fs_checksum(s1), G[f"{name}__input_crc"])
             res = mo(0.6, mk["check_ori"]).SearchForTriangulation(s1, s2, i1, i2, F12, epi, sf, s2t, bOnlyStereo=mk["only_stereo"])
             _check(res, G, name, ("nmatches", "match12", "match_dist"))
+        elif kind == "best":
+            fs, qs, inv = gen.best_inputs(g)
+            res = mo(0.6, False).SearchWindowBest(fs, qs, inv if mk["gate"] else None, mk["skip"])
+            _check(res, G, name, ("q_best_idx", "q_best_dist"))
+            res["nmatches"] = np.array([(res["q_best_idx"] >= 0).sum()])
+        elif kind == "init":
+            fs2, qs = mc.init_case(**g)
+            res = mo(mk["nnratio"], mk["check_ori"]).SearchForInitialization(fs2, qs)
+            _check(res, G, name, ("nmatches", "match12"))
+        elif kind == "distinctive":
+            off, desc = mc.distinctive_case(**g)
+            idx, med = ol.distinctive_descriptors(ol.load_port(), off, desc)
+            assert np.array_equal(idx, G[f"{name}__best_idx"]) and np.array_equal(med, G[f"{name}__best_median"])
+            res = {"nmatches": np.array([(idx > 0).sum()])}
+        elif kind == "frustum":
+            args = mc.frustum_case(**g)
+            res = ol.is_in_frustum(ol.load_port(), *args)
+            for k in ("in_view", "proj_x", "proj_y", "proj_xr", "view_cos"):
+                assert res[k].tobytes() == G[f"{name}__{k}"].tobytes(), f"{name}: {k}"
+            # glibc logf (C oracle) vs correctly rounded log (Python restatement): a level may differ by one on an exact boundary
+            diff = np.nonzero(res["level"] != G[f"{name}__level"])[0]
+            assert len(diff) <= 1 and np.all(np.abs(res["level"][diff] - G[f"{name}__level"][diff]) == 1)
+            res["nmatches"] = np.array([res["in_view"].sum()])
         elif kind == "win":
             fs, qs = mc.win_case(**g)
             res = mo(0.6, mk["check_ori"]).SearchWindowed(fs, qs, mk["th_dist"], mk["skip_any"])
