@@ -322,6 +322,16 @@ int orbgpu_is_in_frustum_dev(orbgpu_matcher* m, int n_frames, const float* cam, 
                              uint8_t* in_view_dev, float* proj_x_dev, float* proj_y_dev, float* proj_xr_dev, int32_t* level_dev,
                              float* view_cos_dev);
 
+/* The projection step of Tracking::SearchLocalPoints (Tracking.cc:1150-1200) straight into a device-resident map-point set:
+ * uploads the local map (same inputs as orbgpu_is_in_frustum, plus `flags` — bit 1: isBad(), bit 2: Observations() > 0, bit 0
+ * is ignored — and the descriptors), runs isInFrustum on the device and leaves proj_x / proj_y / proj_xr / view_cos / level and
+ * the visibility bit where orbgpu_search_by_projection_dev reads them: projection -> window -> candidates -> match without
+ * the mTrack* fields ever visiting the host.  Release with orbgpu_mappoint_set_release. */
+int orbgpu_mappoint_set_project(orbgpu_matcher* m, int n_frames, const float* cam, float log_scale_factor, int n_levels,
+                                float viewing_cos_limit, const int32_t* mp_off, const float* world_pos, const float* normal,
+                                const float* min_dist_inv, const float* max_dist_inv, const float* max_distance, const uint8_t* flags,
+                                const uint8_t* desc, orbgpu_mappoint_set_dev** out);
+
 /* Best-only windowed search: the candidate loops of ORBmatcher::Fuse(KeyFrame*, const vector<MapPoint*>&, th)
  * (ORBmatcher.cc:1051-1112), Fuse(KeyFrame*, Scw, ...) (:1211-1246) and both directions of SearchBySim3 (:1363-1401,
  * :1443-1481).  Queries are independent — no key point is taken by an earlier query; the map updates that follow in the

@@ -2103,6 +2103,7 @@ struct FrustumArgs {
     const float* cam;        // [n_frames][24]
     const int32_t* mp_off;   // device copy
     const float *world_pos, *normal, *min_d, *max_d, *max_distance;
+    const uint8_t* flags_in;   // optional: bits 1.. are kept, bit 0 becomes the visibility (orbgpu_mappoint_set flags)
     uint8_t* in_view;
     float *proj_x, *proj_y, *proj_xr, *view_cos;
     int32_t* level;
@@ -2147,7 +2148,7 @@ __global__ void __launch_bounds__(256) k_frustum(FrustumArgs A) {
         if (!(qf == qf)) lvl = 0;   // NaN: the reference's float -> int conversion is undefined here
         ok = 1; u = uu; v = vv; ur = uu - __ldg(c + 19) * invz; vc = viewCos;
     } while (0);
-    A.in_view[q] = ok;
+    A.in_view[q] = A.flags_in ? (uint8_t)((A.flags_in[q] & 0xFEu) | ok) : ok;
     A.proj_x[q] = u; A.proj_y[q] = v; A.proj_xr[q] = ur; A.view_cos[q] = vc;
     A.level[q] = lvl;
 }
@@ -2176,7 +2177,7 @@ extern "C" int orbgpu_is_in_frustum_dev(orbgpu_matcher* m, int n_frames, const f
     OGM_CUDA(m->s_grid_items.grab((size_t)(n_frames + 1) * 4, &d_off));
     OGM_CUDA(cudaMemcpyAsync(d_cam, cam, (size_t)n_frames * 24 * 4, cudaMemcpyHostToDevice, m->stream));
     OGM_CUDA(cudaMemcpyAsync(d_off, mp_off, (size_t)(n_frames + 1) * 4, cudaMemcpyHostToDevice, m->stream));
-    og::FrustumArgs A = {(const float*)d_cam, (const int32_t*)d_off, world_pos, normal, min_d, max_d, max_distance, in_view, proj_x, proj_y,
+    og::FrustumArgs A = {(const float*)d_cam, (const int32_t*)d_off, world_pos, normal, min_d, max_d, max_distance, nullptr, in_view, proj_x, proj_y,
                          proj_xr, view_cos, level, log_scale_factor, viewing_cos_limit, n_levels};
     og::k_frustum<<<dim3((max_n + 255) / 256, n_frames), 256, 0, m->stream>>>(A);
     m->last_launches = 1;
@@ -2325,4 +2326,66 @@ extern "C" int orbgpu_search_for_initialization(orbgpu_matcher* m, const orbgpu_
     if (!match12) return og_fail(ORBGPU_ERR_ARG, "search_for_initialization: null match12");
     return win_host(m, frames2, queries1, ORBGPU_TH_LOW, 0, check_orientation, nullptr, nullptr, nullptr, nmatches, false, nullptr, 0, true, nnratio,
                     match12);
+}
+
+// Tracking::SearchLocalPoints' projection step (Tracking.cc:1150-1200) straight into a device-resident map-point set
+extern "C" int orbgpu_mappoint_set_project(orbgpu_matcher* m, int n_frames, const float* cam, float log_scale_factor, int n_levels,
+                                           float viewing_cos_limit, const int32_t* mp_off, const float* world_pos, const float* normal,
+                                           const float* min_d, const float* max_d, const float* max_distance, const uint8_t* flags,
+                                           const uint8_t* desc, orbgpu_mappoint_set_dev** out) {
+    int rc = check_matcher(m);
+    if (rc) return rc;
+    if (!out) return og_fail(ORBGPU_ERR_ARG, "null out");
+    *out = nullptr;
+    if (n_frames < 1 || !cam || !mp_off) return og_fail(ORBGPU_ERR_ARG, "mappoint_set_project: null cam / mp_off");
+    const size_t n = (size_t)mp_off[n_frames];
+    int max_n = 0;
+    for (int f = 0; f < n_frames; ++f) {
+        if (mp_off[f + 1] < mp_off[f]) return og_fail(ORBGPU_ERR_ARG, "mappoint_set_project: mp_off must be non-decreasing");
+        max_n = std::max(max_n, mp_off[f + 1] - mp_off[f]);
+    }
+    if (n && (!world_pos || !normal || !min_d || !max_d || !max_distance || !flags || !desc))
+        return og_fail(ORBGPU_ERR_ARG, "mappoint_set_project: null array");
+    if (!(log_scale_factor > 0.f) || n_levels < 1) return og_fail(ORBGPU_ERR_ARG, "mappoint_set_project: bad scale factor / level count");
+    cudaStream_t st = m->stream;
+    orbgpu_mappoint_set_dev* mp = new orbgpu_mappoint_set_dev();
+    mp->device = m->device; mp->n_frames = n_frames; mp->nmp = (int)n;
+    auto bail = [&](int code) { free_owned(mp->owned); delete mp; return code; };
+    rc = upload_array(mp_off, (size_t)n_frames + 1, mp->owned, &mp->v.mp_off, st);
+    if (!rc) rc = upload_array(desc, n * 32, mp->owned, &mp->v.desc, st);
+    if (rc) return bail(rc);
+    void* o[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    const size_t ob[6] = {n * 4, n * 4, n * 4, n * 4, n * 4, n};
+    for (int i = 0; i < 6; ++i) {
+        cudaError_t e = cudaMalloc(&o[i], std::max<size_t>(ob[i], 256));
+        if (e != cudaSuccess) return bail(og_fail(ORBGPU_ERR_CUDA, std::string("mappoint_set_project: ") + cudaGetErrorString(e)));
+        mp->owned.push_back(o[i]);
+    }
+    mp->v.proj_x = (const float*)o[0]; mp->v.proj_y = (const float*)o[1]; mp->v.proj_xr = (const float*)o[2];
+    mp->v.view_cos = (const float*)o[3]; mp->v.level = (const int32_t*)o[4]; mp->v.flags = (const uint8_t*)o[5];
+    if (n) {
+        m->tmp_next = 0;
+        const void* src[6] = {world_pos, normal, min_d, max_d, max_distance, flags};
+        const size_t sb[6] = {n * 12, n * 12, n * 4, n * 4, n * 4, n};
+        void* din[6];
+        for (int i = 0; i < 6; ++i) {
+            cudaError_t e = m->s_tmp[m->tmp_next++].grab(sb[i], &din[i]);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(din[i], src[i], sb[i], cudaMemcpyHostToDevice, st);
+            if (e != cudaSuccess) return bail(og_fail(ORBGPU_ERR_CUDA, std::string("mappoint_set_project: ") + cudaGetErrorString(e)));
+        }
+        void *d_cam, *d_off;
+        cudaError_t e = m->s_grid_start.grab((size_t)n_frames * 24 * 4, &d_cam);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_cam, cam, (size_t)n_frames * 24 * 4, cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) return bail(og_fail(ORBGPU_ERR_CUDA, std::string("mappoint_set_project: ") + cudaGetErrorString(e)));
+        d_off = (void*)mp->v.mp_off;
+        og::FrustumArgs A = {(const float*)d_cam, (const int32_t*)d_off, (const float*)din[0], (const float*)din[1], (const float*)din[2],
+                             (const float*)din[3], (const float*)din[4], (const uint8_t*)din[5], (uint8_t*)o[5], (float*)o[0], (float*)o[1],
+                             (float*)o[2], (float*)o[3], (int32_t*)o[4], log_scale_factor, viewing_cos_limit, n_levels};
+        og::k_frustum<<<dim3((max_n + 255) / 256, n_frames), 256, 0, st>>>(A);
+        m->last_launches = 1;
+    }
+    cudaError_t e = cudaStreamSynchronize(st);   // the staging buffers are reused by the next call
+    if (e != cudaSuccess) return bail(og_fail(ORBGPU_ERR_CUDA, std::string("mappoint_set_project: ") + cudaGetErrorString(e)));
+    *out = mp;
+    return ORBGPU_OK;
 }

@@ -141,6 +141,7 @@ def _bind(L):
     L.orbgpu_search_for_initialization.argtypes = [vp, C.POINTER(CFrameSet), C.POINTER(CWindowQuerySet), f, i, vp, vp]
     L.orbgpu_search_window_best.argtypes = [vp, C.POINTER(CFrameSet), C.POINTER(CWindowQuerySet), vp, i, i, vp, vp]
     L.orbgpu_distinctive_descriptors.argtypes = [vp, i, vp, vp, vp, vp]
+    L.orbgpu_mappoint_set_project.argtypes = [vp, i, vp, f, i, f] + [vp] * 8 + [C.POINTER(vp)]
     L.orbgpu_is_in_frustum.argtypes = [vp, i, vp, f, i, f] + [vp] * 12
     L.orbgpu_is_in_frustum_dev.argtypes = [vp, i, vp, f, i, f] + [vp] * 12
     L.orbgpu_frame_set_from_extraction.argtypes = [vp, vp, vp, i, i, vp, i, vp, C.POINTER(vp)]
@@ -295,6 +296,19 @@ class ORBmatcher:
         idx, med = np.zeros(n, np.int32), np.zeros(n, np.int32)
         capi.check(self._lib.orbgpu_distinctive_descriptors(self._h, n, obs_off.ctypes.data, desc.ctypes.data, idx.ctypes.data, med.ctypes.data))
         return idx, med
+
+    def project_mappoints(self, cam, log_scale_factor, n_levels, viewing_cos_limit, mp_off, world_pos, normal, min_dist_inv, max_dist_inv,
+                          max_distance, flags, desc) -> C.c_void_p:
+        """isInFrustum on the device straight into a device-resident map-point set (orbgpu_mappoint_set_project)."""
+        cam = np.ascontiguousarray(cam, np.float32).reshape(-1, 24)
+        mp_off = np.ascontiguousarray(mp_off, np.int32)
+        ins = [np.ascontiguousarray(a, np.float32) for a in (world_pos, normal, min_dist_inv, max_dist_inv, max_distance)]
+        fl, ds = np.ascontiguousarray(flags, np.uint8), np.ascontiguousarray(desc, np.uint8)
+        h = C.c_void_p()
+        capi.check(self._lib.orbgpu_mappoint_set_project(self._h, len(cam), cam.ctypes.data, float(log_scale_factor), n_levels,
+                                                         float(viewing_cos_limit), mp_off.ctypes.data, *[a.ctypes.data for a in ins],
+                                                         fl.ctypes.data, ds.ctypes.data, C.byref(h)))
+        return h
 
     def upload(self, fs: FrameSet) -> C.c_void_p:
         h = C.c_void_p()

@@ -235,3 +235,55 @@ def init_case(seed, n_frames=3, n_lo=800, n_hi=1600, window=100.0, p_flip=0.08):
     cat = {k2: np.concatenate([p[k2] for p in parts]) for k2 in parts[0]}
     qs = WindowQuerySet(np.array(q_off, np.int32), cat["u"], cat["v"], cat["radius"], cat["lo"], cat["hi"], cat["flags"], cat["desc"], angle=cat["angle"])
     return fs2, qs
+
+
+def local_map_case(seed, n_frames=3, n_lo=500, n_hi=900, n_mp=1500):
+    """Tracking::SearchLocalPoints in full: frames with key points, and a local map in WORLD coordinates whose points project
+    (through each frame's pose) onto some of that frame's key points — so isInFrustum's outputs feed SearchByProjection."""
+    rs, kp_off, keys, desc = _frames(seed, n_frames, n_lo, n_hi)
+    grid = np.tile(synth.frame_grid(W, H), (n_frames, 1))
+    flags_kp = np.zeros(len(keys), np.uint8)
+    flags_kp[rs.uniform(size=len(keys)) < 0.1] = 1
+    fs = FrameSet(kp_off, keys, desc, kp_flags=flags_kp, grid=grid)
+    fx, fy, cx, cy = 517.3, 516.5, 318.6, 255.3
+    cams, offs = [], [0]
+    P, Nn, dmin, dmax, dref, fl, dd = [], [], [], [], [], [], []
+    for f in range(n_frames):
+        a, b, c = rs.normal(0, 0.04, 3)
+        Rx = np.array([[1, 0, 0], [0, np.cos(a), -np.sin(a)], [0, np.sin(a), np.cos(a)]])
+        Ry = np.array([[np.cos(b), 0, np.sin(b)], [0, 1, 0], [-np.sin(b), 0, np.cos(b)]])
+        Rz = np.array([[np.cos(c), -np.sin(c), 0], [np.sin(c), np.cos(c), 0], [0, 0, 1]])
+        R = (Rx @ Ry @ Rz).astype(np.float32)
+        t = rs.normal(0, 0.4, 3).astype(np.float32)
+        Ow = (-(R.astype(np.float64).T @ t.astype(np.float64))).astype(np.float32)
+        cams.append(np.concatenate([R.ravel(), t, Ow, [fx, fy, cx, cy, 40.0, 0.0, float(W), 0.0, float(H)]]).astype(np.float32))
+        k, d = keys[kp_off[f]:kp_off[f + 1]], desc[kp_off[f]:kp_off[f + 1]]
+        n = int(n_mp * rs.uniform(0.7, 1.0))
+        src = rs.randint(0, len(k), n)
+        z = rs.uniform(1.0, 20.0, n)
+        u = k["x"][src] + rs.normal(0, 1.5, n)
+        v = k["y"][src] + rs.normal(0, 1.5, n)
+        far = rs.uniform(size=n) < 0.15                       # some points nowhere near a key point / outside the image
+        u[far] = rs.uniform(-100, W + 100, int(far.sum()))
+        v[far] = rs.uniform(-100, H + 100, int(far.sum()))
+        z[rs.uniform(size=n) < 0.05] *= -1                     # behind the camera
+        pc = np.stack([(u - cx) / fx * z, (v - cy) / fy * z, z], 1)
+        pw = ((pc - t.astype(np.float64)) @ R.astype(np.float64)).astype(np.float32)
+        dist = np.linalg.norm(pw.astype(np.float64) - Ow, axis=1)
+        nrm = (pw.astype(np.float64) - Ow) / np.maximum(dist, 1e-6)[:, None] + rs.normal(0, 0.3, (n, 3))
+        nrm /= np.linalg.norm(nrm, axis=1)[:, None]
+        ref = dist * 1.2 ** (k["octave"][src] - rs.uniform(0.2, 0.8, n))      # PredictScale gives the key point's octave
+        ref[rs.uniform(size=n) < 0.05] *= 50.0                                  # outside the scale-invariance range
+        P.append(pw); Nn.append(nrm.astype(np.float32)); dref.append(ref.astype(np.float32))
+        dmax.append((np.float32(1.2) * ref.astype(np.float32)).astype(np.float32))
+        dmin.append((np.float32(0.8) * (ref / 1.2 ** 7).astype(np.float32)).astype(np.float32))
+        fb = np.full(n, 4, np.uint8)
+        r2 = rs.uniform(size=n)
+        fb[r2 < 0.04] |= 2                                     # bad
+        fb[(r2 >= 0.04) & (r2 < 0.15)] &= ~np.uint8(4)         # no observations
+        fl.append(fb)
+        dd.append(synth.flip_bits(d[src], rs, 0.05))
+        offs.append(offs[-1] + n)
+    sf, _ = synth.scale_tables()
+    return (fs, sf, np.stack(cams), np.float32(np.log(np.float32(1.2))), 8, 0.5, np.array(offs, np.int32), np.concatenate(P), np.concatenate(Nn),
+            np.concatenate(dmin), np.concatenate(dmax), np.concatenate(dref), np.concatenate(fl), np.concatenate(dd))

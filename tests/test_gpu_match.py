@@ -308,3 +308,28 @@ def test_search_for_initialization_vs_oracle(gm, mo, ratio, ori):
         exp = mo(ratio, ori).SearchForInitialization(fs2, qs)
         same(got, exp, ("nmatches", "match12"), f"init seed {seed}")
         assert exp["nmatches"].sum() > 150
+
+
+def test_search_local_points_chain_on_device():
+    """Tracking::SearchLocalPoints (Tracking.cc:1150-1200): isInFrustum on the device straight into a device-resident map-point
+    set, then SearchByProjection on it — against oracle isInFrustum -> host MapPointSet -> oracle SearchByProjection."""
+    import torch
+    from orb_slam2_with_comment_b200.matcher import ORBmatcher
+    fs, sf, cam, lsf, nl, cosl, off, P, Nn, dmin, dmax, dref, fl, dd = mc.local_map_case(5)
+    fr = ol.is_in_frustum(ol.load_port(), cam, lsf, nl, cosl, off, P, Nn, dmin, dmax, dref)
+    mps = MapPointSet(off, fr["proj_x"], fr["proj_y"], fr["view_cos"], fr["level"], (fl & 0xFE) | fr["in_view"], dd, proj_xr=fr["proj_xr"])
+    exp = ol.MatcherOracle(ol.load_port(), 0.8, True).SearchByProjection(fs, mps, sf, 3.0)
+    m = ORBmatcher(0.8, True)
+    hf = m.upload(fs)
+    hm = m.project_mappoints(cam, lsf, nl, cosl, off, P, Nn, dmin, dmax, dref, fl, dd)
+    dev = torch.device("cuda:0")
+    nkp, nmp, nf = int(fs.kp_off[-1]), int(off[-1]), fs.n_frames
+    o = [torch.zeros(nkp, dtype=torch.int32, device=dev)] + [torch.zeros(nmp, dtype=torch.int32, device=dev) for _ in range(3)]
+    o.append(torch.zeros(nf, dtype=torch.int32, device=dev))
+    m.search_by_projection_dev(hf, hm, sf, 3.0, *[t.data_ptr() for t in o])
+    m.sync()
+    assert np.array_equal(o[4].cpu().numpy(), exp["nmatches"]) and exp["nmatches"].sum() > 600
+    assert np.array_equal(o[0].cpu().numpy(), exp["kp_match"])
+    assert np.array_equal(o[1].cpu().numpy(), exp["mp_best_idx"]) and np.array_equal(o[2].cpu().numpy(), exp["mp_best_dist"])
+    assert 0.4 < fr["in_view"].mean() < 0.95
+    m.release_mappoints(hm); m.release(hf); m.close()
