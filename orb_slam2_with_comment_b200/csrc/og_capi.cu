@@ -76,7 +76,7 @@ struct orbgpu_extractor {
     og::BlurTile* d_btiles = nullptr;
     uint32_t* d_ic_tab = nullptr;
     int n_btiles = 0;
-    CUtensorMap* d_tmaps = nullptr;   // [2][kMaxLevels]: FAST tile boxes over pyr, then (reserved) over blur
+    CUtensorMap* d_tmaps = nullptr;   // [4][kMaxLevels]: FAST tile boxes, blur input boxes, IC_Angle boxes (all over pyr), descriptor boxes over blur
     int fast_smem = 0;
     og::Tap* d_taps = nullptr;
     int32_t *d_cell_count = nullptr, *d_sel_count = nullptr, *d_counts = nullptr;
@@ -376,7 +376,7 @@ int ensure_geometry(orbgpu_extractor* ex, int w, int h) {
     OG_CUDA(cudaMemcpyAsync(ex->d_btiles, G.btiles.data(), G.btiles.size() * sizeof(og::BlurTile), cudaMemcpyHostToDevice, ex->stream));
     ex->n_btiles = (int)G.btiles.size();
     {
-        std::vector<CUtensorMap> maps(2 * og::kMaxLevels);
+        std::vector<CUtensorMap> maps(4 * og::kMaxLevels);
         memset(maps.data(), 0, maps.size() * sizeof(CUtensorMap));
         int smem = 0;
         for (int l = 0; l < ex->nlevels; ++l) {
@@ -384,6 +384,12 @@ int ensure_geometry(orbgpu_extractor* ex, int w, int h) {
             std::string e = make_level_tmap(&maps[l], ex->d_pyr + L.base, L.pitch, L.rows, L.frame_stride, ex->max_batch, og::kSegPitch, L.hbox);
             if (e.empty())
                 e = make_level_tmap(&maps[og::kMaxLevels + l], ex->d_pyr + L.base, L.pitch, L.rows, L.frame_stride, ex->max_batch, 256, og::kBlurBox);
+            if (e.empty())
+                e = make_level_tmap(&maps[2 * og::kMaxLevels + l], ex->d_pyr + L.base, L.pitch, L.rows, L.frame_stride, ex->max_batch, og::kIcBoxW,
+                                    og::kIcRows);
+            if (e.empty())
+                e = make_level_tmap(&maps[3 * og::kMaxLevels + l], ex->d_blur + L.base, L.pitch, L.rows, L.frame_stride, ex->max_batch, og::kBlurBoxW,
+                                    og::kPatchRows);
             if (!e.empty()) return fail(ORBGPU_ERR_CUDA, e);
             smem = std::max(smem, og::fast_seg_smem_bytes(L.hbox, L.hbox - 6));
         }
@@ -518,7 +524,7 @@ int launch_extract(orbgpu_extractor* ex, const uint8_t* d_images, int batch, siz
     }
     mark(4);
     og::k_orient_desc<<<dim3((ex->kp_cap + og::kDescWarps * og::kDescPerWarp - 1) / (og::kDescWarps * og::kDescPerWarp), batch), og::kDescWarps * 32, 0, st>>>(
-        P, d_kp, d_desc, d_counts);
+        P, ex->d_tmaps, d_kp, d_desc, d_counts);
     ++launches;
     mark(5);
     OG_CUDA(cudaGetLastError());
@@ -603,7 +609,7 @@ int orbgpu_extractor_create(orbgpu_extractor** out, int device, int nfeatures, f
     alloc((void**)&ex->d_cells, ex->cap_cells * sizeof(og::Cell));
     alloc((void**)&ex->d_segs, ex->cap_cells * sizeof(og::Segment));
     alloc((void**)&ex->d_btiles, ex->cap_cells * sizeof(og::BlurTile));
-    alloc((void**)&ex->d_tmaps, 2 * og::kMaxLevels * sizeof(CUtensorMap));
+    alloc((void**)&ex->d_tmaps, 4 * og::kMaxLevels * sizeof(CUtensorMap));
     alloc((void**)&ex->d_taps, ex->cap_taps * sizeof(og::Tap));
     alloc((void**)&ex->d_cell_count, ex->cap_cellcount * B * 4);
     alloc((void**)&ex->d_cand_xy, ex->cap_cand * B * 4);

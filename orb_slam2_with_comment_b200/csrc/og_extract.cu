@@ -790,7 +790,8 @@ __global__ void __launch_bounds__(kBlurThreads) k_blur_tma(const __grid_constant
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kDescWarps = 8, kDescPerWarp = 4;
 constexpr int kIcWords = 9, kIcRows = 31;           // table [4 alignments][31 rows][9 words][2]
-constexpr int kPatchRows = 37, kPatchPitch = 40;    // 37 x 37 window + up to 3 bytes of alignment
+constexpr int kIcBoxW = 48, kBlurBoxW = 64, kPatchRows = 37;   // TMA boxes: 48 x 31 of the level, 64 x 37 of its blur
+constexpr int kIcSlot = 1536, kBlurSlot = 2432;     // box bytes rounded up to the 128 B a TMA destination wants
 __constant__ int8_t c_pat_x[512] = {ORB_PATTERN_X_INIT};
 __constant__ int8_t c_pat_y[512] = {ORB_PATTERN_Y_INIT};
 
@@ -800,17 +801,26 @@ __device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c) {   // uns
     return r;
 }
 
-__global__ void __launch_bounds__(kDescWarps * 32, 6) k_orient_desc(const __grid_constant__ ExtractParams P, KeyPoint* __restrict__ kp_out,
-                                                                 uint8_t* __restrict__ desc_out,
-                                                                 int32_t* __restrict__ counts) {
+// Both neighbourhoods of a key point arrive by TMA (one elected lane, two boxes, one mbarrier each per warp): the 31 x 31
+// disc of the level for IC_Angle and the 37 x 37 window of the blurred level for the descriptor.  A box starts at a 16-byte
+// aligned column at or left of the window (TMA's alignment rule), so it is 48 / 64 bytes wide.  tmaps: [2K + l] level boxes,
+// [3K + l] blur boxes (K = kMaxLevels).
+__global__ void __launch_bounds__(kDescWarps * 32, 6) k_orient_desc(const __grid_constant__ ExtractParams P, const CUtensorMap* __restrict__ tmaps,
+                                                                    KeyPoint* __restrict__ kp_out, uint8_t* __restrict__ desc_out,
+                                                                    int32_t* __restrict__ counts) {
     // pattern point j of lane i (= bit_pattern_31_ point 16 i + j) at spat[j * 32 + i]: the 32 lanes of a load hit 32
     // consecutive 8-byte slots (no bank conflicts), and the coordinates are already floats (no I2F in the sample loop)
     __shared__ float2 spat[512];
-    __shared__ __align__(16) uint8_t patch[kDescWarps][kPatchRows * kPatchPitch];
+    __shared__ __align__(128) uint8_t patch[kDescWarps][kIcSlot + kBlurSlot];
+    __shared__ uint64_t bars[kDescWarps][2];
     for (int i = threadIdx.x; i < 512; i += blockDim.x) spat[(i & 15) * 32 + (i >> 4)] = make_float2((float)c_pat_x[i], (float)c_pat_y[i]);
-    __syncthreads();
     const int frame = P.frame0 + blockIdx.y;
     const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+    if (lane == 0) {
+        mbar_init(&bars[wi][0], 1);
+        mbar_init(&bars[wi][1], 1);
+    }
+    __syncthreads();
     // keypoints are concatenated in level order (:1076-1103): level starts from the per-level counts
     const int32_t* sc = P.sel_count + frame * P.n_levels;
     int lstart[kMaxLevels + 1];
@@ -819,9 +829,9 @@ __global__ void __launch_bounds__(kDescWarps * 32, 6) k_orient_desc(const __grid
     for (int l = 0; l < kMaxLevels; ++l) lstart[l + 1] = lstart[l] + (l < P.n_levels ? sc[l] : 0);
     const int total = min(lstart[kMaxLevels], P.kp_cap);
     if (blockIdx.x == 0 && threadIdx.x == 0) counts[frame] = total;
-    uint8_t* pw = patch[wi];
+    uint8_t* ic_tile = patch[wi];
+    uint8_t* bl_tile = patch[wi] + kIcSlot;
     const int ic_r = lane / kIcWords, ic_j = lane - ic_r * kIcWords;     // lanes 0..26: 3 disc rows x 9 words per step
-    const int pt_r = lane / 10, pt_j = lane - pt_r * 10;                 // lanes 0..29: 3 patch rows x 10 words per step
 
     for (int n = 0; n < kDescPerWarp; ++n) {
         const int idx = (blockIdx.x * kDescPerWarp + n) * kDescWarps + wi;   // index among the frame's keypoints
@@ -835,19 +845,29 @@ __global__ void __launch_bounds__(kDescWarps * 32, 6) k_orient_desc(const __grid
         const uint32_t xy = P.sel_xy[(long long)frame * P.total_sel_cap + L.sel_base + off];
         const int resp = P.sel_resp[(long long)frame * P.total_sel_cap + L.sel_base + off];
         const int cx = (int)(xy & 0xffffu) + 16, cy = (int)(xy >> 16) + 16;   // level coordinates (:840-841)
+        const int icx = kXPad + cx - kHalfPatch, blx = kXPad + cx - 18;       // first column of the disc / of the 37-wide window
+        __syncwarp();   // every lane is done with the previous key point's tiles
+        if (lane == 0) {
+            mbar_expect_tx(&bars[wi][0], kIcBoxW * kIcRows);
+            tma_load_3d(ic_tile, tmaps + 2 * kMaxLevels + level, icx & ~15, kEdge + cy - kHalfPatch, frame, &bars[wi][0]);
+            mbar_expect_tx(&bars[wi][1], kBlurBoxW * kPatchRows);
+            tma_load_3d(bl_tile, tmaps + 3 * kMaxLevels + level, blx & ~15, kEdge + cy - 18, frame, &bars[wi][1]);
+        }
+        const uint32_t phase = (uint32_t)(n & 1);
 
         // ---- IC_Angle
         int m10 = 0, m01 = 0;
+        mbar_wait(&bars[wi][0], phase);
         {
-            const int A = (kXPad + cx - kHalfPatch) & 3;
-            const uint8_t* base = level_ptr(P.pyr, L, frame) + (long long)(kEdge + cy - kHalfPatch) * L.pitch + (kXPad + cx - kHalfPatch - A);
+            const int A = icx & 3;
+            const uint32_t* base = reinterpret_cast<const uint32_t*>(ic_tile + ((icx & 15) & ~3)) + ic_j;   // aligned word holding the disc's first column
             const uint2* tab = reinterpret_cast<const uint2*>(P.ic_tab) + (A * kIcRows) * kIcWords + ic_j;
             if (lane < 3 * kIcWords) {
 #pragma unroll
                 for (int it = 0; it < (kIcRows + 2) / 3; ++it) {
                     const int row = 3 * it + ic_r;
                     if (row < kIcRows) {
-                        const uint32_t px = __ldg(reinterpret_cast<const uint32_t*>(base + (long long)row * L.pitch) + ic_j);
+                        const uint32_t px = base[row * (kIcBoxW / 4)];
                         const uint2 w = __ldg(tab + row * kIcWords);
                         m10 = dp4a_us(px, w.x, m10);
                         m01 = dp4a_us(px, w.y, m01);
@@ -862,26 +882,11 @@ __global__ void __launch_bounds__(kDescWarps * 32, 6) k_orient_desc(const __grid
         }
         const float angle = fast_atan2((float)m01, (float)m10, P.atan);
 
-        // ---- stage the blurred 37 x 37 neighbourhood
-        const int A2 = (kXPad + cx - 18) & 3;
-        {
-            const uint8_t* bsrc = level_ptr(P.blur, L, frame) + (long long)(kEdge + cy - 18) * L.pitch + (kXPad + cx - 18 - A2);
-            __syncwarp();
-            if (lane < 30) {
-#pragma unroll
-                for (int it = 0; it < (kPatchRows + 2) / 3; ++it) {
-                    const int row = 3 * it + pt_r;
-                    if (row < kPatchRows)
-                        reinterpret_cast<uint32_t*>(pw + row * kPatchPitch)[pt_j] =
-                            __ldg(reinterpret_cast<const uint32_t*>(bsrc + (long long)row * L.pitch) + pt_j);
-                }
-            }
-            __syncwarp();
-        }
-        // ---- rotated BRIEF
+        // ---- rotated BRIEF on the blurred window
         const float ang = fmul(angle, P.factor_pi);
         const float a = (float)cos((double)ang), b = (float)sin((double)ang);
-        const uint8_t* b0 = pw + 18 * kPatchPitch + 18 + A2;
+        mbar_wait(&bars[wi][1], phase);
+        const uint8_t* b0 = bl_tile + 18 * kBlurBoxW + 18 + (blx & 15);
         int val = 0;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -889,7 +894,7 @@ __global__ void __launch_bounds__(kDescWarps * 32, 6) k_orient_desc(const __grid
             int r0, q0, r1, q1;
             brief_offset_f(p0.x, p0.y, a, b, &r0, &q0);
             brief_offset_f(p1.x, p1.y, a, b, &r1, &q1);
-            const int t0 = b0[r0 * kPatchPitch + q0], t1 = b0[r1 * kPatchPitch + q1];
+            const int t0 = b0[r0 * kBlurBoxW + q0], t1 = b0[r1 * kBlurBoxW + q1];
             val |= (t0 < t1) << k;
         }
         desc_out[((long long)frame * P.kp_cap + idx) * 32 + lane] = (uint8_t)val;
