@@ -788,7 +788,7 @@ __global__ void __launch_bounds__(kBlurThreads) k_blur_tma(const __grid_constant
 //   coalesced word loads; lane i produces descriptor byte i from pattern points 16i .. 16i+15.  cos/sin of the float
 //   angle are evaluated in double and rounded to float.
 // ------------------------------------------------------------------------------------------------------------
-constexpr int kDescWarps = 8, kDescPerWarp = 4;
+constexpr int kDescWarps = 6, kDescPerWarp = 16;   // measured on B200 (device / host-path k frames/s): 8x4 96.3 / 82.2, 4x16 96.9 / 86.9, 6x16 97.8 / 87.1
 constexpr int kIcWords = 9, kIcRows = 31;           // table [4 alignments][31 rows][9 words][2]
 constexpr int kIcBoxW = 48, kBlurBoxW = 64, kPatchRows = 37;   // TMA boxes: 48 x 31 of the level, 64 x 37 of its blur
 constexpr int kIcSlot = 1536, kBlurSlot = 2432;     // box bytes rounded up to the 128 B a TMA destination wants
