@@ -62,15 +62,35 @@ struct OtNode {
 };
 
 // Per-node scratch for one division pass.
-struct OtTmp {
+struct alignas(8) OtTmp {
+    // header: one 8-byte load gives the key loops everything they need to classify a key of this node
+    int16_t sx, sy;   // split lines
+    uint8_t cand, processed;
+    uint16_t pad;
     int32_t pre[4];   // class counts of keys BEFORE this node's segment (scan value at segment start)
     int32_t cnt[4];   // keys per child
     int32_t ord;      // index in processing order, -1 = not a candidate
     int32_t qbase;    // creation index of the first child
     int32_t newpos;   // list position in the next list (survivors) / unused
-    int16_t sx, sy;   // split lines
-    uint8_t cand, processed;
+    int32_t pad2;
 };
+
+// sx | sy << 16 in .x, cand | processed << 8 in .y
+struct OtHead { int sx, sy; bool cand, processed; };
+OG_HD OtHead ot_head(const OtTmp* t) {
+    OtHead h;
+#if OG_DEVICE_PASS
+    const uint2 v = *reinterpret_cast<const uint2*>(t);
+    h.sx = (int)(int16_t)(v.x & 0xffffu);
+    h.sy = (int)(int16_t)(v.x >> 16);
+    h.cand = (v.y & 0xffu) != 0;
+    h.processed = ((v.y >> 8) & 0xffu) != 0;
+#else
+    h.sx = t->sx; h.sy = t->sy; h.cand = t->cand != 0; h.processed = t->processed != 0;
+#endif
+    return h;
+}
+constexpr int kOtBatch = 4;   // keys a thread has in flight in the key loops (their loads are independent)
 
 // Block-shared scalars.
 struct OtShared {
@@ -186,12 +206,25 @@ OG_HD void ot_pass(const OtWork& W, OtShared* sh, int cur, int rcur, int M, int 
     OG_THREADS_BEGIN(tt, TT)
         OG_CHUNK(M, tt, TT, lo, hi)
         int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-        for (int p = lo; p < hi; ++p) {
-            const int i = knode[p];
-            if (!tmp[i].cand) continue;
-            const int x = (int)(kxy[p] & 0xffffu), y = (int)(kxy[p] >> 16);
-            const int c = (x >= tmp[i].sx ? 1 : 0) + (y >= tmp[i].sy ? 2 : 0);
-            c0 += (c == 0); c1 += (c == 1); c2 += (c == 2); c3 += (c == 3);
+        for (int p0 = lo; p0 < hi; p0 += kOtBatch) {
+            int ii[kOtBatch];
+            uint32_t kk[kOtBatch];
+            OtHead hh[kOtBatch];
+#pragma unroll
+            for (int u = 0; u < kOtBatch; ++u) {
+                const int p = p0 + u < hi ? p0 + u : hi - 1;
+                ii[u] = knode[p];
+                kk[u] = kxy[p];
+            }
+#pragma unroll
+            for (int u = 0; u < kOtBatch; ++u) hh[u] = ot_head(&tmp[ii[u]]);
+#pragma unroll
+            for (int u = 0; u < kOtBatch; ++u) {
+                if (p0 + u >= hi || !hh[u].cand) continue;
+                const int x = (int)(kk[u] & 0xffffu), y = (int)(kk[u] >> 16);
+                const int c = (x >= hh[u].sx ? 1 : 0) + (y >= hh[u].sy ? 2 : 0);
+                c0 += (c == 0); c1 += (c == 1); c2 += (c == 2); c3 += (c == 3);
+            }
         }
         W.thr[tt * 4 + 0] = c0; W.thr[tt * 4 + 1] = c1; W.thr[tt * 4 + 2] = c2; W.thr[tt * 4 + 3] = c3;
     OG_THREADS_END
@@ -238,17 +271,35 @@ OG_HD void ot_pass(const OtWork& W, OtShared* sh, int cur, int rcur, int M, int 
     OG_THREADS_BEGIN(tt, TT)
         OG_CHUNK(M, tt, TT, lo, hi)
         int c[4] = {W.thr[tt * 4 + 0], W.thr[tt * 4 + 1], W.thr[tt * 4 + 2], W.thr[tt * 4 + 3]};
-        for (int p = lo; p < hi; ++p) {
-            const int i = knode[p];
-            if (!tmp[i].cand) continue;
-            if (p == nodes[i].start) { tmp[i].pre[0] = c[0]; tmp[i].pre[1] = c[1]; tmp[i].pre[2] = c[2]; tmp[i].pre[3] = c[3]; }
-            const int x = (int)(kxy[p] & 0xffffu), y = (int)(kxy[p] >> 16);
-            const int cl = (x >= tmp[i].sx ? 1 : 0) + (y >= tmp[i].sy ? 2 : 0);
-            c[cl]++;
-            if (p == nodes[i].start + nodes[i].count - 1) {
-                // pre[] of this node is written by the thread that owns the segment start (possibly another
-                // thread), so the end values are stashed in cnt and pre is subtracted after the sync
-                tmp[i].cnt[0] = c[0]; tmp[i].cnt[1] = c[1]; tmp[i].cnt[2] = c[2]; tmp[i].cnt[3] = c[3];
+        for (int p0 = lo; p0 < hi; p0 += kOtBatch) {
+            int ii[kOtBatch], ns[kOtBatch], ne[kOtBatch];
+            uint32_t kk[kOtBatch];
+            OtHead hh[kOtBatch];
+#pragma unroll
+            for (int u = 0; u < kOtBatch; ++u) {
+                const int p = p0 + u < hi ? p0 + u : hi - 1;
+                ii[u] = knode[p];
+                kk[u] = kxy[p];
+            }
+#pragma unroll
+            for (int u = 0; u < kOtBatch; ++u) {
+                hh[u] = ot_head(&tmp[ii[u]]);
+                ns[u] = nodes[ii[u]].start;
+                ne[u] = ns[u] + nodes[ii[u]].count - 1;
+            }
+#pragma unroll
+            for (int u = 0; u < kOtBatch; ++u) {
+                const int p = p0 + u, i = ii[u];
+                if (p >= hi || !hh[u].cand) continue;
+                if (p == ns[u]) { tmp[i].pre[0] = c[0]; tmp[i].pre[1] = c[1]; tmp[i].pre[2] = c[2]; tmp[i].pre[3] = c[3]; }
+                const int x = (int)(kk[u] & 0xffffu), y = (int)(kk[u] >> 16);
+                const int cl = (x >= hh[u].sx ? 1 : 0) + (y >= hh[u].sy ? 2 : 0);
+                c[cl]++;
+                if (p == ne[u]) {
+                    // pre[] of this node is written by the thread that owns the segment start (possibly another
+                    // thread), so the end values are stashed in cnt and pre is subtracted after the sync
+                    tmp[i].cnt[0] = c[0]; tmp[i].cnt[1] = c[1]; tmp[i].cnt[2] = c[2]; tmp[i].cnt[3] = c[3];
+                }
             }
         }
     OG_THREADS_END
@@ -361,7 +412,19 @@ OG_HD void ot_pass(const OtWork& W, OtShared* sh, int cur, int rcur, int M, int 
                 }
                 start += c;
             }
-            t.qbase = W.ordv[t.ord];
+            // move records for the key pass below: a key of class cl with running class count c goes to pre[cl] + c and
+            // belongs to list node cnt[cl] (pre / cnt have served their purpose)
+            {
+                const int q0 = W.ordv[t.ord];
+                int off = 0, before = 0;
+                for (int k = 0; k < 4; ++k) {
+                    const int c = t.cnt[k];
+                    t.pre[k] = nd.start + off - t.pre[k];
+                    t.cnt[k] = T - 1 - (q0 + before);
+                    off += c;
+                    before += c > 0;
+                }
+            }
         }
     }
     OG_SYNC();
@@ -375,29 +438,51 @@ OG_HD void ot_pass(const OtWork& W, OtShared* sh, int cur, int rcur, int M, int 
         OG_THREADS_BEGIN(tt, TT)
             OG_CHUNK(M, tt, TT, lo, hi)
             int c[4] = {W.thr[tt * 4 + 0], W.thr[tt * 4 + 1], W.thr[tt * 4 + 2], W.thr[tt * 4 + 3]};
-            for (int p = lo; p < hi; ++p) {
-                const int i = knode[p];
-                const OtTmp& t = tmp[i];
-                int np = p, nn;
-                if (t.cand) {
-                    const int x = (int)(kxy[p] & 0xffffu), y = (int)(kxy[p] >> 16);
-                    const int cl = (x >= t.sx ? 1 : 0) + (y >= t.sy ? 2 : 0);
-                    const int rank = c[cl] - t.pre[cl];
-                    c[cl]++;
-                    if (t.processed) {
-                        int off = 0, before = 0;
-                        for (int k = 0; k < cl; ++k) { off += t.cnt[k]; before += t.cnt[k] > 0; }
-                        np = nodes[i].start + off + rank;
-                        nn = T - 1 - (t.qbase + before);
-                    } else {
-                        nn = t.newpos;
-                    }
-                } else {
-                    nn = t.newpos;
+            for (int p0 = lo; p0 < hi; p0 += kOtBatch) {
+                int ii[kOtBatch], cls[kOtBatch], run[kOtBatch], np[kOtBatch], nn[kOtBatch];
+                uint32_t kk[kOtBatch];
+                uint8_t rr[kOtBatch];
+                OtHead hh[kOtBatch];
+#pragma unroll
+                for (int u = 0; u < kOtBatch; ++u) {
+                    const int p = p0 + u < hi ? p0 + u : hi - 1;
+                    ii[u] = knode[p];
+                    kk[u] = kxy[p];
+                    rr[u] = kr[p];
                 }
-                kxy2[np] = kxy[p];
-                kr2[np] = kr[p];
-                kn2[np] = (uint16_t)nn;
+#pragma unroll
+                for (int u = 0; u < kOtBatch; ++u) hh[u] = ot_head(&tmp[ii[u]]);
+                // running class counts first (sequential over the batch), then the dependent loads of all keys together
+#pragma unroll
+                for (int u = 0; u < kOtBatch; ++u) {
+                    cls[u] = -1;
+                    run[u] = 0;
+                    if (p0 + u < hi && hh[u].cand) {
+                        const int x = (int)(kk[u] & 0xffffu), y = (int)(kk[u] >> 16);
+                        const int cl = (x >= hh[u].sx ? 1 : 0) + (y >= hh[u].sy ? 2 : 0);
+                        cls[u] = cl;
+                        run[u] = c[cl];
+                        c[cl]++;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < kOtBatch; ++u) {
+                    const OtTmp& t = tmp[ii[u]];
+                    if (cls[u] >= 0 && hh[u].processed) {
+                        np[u] = t.pre[cls[u]] + run[u];
+                        nn[u] = t.cnt[cls[u]];
+                    } else {
+                        np[u] = p0 + u;
+                        nn[u] = t.newpos;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < kOtBatch; ++u) {
+                    if (p0 + u >= hi) continue;
+                    kxy2[np[u]] = kk[u];
+                    kr2[np[u]] = rr[u];
+                    kn2[np[u]] = (uint16_t)nn[u];
+                }
             }
         OG_THREADS_END
     }
