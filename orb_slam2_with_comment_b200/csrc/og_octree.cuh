@@ -90,7 +90,7 @@ OG_HD OtHead ot_head(const OtTmp* t) {
 #endif
     return h;
 }
-constexpr int kOtBatch = 4;   // keys a thread has in flight in the key loops (their loads are independent)
+constexpr int kOtBatch = 2;   // keys a thread has in flight in the key loops (measured on B200: 2, 3 and 4 are equal, 6 and 8 slower)
 
 // Block-shared scalars.
 struct OtShared {
