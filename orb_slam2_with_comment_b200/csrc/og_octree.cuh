@@ -271,8 +271,10 @@ OG_HD void ot_pass(const OtWork& W, OtShared* sh, int cur, int rcur, int M, int 
     OG_THREADS_BEGIN(tt, TT)
         OG_CHUNK(M, tt, TT, lo, hi)
         int c[4] = {W.thr[tt * 4 + 0], W.thr[tt * 4 + 1], W.thr[tt * 4 + 2], W.thr[tt * 4 + 3]};
+        // a node's segment starts / ends where the owner of the neighbouring key differs (no look-up of the node itself)
+        int prev = lo > 0 && lo < hi ? (int)knode[lo - 1] : -1;
         for (int p0 = lo; p0 < hi; p0 += kOtBatch) {
-            int ii[kOtBatch], ns[kOtBatch], ne[kOtBatch];
+            int ii[kOtBatch], nx[kOtBatch];
             uint32_t kk[kOtBatch];
             OtHead hh[kOtBatch];
 #pragma unroll
@@ -280,26 +282,27 @@ OG_HD void ot_pass(const OtWork& W, OtShared* sh, int cur, int rcur, int M, int 
                 const int p = p0 + u < hi ? p0 + u : hi - 1;
                 ii[u] = knode[p];
                 kk[u] = kxy[p];
+                nx[u] = p + 1 < M ? (int)knode[p + 1] : -1;
             }
 #pragma unroll
-            for (int u = 0; u < kOtBatch; ++u) {
-                hh[u] = ot_head(&tmp[ii[u]]);
-                ns[u] = nodes[ii[u]].start;
-                ne[u] = ns[u] + nodes[ii[u]].count - 1;
-            }
+            for (int u = 0; u < kOtBatch; ++u) hh[u] = ot_head(&tmp[ii[u]]);
 #pragma unroll
             for (int u = 0; u < kOtBatch; ++u) {
                 const int p = p0 + u, i = ii[u];
-                if (p >= hi || !hh[u].cand) continue;
-                if (p == ns[u]) { tmp[i].pre[0] = c[0]; tmp[i].pre[1] = c[1]; tmp[i].pre[2] = c[2]; tmp[i].pre[3] = c[3]; }
-                const int x = (int)(kk[u] & 0xffffu), y = (int)(kk[u] >> 16);
-                const int cl = (x >= hh[u].sx ? 1 : 0) + (y >= hh[u].sy ? 2 : 0);
-                c[cl]++;
-                if (p == ne[u]) {
-                    // pre[] of this node is written by the thread that owns the segment start (possibly another
-                    // thread), so the end values are stashed in cnt and pre is subtracted after the sync
-                    tmp[i].cnt[0] = c[0]; tmp[i].cnt[1] = c[1]; tmp[i].cnt[2] = c[2]; tmp[i].cnt[3] = c[3];
+                if (p >= hi) continue;
+                const int nxt = nx[u];
+                if (hh[u].cand) {
+                    if (i != prev) { tmp[i].pre[0] = c[0]; tmp[i].pre[1] = c[1]; tmp[i].pre[2] = c[2]; tmp[i].pre[3] = c[3]; }
+                    const int x = (int)(kk[u] & 0xffffu), y = (int)(kk[u] >> 16);
+                    const int cl = (x >= hh[u].sx ? 1 : 0) + (y >= hh[u].sy ? 2 : 0);
+                    c[cl]++;
+                    if (i != nxt) {
+                        // pre[] of this node is written by the thread that owns the segment start (possibly another
+                        // thread), so the end values are stashed in cnt and pre is subtracted after the sync
+                        tmp[i].cnt[0] = c[0]; tmp[i].cnt[1] = c[1]; tmp[i].cnt[2] = c[2]; tmp[i].cnt[3] = c[3];
+                    }
                 }
+                prev = i;
             }
         }
     OG_THREADS_END
