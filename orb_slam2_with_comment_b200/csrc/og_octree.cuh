@@ -324,11 +324,14 @@ OG_HD void ot_pass(const OtWork& W, OtShared* sh, int cur, int rcur, int M, int 
     } else {
         m = nR;
         const int32_t* R = W.R[rcur];
+        int32_t* sz = W.ordv2;   // sizes of the expandable nodes, gathered once: the ranking below reads them nR times each
+        OG_FOR(j, nR) sz[j] = nodes[R[j]].count;
+        OG_SYNC();
         OG_FOR(j, nR) {
-            const int cj = nodes[R[j]].count;
+            const int cj = sz[j];
             int r = 0;
             for (int j2 = 0; j2 < nR; ++j2) {
-                const int c2 = nodes[R[j2]].count;
+                const int c2 = sz[j2];
                 r += (c2 > cj) || (c2 == cj && j2 > j);
             }
             tmp[R[j]].ord = r;
