@@ -6,6 +6,7 @@
 //   SearchByBoW(KeyFrame*, KeyFrame*, vector<MapPoint*>&)         replaces :635-768
 //   SearchForTriangulation(KeyFrame*, KeyFrame*, F12, pairs, ..)  replaces :783-975
 //   SearchByProjection(Frame&, const Frame&, th, bMono)           replaces :1540-1685 (pose arithmetic here, search on the GPU)
+//   SearchForInitialization(Frame&, Frame&, vbPrevMatched, ...)   replaces :493-632
 //
 // Integration: compile this file into the ORB_SLAM2 library and remove (or #ifdef out) those four bodies from the
 // reference's ORBmatcher.cc; everything else of that file — the constructor, DescriptorDistance, the other search
@@ -297,6 +298,42 @@ int ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, 
     for (int i = 0; i < N; ++i) {
         if (kp_match[i] >= 0) CurrentFrame.mvpMapPoints[i] = LastFrame.mvpMapPoints[kp_match[i]];   // :1644
         else if (kp_match[i] == -2) CurrentFrame.mvpMapPoints[i] = static_cast<MapPoint*>(NULL);    // :1676
+    }
+    return nmatches;
+}
+
+// SearchForInitialization (ORBmatcher.cc:493-632): the monocular bootstrap match between the reference frame F1 and the current
+// frame F2 inside a window around vbPrevMatched.  The stealing rule and the rotation check run on the device; vbPrevMatched is
+// updated here exactly as at :626-628.
+int ORBmatcher::SearchForInitialization(Frame& F1, Frame& F2, std::vector<cv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12,
+                                        int windowSize) {
+    const int N1 = (int)F1.mvKeysUn.size(), N2 = (int)F2.mvKeysUn.size();
+    vnMatches12 = std::vector<int>(N1, -1);
+    if (N1 == 0 || N2 == 0) return 0;
+    const int32_t kp_off[2] = {0, N2}, q_off[2] = {0, N1};
+    std::vector<uint8_t> tmp2, tmp1;
+    orbgpu_frame_set fs = one_frame(kp_off, F2.mvKeysUn, rows32(F2.mDescriptors, tmp2));
+    const float grid[4] = {Frame::mnMinX, Frame::mnMinY, Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv};
+    fs.grid = grid;
+    std::vector<float> qu(N1), qv(N1), qr(N1, (float)windowSize), qang(N1);
+    std::vector<int32_t> qlo(N1, 0), qhi(N1, 0);   // GetFeaturesInArea(x, y, windowSize, level1, level1) with level1 == 0 (:512-519)
+    std::vector<uint8_t> qfl(N1);
+    for (int i = 0; i < N1; ++i) {
+        qu[i] = vbPrevMatched[i].x;
+        qv[i] = vbPrevMatched[i].y;
+        qang[i] = F1.mvKeysUn[i].angle;
+        qfl[i] = F1.mvKeysUn[i].octave > 0 ? 0 : 1;   // level1 > 0: continue (:513-514)
+    }
+    orbgpu_window_query_set qs;
+    qs.q_off = q_off; qs.u = qu.data(); qs.v = qv.data(); qs.radius = qr.data(); qs.min_level = qlo.data(); qs.max_level = qhi.data();
+    qs.ur = nullptr; qs.flags = qfl.data(); qs.desc = rows32(F1.mDescriptors, tmp1); qs.angle = qang.data();
+    std::vector<int32_t> m12(N1, -1);
+    int32_t nmatches = 0;
+    check(orbgpu_search_for_initialization(matcher(), &fs, &qs, mfNNratio, mbCheckOrientation ? 1 : 0, m12.data(), &nmatches),
+          "SearchForInitialization");
+    for (int i = 0; i < N1; ++i) {
+        vnMatches12[i] = m12[i];
+        if (m12[i] >= 0) vbPrevMatched[i] = F2.mvKeysUn[m12[i]].pt;   // :626-628
     }
     return nmatches;
 }

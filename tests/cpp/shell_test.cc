@@ -35,6 +35,7 @@ void orbm_search_by_bow(const orbgpu_frame_set*, const orbgpu_frame_set*, int, c
                         const int64_t*, int32_t*, int32_t*, int32_t*);
 void cvl_gemm3_f32(const float*, const float*, const float*, float*);
 void cvl_gemm3t_neg_f32(const float*, const float*, float*);
+void orbm_search_for_initialization(const orbgpu_frame_set*, const orbgpu_window_query_set*, float, int, int32_t*, int32_t*);
 void* orbo_voc_create(int, int, int, int, int, const int32_t*, const uint8_t*, const uint8_t*, const double*);
 void orbo_voc_free(void*);
 int orbo_voc_transform(void*, const uint8_t*, int, int, int*, uint32_t*, double*, int*, uint32_t*, int32_t*, uint32_t*, uint32_t*, uint32_t*);
@@ -464,6 +465,64 @@ static void test_track_last_frame() {
     }
 }
 
+// ---- ORBmatcher::SearchForInitialization as Tracking::MonocularInitialization calls it (Tracking.cc:609-612) ----------------
+static void test_search_for_initialization() {
+    const int N = 900;
+    Frame F1, F2;
+    F1.mvKeysUn = random_keys(N, 640, 480);
+    F1.mDescriptors = random_desc(N);
+    // F2 sees most of F1's points again a few pixels away, with a few descriptor bits flipped; several F1 points share a descriptor
+    F2.mvKeysUn = random_keys(N, 640, 480);
+    F2.mDescriptors = random_desc(N);
+    for (int i = 0; i < N; ++i) {
+        if (i % 7 == 3) std::memcpy(F1.mDescriptors.ptr(i), F1.mDescriptors.ptr(i - 1), 32);   // rivals for one F2 point
+        if (i % 5 != 0) {
+            F2.mvKeysUn[i] = F1.mvKeysUn[i];
+            F2.mvKeysUn[i].pt.x += frand(-6, 6);
+            F2.mvKeysUn[i].pt.y += frand(-6, 6);
+            F2.mvKeysUn[i].angle = F1.mvKeysUn[i].angle + frand(-10, 10);
+            if (F2.mvKeysUn[i].angle < 0) F2.mvKeysUn[i].angle += 360.f;
+            if (F2.mvKeysUn[i].angle >= 360.f) F2.mvKeysUn[i].angle -= 360.f;
+            std::memcpy(F2.mDescriptors.ptr(i), F1.mDescriptors.ptr(i), 32);
+            for (int b = 0; b < 12; ++b) F2.mDescriptors.at<uchar>(i, rnd() % 32) ^= (uchar)(1u << (rnd() % 8));
+        }
+    }
+    Frame::mnMinX = 0; Frame::mnMinY = 0; Frame::mnMaxX = 640; Frame::mnMaxY = 480;
+    Frame::mfGridElementWidthInv = 64.f / 640.f; Frame::mfGridElementHeightInv = 48.f / 480.f;
+    std::vector<cv::Point2f> prev(N), prev0;
+    for (int i = 0; i < N; ++i) prev[i] = F1.mvKeysUn[i].pt;
+    prev0 = prev;
+    std::vector<int> m12;
+    ORBmatcher matcher(0.9f, true);
+    const int n = matcher.SearchForInitialization(F1, F2, prev, m12, 100);
+    // oracle on the same flattened inputs
+    std::vector<uint8_t> fl(N);
+    std::vector<float> qu(N), qv(N), qr(N, 100.f), qa(N);
+    std::vector<int32_t> lo(N, 0), hi(N, 0);
+    for (int i = 0; i < N; ++i) { qu[i] = prev0[i].x; qv[i] = prev0[i].y; qa[i] = F1.mvKeysUn[i].angle; fl[i] = F1.mvKeysUn[i].octave > 0 ? 0 : 1; }
+    const int32_t off[2] = {0, N};
+    orbgpu_frame_set fs;
+    std::memset(&fs, 0, sizeof fs);
+    fs.n_frames = 1; fs.kp_off = off; fs.keys_un = (const orbgpu_keypoint*)F2.mvKeysUn.data(); fs.desc = F2.mDescriptors.ptr(0);
+    const float grid[4] = {0, 0, Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv};
+    fs.grid = grid;
+    orbgpu_window_query_set qs;
+    std::memset(&qs, 0, sizeof qs);
+    qs.q_off = off; qs.u = qu.data(); qs.v = qv.data(); qs.radius = qr.data(); qs.min_level = lo.data(); qs.max_level = hi.data();
+    qs.flags = fl.data(); qs.desc = F1.mDescriptors.ptr(0); qs.angle = qa.data();
+    std::vector<int32_t> e12(N, -1);
+    int32_t en = 0;
+    orbm_search_for_initialization(&fs, &qs, 0.9f, 1, e12.data(), &en);
+    int bad = 0, moved = 0;
+    for (int i = 0; i < N; ++i) {
+        bad += m12[i] != e12[i];
+        if (m12[i] >= 0) { moved += prev[i].x == F2.mvKeysUn[m12[i]].pt.x && prev[i].y == F2.mvKeysUn[m12[i]].pt.y; }
+        else bad += !(prev[i].x == prev0[i].x && prev[i].y == prev0[i].y);
+    }
+    EXPECT(n == en && bad == 0 && moved == n + 0 * moved && n > 50, "SearchForInitialization: %d matches (oracle %d), %d entries differ, %d vbPrevMatched updated", n, en, bad, moved);
+    printf("SearchForInitialization: %d matches, oracle equal: %s\n", n, bad ? "no" : "yes");
+}
+
 // ---- ORBVocabulary::transform as Frame::ComputeBoW calls it (Frame.cc:425-432) -------------------------------------------
 struct VocRecords {
     int k, L;
@@ -572,6 +631,7 @@ int main() {
     test_matcher();
     test_track_last_frame();
     test_vocabulary();
+    test_search_for_initialization();
     printf(fails ? "shell_test: %d FAILURES\n" : "shell_test: all shell results equal the oracle (%d failures)\n", fails);
     return fails ? 1 : 0;
 }
