@@ -749,32 +749,43 @@ __global__ void __launch_bounds__(kBlurThreads) k_blur_tma(const __grid_constant
     const uint32_t KLO = OG_G0 | (OG_G1 << 8) | (OG_G2 << 16) | (OG_G3 << 24), KHI = OG_G2 | (OG_G1 << 8) | (OG_G0 << 16);
     uint8_t* dst = level_ptr(P.blur, L, frame) + (long long)(kEdge + ybase) * L.pitch + kXPad + x;
     const int nrows = min(32, L.h - ybase);
-    uint32_t a[7][4];
+    // Vertical pass on row PAIRS: a horizontal sum is at most 255 * 256 < 2^16, so two vertically adjacent sums share a word
+    // (pr[k] = row k | row k+1 << 16) and one DP2A applies two taps: 3 DP2A + 1 IMAD per pixel instead of 7 multiply-adds.
+    uint32_t pr[6][4], hprev[4] = {0u, 0u, 0u, 0u};
+    const uint32_t K01 = OG_G0 | (OG_G1 << 8), K23 = OG_G2 | (OG_G3 << 8), K21 = OG_G2 | (OG_G1 << 8);
 #pragma unroll
     for (int i = 0; i < 38; ++i) {
         // horizontal pass of tile row 32*band + i
         const uint32_t pw = T[i * 64 - 1], cw = T[i * 64], nw = T[i * 64 + 1];
         const uint32_t m3 = __funnelshift_r(pw, cw, 8), m2 = __funnelshift_r(pw, cw, 16), m1 = __funnelshift_r(pw, cw, 24);
         const uint32_t p1 = __funnelshift_r(cw, nw, 8), p2 = __funnelshift_r(cw, nw, 16), p3 = __funnelshift_r(cw, nw, 24);
-        uint32_t* h = a[i % 7];
+        uint32_t h[4];
         h[0] = __dp4a(m3, KLO, __dp4a(p1, KHI, 0u));
         h[1] = __dp4a(m2, KLO, __dp4a(p2, KHI, 0u));
         h[2] = __dp4a(m1, KLO, __dp4a(p3, KHI, 0u));
         h[3] = __dp4a(cw, KLO, __dp4a(nw, KHI, 0u));
+        if (i >= 1) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) pr[(i - 1) % 6][j] = hprev[j] | (h[j] << 16);   // rows i-1, i
+        }
         if (i >= 6) {
-            const int r = i - 6;   // output row of the band; window rows r..r+6 live in a[(r+k) % 7]
+            const int r = i - 6;   // output row of the band: window rows r..r+6 = pairs r, r+2, r+4 and row r+6 (= h)
             if (r < nrows) {
                 uint32_t o[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const uint32_t acc = OG_G0 * (a[(r + 0) % 7][j] + a[(r + 6) % 7][j]) + OG_G1 * (a[(r + 1) % 7][j] + a[(r + 5) % 7][j]) +
-                                         OG_G2 * (a[(r + 2) % 7][j] + a[(r + 4) % 7][j]) + OG_G3 * a[(r + 3) % 7][j] + 32768u;
+                    uint32_t acc = OG_G0 * h[j] + 32768u;
+                    acc = __dp2a_lo(pr[r % 6][j], K01, acc);
+                    acc = __dp2a_lo(pr[(r + 2) % 6][j], K23, acc);
+                    acc = __dp2a_lo(pr[(r + 4) % 6][j], K21, acc);
                     o[j] = acc;   // result byte = bits 16..23
                 }
                 const uint32_t lo = __byte_perm(o[0], o[1], 0x0062), hi = __byte_perm(o[2], o[3], 0x0062);
                 *reinterpret_cast<uint32_t*>(dst + (long long)r * L.pitch) = __byte_perm(lo, hi, 0x5410);
             }
         }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) hprev[j] = h[j];
     }
 }
 
