@@ -7,13 +7,16 @@
 //   SearchForTriangulation(KeyFrame*, KeyFrame*, F12, pairs, ..)  replaces :783-975
 //   SearchByProjection(Frame&, const Frame&, th, bMono)           replaces :1540-1685 (pose arithmetic here, search on the GPU)
 //   SearchForInitialization(Frame&, Frame&, vbPrevMatched, ...)   replaces :493-632
+//   SearchByProjection(Frame&, KeyFrame*, set<MapPoint*>&, th, d)  replaces :1711-1849 (Relocalization)
 //
 // Integration: compile this file into the ORB_SLAM2 library and remove (or #ifdef out) those four bodies from the
 // reference's ORBmatcher.cc; everything else of that file — the constructor, DescriptorDistance, the other search
 // functions — stays the reference's CPU code.  Each function flattens the Frame / KeyFrame / MapPoint
 // members the reference body reads into the views of orbgpu.h, makes ONE call, and writes the result back into the
 // caller's containers exactly where the reference does.  No distance is computed on the host.
+#include <cmath>
 #include <cstring>
+#include <set>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -298,6 +301,73 @@ int ORBmatcher::SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, 
     for (int i = 0; i < N; ++i) {
         if (kp_match[i] >= 0) CurrentFrame.mvpMapPoints[i] = LastFrame.mvpMapPoints[kp_match[i]];   // :1644
         else if (kp_match[i] == -2) CurrentFrame.mvpMapPoints[i] = static_cast<MapPoint*>(NULL);    // :1676
+    }
+    return nmatches;
+}
+
+// SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) (ORBmatcher.cc:1711-1849): the projection search of
+// Tracking::Relocalization.  The per-map-point pose arithmetic (:1713-1757) stays here, in cv::gemm's evaluation order; the
+// windowed search, the "key point already holds a MapPoint" rule (:1776-1777) and the rotation check run on the GPU.
+int ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const std::set<MapPoint*>& sAlreadyFound, const float th, const int ORBdist) {
+    const int N = (int)CurrentFrame.mvKeysUn.size();
+    const std::vector<MapPoint*> vpMPs = pKF->GetMapPointMatches();
+    const int NQ = (int)vpMPs.size();
+    if (N == 0 || NQ == 0) return 0;
+    // Ow = -Rcw^T * tcw (a transposed operand takes cv::gemm's general path: double accumulation)
+    float Ow[3];
+    for (int i = 0; i < 3; ++i) {
+        double acc = 0.0;
+        for (int j = 0; j < 3; ++j) acc += (double)CurrentFrame.mTcw.at<float>(j, i) * (double)CurrentFrame.mTcw.at<float>(j, 3);
+        Ow[i] = (float)(-acc);
+    }
+    const int32_t kp_off[2] = {0, N}, q_off[2] = {0, NQ};
+    std::vector<uint8_t> tmp, kflags(N, 0);
+    orbgpu_frame_set fs = one_frame(kp_off, CurrentFrame.mvKeysUn, rows32(CurrentFrame.mDescriptors, tmp));
+    for (int i = 0; i < N; ++i)
+        if (CurrentFrame.mvpMapPoints[i]) kflags[i] = 2;   // any MapPoint blocks the key point (:1776-1777)
+    fs.kp_flags = kflags.data();
+    const float grid[4] = {Frame::mnMinX, Frame::mnMinY, Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv};
+    fs.grid = grid;
+    std::vector<float> qu(NQ), qv(NQ), qr(NQ), qang(NQ);
+    std::vector<int32_t> qlo(NQ), qhi(NQ);
+    std::vector<uint8_t> qfl(NQ, 0), qdesc((size_t)NQ * 32, 0);
+    for (int i = 0; i < NQ; ++i) {
+        MapPoint* pMP = vpMPs[i];
+        if (!pMP || pMP->isBad() || sAlreadyFound.count(pMP)) continue;   // :1727-1731
+        const cv::Mat x3Dw = pMP->GetWorldPos();
+        const float xw[3] = {x3Dw.at<float>(0, 0), x3Dw.at<float>(1, 0), x3Dw.at<float>(2, 0)};
+        float xc[3];
+        rt_apply(CurrentFrame.mTcw, xw, xc);                              // :1735
+        const float invzc = 1.0 / xc[2];
+        const float u = Frame::fx * xc[0] * invzc + Frame::cx;
+        const float v = Frame::fy * xc[1] * invzc + Frame::cy;
+        if (u < Frame::mnMinX || u > Frame::mnMaxX) continue;
+        if (v < Frame::mnMinY || v > Frame::mnMaxY) continue;
+        // dist3D = cv::norm(x3Dw - Ow): float differences, squares summed in double (:1752-1753)
+        double s2 = 0.0;
+        for (int k = 0; k < 3; ++k) { const float d = xw[k] - Ow[k]; s2 += (double)d * (double)d; }
+        float dist3D = (float)std::sqrt(s2);
+        if (dist3D < pMP->GetMinDistanceInvariance() || dist3D > pMP->GetMaxDistanceInvariance()) continue;
+        const int nPredictedLevel = pMP->PredictScale(dist3D, &CurrentFrame);
+        qu[i] = u; qv[i] = v;
+        qr[i] = th * CurrentFrame.mvScaleFactors[nPredictedLevel];       // :1764
+        qlo[i] = nPredictedLevel - 1; qhi[i] = nPredictedLevel + 1;
+        qang[i] = pKF->mvKeysUn[i].angle;
+        qfl[i] = 1;
+        const cv::Mat d = pMP->GetDescriptor();
+        std::memcpy(&qdesc[(size_t)i * 32], d.ptr(0), 32);
+    }
+    orbgpu_window_query_set qs;
+    qs.q_off = q_off; qs.u = qu.data(); qs.v = qv.data(); qs.radius = qr.data(); qs.min_level = qlo.data(); qs.max_level = qhi.data();
+    qs.ur = nullptr; qs.flags = qfl.data(); qs.desc = qdesc.data(); qs.angle = qang.data();
+    std::vector<int32_t> kp_match(N, -1);
+    int32_t nmatches = 0;
+    check(orbgpu_search_windowed(matcher(), &fs, &qs, ORBdist, /*skip_any_mappoint*/ 1, mbCheckOrientation ? 1 : 0, kp_match.data(), nullptr,
+                                 nullptr, &nmatches),
+          "SearchByProjection(Frame, KeyFrame)");
+    for (int i = 0; i < N; ++i) {
+        if (kp_match[i] >= 0) CurrentFrame.mvpMapPoints[i] = vpMPs[kp_match[i]];                   // :1795
+        else if (kp_match[i] == -2) CurrentFrame.mvpMapPoints[i] = static_cast<MapPoint*>(NULL);    // :1841
     }
     return nmatches;
 }

@@ -23,11 +23,15 @@ class BowVector : public std::map<WordId, WordValue> {};   // BowVector.h:58-60
 namespace ORB_SLAM2 {
 
 class KeyFrame;
+class Frame;
 
 class MapPoint {
 public:
     MapPoint() : mTrackProjX(0), mTrackProjY(0), mTrackProjXR(0), mbTrackInView(false), mnTrackScaleLevel(0), mTrackViewCos(0),
-                 mbBad(false), nObs(0) {}
+                 mbBad(false), nObs(0), mfMinDistance(0), mfMaxDistance(0) {}
+    float GetMinDistanceInvariance() { return 0.8f * mfMinDistance; }   // MapPoint.cc:392-396
+    float GetMaxDistanceInvariance() { return 1.2f * mfMaxDistance; }   // MapPoint.cc:398-402
+    inline int PredictScale(const float& currentDist, Frame* pF);       // MapPoint.cc:421-436
     int Observations() { return nObs; }
     bool isBad() { return mbBad; }
     cv::Mat GetDescriptor() { return mDescriptor.clone(); }
@@ -41,6 +45,7 @@ public:
     // stub state
     bool mbBad;
     int nObs;
+    float mfMinDistance, mfMaxDistance;
     cv::Mat mDescriptor;
     cv::Mat mWorldPos;   // 3x1 CV_32F
 };
@@ -56,12 +61,22 @@ public:
     std::vector<MapPoint*> mvpMapPoints;
     std::vector<bool> mvbOutlier;
     std::vector<float> mvScaleFactors;
+    float mfLogScaleFactor;
+    int mnScaleLevels;
     cv::Mat mTcw;        // 4x4 CV_32F
     float mb, mbf;
     static float fx, fy, cx, cy;
     static float mfGridElementWidthInv, mfGridElementHeightInv;
     static float mnMinX, mnMaxX, mnMinY, mnMaxY;
 };
+
+inline int MapPoint::PredictScale(const float& currentDist, Frame* pF) {
+    const float ratio = mfMaxDistance / currentDist;
+    int nScale = (int)std::ceil(std::log(ratio) / pF->mfLogScaleFactor);
+    if (nScale < 0) nScale = 0;
+    else if (nScale >= pF->mnScaleLevels) nScale = pF->mnScaleLevels - 1;
+    return nScale;
+}
 
 class KeyFrame {
 public:

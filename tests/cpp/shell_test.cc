@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <set>
 #include <stdexcept>
 #include <string>
 #include <thread>
@@ -35,6 +36,7 @@ void orbm_search_by_bow(const orbgpu_frame_set*, const orbgpu_frame_set*, int, c
                         const int64_t*, int32_t*, int32_t*, int32_t*);
 void cvl_gemm3_f32(const float*, const float*, const float*, float*);
 void cvl_gemm3t_neg_f32(const float*, const float*, float*);
+double cvl_norm3_f32(const float*);
 void orbm_search_for_initialization(const orbgpu_frame_set*, const orbgpu_window_query_set*, float, int, int32_t*, int32_t*);
 void* orbo_voc_create(int, int, int, int, int, const int32_t*, const uint8_t*, const uint8_t*, const double*);
 void orbo_voc_free(void*);
@@ -465,6 +467,113 @@ static void test_track_last_frame() {
     }
 }
 
+// --- SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist): Relocalization's matcher (Tracking.cc:1435-1475) ---
+static void test_relocalization_search() {
+    const int W = 640, H = 480, N = 1000;
+    Frame::fx = 517.3f; Frame::fy = 516.5f; Frame::cx = 318.6f; Frame::cy = 255.3f;
+    Frame::mnMinX = 0; Frame::mnMinY = 0; Frame::mnMaxX = W; Frame::mnMaxY = H;
+    Frame::mfGridElementWidthInv = 64.0f / W; Frame::mfGridElementHeightInv = 48.0f / H;
+    std::vector<cv::KeyPoint> kkeys = random_keys(N, W, H);
+    cv::Mat kdesc = random_desc(N);
+    KeyFrame kf(kkeys, std::vector<float>(N, -1.f), kdesc, g_sf, g_s2, Frame::fx, Frame::fy, Frame::cx, Frame::cy);
+    Frame cur;
+    cur.N = N;
+    cur.mvScaleFactors = g_sf;
+    cur.mfLogScaleFactor = std::log(1.2f);
+    cur.mnScaleLevels = 8;
+    cur.mTcw = cv::Mat(4, 4, CV_32FC1);
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) cur.mTcw.at<float>(i, j) = i == j;
+    const float ang = -0.015f;
+    cur.mTcw.at<float>(0, 0) = std::cos(ang); cur.mTcw.at<float>(0, 2) = std::sin(ang); cur.mTcw.at<float>(2, 0) = -std::sin(ang); cur.mTcw.at<float>(2, 2) = std::cos(ang);
+    cur.mTcw.at<float>(0, 3) = -0.04f; cur.mTcw.at<float>(1, 3) = 0.01f; cur.mTcw.at<float>(2, 3) = 0.05f;
+    float Rc[9], tcv[3], Ow[3];
+    for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) Rc[3 * i + j] = cur.mTcw.at<float>(i, j); tcv[i] = cur.mTcw.at<float>(i, 3); }
+    cvl_gemm3t_neg_f32(Rc, tcv, Ow);
+    // the key frame's map points: back-projection of its key points (key frame at the origin), distance ranges around the octave
+    std::vector<MapPoint> pool(N);
+    std::set<MapPoint*> found;
+    for (int i = 0; i < N; ++i) {
+        if (rnd() % 10 >= 8) continue;
+        MapPoint& p = pool[i];
+        const float z = frand(2.f, 12.f);
+        p.mWorldPos = cv::Mat(3, 1, CV_32FC1);
+        p.mWorldPos.at<float>(0, 0) = (kkeys[i].pt.x - Frame::cx) / Frame::fx * z;
+        p.mWorldPos.at<float>(1, 0) = (kkeys[i].pt.y - Frame::cy) / Frame::fy * z;
+        p.mWorldPos.at<float>(2, 0) = z;
+        const float d = std::sqrt(p.mWorldPos.at<float>(0, 0) * p.mWorldPos.at<float>(0, 0) + p.mWorldPos.at<float>(1, 0) * p.mWorldPos.at<float>(1, 0) + z * z);
+        p.mfMaxDistance = d * std::pow(1.2f, (float)kkeys[i].octave - 0.5f) * (rnd() % 25 == 0 ? 40.f : 1.f);   // a few out of range
+        p.mfMinDistance = p.mfMaxDistance / std::pow(1.2f, 7.f);
+        p.mDescriptor = cv::Mat(1, 32, CV_8UC1);
+        std::memcpy(p.mDescriptor.ptr(0), kdesc.ptr(i), 32);
+        p.mbBad = rnd() % 30 == 0;
+        kf.mvpMapPoints[i] = &p;
+        if (rnd() % 12 == 0) found.insert(&p);
+    }
+    // current frame: the same points seen from the new pose (+ noise), plus unrelated key points; some key points already hold a MapPoint
+    cur.mvKeys = random_keys(N, W, H);
+    cur.mDescriptors = random_desc(N);
+    for (int i = 0; i < N; ++i) {
+        MapPoint* p = kf.mvpMapPoints[i];
+        if (!p || rnd() % 10 >= 8) continue;
+        float xc[3];
+        cvl_gemm3_f32(Rc, p->mWorldPos.ptr<float>(0), tcv, xc);
+        if (xc[2] <= 0.1f) continue;
+        const int j = rnd() % N;
+        cur.mvKeys[j] = kkeys[i];
+        cur.mvKeys[j].pt.x = Frame::fx * xc[0] / xc[2] + Frame::cx + frand(-2, 2);
+        cur.mvKeys[j].pt.y = Frame::fy * xc[1] / xc[2] + Frame::cy + frand(-2, 2);
+        cur.mvKeys[j].angle = std::fmod(kkeys[i].angle + frand(-12, 12) + 360.f, 360.f);
+        std::memcpy(cur.mDescriptors.ptr(j), kdesc.ptr(i), 32);
+        flip(cur.mDescriptors.ptr(j), 10);
+    }
+    cur.mvKeysUn = cur.mvKeys;
+    std::vector<MapPoint> held(N);
+    cur.mvpMapPoints.assign(N, nullptr);
+    for (int i = 0; i < N; ++i) if (rnd() % 12 == 0) cur.mvpMapPoints[i] = &held[i];
+    const float th = 10.f;
+    const int ORBdist = 100;
+
+    // ---- oracle: the same projection arithmetic, then the windowed search port (any MapPoint blocks a key point)
+    Flat a(cur.mvKeysUn, cur.mDescriptors, nullptr);
+    for (int i = 0; i < N; ++i) a.flags[i] = cur.mvpMapPoints[i] ? 2 : 0;
+    const float grid[4] = {0, 0, Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv};
+    a.s.grid = grid;
+    int32_t q_off[2] = {0, N};
+    std::vector<float> qu(N), qv(N), qr(N), qa(N);
+    std::vector<int32_t> lo(N), hi(N);
+    std::vector<uint8_t> qf(N, 0), qd((size_t)N * 32, 0);
+    int live = 0;
+    for (int i = 0; i < N; ++i) {
+        MapPoint* p = kf.mvpMapPoints[i];
+        if (!p || p->mbBad || found.count(p)) continue;
+        float xc[3];
+        cvl_gemm3_f32(Rc, p->mWorldPos.ptr<float>(0), tcv, xc);
+        const float invzc = 1.0 / xc[2];
+        const float u = Frame::fx * xc[0] * invzc + Frame::cx, v = Frame::fy * xc[1] * invzc + Frame::cy;
+        if (u < 0 || u > W || v < 0 || v > H) continue;
+        const float po[3] = {p->mWorldPos.at<float>(0, 0) - Ow[0], p->mWorldPos.at<float>(1, 0) - Ow[1], p->mWorldPos.at<float>(2, 0) - Ow[2]};
+        const float dist3D = (float)cvl_norm3_f32(po);
+        if (dist3D < 0.8f * p->mfMinDistance || dist3D > 1.2f * p->mfMaxDistance) continue;
+        const int lvl = p->PredictScale(dist3D, &cur);
+        qu[i] = u; qv[i] = v; qr[i] = th * g_sf[lvl]; qa[i] = kkeys[i].angle;
+        lo[i] = lvl - 1; hi[i] = lvl + 1;
+        qf[i] = 1;
+        ++live;
+        std::memcpy(&qd[(size_t)i * 32], p->mDescriptor.ptr(0), 32);
+    }
+    orbgpu_window_query_set qs = {q_off, qu.data(), qv.data(), qr.data(), lo.data(), hi.data(), nullptr, qf.data(), qd.data(), qa.data()};
+    std::vector<int32_t> kpm(N, -1); int32_t nm = 0;
+    orbm_search_windowed(&a.s, &qs, ORBdist, 1, 1, kpm.data(), nullptr, nullptr, &nm);
+    std::vector<MapPoint*> exp = cur.mvpMapPoints;
+    for (int i = 0; i < N; ++i) { if (kpm[i] >= 0) exp[i] = kf.mvpMapPoints[kpm[i]]; else if (kpm[i] == -2) exp[i] = nullptr; }
+
+    ORBmatcher m(0.9f, true);
+    const int n = m.SearchByProjection(cur, &kf, found, th, ORBdist);
+    EXPECT(n == nm && nm > 100, "SearchByProjection(Frame,KeyFrame): %d matches vs oracle %d (%d live queries)", n, nm, live);
+    EXPECT(cur.mvpMapPoints == exp, "SearchByProjection(Frame,KeyFrame): mvpMapPoints differ");
+    printf("SearchByProjection(Frame,KeyFrame): %d matches of %d live queries, oracle equal: %s\n", n, live, cur.mvpMapPoints == exp ? "yes" : "no");
+}
+
 // ---- ORBmatcher::SearchForInitialization as Tracking::MonocularInitialization calls it (Tracking.cc:609-612) ----------------
 static void test_search_for_initialization() {
     const int N = 900;
@@ -632,6 +741,7 @@ int main() {
     test_track_last_frame();
     test_vocabulary();
     test_search_for_initialization();
+    test_relocalization_search();
     printf(fails ? "shell_test: %d FAILURES\n" : "shell_test: all shell results equal the oracle (%d failures)\n", fails);
     return fails ? 1 : 0;
 }
