@@ -8,6 +8,7 @@
 //   SearchByProjection(Frame&, const Frame&, th, bMono)           replaces :1540-1685 (pose arithmetic here, search on the GPU)
 //   SearchForInitialization(Frame&, Frame&, vbPrevMatched, ...)   replaces :493-632
 //   SearchByProjection(Frame&, KeyFrame*, set<MapPoint*>&, th, d)  replaces :1711-1849 (Relocalization)
+//   Fuse(KeyFrame*, const vector<MapPoint*>&, th)                  replaces :977-1137 (search on the GPU, map updates here)
 //
 // Integration: compile this file into the ORB_SLAM2 library and remove (or #ifdef out) those four bodies from the
 // reference's ORBmatcher.cc; everything else of that file — the constructor, DescriptorDistance, the other search
@@ -370,6 +371,90 @@ int ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, const std
         else if (kp_match[i] == -2) CurrentFrame.mvpMapPoints[i] = static_cast<MapPoint*>(NULL);    // :1841
     }
     return nmatches;
+}
+
+// Fuse(pKF, vpMapPoints, th) (ORBmatcher.cc:977-1137, LocalMapping::SearchInNeighbors): project the map points into the key
+// frame, look for the best key point in a window with the chi-square gate — that search runs on the GPU for all points at
+// once (orbgpu_search_window_best: queries are independent, candidates are not filtered by the MapPoints they hold) — then
+// apply Replace / AddObservation in vector order here, with isBad() / IsInKeyFrame() evaluated at each point's turn exactly
+// as the reference's loop does (an earlier Replace can turn a later point bad).
+int ORBmatcher::Fuse(KeyFrame* pKF, const std::vector<MapPoint*>& vpMapPoints, const float th) {
+    const int N = (int)pKF->mvKeysUn.size(), NQ = (int)vpMapPoints.size();
+    if (N == 0 || NQ == 0) return 0;
+    const cv::Mat Rcw = pKF->GetRotation(), tcw = pKF->GetTranslation(), Owm = pKF->GetCameraCenter();
+    float R[9], t[3], Ow[3];
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) R[3 * i + j] = Rcw.at<float>(i, j);
+        t[i] = tcw.at<float>(i, 0);
+        Ow[i] = Owm.at<float>(i, 0);
+    }
+    const float fx = pKF->fx, fy = pKF->fy, cx = pKF->cx, cy = pKF->cy, bf = pKF->mbf;
+    const int32_t kp_off[2] = {0, N}, q_off[2] = {0, NQ};
+    std::vector<uint8_t> tmp;
+    orbgpu_frame_set fs = one_frame(kp_off, pKF->mvKeysUn, rows32(pKF->mDescriptors, tmp));
+    fs.u_right = pKF->mvuRight.empty() ? nullptr : pKF->mvuRight.data();
+    const float grid[4] = {(float)pKF->mnMinX, (float)pKF->mnMinY, pKF->mfGridElementWidthInv, pKF->mfGridElementHeightInv};
+    fs.grid = grid;
+    std::vector<float> qu(NQ), qv(NQ), qr(NQ), qur(NQ);
+    std::vector<int32_t> qlo(NQ), qhi(NQ);
+    std::vector<uint8_t> qfl(NQ, 0), qdesc((size_t)NQ * 32, 0);
+    for (int i = 0; i < NQ; ++i) {
+        MapPoint* pMP = vpMapPoints[i];
+        if (!pMP) continue;
+        const cv::Mat p3Dw = pMP->GetWorldPos();
+        const float xw[3] = {p3Dw.at<float>(0, 0), p3Dw.at<float>(1, 0), p3Dw.at<float>(2, 0)};
+        float pc[3];
+        for (int r = 0; r < 3; ++r) {   // Rcw*p3Dw + tcw: cv::gemm's small-matrix path (float dot product, addend joined in double)
+            const float d = R[3 * r] * xw[0] + R[3 * r + 1] * xw[1] + R[3 * r + 2] * xw[2];
+            pc[r] = (float)((double)d + (double)t[r]);
+        }
+        if (pc[2] < 0.0f) continue;                                   // :1011-1012
+        const float invz = 1 / pc[2];
+        const float x = pc[0] * invz, y = pc[1] * invz;
+        const float u = fx * x + cx, v = fy * y + cy;
+        if (!pKF->IsInImage(u, v)) continue;                          // :1023-1024
+        const float ur = u - bf * invz;
+        const float maxDistance = pMP->GetMaxDistanceInvariance(), minDistance = pMP->GetMinDistanceInvariance();
+        const float PO[3] = {xw[0] - Ow[0], xw[1] - Ow[1], xw[2] - Ow[2]};
+        const float dist3D = (float)std::sqrt((double)PO[0] * PO[0] + (double)PO[1] * PO[1] + (double)PO[2] * PO[2]);   // cv::norm
+        if (dist3D < minDistance || dist3D > maxDistance) continue;  // :1035-1036
+        const cv::Mat Pn = pMP->GetNormal();
+        const double dot = (double)PO[0] * Pn.at<float>(0, 0) + (double)PO[1] * Pn.at<float>(1, 0) + (double)PO[2] * Pn.at<float>(2, 0);
+        if (dot < 0.5 * dist3D) continue;                             // :1041-1042
+        const int nPredictedLevel = pMP->PredictScale(dist3D, pKF);
+        qu[i] = u; qv[i] = v; qur[i] = ur;
+        qr[i] = th * pKF->mvScaleFactors[nPredictedLevel];           // :1047
+        qlo[i] = nPredictedLevel - 1; qhi[i] = nPredictedLevel;       // :1066-1067
+        qfl[i] = 1;
+        const cv::Mat d = pMP->GetDescriptor();
+        std::memcpy(&qdesc[(size_t)i * 32], d.ptr(0), 32);
+    }
+    orbgpu_window_query_set qs;
+    qs.q_off = q_off; qs.u = qu.data(); qs.v = qv.data(); qs.radius = qr.data(); qs.min_level = qlo.data(); qs.max_level = qhi.data();
+    qs.ur = qur.data(); qs.flags = qfl.data(); qs.desc = qdesc.data(); qs.angle = nullptr;
+    std::vector<int32_t> best(NQ, -1), bdist(NQ, 256);
+    check(orbgpu_search_window_best(matcher(), &fs, &qs, pKF->mvInvLevelSigma2.data(), (int)pKF->mvInvLevelSigma2.size(), 0, best.data(), bdist.data()),
+          "Fuse");
+    int nFused = 0;
+    for (int i = 0; i < NQ; ++i) {
+        MapPoint* pMP = vpMapPoints[i];
+        if (!pMP || !qfl[i]) continue;
+        if (pMP->isBad() || pMP->IsInKeyFrame(pKF)) continue;        // :999-1000, at this point's turn
+        if (bdist[i] > TH_LOW) continue;                              // :1114
+        const int bestIdx = best[i];
+        MapPoint* pMPinKF = pKF->GetMapPoint(bestIdx);
+        if (pMPinKF) {
+            if (!pMPinKF->isBad()) {
+                if (pMPinKF->Observations() > pMP->Observations()) pMP->Replace(pMPinKF);
+                else pMPinKF->Replace(pMP);
+            }
+        } else {
+            pMP->AddObservation(pKF, bestIdx);
+            pKF->AddMapPoint(pMP, bestIdx);
+        }
+        nFused++;
+    }
+    return nFused;
 }
 
 // SearchForInitialization (ORBmatcher.cc:493-632): the monocular bootstrap match between the reference frame F1 and the current

@@ -32,6 +32,15 @@ public:
     float GetMinDistanceInvariance() { return 0.8f * mfMinDistance; }   // MapPoint.cc:392-396
     float GetMaxDistanceInvariance() { return 1.2f * mfMaxDistance; }   // MapPoint.cc:398-402
     inline int PredictScale(const float& currentDist, Frame* pF);       // MapPoint.cc:421-436
+    inline int PredictScale(const float& currentDist, KeyFrame* pKF);   // MapPoint.cc:404-419
+    cv::Mat GetNormal() { return mNormalVector.clone(); }
+    bool IsInKeyFrame(KeyFrame* pKF) { return mObservations.count(pKF) != 0; }        // MapPoint.cc:325-329
+    void AddObservation(KeyFrame* pKF, size_t idx) {                                   // MapPoint.cc:85-96 (monocular count)
+        if (mObservations.count(pKF)) return;
+        mObservations[pKF] = idx;
+        nObs++;
+    }
+    inline void Replace(MapPoint* pMP);                                                // MapPoint.cc:189-238
     int Observations() { return nObs; }
     bool isBad() { return mbBad; }
     cv::Mat GetDescriptor() { return mDescriptor.clone(); }
@@ -48,6 +57,9 @@ public:
     float mfMinDistance, mfMaxDistance;
     cv::Mat mDescriptor;
     cv::Mat mWorldPos;   // 3x1 CV_32F
+    cv::Mat mNormalVector;   // 3x1 CV_32F
+    std::map<KeyFrame*, size_t> mObservations;
+    MapPoint* mpReplaced = 0;
 };
 
 class Frame {
@@ -89,6 +101,8 @@ public:
     cv::Mat GetTranslation() { return tcw.clone(); }
     std::vector<MapPoint*> GetMapPointMatches() { return mvpMapPoints; }
     MapPoint* GetMapPoint(const size_t& idx) { return mvpMapPoints[idx]; }
+    void AddMapPoint(MapPoint* pMP, const size_t& idx) { mvpMapPoints[idx] = pMP; }                       // KeyFrame.cc:219-223
+    bool IsInImage(const float& x, const float& y) const { return x >= mnMinX && x < mnMaxX && y >= mnMinY && y < mnMaxY; }   // KeyFrame.cc:624-627
 
     const float fx, fy, cx, cy;
     const int N;
@@ -99,10 +113,42 @@ public:
     const std::vector<float> mvScaleFactors;
     const std::vector<float> mvLevelSigma2;
 
+    float mbf = 0.f, mfLogScaleFactor = 0.f;
+    int mnScaleLevels = 0;
+    std::vector<float> mvInvLevelSigma2;
+    int mnMinX = 0, mnMinY = 0, mnMaxX = 0, mnMaxY = 0;
+    float mfGridElementWidthInv = 0.f, mfGridElementHeightInv = 0.f;
+
     // stub state
     std::vector<MapPoint*> mvpMapPoints;
     cv::Mat Ow, Rcw, tcw;   // 3x1, 3x3, 3x1 CV_32F
 };
+
+inline int MapPoint::PredictScale(const float& currentDist, KeyFrame* pKF) {
+    const float ratio = mfMaxDistance / currentDist;
+    int nScale = (int)std::ceil(std::log(ratio) / pKF->mfLogScaleFactor);
+    if (nScale < 0) nScale = 0;
+    else if (nScale >= pKF->mnScaleLevels) nScale = pKF->mnScaleLevels - 1;
+    return nScale;
+}
+
+// MapPoint::Replace (MapPoint.cc:189-238): this point goes bad, its observations move to pMP (or are erased where pMP is seen already)
+inline void MapPoint::Replace(MapPoint* pMP) {
+    if (pMP == this) return;
+    std::map<KeyFrame*, size_t> obs = mObservations;
+    mObservations.clear();
+    mbBad = true;
+    mpReplaced = pMP;
+    for (std::map<KeyFrame*, size_t>::iterator it = obs.begin(); it != obs.end(); ++it) {
+        KeyFrame* pKF = it->first;
+        if (!pMP->IsInKeyFrame(pKF)) {
+            pKF->mvpMapPoints[it->second] = pMP;   // ReplaceMapPointMatch
+            pMP->AddObservation(pKF, it->second);
+        } else {
+            pKF->mvpMapPoints[it->second] = static_cast<MapPoint*>(0);   // EraseMapPointMatch
+        }
+    }
+}
 
 }  // namespace ORB_SLAM2
 #endif

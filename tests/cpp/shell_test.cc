@@ -37,6 +37,8 @@ void orbm_search_by_bow(const orbgpu_frame_set*, const orbgpu_frame_set*, int, c
 void cvl_gemm3_f32(const float*, const float*, const float*, float*);
 void cvl_gemm3t_neg_f32(const float*, const float*, float*);
 double cvl_norm3_f32(const float*);
+double cvl_dot3_f32(const float*, const float*);
+void orbm_search_window_best(const orbgpu_frame_set*, const orbgpu_window_query_set*, const float*, int, int32_t*, int32_t*);
 void orbm_search_for_initialization(const orbgpu_frame_set*, const orbgpu_window_query_set*, float, int, int32_t*, int32_t*);
 void* orbo_voc_create(int, int, int, int, int, const int32_t*, const uint8_t*, const uint8_t*, const double*);
 void orbo_voc_free(void*);
@@ -574,6 +576,159 @@ static void test_relocalization_search() {
     printf("SearchByProjection(Frame,KeyFrame): %d matches of %d live queries, oracle equal: %s\n", n, live, cur.mvpMapPoints == exp ? "yes" : "no");
 }
 
+// --- Fuse(pKF, vpMapPoints, th): LocalMapping::SearchInNeighbors' matcher (LocalMapping.cc:589-640) -------------------------
+struct FuseWorld {
+    std::vector<cv::KeyPoint> keys;
+    cv::Mat desc;
+    std::vector<float> ur;
+    KeyFrame *kf, *other;
+    std::vector<MapPoint> held, cand;
+    std::vector<MapPoint*> vp;
+    FuseWorld() : kf(nullptr), other(nullptr) {}
+    ~FuseWorld() { delete kf; delete other; }
+    int id(MapPoint* p) const {
+        if (!p) return -1;
+        if (!held.empty() && p >= &held[0] && p <= &held[held.size() - 1]) return 1000 + (int)(p - &held[0]);
+        return 5000 + (int)(p - &cand[0]);
+    }
+};
+static void make_fuse_world(FuseWorld& w, uint32_t seed) {
+    g_seed = seed;
+    const int W = 640, H = 480, N = 800, M = 700;
+    w.keys = random_keys(N, W, H);
+    w.desc = random_desc(N);
+    w.ur.assign(N, -1.f);
+    for (int i = 0; i < N; ++i) if (rnd() % 2) w.ur[i] = w.keys[i].pt.x - frand(2, 18);
+    const float fx = 517.3f, fy = 516.5f, cx = 318.6f, cy = 255.3f;
+    w.kf = new KeyFrame(w.keys, w.ur, w.desc, g_sf, g_s2, fx, fy, cx, cy);
+    w.other = new KeyFrame(w.keys, w.ur, w.desc, g_sf, g_s2, fx, fy, cx, cy);
+    KeyFrame& kf = *w.kf;
+    kf.mbf = 40.f; kf.mfLogScaleFactor = std::log(1.2f); kf.mnScaleLevels = 8;
+    kf.mvInvLevelSigma2.resize(8);
+    for (int l = 0; l < 8; ++l) kf.mvInvLevelSigma2[l] = 1.0f / g_s2[l];
+    kf.mnMinX = 0; kf.mnMinY = 0; kf.mnMaxX = W; kf.mnMaxY = H;
+    kf.mfGridElementWidthInv = 64.0f / W; kf.mfGridElementHeightInv = 48.0f / H;
+    const float ang = 0.02f;
+    float R[9] = {std::cos(ang), 0.f, std::sin(ang), 0.f, 1.f, 0.f, -std::sin(ang), 0.f, std::cos(ang)}, t[3] = {0.05f, -0.02f, 0.1f}, Ow[3];
+    cvl_gemm3t_neg_f32(R, t, Ow);
+    kf.Rcw = cv::Mat(3, 3, CV_32FC1); kf.tcw = cv::Mat(3, 1, CV_32FC1); kf.Ow = cv::Mat(3, 1, CV_32FC1);
+    for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) kf.Rcw.at<float>(i, j) = R[3 * i + j]; kf.tcw.at<float>(i, 0) = t[i]; kf.Ow.at<float>(i, 0) = Ow[i]; }
+    // some key points of the key frame already hold a MapPoint (seen from `other` too)
+    w.held.resize(N);
+    for (int i = 0; i < N; ++i) {
+        if (rnd() % 3) continue;
+        MapPoint& p = w.held[i];
+        p.AddObservation(w.kf, i);
+        if (rnd() % 2) { p.AddObservation(w.other, i); w.other->mvpMapPoints[i] = &p; }
+        if (rnd() % 3 == 0) p.nObs += 2;
+        p.mbBad = rnd() % 25 == 0;
+        kf.mvpMapPoints[i] = &p;
+    }
+    // candidate points: world positions that project onto key points of the key frame (+ noise), a few impossible ones
+    w.cand.resize(M);
+    w.vp.assign(M, nullptr);
+    for (int k = 0; k < M; ++k) {
+        MapPoint& p = w.cand[k];
+        const int j = rnd() % N;
+        const float z = (rnd() % 30 == 0 ? -1.f : 1.f) * frand(2.f, 12.f);
+        const float u = w.keys[j].pt.x + frand(-1.5f, 1.5f), v = w.keys[j].pt.y + frand(-1.5f, 1.5f);
+        const float pc[3] = {(u - cx) / fx * z - t[0], (v - cy) / fy * z - t[1], z - t[2]};
+        p.mWorldPos = cv::Mat(3, 1, CV_32FC1);
+        for (int r = 0; r < 3; ++r) p.mWorldPos.at<float>(r, 0) = R[r] * pc[0] + R[3 + r] * pc[1] + R[6 + r] * pc[2];   // R^T (pc - t)
+        float po[3], d = 0;
+        for (int r = 0; r < 3; ++r) { po[r] = p.mWorldPos.at<float>(r, 0) - Ow[r]; d += po[r] * po[r]; }
+        d = std::sqrt(d);
+        p.mNormalVector = cv::Mat(3, 1, CV_32FC1);
+        for (int r = 0; r < 3; ++r) p.mNormalVector.at<float>(r, 0) = po[r] / d * (rnd() % 20 == 0 ? -1.f : 1.f);
+        p.mfMaxDistance = d * std::pow(1.2f, (float)w.keys[j].octave - 0.5f) * (rnd() % 25 == 0 ? 40.f : 1.f);
+        p.mfMinDistance = p.mfMaxDistance / std::pow(1.2f, 7.f);
+        p.mDescriptor = cv::Mat(1, 32, CV_8UC1);
+        std::memcpy(p.mDescriptor.ptr(0), w.desc.ptr(j), 32);
+        flip(p.mDescriptor.ptr(0), rnd() % 6 == 0 ? 90 : 12);
+        p.nObs = rnd() % 5;
+        p.mbBad = rnd() % 30 == 0;
+        if (rnd() % 20 == 0) p.AddObservation(w.kf, (size_t)(rnd() % N));   // already seen in this key frame
+        if (rnd() % 15) w.vp[k] = &p;
+        if (k > 3 && rnd() % 12 == 0) w.vp[k] = w.vp[k - 3];                  // the same point twice in the list
+    }
+}
+static void test_fuse() {
+    FuseWorld A, B;
+    make_fuse_world(A, 4242);
+    make_fuse_world(B, 4242);
+    const float th = 3.0f;
+    ORBmatcher m;
+    const int nA = m.Fuse(A.kf, A.vp, th);
+    // world B: the reference's loop (ORBmatcher.cc:977-1137) restated around the oracle's best-only search
+    KeyFrame& kf = *B.kf;
+    const int N = kf.N, M = (int)B.vp.size();
+    float R[9], t[3], Ow[3];
+    for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) R[3 * i + j] = kf.Rcw.at<float>(i, j); t[i] = kf.tcw.at<float>(i, 0); Ow[i] = kf.Ow.at<float>(i, 0); }
+    Flat a(kf.mvKeysUn, kf.mDescriptors, nullptr);
+    a.s.kp_flags = nullptr;
+    a.s.u_right = kf.mvuRight.data();
+    const float grid[4] = {0, 0, kf.mfGridElementWidthInv, kf.mfGridElementHeightInv};
+    a.s.grid = grid;
+    int32_t q_off[2] = {0, M};
+    std::vector<float> qu(M), qv(M), qr(M), qur(M);
+    std::vector<int32_t> lo(M), hi(M);
+    std::vector<uint8_t> qf(M, 0), qd((size_t)M * 32, 0);
+    for (int i = 0; i < M; ++i) {
+        MapPoint* p = B.vp[i];
+        if (!p) continue;
+        float pc[3];
+        cvl_gemm3_f32(R, p->mWorldPos.ptr<float>(0), t, pc);
+        if (pc[2] < 0.0f) continue;
+        const float invz = 1 / pc[2];
+        const float x = pc[0] * invz, y = pc[1] * invz;
+        const float u = kf.fx * x + kf.cx, v = kf.fy * y + kf.cy;
+        if (!kf.IsInImage(u, v)) continue;
+        const float po[3] = {p->mWorldPos.at<float>(0, 0) - Ow[0], p->mWorldPos.at<float>(1, 0) - Ow[1], p->mWorldPos.at<float>(2, 0) - Ow[2]};
+        const float dist3D = (float)cvl_norm3_f32(po);
+        if (dist3D < p->GetMinDistanceInvariance() || dist3D > p->GetMaxDistanceInvariance()) continue;
+        const float nrm[3] = {p->mNormalVector.at<float>(0, 0), p->mNormalVector.at<float>(1, 0), p->mNormalVector.at<float>(2, 0)};
+        if (cvl_dot3_f32(po, nrm) < 0.5 * dist3D) continue;
+        const int lvl = p->PredictScale(dist3D, &kf);
+        qu[i] = u; qv[i] = v; qur[i] = u - kf.mbf * invz; qr[i] = th * g_sf[lvl];
+        lo[i] = lvl - 1; hi[i] = lvl;
+        qf[i] = 1;
+        std::memcpy(&qd[(size_t)i * 32], p->mDescriptor.ptr(0), 32);
+    }
+    orbgpu_window_query_set qs = {q_off, qu.data(), qv.data(), qr.data(), lo.data(), hi.data(), qur.data(), qf.data(), qd.data(), nullptr};
+    std::vector<int32_t> best(M, -1), bd(M, 256);
+    orbm_search_window_best(&a.s, &qs, kf.mvInvLevelSigma2.data(), 0, best.data(), bd.data());
+    int nB = 0, replaced_a = 0, replaced_b = 0, added = 0;
+    for (int i = 0; i < M; ++i) {
+        MapPoint* pMP = B.vp[i];
+        if (!pMP || !qf[i]) continue;
+        if (pMP->isBad() || pMP->IsInKeyFrame(&kf)) continue;
+        if (bd[i] > 50) continue;
+        MapPoint* pMPinKF = kf.GetMapPoint(best[i]);
+        if (pMPinKF) {
+            if (!pMPinKF->isBad()) {
+                if (pMPinKF->Observations() > pMP->Observations()) { pMP->Replace(pMPinKF); ++replaced_a; }
+                else { pMPinKF->Replace(pMP); ++replaced_b; }
+            }
+        } else {
+            pMP->AddObservation(&kf, best[i]);
+            kf.AddMapPoint(pMP, best[i]);
+            ++added;
+        }
+        nB++;
+    }
+    int bad = 0;
+    for (int i = 0; i < N; ++i) {
+        bad += A.id(A.kf->mvpMapPoints[i]) != B.id(B.kf->mvpMapPoints[i]);
+        bad += A.id(A.other->mvpMapPoints[i]) != B.id(B.other->mvpMapPoints[i]);
+        bad += A.held[i].mbBad != B.held[i].mbBad || A.held[i].nObs != B.held[i].nObs || A.id(A.held[i].mpReplaced) != B.id(B.held[i].mpReplaced);
+    }
+    for (int k = 0; k < M; ++k)
+        bad += A.cand[k].mbBad != B.cand[k].mbBad || A.cand[k].nObs != B.cand[k].nObs || A.id(A.cand[k].mpReplaced) != B.id(B.cand[k].mpReplaced);
+    EXPECT(nA == nB && bad == 0 && added > 30 && replaced_a > 5 && replaced_b > 5, "Fuse: %d fused (oracle loop %d), %d state differences; added %d, replaced %d / %d", nA, nB,
+           bad, added, replaced_a, replaced_b);
+    printf("Fuse: %d fused (%d added, %d + %d replaced), map state equal to the restated loop: %s\n", nA, added, replaced_a, replaced_b, bad ? "no" : "yes");
+}
+
 // ---- ORBmatcher::SearchForInitialization as Tracking::MonocularInitialization calls it (Tracking.cc:609-612) ----------------
 static void test_search_for_initialization() {
     const int N = 900;
@@ -742,6 +897,7 @@ int main() {
     test_vocabulary();
     test_search_for_initialization();
     test_relocalization_search();
+    test_fuse();
     printf(fails ? "shell_test: %d FAILURES\n" : "shell_test: all shell results equal the oracle (%d failures)\n", fails);
     return fails ? 1 : 0;
 }
