@@ -44,3 +44,29 @@ def test_no_cpu_fallback_without_device():
 def test_keypoint_layout_is_cv_keypoint():
     from orb_slam2_with_comment_b200 import KP_DTYPE
     assert KP_DTYPE.itemsize == 28 and KP_DTYPE.names == ("x", "y", "size", "angle", "response", "octave", "class_id")
+
+
+def test_product_never_touches_the_oracle():
+    """oracle/ is test infrastructure: no product source (package, C ABI, shells) may import, include or link it."""
+    pkg = os.path.join(ROOT, "orb_slam2_with_comment_b200")
+    offenders = []
+    for base, _, files in os.walk(pkg):
+        for f in files:
+            if not f.endswith((".py", ".cu", ".cuh", ".h", ".cc", ".cpp", "Makefile")):
+                continue
+            text = open(os.path.join(base, f), errors="ignore").read()
+            for needle in ("oracle_lib", "liborboracle", "liborbref", "libdbowref", "/oracle/", "import oracle", "from oracle"):
+                if needle in text:
+                    offenders.append((os.path.relpath(os.path.join(base, f), ROOT), needle))
+    assert not offenders, offenders
+
+
+def test_new_entries_fail_loudly_without_a_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import numpy as np
+    from orb_slam2_with_comment_b200 import capi, synth
+    from orb_slam2_with_comment_b200.vocabulary import ORBVocabulary
+    with pytest.raises(capi.OrbGpuError, match="no CUDA device"):
+        ORBVocabulary().from_records(synth.vocabulary_tree(k=3, L=2, seed=1))
