@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cassert>
 #include <cfloat>
+#include <climits>
 #include <cmath>
 #include <cstddef>
 #include <cstdint>
@@ -75,6 +76,9 @@ struct KeyPoint {
         : pt(x, y), size(_size), angle(_angle), response(_response), octave(_octave), class_id(_class_id) {}
 };
 
+class MatExpr;
+class _OutputArray;
+
 // Byte-addressed 2-D array header with shared ownership of the pixel buffer (like cv::Mat,
 // one channel only: CV_8UC1 or CV_32FC1).
 class Mat {
@@ -99,7 +103,7 @@ public:
     }
 
     void create(int r, int c, int type) {
-        if (data && rows == r && cols == c && type_ == type && isContinuous()) return;
+        if (data && rows == r && cols == c && type_ == type) return;   // like cv::Mat::create: same geometry => keep (also a view)
         type_ = type;
         rows = r;
         cols = c;
@@ -140,6 +144,35 @@ public:
     Mat rowRange(int a, int b) const { return (*this)(Rect(0, a, cols, b - a)); }
     Mat colRange(int a, int b) const { return (*this)(Rect(a, 0, b - a, rows)); }
     Mat row(int r) const { return rowRange(r, r + 1); }
+    Mat col(int c) const { return colRange(c, c + 1); }
+
+    // small float algebra (mat_algebra.hpp)
+    Mat(const MatExpr& e);
+    Mat& operator=(const MatExpr& e);
+    MatExpr t() const;
+    static MatExpr eye(int r, int c, int type);
+    static MatExpr ones(int r, int c, int type);
+    // Mat::dot of two float vectors / matrices of equal size: products and sum in double
+    double dot(const Mat& m) const {
+        double s = 0.0;
+        for (int r = 0; r < rows; ++r)
+            for (int c = 0; c < cols; ++c) s += (double)at<float>(r, c) * (double)m.at<float>(r, c);
+        return s;
+    }
+    void copyTo(const _OutputArray& dst) const;
+    // convertTo without scaling: 8U -> 32F (Frame.cc:599, :616) or same type
+    void convertTo(Mat& dst, int rtype) const {
+        Mat out(rows, cols, rtype);
+        for (int r = 0; r < rows; ++r)
+            for (int c = 0; c < cols; ++c) {
+                const float v = type_ == CV_32FC1 ? at<float>(r, c) : (float)at<uchar>(r, c);
+                if (rtype == CV_32FC1) out.at<float>(r, c) = v; else out.at<uchar>(r, c) = (uchar)v;
+            }
+        dst = out;
+    }
+    // multi-channel views exist only on the distorted-camera branch (Frame.cc:454-457, :482-484), which ends in
+    // cv::undistortPoints (not provided): reshape is the identity here and that call aborts
+    Mat reshape(int) const { return *this; }
 
     Mat clone() const {
         Mat m(rows, cols, type_);
@@ -147,6 +180,9 @@ public:
         return m;
     }
 
+    // single index: element i of a row or column vector (cv::Mat::at(int i0))
+    template <typename T> T& at(int i) { return (rows == 1 || isContinuous()) ? ((T*)data)[i] : *(T*)(data + (size_t)i * step.v); }
+    template <typename T> const T& at(int i) const { return (rows == 1 || isContinuous()) ? ((const T*)data)[i] : *(const T*)(data + (size_t)i * step.v); }
     template <typename T> T& at(int r, int c) { return *(T*)(data + (size_t)r * step.v + (size_t)c * sizeof(T)); }
     template <typename T> const T& at(int r, int c) const { return *(const T*)(data + (ptrdiff_t)r * (ptrdiff_t)step.v + (ptrdiff_t)c * (ptrdiff_t)sizeof(T)); }
     uchar* ptr(int r = 0) { return data + (size_t)r * step.v; }
@@ -174,6 +210,7 @@ class _OutputArray : public _InputArray {
 public:
     _OutputArray() {}
     _OutputArray(Mat& m) { m_ = &m; }
+    _OutputArray(const Mat& m) { m_ = const_cast<Mat*>(&m); }   // a temporary view as destination (KeyFrame.cc:82-83)
     void create(int r, int c, int type) const { if (m_) m_->create(r, c, type); }
     void release() const { if (m_) m_->release(); }
 };
@@ -186,6 +223,22 @@ enum { INTER_NEAREST = 0, INTER_LINEAR = 1 };
 
 float fastAtan2(float y, float x);
 
+inline void Mat::copyTo(const _OutputArray& dst) const {
+    dst.create(rows, cols, type_);
+    Mat d = dst.getMat();
+    for (int r = 0; r < rows; ++r) std::memcpy(d.data + (size_t)r * d.step.v, data + (size_t)r * step.v, (size_t)cols * elemSize());
+}
+
+typedef Point_<float> Point2f;
+template <typename T> struct Point3_ {
+    T x, y, z;
+    Point3_() : x(0), y(0), z(0) {}
+    Point3_(T _x, T _y, T _z) : x(_x), y(_y), z(_z) {}
+};
+typedef Point3_<float> Point3f;
+
 }  // namespace cv
+
+#include "mat_algebra.hpp"
 
 #endif

@@ -114,10 +114,11 @@ def sbp_case(seed, n_frames=4, n_lo=300, n_hi=700, n_mp=1500, stereo_frac=0.0, o
     return fs, mps, sf, th
 
 
-def win_case(seed, n_frames=3, n_lo=400, n_hi=800, n_q=700, stereo_frac=0.0, mode="frame", th=15.0):
+def win_case(seed, n_frames=3, n_lo=400, n_hi=800, n_q=700, stereo_frac=0.0, mode="frame", th=15.0, mbf=None):
     """Queries for the generic windowed search: the map points of a 'last frame' projected into the current frame
     (mode 'frame': level range l-1..l+1 or, for a third of the frames each, the forward [l, inf) / backward [0, l] ranges
-    of ORBmatcher.cc:1604-1611; mode 'keyframe': always l-1..l+1)."""
+    of ORBmatcher.cc:1604-1611; mode 'keyframe': always l-1..l+1).  With `mbf` the view is one the reference function itself
+    can produce (oracle/slam_ref.cc): ur = u - mbf as at ORBmatcher.cc:1626, and no live projection left of / above the image."""
     from orb_slam2_with_comment_b200.matcher import WindowQuerySet
     rs, kp_off, keys, desc = _frames(seed, n_frames + 1, n_lo, n_hi)
     ko = kp_off[1:] - kp_off[1]
@@ -149,8 +150,13 @@ def win_case(seed, n_frames=3, n_lo=400, n_hi=800, n_q=700, stereo_frac=0.0, mod
         z = rs.uniform(size=nq)
         fl[z < 0.05] = 0                                      # projection failed
         fl[(z >= 0.05) & (z < 0.25)] &= ~np.uint8(4)          # temporal MapPoint without observations
-        parts.append({"u": u, "v": (k["y"] + rs.normal(0, 3, nq)).astype(np.float32), "radius": (np.float32(th) * sf[lvl]).astype(np.float32),
-                      "lo": lo.astype(np.int32), "hi": hi.astype(np.int32), "ur": (u - rs.uniform(1, 30, nq)).astype(np.float32), "flags": fl,
+        v = (k["y"] + rs.normal(0, 3, nq)).astype(np.float32)
+        ur = (u - rs.uniform(1, 30, nq)).astype(np.float32)
+        if mbf is not None:
+            ur = (u - np.float32(mbf)).astype(np.float32)
+            fl[(u < 0) | (v < 0)] = 0
+        parts.append({"u": u, "v": v, "radius": (np.float32(th) * sf[lvl]).astype(np.float32),
+                      "lo": lo.astype(np.int32), "hi": hi.astype(np.int32), "ur": ur, "flags": fl,
                       "desc": synth.flip_bits(prev_d[src], rs, 0.05), "angle": k["angle"]})
         q_off.append(q_off[-1] + nq)
     cat = {k2: np.concatenate([p[k2] for p in parts]) for k2 in parts[0]}
@@ -159,11 +165,11 @@ def win_case(seed, n_frames=3, n_lo=400, n_hi=800, n_q=700, stereo_frac=0.0, mod
     return fs, qs
 
 
-def frustum_case(seed, n_frames=4, n_mp=6000):
+def frustum_case(seed, n_frames=4, n_mp=6000, raw=False):
     """Poses and local-map points for Frame::isInFrustum: a point cloud in front of (and partly behind / beside) slightly
     rotated cameras, normals roughly facing them, distance-invariance ranges that cut some of the points."""
     rs = np.random.RandomState(seed)
-    cams, offs, P, Nn, dmin, dmax, dref = [], [0], [], [], [], [], []
+    cams, offs, P, Nn, dmin, dmax, dref, rmin = [], [0], [], [], [], [], [], []
     for f in range(n_frames):
         a, b, c = rs.normal(0, 0.05, 3)
         Rx = np.array([[1, 0, 0], [0, np.cos(a), -np.sin(a)], [0, np.sin(a), np.cos(a)]])
@@ -184,9 +190,12 @@ def frustum_case(seed, n_frames=4, n_mp=6000):
         dref.append(ref.astype(np.float32))
         dmax.append((np.float32(1.2) * ref.astype(np.float32)).astype(np.float32))
         dmin.append((np.float32(0.8) * (ref / 1.2 ** 7).astype(np.float32)).astype(np.float32))
+        rmin.append((ref / 1.2 ** 7).astype(np.float32))
         offs.append(offs[-1] + n)
-    return (np.stack(cams), np.float32(np.log(np.float32(1.2))), 8, 0.5, np.array(offs, np.int32), np.concatenate(P), np.concatenate(Nn),
-            np.concatenate(dmin), np.concatenate(dmax), np.concatenate(dref))
+    out = (np.stack(cams), np.float32(np.log(np.float32(1.2))), 8, 0.5, np.array(offs, np.int32), np.concatenate(P), np.concatenate(Nn),
+           np.concatenate(dmin), np.concatenate(dmax), np.concatenate(dref))
+    # raw: also mfMinDistance itself (the reference applies the 0.8 / 1.2 factors of Get{Min,Max}DistanceInvariance)
+    return out + (np.concatenate(rmin),) if raw else out
 
 
 def distinctive_case(seed, n_points=3000, n_max=60):

@@ -423,3 +423,150 @@ def distinctive_descriptors(lib, obs_off, desc):
     idx, med = np.zeros(n, np.int32), np.zeros(n, np.int32)
     lib.orbm_distinctive_descriptors(n, _p(obs_off, vp), _p(desc, vp), _p(idx, vp), _p(med, vp))
     return idx, med
+
+
+# ---- the reference's own ORBmatcher / Frame / KeyFrame / MapPoint (oracle/slam_ref.cc -> oracle/_ref/libslamref.so) -------------
+def load_slam_ref():
+    """The reference's ORBmatcher.cc, Frame.cc, KeyFrame.cc, MapPoint.cc, ... compiled where they lie; None where it cannot be
+    built (no /root/reference) and was not shipped."""
+    path = os.path.join(ORACLE_DIR, "_ref", "libslamref.so")
+    if not os.path.exists(path):
+        if os.path.isdir("/root/reference"):
+            subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "ref"])
+        else:
+            return None
+    lib = C.CDLL(path)
+    from orb_slam2_with_comment_b200.matcher import CFrameSet, CMapPointSet, CWindowQuerySet
+    vp, i, f = C.c_void_p, C.c_int, C.c_float
+    FS, MS, QS = C.POINTER(CFrameSet), C.POINTER(CMapPointSet), C.POINTER(CWindowQuerySet)
+    lib.slamref_hamming.argtypes = [u8p, u8p]
+    lib.slamref_search_by_projection.restype = None
+    lib.slamref_search_by_projection.argtypes = [FS, MS, vp, i, f, f, vp, vp, vp, vp, vp]
+    lib.slamref_search_windowed.argtypes = [FS, QS, i, i, i, vp, vp, vp, vp, vp, i, f, f]
+    lib.slamref_search_for_triangulation.restype = None
+    lib.slamref_search_for_triangulation.argtypes = [FS, FS, i, vp, vp, vp, vp, vp, vp, i, i, i, vp, vp, vp, vp]
+    lib.slamref_search_by_bow.argtypes = [FS, FS, i, vp, vp, f, i, i, i, i, vp, vp, vp, vp]
+    lib.slamref_search_for_initialization.argtypes = [FS, QS, f, i, vp, vp]
+    lib.slamref_fuse_best.argtypes = [FS, QS, vp, vp, i, f, f, vp]
+    lib.slamref_is_in_frustum.restype = None
+    lib.slamref_is_in_frustum.argtypes = [i, vp, f, i, f] + [vp] * 11
+    lib.slamref_distinctive_descriptors.restype = None
+    lib.slamref_distinctive_descriptors.argtypes = [i, vp, vp, vp, vp]
+    lib.slamref_stereo_frame.argtypes = [vp, vp, i, i, i, f, i, i, i, f, f, f, f, f, f, vp, vp, vp, vp, i]
+    lib.slamref_features_in_area.argtypes = [FS, i, f, f, f, i, i, vp, i]
+    return lib
+
+
+class MatcherRef:
+    """Same method names / return dicts as MatcherOracle, computed by the reference's own member functions on real Frame / KeyFrame /
+    MapPoint objects.  Returns only what the reference function makes observable (no internal best / second distances)."""
+    TH_LOW, TH_HIGH, HISTO_LENGTH = 50, 100, 30
+
+    def __init__(self, lib, nnratio=0.6, checkOri=True):
+        self.lib, self.mfNNratio, self.mbCheckOrientation = lib, float(nnratio), bool(checkOri)
+
+    def hamming_pairs(self, a, b):
+        a = np.ascontiguousarray(a, np.uint8).reshape(-1, 32)
+        b = np.ascontiguousarray(b, np.uint8).reshape(-1, 32)
+        return np.array([self.lib.slamref_hamming(_p(a[i]), _p(b[i])) for i in range(len(a))], np.int32)
+
+    def SearchByProjection(self, frames, mps, scale_factors, th=3.0):
+        sf = np.ascontiguousarray(scale_factors, np.float32)
+        kp_match = np.full(int(frames.kp_off[-1]), -1, np.int32)
+        nm = np.zeros(frames.n_frames, np.int32)
+        self.lib.slamref_search_by_projection(C.byref(frames.c), C.byref(mps.c), sf.ctypes.data, len(sf), th, self.mfNNratio,
+                                              kp_match.ctypes.data, None, None, None, nm.ctypes.data)
+        return {"nmatches": nm, "kp_match": kp_match}
+
+    def SearchWindowed(self, frames, queries, scale_factors, th, mbf, th_dist=100, skip_any_mappoint=False):
+        sf = np.ascontiguousarray(scale_factors, np.float32)
+        kp_match = np.full(int(frames.kp_off[-1]), -1, np.int32)
+        nm = np.zeros(frames.n_frames, np.int32)
+        rc = self.lib.slamref_search_windowed(C.byref(frames.c), C.byref(queries.c), th_dist, int(skip_any_mappoint), int(self.mbCheckOrientation),
+                                              kp_match.ctypes.data, None, None, nm.ctypes.data, sf.ctypes.data, len(sf), th, mbf)
+        assert rc == 0, f"the view is not representable by the reference function (code {rc})"
+        return {"nmatches": nm, "kp_match": kp_match}
+
+    def SearchForInitialization(self, frames2, queries1):
+        m12, nm = np.full(queries1.n, -1, np.int32), np.zeros(frames2.n_frames, np.int32)
+        rc = self.lib.slamref_search_for_initialization(C.byref(frames2.c), C.byref(queries1.c), self.mfNNratio, int(self.mbCheckOrientation),
+                                                        m12.ctypes.data, nm.ctypes.data)
+        assert rc == 0, rc
+        return {"match12": m12, "nmatches": nm}
+
+    def FuseBest(self, frames, queries, scale_factors, level_sigma2, th, mbf):
+        """Winner of Fuse(KeyFrame*, vpMapPoints, th)'s candidate loop per query, -1 where the reference did not fuse (best > TH_LOW)."""
+        sf, s2 = np.ascontiguousarray(scale_factors, np.float32), np.ascontiguousarray(level_sigma2, np.float32)
+        bi = np.full(queries.n, -1, np.int32)
+        rc = self.lib.slamref_fuse_best(C.byref(frames.c), C.byref(queries.c), sf.ctypes.data, s2.ctypes.data, len(sf), th, mbf, bi.ctypes.data)
+        assert rc == 0, f"the view is not representable by the reference function (code {rc})"
+        return {"q_best_idx": bi}
+
+    def SearchForTriangulation(self, set1, set2, idx1, idx2, F12, epipole, scale_factors, level_sigma2, bOnlyStereo=False):
+        from orb_slam2_with_comment_b200.matcher import match_offsets
+        idx1, idx2 = np.ascontiguousarray(idx1, np.int32), np.ascontiguousarray(idx2, np.int32)
+        F12 = np.ascontiguousarray(F12, np.float32).reshape(len(idx1), 9)
+        ep = np.ascontiguousarray(epipole, np.float32).reshape(len(idx1), 2)
+        sf, s2 = np.ascontiguousarray(scale_factors, np.float32), np.ascontiguousarray(level_sigma2, np.float32)
+        off, total = match_offsets(set1, idx1)
+        m12, nm = np.full(total, -1, np.int32), np.zeros(len(idx1), np.int32)
+        self.lib.slamref_search_for_triangulation(C.byref(set1.c), C.byref(set2.c), len(idx1), idx1.ctypes.data, idx2.ctypes.data,
+                                                  F12.ctypes.data, ep.ctypes.data, sf.ctypes.data, s2.ctypes.data, len(sf),
+                                                  int(bOnlyStereo), int(self.mbCheckOrientation), off.ctypes.data, m12.ctypes.data, None, nm.ctypes.data)
+        return {"nmatches": nm, "match12": m12, "match_off": off}
+
+    def SearchByBoW(self, set1, set2, idx1, idx2, kf_frame=False):
+        from orb_slam2_with_comment_b200.matcher import match_offsets
+        idx1, idx2 = np.ascontiguousarray(idx1, np.int32), np.ascontiguousarray(idx2, np.int32)
+        off, total = match_offsets(set1, idx1)
+        m12, nm = np.full(total, -1, np.int32), np.zeros(len(idx1), np.int32)
+        rc = self.lib.slamref_search_by_bow(C.byref(set1.c), C.byref(set2.c), len(idx1), idx1.ctypes.data, idx2.ctypes.data, self.mfNNratio,
+                                            int(self.mbCheckOrientation), self.TH_LOW, int(kf_frame), int(not kf_frame), off.ctypes.data,
+                                            m12.ctypes.data, None, nm.ctypes.data)
+        assert rc == 0, rc
+        return {"nmatches": nm, "match12": m12, "match_off": off}
+
+
+def ref_is_in_frustum(lib, cam, log_scale_factor, n_levels, viewing_cos_limit, mp_off, world_pos, normal, min_distance, max_distance):
+    """Frame::isInFrustum of the reference; min_distance / max_distance are the raw mfMinDistance / mfMaxDistance."""
+    vp = C.c_void_p
+    cam = np.ascontiguousarray(cam, np.float32).reshape(-1, 24)
+    mp_off = np.ascontiguousarray(mp_off, np.int32)
+    n = int(mp_off[-1])
+    ins = [np.ascontiguousarray(a, np.float32) for a in (world_pos, normal, min_distance, max_distance)]
+    out = {"in_view": np.zeros(n, np.uint8), "proj_x": np.zeros(n, np.float32), "proj_y": np.zeros(n, np.float32),
+           "proj_xr": np.zeros(n, np.float32), "level": np.zeros(n, np.int32), "view_cos": np.zeros(n, np.float32)}
+    lib.slamref_is_in_frustum(len(cam), _p(cam, vp), float(log_scale_factor), n_levels, float(viewing_cos_limit), _p(mp_off, vp),
+                              *[_p(a, vp) for a in ins], *[_p(out[k], vp) for k in ("in_view", "proj_x", "proj_y", "proj_xr", "level", "view_cos")])
+    return out
+
+
+def ref_distinctive_descriptors(lib, obs_off, desc):
+    """MapPoint::ComputeDistinctiveDescriptors of the reference: (has_descriptor[n], descriptor[n][32])."""
+    vp = C.c_void_p
+    obs_off = np.ascontiguousarray(obs_off, np.int32)
+    desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+    n = len(obs_off) - 1
+    best, has = np.zeros((n, 32), np.uint8), np.zeros(n, np.uint8)
+    lib.slamref_distinctive_descriptors(n, _p(obs_off, vp), _p(desc, vp), _p(best, vp), _p(has, vp))
+    return has, best
+
+
+def ref_stereo_frame(lib, img_l, img_r, nfeatures, mbf, mb, fx=718.856, fy=718.856, cx=607.19, cy=185.2, nlevels=8):
+    """The reference's stereo Frame constructor (both extractions + ComputeStereoMatches): kp, desc, mvuRight, mvDepth.  `mb` is the
+    value Frame::mb holds when ComputeStereoMatches runs (the reference sets it only afterwards, Frame.cc:88 vs :113)."""
+    vp = C.c_void_p
+    img_l, img_r = np.ascontiguousarray(img_l), np.ascontiguousarray(img_r)
+    cap = nfeatures + 3 * nlevels + 64
+    kp, desc = np.zeros(cap, KP_DTYPE), np.zeros((cap, 32), np.uint8)
+    ur, dp = np.zeros(cap, np.float32), np.zeros(cap, np.float32)
+    n = lib.slamref_stereo_frame(_p(img_l, vp), _p(img_r, vp), img_l.shape[1], img_l.shape[0], nfeatures, 1.2, nlevels, 20, 7, fx, fy, cx, cy, mbf, mb,
+                                 _p(kp, vp), _p(desc, vp), _p(ur, vp), _p(dp, vp), cap)
+    assert 0 <= n <= cap
+    return kp[:n].copy(), desc[:n].copy(), ur[:n].copy(), dp[:n].copy()
+
+
+def ref_features_in_area(lib, frames, f, x, y, r, min_level=-1, max_level=-1):
+    out = np.zeros(max(int(frames.kp_off[f + 1] - frames.kp_off[f]), 1), np.int32)
+    n = lib.slamref_features_in_area(C.byref(frames.c), f, x, y, r, min_level, max_level, out.ctypes.data, len(out))
+    return out[:n].copy()
