@@ -32,14 +32,27 @@ sys.path.insert(0, ROOT)
 
 W, H, NFEATURES, NLEVELS, SCALE, INI_TH, MIN_TH = 1241, 376, 2000, 8, 1.2, 20, 7
 METRIC = "ORB frames/s @1241x376 2k feats"
-N_DISTINCT = 16  # distinct synthetic frames; the batch tiles them (every copy has its own HBM address)
+N_DISTINCT = 256  # distinct synthetic frames (seeds); larger batches tile them (every copy has its own HBM address)
+
+
+def _g_rects_seed(s: int) -> np.ndarray:
+    from orb_slam2_with_comment_b200 import synth
+    return synth.g_rects(W, H, s)
 
 
 def make_frames(batch: int, first: int = 0) -> np.ndarray:
-    """Frames first .. first+batch of the global work list (frame i is G_rects seed i mod N_DISTINCT)."""
-    from orb_slam2_with_comment_b200 import synth
-    base = [synth.g_rects(W, H, s) for s in range(min(N_DISTINCT, max(batch, 1)))]
-    return np.ascontiguousarray(np.stack([base[(first + i) % len(base)] for i in range(batch)]))
+    """Frames first .. first+batch of the global work list (frame i is G_rects seed i mod N_DISTINCT): 256 distinct images, so
+    the latency-bound kernels (octree, FAST queues) see real divergence between neighbouring frames."""
+    from concurrent.futures import ProcessPoolExecutor
+    n = min(N_DISTINCT, max(batch, 1))
+    seeds = sorted(set((first + i) % N_DISTINCT for i in range(n)))
+    if len(seeds) >= 16:
+        with ProcessPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as ex:
+            imgs = list(ex.map(_g_rects_seed, seeds, chunksize=4))
+    else:
+        imgs = [_g_rects_seed(s) for s in seeds]
+    base = dict(zip(seeds, imgs))
+    return np.ascontiguousarray(np.stack([base[(first + i) % N_DISTINCT] for i in range(batch)]))
 
 
 def level_sizes():

@@ -46,6 +46,11 @@ const char* orbgpu_last_error(void);
 int orbgpu_device_count(int* count);
 /* ABI version of this header; bumped when a signature changes. */
 int orbgpu_abi_version(void);
+/* Process-wide default device of the C++ shells: ORBextractor::SetDevice stores it here, and the extractor, matcher and
+ * vocabulary shells all create their handles on it — so extraction, BoW and matching of one process share a GPU and the
+ * device-side chaining (orbgpu_frame_set_from_extraction) never meets handles of different devices.  Default 0. */
+int orbgpu_set_default_device(int device);
+int orbgpu_default_device(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Extraction — replaces ORBextractor (ORBextractor.h:45-111)
@@ -382,6 +387,13 @@ typedef struct orbgpu_vocabulary orbgpu_vocabulary;
 int orbgpu_vocabulary_create(orbgpu_vocabulary** out, int device, int k, int L, int scoring, int weighting, int n_records,
                              const int32_t* parent, const uint8_t* is_leaf, const uint8_t* desc, const double* weight);
 int orbgpu_vocabulary_destroy(orbgpu_vocabulary* v);
+/* Thread safety.  The reference shares ONE ORBVocabulary between its threads (Tracking calls Frame::ComputeBoW, Tracking.cc:874,
+ * :1585, while LocalMapping calls KeyFrame::ComputeBoW, LocalMapping.cc:164).  A handle owns one stream and one set of scratch
+ * buffers: orbgpu_bow_transform (host pointers) locks the handle for the whole call, so concurrent callers of one handle are
+ * serialised, never interleaved; orbgpu_bow_transform_dev does not lock (one thread per handle).  For real concurrency give
+ * every host thread its own fork: a second handle on the SAME read-only tree in HBM (no copy; the tree is freed with the last
+ * handle on it) with its own stream and scratch.  Destroy a fork with orbgpu_vocabulary_destroy, in any order. */
+int orbgpu_vocabulary_fork(const orbgpu_vocabulary* v, orbgpu_vocabulary** out);
 int orbgpu_vocabulary_info(const orbgpu_vocabulary* v, int* n_nodes, int* n_words);
 int orbgpu_vocabulary_sync(orbgpu_vocabulary* v);
 int orbgpu_vocabulary_last_launches(const orbgpu_vocabulary* v);

@@ -2,8 +2,10 @@
 // orbgpu_bow_transform, include/orbgpu.h).  No distance is computed on the host.
 #include "ORBVocabulary.h"
 
+#include <atomic>
 #include <cstring>
 #include <fstream>
+#include <map>
 #include <sstream>
 #include <stdexcept>
 
@@ -15,9 +17,34 @@ namespace {
 void check(int rc, const char* what) {
     if (rc != 0) throw std::runtime_error(std::string("ORBVocabulary (GPU): ") + what + ": " + orbgpu_last_error());
 }
+
+// One vocabulary object is shared by the Tracking, LocalMapping and LoopClosing threads (Tracking.cc:874, LocalMapping.cc:164).
+// Each host thread transforms through its own fork of the device handle — same tree in HBM, own stream and scratch — so
+// concurrent ComputeBoW calls neither interleave on one stream nor free each other's buffers.  Forks are keyed by the upload's
+// generation id (an address could be reused by a later vocabulary) and die with their thread.
+std::atomic<unsigned long long> g_next_upload_id{1};
+struct ThreadForks {
+    std::map<unsigned long long, orbgpu_vocabulary*> forks;
+    ~ThreadForks() {
+        for (std::map<unsigned long long, orbgpu_vocabulary*>::iterator it = forks.begin(); it != forks.end(); ++it) orbgpu_vocabulary_destroy(it->second);
+    }
+};
+orbgpu_vocabulary* thread_fork(const orbgpu_vocabulary* base, unsigned long long id) {
+    thread_local ThreadForks t;
+    std::map<unsigned long long, orbgpu_vocabulary*>::iterator it = t.forks.find(id);
+    if (it != t.forks.end()) return it->second;
+    if (t.forks.size() > 8) {   // vocabularies come and go rarely; keep the per-thread table small
+        for (it = t.forks.begin(); it != t.forks.end(); ++it) orbgpu_vocabulary_destroy(it->second);
+        t.forks.clear();
+    }
+    orbgpu_vocabulary* f = 0;
+    check(orbgpu_vocabulary_fork(base, &f), "cannot fork the device vocabulary for this thread");
+    t.forks[id] = f;
+    return f;
+}
 }  // namespace
 
-ORBVocabulary::ORBVocabulary() : dev_(0), n_words_(0) {}
+ORBVocabulary::ORBVocabulary() : dev_(0), n_words_(0), upload_id_(0) {}
 
 ORBVocabulary::~ORBVocabulary() {
     if (dev_) orbgpu_vocabulary_destroy(dev_);
@@ -29,7 +56,8 @@ void ORBVocabulary::upload(int k, int L, int scoring, int weighting, const std::
         orbgpu_vocabulary_destroy(dev_);
         dev_ = 0;
     }
-    check(orbgpu_vocabulary_create(&dev_, 0, k, L, scoring, weighting, (int)parent.size(), parent.data(), is_leaf.data(), desc.data(),
+    upload_id_ = g_next_upload_id.fetch_add(1);
+    check(orbgpu_vocabulary_create(&dev_, orbgpu_default_device(), k, L, scoring, weighting, (int)parent.size(), parent.data(), is_leaf.data(), desc.data(),
                                    weight.data()),
           "cannot upload the vocabulary");
     check(orbgpu_vocabulary_info(dev_, 0, &n_words_), "vocabulary info");
@@ -124,7 +152,7 @@ void ORBVocabulary::transform(const std::vector<cv::Mat>& features, DBoW2::BowVe
     std::vector<uint32_t> word(n);
     std::vector<double> value(n);
     std::vector<int32_t> node_id(n), feat_off(n + 1), feat(n);
-    check(orbgpu_bow_transform(dev_, 1, kp_off, rows.data(), levelsup, bv_off, word.data(), value.data(), node_off, node_id.data(), feat_off.data(),
+    check(orbgpu_bow_transform(thread_fork(dev_, upload_id_), 1, kp_off, rows.data(), levelsup, bv_off, word.data(), value.data(), node_off, node_id.data(), feat_off.data(),
                                feat.data(), 0, 0),
           "transform");
     for (int i = 0; i < bv_off[1]; ++i) v.insert(v.end(), std::make_pair((DBoW2::WordId)word[i], (DBoW2::WordValue)value[i]));

@@ -60,6 +60,7 @@ private:
                 const std::vector<uint8_t>& desc, const std::vector<double>& weight);
     orbgpu_vocabulary* dev_;
     int n_words_;
+    unsigned long long upload_id_;   // generation of the device copy: keys the per-thread forks (ORBVocabulary.cc)
 };
 
 }  // namespace ORB_SLAM2

@@ -14,13 +14,12 @@ namespace ORB_SLAM2 {
 static_assert(sizeof(cv::KeyPoint) == sizeof(orbgpu_keypoint), "cv::KeyPoint must be the 28-byte record the C ABI writes");
 
 namespace {
-int g_device = 0;
 void check(int rc, const char* what) {
     if (rc != 0) throw std::runtime_error(std::string("ORBextractor (GPU): ") + what + ": " + orbgpu_last_error());
 }
 }  // namespace
 
-void ORBextractor::SetDevice(int device) { g_device = device; }
+void ORBextractor::SetDevice(int device) { check(orbgpu_set_default_device(device), "SetDevice"); }
 
 ORBextractor::ORBextractor(int _nfeatures, float _scaleFactor, int _nlevels, int _iniThFAST, int _minThFAST)
     : nfeatures(_nfeatures), scaleFactor(_scaleFactor), nlevels(_nlevels), iniThFAST(_iniThFAST), minThFAST(_minThFAST),
@@ -51,7 +50,7 @@ void ORBextractor::EnsureHandle(int width, int height) {
     }
     mnMaxWidth = width > mnMaxWidth ? width : mnMaxWidth;
     mnMaxHeight = height > mnMaxHeight ? height : mnMaxHeight;
-    check(orbgpu_extractor_create(&mpHandle, g_device, nfeatures, (float)scaleFactor, nlevels, iniThFAST, minThFAST, mnMaxWidth,
+    check(orbgpu_extractor_create(&mpHandle, orbgpu_default_device(), nfeatures, (float)scaleFactor, nlevels, iniThFAST, minThFAST, mnMaxWidth,
                                   mnMaxHeight, 1),
           "cannot create the device extractor");
     const int cap = orbgpu_extractor_max_keypoints(mpHandle);

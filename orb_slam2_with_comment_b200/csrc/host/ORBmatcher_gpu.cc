@@ -44,7 +44,7 @@ struct ThreadMatcher {
 };
 orbgpu_matcher* matcher() {
     thread_local ThreadMatcher t;
-    if (!t.m) check(orbgpu_matcher_create(&t.m, 0), "cannot create the device matcher");
+    if (!t.m) check(orbgpu_matcher_create(&t.m, orbgpu_default_device()), "cannot create the device matcher");
     return t.m;
 }
 

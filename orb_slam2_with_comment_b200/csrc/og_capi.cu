@@ -3,6 +3,7 @@
 // ComputeKeyPointsOctTree line by line (cited inline); no pixel is ever touched on the host.
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <atomic>
 
 #include <algorithm>
 #include <cfloat>
@@ -553,7 +554,18 @@ int check_call(orbgpu_extractor* ex, int batch, int width, int height, size_t ro
 extern "C" {
 
 const char* orbgpu_last_error(void) { return g_err.c_str(); }
-int orbgpu_abi_version(void) { return 1; }
+int orbgpu_abi_version(void) { return 2; }
+
+// process-wide default device of the C++ shells (ORBextractor::SetDevice): one selector for extraction, matching and vocabulary
+static std::atomic<int> g_default_device{0};
+int orbgpu_set_default_device(int device) {
+    int n = 0;
+    OG_CUDA(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n) return fail(ORBGPU_ERR_ARG, "device index out of range");
+    g_default_device.store(device);
+    return ORBGPU_OK;
+}
+int orbgpu_default_device(void) { return g_default_device.load(); }
 
 int orbgpu_device_count(int* count) {
     if (!count) return fail(ORBGPU_ERR_ARG, "null count");
@@ -726,7 +738,42 @@ int orbgpu_extract_batch_dev(orbgpu_extractor* ex, const uint8_t* images_dev, in
     int rc = check_call(ex, batch, width, height, row_stride, kp_capacity);
     if (rc) return rc;
     if (!images_dev || !kp_out_dev || !desc_out_dev || !counts_dev) return fail(ORBGPU_ERR_ARG, "null device pointer");
-    return launch_extract(ex, images_dev, batch, row_stride, frame_stride, (og::KeyPoint*)kp_out_dev, desc_out_dev, kp_capacity, counts_dev);
+    // Large batches are pipelined as sub-batches over the compute streams: the latency-bound octree of one sub-batch (18 % of
+    // the issue slots, ncu) runs beside the issue-bound FAST / blur / descriptor kernels of its neighbours instead of alone
+    // on the GPU.  The caller still sees one in-order stream: the side streams fork from and join ex->stream.
+    static const int split_env = []() { const char* e = getenv("ORBGPU_DEV_SPLIT"); return e ? atoi(e) : -1; }();
+    static const int nstr_env = []() { const char* e = getenv("ORBGPU_DEV_STREAMS"); return e ? atoi(e) : 0; }();
+    const int min_sub = 128;
+    int nsub = split_env >= 0 ? split_env : 4;
+    if (ex->profiling || nsub <= 1 || batch < 2 * min_sub) nsub = 1;
+    nsub = std::min(nsub, batch / min_sub);
+    if (nsub <= 1)
+        return launch_extract(ex, images_dev, batch, row_stride, frame_stride, (og::KeyPoint*)kp_out_dev, desc_out_dev, kp_capacity, counts_dev);
+    const int n_streams = std::min(nstr_env > 0 ? nstr_env : 4, std::min(nsub, (int)orbgpu_extractor::kStreams));
+    while ((int)ex->ev_out.size() < n_streams) {
+        cudaEvent_t a, b;
+        OG_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        ex->ev_in.push_back(a);
+        OG_CUDA(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        ex->ev_out.push_back(b);
+    }
+    OG_CUDA(cudaEventRecord(ex->ev_begin, ex->stream));
+    for (int k = 1; k < n_streams; ++k) OG_CUDA(cudaStreamWaitEvent(ex->compute_stream(k), ex->ev_begin, 0));
+    int launches = 0;
+    for (int c = 0; c < nsub; ++c) {
+        const int f0 = (int)((long long)batch * c / nsub), f1 = (int)((long long)batch * (c + 1) / nsub);
+        rc = launch_extract(ex, images_dev, f1 - f0, row_stride, frame_stride, (og::KeyPoint*)kp_out_dev, desc_out_dev, kp_capacity, counts_dev, f0,
+                            ex->compute_stream(c % n_streams));
+        if (rc) return rc;
+        launches += ex->last_launches;
+    }
+    for (int k = 1; k < n_streams; ++k) {
+        OG_CUDA(cudaEventRecord(ex->ev_out[k], ex->compute_stream(k)));
+        OG_CUDA(cudaStreamWaitEvent(ex->stream, ex->ev_out[k], 0));
+    }
+    ex->last_batch = batch;
+    ex->last_launches = launches;
+    return ORBGPU_OK;
 }
 
 int orbgpu_extract_batch(orbgpu_extractor* ex, const uint8_t* images, int batch, int width, int height, size_t row_stride,

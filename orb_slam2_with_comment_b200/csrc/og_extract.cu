@@ -319,6 +319,15 @@ __host__ __device__ inline int fast_seg_smem_bytes(int hbox, int th_max) {
     return hbox * kSegPitch + (th_max + 2) * kSegPitch + th_max * 64 + 2 * th_max * kBmWords * 4 + kSegMaxTw * th_max * 2 + 256 + 128;
 }
 
+// atomicAdd on a shared-memory counter as ONE instruction (ATOMS.ADD).  With the intrinsic the compiler wraps every call in a
+// warp-aggregation loop (match / elect / shuffle, ~150 SASS instructions per site) although the callers already aggregate:
+// that was 5.9 % of k_fast_seg's executed instructions (profiles/r2_fast_seg_v0_lines.txt).
+__device__ __forceinline__ int smem_atomic_add(int* p, int v) {
+    int old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v) : "memory");
+    return old;
+}
+
 __device__ __forceinline__ uint32_t gt_bytes(uint32_t x, uint32_t kadd, bool big) {
     // 0x80 in every byte of x that is > t.  t < 127: kadd = (0x7f - t) per byte, carry from the low 7 bits or bit 7 itself;
     // t >= 127: needs bit 7 and the low 7 bits > t - 128: kadd = (0xff - t) per byte.
@@ -426,7 +435,7 @@ __global__ void __launch_bounds__(kSegThreads, 5) k_fast_seg(const __grid_consta
                     if (lane >= d) inc += o;
                 }
                 int base = 0;
-                if (lane == 31 && inc) base = atomicAdd(&qn, inc);
+                if (lane == 31 && inc) base = smem_atomic_add(&qn, inc);
                 base = __shfl_sync(0xffffffffu, base, 31) + inc - cnt;
                 const int e0 = i << 4;   // 16 rows-of-16 per tile row: row * 256 + 16 * (i & 15)
                 while (v) {
@@ -438,56 +447,61 @@ __global__ void __launch_bounds__(kSegThreads, 5) k_fast_seg(const __grid_consta
         }
         __syncthreads();
         const int nq = qn;
-        // ---- 3. exact score of the queued pixels --------------------------------------------------------------
-        const uint32_t thr2 = (uint32_t)(256 + tcur);
-        for (int q = t; q < nq; q += kSegThreads) {
-            const int e = queue[q];
-            const uint8_t* p = tile + 3 * kSegPitch + e;
-            const uint32_t v = p[0];
-            const uint32_t bias = ((256u - v) << 16) | (256u + v);
-            uint32_t E[16];
-            E[0] = p[3 * kSegPitch] * 0xFFFFu + bias;  E[4] = p[3] * 0xFFFFu + bias;   // lo: 256 + d_k, hi: 256 - d_k
-            E[8] = p[-3 * kSegPitch] * 0xFFFFu + bias; E[12] = p[-3] * 0xFFFFu + bias;
-            {
-                // an arc of 9 covers two of the four compass pixels: the second largest of the four (per half) must pass
-                const uint32_t a = __vmaxu2(E[0], E[4]), b = __vminu2(E[0], E[4]), c = __vmaxu2(E[8], E[12]), d = __vminu2(E[8], E[12]);
-                const uint32_t s2 = __vmaxu2(__vminu2(a, c), __vmaxu2(b, d));
-                if ((s2 & 0xffffu) <= thr2 && (s2 >> 16) <= thr2) continue;
-            }
-            E[1] = p[3 * kSegPitch + 1] * 0xFFFFu + bias;   E[2] = p[2 * kSegPitch + 2] * 0xFFFFu + bias;   E[3] = p[kSegPitch + 3] * 0xFFFFu + bias;
-            E[5] = p[-kSegPitch + 3] * 0xFFFFu + bias;      E[6] = p[-2 * kSegPitch + 2] * 0xFFFFu + bias;  E[7] = p[-3 * kSegPitch + 1] * 0xFFFFu + bias;
-            E[9] = p[-3 * kSegPitch - 1] * 0xFFFFu + bias;  E[10] = p[-2 * kSegPitch - 2] * 0xFFFFu + bias; E[11] = p[-kSegPitch - 3] * 0xFFFFu + bias;
-            E[13] = p[kSegPitch - 3] * 0xFFFFu + bias;      E[14] = p[2 * kSegPitch - 2] * 0xFFFFu + bias;  E[15] = p[3 * kSegPitch - 1] * 0xFFFFu + bias;
-            uint32_t m3[16], m9[16];
-#pragma unroll
-            for (int k = 0; k < 16; ++k) m3[k] = __vimin3_u16x2(E[k], E[(k + 1) & 15], E[(k + 2) & 15]);
-#pragma unroll
-            for (int k = 0; k < 16; ++k) m9[k] = __vimin3_u16x2(m3[k], m3[(k + 3) & 15], m3[(k + 6) & 15]);
-            uint32_t a = __vimax3_u16x2(m9[0], m9[1], m9[2]), b = __vimax3_u16x2(m9[3], m9[4], m9[5]);
-            uint32_t c = __vimax3_u16x2(m9[6], m9[7], m9[8]), d = __vimax3_u16x2(m9[9], m9[10], m9[11]);
-            uint32_t f = __vimax3_u16x2(m9[12], m9[13], m9[14]);
-            a = __vimax3_u16x2(a, b, c);
-            d = __vimax3_u16x2(d, f, m9[15]);
-            a = __vmaxu2(a, d);
-            const int V = max((int)(a & 0xffffu), (int)(a >> 16)) - 257;
-            if (V >= tcur) score[e + kSegPitch + 4 - ox] = (uint8_t)V;   // (row + 1) * 256 + px + 4
-        }
-        __syncthreads();
-        // ---- 4a. the corners among the queued pixels, compacted into the (now dead) tile -----------------------
-        uint16_t* cq = reinterpret_cast<uint16_t*>(tile);
-        const int cq_cap = hbox * kSegPitch / 2;
+        __syncthreads();   // everyone has read the queue length: the counter now counts corners
         if (t == 0) { qn = 0; nneed = 0; }
         if (t < 8) need[t] = 0;
         __syncthreads();
+        // ---- 3. exact score of the queued pixels; the corners among them go straight into a list --------------------
+        // The list lives in the rejection-mask area (dead until the next pass writes it again); if the corners outnumber it the
+        // NMS below walks all queued pixels instead.
+        uint16_t* cq = reinterpret_cast<uint16_t*>(mk);
+        const int cq_cap = th * 32;
+        const uint32_t thr2 = (uint32_t)(256 + tcur);
         for (int q0 = 0; q0 < nq; q0 += kSegThreads) {
             const int q = q0 + t;
-            const int e = q < nq ? queue[q] : 0;
-            const bool corner = q < nq && score[e + kSegPitch + 4 - ox] >= tcur;
+            bool corner = false;
+            int e = 0;
+            if (q < nq) {
+                e = queue[q];
+                const uint8_t* p = tile + 3 * kSegPitch + e;
+                const uint32_t v = p[0];
+                const uint32_t bias = ((256u - v) << 16) | (256u + v);
+                uint32_t E[16];
+                E[0] = p[3 * kSegPitch] * 0xFFFFu + bias;  E[4] = p[3] * 0xFFFFu + bias;   // lo: 256 + d_k, hi: 256 - d_k
+                E[8] = p[-3 * kSegPitch] * 0xFFFFu + bias; E[12] = p[-3] * 0xFFFFu + bias;
+                // an arc of 9 covers two of the four compass pixels: the second largest of the four (per half) must pass
+                const uint32_t ca = __vmaxu2(E[0], E[4]), cb = __vminu2(E[0], E[4]), cc = __vmaxu2(E[8], E[12]), cd = __vminu2(E[8], E[12]);
+                const uint32_t s2 = __vmaxu2(__vminu2(ca, cc), __vmaxu2(cb, cd));
+                if ((s2 & 0xffffu) > thr2 || (s2 >> 16) > thr2) {
+                    E[1] = p[3 * kSegPitch + 1] * 0xFFFFu + bias;   E[2] = p[2 * kSegPitch + 2] * 0xFFFFu + bias;   E[3] = p[kSegPitch + 3] * 0xFFFFu + bias;
+                    E[5] = p[-kSegPitch + 3] * 0xFFFFu + bias;      E[6] = p[-2 * kSegPitch + 2] * 0xFFFFu + bias;  E[7] = p[-3 * kSegPitch + 1] * 0xFFFFu + bias;
+                    E[9] = p[-3 * kSegPitch - 1] * 0xFFFFu + bias;  E[10] = p[-2 * kSegPitch - 2] * 0xFFFFu + bias; E[11] = p[-kSegPitch - 3] * 0xFFFFu + bias;
+                    E[13] = p[kSegPitch - 3] * 0xFFFFu + bias;      E[14] = p[2 * kSegPitch - 2] * 0xFFFFu + bias;  E[15] = p[3 * kSegPitch - 1] * 0xFFFFu + bias;
+                    uint32_t m3[16], m9[16];
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) m3[k] = __vimin3_u16x2(E[k], E[(k + 1) & 15], E[(k + 2) & 15]);
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) m9[k] = __vimin3_u16x2(m3[k], m3[(k + 3) & 15], m3[(k + 6) & 15]);
+                    uint32_t a = __vimax3_u16x2(m9[0], m9[1], m9[2]), b = __vimax3_u16x2(m9[3], m9[4], m9[5]);
+                    uint32_t c = __vimax3_u16x2(m9[6], m9[7], m9[8]), d = __vimax3_u16x2(m9[9], m9[10], m9[11]);
+                    uint32_t f = __vimax3_u16x2(m9[12], m9[13], m9[14]);
+                    a = __vimax3_u16x2(a, b, c);
+                    d = __vimax3_u16x2(d, f, m9[15]);
+                    a = __vmaxu2(a, d);
+                    const int V = max((int)(a & 0xffffu), (int)(a >> 16)) - 257;
+                    if (V >= tcur) {
+                        score[e + kSegPitch + 4 - ox] = (uint8_t)V;   // (row + 1) * 256 + px + 4
+                        corner = true;
+                    }
+                }
+            }
             const unsigned bal = __ballot_sync(0xffffffffu, corner);
-            int base = 0;
-            if (lane == 0 && bal) base = atomicAdd(&qn, __popc(bal));
-            base = __shfl_sync(0xffffffffu, base, 0) + __popc(bal & ((1u << lane) - 1));
-            if (corner && base < cq_cap) cq[base] = (uint16_t)e;
+            if (bal) {
+                int base = 0;
+                if (lane == 0) base = smem_atomic_add(&qn, __popc(bal));
+                base = __shfl_sync(0xffffffffu, base, 0) + __popc(bal & ((1u << lane) - 1));
+                if (corner && base < cq_cap) cq[base] = (uint16_t)e;
+            }
         }
         __syncthreads();
         // ---- 4b. NMS over the corners (all queued pixels if the corner list overflowed its buffer) ---------------
@@ -523,25 +537,19 @@ __global__ void __launch_bounds__(kSegThreads, 5) k_fast_seg(const __grid_consta
                 const int sh = cx & 31;
                 any |= (((uint64_t)__funnelshift_r(bw[1], bw[2], sh) << 32) | __funnelshift_r(bw[0], bw[1], sh)) & wmask;
             }
-            if (!__any_sync(0xffffffffu, any != 0) && lane == 0) { need[j] = 1; atomicAdd(&nneed, 1); }
+            if (!__any_sync(0xffffffffu, any != 0) && lane == 0) { need[j] = 1; smem_atomic_add(&nneed, 1); }
         }
-        fence_async_smem();   // generic-proxy accesses to the tile region (corner list) are ordered before the TMA reload
         __syncthreads();
         if (nneed == 0) break;
-        // ---- prepare pass 1: column mask of the needy cells, fresh tile (the corner list overwrote it), empty queue
+        // ---- prepare pass 1: column mask of the needy cells, empty queue (the tile is still intact) ---------------------
         {
             const int px = t - ox;
             const bool on = px >= 0 && px < tw && need[px / wcell];
             const unsigned bal = __ballot_sync(0xffffffffu, on);
             if (lane == 0) colmask[wi] = bal;
-            if (t == 0) {
-                qn = 0;
-                mbar_expect_tx(&mbar, (uint32_t)(hbox * kSegPitch));
-                tma_load_3d(tile, tmaps + sg.level, gx, kEdge + sg.y0 - 3, frame, &mbar);
-            }
+            if (t == 0) qn = 0;
         }
         __syncthreads();
-        mbar_wait(&mbar, 1);
     }
     // ---- 5. per-cell threshold vote and ordered emission ------------------------------------------------------
     const int wc = L.wcell;

@@ -16,6 +16,8 @@
 
 #include <algorithm>
 #include <string>
+#include <memory>
+#include <mutex>
 #include <vector>
 
 #include "../../include/orbgpu.h"
@@ -339,14 +341,31 @@ struct Buf {
 
 }  // namespace
 
+// The read-only tree in HBM, shared by a vocabulary handle and its forks (orbgpu_vocabulary_fork); freed with the last of them.
+struct VocTree {
+    int device = 0;
+    int32_t *d_child_off = nullptr, *d_child_ids = nullptr, *d_node_word = nullptr;
+    uint8_t* d_node_desc = nullptr;
+    double* d_node_weight = nullptr;
+    ~VocTree() {
+        cudaSetDevice(device);
+        cudaFree(d_child_off);
+        cudaFree(d_child_ids);
+        cudaFree(d_node_word);
+        cudaFree(d_node_desc);
+        cudaFree(d_node_weight);
+    }
+};
+
 struct orbgpu_vocabulary {
     int device = 0;
     int k = 0, L = 0, scoring = 0, weighting = 0;
     int n_nodes = 0, n_words = 0, max_children = 0;
+    std::shared_ptr<VocTree> tree;
+    // per-handle execution context: stream + grow-only scratch.  The host-pointer transform holds `mu` from its first copy to
+    // its last, so concurrent callers of ONE handle are serialised (never interleaved on the stream); forks run concurrently.
+    std::mutex mu;
     cudaStream_t stream = nullptr;
-    int32_t *d_child_off = nullptr, *d_child_ids = nullptr, *d_node_word = nullptr;
-    uint8_t* d_node_desc = nullptr;
-    double* d_node_weight = nullptr;
     int last_launches = 0;
     int frame_smem_set = 0;
     Buf b_kp_off, b_desc, b_feat_word, b_feat_node, b_feat_w, b_seg_node_id, b_seg_node_start, b_seg_feat, b_seg_word, b_seg_val, b_counts,
@@ -359,11 +378,6 @@ int orbgpu_vocabulary_destroy(orbgpu_vocabulary* v) {
     if (!v) return ORBGPU_OK;
     cudaSetDevice(v->device);
     if (v->stream) cudaStreamSynchronize(v->stream);
-    cudaFree(v->d_child_off);
-    cudaFree(v->d_child_ids);
-    cudaFree(v->d_node_word);
-    cudaFree(v->d_node_desc);
-    cudaFree(v->d_node_weight);
     Buf* bs[] = {&v->b_kp_off, &v->b_desc, &v->b_feat_word, &v->b_feat_node, &v->b_feat_w, &v->b_seg_node_id, &v->b_seg_node_start,
                  &v->b_seg_feat, &v->b_seg_word, &v->b_seg_val, &v->b_counts, &v->b_node_off, &v->b_word_off, &v->b_valid_off};
     for (Buf* b : bs) b->release();
@@ -414,23 +428,43 @@ int orbgpu_vocabulary_create(orbgpu_vocabulary** out, int device, int k, int L, 
     orbgpu_vocabulary* v = new orbgpu_vocabulary();
     v->device = device; v->k = k; v->L = L; v->scoring = scoring; v->weighting = weighting;
     v->n_nodes = n; v->n_words = n_words; v->max_children = max_children;
+    v->tree = std::make_shared<VocTree>();
+    VocTree* T = v->tree.get();
+    T->device = device;
     cudaError_t ce = cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking);
-    if (ce == cudaSuccess) ce = cudaMalloc((void**)&v->d_child_off, (size_t)(n + 1) * 4);
-    if (ce == cudaSuccess) ce = cudaMalloc((void**)&v->d_child_ids, (size_t)n_records * 4);
-    if (ce == cudaSuccess) ce = cudaMalloc((void**)&v->d_node_word, (size_t)n * 4);
-    if (ce == cudaSuccess) ce = cudaMalloc((void**)&v->d_node_desc, (size_t)n * 32);
-    if (ce == cudaSuccess) ce = cudaMalloc((void**)&v->d_node_weight, (size_t)n * 8);
-    if (ce == cudaSuccess) ce = cudaMemcpy(v->d_child_off, cnt.data(), (size_t)(n + 1) * 4, cudaMemcpyHostToDevice);
-    if (ce == cudaSuccess) ce = cudaMemcpy(v->d_child_ids, ids.data(), (size_t)n_records * 4, cudaMemcpyHostToDevice);
-    if (ce == cudaSuccess) ce = cudaMemcpy(v->d_node_word, word.data(), (size_t)n * 4, cudaMemcpyHostToDevice);
-    if (ce == cudaSuccess) ce = cudaMemcpy(v->d_node_desc, nd.data(), (size_t)n * 32, cudaMemcpyHostToDevice);
-    if (ce == cudaSuccess) ce = cudaMemcpy(v->d_node_weight, nw.data(), (size_t)n * 8, cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess) ce = cudaMalloc((void**)&T->d_child_off, (size_t)(n + 1) * 4);
+    if (ce == cudaSuccess) ce = cudaMalloc((void**)&T->d_child_ids, (size_t)n_records * 4);
+    if (ce == cudaSuccess) ce = cudaMalloc((void**)&T->d_node_word, (size_t)n * 4);
+    if (ce == cudaSuccess) ce = cudaMalloc((void**)&T->d_node_desc, (size_t)n * 32);
+    if (ce == cudaSuccess) ce = cudaMalloc((void**)&T->d_node_weight, (size_t)n * 8);
+    if (ce == cudaSuccess) ce = cudaMemcpy(T->d_child_off, cnt.data(), (size_t)(n + 1) * 4, cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess) ce = cudaMemcpy(T->d_child_ids, ids.data(), (size_t)n_records * 4, cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess) ce = cudaMemcpy(T->d_node_word, word.data(), (size_t)n * 4, cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess) ce = cudaMemcpy(T->d_node_desc, nd.data(), (size_t)n * 32, cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess) ce = cudaMemcpy(T->d_node_weight, nw.data(), (size_t)n * 8, cudaMemcpyHostToDevice);
     if (ce != cudaSuccess) {
         std::string msg = std::string("vocabulary upload failed: ") + cudaGetErrorString(ce);
         orbgpu_vocabulary_destroy(v);
         return og_fail(ORBGPU_ERR_CUDA, msg);
     }
     *out = v;
+    return ORBGPU_OK;
+}
+
+int orbgpu_vocabulary_fork(const orbgpu_vocabulary* v, orbgpu_vocabulary** out) {
+    if (!v || !out) return og_fail(ORBGPU_ERR_ARG, "null argument");
+    *out = nullptr;
+    OGV_CUDA(cudaSetDevice(v->device));
+    orbgpu_vocabulary* f = new orbgpu_vocabulary();
+    f->device = v->device; f->k = v->k; f->L = v->L; f->scoring = v->scoring; f->weighting = v->weighting;
+    f->n_nodes = v->n_nodes; f->n_words = v->n_words; f->max_children = v->max_children;
+    f->tree = v->tree;
+    const cudaError_t ce = cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking);
+    if (ce != cudaSuccess) {
+        delete f;
+        return og_fail(ORBGPU_ERR_CUDA, std::string("vocabulary fork: ") + cudaGetErrorString(ce));
+    }
+    *out = f;
     return ORBGPU_OK;
 }
 
@@ -483,7 +517,8 @@ int orbgpu_bow_transform_dev(orbgpu_vocabulary* v, int n_frames, const int32_t* 
     if (!bv_off) { OGV_CUDA(v->b_word_off.grab((size_t)(n_frames + 1) * 4, &wo)); } else wo = bv_off;
     OGV_CUDA(v->b_valid_off.grab((size_t)(n_frames + 1) * 4, &vo));
 
-    og::VocView V = {v->d_child_off, v->d_child_ids, v->d_node_desc, v->d_node_word, v->d_node_weight};
+    const VocTree* T = v->tree.get();
+    og::VocView V = {T->d_child_off, T->d_child_ids, T->d_node_desc, T->d_node_word, T->d_node_weight};
     const int nid_level = v->L - levelsup;
     if (n_features > 0) {
         if (v->max_children <= 16) {
@@ -529,6 +564,7 @@ int orbgpu_bow_transform(orbgpu_vocabulary* v, int n_frames, const int32_t* kp_o
     const int n = kp_off[n_frames] - kp_off[0];
     if (kp_off[0] != 0) return og_fail(ORBGPU_ERR_ARG, "bow_transform: kp_off[0] must be 0");
     if (n > 0 && !desc) return og_fail(ORBGPU_ERR_ARG, "bow_transform: null descriptors");
+    std::lock_guard<std::mutex> lock(v->mu);   // one host call at a time per handle (ORBVocabulary is shared between threads)
     OGV_CUDA(cudaSetDevice(v->device));
     cudaStream_t st = v->stream;
     void *dko, *dd;

@@ -867,6 +867,46 @@ static void test_vocabulary() {
     orbo_voc_free(o);
 }
 
+// Tracking (Frame::ComputeBoW, Tracking.cc:874) and LocalMapping (KeyFrame::ComputeBoW, LocalMapping.cc:164) call transform on ONE
+// shared ORBVocabulary from two threads: every thread must get the result of its own descriptors, for frames of different sizes
+// (different scratch sizes, so a shared scratch buffer would be reallocated under the other thread).
+static void test_vocabulary_two_threads() {
+    VocRecords V;
+    V.k = 5; V.L = 4;
+    const uint8_t zero[32] = {0};
+    grow(V, 0, zero, 1);
+    const std::string path = write_voc(V);
+    ORBVocabulary voc;
+    EXPECT(voc.loadFromTextFile(path), "loadFromTextFile failed");
+    remove(path.c_str());
+    const int kFrames = 24;
+    std::vector<cv::Mat> D(kFrames);
+    for (int f = 0; f < kFrames; ++f) {
+        const int n = 200 + (int)(rnd() % 1800);
+        D[f] = cv::Mat(n, 32, CV_8U);
+        for (int i = 0; i < n; ++i) {
+            const size_t leaf = rnd() % V.parent.size();
+            for (int b = 0; b < 32; ++b) D[f].at<uchar>(i, b) = (uint8_t)(V.desc[leaf * 32 + b] ^ ((rnd() % 9 == 0) ? (1u << (rnd() % 8)) : 0u));
+        }
+    }
+    std::vector<DBoW2::BowVector> bv1(kFrames), bv2(kFrames);
+    std::vector<DBoW2::FeatureVector> fv1(kFrames), fv2(kFrames);
+    for (int f = 0; f < kFrames; ++f) voc.transform(toDescriptorVector(D[f]), bv1[f], fv1[f], 2);   // serial results
+    std::string err;
+    auto work = [&](int first) {
+        try {
+            for (int rep = 0; rep < 6; ++rep)
+                for (int f = first; f < kFrames; f += 2) voc.transform(toDescriptorVector(D[f]), bv2[f], fv2[f], 2);
+        } catch (const std::exception& e) { err = e.what(); }
+    };
+    std::thread a(work, 0), b(work, 1);
+    a.join(); b.join();
+    int bad = 0;
+    for (int f = 0; f < kFrames; ++f) bad += !(bv1[f] == bv2[f]) || !(fv1[f] == fv2[f]);
+    EXPECT(err.empty() && bad == 0, "vocabulary on two threads: %d of %d frames differ from the serial results %s", bad, kFrames, err.c_str());
+    printf("vocabulary on two threads: %d frames x 6 rounds, %d differences\n", kFrames, bad);
+}
+
 int main() {
     int ndev = 0;
     if (orbgpu_device_count(&ndev) != 0 || ndev == 0) {
@@ -895,6 +935,7 @@ int main() {
     test_matcher();
     test_track_last_frame();
     test_vocabulary();
+    test_vocabulary_two_threads();
     test_search_for_initialization();
     test_relocalization_search();
     test_fuse();

@@ -149,3 +149,48 @@ def fuse_best(impl, ref, sizes=(3, 500, 1000, 500)):
         assert np.array_equal(want, exp["q_best_idx"]), f"Fuse seed {seed}: differs at {np.nonzero(want != exp['q_best_idx'])[0][:8]}"
         fused += int((exp["q_best_idx"] >= 0).sum())
     assert fused > 200
+
+
+# ---- committed fixtures of the reference build (tests/golden/reference_golden.npz) -------------------------------------------
+GOLDEN_SIZES = {"search_by_projection": (3, 300, 600, 1200), "search_by_bow": (4, 150, 400), "search_for_triangulation": (4, 300, 700),
+                "search_windowed": (3, 300, 600, 500), "search_for_initialization": (2, 400, 700), "fuse_best": (3, 300, 600, 400)}
+SUITE = {"search_by_projection": search_by_projection, "search_by_bow": search_by_bow, "search_for_triangulation": search_for_triangulation,
+         "search_windowed": search_windowed, "search_for_initialization": search_for_initialization, "fuse_best": fuse_best}
+
+
+class TapeRef:
+    """A MatcherRef stand-in that records (store given, inner given) or replays (inner None) the reference's results call by
+    call.  Replaying needs neither /root/reference nor libslamref.so: the fixtures were produced by the reference's own
+    ORBmatcher.cc (tests/golden/gen_reference_golden.py).  Every record carries a CRC of its inputs so drifting synthetic
+    inputs are noticed."""
+
+    def __init__(self, store, prefix, inner_factory=None):
+        self.store, self.prefix, self.inner_factory, self.n = store, prefix, inner_factory, 0
+
+    def __call__(self, nnratio=0.6, checkOri=True):
+        tape = self
+
+        class _One:
+            def __getattr__(self, name):
+                def call(*args, **kw):
+                    import zlib
+                    key = f"{tape.prefix}/{tape.n}/{name}"
+                    tape.n += 1
+                    crc = 0
+                    for a in args:
+                        for attr in ("desc", "keys_un", "u", "proj_x"):
+                            v = getattr(a, attr, None)
+                            if isinstance(v, np.ndarray):
+                                crc = zlib.crc32(np.ascontiguousarray(v).tobytes(), crc)
+                    crc = np.array([crc, int(round(nnratio * 1000)), int(checkOri)], np.int64)
+                    if tape.inner_factory is not None:
+                        res = getattr(tape.inner_factory(nnratio, checkOri), name)(*args, **kw)
+                        for k, v in res.items():
+                            tape.store[f"{key}/{k}"] = np.asarray(v)
+                        tape.store[f"{key}/_crc"] = crc
+                        return res
+                    assert np.array_equal(tape.store[f"{key}/_crc"], crc), f"{key}: inputs or parameters drifted from the fixture"
+                    pre = key + "/"
+                    return {k[len(pre):]: tape.store[k] for k in tape.store if k.startswith(pre) and not k.endswith("/_crc")}
+                return call
+        return _One()

@@ -7,8 +7,9 @@ from orb_slam2_with_comment_b200 import ORBextractor, synth
 W, H, NF = 1241, 376, 2000
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
-base = np.stack([synth.g_rects(W, H, s) for s in range(8)])
-imgs = np.concatenate([base] * (B // 8))[:B].copy()
+ND = int(sys.argv[3]) if len(sys.argv) > 3 else 64   # distinct frames
+base = np.stack([synth.g_rects(W, H, s) for s in range(min(ND, B))])
+imgs = np.concatenate([base] * ((B + len(base) - 1) // len(base)))[:B].copy()
 ex = ORBextractor(NF, 1.2, 8, 20, 7, max_width=W, max_height=H, max_batch=B)
 d_img = torch.from_numpy(imgs).cuda()
 d_kp = torch.zeros(B * ex.kp_cap * 28, dtype=torch.uint8, device="cuda")
