@@ -148,6 +148,29 @@ int orbgpu_stereo_matches_dev(orbgpu_extractor* left, orbgpu_extractor* right, f
 
 
 /* ------------------------------------------------------------------------------------------------
+ * Multi-GPU extraction inside one process (the path shards by frame; there is no exchange step and no collective):
+ * one host thread + one extractor per device; a call cuts the batch into contiguous frame ranges
+ * [g*batch/G, (g+1)*batch/G), every device runs the H2D -> kernels -> D2H pipeline of orbgpu_extract_batch on its range and
+ * writes straight into the caller's arrays at the range's offsets (host gather, input order preserved).  The results are
+ * byte-identical to orbgpu_extract_batch on one device.  `devices` = n_devices distinct CUDA device indices (NULL = 0..n-1);
+ * max_batch_per_device bounds the frames one device works on at a time (longer ranges run as several passes).  Host buffers
+ * should be page-locked (cudaHostAlloc / cudaHostRegister) for full copy bandwidth.  The handle is not thread-safe.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct orbgpu_multi_extractor orbgpu_multi_extractor;
+int orbgpu_multi_extractor_create(orbgpu_multi_extractor** out, const int* devices, int n_devices, int nfeatures, float scale_factor,
+                                  int nlevels, int ini_th_fast, int min_th_fast, int max_width, int max_height, int max_batch_per_device);
+int orbgpu_multi_extractor_destroy(orbgpu_multi_extractor* me);
+int orbgpu_multi_extractor_device_count(const orbgpu_multi_extractor* me);
+int orbgpu_multi_extractor_max_keypoints(const orbgpu_multi_extractor* me);
+/* Frames [*first, *last) of a batch that device slot g works on. */
+int orbgpu_multi_extractor_frame_range(const orbgpu_multi_extractor* me, int batch, int g, int* first, int* last);
+/* ORBextractor::operator() for `batch` frames over all devices; arguments as orbgpu_extract_batch (host pointers). */
+int orbgpu_multi_extract_batch(orbgpu_multi_extractor* me, const uint8_t* images, int batch, int width, int height, size_t row_stride,
+                               size_t frame_stride, orbgpu_keypoint* kp_out, uint8_t* desc_out, int kp_capacity, int32_t* counts);
+/* Kernels launched by the last call, summed over the devices. */
+int orbgpu_multi_extractor_last_launches(const orbgpu_multi_extractor* me);
+
+/* ------------------------------------------------------------------------------------------------
  * Matching — replaces the Hamming path of ORBmatcher (ORBmatcher.h:37-102)
  *
  * ORBmatcher's search functions read Frame / KeyFrame / MapPoint members; the C ABI takes flat, read-only views of

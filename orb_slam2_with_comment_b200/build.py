@@ -14,7 +14,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "liborbgpu.so")
-SOURCES = ["og_capi.cu", "og_match.cu", "og_vocab.cu"]
+SOURCES = ["og_capi.cu", "og_match.cu", "og_vocab.cu", "og_multi.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--fmad=false",            # bit-exact float paths (fastAtan2, rotated BRIEF, epipolar tests) are plain mul/add

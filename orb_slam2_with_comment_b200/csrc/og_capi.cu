@@ -738,13 +738,15 @@ int orbgpu_extract_batch_dev(orbgpu_extractor* ex, const uint8_t* images_dev, in
     int rc = check_call(ex, batch, width, height, row_stride, kp_capacity);
     if (rc) return rc;
     if (!images_dev || !kp_out_dev || !desc_out_dev || !counts_dev) return fail(ORBGPU_ERR_ARG, "null device pointer");
-    // Large batches are pipelined as sub-batches over the compute streams: the latency-bound octree of one sub-batch (18 % of
-    // the issue slots, ncu) runs beside the issue-bound FAST / blur / descriptor kernels of its neighbours instead of alone
-    // on the GPU.  The caller still sees one in-order stream: the side streams fork from and join ex->stream.
+    // Optional (ORBGPU_DEV_SPLIT=k): the batch as k sub-batches over the compute streams, so that the latency-bound octree of one
+    // sub-batch could run beside the issue-bound FAST / blur / descriptor kernels of its neighbours; the side streams fork from
+    // and join ex->stream.  Measured on B200 at 1024 KITTI frames: 10.24 ms unsplit, 10.93 / 10.81 / 10.82 ms for k = 2 / 4 / 8
+    // (profiles/r2_dev_split_sweep.txt) — co-resident octree CTAs take the registers FAST needs and gain nothing themselves, so
+    // the default stays one in-order sequence.
     static const int split_env = []() { const char* e = getenv("ORBGPU_DEV_SPLIT"); return e ? atoi(e) : -1; }();
     static const int nstr_env = []() { const char* e = getenv("ORBGPU_DEV_STREAMS"); return e ? atoi(e) : 0; }();
     const int min_sub = 128;
-    int nsub = split_env >= 0 ? split_env : 4;
+    int nsub = split_env >= 0 ? split_env : 1;
     if (ex->profiling || nsub <= 1 || batch < 2 * min_sub) nsub = 1;
     nsub = std::min(nsub, batch / min_sub);
     if (nsub <= 1)

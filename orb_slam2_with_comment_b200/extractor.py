@@ -165,3 +165,58 @@ class ORBextractor:
         capi.check(self._lib.orbgpu_octree(self._h, cand.ctypes.data, len(cand), min_x, max_x, min_y, max_y, n_features,
                                            out.ctypes.data, len(out), C.byref(n)))
         return out[:n.value].copy()
+
+
+class MultiGpuExtractor:
+    """ORBextractor::operator() for a batch of frames over several GPUs of one box from ONE process
+    (orbgpu_multi_extract_batch): contiguous frame ranges per device, one host thread and one copy/compute pipeline per
+    device, results gathered in input order into one host array.  No collective: frames are independent."""
+
+    def __init__(self, devices, nfeatures: int, scaleFactor: float, nlevels: int, iniThFAST: int, minThFAST: int, *,
+                 max_width: int = 1241, max_height: int = 480, max_batch_per_device: int = 256):
+        self._lib = capi.lib()
+        L = self._lib
+        vp, i, f = C.c_void_p, C.c_int, C.c_float
+        L.orbgpu_multi_extractor_create.argtypes = [C.POINTER(vp), vp, i, i, f, i, i, i, i, i, i]
+        L.orbgpu_multi_extractor_destroy.argtypes = [vp]
+        L.orbgpu_multi_extractor_device_count.argtypes = [vp]
+        L.orbgpu_multi_extractor_max_keypoints.argtypes = [vp]
+        L.orbgpu_multi_extractor_last_launches.argtypes = [vp]
+        L.orbgpu_multi_extractor_frame_range.argtypes = [vp, i, i, C.POINTER(i), C.POINTER(i)]
+        L.orbgpu_multi_extract_batch.argtypes = [vp, vp, i, i, i, C.c_size_t, C.c_size_t, vp, vp, i, vp]
+        self._h = vp()
+        dev = np.ascontiguousarray(list(devices), np.int32)
+        capi.check(L.orbgpu_multi_extractor_create(C.byref(self._h), dev.ctypes.data, len(dev), nfeatures, scaleFactor, nlevels, iniThFAST,
+                                                   minThFAST, max_width, max_height, max_batch_per_device))
+        self.devices = dev.tolist()
+        self.kp_cap = L.orbgpu_multi_extractor_max_keypoints(self._h)
+
+    def frame_range(self, batch: int, g: int):
+        a, b = C.c_int(), C.c_int()
+        capi.check(self._lib.orbgpu_multi_extractor_frame_range(self._h, batch, g, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def extract_batch(self, images: np.ndarray, kp_out=None, desc_out=None, counts=None):
+        """images: (B, H, W) uint8, C-contiguous (page-locked for full copy bandwidth).  Returns (kp (B,cap), desc (B,cap,32), counts (B,))."""
+        assert images.dtype == np.uint8 and images.ndim == 3 and images.flags.c_contiguous
+        B, H, W = images.shape
+        kp = np.zeros((B, self.kp_cap), KP_DTYPE) if kp_out is None else kp_out
+        desc = np.zeros((B, self.kp_cap, 32), np.uint8) if desc_out is None else desc_out
+        cnt = np.zeros(B, np.int32) if counts is None else counts
+        capi.check(self._lib.orbgpu_multi_extract_batch(self._h, images.ctypes.data, B, W, H, W, W * H, kp.ctypes.data, desc.ctypes.data,
+                                                        self.kp_cap, cnt.ctypes.data))
+        return kp, desc, cnt
+
+    def last_launches(self) -> int:
+        return self._lib.orbgpu_multi_extractor_last_launches(self._h)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.orbgpu_multi_extractor_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -22,7 +22,7 @@ for i in range(reps + 2):
     ex.extract_batch_dev(d_img.data_ptr(), B, W, H, d_kp.data_ptr(), d_desc.data_ptr(), d_cnt.data_ptr())
     ex.sync()
     if i >= 2:
-        acc += np.array(ex.stage_ms())
+        acc += np.array([ex.stage_ms()[k] for k in ex.STAGES])
 acc /= reps
 names = ("pyramid", "fast_cells", "octree", "blur", "orient_desc")
 print(f"B={B} " + "  ".join(f"{n} {v:.3f}" for n, v in zip(names, acc)) + f"  sum {acc.sum():.3f} ms")
