@@ -9,6 +9,9 @@
 //   SearchForInitialization(Frame&, Frame&, vbPrevMatched, ...)   replaces :493-632
 //   SearchByProjection(Frame&, KeyFrame*, set<MapPoint*>&, th, d)  replaces :1711-1849 (Relocalization)
 //   Fuse(KeyFrame*, const vector<MapPoint*>&, th)                  replaces :977-1137 (search on the GPU, map updates here)
+//   SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th)    replaces :359-491 (LoopClosing)
+//   Fuse(KeyFrame*, Scw, vpPoints, th, vpReplacePoint)             replaces :1139-1283 (LoopClosing)
+//   SearchBySim3(KeyFrame*, KeyFrame*, vpMatches12, s12, R12, t12, th)  replaces :1285-1520 (LoopClosing)
 //
 // Integration: compile this file into the ORB_SLAM2 library and remove (or #ifdef out) those four bodies from the
 // reference's ORBmatcher.cc; everything else of that file — the constructor, DescriptorDistance, the other search
@@ -493,12 +496,253 @@ int ORBmatcher::SearchForInitialization(Frame& F1, Frame& F2, std::vector<cv::Po
     return nmatches;
 }
 
-#ifdef ORBGPU_SHELL_STANDALONE
-// Builds without the reference's ORBmatcher.cc (tests): the members that file would provide.
+namespace {
+// One side of the Sim3-guided searches: every MapPoint of `points` with a pose-independent reason to be searched (`live`) is
+// projected by `project` (the reference's own cv::Mat expressions), gated exactly as the reference gates it, and turned into a
+// window query on pKF's key points.  The best-candidate search of all queries is ONE device call.
+struct BestSearch {
+    std::vector<float> qu, qv, qr;
+    std::vector<int32_t> qlo, qhi, best, bdist;
+    std::vector<uint8_t> qfl, qdesc;
+    explicit BestSearch(int n) : qu(n), qv(n), qr(n), qlo(n), qhi(n), best(n, -1), bdist(n, 256), qfl(n, 0), qdesc((size_t)n * 32, 0) {}
+    void add(int i, float u, float v, float radius, int level, MapPoint* pMP) {
+        qu[i] = u; qv[i] = v; qr[i] = radius;
+        qlo[i] = level - 1; qhi[i] = level;   // kpLevel < nPredictedLevel-1 || kpLevel > nPredictedLevel: continue
+        qfl[i] = 1;
+        const cv::Mat d = pMP->GetDescriptor();
+        std::memcpy(&qdesc[(size_t)i * 32], d.ptr(0), 32);
+    }
+    void run(KeyFrame* pKF, const char* what) {
+        const int N = (int)pKF->mvKeysUn.size(), NQ = (int)qu.size();
+        if (N == 0 || NQ == 0) return;
+        const int32_t kp_off[2] = {0, N}, q_off[2] = {0, NQ};
+        std::vector<uint8_t> tmp;
+        orbgpu_frame_set fs = one_frame(kp_off, pKF->mvKeysUn, rows32(pKF->mDescriptors, tmp));
+        const float grid[4] = {(float)pKF->mnMinX, (float)pKF->mnMinY, pKF->mfGridElementWidthInv, pKF->mfGridElementHeightInv};
+        fs.grid = grid;
+        orbgpu_window_query_set qs;
+        qs.q_off = q_off; qs.u = qu.data(); qs.v = qv.data(); qs.radius = qr.data(); qs.min_level = qlo.data(); qs.max_level = qhi.data();
+        qs.ur = nullptr; qs.flags = qfl.data(); qs.desc = qdesc.data(); qs.angle = nullptr;
+        check(orbgpu_search_window_best(matcher(), &fs, &qs, nullptr, 0, 0, best.data(), bdist.data()), what);
+    }
+};
+
+// Scw -> Rcw, tcw, Ow exactly as the reference writes it (ORBmatcher.cc:368-374, :1148-1153)
+void decompose_sim3(const cv::Mat& Scw, cv::Mat& Rcw, cv::Mat& tcw, cv::Mat& Ow) {
+    cv::Mat sRcw = Scw.rowRange(0, 3).colRange(0, 3);
+    const float scw = sqrt(sRcw.row(0).dot(sRcw.row(0)));
+    Rcw = sRcw / scw;
+    tcw = Scw.rowRange(0, 3).col(3) / scw;
+    Ow = -Rcw.t() * tcw;
+}
+
+// The gates shared by SearchByProjection(KF, Scw), Fuse(KF, Scw) (:393-436, :1175-1216): projection, image bounds, distance
+// range, viewing angle.  Returns false where the reference `continue`s.
+bool project_with_normal(KeyFrame* pKF, MapPoint* pMP, const cv::Mat& Rcw, const cv::Mat& tcw, const cv::Mat& Ow, float& u, float& v, float& dist3D) {
+    cv::Mat p3Dw = pMP->GetWorldPos();
+    cv::Mat p3Dc = Rcw * p3Dw + tcw;
+    if (p3Dc.at<float>(2) < 0.0) return false;
+    const float invz = 1 / p3Dc.at<float>(2);
+    const float x = p3Dc.at<float>(0) * invz;
+    const float y = p3Dc.at<float>(1) * invz;
+    u = pKF->fx * x + pKF->cx;
+    v = pKF->fy * y + pKF->cy;
+    if (!pKF->IsInImage(u, v)) return false;
+    const float maxDistance = pMP->GetMaxDistanceInvariance();
+    const float minDistance = pMP->GetMinDistanceInvariance();
+    cv::Mat PO = p3Dw - Ow;
+    dist3D = cv::norm(PO);
+    if (dist3D < minDistance || dist3D > maxDistance) return false;
+    cv::Mat Pn = pMP->GetNormal();
+    if (PO.dot(Pn) < 0.5 * dist3D) return false;
+    return true;
+}
+}  // namespace
+
+// SearchByProjection(pKF, Scw, vpPoints, vpMatched, th) (ORBmatcher.cc:359-491, LoopClosing::ComputeSim3): the loop map points
+// projected with the Sim3 pose; a key point that already has a match (before the call or from an earlier point of this call)
+// is skipped (:453-454), so the search is the greedy windowed one (orbgpu_search_windowed, every occupied key point blocked).
+int ORBmatcher::SearchByProjection(KeyFrame* pKF, cv::Mat Scw, const std::vector<MapPoint*>& vpPoints, std::vector<MapPoint*>& vpMatched, int th) {
+    const int N = (int)pKF->mvKeysUn.size(), NQ = (int)vpPoints.size();
+    if (N == 0 || NQ == 0) return 0;
+    cv::Mat Rcw, tcw, Ow;
+    decompose_sim3(Scw, Rcw, tcw, Ow);
+    std::set<MapPoint*> spAlreadyFound(vpMatched.begin(), vpMatched.end());
+    spAlreadyFound.erase(static_cast<MapPoint*>(NULL));
+
+    const int32_t kp_off[2] = {0, N}, q_off[2] = {0, NQ};
+    std::vector<uint8_t> tmp, kflags(N, 0);
+    orbgpu_frame_set fs = one_frame(kp_off, pKF->mvKeysUn, rows32(pKF->mDescriptors, tmp));
+    for (int i = 0; i < N; ++i)
+        if (vpMatched[i]) kflags[i] = 2;
+    fs.kp_flags = kflags.data();
+    const float grid[4] = {(float)pKF->mnMinX, (float)pKF->mnMinY, pKF->mfGridElementWidthInv, pKF->mfGridElementHeightInv};
+    fs.grid = grid;
+    BestSearch Q(NQ);
+    for (int i = 0; i < NQ; ++i) {
+        MapPoint* pMP = vpPoints[i];
+        if (pMP->isBad() || spAlreadyFound.count(pMP)) continue;      // :389-390
+        float u, v, dist;
+        if (!project_with_normal(pKF, pMP, Rcw, tcw, Ow, u, v, dist)) continue;
+        const int nPredictedLevel = pMP->PredictScale(dist, pKF);
+        Q.add(i, u, v, th * pKF->mvScaleFactors[nPredictedLevel], nPredictedLevel, pMP);   // :435
+    }
+    orbgpu_window_query_set qs;
+    qs.q_off = q_off; qs.u = Q.qu.data(); qs.v = Q.qv.data(); qs.radius = Q.qr.data(); qs.min_level = Q.qlo.data(); qs.max_level = Q.qhi.data();
+    qs.ur = nullptr; qs.flags = Q.qfl.data(); qs.desc = Q.qdesc.data(); qs.angle = nullptr;
+    std::vector<int32_t> kp_match(N, -1);
+    int32_t nmatches = 0;
+    check(orbgpu_search_windowed(matcher(), &fs, &qs, TH_LOW, /*skip_any_mappoint*/ 1, /*check_orientation*/ 0, kp_match.data(), nullptr, nullptr,
+                                 &nmatches),
+          "SearchByProjection(KeyFrame, Scw)");
+    for (int i = 0; i < N; ++i)
+        if (kp_match[i] >= 0) vpMatched[i] = vpPoints[kp_match[i]];    // :473
+    return nmatches;
+}
+
+// Fuse(pKF, Scw, vpPoints, th, vpReplacePoint) (ORBmatcher.cc:1139-1283, LoopClosing::SearchAndFuse): like Fuse(pKF, vpMapPoints,
+// th) without the chi-square gate; a point whose best key point already holds a MapPoint is reported for replacement instead of
+// being replaced here.  The search runs on the GPU for all points at once, the map updates in vector order here (a key point
+// filled by an earlier point of this call is seen by the later ones, :1262-1272).
+int ORBmatcher::Fuse(KeyFrame* pKF, cv::Mat Scw, const std::vector<MapPoint*>& vpPoints, float th, std::vector<MapPoint*>& vpReplacePoint) {
+    const int N = (int)pKF->mvKeysUn.size(), NQ = (int)vpPoints.size();
+    if (N == 0 || NQ == 0) return 0;
+    cv::Mat Rcw, tcw, Ow;
+    decompose_sim3(Scw, Rcw, tcw, Ow);
+    const std::set<MapPoint*> spAlreadyFound = pKF->GetMapPoints();   // :1157, taken before the loop
+    BestSearch Q(NQ);
+    for (int i = 0; i < NQ; ++i) {
+        MapPoint* pMP = vpPoints[i];
+        if (pMP->isBad() || spAlreadyFound.count(pMP)) continue;      // :1170-1171 (nothing in this loop changes either)
+        float u, v, dist3D;
+        if (!project_with_normal(pKF, pMP, Rcw, tcw, Ow, u, v, dist3D)) continue;
+        const int nPredictedLevel = pMP->PredictScale(dist3D, pKF);
+        Q.add(i, u, v, th * pKF->mvScaleFactors[nPredictedLevel], nPredictedLevel, pMP);   // :1215
+    }
+    Q.run(pKF, "Fuse(KeyFrame, Scw)");
+    int nFused = 0;
+    for (int i = 0; i < NQ; ++i) {
+        if (!Q.qfl[i] || Q.bdist[i] > TH_LOW) continue;                // :1259
+        MapPoint* pMP = vpPoints[i];
+        const int bestIdx = Q.best[i];
+        MapPoint* pMPinKF = pKF->GetMapPoint(bestIdx);
+        if (pMPinKF) {
+            if (!pMPinKF->isBad()) vpReplacePoint[i] = pMPinKF;
+        } else {
+            pMP->AddObservation(pKF, bestIdx);
+            pKF->AddMapPoint(pMP, bestIdx);
+        }
+        nFused++;
+    }
+    return nFused;
+}
+
+// SearchBySim3 (ORBmatcher.cc:1285-1520, LoopClosing::ComputeSim3): the map points of each key frame projected into the other
+// with the Sim3 estimate, best key point within a window (two device calls, one per direction), then the mutual-agreement
+// check (:1497-1517) here.
+int ORBmatcher::SearchBySim3(KeyFrame* pKF1, KeyFrame* pKF2, std::vector<MapPoint*>& vpMatches12, const float& s12, const cv::Mat& R12,
+                             const cv::Mat& t12, const float th) {
+    const float &fx = pKF1->fx, &fy = pKF1->fy, &cx = pKF1->cx, &cy = pKF1->cy;
+    cv::Mat R1w = pKF1->GetRotation();
+    cv::Mat t1w = pKF1->GetTranslation();
+    cv::Mat R2w = pKF2->GetRotation();
+    cv::Mat t2w = pKF2->GetTranslation();
+    cv::Mat sR12 = s12 * R12;                    // :1304-1308
+    cv::Mat sR21 = (1.0 / s12) * R12.t();
+    cv::Mat t21 = -sR21 * t12;
+
+    const std::vector<MapPoint*> vpMapPoints1 = pKF1->GetMapPointMatches();
+    const int N1 = (int)vpMapPoints1.size();
+    const std::vector<MapPoint*> vpMapPoints2 = pKF2->GetMapPointMatches();
+    const int N2 = (int)vpMapPoints2.size();
+    std::vector<bool> vbAlreadyMatched1(N1, false), vbAlreadyMatched2(N2, false);
+    for (int i = 0; i < N1; i++) {
+        MapPoint* pMP = vpMatches12[i];
+        if (pMP) {
+            vbAlreadyMatched1[i] = true;
+            const int idx2 = pMP->GetIndexInKeyFrame(pKF2);
+            if (idx2 >= 0 && idx2 < N2) vbAlreadyMatched2[idx2] = true;
+        }
+    }
+    // direction 1 -> 2 (:1337-1401)
+    BestSearch Q1(N1);
+    for (int i1 = 0; i1 < N1; i1++) {
+        MapPoint* pMP = vpMapPoints1[i1];
+        if (!pMP || vbAlreadyMatched1[i1]) continue;
+        if (pMP->isBad()) continue;
+        cv::Mat p3Dw = pMP->GetWorldPos();
+        cv::Mat p3Dc1 = R1w * p3Dw + t1w;
+        cv::Mat p3Dc2 = sR21 * p3Dc1 + t21;
+        if (p3Dc2.at<float>(2) < 0.0) continue;
+        const float invz = 1.0 / p3Dc2.at<float>(2);
+        const float x = p3Dc2.at<float>(0) * invz;
+        const float y = p3Dc2.at<float>(1) * invz;
+        const float u = fx * x + cx;
+        const float v = fy * y + cy;
+        if (!pKF2->IsInImage(u, v)) continue;
+        const float maxDistance = pMP->GetMaxDistanceInvariance();
+        const float minDistance = pMP->GetMinDistanceInvariance();
+        const float dist3D = cv::norm(p3Dc2);
+        if (dist3D < minDistance || dist3D > maxDistance) continue;
+        const int nPredictedLevel = pMP->PredictScale(dist3D, pKF2);
+        Q1.add(i1, u, v, th * pKF2->mvScaleFactors[nPredictedLevel], nPredictedLevel, pMP);
+    }
+    Q1.run(pKF2, "SearchBySim3 (1 -> 2)");
+    // direction 2 -> 1 (:1417-1481)
+    BestSearch Q2(N2);
+    for (int i2 = 0; i2 < N2; i2++) {
+        MapPoint* pMP = vpMapPoints2[i2];
+        if (!pMP || vbAlreadyMatched2[i2]) continue;
+        if (pMP->isBad()) continue;
+        cv::Mat p3Dw = pMP->GetWorldPos();
+        cv::Mat p3Dc2 = R2w * p3Dw + t2w;
+        cv::Mat p3Dc1 = sR12 * p3Dc2 + t12;
+        if (p3Dc1.at<float>(2) < 0.0) continue;
+        const float invz = 1.0 / p3Dc1.at<float>(2);
+        const float x = p3Dc1.at<float>(0) * invz;
+        const float y = p3Dc1.at<float>(1) * invz;
+        const float u = fx * x + cx;
+        const float v = fy * y + cy;
+        if (!pKF1->IsInImage(u, v)) continue;
+        const float maxDistance = pMP->GetMaxDistanceInvariance();
+        const float minDistance = pMP->GetMinDistanceInvariance();
+        const float dist3D = cv::norm(p3Dc1);
+        if (dist3D < minDistance || dist3D > maxDistance) continue;
+        const int nPredictedLevel = pMP->PredictScale(dist3D, pKF1);
+        Q2.add(i2, u, v, th * pKF1->mvScaleFactors[nPredictedLevel], nPredictedLevel, pMP);
+    }
+    Q2.run(pKF1, "SearchBySim3 (2 -> 1)");
+    // agreement (:1497-1517)
+    int nFound = 0;
+    for (int i1 = 0; i1 < N1; i1++) {
+        const int idx2 = (Q1.qfl[i1] && Q1.bdist[i1] <= TH_HIGH) ? Q1.best[i1] : -1;
+        if (idx2 >= 0) {
+            const int idx1 = (Q2.qfl[idx2] && Q2.bdist[idx2] <= TH_HIGH) ? Q2.best[idx2] : -1;
+            if (idx1 == i1) {
+                vpMatches12[i1] = vpMapPoints2[idx2];
+                nFound++;
+            }
+        }
+    }
+    return nFound;
+}
+
+#if defined(ORBGPU_SHELL_STANDALONE) || defined(ORBGPU_SHELL_REPLACES_ORBMATCHER_CC)
+// Builds without the reference's ORBmatcher.cc (tests; or a deployment that drops that file altogether, since all eleven search
+// members live here): the remaining members of the class.
 const int ORBmatcher::TH_HIGH = ORBGPU_TH_HIGH;
 const int ORBmatcher::TH_LOW = ORBGPU_TH_LOW;
 const int ORBmatcher::HISTO_LENGTH = ORBGPU_HISTO_LENGTH;
 ORBmatcher::ORBmatcher(float nnratio, bool checkOri) : mfNNratio(nnratio), mbCheckOrientation(checkOri) {}
+// ORBmatcher::DescriptorDistance (ORBmatcher.cc:1901-1917) for the CPU callers that stay CPU code (Frame::ComputeStereoMatches when
+// the extractor hook is not used, MapPoint::ComputeDistinctiveDescriptors): 256-bit Hamming distance of two descriptor rows.
+int ORBmatcher::DescriptorDistance(const cv::Mat& a, const cv::Mat& b) {
+    const uint32_t* pa = a.ptr<uint32_t>();
+    const uint32_t* pb = b.ptr<uint32_t>();
+    int dist = 0;
+    for (int i = 0; i < 8; ++i) dist += __builtin_popcount(pa[i] ^ pb[i]);
+    return dist;
+}
 #endif
 
 }  // namespace ORB_SLAM2

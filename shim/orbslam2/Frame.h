@@ -35,6 +35,10 @@ public:
     inline int PredictScale(const float& currentDist, KeyFrame* pKF);   // MapPoint.cc:404-419
     cv::Mat GetNormal() { return mNormalVector.clone(); }
     bool IsInKeyFrame(KeyFrame* pKF) { return mObservations.count(pKF) != 0; }        // MapPoint.cc:325-329
+    int GetIndexInKeyFrame(KeyFrame* pKF) {                                            // MapPoint.cc:240-246
+        std::map<KeyFrame*, size_t>::iterator it = mObservations.find(pKF);
+        return it == mObservations.end() ? -1 : (int)it->second;
+    }
     void AddObservation(KeyFrame* pKF, size_t idx) {                                   // MapPoint.cc:85-96 (monocular count)
         if (mObservations.count(pKF)) return;
         mObservations[pKF] = idx;
@@ -101,6 +105,12 @@ public:
     cv::Mat GetTranslation() { return tcw.clone(); }
     std::vector<MapPoint*> GetMapPointMatches() { return mvpMapPoints; }
     MapPoint* GetMapPoint(const size_t& idx) { return mvpMapPoints[idx]; }
+    std::set<MapPoint*> GetMapPoints() {                                                                  // KeyFrame.cc:248-261
+        std::set<MapPoint*> s;
+        for (size_t i = 0; i < mvpMapPoints.size(); ++i)
+            if (mvpMapPoints[i] && !mvpMapPoints[i]->isBad()) s.insert(mvpMapPoints[i]);
+        return s;
+    }
     void AddMapPoint(MapPoint* pMP, const size_t& idx) { mvpMapPoints[idx] = pMP; }                       // KeyFrame.cc:219-223
     bool IsInImage(const float& x, const float& y) const { return x >= mnMinX && x < mnMaxX && y >= mnMinY && y < mnMaxY; }   // KeyFrame.cc:624-627
 

@@ -91,3 +91,23 @@ def test_derived_vocabulary_equals_reference_transform_on_gpu(tmp_path):
         r = subprocess.run([DERIVED, path, dpath, levelsup], capture_output=True, text=True)
         print(r.stdout)
         assert r.returncode == 0, r.stdout + r.stderr
+
+
+TWIN = os.path.join(ROOT, "oracle", "_ref", "ref_twin_test")
+
+
+@pytest.mark.gpu
+def test_shell_members_equal_the_references_orbmatcher_on_twin_worlds():
+    """tests/cpp/ref_twin_test.cc: the ORBmatcher shell compiled against the reference's own headers and linked with the reference's
+    Frame.cc / KeyFrame.cc / MapPoint.cc / Map.cc (deployment form) vs the reference's own ORBmatcher.cc (class renamed) on twin
+    worlds of real objects — all eleven search members, complete world state compared.  Prebuilt in the build container
+    (oracle/Makefile: it needs /root/reference); travels with the snapshot."""
+    if not os.path.exists(TWIN):
+        if os.path.isdir("/root/reference"):
+            subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref"])
+        else:
+            pytest.skip("oracle/_ref/ref_twin_test not shipped")
+    r = subprocess.run([TWIN], capture_output=True, text=True)
+    print(r.stdout[-4000:])
+    assert r.returncode == 0, r.stdout[-6000:] + r.stderr[-2000:]
+    assert r.stdout.count("world state equal") >= 14 and "DIFFER" not in r.stdout
