@@ -399,6 +399,8 @@ int ensure_geometry(orbgpu_extractor* ex, int w, int h) {
         if (smem > 200 * 1024) return fail(ORBGPU_ERR_ARG, "internal: FAST tile does not fit shared memory");
         // the attribute is per function, not per handle: always allow the largest tile any geometry can ask for
         OG_CUDA(cudaFuncSetAttribute(og::k_octree<og::kOctLatThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, og::kOctSmem));
+        OG_CUDA(cudaFuncSetAttribute(og::k_octree<og::kOctThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, og::kOctSmem));
+        OG_CUDA(cudaFuncSetAttribute(og::k_octree<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, og::kOctSmem));
         OG_CUDA(cudaFuncSetAttribute(og::k_fast_seg, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      og::fast_seg_smem_bytes(og::kCellMax + 6, og::kCellMax)));
         ex->fast_smem = smem;
@@ -510,10 +512,19 @@ int launch_extract(orbgpu_extractor* ex, const uint8_t* d_images, int batch, siz
         ++launches;
     }
     {
-        if (batch <= og::kOctSmemMaxBatch)
+        // tuning hooks (development): ORBGPU_OCT_SMEM = bytes of shared-memory workspace per CTA for large batches (0 = HBM only),
+        // ORBGPU_OCT_THREADS = 128 | 256 | 512
+        static const int oct_smem_env = []() { const char* e = getenv("ORBGPU_OCT_SMEM"); return e ? atoi(e) : -1; }();
+        static const int oct_thr_env = []() { const char* e = getenv("ORBGPU_OCT_THREADS"); return e ? atoi(e) : 0; }();
+        if (batch <= og::kOctSmemMaxBatch) {
             og::k_octree<og::kOctLatThreads><<<dim3(P.n_levels, batch), og::kOctLatThreads, og::kOctSmem, st>>>(P, og::kOctSmem);
-        else
-            og::k_octree<og::kOctThreads><<<dim3(P.n_levels, batch), og::kOctThreads, 0, st>>>(P, 0);
+        } else {
+            const int sm = oct_smem_env >= 0 ? oct_smem_env : 0;
+            const int thr = oct_thr_env ? oct_thr_env : 256;   // measured at 1024 frames: 128 threads 1.62 ms, 256 1.56 ms, 512 2.19 ms
+            if (thr == 512) og::k_octree<512><<<dim3(P.n_levels, batch), 512, sm, st>>>(P, sm);
+            else if (thr == 256) og::k_octree<256><<<dim3(P.n_levels, batch), 256, sm, st>>>(P, sm);
+            else og::k_octree<og::kOctThreads><<<dim3(P.n_levels, batch), og::kOctThreads, sm, st>>>(P, sm);
+        }
     }
     ++launches;
     mark(3);
