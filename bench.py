@@ -32,6 +32,9 @@ sys.path.insert(0, ROOT)
 
 W, H, NFEATURES, NLEVELS, SCALE, INI_TH, MIN_TH = 1241, 376, 2000, 8, 1.2, 20, 7
 METRIC = "ORB frames/s @1241x376 2k feats"
+# one workload string for both arms (the reference arm runs bounded samples of the same frames; it says so in cpu_baseline.sample)
+WORKLOAD = ("synthetic KITTI-shaped 1241x376 G_rects frames (configs[0] shape, the one the metric is quoted on), "
+            "nFeatures=2000, 8 levels, scale 1.2, FAST 20/7")
 N_DISTINCT = 256  # distinct synthetic frames (seeds); larger batches tile them (every copy has its own HBM address)
 
 
@@ -376,6 +379,51 @@ def cpu_reference_run(frames: np.ndarray, threads: int, reps: int):
     return len(frames) / sec, kind, tot.value
 
 
+def opencv_primitives_timing(frames: np.ndarray) -> dict:
+    """How far the scalar cv:: shim of the CPU arm is from a real OpenCV build: the four OpenCV primitives of the hot path
+    (resize chain, copyMakeBorder, FAST with non-max suppression at iniTh, GaussianBlur 7x7) timed through cv2 (SIMD, one thread)
+    on whole level images, per frame.  It is a LOWER bound of a real build's per-frame time (no octree, orientation, descriptors
+    and no per-cell second FAST pass), reported beside the shim's per-frame, per-core time."""
+    try:
+        import cv2
+    except Exception as e:
+        return {"opencv_primitives_ms_per_frame_1thread": None, "opencv_note": f"cv2 unavailable: {e}"}
+    cv2.setNumThreads(1)
+    sizes = level_sizes()
+    fast = cv2.FastFeatureDetector_create(INI_TH, True)
+    best = 1e30
+    for _ in range(3):
+        t0 = time.perf_counter()
+        for img in frames:
+            lv = img
+            for l, (w, h) in enumerate(sizes):
+                if l:
+                    lv = cv2.resize(lv, (w, h), interpolation=cv2.INTER_LINEAR)
+                cv2.copyMakeBorder(lv, 19, 19, 19, 19, cv2.BORDER_REFLECT_101)
+                fast.detect(lv, None)
+                cv2.GaussianBlur(lv, (7, 7), 2, 2, borderType=cv2.BORDER_REFLECT_101)
+        best = min(best, (time.perf_counter() - t0) / len(frames))
+    return {"opencv_primitives_ms_per_frame_1thread": best * 1e3, "opencv_version": cv2.__version__,
+            "opencv_note": "cv2 (SIMD) resize + copyMakeBorder + FAST(iniTh, NMS) + GaussianBlur over the 8 levels, one thread: lower "
+                           "bound of a real OpenCV build's time per frame"}
+
+
+def transfer_ceiling(n_gpus: int, e2e_value: float) -> dict:
+    """The box's measured host<->device copy ceiling for this transfer pattern at n_gpus concurrent devices
+    (profiles/r2_pcie_ceiling.jsonl from tools/pcie_bw.py: pinned H2D of the images + D2H of the results at once), if recorded."""
+    path = os.path.join(ROOT, "profiles", "r2_pcie_ceiling.jsonl")
+    try:
+        for ln in open(path):
+            r = json.loads(ln)
+            if r.get("gpus") == n_gpus and not r.get("write_combined"):
+                c = float(r["frames_per_s_ceiling"])
+                return {"transfer_ceiling_frames_per_s": c, "frac_of_transfer_ceiling": e2e_value / c,
+                        "transfer_ceiling_source": "profiles/r2_pcie_ceiling.jsonl (tools/pcie_bw.py on this pool's 8xB200 box)"}
+    except Exception:
+        pass
+    return {}
+
+
 def dist_setup(n_gpus: int):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -403,11 +451,12 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": f"synthetic KITTI-shaped 1241x376 G_rects frames, nFeatures=2000, 8 levels, 1.2, FAST 20/7; "
-                               f"CPU sample of {sample} frames per step"},
-        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": kind,
-                         "sample": f"{sample} frames per step, one frame per std::thread, {cores} threads; reference ORBextractor.cc "
-                                   "compiled -O3 -march=x86-64-v3 against the cv:: shim (restated OpenCV 4.13 primitives, scalar)"},
+        "config": {"workload": WORKLOAD, "frames_per_step": sample, "parallelism": f"{cores} host threads, one frame per thread"},
+        "cpu_baseline": dict({"value": value, "unit": "frames/s", "cores": cores, "kind": kind,
+                              "sample": f"{sample} of the same frames per step, one frame per std::thread, {cores} threads; reference "
+                                        "ORBextractor.cc compiled -O3 -march=x86-64-v3 against the cv:: shim (restated OpenCV 4.13 "
+                                        "primitives, SCALAR code — a real SIMD OpenCV build is faster: see opencv_primitives_*)"},
+                             **opencv_primitives_timing(frames[:8])),
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -547,8 +596,10 @@ def run_ours(args):
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
-        try:   # DRAM bytes per frame of the stage's kernels from the committed ncu --set full capture, scaled to this launch
-            traffic = float(json.load(open(tpath))["dram_bytes_per_frame"][dominant]) * B
+        try:   # DRAM bytes per frame of the stage's kernels from the committed ncu --set full capture AT THE BENCH BATCH
+            tj = json.load(open(tpath))
+            if int(tj.get("batch", 0)) == B:
+                traffic = float(tj["dram_bytes_per_frame"][dominant]) * B
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -562,14 +613,13 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
         "data": "synthetic",
-        "config": {"workload": "synthetic KITTI-shaped 1241x376 G_rects frames (configs[0] shape, the one the metric is quoted on), "
-                               "nFeatures=2000, 8 levels, scale 1.2, FAST 20/7", "batch_per_gpu": B, "frames_per_step": world * B,
+        "config": {"workload": WORKLOAD, "batch_per_gpu": B, "frames_per_step": world * B, "distinct_frames": min(N_DISTINCT, B),
                    "parallelism": f"frame-sharded x{world}, no collective",
                    "l2_policy": f"inputs larger than L2: {B * W * H / 1e6:.0f} MB of frames + {B * 1.9:.0f} MB pyramid per step per GPU",
                    "keypoints_per_frame": kp_per_frame},
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(B * W * H),
-                "d2h_bytes_per_step": int(B * (ex.kp_cap * 60 + 4)), "ms_per_step": ms_e2e / args.steps},
+        "e2e": dict({"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(B * W * H),
+                     "d2h_bytes_per_step": int(B * (ex.kp_cap * 60 + 4)), "ms_per_step": ms_e2e / args.steps}, **transfer_ceiling(world, e2e_value)),
         "gpu_launches": ex_launches_total + (matching["gpu_launches"] if matching else 0) + (vocab["gpu_launches"] if vocab else 0),
         "roofline": roofline,
     }
@@ -581,10 +631,14 @@ def run_ours(args):
         cores = os.cpu_count() or 1
         sample = max(64, 2 * cores)
         try:
-            v, kind, _ = cpu_reference_run(make_frames(sample), cores, 2)
-            line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": cores, "kind": kind,
-                                    "sample": f"{sample} of the same frames, one frame per std::thread, {cores} threads, best of 2; "
-                                              "reference ORBextractor.cc compiled -O3 -march=x86-64-v3 against the cv:: shim"}
+            cframes = make_frames(sample)
+            v, kind, _ = cpu_reference_run(cframes, cores, 2)
+            line["cpu_baseline"] = dict({"value": v, "unit": "frames/s", "cores": cores, "kind": kind,
+                                         "ms_per_frame_per_core": 1e3 * cores / v,
+                                         "sample": f"{sample} of the same frames, one frame per std::thread, {cores} threads, best of 2; "
+                                                   "reference ORBextractor.cc compiled -O3 -march=x86-64-v3 against the cv:: shim "
+                                                   "(restated OpenCV 4.13 primitives, scalar code)"},
+                                        **opencv_primitives_timing(cframes[:8]))
         except Exception as e:  # the oracle is test infrastructure; its absence must not hide the GPU number
             line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": cores, "kind": "reference", "sample": f"unavailable: {e}"}
     print(json.dumps(line))

@@ -399,11 +399,17 @@ __global__ void __launch_bounds__(kSegThreads, 5) k_fast_seg(const __grid_consta
             // and the (+-2, +-2) diagonals), so a corner has 4 consecutive of those with |I - Ic| > t.  Twice the arithmetic of the
             // plain compass test ("2 of 4"), but it lets through half as many pixels (10 % instead of 18.6 % on the bench
             // frames; true corners are 2.8 %), and everything downstream — compaction, exact score — scales with that count.
-            auto far = [&](uint32_t c, uint32_t x) { return gt_bytes(__vabsdiffu4(c, x), kadd, big); };
+            // far(): bit 7 of every byte of the result says |c - x| > t for that pixel; the other bits are garbage and are
+            // masked once, after the AND / OR network (t < 127: carry out of the low 7 bits, or bit 7 of the difference itself;
+            // t >= 127: bit 7 and the carry).
+            auto far = [&](uint32_t c, uint32_t x) {
+                const uint32_t d = __vabsdiffu4(c, x), s = (d & 0x7f7f7f7fu) + kadd;
+                return big ? (s & d) : (s | d);
+            };
             auto run4 = [&](uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3, uint32_t m4, uint32_t m5, uint32_t m6, uint32_t m7) {
                 const uint32_t a0 = m0 & m1, a1 = m1 & m2, a2 = m2 & m3, a3 = m3 & m4, a4 = m4 & m5, a5 = m5 & m6, a6 = m6 & m7, a7 = m7 & m0;
-                const uint32_t g = (a0 & a2) | (a1 & a3) | (a2 & a4) | (a3 & a5) | (a4 & a6) | (a5 & a7) | (a6 & a0) | (a7 & a1);
-                return (((g >> 7) * 0x01020408u) >> 24) & 0xfu;   // bits 7,15,23,31 -> 4-bit value
+                const uint32_t g = ((a0 & a2) | (a1 & a3) | (a2 & a4) | (a3 & a5) | (a4 & a6) | (a5 & a7) | (a6 & a0) | (a7 & a1)) & 0x80808080u;
+                return ((g >> 7) * 0x01020408u) >> 24;   // bits 7,15,23,31 -> 4-bit value
             };
             const uint8_t* cmb = reinterpret_cast<const uint8_t*>(colmask);
             for (int u = t; u < total; u += kSegThreads) {
