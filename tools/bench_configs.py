@@ -34,9 +34,20 @@ def ev_time(stream_ptr, fn, reps, sync):
     return e0.elapsed_time(e1) / reps
 
 
-def frames(w, h, n, distinct=16):
-    base = [synth.g_rects(w, h, s) for s in range(min(distinct, n))]
-    return np.ascontiguousarray(np.stack([base[i % len(base)] for i in range(n)]))
+def frames(w, h, n, distinct=64, drift=0):
+    """n frames from `distinct` scenes; with drift > 0 consecutive frames of a scene are the same scene shifted by `drift` px
+    (so the previous frame's key points reappear), 8 frames per scene."""
+    if not drift:
+        base = [synth.g_rects(w, h, s) for s in range(min(distinct, n))]
+        return np.ascontiguousarray(np.stack([base[i % len(base)] for i in range(n)]))
+    wide = [synth.g_rects(w + 8 * drift, h, s) for s in range(min(distinct, (n + 7) // 8))]
+    return np.ascontiguousarray(np.stack([wide[(i // 8) % len(wide)][:, drift * (i % 8):drift * (i % 8) + w] for i in range(n)]))
+
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+import oracle_lib as ol   # parity assertions of the configs (the checker, never the thing measured)
+PORT = ol.load_port()
+SLAMREF = ol.load_slam_ref()
 
 
 def extract_dev(ex, imgs, w, h):
@@ -70,7 +81,7 @@ ex.close()
 W, H, NF = 640, 480, 1000
 B = max(8, int(256 * args.scale))
 ex = ORBextractor(NF, 1.2, 8, 20, 7, max_width=W, max_height=H, max_batch=B)
-imgs = frames(W, H, B)
+imgs = frames(W, H, B, drift=3)
 fn, d_kp, d_desc, d_cnt = extract_dev(ex, imgs, W, H)
 ms_ex = ev_time(ex.stream(), fn, args.reps, ex.sync)
 kp, desc, cnt = ex.extract_batch(imgs)
@@ -79,7 +90,7 @@ keys = np.concatenate([kp[f, :cnt[f]] for f in range(B)])
 descs = np.concatenate([desc[f, :cnt[f]] for f in range(B)])
 parts, mp_off = [], [0]
 for f in range(B):
-    p = f   # the local map re-observes this frame's own keypoints (projection noise N(0,2) px, 5 % descriptor bit flips)
+    p = f - 1 if f else 0   # the local map of frame f is built from the PREVIOUS frame's real extraction
     parts.append(synth.local_map(kp[p, :cnt[p]], desc[p, :cnt[p]], 5000, W, H, 7000 + f))
     mp_off.append(mp_off[-1] + 5000)
 cat = {k: np.concatenate([q[k] for q in parts]) for k in parts[0]}
@@ -94,7 +105,21 @@ ms_m = ev_time(m.stream(), fn, args.reps, m.sync)
 _, evals = m.last_stats()
 r = m.SearchByProjection(fs, mps, sf, 1.0)
 t0 = time.time(); r = m.SearchByProjection(fs, mps, sf, 1.0); ms_host = (time.time() - t0) * 1e3
-out({"config": 2, "what": f"{B} TUM 640x480 frames, 1000 features; SearchByProjection vs 5000 map points per frame (th=1, nnratio 0.8)",
+# parity of this very workload: every frame against the CPU port, the first frames against the reference's own ORBmatcher.cc
+exp = ol.MatcherOracle(PORT, 0.8, True).SearchByProjection(fs, mps, sf, 1.0)
+for k in ("nmatches", "kp_match", "mp_best_idx", "mp_best_dist", "mp_second_dist"):
+    assert np.array_equal(r[k], exp[k]), f"config 2: {k} differs from the port"
+nref = 0
+if SLAMREF is not None:
+    nref = min(B, 8)
+    fs8 = FrameSet(kp_off[:nref + 1], keys[:kp_off[nref]], descs[:kp_off[nref]], grid=np.tile(synth.frame_grid(W, H), (nref, 1)))
+    sl = slice(0, mp_off[nref])
+    mps8 = MapPointSet(np.array(mp_off[:nref + 1], np.int32), cat["proj_x"][sl], cat["proj_y"][sl], cat["view_cos"][sl], cat["level"][sl],
+                       cat["flags"][sl], cat["desc"][sl])
+    e8 = ol.MatcherRef(SLAMREF, 0.8, True).SearchByProjection(fs8, mps8, sf, 1.0)
+    assert np.array_equal(r["nmatches"][:nref], e8["nmatches"]) and np.array_equal(r["kp_match"][:kp_off[nref]], e8["kp_match"]), "config 2 differs from the reference"
+out({"config": 2, "what": f"{B} TUM 640x480 frames, 1000 features; SearchByProjection vs 5000 map points per frame built from the previous frame's extraction (th=1, nnratio 0.8)",
+     "parity": f"{B} frames bit-exact vs the CPU port, {nref} frames vs the reference's ORBmatcher.cc (libslamref.so)",
      "extract_frames_per_s": B / ms_ex * 1e3, "match_frames_per_s": B / ms_m * 1e3, "match_ms": ms_m, "match_host_call_ms": ms_host,
      "matches_per_frame": float(r["nmatches"].mean()), "distance_evals": int(evals), "matches_per_s": float(r["nmatches"].sum()) / ms_m * 1e3})
 m.release(hf); m.release_mappoints(hm); m.close(); ex.close()
@@ -130,7 +155,17 @@ d12, dd, dn = (torch.zeros(total, dtype=torch.int32, device=dev), torch.zeros(to
 fn = lambda: m.search_for_triangulation_dev(h, h, i1, i2, F12, EP, sf, s2, off, d12.data_ptr(), dd.data_ptr(), dn.data_ptr())
 ms_m = ev_time(m.stream(), fn, args.reps, m.sync)
 _, evals = m.last_stats()
-out({"config": 3, "what": f"{P} KITTI stereo pairs: extraction of {2 * (P + 1)} images, SearchForTriangulation left vs right image of every pair "
+# parity: the first pairs against the CPU port and against the reference's own SearchForTriangulation
+ncheck = min(P, 12)
+got = m.SearchForTriangulation(fs, fs, i1[:ncheck], i2[:ncheck], F12[:ncheck], EP[:ncheck], sf, s2)
+exp = ol.MatcherOracle(PORT, 0.6, False).SearchForTriangulation(fs, fs, i1[:ncheck], i2[:ncheck], F12[:ncheck], EP[:ncheck], sf, s2)
+for k in ("nmatches", "match12", "match_dist"):
+    assert np.array_equal(got[k], exp[k]), f"config 3: {k} differs from the port"
+if SLAMREF is not None:
+    e3 = ol.MatcherRef(SLAMREF, 0.6, False).SearchForTriangulation(fs, fs, i1[:ncheck], i2[:ncheck], F12[:ncheck], EP[:ncheck], sf, s2)
+    assert np.array_equal(got["nmatches"], e3["nmatches"]) and np.array_equal(got["match12"], e3["match12"]), "config 3 differs from the reference"
+out({"config": 3, "parity": f"{ncheck} pairs bit-exact vs the CPU port" + (" and the reference's ORBmatcher.cc" if SLAMREF is not None else ""),
+     "what": f"{P} KITTI stereo pairs: extraction of {2 * (P + 1)} images, SearchForTriangulation left vs right image of every pair "
      "(synthetic 10x10 vocabulary, no MapPoints, mono, checkOri off)", "extract_images_per_s": 2 * (P + 1) / ms_ex * 1e3, "pairs_per_s": P / ms_m * 1e3,
      "match_ms": ms_m, "distance_evals": int(evals), "matches_per_pair": float(dn.float().mean().item())})
 m.release(h); m.close(); ex.close()
