@@ -917,7 +917,8 @@ __global__ void __launch_bounds__(kDescWarps * 32, 6) k_orient_desc(const __grid
 
         // ---- rotated BRIEF on the blurred window
         const float ang = fmul(angle, P.factor_pi);
-        const float a = (float)cos((double)ang), b = (float)sin((double)ang);
+        float a, b;
+        sincosf_glibc(ang, &b, &a);   // a = cos, b = sin, as glibc's sincosf returns them to the reference (:113)
         mbar_wait(&bars[wi][1], phase);
         const uint8_t* b0 = bl_tile + 18 * kBlurBoxW + 18 + (blx & 15);
         int val = 0;

@@ -238,13 +238,16 @@ struct SelectArgs {
     int taken_words;       // shared-memory words of the taken mask
 };
 
-// Phase B, one warp per pair.
-__global__ void __launch_bounds__(32) k_bow_select(const __grid_constant__ BowArgs A, const __grid_constant__ SelectArgs Z) {
+// Phase B, one warp per pair, kSelectWarps pairs per CTA (the walk is sequential by definition, so throughput comes from
+// resident warps: a 32-thread CTA capped the SM at 32 pairs, 3 % occupancy in the r1 profile).
+constexpr int kSelectWarps = 4;
+__global__ void __launch_bounds__(kSelectWarps * 32) k_bow_select(const __grid_constant__ BowArgs A, const __grid_constant__ SelectArgs Z) {
     extern __shared__ uint32_t smem[];
-    uint32_t* taken = smem;
-    int* hist = (int*)(smem + Z.taken_words);
-    const int lane = threadIdx.x;
-    const int p = blockIdx.x;
+    const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+    uint32_t* taken = smem + (size_t)wi * (Z.taken_words + 32);
+    int* hist = (int*)(taken + Z.taken_words);
+    const int p = blockIdx.x * kSelectWarps + wi;
+    if (p >= A.n_pairs) return;
     const PairCtx c = pair_ctx(A.S1, A.S2, A.idx1, A.idx2, p);
     for (int i = lane; i < (c.nb + 31) / 32; i += 32) taken[i] = 0;
     hist[lane] = 0;
@@ -1334,7 +1337,7 @@ int bow_dev(orbgpu_matcher* m, const orbgpu_frame_set_dev* s1, const orbgpu_fram
     Z.entry_bin = (int8_t*)ptr;
     Z.match12 = d_match12; Z.match_dist = d_match_dist; Z.nmatches = d_nmatches;
     Z.taken_words = (P.max_nb + 31) / 32 + 1;
-    const size_t smem = ((size_t)Z.taken_words + 32) * 4;
+    const size_t smem = ((size_t)Z.taken_words + 32) * 4 * kSelectWarps;
     if (smem > 200 * 1024) return og_fail(ORBGPU_ERR_CAPACITY, "frame too large for the shared-memory taken mask");
 
     cudaStream_t st = m->stream;
@@ -1355,7 +1358,7 @@ int bow_dev(orbgpu_matcher* m, const orbgpu_frame_set_dev* s1, const orbgpu_fram
         m->last_launches += 1;
     }
     if (smem > 48 * 1024) OGM_CUDA(cudaFuncSetAttribute(k_bow_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_bow_select<<<n_pairs, 32, smem, st>>>(A, Z);
+    k_bow_select<<<(n_pairs + kSelectWarps - 1) / kSelectWarps, kSelectWarps * 32, smem, st>>>(A, Z);
     m->last_launches += 1;
     OGM_CUDA(cudaEventRecord(m->ev1, st));
     OGM_CUDA(cudaGetLastError());
