@@ -1094,6 +1094,10 @@ static int stereo_launch(orbgpu_extractor* L, orbgpu_extractor* R, float mb, flo
     if (L->last_batch < 1 || L->last_batch != R->last_batch || L->cur_w != R->cur_w || L->cur_h != R->cur_h || L->nlevels != R->nlevels ||
         L->last_stride != R->last_stride || !L->last_kp || !R->last_kp)
         return fail(ORBGPU_ERR_ARG, "stereo matching needs the left and right extractor to have just processed equally sized batches of equally sized images");
+    // the reference indexes both pyramids with the frame's single scale table (Frame.cc:598-616): the two extractors must agree on it
+    for (int l = 0; l < L->nlevels; ++l)
+        if (L->scale[l] != R->scale[l] || L->P.lv[l].w != R->P.lv[l].w || L->P.lv[l].h != R->P.lv[l].h)
+            return fail(ORBGPU_ERR_ARG, "stereo matching needs the left and right extractor to share the scale factor and the level geometry");
     if (!(mb > 0.f) || out_stride < L->last_stride) return fail(ORBGPU_ERR_ARG, "bad mb or output stride");
     if (L->last_stride > (int)og::kPosMask) return fail(ORBGPU_ERR_ARG, "too many key points per frame");
     OG_CUDA(cudaSetDevice(L->device));

@@ -67,3 +67,18 @@ def test_stereo_edge_cases(oracle):
     eur, edp, _ = ol.stereo_matches(oracle, S, 1.0, 3.0)
     assert np.array_equal(ur[0, :len(kpL)], eur) and np.array_equal(dp[0, :len(kpL)], edp)
     exL.close(); exR.close()
+
+
+def test_stereo_rejects_extractors_with_different_scale_tables():
+    """The reference indexes both pyramids with ONE scale table (Frame.cc:598-616): two extractors that disagree on the scale
+    factor must be refused instead of silently reading the wrong pixels."""
+    from orb_slam2_with_comment_b200 import ORBextractor
+    from orb_slam2_with_comment_b200.capi import OrbGpuError
+    w, h, nf = 640, 480, 1000
+    exL = ORBextractor(nf, 1.2, 8, 20, 7, max_width=w, max_height=h)
+    exR = ORBextractor(nf, 1.25, 8, 20, 7, max_width=w, max_height=h)
+    left, right = synth.stereo_pair(w, h, 6)
+    exL(left); exR(right)
+    with pytest.raises(OrbGpuError):
+        exL.stereo_matches(exR, 0.1, 40.0)
+    exL.close(); exR.close()
