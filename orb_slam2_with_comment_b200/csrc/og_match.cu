@@ -777,9 +777,17 @@ __global__ void __launch_bounds__(32) k_sbp_select(const __grid_constant__ SbpAr
             for (int j = 0; j < kTopK; ++j)
                 if (ci[j] >= 0) co[j] = A.F.keys[k0 + ci[j]].octave;
             fl = A.M.flags[q];
+            if (k[0] == kEmptyKey) {   // nothing in the window: no walk step needed, the defaults are written lane-parallel
+                if (A.mp_best_idx) A.mp_best_idx[q] = -1;
+                if (A.mp_best_dist) A.mp_best_dist[q] = 256;
+                if (A.mp_second_dist) A.mp_second_dist[q] = 256;
+            }
         }
-        const int cnt_chunk = min(32, q1 - base);
-        for (int l = 0; l < cnt_chunk; ++l) {
+        // the sequential walk only visits queries that have at least one candidate (most local map points have none)
+        unsigned act = __ballot_sync(0xffffffffu, k[0] != kEmptyKey);
+        while (act) {
+            const int l = __ffs(act) - 1;
+            act &= act - 1;
             uint32_t kk[kTopK];
             int cc[kTopK], oo[kTopK];
 #pragma unroll
@@ -878,8 +886,14 @@ __global__ void __launch_bounds__(32) k_win_select(const __grid_constant__ SbpAr
                     if (ci[j] >= 0) ca[j] = A.F.keys[k0 + ci[j]].angle;
             }
         }
-        const int cnt_chunk = min(32, q1 - base);
-        for (int l = 0; l < cnt_chunk; ++l) {
+        if (q < q1 && k[0] == kEmptyKey) {   // nothing in the window: defaults lane-parallel, no walk step
+            if (A.mp_best_idx) A.mp_best_idx[q] = -1;
+            if (A.mp_best_dist) A.mp_best_dist[q] = 256;
+        }
+        unsigned act = __ballot_sync(0xffffffffu, k[0] != kEmptyKey);
+        while (act) {
+            const int l = __ffs(act) - 1;
+            act &= act - 1;
             uint32_t kk[kTopK];
             int cc[kTopK];
             float aa[kTopK];

@@ -207,17 +207,29 @@ __global__ void __launch_bounds__(kStereoThreads) k_stereo_filter(const __grid_c
     __syncthreads();
     const int n = s_n;
     if (n == 0) return;   // the reference indexes an empty vector here (undefined); nothing to remove
+    // vDistIdx[size / 2].first after std::sort (:659-661): only the VALUE of the element of rank n/2 matters, i.e. the largest v with
+    // |{sad < v}| <= n/2 — found bit by bit with block-wide counts (17 rounds of n/256 compares per thread instead of the n^2
+    // rank counting this kernel started with: 0.52 ms -> a few microseconds per 256 frames).
     const int target = n / 2;
-    for (int i = t; i < nl; i += kStereoThreads) {
-        const int si = sad[i];
-        if (si < 0) continue;
-        int rank = 0;
-        for (int j = 0; j < nl; ++j) {
-            const int sj = sad[j];
-            rank += sj >= 0 && (sj < si || (sj == si && j < i));
+    int v = 0;
+    for (int bit = 16; bit >= 0; --bit) {   // SAD <= 121 * 2 * 255 < 2^17
+        const int cand = v + (1 << bit);
+        int below = 0;
+        for (int i = t; i < nl; i += kStereoThreads) {
+            const int si = sad[i];
+            below += si >= 0 && si < cand;
         }
-        if (rank == target) s_med = si;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) below += __shfl_xor_sync(0xffffffffu, below, d);
+        __syncthreads();   // wtot of the previous round has been read by everyone
+        if ((t & 31) == 0) wtot[t >> 5] = below;
+        __syncthreads();
+        int tot = 0;
+#pragma unroll
+        for (int k = 0; k < kStereoThreads / 32; ++k) tot += wtot[k];
+        if (tot <= target) v = cand;
     }
+    if (t == 0) s_med = v;
     __syncthreads();
     const float th = __fmul_rn(__fmul_rn(1.5f, 1.4f), (float)s_med);
     for (int i = t; i < nl; i += kStereoThreads) {
