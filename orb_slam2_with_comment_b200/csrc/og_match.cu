@@ -207,9 +207,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_bow_topk_warp(const __g
     if (A.n_sparse && *A.n_sparse == 0) return;   // every matched node pair went to the tiled kernel (which also wrote the empty lists)
     if (threadIdx.x == 0) s_evals = 0;
     __syncthreads();
-    const long long g = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     int evals = 0;
-    if (g < total_entries) {
+    // grid-stride over the queries: the grid is a few waves of CTAs, not one CTA per 8 queries (a call with a million CTAs
+    // that all exit at once still cost 0.5 ms of launch work)
+    for (long long g = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); g < total_entries; g += (long long)gridDim.x * kWarpsPerBlock) {
         const int p = upper_slot_i64(A.entry_off, 0, A.n_pairs, g);
         const PairCtx c = pair_ctx(A.S1, A.S2, A.idx1, A.idx2, p);
         const int e = (int)(g - A.entry_off[p]);
@@ -221,7 +222,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_bow_topk_warp(const __g
             uint32_t out[kTopK] = {kEmptyKey, kEmptyKey, kEmptyKey, kEmptyKey};
             const int i1 = A.S1.feat[c.fbase + e];
             const bool ok = b >= 0 && A.S1.flags && (A.S1.flags[c.ka + i1] & 1);
-            if (ok) evals = bow_scan_warp(A.S2, c.kb, b, load_desc(A.S1.desc, c.ka + i1), A.require_mp2, nullptr, A.dmax, out);
+            if (ok) evals += bow_scan_warp(A.S2, c.kb, b, load_desc(A.S1.desc, c.ka + i1), A.require_mp2, nullptr, A.dmax, out);
             if ((threadIdx.x & 31) == 0) *reinterpret_cast<uint4*>(A.topk + g * kTopK) = make_uint4(out[0], out[1], out[2], out[3]);
         }
     }
@@ -683,6 +684,7 @@ __device__ __forceinline__ int sbp_scan_warp(const SbpArgs& A, const SbpQuery& Q
             b = cs[ix * kGridRows + iy];
             n = cs[ix * kGridRows + iy + 1] - b;
         }
+        if (!__any_sync(0xffffffffu, n > 0)) continue;   // these cells hold no key point
         int inc = n;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -726,6 +728,11 @@ __device__ __forceinline__ int sbp_scan_warp(const SbpArgs& A, const SbpQuery& Q
             const uint32_t key = (dist << kPosBits) | (uint32_t)(pos0 + j);
             if (key < t[kTopK - 1]) topk_insert2(t, v, key, idx);
         }
+    }
+    if (!__any_sync(0xffffffffu, t[0] != kEmptyKey)) {   // an empty window (most local map points at th = 1): nothing to merge
+#pragma unroll
+        for (int k = 0; k < kTopK; ++k) { out[k] = kEmptyKey; outi[k] = -1; }
+        return __reduce_add_sync(0xffffffffu, evals);
     }
     warp_topk_merge2(t, v, out, outi);
     return __reduce_add_sync(0xffffffffu, evals);   // warp total, identical in every lane
@@ -1366,8 +1373,7 @@ int bow_dev(orbgpu_matcher* m, const orbgpu_frame_set_dev* s1, const orbgpu_fram
             if (rq == 8) k_bow_topk_tile<8><<<grid, kTileThreads, 0, st>>>(A); else k_bow_topk_tile<4><<<grid, kTileThreads, 0, st>>>(A);
             m->last_launches += 2;
         }
-        const long long blocks = (P.total_entries + kWarpsPerBlock - 1) / kWarpsPerBlock;
-        if (blocks > 0x7fffffffLL) return og_fail(ORBGPU_ERR_CAPACITY, "too many queries in one call");
+        const long long blocks = std::min<long long>((P.total_entries + kWarpsPerBlock - 1) / kWarpsPerBlock, (long long)m->sm_count * 64);
         k_bow_topk_warp<<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(A, P.total_entries);
         m->last_launches += 1;
     }
