@@ -16,6 +16,8 @@
 // fills through code outside the hot path (constructors that run a full extraction, UpdateNormalAndDepth, ...).
 #include "slam_world.h"
 
+#include <chrono>
+
 using namespace slamworld;
 
 namespace {
@@ -430,6 +432,43 @@ int slamref_features_in_area(const orbgpu_frame_set* fs, int f, float x, float y
     const std::vector<size_t> v = F->GetFeaturesInArea(x, y, r, min_level, max_level);
     for (size_t i = 0; i < v.size() && (int)i < capacity; ++i) out[i] = (int32_t)v[i];
     return (int)v.size();
+}
+
+// CPU baseline of the matching leg (bench.py): the reference's own ORBmatcher::SearchByBoW(KeyFrame*, KeyFrame*, ...) on n_pairs
+// key-frame pairs, one pair at a time per std::thread.  The KeyFrame / MapPoint objects are built first (untimed: in ORB-SLAM2 they
+// exist already); the returned seconds cover the search calls only.  *matches receives the sum of the return values.
+double slamref_bench_bow(const orbgpu_frame_set* s1, const orbgpu_frame_set* s2, int n_pairs, const int32_t* idx1v, const int32_t* idx2v,
+                         float nnratio, int check_orientation, int nthreads, long long* matches) {
+    const float one_scale[8] = {1.f, 1.2f, 1.44f, 1.728f, 2.0736f, 2.48832f, 2.985984f, 3.5831808f};
+    std::vector<std::unique_ptr<World> > worlds;
+    std::vector<std::pair<KeyFrame*, KeyFrame*> > kfs;
+    for (int p = 0; p < n_pairs; ++p) {
+        worlds.emplace_back(new World());
+        World& W = *worlds.back();
+        Camera cam = identity_camera(nullptr);
+        const int fa = idx1v[p], fb = idx2v[p];
+        const int ka = s1->kp_off[fa], na = s1->kp_off[fa + 1] - ka, kb = s2->kp_off[fb], nb = s2->kp_off[fb + 1] - kb;
+        Frame* F1 = W.frame(s1, fa, one_scale, 8, nullptr, cam, false);
+        Frame* F2 = W.frame(s2, fb, one_scale, 8, nullptr, cam, false);
+        if (s1->kp_flags) for (int i = 0; i < na; ++i) if (s1->kp_flags[ka + i] & 1) F1->mvpMapPoints[i] = W.occupant(1);
+        if (s2->kp_flags) for (int i = 0; i < nb; ++i) if (s2->kp_flags[kb + i] & 1) F2->mvpMapPoints[i] = W.occupant(1);
+        kfs.push_back(std::make_pair(W.keyframe(F1), W.keyframe(F2)));
+    }
+    std::vector<long long> found(nthreads, 0);
+    std::vector<std::thread> th;
+    const std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    for (int t = 0; t < nthreads; ++t)
+        th.emplace_back([&, t]() {
+            ORBmatcher matcher(nnratio, check_orientation != 0);
+            std::vector<MapPoint*> v12;
+            for (int p = t; p < n_pairs; p += nthreads) found[t] += matcher.SearchByBoW(kfs[p].first, kfs[p].second, v12);
+        });
+    for (std::thread& x : th) x.join();
+    const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    long long tot = 0;
+    for (long long v : found) tot += v;
+    if (matches) *matches = tot;
+    return sec;
 }
 
 }  // extern "C"

@@ -454,6 +454,8 @@ def load_slam_ref():
     lib.slamref_distinctive_descriptors.argtypes = [i, vp, vp, vp, vp]
     lib.slamref_stereo_frame.argtypes = [vp, vp, i, i, i, f, i, i, i, f, f, f, f, f, f, vp, vp, vp, vp, i]
     lib.slamref_features_in_area.argtypes = [FS, i, f, f, f, i, i, vp, i]
+    lib.slamref_bench_bow.restype = C.c_double
+    lib.slamref_bench_bow.argtypes = [FS, FS, i, vp, vp, f, i, i, C.POINTER(C.c_longlong)]
     return lib
 
 
@@ -525,6 +527,14 @@ class MatcherRef:
                                             m12.ctypes.data, None, nm.ctypes.data)
         assert rc == 0, rc
         return {"nmatches": nm, "match12": m12, "match_off": off}
+
+
+def ref_bench_bow(lib, set1, set2, idx1, idx2, nnratio, check_ori, threads):
+    """Seconds the reference's own ORBmatcher::SearchByBoW(KF, KF) needs for the pairs (search calls only), and the matches found."""
+    idx1, idx2 = np.ascontiguousarray(idx1, np.int32), np.ascontiguousarray(idx2, np.int32)
+    n = C.c_longlong(0)
+    sec = lib.slamref_bench_bow(C.byref(set1.c), C.byref(set2.c), len(idx1), idx1.ctypes.data, idx2.ctypes.data, nnratio, int(check_ori), threads, C.byref(n))
+    return sec, int(n.value)
 
 
 def ref_is_in_frustum(lib, cam, log_scale_factor, n_levels, viewing_cos_limit, mp_off, world_pos, normal, min_distance, max_distance):
