@@ -79,6 +79,9 @@ struct orbgpu_extractor {
     int n_btiles = 0;
     CUtensorMap* d_tmaps = nullptr;   // [4][kMaxLevels]: FAST tile boxes, blur input boxes, IC_Angle boxes (all over pyr), descriptor boxes over blur
     int fast_smem = 0;
+    int oct_direct_smem = 0;      // shared memory of the pass-free octree (max over levels, for 256 / 512 threads: [0] / [1])
+    int oct_direct_smem_lat = 0;
+    int last_octree_direct = 0;   // orbgpu_octree: 1 when the pass-free construction produced the last result
     og::Tap* d_taps = nullptr;
     int32_t *d_cell_count = nullptr, *d_sel_count = nullptr, *d_counts = nullptr;
     uint32_t *d_cand_xy = nullptr, *d_sel_xy = nullptr;
@@ -398,12 +401,21 @@ int ensure_geometry(orbgpu_extractor* ex, int w, int h) {
         OG_CUDA(cudaStreamSynchronize(ex->stream));   // `maps` is a local
         if (smem > 200 * 1024) return fail(ORBGPU_ERR_ARG, "internal: FAST tile does not fit shared memory");
         // the attribute is per function, not per handle: always allow the largest tile any geometry can ask for
-        OG_CUDA(cudaFuncSetAttribute(og::k_octree<og::kOctLatThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, og::kOctSmem));
+        OG_CUDA(cudaFuncSetAttribute(og::k_octree<og::kOctLatThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
         OG_CUDA(cudaFuncSetAttribute(og::k_octree<og::kOctThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, og::kOctSmem));
         OG_CUDA(cudaFuncSetAttribute(og::k_octree<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, og::kOctSmem));
         OG_CUDA(cudaFuncSetAttribute(og::k_fast_seg, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      og::fast_seg_smem_bytes(og::kCellMax + 6, og::kCellMax)));
         ex->fast_smem = smem;
+        int od = 0, odl = 0;
+        for (int l = 0; l < ex->nlevels; ++l) {
+            const og::Level& L = P.lv[l];
+            const int Dh = og::ot2_depth(L.n_ini, og::kOt2Budget);
+            od = std::max(od, (int)og::ot2_smem_bytes(L.n_ini, Dh, std::max(L.node_cap, 256)));
+            odl = std::max(odl, (int)og::ot2_smem_bytes(L.n_ini, Dh, std::max(L.node_cap, og::kOctLatThreads)));
+        }
+        ex->oct_direct_smem = od <= 100 * 1024 ? od : 0;        // larger than that (huge nfeatures): the general path alone
+        ex->oct_direct_smem_lat = odl <= 100 * 1024 ? odl : 0;
     }
     if (!G.taps.empty())
         OG_CUDA(cudaMemcpyAsync(ex->d_taps, G.taps.data(), G.taps.size() * sizeof(og::Tap), cudaMemcpyHostToDevice, ex->stream));
@@ -516,14 +528,18 @@ int launch_extract(orbgpu_extractor* ex, const uint8_t* d_images, int batch, siz
         // ORBGPU_OCT_THREADS = 128 | 256 | 512
         static const int oct_smem_env = []() { const char* e = getenv("ORBGPU_OCT_SMEM"); return e ? atoi(e) : -1; }();
         static const int oct_thr_env = []() { const char* e = getenv("ORBGPU_OCT_THREADS"); return e ? atoi(e) : 0; }();
+        static const int direct_env = []() { const char* e = getenv("ORBGPU_OCT_DIRECT"); return e ? atoi(e) : 1; }();
         if (batch <= og::kOctSmemMaxBatch) {
-            og::k_octree<og::kOctLatThreads><<<dim3(P.n_levels, batch), og::kOctLatThreads, og::kOctSmem, st>>>(P, og::kOctSmem);
+            const int db = direct_env ? ex->oct_direct_smem_lat : 0;
+            const int budget = std::min(og::kOctSmem, 226 * 1024 - db) & ~15;
+            og::k_octree<og::kOctLatThreads><<<dim3(P.n_levels, batch), og::kOctLatThreads, db + budget, st>>>(P, budget, db);
         } else {
             const int sm = oct_smem_env >= 0 ? oct_smem_env : 0;
-            const int thr = oct_thr_env ? oct_thr_env : 256;   // measured at 1024 frames: 128 threads 1.62 ms, 256 1.56 ms, 512 2.19 ms
-            if (thr == 512) og::k_octree<512><<<dim3(P.n_levels, batch), 512, sm, st>>>(P, sm);
-            else if (thr == 256) og::k_octree<256><<<dim3(P.n_levels, batch), 256, sm, st>>>(P, sm);
-            else og::k_octree<og::kOctThreads><<<dim3(P.n_levels, batch), og::kOctThreads, sm, st>>>(P, sm);
+            const int thr = oct_thr_env ? oct_thr_env : 256;   // measured at 1024 frames (division passes): 128 threads 1.62 ms, 256 1.56 ms, 512 2.19 ms
+            const int db = direct_env ? (thr == 512 ? ex->oct_direct_smem_lat : ex->oct_direct_smem) : 0;
+            if (thr == 512) og::k_octree<512><<<dim3(P.n_levels, batch), 512, db + sm, st>>>(P, sm, db);
+            else if (thr == 256) og::k_octree<256><<<dim3(P.n_levels, batch), 256, db + sm, st>>>(P, sm, db);
+            else og::k_octree<og::kOctThreads><<<dim3(P.n_levels, batch), og::kOctThreads, db + sm, st>>>(P, sm, db);
         }
     }
     ++launches;
@@ -1060,14 +1076,23 @@ int orbgpu_octree(orbgpu_extractor* ex, const orbgpu_keypoint* candidates, int n
     OG_CUDA(cudaMalloc((void**)&d_rr, cap));
     OG_CUDA(cudaMalloc((void**)&d_oxy, (size_t)sel_cap * 4));
     OG_CUDA(cudaMalloc((void**)&d_orr, sel_cap));
-    OG_CUDA(cudaMalloc((void**)&d_n, 4));
+    OG_CUDA(cudaMalloc((void**)&d_n, 8));
     OG_CUDA(cudaMemcpy(d_xy, xy.data(), (size_t)cap * 4, cudaMemcpyHostToDevice));
     OG_CUDA(cudaMemcpy(d_rr, rr.data(), cap, cudaMemcpyHostToDevice));
-    og::k_octree_single<<<1, og::kOctThreads, 0, ex->stream>>>(ws, cap, node_cap, d_xy, d_rr, n, n_ini, hx, height, n_features, d_oxy, d_orr, sel_cap, d_n);
+    // ORBGPU_OCT_DIRECT=0: the division-pass state machine alone (the general path the direct construction falls back to)
+    static const int direct_env = []() { const char* e = getenv("ORBGPU_OCT_DIRECT"); return e ? atoi(e) : 1; }();
+    const int Dh = og::ot2_depth(n_ini, og::kOt2Budget);
+    int direct_bytes = direct_env ? (int)og::ot2_smem_bytes(n_ini, Dh, std::max(node_cap, og::kOctThreads)) : 0;
+    if (direct_bytes > og::kOctSmem) direct_bytes = 0;
+    OG_CUDA(cudaFuncSetAttribute(og::k_octree_single, cudaFuncAttributeMaxDynamicSharedMemorySize, og::kOctSmem));
+    og::k_octree_single<<<1, og::kOctThreads, direct_bytes, ex->stream>>>(ws, cap, node_cap, d_xy, d_rr, n, n_ini, hx, height, n_features, d_oxy, d_orr,
+                                                                         sel_cap, d_n, direct_bytes);
     OG_CUDA(cudaGetLastError());
     OG_CUDA(cudaStreamSynchronize(ex->stream));
-    int m = 0;
-    OG_CUDA(cudaMemcpy(&m, d_n, 4, cudaMemcpyDeviceToHost));
+    int mm[2] = {0, 0};
+    OG_CUDA(cudaMemcpy(mm, d_n, 8, cudaMemcpyDeviceToHost));
+    const int m = mm[0];
+    ex->last_octree_direct = mm[1];
     std::vector<uint32_t> oxy(std::max(m, 1));
     std::vector<uint8_t> orr(std::max(m, 1));
     if (m) {

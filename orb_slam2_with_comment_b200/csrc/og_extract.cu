@@ -13,8 +13,11 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "../../include/orbgpu_pattern.inc"
 #include "og_octree.cuh"
+#include "og_octree2.cuh"
 #include "og_tma.cuh"
 #include "og_types.h"
 
@@ -297,6 +300,153 @@ __global__ void __launch_bounds__(kBorderThreads) k_border_caps(const __grid_con
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// DistributeOctTree: one CTA per (level, frame).  Gathers the level's candidates from the per-cell slots in
+// emission order (cell-row-major, row-major inside a cell), then runs the block-cooperative state machine.
+// ------------------------------------------------------------------------------------------------------------
+#ifndef OG_OCT_THREADS
+#define OG_OCT_THREADS 128
+#endif
+constexpr int kOctThreads = OG_OCT_THREADS;
+constexpr int kOctSmem = 160 * 1024;   // shared-memory workspace budget of one octree CTA in latency mode (small batches)
+constexpr int kOctSmemMaxBatch = 16;
+constexpr int kOctLatThreads = 512;      // CTA size in latency mode (per-thread key chunks shrink 4x; occupancy is irrelevant there)
+constexpr int kOctMaxThreads = 1024;     // sizes the per-thread scan scratch
+#ifndef OG_OT2_BUDGET
+#define OG_OT2_BUDGET 16384
+#endif
+constexpr int kOt2Budget = OG_OT2_BUDGET;   // cells of the deepest histogram level of the pass-free octree (2 bytes each)
+
+__device__ __forceinline__ OtWork carve_work(uint8_t* ws, int cap, int node_cap) {
+    OtWork W;
+    auto take = [&](size_t bytes) { uint8_t* p = ws; ws += (bytes + 15) & ~size_t(15); return p; };
+    W.kxy[0] = (uint32_t*)take((size_t)cap * 4);
+    W.kxy[1] = (uint32_t*)take((size_t)cap * 4);
+    W.knode[0] = (uint16_t*)take((size_t)cap * 2);
+    W.knode[1] = (uint16_t*)take((size_t)cap * 2);
+    W.kresp[0] = (uint8_t*)take((size_t)cap);
+    W.kresp[1] = (uint8_t*)take((size_t)cap);
+    W.nodes[0] = (OtNode*)take((size_t)node_cap * sizeof(OtNode));
+    W.nodes[1] = (OtNode*)take((size_t)node_cap * sizeof(OtNode));
+    W.tmp = (OtTmp*)take((size_t)node_cap * sizeof(OtTmp));
+    W.R[0] = (int32_t*)take((size_t)node_cap * 4);
+    W.R[1] = (int32_t*)take((size_t)node_cap * 4);
+    W.ordv = (int32_t*)take((size_t)node_cap * 4);
+    W.ordv2 = (int32_t*)take((size_t)node_cap * 4);
+    W.surv = (int32_t*)take((size_t)node_cap * 4);
+    W.thr = (int32_t*)take((size_t)kOctMaxThreads * 4 * 4);
+    W.cap = cap;
+    W.node_cap = node_cap;
+    return W;
+}
+
+// Workspace bytes of one (level, frame) for `cap` keys and `node_cap` nodes (same carving as carve_work).
+__host__ __device__ inline size_t octree_ws_bytes_dev(int cap, int node_cap) {
+    size_t b = 0;
+    auto take = [&](size_t bytes) { b += (bytes + 15) & ~size_t(15); };
+    take((size_t)cap * 4); take((size_t)cap * 4);
+    take((size_t)cap * 2); take((size_t)cap * 2);
+    take((size_t)cap); take((size_t)cap);
+    take((size_t)node_cap * sizeof(OtNode)); take((size_t)node_cap * sizeof(OtNode));
+    take((size_t)node_cap * sizeof(OtTmp));
+    for (int i = 0; i < 5; ++i) take((size_t)node_cap * 4);
+    take((size_t)kOctMaxThreads * 16);
+    return b;
+}
+
+// DistributeOctTree of one (level, frame): gathers the level's candidates from the per-cell slots in emission order, runs
+// the state machine, writes the selected keys.  Called by all threads of a CTA (k_octree, or the last k_fast_seg CTA of the
+// level).  The FAST outputs are read with ld.global.cg: in the fused kernel other CTAs wrote them during this launch, and
+// a 128-byte line at the edge of a level's slice may already sit in this SM's L1 from a neighbouring level's octree.
+// smem_budget > 0 (small batches, where the kernel's own latency is what counts): the workspace of a (level, frame) lives
+// in shared memory when it fits — data written in one phase is read in the next, which from global memory is an L2 round
+// trip (stores do not allocate in L1).  Large batches keep the workspace in HBM: there occupancy hides the latency and
+// shared memory would cut the resident CTAs per SM.
+// direct_mem != nullptr: ot2_smem_bytes() of shared memory for the pass-free construction (og_octree2.cuh), tried first.
+__device__ __forceinline__ void octree_level(const ExtractParams& P, int level, int frame, OtShared& sh, uint8_t* oct_smem, int smem_budget,
+                                             uint8_t* direct_mem = nullptr, Ot2Shared* s2 = nullptr) {
+    const Level& L = P.lv[level];
+    const int THREADS = (int)blockDim.x;
+    const int32_t* ccount = P.cell_count + (long long)frame * P.total_cells + L.cell_base;
+    bool in_smem = false;
+    int cap_s = 0;
+    if (smem_budget > 0) {
+        // number of candidates of this level = sum of the per-cell counts
+        int part = 0;
+        for (int i = threadIdx.x; i < L.n_cells; i += THREADS) part += __ldcg(ccount + i);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+        if ((threadIdx.x & 31) == 0) sh.warp_sums[threadIdx.x >> 5] = part;
+        __syncthreads();
+        int Mtot = 0;
+        for (int w = 0; w < THREADS / 32; ++w) Mtot += sh.warp_sums[w];
+        __syncthreads();
+        cap_s = max(max(Mtot, L.n_cells), 1);   // kxy[0] doubles as the cell-offset scan buffer
+        in_smem = octree_ws_bytes_dev(cap_s, L.node_cap) <= (size_t)smem_budget;
+    }
+    OtWork W = in_smem ? carve_work(oct_smem, cap_s, L.node_cap)
+                       : carve_work(P.ot_ws + (long long)frame * P.ot_frame_bytes + L.ot_base, L.cand_cap, L.node_cap);
+
+    // exclusive scan of the per-cell counts -> emission-order offsets (cells may exceed node_cap, so the scan lives in
+    // kxy[0], which is free until the root partition)
+    int32_t* coff = (int32_t*)W.kxy[0];
+    OG_FOR(i, L.n_cells) coff[i] = __ldcg(ccount + i);
+    OG_SYNC();
+    block_exscan(coff, L.n_cells, &sh);
+    const int M = sh.scan_total;
+    const uint32_t* cxy = P.cand_xy + (long long)frame * P.total_cand_cap + L.cand_base;
+    const uint8_t* crr = P.cand_resp + (long long)frame * P.total_cand_cap + L.cand_base;
+    const Cell* cells = P.cells + L.cell_base;
+    // one thread per cell copies the cell's run (a handful of candidates): all lanes busy, the loads of different
+    // cells overlap
+    for (int ci = threadIdx.x; ci < L.n_cells; ci += THREADS) {
+        const int n = __ldcg(ccount + ci), dst = coff[ci], src = cells[ci].slot;
+        for (int k = 0; k < n; ++k) {
+            W.kxy[1][dst + k] = __ldcg(cxy + src + k);
+            W.kresp[1][dst + k] = __ldcg(crr + src + k);
+        }
+    }
+    OG_SYNC();
+    uint32_t* oxy = P.sel_xy + (long long)frame * P.total_sel_cap + L.sel_base;
+    uint8_t* orr = P.sel_resp + (long long)frame * P.total_sel_cap + L.sel_base;
+    int n = -1;
+    if (direct_mem)
+        n = ot_run_direct(W.kxy[1], W.kresp[1], M, direct_mem, ot2_depth(L.n_ini, kOt2Budget), max(L.node_cap, THREADS), &sh, s2, L.n_ini, L.hx,
+                          L.det_h, L.quota, oxy, orr, L.sel_cap);
+    if (n < 0) n = ot_run(W, &sh, M, L.n_ini, L.hx, L.det_h, L.quota, oxy, orr, L.sel_cap);
+    if (threadIdx.x == 0) P.sel_count[frame * P.n_levels + level] = n;
+}
+
+// Dynamic shared memory: [direct_bytes of the pass-free construction][smem_budget of latency-mode workspace].
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_octree(const __grid_constant__ ExtractParams P, int smem_budget, int direct_bytes) {
+    extern __shared__ __align__(16) uint8_t oct_smem[];
+    __shared__ OtShared sh;
+    __shared__ Ot2Shared s2;
+    octree_level(P, blockIdx.x, P.frame0 + blockIdx.y, sh, oct_smem + direct_bytes, smem_budget, direct_bytes ? oct_smem : nullptr, &s2);
+}
+
+// Stand-alone octree on caller-provided candidates (stage-level parity tests, orbgpu_octree).  direct_bytes > 0: the pass-free
+// construction is tried first (dynamic shared memory), as in the extraction path; 0 runs the division-pass state machine alone.
+__global__ void __launch_bounds__(kOctThreads) k_octree_single(uint8_t* ws, int cap, int node_cap, const uint32_t* xy,
+                                                               const uint8_t* resp, int M, int n_ini, float hx, int height,
+                                                               int N, uint32_t* out_xy, uint8_t* out_resp, int out_cap,
+                                                               int* out_n, int direct_bytes) {
+    extern __shared__ __align__(16) uint8_t oct_smem[];
+    __shared__ OtShared sh;
+    __shared__ Ot2Shared s2;
+    OtWork W = carve_work(ws, cap, node_cap);
+    OG_FOR(i, M) { W.kxy[1][i] = xy[i]; W.kresp[1][i] = resp[i]; }
+    OG_SYNC();
+    int n = -1;
+    if (direct_bytes)
+        n = ot_run_direct(W.kxy[1], W.kresp[1], M, oct_smem, ot2_depth(n_ini, kOt2Budget), max(node_cap, kOctThreads), &sh, &s2, n_ini, hx, height, N,
+                          out_xy, out_resp, out_cap);
+    if (threadIdx.x == 0) out_n[1] = n >= 0;   // which path produced the result (tests)
+    if (n < 0) n = ot_run(W, &sh, M, n_ini, hx, height, N, out_xy, out_resp, out_cap);
+    if (threadIdx.x == 0) *out_n = n;
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // FAST per cell (:789-829): one CTA per (segment, frame), a segment being up to 8 consecutive cells of one
 // cell row.  The tile arrives by TMA.  The work is organised so that only the cheap rejection test touches every
 // pixel and everything expensive runs over a compacted queue:
@@ -393,8 +543,7 @@ __global__ void __launch_bounds__(kSegThreads, 5) k_fast_seg(const __grid_consta
         {
             const uint32_t* T = reinterpret_cast<const uint32_t*>(tile);
             const int b0 = ox >> 3, nb = ((ox + tw - 1) >> 3) - b0 + 1, total = th * nb;
-            const bool big = tcur >= 127;
-            const uint32_t kadd = (uint32_t)(big ? 0xff - tcur : 0x7f - tcur) * 0x01010101u;
+            const uint32_t kadd = (uint32_t)(tcur >= 127 ? 0xff - tcur : 0x7f - tcur) * 0x01010101u;
             // An arc of 9 contiguous ring pixels covers at least 4 CONSECUTIVE of the 8 even ring positions (the compass points
             // and the (+-2, +-2) diagonals), so a corner has 4 consecutive of those with |I - Ic| > t.  Twice the arithmetic of the
             // plain compass test ("2 of 4"), but it lets through half as many pixels (10 % instead of 18.6 % on the bench
@@ -402,6 +551,9 @@ __global__ void __launch_bounds__(kSegThreads, 5) k_fast_seg(const __grid_consta
             // far(): bit 7 of every byte of the result says |c - x| > t for that pixel; the other bits are garbage and are
             // masked once, after the AND / OR network (t < 127: carry out of the low 7 bits, or bit 7 of the difference itself;
             // t >= 127: bit 7 and the carry).
+            // The threshold class is a compile-time constant of the loop (one LOP3 per test instead of a predicated pair).
+            auto reject = [&](auto big_c) {
+            constexpr bool big = decltype(big_c)::value;
             auto far = [&](uint32_t c, uint32_t x) {
                 const uint32_t d = __vabsdiffu4(c, x), s = (d & 0x7f7f7f7fu) + kadd;
                 return big ? (s & d) : (s | d);
@@ -436,6 +588,8 @@ __global__ void __launch_bounds__(kSegThreads, 5) k_fast_seg(const __grid_consta
                 }
                 mk[r * 32 + B] = (uint8_t)m;
             }
+            };
+            if (tcur >= 127) reject(std::true_type{}); else reject(std::false_type{});
         }
         __syncthreads();
         // ---- 2. compaction of the surviving pixels into the queue (entry = tile row << 8 | tile column) ----------
@@ -613,125 +767,6 @@ __global__ void __launch_bounds__(kSegThreads, 5) k_fast_seg(const __grid_consta
         }
         if (lane == 0) P.cell_count[(long long)frame * P.total_cells + ci] = tot0 + tot1;
     }
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// DistributeOctTree: one CTA per (level, frame).  Gathers the level's candidates from the per-cell slots in
-// emission order (cell-row-major, row-major inside a cell), then runs the block-cooperative state machine.
-// ------------------------------------------------------------------------------------------------------------
-#ifndef OG_OCT_THREADS
-#define OG_OCT_THREADS 128
-#endif
-constexpr int kOctThreads = OG_OCT_THREADS;
-constexpr int kOctSmem = 160 * 1024;   // shared-memory workspace budget of one octree CTA in latency mode (small batches)
-constexpr int kOctSmemMaxBatch = 16;
-constexpr int kOctLatThreads = 512;      // CTA size in latency mode (per-thread key chunks shrink 4x; occupancy is irrelevant there)
-constexpr int kOctMaxThreads = 1024;     // sizes the per-thread scan scratch
-
-__device__ __forceinline__ OtWork carve_work(uint8_t* ws, int cap, int node_cap) {
-    OtWork W;
-    auto take = [&](size_t bytes) { uint8_t* p = ws; ws += (bytes + 15) & ~size_t(15); return p; };
-    W.kxy[0] = (uint32_t*)take((size_t)cap * 4);
-    W.kxy[1] = (uint32_t*)take((size_t)cap * 4);
-    W.knode[0] = (uint16_t*)take((size_t)cap * 2);
-    W.knode[1] = (uint16_t*)take((size_t)cap * 2);
-    W.kresp[0] = (uint8_t*)take((size_t)cap);
-    W.kresp[1] = (uint8_t*)take((size_t)cap);
-    W.nodes[0] = (OtNode*)take((size_t)node_cap * sizeof(OtNode));
-    W.nodes[1] = (OtNode*)take((size_t)node_cap * sizeof(OtNode));
-    W.tmp = (OtTmp*)take((size_t)node_cap * sizeof(OtTmp));
-    W.R[0] = (int32_t*)take((size_t)node_cap * 4);
-    W.R[1] = (int32_t*)take((size_t)node_cap * 4);
-    W.ordv = (int32_t*)take((size_t)node_cap * 4);
-    W.ordv2 = (int32_t*)take((size_t)node_cap * 4);
-    W.surv = (int32_t*)take((size_t)node_cap * 4);
-    W.thr = (int32_t*)take((size_t)kOctMaxThreads * 4 * 4);
-    W.cap = cap;
-    W.node_cap = node_cap;
-    return W;
-}
-
-// Workspace bytes of one (level, frame) for `cap` keys and `node_cap` nodes (same carving as carve_work).
-__host__ __device__ inline size_t octree_ws_bytes_dev(int cap, int node_cap) {
-    size_t b = 0;
-    auto take = [&](size_t bytes) { b += (bytes + 15) & ~size_t(15); };
-    take((size_t)cap * 4); take((size_t)cap * 4);
-    take((size_t)cap * 2); take((size_t)cap * 2);
-    take((size_t)cap); take((size_t)cap);
-    take((size_t)node_cap * sizeof(OtNode)); take((size_t)node_cap * sizeof(OtNode));
-    take((size_t)node_cap * sizeof(OtTmp));
-    for (int i = 0; i < 5; ++i) take((size_t)node_cap * 4);
-    take((size_t)kOctMaxThreads * 16);
-    return b;
-}
-
-// smem_budget > 0 (small batches, where the kernel's own latency is what counts): the workspace of a (level, frame) lives
-// in shared memory when it fits — data written in one phase is read in the next, which from global memory is an L2 round
-// trip (stores do not allocate in L1).  Large batches keep the workspace in HBM: there occupancy hides the latency and
-// shared memory would cut the resident CTAs per SM.
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS) k_octree(const __grid_constant__ ExtractParams P, int smem_budget) {
-    extern __shared__ __align__(16) uint8_t oct_smem[];
-    __shared__ OtShared sh;
-    const int level = blockIdx.x, frame = P.frame0 + blockIdx.y;
-    const Level& L = P.lv[level];
-    const int32_t* ccount = P.cell_count + (long long)frame * P.total_cells + L.cell_base;
-    bool in_smem = false;
-    int cap_s = 0;
-    if (smem_budget > 0) {
-        // number of candidates of this level = sum of the per-cell counts
-        int part = 0;
-        for (int i = threadIdx.x; i < L.n_cells; i += THREADS) part += ccount[i];
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
-        if ((threadIdx.x & 31) == 0) sh.warp_sums[threadIdx.x >> 5] = part;
-        __syncthreads();
-        int Mtot = 0;
-        for (int w = 0; w < THREADS / 32; ++w) Mtot += sh.warp_sums[w];
-        __syncthreads();
-        cap_s = max(max(Mtot, L.n_cells), 1);   // kxy[0] doubles as the cell-offset scan buffer
-        in_smem = octree_ws_bytes_dev(cap_s, L.node_cap) <= (size_t)smem_budget;
-    }
-    OtWork W = in_smem ? carve_work(oct_smem, cap_s, L.node_cap)
-                       : carve_work(P.ot_ws + (long long)frame * P.ot_frame_bytes + L.ot_base, L.cand_cap, L.node_cap);
-
-    // exclusive scan of the per-cell counts -> emission-order offsets (stored in ordv2... cells may exceed
-    // node_cap, so the scan lives in kxy[0] which is free until the root partition)
-    int32_t* coff = (int32_t*)W.kxy[0];
-    OG_FOR(i, L.n_cells) coff[i] = ccount[i];
-    OG_SYNC();
-    block_exscan(coff, L.n_cells, &sh);
-    const int M = sh.scan_total;
-    const uint32_t* cxy = P.cand_xy + (long long)frame * P.total_cand_cap + L.cand_base;
-    const uint8_t* crr = P.cand_resp + (long long)frame * P.total_cand_cap + L.cand_base;
-    const Cell* cells = P.cells + L.cell_base;
-    // one thread per cell copies the cell's run (a handful of candidates): all lanes busy, the loads of different
-    // cells overlap
-    for (int ci = threadIdx.x; ci < L.n_cells; ci += THREADS) {
-        const int n = ccount[ci], dst = coff[ci], src = cells[ci].slot;
-        for (int k = 0; k < n; ++k) {
-            W.kxy[1][dst + k] = cxy[src + k];
-            W.kresp[1][dst + k] = crr[src + k];
-        }
-    }
-    OG_SYNC();
-    uint32_t* oxy = P.sel_xy + (long long)frame * P.total_sel_cap + L.sel_base;
-    uint8_t* orr = P.sel_resp + (long long)frame * P.total_sel_cap + L.sel_base;
-    const int n = ot_run(W, &sh, M, L.n_ini, L.hx, L.det_h, L.quota, oxy, orr, L.sel_cap);
-    if (threadIdx.x == 0) P.sel_count[frame * P.n_levels + level] = n;
-}
-
-// Stand-alone octree on caller-provided candidates (stage-level parity tests, orbgpu_octree).
-__global__ void __launch_bounds__(kOctThreads) k_octree_single(uint8_t* ws, int cap, int node_cap, const uint32_t* xy,
-                                                               const uint8_t* resp, int M, int n_ini, float hx, int height,
-                                                               int N, uint32_t* out_xy, uint8_t* out_resp, int out_cap,
-                                                               int* out_n) {
-    __shared__ OtShared sh;
-    OtWork W = carve_work(ws, cap, node_cap);
-    OG_FOR(i, M) { W.kxy[1][i] = xy[i]; W.kresp[1][i] = resp[i]; }
-    OG_SYNC();
-    const int n = ot_run(W, &sh, M, n_ini, hx, height, N, out_xy, out_resp, out_cap);
-    if (threadIdx.x == 0) *out_n = n;
 }
 
 // ------------------------------------------------------------------------------------------------------------

@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "../../orb_slam2_with_comment_b200/csrc/og_octree.cuh"
+#include "../../orb_slam2_with_comment_b200/csrc/og_octree2.cuh"
 
 extern "C" int ogm_octree(const uint32_t* xy, const uint8_t* resp, int M, int width, int height, int N,
                           uint32_t* out_xy, uint8_t* out_resp, int out_cap) {
@@ -34,4 +35,24 @@ extern "C" int ogm_octree(const uint32_t* xy, const uint8_t* resp, int M, int wi
     OtShared sh;
     memset(&sh, 0, sizeof(sh));
     return ot_run(W, &sh, M, nIni, hX, height, N, out_xy, out_resp, out_cap);
+}
+
+// The pass-free construction (og_octree2.cuh).  budget = cells of the deepest histogram level.  Returns -1 when the
+// construction asks for the general path (ogm_octree).
+extern "C" int ogm_octree_direct(const uint32_t* xy, const uint8_t* resp, int M, int width, int height, int N, int budget,
+                                 uint32_t* out_xy, uint8_t* out_resp, int out_cap) {
+    using namespace og;
+    const int nIni = (int)roundf((float)width / (float)height);
+    if (nIni < 1) return -2;
+    const float hX = (float)width / (float)nIni;
+    const int node_cap = std::max(N + 3, 4 * nIni) + 8;
+    const int Dh = ot2_depth(nIni, budget);
+    const int small_cap = std::max(node_cap, OG_NTHREADS());
+    std::vector<uint8_t> mem(ot2_smem_bytes(nIni, Dh, small_cap) + 16);
+    uint8_t* base = mem.data() + ((16 - ((uintptr_t)mem.data() & 15)) & 15);
+    OtShared sh;
+    Ot2Shared s2;
+    memset(&sh, 0, sizeof(sh));
+    memset(&s2, 0, sizeof(s2));
+    return ot_run_direct(xy, resp, M, base, Dh, small_cap, &sh, &s2, nIni, hX, height, N, out_xy, out_resp, out_cap);
 }

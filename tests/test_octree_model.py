@@ -19,10 +19,12 @@ def model():
     src = os.path.join(HERE, "host_model", "octree_model.cc")
     out = os.path.join(HERE, "host_model", "libogmodel.so")
     hdr = os.path.join(HERE, "..", "orb_slam2_with_comment_b200", "csrc", "og_octree.cuh")
-    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    hdr2 = os.path.join(HERE, "..", "orb_slam2_with_comment_b200", "csrc", "og_octree2.cuh")
+    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(hdr), os.path.getmtime(hdr2)):
         subprocess.check_call(["g++", "-std=c++14", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-x", "c++", src, "-o", out])
     lib = C.CDLL(out)
     lib.ogm_octree.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    lib.ogm_octree_direct.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
     return lib
 
 
@@ -37,11 +39,37 @@ def run_model(lib, cand, width, height, N):
     return (oxy[:n] & 0xffff).astype(np.float32), (oxy[:n] >> 16).astype(np.float32), orr[:n].astype(np.float32)
 
 
+def run_direct(lib, cand, width, height, N, budget):
+    """The pass-free construction (og_octree2.cuh); None when it hands the case to the division-pass path."""
+    xy = (cand["y"].astype(np.uint32) << 16) | cand["x"].astype(np.uint32)
+    resp = cand["response"].astype(np.uint8)
+    cap = N + 1024
+    oxy = np.zeros(cap, np.uint32)
+    orr = np.zeros(cap, np.uint8)
+    n = lib.ogm_octree_direct(xy.ctypes.data, resp.ctypes.data, len(cand), width, height, N, budget, oxy.ctypes.data, orr.ctypes.data, cap)
+    assert n >= -1
+    if n < 0:
+        return None
+    return (oxy[:n] & 0xffff).astype(np.float32), (oxy[:n] >> 16).astype(np.float32), orr[:n].astype(np.float32)
+
+
+DIRECT_STATS = {"direct": 0, "fallback": 0}
+
+
 def check(lib, oracle, cand, width, height, N):
     exp = ol.octree(oracle, "orbo", cand, 16, 16 + width, 16, 16 + height, N)
     x, y, r = run_model(lib, cand, width, height, N)
     assert len(x) == len(exp)
     assert np.array_equal(x, exp["x"]) and np.array_equal(y, exp["y"]) and np.array_equal(r, exp["response"])
+    # the pass-free construction, with a small and with the product's histogram: equal whenever it answers
+    for budget in (256, 16384):
+        got = run_direct(lib, cand, width, height, N, budget)
+        if got is None:
+            DIRECT_STATS["fallback"] += 1
+            continue
+        DIRECT_STATS["direct"] += 1
+        assert len(got[0]) == len(exp)
+        assert np.array_equal(got[0], exp["x"]) and np.array_equal(got[1], exp["y"]) and np.array_equal(got[2], exp["response"])
     return len(exp)
 
 
@@ -57,6 +85,10 @@ def test_model_on_real_candidates(model, oracle, shape):
             lw, lh = ex.level(l).shape[1], ex.level(l).shape[0]
             n = check(model, oracle, cand, lw - 32, lh - 32, int(quota[l]))
             assert n <= max(int(quota[l]) + 3, 4 * round((lw - 32) / (lh - 32)))
+            # candidate sets of the benchmark shapes never need the general path with the product's histogram (4000 features on
+            # a 320x240 image divide down to single pixels: that one hands over)
+            if nf <= 2000:
+                assert run_direct(model, cand, lw - 32, lh - 32, int(quota[l]), 16384) is not None
 
 
 def test_model_random_stress(model, oracle, refso):
@@ -84,3 +116,20 @@ def test_model_random_stress(model, oracle, refso):
         a = ol.octree(oracle, "orbo", cand, 16, 16 + width, 16, 16 + height, N)
         b = ol.octree(refso, "orbref", cand, 16, 16 + width, 16, 16 + height, N)
         assert a.tobytes() == b.tobytes()
+
+
+def test_direct_construction_answers_most_cases(model, oracle):
+    """The stress above must have exercised both outcomes of the pass-free construction (answers and hand-overs)."""
+    rs = np.random.RandomState(11)
+    for it in range(60):
+        width, height = int(rs.randint(200, 1300)), int(rs.randint(100, 400))
+        if round(width / height) < 1:
+            continue
+        M, N = int(rs.randint(200, 5000)), int(rs.randint(20, 600))
+        pts = np.unique(np.stack([rs.randint(3, height - 3, M), rs.randint(3, width - 3, M)], 1), axis=0)
+        pts = pts[rs.permutation(len(pts))]
+        cand = np.zeros(len(pts), ol.KP_DTYPE)
+        cand["x"], cand["y"] = pts[:, 1], pts[:, 0]
+        cand["response"] = rs.randint(7, 255, len(pts))
+        check(model, oracle, cand, width, height, N)
+    assert DIRECT_STATS["direct"] > 100 and DIRECT_STATS["fallback"] > 0, DIRECT_STATS
