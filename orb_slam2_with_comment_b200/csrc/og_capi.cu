@@ -81,6 +81,7 @@ struct orbgpu_extractor {
     int fast_smem = 0;
     int oct_direct_smem = 0;      // shared memory of the pass-free octree (max over levels, for 256 / 512 threads: [0] / [1])
     int oct_direct_smem_lat = 0;
+    int oct_kcap = 0, oct_kcap_lat = 0;   // keys whose path codes the pass-free octree caches in shared memory
     int last_octree_direct = 0;   // orbgpu_octree: 1 when the pass-free construction produced the last result
     og::Tap* d_taps = nullptr;
     int32_t *d_cell_count = nullptr, *d_sel_count = nullptr, *d_counts = nullptr;
@@ -407,13 +408,22 @@ int ensure_geometry(orbgpu_extractor* ex, int w, int h) {
         OG_CUDA(cudaFuncSetAttribute(og::k_fast_seg, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      og::fast_seg_smem_bytes(og::kCellMax + 6, og::kCellMax)));
         ex->fast_smem = smem;
-        int od = 0, odl = 0;
+        // shared memory of the pass-free octree: histogram + node arrays (max over levels) + cell offsets + a cache of path codes
+        // for as many keys as fit into kOctDirectSmem (3 bytes each)
+        int od = 0, odl = 0, cells_max = 0;
         for (int l = 0; l < ex->nlevels; ++l) {
             const og::Level& L = P.lv[l];
             const int Dh = og::ot2_depth(L.n_ini, og::kOt2Budget);
-            od = std::max(od, (int)og::ot2_smem_bytes(L.n_ini, Dh, std::max(L.node_cap, 256)));
-            odl = std::max(odl, (int)og::ot2_smem_bytes(L.n_ini, Dh, std::max(L.node_cap, og::kOctLatThreads)));
+            od = std::max(od, (int)og::ot2_smem_bytes(L.n_ini, Dh, std::max(L.node_cap, 256), 0));
+            odl = std::max(odl, (int)og::ot2_smem_bytes(L.n_ini, Dh, std::max(L.node_cap, og::kOctLatThreads), 0));
+            cells_max = std::max(cells_max, L.n_cells);
         }
+        const int coff_bytes = 4 * cells_max + 16;
+        auto kcap_for = [&](int base, int budget) { return std::max(0, std::min(16384, (budget - base - coff_bytes) / 3)) & ~15; };
+        ex->oct_kcap = kcap_for(od, og::kOctDirectSmem);
+        ex->oct_kcap_lat = kcap_for(odl, 96 * 1024);
+        od += 3 * ex->oct_kcap + coff_bytes;
+        odl += 3 * ex->oct_kcap_lat + coff_bytes;
         ex->oct_direct_smem = od <= 100 * 1024 ? od : 0;        // larger than that (huge nfeatures): the general path alone
         ex->oct_direct_smem_lat = odl <= 100 * 1024 ? odl : 0;
     }
@@ -532,14 +542,15 @@ int launch_extract(orbgpu_extractor* ex, const uint8_t* d_images, int batch, siz
         if (batch <= og::kOctSmemMaxBatch) {
             const int db = direct_env ? ex->oct_direct_smem_lat : 0;
             const int budget = std::min(og::kOctSmem, 226 * 1024 - db) & ~15;
-            og::k_octree<og::kOctLatThreads><<<dim3(P.n_levels, batch), og::kOctLatThreads, db + budget, st>>>(P, budget, db);
+            og::k_octree<og::kOctLatThreads><<<dim3(P.n_levels, batch), og::kOctLatThreads, db + budget, st>>>(P, budget, db, ex->oct_kcap_lat);
         } else {
             const int sm = oct_smem_env >= 0 ? oct_smem_env : 0;
             const int thr = oct_thr_env ? oct_thr_env : 256;   // measured at 1024 frames (division passes): 128 threads 1.62 ms, 256 1.56 ms, 512 2.19 ms
             const int db = direct_env ? (thr == 512 ? ex->oct_direct_smem_lat : ex->oct_direct_smem) : 0;
-            if (thr == 512) og::k_octree<512><<<dim3(P.n_levels, batch), 512, db + sm, st>>>(P, sm, db);
-            else if (thr == 256) og::k_octree<256><<<dim3(P.n_levels, batch), 256, db + sm, st>>>(P, sm, db);
-            else og::k_octree<og::kOctThreads><<<dim3(P.n_levels, batch), og::kOctThreads, db + sm, st>>>(P, sm, db);
+            const int kc = thr == 512 ? ex->oct_kcap_lat : ex->oct_kcap;
+            if (thr == 512) og::k_octree<512><<<dim3(P.n_levels, batch), 512, db + sm, st>>>(P, sm, db, kc);
+            else if (thr == 256) og::k_octree<256><<<dim3(P.n_levels, batch), 256, db + sm, st>>>(P, sm, db, kc);
+            else og::k_octree<og::kOctThreads><<<dim3(P.n_levels, batch), og::kOctThreads, db + sm, st>>>(P, sm, db, kc);
         }
     }
     ++launches;
@@ -1082,11 +1093,12 @@ int orbgpu_octree(orbgpu_extractor* ex, const orbgpu_keypoint* candidates, int n
     // ORBGPU_OCT_DIRECT=0: the division-pass state machine alone (the general path the direct construction falls back to)
     static const int direct_env = []() { const char* e = getenv("ORBGPU_OCT_DIRECT"); return e ? atoi(e) : 1; }();
     const int Dh = og::ot2_depth(n_ini, og::kOt2Budget);
-    int direct_bytes = direct_env ? (int)og::ot2_smem_bytes(n_ini, Dh, std::max(node_cap, og::kOctThreads)) : 0;
+    const int kcap = 4096;
+    int direct_bytes = direct_env ? (int)og::ot2_smem_bytes(n_ini, Dh, std::max(node_cap, og::kOctThreads), kcap) : 0;
     if (direct_bytes > og::kOctSmem) direct_bytes = 0;
     OG_CUDA(cudaFuncSetAttribute(og::k_octree_single, cudaFuncAttributeMaxDynamicSharedMemorySize, og::kOctSmem));
     og::k_octree_single<<<1, og::kOctThreads, direct_bytes, ex->stream>>>(ws, cap, node_cap, d_xy, d_rr, n, n_ini, hx, height, n_features, d_oxy, d_orr,
-                                                                         sel_cap, d_n, direct_bytes);
+                                                                         sel_cap, d_n, direct_bytes, kcap);
     OG_CUDA(cudaGetLastError());
     OG_CUDA(cudaStreamSynchronize(ex->stream));
     int mm[2] = {0, 0};

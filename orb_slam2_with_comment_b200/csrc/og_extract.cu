@@ -314,6 +314,7 @@ constexpr int kOctMaxThreads = 1024;     // sizes the per-thread scan scratch
 #ifndef OG_OT2_BUDGET
 #define OG_OT2_BUDGET 16384
 #endif
+constexpr int kOctDirectSmem = 74 * 1024;    // shared memory of one CTA of the pass-free octree (three CTAs per SM)
 constexpr int kOt2Budget = OG_OT2_BUDGET;   // cells of the deepest histogram level of the pass-free octree (2 bytes each)
 
 __device__ __forceinline__ OtWork carve_work(uint8_t* ws, int cap, int node_cap) {
@@ -353,76 +354,81 @@ __host__ __device__ inline size_t octree_ws_bytes_dev(int cap, int node_cap) {
     return b;
 }
 
-// DistributeOctTree of one (level, frame): gathers the level's candidates from the per-cell slots in emission order, runs
-// the state machine, writes the selected keys.  Called by all threads of a CTA (k_octree, or the last k_fast_seg CTA of the
-// level).  The FAST outputs are read with ld.global.cg: in the fused kernel other CTAs wrote them during this launch, and
-// a 128-byte line at the edge of a level's slice may already sit in this SM's L1 from a neighbouring level's octree.
-// smem_budget > 0 (small batches, where the kernel's own latency is what counts): the workspace of a (level, frame) lives
+// DistributeOctTree of one (level, frame): reads the level's candidates from the per-cell slots in emission order, writes the
+// selected keys.  Called by all threads of a CTA.
+// smem_budget > 0 (small batches, where the kernel's own latency is what counts): the workspace of the general path lives
 // in shared memory when it fits — data written in one phase is read in the next, which from global memory is an L2 round
-// trip (stores do not allocate in L1).  Large batches keep the workspace in HBM: there occupancy hides the latency and
-// shared memory would cut the resident CTAs per SM.
-// direct_mem != nullptr: ot2_smem_bytes() of shared memory for the pass-free construction (og_octree2.cuh), tried first.
+// trip (stores do not allocate in L1).  Large batches keep that workspace in HBM.
+// direct_mem != nullptr: shared memory for the pass-free construction (og_octree2.cuh), tried first: ot2_smem_bytes() followed
+// by 4 * n_cells bytes for the emission-order offsets of the cells.  It reads the candidates where k_fast_seg left them.
 __device__ __forceinline__ void octree_level(const ExtractParams& P, int level, int frame, OtShared& sh, uint8_t* oct_smem, int smem_budget,
-                                             uint8_t* direct_mem = nullptr, Ot2Shared* s2 = nullptr) {
+                                             uint8_t* direct_mem = nullptr, Ot2Shared* s2 = nullptr, int direct_kcap = 0) {
     const Level& L = P.lv[level];
     const int THREADS = (int)blockDim.x;
     const int32_t* ccount = P.cell_count + (long long)frame * P.total_cells + L.cell_base;
-    bool in_smem = false;
-    int cap_s = 0;
-    if (smem_budget > 0) {
-        // number of candidates of this level = sum of the per-cell counts
-        int part = 0;
-        for (int i = threadIdx.x; i < L.n_cells; i += THREADS) part += __ldcg(ccount + i);
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
-        if ((threadIdx.x & 31) == 0) sh.warp_sums[threadIdx.x >> 5] = part;
-        __syncthreads();
-        int Mtot = 0;
-        for (int w = 0; w < THREADS / 32; ++w) Mtot += sh.warp_sums[w];
-        __syncthreads();
-        cap_s = max(max(Mtot, L.n_cells), 1);   // kxy[0] doubles as the cell-offset scan buffer
-        in_smem = octree_ws_bytes_dev(cap_s, L.node_cap) <= (size_t)smem_budget;
-    }
-    OtWork W = in_smem ? carve_work(oct_smem, cap_s, L.node_cap)
-                       : carve_work(P.ot_ws + (long long)frame * P.ot_frame_bytes + L.ot_base, L.cand_cap, L.node_cap);
-
-    // exclusive scan of the per-cell counts -> emission-order offsets (cells may exceed node_cap, so the scan lives in
-    // kxy[0], which is free until the root partition)
-    int32_t* coff = (int32_t*)W.kxy[0];
-    OG_FOR(i, L.n_cells) coff[i] = __ldcg(ccount + i);
-    OG_SYNC();
-    block_exscan(coff, L.n_cells, &sh);
-    const int M = sh.scan_total;
     const uint32_t* cxy = P.cand_xy + (long long)frame * P.total_cand_cap + L.cand_base;
     const uint8_t* crr = P.cand_resp + (long long)frame * P.total_cand_cap + L.cand_base;
     const Cell* cells = P.cells + L.cell_base;
-    // one thread per cell copies the cell's run (a handful of candidates): all lanes busy, the loads of different
-    // cells overlap
-    for (int ci = threadIdx.x; ci < L.n_cells; ci += THREADS) {
-        const int n = __ldcg(ccount + ci), dst = coff[ci], src = cells[ci].slot;
-        for (int k = 0; k < n; ++k) {
-            W.kxy[1][dst + k] = __ldcg(cxy + src + k);
-            W.kresp[1][dst + k] = __ldcg(crr + src + k);
-        }
-    }
-    OG_SYNC();
     uint32_t* oxy = P.sel_xy + (long long)frame * P.total_sel_cap + L.sel_base;
     uint8_t* orr = P.sel_resp + (long long)frame * P.total_sel_cap + L.sel_base;
     int n = -1;
-    if (direct_mem)
-        n = ot_run_direct(W.kxy[1], W.kresp[1], M, direct_mem, ot2_depth(L.n_ini, kOt2Budget), max(L.node_cap, THREADS), &sh, s2, L.n_ini, L.hx,
-                          L.det_h, L.quota, oxy, orr, L.sel_cap);
-    if (n < 0) n = ot_run(W, &sh, M, L.n_ini, L.hx, L.det_h, L.quota, oxy, orr, L.sel_cap);
+    if (direct_mem) {
+        const int Dh = ot2_depth(L.n_ini, kOt2Budget), small_cap = max(L.node_cap, THREADS);
+        int32_t* coff = reinterpret_cast<int32_t*>(direct_mem + ot2_smem_bytes(L.n_ini, Dh, small_cap, direct_kcap));
+        OG_FOR(i, L.n_cells) coff[i] = ccount[i];
+        OG_SYNC();
+        block_exscan(coff, L.n_cells, &sh);
+        const Ot2CellKeys keys{coff, cells, cxy, crr, L.n_cells};
+        n = ot_run_direct(keys, sh.scan_total, direct_mem, Dh, small_cap, direct_kcap, &sh, s2, L.n_ini, L.hx, L.det_h, L.quota, oxy, orr, L.sel_cap);
+    }
+    if (n < 0) {
+        // the general path: division passes over a workspace of keys
+        bool in_smem = false;
+        int cap_s = 0;
+        if (smem_budget > 0) {
+            // number of candidates of this level = sum of the per-cell counts
+            int part = 0;
+            for (int i = threadIdx.x; i < L.n_cells; i += THREADS) part += ccount[i];
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+            if ((threadIdx.x & 31) == 0) sh.warp_sums[threadIdx.x >> 5] = part;
+            __syncthreads();
+            int Mtot = 0;
+            for (int w = 0; w < THREADS / 32; ++w) Mtot += sh.warp_sums[w];
+            __syncthreads();
+            cap_s = max(max(Mtot, L.n_cells), 1);   // kxy[0] doubles as the cell-offset scan buffer
+            in_smem = octree_ws_bytes_dev(cap_s, L.node_cap) <= (size_t)smem_budget;
+        }
+        OtWork W = in_smem ? carve_work(oct_smem, cap_s, L.node_cap)
+                           : carve_work(P.ot_ws + (long long)frame * P.ot_frame_bytes + L.ot_base, L.cand_cap, L.node_cap);
+        // exclusive scan of the per-cell counts -> emission-order offsets (cells may exceed node_cap, so the scan lives in
+        // kxy[0], which is free until the root partition)
+        int32_t* coff = (int32_t*)W.kxy[0];
+        OG_FOR(i, L.n_cells) coff[i] = ccount[i];
+        OG_SYNC();
+        block_exscan(coff, L.n_cells, &sh);
+        const int M = sh.scan_total;
+        // one thread per cell copies the cell's run (a handful of candidates)
+        for (int ci = threadIdx.x; ci < L.n_cells; ci += THREADS) {
+            const int nk = ccount[ci], dst = coff[ci], src = cells[ci].slot;
+            for (int k = 0; k < nk; ++k) {
+                W.kxy[1][dst + k] = cxy[src + k];
+                W.kresp[1][dst + k] = crr[src + k];
+            }
+        }
+        OG_SYNC();
+        n = ot_run(W, &sh, M, L.n_ini, L.hx, L.det_h, L.quota, oxy, orr, L.sel_cap);
+    }
     if (threadIdx.x == 0) P.sel_count[frame * P.n_levels + level] = n;
 }
 
 // Dynamic shared memory: [direct_bytes of the pass-free construction][smem_budget of latency-mode workspace].
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS) k_octree(const __grid_constant__ ExtractParams P, int smem_budget, int direct_bytes) {
+__global__ void __launch_bounds__(THREADS) k_octree(const __grid_constant__ ExtractParams P, int smem_budget, int direct_bytes, int direct_kcap) {
     extern __shared__ __align__(16) uint8_t oct_smem[];
     __shared__ OtShared sh;
     __shared__ Ot2Shared s2;
-    octree_level(P, blockIdx.x, P.frame0 + blockIdx.y, sh, oct_smem + direct_bytes, smem_budget, direct_bytes ? oct_smem : nullptr, &s2);
+    octree_level(P, blockIdx.x, P.frame0 + blockIdx.y, sh, oct_smem + direct_bytes, smem_budget, direct_bytes ? oct_smem : nullptr, &s2, direct_kcap);
 }
 
 // Stand-alone octree on caller-provided candidates (stage-level parity tests, orbgpu_octree).  direct_bytes > 0: the pass-free
@@ -430,7 +436,7 @@ __global__ void __launch_bounds__(THREADS) k_octree(const __grid_constant__ Extr
 __global__ void __launch_bounds__(kOctThreads) k_octree_single(uint8_t* ws, int cap, int node_cap, const uint32_t* xy,
                                                                const uint8_t* resp, int M, int n_ini, float hx, int height,
                                                                int N, uint32_t* out_xy, uint8_t* out_resp, int out_cap,
-                                                               int* out_n, int direct_bytes) {
+                                                               int* out_n, int direct_bytes, int direct_kcap) {
     extern __shared__ __align__(16) uint8_t oct_smem[];
     __shared__ OtShared sh;
     __shared__ Ot2Shared s2;
@@ -439,8 +445,8 @@ __global__ void __launch_bounds__(kOctThreads) k_octree_single(uint8_t* ws, int 
     OG_SYNC();
     int n = -1;
     if (direct_bytes)
-        n = ot_run_direct(W.kxy[1], W.kresp[1], M, oct_smem, ot2_depth(n_ini, kOt2Budget), max(node_cap, kOctThreads), &sh, &s2, n_ini, hx, height, N,
-                          out_xy, out_resp, out_cap);
+        n = ot_run_direct(Ot2CompactKeys{W.kxy[1], W.kresp[1]}, M, oct_smem, ot2_depth(n_ini, kOt2Budget), max(node_cap, kOctThreads), direct_kcap, &sh,
+                          &s2, n_ini, hx, height, N, out_xy, out_resp, out_cap);
     if (threadIdx.x == 0) out_n[1] = n >= 0;   // which path produced the result (tests)
     if (n < 0) n = ot_run(W, &sh, M, n_ini, hx, height, N, out_xy, out_resp, out_cap);
     if (threadIdx.x == 0) *out_n = n;

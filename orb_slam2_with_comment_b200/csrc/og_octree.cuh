@@ -43,8 +43,14 @@
 #define OG_THREADS_END }}
 #define OG_NTHREADS() (OG_HOST_THREADS)
 #endif
+// per-thread chunk length; the device blocks are powers of two (128 / 256 / 512 threads): a shift instead of a division
+#if OG_DEVICE_PASS
+#define OG_DIV_THREADS(x, TT) ((x) >> (31 - __clz(TT)))
+#else
+#define OG_DIV_THREADS(x, TT) ((x) / (TT))
+#endif
 #define OG_CHUNK(M, tt, TT, lo, hi)                       \
-    const int og_chunk_ = ((M) + (TT) - 1) / (TT);          \
+    const int og_chunk_ = OG_DIV_THREADS((M) + (TT) - 1, TT); \
     const int lo = (tt) * og_chunk_ < (M) ? (tt) * og_chunk_ : (M); \
     const int hi = lo + og_chunk_ < (M) ? lo + og_chunk_ : (M);
 
@@ -127,7 +133,7 @@ struct OtWork {
 OG_HD void block_exscan(int32_t* a, int n, OtShared* sh) {
 #if OG_DEVICE_PASS
     const int T = blockDim.x, t = threadIdx.x;
-    const int chunk = (n + T - 1) / T;
+    const int chunk = OG_DIV_THREADS(n + T - 1, T);
     const int lo = t * chunk < n ? t * chunk : n;
     const int hi = lo + chunk < n ? lo + chunk : n;
     int s = 0;

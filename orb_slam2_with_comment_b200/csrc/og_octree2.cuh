@@ -33,7 +33,10 @@
 //
 // Written once, compiled twice like og_octree.cuh (device: one CTA; host: tests/host_model only).
 #pragma once
+#include <string.h>
+
 #include "og_octree.cuh"
+#include "og_types.h"
 
 namespace og {
 
@@ -62,10 +65,11 @@ OG_HD int ot2_hist_cells(int n_ini, int Dh) {
 // Bytes of the histogram and the small per-node arrays behind it (list x2, candidates x2, sizes, child counts, order, 3 scan
 // arrays, best).  node_cap here = max(node capacity of the level, threads of the block): the scan arrays also carry
 // per-thread totals.
-OG_HD size_t ot2_smem_bytes(int n_ini, int Dh, int node_cap) {
+// kcap = keys whose path code and response are cached between the two key passes (3 bytes each; a multiple of 16).
+OG_HD size_t ot2_smem_bytes(int n_ini, int Dh, int node_cap, int kcap) {
     const size_t hist = ((size_t)ot2_hist_cells(n_ini, Dh) * 2 + 15) & ~size_t(15);
-    const size_t nc = ((size_t)node_cap + 3) & ~size_t(3);
-    return hist + nc * (4 + 4 + 2 + 2 + 2 + 2 + 2 + 4 + 4 + 4 + 4);
+    const size_t nc = ((size_t)node_cap + 7) & ~size_t(3);
+    return hist + nc * (4 + 4 + 2 + 2 + 2 + 2 + 2 + 4 + 4 + 4 + 4) + (size_t)kcap * 3;
 }
 
 struct Ot2Work {
@@ -81,15 +85,18 @@ struct Ot2Work {
     int32_t* sb;
     int32_t* sc;
     uint32_t* best;                    // per list node: response << 24 | (0xffffff - emission index)
+    uint16_t* kcode;                   // [kcap] first the owning cell of a key (Ot2CellKeys), then its depth-Dh cell
+    uint8_t* kres;                     // [kcap] response
+    int kcap;
 };
 
-OG_HD Ot2Work ot2_carve(uint8_t* mem, int n_ini, int Dh, int node_cap) {
+OG_HD Ot2Work ot2_carve(uint8_t* mem, int n_ini, int Dh, int node_cap, int kcap) {
     Ot2Work Q;
     Q.hist = reinterpret_cast<uint16_t*>(mem);
     Q.n_ini = n_ini;
     Q.top = 4 << (2 * Dh);
     uint8_t* p = mem + (((size_t)ot2_hist_cells(n_ini, Dh) * 2 + 15) & ~size_t(15));
-    const size_t nc = ((size_t)node_cap + 3) & ~size_t(3);
+    const size_t nc = ((size_t)node_cap + 7) & ~size_t(3);   // + 4: the rank loop reads whole vectors
     Q.list[0] = (uint32_t*)p; p += nc * 4;
     Q.list[1] = (uint32_t*)p; p += nc * 4;
     Q.sa = (int32_t*)p; p += nc * 4;
@@ -101,6 +108,9 @@ OG_HD Ot2Work ot2_carve(uint8_t* mem, int n_ini, int Dh, int node_cap) {
     Q.sz = (uint16_t*)p; p += nc * 2;
     Q.kids = (uint16_t*)p; p += nc * 2;
     Q.ordj = (uint16_t*)p; p += nc * 2;
+    Q.kcode = (uint16_t*)p; p += (size_t)kcap * 2;
+    Q.kres = p;
+    Q.kcap = kcap;
     return Q;
 }
 
@@ -137,7 +147,13 @@ OG_HD int ot2_unflip(int f, int dd, int n_ini) {
 }
 
 #if OG_DEVICE_PASS
-#define OT2_ATOMIC_ADD_U16(base, idx) atomicAdd(reinterpret_cast<unsigned int*>(base) + ((idx) >> 1), 1u << (16 * ((idx) & 1)))
+// +1 on the 16-bit counter idx (two per 32-bit word; no carry: counts stay below 2^15), returns the counter's old value
+__device__ __forceinline__ int ot2_atomic_inc_u16(uint16_t* base, int idx) {
+    const int sh = 16 * (idx & 1);
+    const unsigned int old = atomicAdd(reinterpret_cast<unsigned int*>(base) + (idx >> 1), 1u << sh);
+    return (int)((old >> sh) & 0xffffu);
+}
+#define OT2_ATOMIC_ADD_U16(base, idx) ot2_atomic_inc_u16((base), (idx))
 #define OT2_ATOMIC_MAX(p, v) atomicMax((p), (v))
 #define OT2_ATOMIC_MIN(p, v) atomicMin((p), (v))
 #define OT2_ATOMIC_ADD(p, v) atomicAdd((p), (v))
@@ -148,52 +164,135 @@ OG_HD int ot2_unflip(int f, int dd, int n_ini) {
 #define OT2_ATOMIC_ADD(p, v) (*(p) += (v))
 #endif
 
-// kxy / kresp: the M candidate keys in emission order.  mem: ot2_smem_bytes() of (shared) memory, 16-byte aligned.
+// Where the M candidate keys come from, by emission index.
+struct Ot2CompactKeys {   // plain arrays in emission order (tests, orbgpu_octree)
+    const uint32_t* kxy;
+    const uint8_t* kresp;
+    OG_HD void prefill(uint16_t*, int) const {}
+    OG_HD void get(int i, int, uint32_t& xy, int& resp) const { xy = kxy[i]; resp = kresp[i]; }
+};
+struct Ot2CellKeys {      // the per-cell slots k_fast_seg fills: coff = exclusive scan of the per-cell counts (emission order)
+    const int32_t* coff;
+    const Cell* cells;
+    const uint32_t* cxy;
+    const uint8_t* crr;
+    int n_cells;
+    // owner[i] = cell of key i for the first `cap` keys (block-wide; the caller synchronises afterwards): spares the first key
+    // pass the binary search
+    OG_HD void prefill(uint16_t* owner, int cap) const {
+        if (n_cells > 65535) return;
+        OG_FOR(ci, n_cells) {
+            const int lo = coff[ci], hi = ci + 1 < n_cells ? coff[ci + 1] : 0x7fffffff;
+            for (int i = lo; i < hi && i < cap; ++i) owner[i] = (uint16_t)ci;   // hi of the last cell: cut by the caller's cap (<= M)
+        }
+    }
+    OG_HD void get(int i, int owner, uint32_t& xy, int& resp) const {
+        int lo = owner;
+        if (lo < 0) {
+            int hi = n_cells;   // last cell whose offset is <= i (empty cells share their successor's offset and are skipped)
+            lo = 0;
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (coff[mid] <= i) lo = mid; else hi = mid;
+            }
+        }
+        const int slot = cells[lo].slot + (i - coff[lo]);
+#if OG_DEVICE_PASS
+        xy = __ldg(cxy + slot);
+        resp = __ldg(crr + slot);
+#else
+        xy = cxy[slot];
+        resp = crr[slot];
+#endif
+    }
+};
+
+OG_HD bool keys_cells_limit(const Ot2CompactKeys&) { return false; }
+OG_HD bool keys_cells_limit(const Ot2CellKeys& k) { return k.n_cells > 65535; }
+
+// keys: the M candidate keys by emission index.  mem: ot2_smem_bytes() of (shared) memory, 16-byte aligned.
 // Returns the number of selected keys (written in list order), or -1 when the general path has to run.
-OG_HD int ot_run_direct(const uint32_t* kxy, const uint8_t* kresp, int M, uint8_t* mem, int Dh, int node_cap, OtShared* sh, Ot2Shared* s2,
+template <class Keys>
+OG_HD int ot_run_direct(const Keys& keys, int M, uint8_t* mem, int Dh, int node_cap, int kcap, OtShared* sh, Ot2Shared* s2,
                         int nIni, float hX, int height, int N, uint32_t* out_xy, uint8_t* out_resp, int out_cap) {
     if (M == 0) return 0;
-    // 15-bit counters: a depth-Dh cell never holds more keys than pixels; the shallower counts saturate at 0x7fff, and a
-    // careful round that meets a saturated size (its sort needs the exact value) hands over.  24-bit emission index.
+    // 15-bit counters.  The deepest three levels are counted by atomics (exact: such a cell never holds more keys than
+    // pixels, checked here); the shallower counts are sums that saturate at 0x7fff, and a careful round that meets a saturated
+    // size (its sort needs the exact value) hands over.  24-bit emission index.
+    const int dA = Dh > 2 ? Dh - 2 : 0;   // depths >= dA: one atomic per key and depth
     if (Dh < 1 || M >= (1 << 24) || node_cap > 32767) return -1;
-    if ((long long)(((int)hX >> Dh) + 2) * ((height >> Dh) + 2) > 32767) return -1;
-    const Ot2Work Q = ot2_carve(mem, nIni, Dh, node_cap);
+    if ((long long)(((int)hX >> dA) + 2) * ((height >> dA) + 2) > 32767) return -1;
+    if (((long long)nIni << (2 * Dh)) > 65536 || keys_cells_limit(keys)) kcap = 0;   // 16-bit path codes / owners
+    const Ot2Work Q = ot2_carve(mem, nIni, Dh, node_cap, kcap);
+    const int kc = kcap < M ? kcap : M;   // cached keys
 
-    // ---- histogram of the keys over the depth-Dh cells --------------------------------------------------------------
+    // ---- histogram of the keys over the cells of depths dA..Dh ---------------------------------------------------------
     {
-        const int words = (ot2_hist_cells(nIni, Dh) + 1) / 2;
-        uint32_t* z = reinterpret_cast<uint32_t*>(Q.cnt(Dh));
-        OG_FOR(i, words) z[i] = 0u;
+        const int vecs = (ot2_hist_cells(nIni, Dh) * 2 + 15) / 16;
+#if OG_DEVICE_PASS
+        uint4* z = reinterpret_cast<uint4*>(Q.hist);
+        OG_FOR(i, vecs) z[i] = make_uint4(0u, 0u, 0u, 0u);
+#else
+        memset(Q.hist, 0, (size_t)vecs * 16);
+#endif
         OG_FOR(i, kOt2MaxDepth + 2) { s2->nd[i] = 0; s2->nexp[i] = 0; }
         OG_ONE { s2->D = 0; s2->careful = 0; s2->fallback = 0; }
+        keys.prefill(Q.kcode, kc);
     }
     OG_SYNC();
-    OG_FOR(i, M) {
-        Ot2Path p;
-        p.start(kxy[i], hX, height);
-        for (int d = 0; d < Dh; ++d) p.step();
-        OT2_ATOMIC_ADD_U16(Q.cnt(Dh), p.cell);
+    {
+        // a cell's first key makes it non-empty, its second one expandable: n_d and nExp_d of the atomically counted depths
+        int nz0 = 0, ne0 = 0, nz1 = 0, ne1 = 0, nz2 = 0, ne2 = 0;
+        OG_FOR(i, M) {
+            Ot2Path p;
+            uint32_t xy;
+            int resp;
+            keys.get(i, i < kc ? (int)Q.kcode[i] : -1, xy, resp);
+            p.start(xy, hX, height);
+            for (int d = 0; d < dA; ++d) p.step();
+            int old = OT2_ATOMIC_ADD_U16(Q.cnt(dA), p.cell);
+            nz0 += old == 0; ne0 += old == 1;
+            if (dA + 1 <= Dh) {
+                p.step();
+                old = OT2_ATOMIC_ADD_U16(Q.cnt(dA + 1), p.cell);
+                nz1 += old == 0; ne1 += old == 1;
+            }
+            if (dA + 2 <= Dh) {
+                p.step();
+                old = OT2_ATOMIC_ADD_U16(Q.cnt(dA + 2), p.cell);
+                nz2 += old == 0; ne2 += old == 1;
+            }
+            if (i < kc) {   // p.cell is the depth-Dh cell now (dA + 2 >= Dh)
+                Q.kcode[i] = (uint16_t)p.cell;
+                Q.kres[i] = (uint8_t)resp;
+            }
+        }
+        if (nz0) OT2_ATOMIC_ADD(&s2->nd[dA], nz0);
+        if (ne0) OT2_ATOMIC_ADD(&s2->nexp[dA], ne0);
+        if (nz1) OT2_ATOMIC_ADD(&s2->nd[dA + 1], nz1);
+        if (ne1) OT2_ATOMIC_ADD(&s2->nexp[dA + 1], ne1);
+        if (nz2) OT2_ATOMIC_ADD(&s2->nd[dA + 2], nz2);
+        if (ne2) OT2_ATOMIC_ADD(&s2->nexp[dA + 2], ne2);
     }
     OG_SYNC();
-    // ---- counts of the shallower depths, n_d and nExp_d ---------------------------------------------------------------
-    for (int d = Dh - 1; d >= 0; --d) {
+    // ---- counts of the shallower depths, their n_d and nExp_d -------------------------------------------------------------
+    for (int d = dA - 1; d >= 0; --d) {
         const int cells = nIni << (2 * d);
-        int nz = 0, ne = 0, pz = 0, pe = 0;   // children (depth d+1) / parents (depth d, only needed for d == 0)
+        int pz = 0, pe = 0;
         OG_FOR(c, cells) {
             const uint16_t* k = Q.cnt(d + 1) + 4 * c;
-            const int a = k[0], b = k[1], e = k[2], f = k[3], s = a + b + e + f;
-            Q.cnt(d)[c] = (uint16_t)(s < 0x7fff ? s : 0x7fff);
-            nz += (a > 0) + (b > 0) + (e > 0) + (f > 0);
-            ne += (a > 1) + (b > 1) + (e > 1) + (f > 1);
-            pz += s > 0;
-            pe += s > 1;
+#if OG_DEVICE_PASS
+            const uint2 kk = *reinterpret_cast<const uint2*>(k);   // 8-byte aligned: every depth starts at a multiple of 4 cells
+            const int sum = (int)((kk.x & 0xffffu) + (kk.x >> 16) + (kk.y & 0xffffu) + (kk.y >> 16));
+#else
+            const int sum = k[0] + k[1] + k[2] + k[3];
+#endif
+            Q.cnt(d)[c] = (uint16_t)(sum < 0x7fff ? sum : 0x7fff);
+            pz += sum > 0;
+            pe += sum > 1;
         }
-        if (nz) OT2_ATOMIC_ADD(&s2->nd[d + 1], nz);
-        if (ne) OT2_ATOMIC_ADD(&s2->nexp[d + 1], ne);
-        if (d == 0) {
-            if (pz) OT2_ATOMIC_ADD(&s2->nd[0], pz);
-            if (pe) OT2_ATOMIC_ADD(&s2->nexp[0], pe);
-        }
+        if (pz) OT2_ATOMIC_ADD(&s2->nd[d], pz);
+        if (pe) OT2_ATOMIC_ADD(&s2->nexp[d], pe);
         OG_SYNC();
     }
     // ---- the pass loop (:588-665) as a scan over depths ----------------------------------------------------------------
@@ -285,13 +384,20 @@ OG_HD int ot_run_direct(const uint32_t* kxy, const uint8_t* kresp, int M, uint8_
         OG_FOR(i, n) Q.sc[i] = 1;   // survivor flags
         OG_SYNC();
         if (s2->fallback) return -1;
-        // b. processing rank: larger size first, equal sizes: later created first (std::sort ascending walked from the back)
+        // b. processing rank: larger size first, equal sizes: later created first (std::sort ascending walked from the back) =
+        //    descending order of size << 16 | creation index
+        OG_FOR(j, nC + 4) Q.sa[j] = j < nC ? (((int)Q.sz[j] << 16) | j) : 0;
+        OG_SYNC();
         OG_FOR(j, nC) {
-            const int sj = Q.sz[j];
+            const int kj = Q.sa[j];
             int r = 0;
-            for (int j2 = 0; j2 < nC; ++j2) {
-                const int s2v = Q.sz[j2];
-                r += (s2v > sj) || (s2v == sj && j2 > j);
+            for (int j2 = 0; j2 < nC; j2 += 4) {
+#if OG_DEVICE_PASS
+                const int4 k4 = *reinterpret_cast<const int4*>(Q.sa + j2);
+                r += (k4.x > kj) + (k4.y > kj) + (k4.z > kj) + (k4.w > kj);
+#else
+                for (int u = 0; u < 4; ++u) r += Q.sa[j2 + u] > kj;
+#endif
             }
             Q.ordj[r] = (uint16_t)j;
         }
@@ -354,23 +460,42 @@ OG_HD int ot_run_direct(const uint32_t* kxy, const uint8_t* kresp, int M, uint8_
         }
         OG_SYNC();
         OG_FOR(i, M) {
-            Ot2Path p;
-            p.start(kxy[i], hX, height);
-            int d = 0;
-            uint32_t v = Q.cnt(0)[p.cell];
-            while (!(v & 0x8000u) && d < Dh) {
-                p.step();
-                ++d;
-                v = Q.cnt(d)[p.cell];
+            uint32_t v;
+            int resp;
+            if (i < kc) {
+                // cached path code: the depth-d cell is a shift away
+                const int code = Q.kcode[i];
+                resp = Q.kres[i];
+                int d = 0;
+                v = Q.cnt(0)[code >> (2 * Dh)];
+                while (!(v & 0x8000u) && d < Dh) {
+                    ++d;
+                    v = Q.cnt(d)[code >> (2 * (Dh - d))];
+                }
+            } else {
+                Ot2Path p;
+                uint32_t xy;
+                keys.get(i, -1, xy, resp);
+                p.start(xy, hX, height);
+                int d = 0;
+                v = Q.cnt(0)[p.cell];
+                while (!(v & 0x8000u) && d < Dh) {
+                    p.step();
+                    ++d;
+                    v = Q.cnt(d)[p.cell];
+                }
             }
-            if (v & 0x8000u) OT2_ATOMIC_MAX(&Q.best[v & 0x7fffu], ((uint32_t)kresp[i] << 24) | (0xffffffu - (uint32_t)i));
+            if (v & 0x8000u) OT2_ATOMIC_MAX(&Q.best[v & 0x7fffu], ((uint32_t)resp << 24) | (0xffffffu - (uint32_t)i));
         }
         OG_SYNC();
         OG_FOR(i, n) {
             if (i < out_cap) {
                 const uint32_t b = Q.best[i];
-                out_xy[i] = kxy[0xffffffu - (b & 0xffffffu)];
-                out_resp[i] = (uint8_t)(b >> 24);
+                uint32_t xy;
+                int resp;
+                keys.get((int)(0xffffffu - (b & 0xffffffu)), -1, xy, resp);
+                out_xy[i] = xy;
+                out_resp[i] = (uint8_t)resp;
             }
         }
         OG_SYNC();

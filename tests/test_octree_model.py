@@ -21,10 +21,12 @@ def model():
     hdr = os.path.join(HERE, "..", "orb_slam2_with_comment_b200", "csrc", "og_octree.cuh")
     hdr2 = os.path.join(HERE, "..", "orb_slam2_with_comment_b200", "csrc", "og_octree2.cuh")
     if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(hdr), os.path.getmtime(hdr2)):
-        subprocess.check_call(["g++", "-std=c++14", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-x", "c++", src, "-o", out])
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-x", "c++", src, "-o", out])
     lib = C.CDLL(out)
     lib.ogm_octree.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
-    lib.ogm_octree_direct.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    lib.ogm_octree_direct.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    lib.ogm_octree_direct_cells.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                            C.c_void_p, C.c_void_p, C.c_int]
     return lib
 
 
@@ -39,18 +41,37 @@ def run_model(lib, cand, width, height, N):
     return (oxy[:n] & 0xffff).astype(np.float32), (oxy[:n] >> 16).astype(np.float32), orr[:n].astype(np.float32)
 
 
-def run_direct(lib, cand, width, height, N, budget):
-    """The pass-free construction (og_octree2.cuh); None when it hands the case to the division-pass path."""
+def run_direct(lib, cand, width, height, N, budget, kcap=0, cells=None):
+    """The pass-free construction (og_octree2.cuh); None when it hands the case to the division-pass path.  kcap = cached path
+    codes; cells = per-cell key counts: the keys are then read through the product's per-cell slot layout."""
     xy = (cand["y"].astype(np.uint32) << 16) | cand["x"].astype(np.uint32)
     resp = cand["response"].astype(np.uint8)
     cap = N + 1024
     oxy = np.zeros(cap, np.uint32)
     orr = np.zeros(cap, np.uint8)
-    n = lib.ogm_octree_direct(xy.ctypes.data, resp.ctypes.data, len(cand), width, height, N, budget, oxy.ctypes.data, orr.ctypes.data, cap)
+    if cells is None:
+        n = lib.ogm_octree_direct(xy.ctypes.data, resp.ctypes.data, len(cand), width, height, N, budget, kcap, oxy.ctypes.data, orr.ctypes.data, cap)
+    else:
+        cells = np.ascontiguousarray(cells, np.int32)
+        n = lib.ogm_octree_direct_cells(xy.ctypes.data, resp.ctypes.data, len(cand), cells.ctypes.data, len(cells), width, height, N, budget, kcap,
+                                        oxy.ctypes.data, orr.ctypes.data, cap)
     assert n >= -1
     if n < 0:
         return None
     return (oxy[:n] & 0xffff).astype(np.float32), (oxy[:n] >> 16).astype(np.float32), orr[:n].astype(np.float32)
+
+
+def random_cells(rs, M):
+    """Cuts M keys into runs (some empty), like the FAST cells of a level."""
+    counts = []
+    left = M
+    while left > 0:
+        c = int(rs.randint(0, 12)) if rs.rand() < 0.8 else 0
+        c = min(c, left)
+        counts.append(c)
+        left -= c
+    counts += [0] * int(rs.randint(0, 3))
+    return counts if counts else [0]
 
 
 DIRECT_STATS = {"direct": 0, "fallback": 0}
@@ -61,9 +82,12 @@ def check(lib, oracle, cand, width, height, N):
     x, y, r = run_model(lib, cand, width, height, N)
     assert len(x) == len(exp)
     assert np.array_equal(x, exp["x"]) and np.array_equal(y, exp["y"]) and np.array_equal(r, exp["response"])
-    # the pass-free construction, with a small and with the product's histogram: equal whenever it answers
-    for budget in (256, 16384):
-        got = run_direct(lib, cand, width, height, N, budget)
+    # the pass-free construction, with a small and with the product's histogram, without / with a partial / with a full cache
+    # of path codes, from plain arrays and through the per-cell slot layout: equal whenever it answers
+    rs = np.random.RandomState(len(cand) * 7 + N)
+    for budget, kcap, cells in ((256, 0, None), (16384, 0, None), (16384, 64, None), (16384, 4096, random_cells(rs, len(cand))),
+                                (1024, 48, random_cells(rs, len(cand))), (16384, 0, random_cells(rs, len(cand)))):
+        got = run_direct(lib, cand, width, height, N, budget, kcap, cells)
         if got is None:
             DIRECT_STATS["fallback"] += 1
             continue
