@@ -61,7 +61,7 @@ struct orbgpu_extractor {
     static constexpr int kStreams = 8;                 // compute streams of the chunked host path: stream, stream2, extra[0..5]
     cudaStream_t s_extra[kStreams - 2] = {};
     cudaStream_t s_aux[kStreams] = {};
-    cudaEvent_t ev_pyr[kStreams] = {}, ev_blur[kStreams] = {};
+    cudaEvent_t ev_pyr[kStreams] = {}, ev_blur[kStreams] = {}, ev_fast[kStreams] = {};
     cudaStream_t compute_stream(int k) const { return k == 0 ? stream : (k == 1 ? stream2 : s_extra[k - 2]); }
     // geometry is rebuilt whenever the frame size changes (buffers are sized for max_w x max_h)
     int cur_w = 0, cur_h = 0;
@@ -499,26 +499,33 @@ int launch_extract(orbgpu_extractor* ex, const uint8_t* d_images, int batch, siz
         }
         ++launches;
     }
-    {
-        // the generic resize writes its own frame; the border kernels then only repeat it (and do level 0)
-        const int sides0 = 2 * P.lv[0].h;
-        og::k_border_sides<<<dim3((sides0 + og::kBorderThreads - 1) / og::kBorderThreads, P.n_levels, batch), og::kBorderThreads, 0, st>>>(P);
-        og::k_border_caps<<<dim3(2 * og::kEdge, P.n_levels, batch), og::kBorderThreads, 0, st>>>(P);
-        ++launches;
-        ++launches;
-    }
-    mark(1);
     // per-stage profiling keeps everything on one stream so that the stage times add up
     int aux = 0;
     for (int k = 1; k < orbgpu_extractor::kStreams; ++k)
         if (st == ex->compute_stream(k)) aux = k;
+    // The reflect-101 frames (two latency-bound kernels that use a few percent of the SMs) are needed by the blur only — FAST
+    // cells start 16 px inside a level — so they run on the auxiliary stream beside FAST.  ORBGPU_ASYNC_FRAME=0: in line.
+    static const int async_frame_env = []() { const char* e = getenv("ORBGPU_ASYNC_FRAME"); return e ? atoi(e) : 1; }();
+    const bool async_frame = !ex->profiling && async_frame_env != 0;
+    auto borders = [&](cudaStream_t s) {
+        // the generic resize writes its own frame; the border kernels then only repeat it (and do level 0)
+        const int sides0 = 2 * P.lv[0].h;
+        og::k_border_sides<<<dim3((sides0 + og::kBorderThreads - 1) / og::kBorderThreads, P.n_levels, batch), og::kBorderThreads, 0, s>>>(P);
+        og::k_border_caps<<<dim3(2 * og::kEdge, P.n_levels, batch), og::kBorderThreads, 0, s>>>(P);
+        launches += 2;
+    };
+    if (!async_frame) borders(st);
+    mark(1);
     // measured on B200: pays off while a launch cannot fill the GPU (53.5k vs 50.0k frames/s at 64 frames), costs 8 % at 1024
     const bool overlap_blur = !ex->profiling && batch <= 128;
-    // larger batches: the blur (issue bound) runs beside the octree (latency bound, ~18 % of the issue slots) instead of FAST
+    // larger batches: the blur (issue bound) runs beside the octree instead of FAST
     const bool blur_with_octree = !ex->profiling && !overlap_blur;
-    if (overlap_blur) {
+    if (async_frame || overlap_blur) {
         OG_CUDA(cudaEventRecord(ex->ev_pyr[aux], st));
         OG_CUDA(cudaStreamWaitEvent(ex->s_aux[aux], ex->ev_pyr[aux], 0));
+        if (async_frame) borders(ex->s_aux[aux]);
+    }
+    if (overlap_blur) {
         og::k_blur_tma<<<dim3(ex->n_btiles, batch), og::kBlurThreads, 0, ex->s_aux[aux]>>>(P, ex->d_btiles, ex->d_tmaps);
         OG_CUDA(cudaEventRecord(ex->ev_blur[aux], ex->s_aux[aux]));
         ++launches;
@@ -527,8 +534,8 @@ int launch_extract(orbgpu_extractor* ex, const uint8_t* d_images, int batch, siz
     ++launches;
     mark(2);
     if (blur_with_octree) {
-        OG_CUDA(cudaEventRecord(ex->ev_pyr[aux], st));
-        OG_CUDA(cudaStreamWaitEvent(ex->s_aux[aux], ex->ev_pyr[aux], 0));
+        OG_CUDA(cudaEventRecord(ex->ev_fast[aux], st));
+        OG_CUDA(cudaStreamWaitEvent(ex->s_aux[aux], ex->ev_fast[aux], 0));
         og::k_blur_tma<<<dim3(ex->n_btiles, batch), og::kBlurThreads, 0, ex->s_aux[aux]>>>(P, ex->d_btiles, ex->d_tmaps);
         OG_CUDA(cudaEventRecord(ex->ev_blur[aux], ex->s_aux[aux]));
         ++launches;
@@ -705,6 +712,7 @@ int orbgpu_extractor_create(orbgpu_extractor** out, int device, int nfeatures, f
         if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&ex->s_aux[k], cudaStreamNonBlocking);
         if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&ex->ev_pyr[k], cudaEventDisableTiming);
         if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&ex->ev_blur[k], cudaEventDisableTiming);
+        if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&ex->ev_fast[k], cudaEventDisableTiming);
     }
     if (ce != cudaSuccess) {
         std::string m = std::string("workspace allocation failed: ") + cudaGetErrorString(ce);
@@ -731,6 +739,7 @@ int orbgpu_extractor_destroy(orbgpu_extractor* ex) {
         if (ex->s_aux[k]) { cudaStreamSynchronize(ex->s_aux[k]); cudaStreamDestroy(ex->s_aux[k]); }
         if (ex->ev_pyr[k]) cudaEventDestroy(ex->ev_pyr[k]);
         if (ex->ev_blur[k]) cudaEventDestroy(ex->ev_blur[k]);
+        if (ex->ev_fast[k]) cudaEventDestroy(ex->ev_fast[k]);
     }
     for (int i = 0; i < 6; ++i) if (ex->ev[i]) cudaEventDestroy(ex->ev[i]);
     if (ex->ev_peer) cudaEventDestroy(ex->ev_peer);

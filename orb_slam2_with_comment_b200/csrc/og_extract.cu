@@ -189,8 +189,11 @@ __global__ void __launch_bounds__(kResizeThreads) k_resize4(const __grid_constan
 // scale <= 1.25, checked on the host per level).  All 3 x kResizeSpan word loads are issued back to back (the row loop above
 // waits for every row's three loads before it can start the next), their horizontal passes are parked in shared memory, and
 // the vertical pass picks its two rows from there.
+// Horizontal pass: the byte pairs of outputs 0,1 lie inside the first two of the three words and those of outputs 2,3 inside
+// two adjacent ones, so ONE byte permute gathers both pairs of two outputs into a word [p(s0) p(s0+1) p(s0') p(s0'+1)] and the
+// low / high DP2A apply the two weight pairs: 2 SEL + 2 PRMT + 4 DP2A per source row instead of 8 SEL + 4 SHF + 4 DP2A.
 constexpr int kResizeSpan = 11;
-__global__ void __launch_bounds__(kResizeThreads) k_resize4_mlp(const __grid_constant__ ExtractParams P, int level, int nwx, uint32_t nwx_magic,
+__global__ void __launch_bounds__(kResizeThreads, 8) k_resize4_mlp(const __grid_constant__ ExtractParams P, int level, int nwx, uint32_t nwx_magic,
                                                                 int n_items) {
     __shared__ uint4 sg[kResizeSpan][kResizeThreads];
     const Level& L = P.lv[level];
@@ -201,17 +204,15 @@ __global__ void __launch_bounds__(kResizeThreads) k_resize4_mlp(const __grid_con
     const int band = (int)__umulhi((uint32_t)id, nwx_magic), wx = id - band * nwx;
     const int x = 4 * wx, y0 = band * kResizeRows;
     const uint4 ta = __ldg(reinterpret_cast<const uint4*>(L.xt + x)), tb = __ldg(reinterpret_cast<const uint4*>(L.xt + x) + 1);
-    const uint32_t tw[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
+    const uint32_t tw[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};   // per output: (s0 | s1 << 16), (w0 | w1 << 16)
     const int base = (int)(tw[0] & 0xffffu) & ~3;
-    int sel[4], sh[4];
-    uint32_t wq[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int o = (int)(tw[2 * j] & 0xffffu) - base;
-        sel[j] = o >> 2;
-        sh[j] = 8 * (o & 3);
-        wq[j] = tw[2 * j + 1];
-    }
+    const int o0 = (int)(tw[0] & 0xffffu) - base, o1 = (int)(tw[2] & 0xffffu) - base;   // byte offsets of the four pairs: 0..9,
+    int o2 = (int)(tw[4] & 0xffffu) - base, o3 = (int)(tw[6] & 0xffffu) - base;         // consecutive ones at most 2 apart
+    const bool hiB = o2 >= 4;   // outputs 2,3 read words 1,2 (else 0,1)
+    if (hiB) { o2 -= 4; o3 -= 4; }
+    const uint32_t selA = (uint32_t)(o0 | ((o0 + 1) << 4) | (o1 << 8) | ((o1 + 1) << 12));
+    const uint32_t selB = (uint32_t)(o2 | ((o2 + 1) << 4) | (o3 << 8) | ((o3 + 1) << 12));
+    const uint32_t wq0 = tw[1], wq1 = tw[3], wq2 = tw[5], wq3 = tw[7];   // (w0 | w1 << 16): the two 11-bit weights as DP2A's 16-bit pair
     const int sfirst = L.yt[y0].s0;
     const uint8_t* src = level_ptr(P.pyr, S, frame) + (long long)(kEdge + sfirst) * S.pitch + kXPad + base;
     uint32_t W[kResizeSpan][3];
@@ -223,13 +224,9 @@ __global__ void __launch_bounds__(kResizeThreads) k_resize4_mlp(const __grid_con
     }
 #pragma unroll
     for (int k = 0; k < kResizeSpan; ++k) {
-        uint32_t g[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const uint32_t lo = sel[j] == 0 ? W[k][0] : (sel[j] == 1 ? W[k][1] : W[k][2]), hi = sel[j] == 0 ? W[k][1] : W[k][2];
-            g[j] = __dp2a_lo(wq[j], __funnelshift_r(lo, hi, sh[j]), 0u) >> 4;
-        }
-        sg[k][threadIdx.x] = make_uint4(g[0], g[1], g[2], g[3]);
+        const uint32_t A = __byte_perm(W[k][0], W[k][1], selA);
+        const uint32_t B = __byte_perm(hiB ? W[k][1] : W[k][0], hiB ? W[k][2] : W[k][1], selB);
+        sg[k][threadIdx.x] = make_uint4(__dp2a_lo(wq0, A, 0u) >> 4, __dp2a_hi(wq1, A, 0u) >> 4, __dp2a_lo(wq2, B, 0u) >> 4, __dp2a_hi(wq3, B, 0u) >> 4);
     }
     uint8_t* dst = level_ptr(P.pyr, L, frame) + (long long)kEdge * L.pitch + kXPad + x;
     const int nrows = min(kResizeRows, L.h - y0);
@@ -239,9 +236,9 @@ __global__ void __launch_bounds__(kResizeThreads) k_resize4_mlp(const __grid_con
         const Tap ty = L.yt[y];
         const uint4 a = sg[ty.s0 - sfirst][threadIdx.x], b = sg[ty.s1 - sfirst][threadIdx.x];   // own slots only: no barrier needed
         const uint32_t b0 = (uint32_t)ty.w0 << 16, b1 = (uint32_t)ty.w1 << 16;
-        const uint32_t o0 = (__umulhi(b0, a.x) + __umulhi(b1, b.x) + 2u) >> 2, o1 = (__umulhi(b0, a.y) + __umulhi(b1, b.y) + 2u) >> 2;
-        const uint32_t o2 = (__umulhi(b0, a.z) + __umulhi(b1, b.z) + 2u) >> 2, o3 = (__umulhi(b0, a.w) + __umulhi(b1, b.w) + 2u) >> 2;
-        *reinterpret_cast<uint32_t*>(dst + (long long)y * L.pitch) = o0 | (o1 << 8) | (o2 << 16) | (o3 << 24);
+        const uint32_t q0 = (__umulhi(b0, a.x) + __umulhi(b1, b.x) + 2u) >> 2, q1 = (__umulhi(b0, a.y) + __umulhi(b1, b.y) + 2u) >> 2;
+        const uint32_t q2 = (__umulhi(b0, a.z) + __umulhi(b1, b.z) + 2u) >> 2, q3 = (__umulhi(b0, a.w) + __umulhi(b1, b.w) + 2u) >> 2;
+        *reinterpret_cast<uint32_t*>(dst + (long long)y * L.pitch) = q0 | (q1 << 8) | (q2 << 16) | (q3 << 24);
     }
 }
 
