@@ -134,6 +134,10 @@ int orbgpu_extractor_read_blurred(orbgpu_extractor* ex, int frame, int level, ui
  * n candidates (x, y, response used), rectangle [min_x,max_x) x [min_y,max_y), quota n_features. */
 int orbgpu_octree(orbgpu_extractor* ex, const orbgpu_keypoint* candidates, int n, int min_x, int max_x, int min_y,
                   int max_y, int n_features, orbgpu_keypoint* out, int capacity, int* n_out);
+/* Which of the two device formulations of DistributeOctTree answered the last orbgpu_octree call: 1 = the pass-free
+ * construction (cell histogram, csrc/og_octree2.cuh), 0 = the division-pass state machine it hands deep trees to
+ * (csrc/og_octree.cuh).  Both reproduce ORBextractor.cc:539-763 exactly; tests use this to cover each of them. */
+int orbgpu_octree_last_path(const orbgpu_extractor* ex);
 
 /* Frame::ComputeStereoMatches (Frame.cc:501-675) for every stereo pair of the last call: `left` and `right` are two
  * extractors on the same device that have just processed the left and the right images of the same batch (same image size,

@@ -51,6 +51,7 @@ def lib() -> C.CDLL:
     L.orbgpu_extractor_read_blurred.argtypes = [vp, i, i, vp, sz]
     L.orbgpu_extractor_read_points.argtypes = [vp, i, i, i, vp, i, C.POINTER(i)]
     L.orbgpu_octree.argtypes = [vp, vp, i, i, i, i, i, i, vp, i, C.POINTER(i)]
+    L.orbgpu_octree_last_path.argtypes = [vp]
     L.orbgpu_extractor_static_tables.argtypes = [i, f, i, vp, vp, vp]
     L.orbgpu_stereo_matches.argtypes = [vp, vp, f, f, vp, vp, i]
     L.orbgpu_stereo_matches_dev.argtypes = [vp, vp, f, f, vp, vp, i]

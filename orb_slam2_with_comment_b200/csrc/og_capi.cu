@@ -1070,6 +1070,8 @@ int orbgpu_extractor_read_points(orbgpu_extractor* ex, int frame, int level, int
     return ORBGPU_OK;
 }
 
+int orbgpu_octree_last_path(const orbgpu_extractor* ex) { return ex ? ex->last_octree_direct : 0; }
+
 int orbgpu_octree(orbgpu_extractor* ex, const orbgpu_keypoint* candidates, int n, int min_x, int max_x, int min_y, int max_y,
                   int n_features, orbgpu_keypoint* out, int capacity, int* n_out) {
     if (!ex || !n_out || n < 0 || n_features < 1) return fail(ORBGPU_ERR_ARG, "bad argument");

@@ -534,6 +534,11 @@ __global__ void __launch_bounds__(kSegThreads, 5) k_fast_seg(const __grid_consta
 
     const int min_th = P.min_th, ini_th = P.ini_th;
     __shared__ uint32_t colmask[8];   // pass 1: tile columns of the cells that need the minTh pass (256 bits)
+    __shared__ uint32_t vmask[8];     // tile columns of the tested pixels
+    {
+        const unsigned bal = __ballot_sync(0xffffffffu, t >= ox && t < ox + tw);
+        if (lane == 0) vmask[wi] = bal;   // read after the barrier behind the rejection test
+    }
     __shared__ int need[8], nneed;
     const int wcell = L.wcell;
     // Pass 0 works at iniTh for the whole segment: FAST(cell, iniTh) only involves pixels with V >= iniTh (a corner's
@@ -547,23 +552,25 @@ __global__ void __launch_bounds__(kSegThreads, 5) k_fast_seg(const __grid_consta
             const uint32_t* T = reinterpret_cast<const uint32_t*>(tile);
             const int b0 = ox >> 3, nb = ((ox + tw - 1) >> 3) - b0 + 1, total = th * nb;
             const uint32_t kadd = (uint32_t)(tcur >= 127 ? 0xff - tcur : 0x7f - tcur) * 0x01010101u;
-            // An arc of 9 contiguous ring pixels covers at least 4 CONSECUTIVE of the 8 even ring positions (the compass points
-            // and the (+-2, +-2) diagonals), so a corner has 4 consecutive of those with |I - Ic| > t.  Twice the arithmetic of the
-            // plain compass test ("2 of 4"), but it lets through half as many pixels (10 % instead of 18.6 % on the bench
-            // frames; true corners are 2.8 %), and everything downstream — compaction, exact score — scales with that count.
-            // far(): bit 7 of every byte of the result says |c - x| > t for that pixel; the other bits are garbage and are
-            // masked once, after the AND / OR network (t < 127: carry out of the low 7 bits, or bit 7 of the difference itself;
-            // t >= 127: bit 7 and the carry).
+            // An arc of 9 contiguous ring pixels contains two neighbouring compass points — one of N / S and one of E / W — and two
+            // neighbouring (+-2, +-2) diagonal points — one of NE / SW and one of SE / NW.  So a corner has
+            //     (N | S) & (E | W) & (NE | SW) & (SE | NW),    X = |I_X - Ic| > t,
+            // which on the bench frames lets through exactly as many pixels as "four consecutive of the eight" (10.2 %; the plain
+            // compass test 17 - 18 %; true corners 2.7 %) for a fifth of its AND / OR network, and everything downstream —
+            // compaction, exact score — scales with that count.
+            // far2(): bit 7 of every byte says that one of the two ring pixels differs from the centre by more than t; the other bits
+            // are garbage and are masked once, after the AND (t < 127: carry out of the low 7 bits, or bit 7 of the difference
+            // itself; t >= 127: bit 7 and the carry).
             // The threshold class is a compile-time constant of the loop (one LOP3 per test instead of a predicated pair).
             auto reject = [&](auto big_c) {
             constexpr bool big = decltype(big_c)::value;
-            auto far = [&](uint32_t c, uint32_t x) {
-                const uint32_t d = __vabsdiffu4(c, x), s = (d & 0x7f7f7f7fu) + kadd;
-                return big ? (s & d) : (s | d);
+            auto far2 = [&](uint32_t c, uint32_t xa, uint32_t xb) {
+                const uint32_t da = __vabsdiffu4(c, xa), db = __vabsdiffu4(c, xb);
+                const uint32_t sa = (da & 0x7f7f7f7fu) + kadd, sb = (db & 0x7f7f7f7fu) + kadd;
+                return big ? ((sa & da) | (sb & db)) : (sa | da | sb | db);
             };
-            auto run4 = [&](uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3, uint32_t m4, uint32_t m5, uint32_t m6, uint32_t m7) {
-                const uint32_t a0 = m0 & m1, a1 = m1 & m2, a2 = m2 & m3, a3 = m3 & m4, a4 = m4 & m5, a5 = m5 & m6, a6 = m6 & m7, a7 = m7 & m0;
-                const uint32_t g = ((a0 & a2) | (a1 & a3) | (a2 & a4) | (a3 & a5) | (a4 & a6) | (a5 & a7) | (a6 & a0) | (a7 & a1)) & 0x80808080u;
+            auto flags = [&](uint32_t ns, uint32_t ew, uint32_t d1, uint32_t d2) {
+                const uint32_t g = ns & ew & d1 & d2 & 0x80808080u;
                 return ((g >> 7) * 0x01020408u) >> 24;   // bits 7,15,23,31 -> 4-bit value
             };
             const uint8_t* cmb = reinterpret_cast<const uint8_t*>(colmask);
@@ -579,15 +586,12 @@ __global__ void __launch_bounds__(kSegThreads, 5) k_fast_seg(const __grid_consta
                     const uint32_t ua = ru[-1], ub = ru[0], uc = ru[1], ud = ru[2], da = rd[-1], db = rd[0], dc = rd[1], dd = rd[2];
                     const uint32_t u_l = __funnelshift_r(ua, ub, 16), u_m = __funnelshift_r(ub, uc, 16), u_r = __funnelshift_r(uc, ud, 16);
                     const uint32_t d_l = __funnelshift_r(da, db, 16), d_m = __funnelshift_r(db, dc, 16), d_r = __funnelshift_r(dc, dd, 16);
-                    // ring order N, NE, E, SE, S, SW, W, NW
-                    const uint32_t n0 = run4(far(c0, row[-3 * 64]), far(c0, u_m), far(c0, __funnelshift_r(c0, c1, 24)), far(c0, d_m), far(c0, row[3 * 64]),
-                                             far(c0, d_l), far(c0, __funnelshift_r(lw, c0, 8)), far(c0, u_l));
-                    const uint32_t n1 = run4(far(c1, row[-3 * 64 + 1]), far(c1, u_r), far(c1, __funnelshift_r(c1, rw, 24)), far(c1, d_r), far(c1, row[3 * 64 + 1]),
-                                             far(c1, d_m), far(c1, __funnelshift_r(c0, c1, 8)), far(c1, u_m));
+                    // pairs (N, S), (E, W), (NE, SW), (SE, NW); the columns outside the tested range are masked by the compaction
+                    const uint32_t n0 = flags(far2(c0, row[-3 * 64], row[3 * 64]), far2(c0, __funnelshift_r(c0, c1, 24), __funnelshift_r(lw, c0, 8)),
+                                              far2(c0, u_m, d_l), far2(c0, d_m, u_l));
+                    const uint32_t n1 = flags(far2(c1, row[-3 * 64 + 1], row[3 * 64 + 1]), far2(c1, __funnelshift_r(c1, rw, 24), __funnelshift_r(c0, c1, 8)),
+                                              far2(c1, u_r, d_m), far2(c1, d_r, u_m));
                     m = n0 | (n1 << 4);
-                    if (br == 0) m &= 0xffu << (ox & 7);                                  // columns before the first tested pixel
-                    if (br == nb - 1) m &= 0xffu >> (7 - ((ox + tw - 1) & 7));            // ... and after the last
-                    if (pass) m &= cmb[B];
                 }
                 mk[r * 32 + B] = (uint8_t)m;
             }
@@ -596,12 +600,14 @@ __global__ void __launch_bounds__(kSegThreads, 5) k_fast_seg(const __grid_consta
         }
         __syncthreads();
         // ---- 2. compaction of the surviving pixels into the queue (entry = tile row << 8 | tile column) ----------
+        // a thread takes 32 pixels (one word of the row bitmaps): one warp scan per 1024 pixels
         {
-            const uint16_t* M = reinterpret_cast<const uint16_t*>(mk);
-            const int nhalf = th * 16;
-            for (int i0 = 0; i0 < nhalf; i0 += kSegThreads) {
+            const uint32_t* M = reinterpret_cast<const uint32_t*>(mk);
+            const uint32_t* vm = pass == 0 ? vmask : colmask;
+            const int nwords = th * 8;
+            for (int i0 = 0; i0 < nwords; i0 += kSegThreads) {
                 const int i = i0 + t;
-                uint32_t v = i < nhalf ? M[i] : 0u;
+                uint32_t v = i < nwords ? (M[i] & vm[i & 7]) : 0u;   // only the tested columns (pass 1: of the cells that need it)
                 const int cnt = __popc(v);
                 int inc = cnt;
 #pragma unroll
@@ -612,7 +618,7 @@ __global__ void __launch_bounds__(kSegThreads, 5) k_fast_seg(const __grid_consta
                 int base = 0;
                 if (lane == 31 && inc) base = smem_atomic_add(&qn, inc);
                 base = __shfl_sync(0xffffffffu, base, 31) + inc - cnt;
-                const int e0 = i << 4;   // 16 rows-of-16 per tile row: row * 256 + 16 * (i & 15)
+                const int e0 = i << 5;   // 8 words per tile row: row * 256 + 32 * (i & 7)
                 while (v) {
                     const int b = __ffs(v) - 1;
                     v &= v - 1;
@@ -621,79 +627,51 @@ __global__ void __launch_bounds__(kSegThreads, 5) k_fast_seg(const __grid_consta
             }
         }
         __syncthreads();
-        const int nq = qn;
-        __syncthreads();   // everyone has read the queue length: the counter now counts corners
-        if (t == 0) { qn = 0; nneed = 0; }
+        const int nq = qn;   // written again only by "prepare pass 1", several barriers from here
+        if (t == 0) nneed = 0;
         if (t < 8) need[t] = 0;
-        __syncthreads();
-        // ---- 3. exact score of the queued pixels; the corners among them go straight into a list --------------------
-        // The list lives in the rejection-mask area (dead until the next pass writes it again); if the corners outnumber it the
-        // NMS below walks all queued pixels instead.
-        uint16_t* cq = reinterpret_cast<uint16_t*>(mk);
-        const int cq_cap = th * 32;
-        for (int q0 = 0; q0 < nq; q0 += kSegThreads) {
-            const int q = q0 + t;
-            bool corner = false;
-            int e = 0;
-            if (q < nq) {
-                e = queue[q];
-                const uint8_t* p = tile + 3 * kSegPitch + e;
-                const uint32_t v = p[0];
-                const uint32_t bias = ((256u - v) << 16) | (256u + v);
-                uint32_t E[16];
-                E[0] = p[3 * kSegPitch] * 0xFFFFu + bias;  E[4] = p[3] * 0xFFFFu + bias;   // lo: 256 + d_k, hi: 256 - d_k
-                E[8] = p[-3 * kSegPitch] * 0xFFFFu + bias; E[12] = p[-3] * 0xFFFFu + bias;
-                {
-                    E[1] = p[3 * kSegPitch + 1] * 0xFFFFu + bias;   E[2] = p[2 * kSegPitch + 2] * 0xFFFFu + bias;   E[3] = p[kSegPitch + 3] * 0xFFFFu + bias;
-                    E[5] = p[-kSegPitch + 3] * 0xFFFFu + bias;      E[6] = p[-2 * kSegPitch + 2] * 0xFFFFu + bias;  E[7] = p[-3 * kSegPitch + 1] * 0xFFFFu + bias;
-                    E[9] = p[-3 * kSegPitch - 1] * 0xFFFFu + bias;  E[10] = p[-2 * kSegPitch - 2] * 0xFFFFu + bias; E[11] = p[-kSegPitch - 3] * 0xFFFFu + bias;
-                    E[13] = p[kSegPitch - 3] * 0xFFFFu + bias;      E[14] = p[2 * kSegPitch - 2] * 0xFFFFu + bias;  E[15] = p[3 * kSegPitch - 1] * 0xFFFFu + bias;
-                    uint32_t m3[16], m9[16];
+        // ---- 3. exact score of the queued pixels ------------------------------------------------------------------------------
+        for (int q = t; q < nq; q += kSegThreads) {
+            const int e = queue[q];
+            const uint8_t* p = tile + 3 * kSegPitch + e;
+            const uint32_t v = p[0];
+            const uint32_t bias = ((256u - v) << 16) | (256u + v);
+            uint32_t E[16];
+            E[0] = p[3 * kSegPitch] * 0xFFFFu + bias;  E[4] = p[3] * 0xFFFFu + bias;   // lo: 256 + d_k, hi: 256 - d_k
+            E[8] = p[-3 * kSegPitch] * 0xFFFFu + bias; E[12] = p[-3] * 0xFFFFu + bias;
+            E[1] = p[3 * kSegPitch + 1] * 0xFFFFu + bias;   E[2] = p[2 * kSegPitch + 2] * 0xFFFFu + bias;   E[3] = p[kSegPitch + 3] * 0xFFFFu + bias;
+            E[5] = p[-kSegPitch + 3] * 0xFFFFu + bias;      E[6] = p[-2 * kSegPitch + 2] * 0xFFFFu + bias;  E[7] = p[-3 * kSegPitch + 1] * 0xFFFFu + bias;
+            E[9] = p[-3 * kSegPitch - 1] * 0xFFFFu + bias;  E[10] = p[-2 * kSegPitch - 2] * 0xFFFFu + bias; E[11] = p[-kSegPitch - 3] * 0xFFFFu + bias;
+            E[13] = p[kSegPitch - 3] * 0xFFFFu + bias;      E[14] = p[2 * kSegPitch - 2] * 0xFFFFu + bias;  E[15] = p[3 * kSegPitch - 1] * 0xFFFFu + bias;
+            uint32_t m3[16], m9[16];
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) m3[k] = __vimin3_u16x2(E[k], E[(k + 1) & 15], E[(k + 2) & 15]);
+            for (int k = 0; k < 16; ++k) m3[k] = __vimin3_u16x2(E[k], E[(k + 1) & 15], E[(k + 2) & 15]);
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) m9[k] = __vimin3_u16x2(m3[k], m3[(k + 3) & 15], m3[(k + 6) & 15]);
-                    uint32_t a = __vimax3_u16x2(m9[0], m9[1], m9[2]), b = __vimax3_u16x2(m9[3], m9[4], m9[5]);
-                    uint32_t c = __vimax3_u16x2(m9[6], m9[7], m9[8]), d = __vimax3_u16x2(m9[9], m9[10], m9[11]);
-                    uint32_t f = __vimax3_u16x2(m9[12], m9[13], m9[14]);
-                    a = __vimax3_u16x2(a, b, c);
-                    d = __vimax3_u16x2(d, f, m9[15]);
-                    a = __vmaxu2(a, d);
-                    const int V = max((int)(a & 0xffffu), (int)(a >> 16)) - 257;
-                    if (V >= tcur) {
-                        score[e + kSegPitch + 4 - ox] = (uint8_t)V;   // (row + 1) * 256 + px + 4
-                        corner = true;
-                    }
-                }
-            }
-            const unsigned bal = __ballot_sync(0xffffffffu, corner);
-            if (bal) {
-                int base = 0;
-                if (lane == 0) base = smem_atomic_add(&qn, __popc(bal));
-                base = __shfl_sync(0xffffffffu, base, 0) + __popc(bal & ((1u << lane) - 1));
-                if (corner && base < cq_cap) cq[base] = (uint16_t)e;
-            }
+            for (int k = 0; k < 16; ++k) m9[k] = __vimin3_u16x2(m3[k], m3[(k + 3) & 15], m3[(k + 6) & 15]);
+            uint32_t a = __vimax3_u16x2(m9[0], m9[1], m9[2]), b = __vimax3_u16x2(m9[3], m9[4], m9[5]);
+            uint32_t c = __vimax3_u16x2(m9[6], m9[7], m9[8]), d = __vimax3_u16x2(m9[9], m9[10], m9[11]);
+            uint32_t f = __vimax3_u16x2(m9[12], m9[13], m9[14]);
+            a = __vimax3_u16x2(a, b, c);
+            d = __vimax3_u16x2(d, f, m9[15]);
+            a = __vmaxu2(a, d);
+            const int V = max((int)(a & 0xffffu), (int)(a >> 16)) - 257;
+            if (V >= tcur) score[e + kSegPitch + 4 - ox] = (uint8_t)V;   // (row + 1) * 256 + px + 4
         }
         __syncthreads();
-        // ---- 4b. NMS over the corners (all queued pixels if the corner list overflowed its buffer) ---------------
-        {
-            const bool use_cq = qn <= cq_cap;
-            const uint16_t* nms_q = use_cq ? cq : queue;
-            const int nms_n = use_cq ? qn : nq;
-            for (int q = t; q < nms_n; q += kSegThreads) {
-                const int e = nms_q[q], r = e >> 8, px = (e & 255) - ox;
-                const uint8_t* s = score + e + kSegPitch + 4 - ox;
-                const int v = s[0];
-                if (v < tcur) continue;
-                const int fl = lut[px];
-                // in pass 0 the score map only holds V >= iniTh; in pass 1 a cell's map holds everything >= minTh
-                bool k = v > s[-kSegPitch] && v > s[kSegPitch];
-                if (!(fl & 1)) k = k && v > s[-1] && v > s[-kSegPitch - 1] && v > s[kSegPitch - 1];
-                if (!(fl & 2)) k = k && v > s[1] && v > s[-kSegPitch + 1] && v > s[kSegPitch + 1];
-                if (k) {
-                    // plain shared-memory reduction (atomicOr makes ptxas build a warp-aggregation loop that costs more than it saves)
-                    asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(smem_u32(&bm_out[r * kBmWords + (px >> 5)])), "r"(1u << (px & 31)) : "memory");
-                }
+        // ---- 4. NMS over the queued pixels that are corners --------------------------------------------------------------------
+        for (int q = t; q < nq; q += kSegThreads) {
+            const int e = queue[q], r = e >> 8, px = (e & 255) - ox;
+            const uint8_t* s = score + e + kSegPitch + 4 - ox;
+            const int v = s[0];
+            if (v < tcur) continue;
+            const int fl = lut[px];
+            // in pass 0 the score map only holds V >= iniTh; in pass 1 a cell's map holds everything >= minTh
+            bool k = v > s[-kSegPitch] && v > s[kSegPitch];
+            if (!(fl & 1)) k = k && v > s[-1] && v > s[-kSegPitch - 1] && v > s[kSegPitch - 1];
+            if (!(fl & 2)) k = k && v > s[1] && v > s[-kSegPitch + 1] && v > s[kSegPitch + 1];
+            if (k) {
+                // plain shared-memory reduction (atomicOr makes ptxas build a warp-aggregation loop that costs more than it saves)
+                asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(smem_u32(&bm_out[r * kBmWords + (px >> 5)])), "r"(1u << (px & 31)) : "memory");
             }
         }
         __syncthreads();

@@ -166,6 +166,10 @@ class ORBextractor:
                                            out.ctypes.data, len(out), C.byref(n)))
         return out[:n.value].copy()
 
+    def octree_last_path(self) -> int:
+        """1: the pass-free construction answered the last octree() call, 0: the division-pass state machine."""
+        return int(self._lib.orbgpu_octree_last_path(self._h))
+
 
 class MultiGpuExtractor:
     """ORBextractor::operator() for a batch of frames over several GPUs of one box from ONE process

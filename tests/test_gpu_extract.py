@@ -174,6 +174,42 @@ def test_octree_stage_against_oracle(gpu, oracle):
             assert np.array_equal(got[f], exp[f]), f"iteration {it} field {f}"
 
 
+def test_octree_both_device_formulations(gpu, oracle):
+    """The pass-free construction (og_octree2.cuh) answers ordinary candidate sets; a tight cluster divides deeper than its cell
+    histogram and goes to the division-pass state machine (og_octree.cuh).  Both equal the oracle; careful-phase-heavy cases
+    (N close to the number of occupied cells) included."""
+    g = gpu(1000, 640, 480)
+    rs = np.random.RandomState(17)
+    paths = {0: 0, 1: 0}
+    for it in range(60):
+        width, height = int(rs.randint(200, 1250)), int(rs.randint(100, 400))
+        if round(width / height) < 1:
+            continue
+        M, N = int(rs.randint(50, 6000)), int(rs.randint(5, 900))
+        if it % 4 == 0:      # everything inside a few pixels: nodes divide down to single pixels
+            cx, cy, s = int(rs.randint(20, width - 20)), int(rs.randint(20, height - 20)), int(rs.randint(3, 12))
+            ys, xs = rs.randint(cy - s, cy + s, M), rs.randint(cx - s, cx + s, M)
+        elif it % 4 == 1:    # a few clusters
+            k = int(rs.randint(2, 6))
+            c = np.stack([rs.randint(10, height - 10, k), rs.randint(10, width - 10, k)], 1)[rs.randint(0, k, M)]
+            ys = np.clip(c[:, 0] + rs.normal(0, 6, M), 3, height - 4).astype(int)
+            xs = np.clip(c[:, 1] + rs.normal(0, 6, M), 3, width - 4).astype(int)
+        else:
+            ys, xs = rs.randint(3, height - 3, M), rs.randint(3, width - 3, M)
+        pts = np.unique(np.stack([ys, xs], 1), axis=0)
+        pts = pts[rs.permutation(len(pts))]
+        cand = np.zeros(len(pts), ol.KP_DTYPE)
+        cand["x"], cand["y"] = pts[:, 1], pts[:, 0]
+        cand["response"] = rs.randint(7, 255 if it % 2 else 40, len(pts))
+        exp = ol.octree(oracle, "orbo", cand, 16, 16 + width, 16, 16 + height, N)
+        got = g.octree(cand, 16, 16 + width, 16, 16 + height, N)
+        paths[g.octree_last_path()] += 1
+        assert len(got) == len(exp), it
+        for f in ("x", "y", "response"):
+            assert np.array_equal(got[f], exp[f]), f"iteration {it} field {f}"
+    assert paths[0] >= 3 and paths[1] >= 20, paths
+
+
 def test_full_size_batch_properties(oracle):
     """BASELINE size (KITTI 1241x376, 2000 features) at a full 512-frame batch: size-independent properties instead of
     512 oracle runs — every copy of a frame inside the batch gives byte-identical results wherever it sits (chunk and
