@@ -631,39 +631,54 @@ __global__ void __launch_bounds__(kSegThreads, 5) k_fast_seg(const __grid_consta
         if (t == 0) nneed = 0;
         if (t < 8) need[t] = 0;
         // ---- 3. exact score of the queued pixels ------------------------------------------------------------------------------
-        for (int q = t; q < nq; q += kSegThreads) {
-            const int e = queue[q];
-            const uint8_t* p = tile + 3 * kSegPitch + e;
-            const uint32_t v = p[0];
-            const uint32_t bias = ((256u - v) << 16) | (256u + v);
-            uint32_t E[16];
-            E[0] = p[3 * kSegPitch] * 0xFFFFu + bias;  E[4] = p[3] * 0xFFFFu + bias;   // lo: 256 + d_k, hi: 256 - d_k
-            E[8] = p[-3 * kSegPitch] * 0xFFFFu + bias; E[12] = p[-3] * 0xFFFFu + bias;
-            E[1] = p[3 * kSegPitch + 1] * 0xFFFFu + bias;   E[2] = p[2 * kSegPitch + 2] * 0xFFFFu + bias;   E[3] = p[kSegPitch + 3] * 0xFFFFu + bias;
-            E[5] = p[-kSegPitch + 3] * 0xFFFFu + bias;      E[6] = p[-2 * kSegPitch + 2] * 0xFFFFu + bias;  E[7] = p[-3 * kSegPitch + 1] * 0xFFFFu + bias;
-            E[9] = p[-3 * kSegPitch - 1] * 0xFFFFu + bias;  E[10] = p[-2 * kSegPitch - 2] * 0xFFFFu + bias; E[11] = p[-kSegPitch - 3] * 0xFFFFu + bias;
-            E[13] = p[kSegPitch - 3] * 0xFFFFu + bias;      E[14] = p[2 * kSegPitch - 2] * 0xFFFFu + bias;  E[15] = p[3 * kSegPitch - 1] * 0xFFFFu + bias;
-            uint32_t m3[16], m9[16];
+        // A warp takes a contiguous share of the queue and moves the corners it finds to the front of that share (ballot + running
+        // count in a register: no atomics, the write position never passes the read position), so the NMS below sees corners only.
+        const int per = ((nq + kSegThreads - 1) / kSegThreads) * 32;   // queue entries per warp
+        const int qlo = wi * per, qhi = min(qlo + per, nq);
+        int ncorner = 0;                                                // corners of this warp (same in all lanes)
+        for (int q0 = qlo; q0 < qhi; q0 += 32) {
+            const int q = q0 + lane;
+            bool corner = false;
+            int e = 0;
+            if (q < qhi) {
+                e = queue[q];
+                const uint8_t* p = tile + 3 * kSegPitch + e;
+                const uint32_t v = p[0];
+                const uint32_t bias = ((256u - v) << 16) | (256u + v);
+                uint32_t E[16];
+                E[0] = p[3 * kSegPitch] * 0xFFFFu + bias;  E[4] = p[3] * 0xFFFFu + bias;   // lo: 256 + d_k, hi: 256 - d_k
+                E[8] = p[-3 * kSegPitch] * 0xFFFFu + bias; E[12] = p[-3] * 0xFFFFu + bias;
+                E[1] = p[3 * kSegPitch + 1] * 0xFFFFu + bias;   E[2] = p[2 * kSegPitch + 2] * 0xFFFFu + bias;   E[3] = p[kSegPitch + 3] * 0xFFFFu + bias;
+                E[5] = p[-kSegPitch + 3] * 0xFFFFu + bias;      E[6] = p[-2 * kSegPitch + 2] * 0xFFFFu + bias;  E[7] = p[-3 * kSegPitch + 1] * 0xFFFFu + bias;
+                E[9] = p[-3 * kSegPitch - 1] * 0xFFFFu + bias;  E[10] = p[-2 * kSegPitch - 2] * 0xFFFFu + bias; E[11] = p[-kSegPitch - 3] * 0xFFFFu + bias;
+                E[13] = p[kSegPitch - 3] * 0xFFFFu + bias;      E[14] = p[2 * kSegPitch - 2] * 0xFFFFu + bias;  E[15] = p[3 * kSegPitch - 1] * 0xFFFFu + bias;
+                uint32_t m3[16], m9[16];
 #pragma unroll
-            for (int k = 0; k < 16; ++k) m3[k] = __vimin3_u16x2(E[k], E[(k + 1) & 15], E[(k + 2) & 15]);
+                for (int k = 0; k < 16; ++k) m3[k] = __vimin3_u16x2(E[k], E[(k + 1) & 15], E[(k + 2) & 15]);
 #pragma unroll
-            for (int k = 0; k < 16; ++k) m9[k] = __vimin3_u16x2(m3[k], m3[(k + 3) & 15], m3[(k + 6) & 15]);
-            uint32_t a = __vimax3_u16x2(m9[0], m9[1], m9[2]), b = __vimax3_u16x2(m9[3], m9[4], m9[5]);
-            uint32_t c = __vimax3_u16x2(m9[6], m9[7], m9[8]), d = __vimax3_u16x2(m9[9], m9[10], m9[11]);
-            uint32_t f = __vimax3_u16x2(m9[12], m9[13], m9[14]);
-            a = __vimax3_u16x2(a, b, c);
-            d = __vimax3_u16x2(d, f, m9[15]);
-            a = __vmaxu2(a, d);
-            const int V = max((int)(a & 0xffffu), (int)(a >> 16)) - 257;
-            if (V >= tcur) score[e + kSegPitch + 4 - ox] = (uint8_t)V;   // (row + 1) * 256 + px + 4
+                for (int k = 0; k < 16; ++k) m9[k] = __vimin3_u16x2(m3[k], m3[(k + 3) & 15], m3[(k + 6) & 15]);
+                uint32_t a = __vimax3_u16x2(m9[0], m9[1], m9[2]), b = __vimax3_u16x2(m9[3], m9[4], m9[5]);
+                uint32_t c = __vimax3_u16x2(m9[6], m9[7], m9[8]), d = __vimax3_u16x2(m9[9], m9[10], m9[11]);
+                uint32_t f = __vimax3_u16x2(m9[12], m9[13], m9[14]);
+                a = __vimax3_u16x2(a, b, c);
+                d = __vimax3_u16x2(d, f, m9[15]);
+                a = __vmaxu2(a, d);
+                const int V = max((int)(a & 0xffffu), (int)(a >> 16)) - 257;
+                if (V >= tcur) {
+                    score[e + kSegPitch + 4 - ox] = (uint8_t)V;   // (row + 1) * 256 + px + 4
+                    corner = true;
+                }
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, corner);   // every lane has read its entry of this chunk by now
+            if (corner) queue[qlo + ncorner + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)e;
+            ncorner += __popc(bal);
         }
         __syncthreads();
-        // ---- 4. NMS over the queued pixels that are corners --------------------------------------------------------------------
-        for (int q = t; q < nq; q += kSegThreads) {
+        // ---- 4. NMS over the corners (each warp walks its own list) ----------------------------------------------------------------
+        for (int q = qlo + lane; q < qlo + ncorner; q += 32) {
             const int e = queue[q], r = e >> 8, px = (e & 255) - ox;
             const uint8_t* s = score + e + kSegPitch + 4 - ox;
             const int v = s[0];
-            if (v < tcur) continue;
             const int fl = lut[px];
             // in pass 0 the score map only holds V >= iniTh; in pass 1 a cell's map holds everything >= minTh
             bool k = v > s[-kSegPitch] && v > s[kSegPitch];
