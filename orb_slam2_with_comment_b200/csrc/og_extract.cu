@@ -768,12 +768,14 @@ __global__ void __launch_bounds__(kSegThreads, 5) k_fast_seg(const __grid_consta
 // ------------------------------------------------------------------------------------------------------------
 // GaussianBlur 7x7 (separable, fixed point, Appendix A.2).  The level buffers carry a 19-px reflect-101 frame, which
 // is exactly what BORDER_REFLECT_101 of the isolated clone needs for taps up to 3 px outside (:1085-1086), so the
-// stencil has no border logic.  One CTA = 224 x 64 outputs of one (level, frame); the 256 x 70 input tile arrives by
+// stencil has no border logic.  One CTA = 224 x 128 outputs of one (level, frame); the 256 x 134 input tile arrives by
 // TMA (16-byte aligned origin: 16 spare columns on each side).  A thread owns one 32-bit word (4 columns) and walks
 // down 32 rows: the horizontal pass is two DP4A per pixel on byte windows cut with funnel shifts, the vertical pass
 // runs on a 7-row register window (fully unrolled, so the window rotates by renaming).
 // ------------------------------------------------------------------------------------------------------------
-constexpr int kBlurW = 224, kBlurH = 64, kBlurBox = kBlurH + 6, kBlurThreads = 128;
+// kBlurBands bands of 32 rows, kBlurW / 4 = 56 threads each: 224 threads = 7 full warps (with 64 threads per band an eighth of the
+// lanes had no column to work on)
+constexpr int kBlurW = 224, kBlurBands = 4, kBlurH = 32 * kBlurBands, kBlurBox = kBlurH + 6, kBlurThreads = kBlurBands * (kBlurW / 4);
 
 struct BlurTile {
     int16_t level, tx, ty, pad;
@@ -790,14 +792,14 @@ __global__ void __launch_bounds__(kBlurThreads) k_blur_tma(const __grid_constant
     __syncthreads();
     if (t == 0) {
         mbar_expect_tx(&mbar, kBlurBox * 256);
-        // tile column 16 = interior column 224*tx (global column kXPad + 224*tx), tile row 3 = interior row 64*ty
+        // tile column 16 = interior column 224*tx (global column kXPad + 224*tx), tile row 3 = interior row kBlurH*ty
         tma_load_3d(tile, tmaps + kMaxLevels + bt.level, kXPad - 16 + kBlurW * bt.tx, kEdge - 3 + kBlurH * bt.ty, frame, &mbar);
     }
-    const int c = t & 63, band = t >> 6;
+    const int band = t / (kBlurW / 4), c = t - band * (kBlurW / 4);
     const int x = kBlurW * bt.tx + 4 * c;          // first of this thread's 4 interior columns
     const int ybase = kBlurH * bt.ty + 32 * band;  // first output row of this band
     mbar_wait(&mbar, 0);
-    if (c >= kBlurW / 4 || x >= L.w || ybase >= L.h) return;
+    if (x >= L.w || ybase >= L.h) return;
     const uint32_t* T = reinterpret_cast<const uint32_t*>(tile) + (32 * band) * 64 + 4 + c;
     const uint32_t KLO = OG_G0 | (OG_G1 << 8) | (OG_G2 << 16) | (OG_G3 << 24), KHI = OG_G2 | (OG_G1 << 8) | (OG_G0 << 16);
     uint8_t* dst = level_ptr(P.blur, L, frame) + (long long)(kEdge + ybase) * L.pitch + kXPad + x;
@@ -808,6 +810,7 @@ __global__ void __launch_bounds__(kBlurThreads) k_blur_tma(const __grid_constant
     const uint32_t K01 = OG_G0 | (OG_G1 << 8), K23 = OG_G2 | (OG_G3 << 8), K21 = OG_G2 | (OG_G1 << 8);
 #pragma unroll
     for (int i = 0; i < 38; ++i) {
+        if (i >= nrows + 6) break;   // bottom tiles: nothing below the level's last row is needed
         // horizontal pass of tile row 32*band + i
         const uint32_t pw = T[i * 64 - 1], cw = T[i * 64], nw = T[i * 64 + 1];
         const uint32_t m3 = __funnelshift_r(pw, cw, 8), m2 = __funnelshift_r(pw, cw, 16), m1 = __funnelshift_r(pw, cw, 24);
