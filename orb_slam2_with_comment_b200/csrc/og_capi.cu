@@ -79,6 +79,7 @@ struct orbgpu_extractor {
     int n_btiles = 0;
     CUtensorMap* d_tmaps = nullptr;   // [4][kMaxLevels]: FAST tile boxes, blur input boxes, IC_Angle boxes (all over pyr), descriptor boxes over blur
     int fast_smem = 0;
+    bool frame_pending = false;   // the levels of the last call have no reflect-101 frame yet (written on demand)
     int oct_direct_smem = 0;      // shared memory of the pass-free octree (max over levels, for 256 / 512 threads: [0] / [1])
     int oct_direct_smem_lat = 0;
     int oct_kcap = 0, oct_kcap_lat = 0;   // keys whose path codes the pass-free octree caches in shared memory
@@ -503,10 +504,14 @@ int launch_extract(orbgpu_extractor* ex, const uint8_t* d_images, int batch, siz
     int aux = 0;
     for (int k = 1; k < orbgpu_extractor::kStreams; ++k)
         if (st == ex->compute_stream(k)) aux = k;
-    // The reflect-101 frames (two latency-bound kernels that use a few percent of the SMs) are needed by the blur only — FAST
-    // cells start 16 px inside a level — so they run on the auxiliary stream beside FAST.  ORBGPU_ASYNC_FRAME=0: in line.
-    static const int async_frame_env = []() { const char* e = getenv("ORBGPU_ASYNC_FRAME"); return e ? atoi(e) : 1; }();
-    const bool async_frame = !ex->profiling && async_frame_env != 0;
+    // The 19-px reflect-101 frame around every level (:1122-1128) is memory behind mvImagePyramid that nothing on this path reads:
+    // FAST cells start 16 px inside a level, the orientation and descriptor windows stay inside it, the blur mirrors its own
+    // 3-px halo.  It is therefore materialised ON DEMAND (orbgpu_extractor_read_level(bordered), the shell's mvImagePyramid
+    // download) and costs the extraction nothing.  ORBGPU_EAGER_FRAME=1 writes it with every call (on the auxiliary stream
+    // beside FAST, or in line when profiling) as before.
+    static const int eager_frame_env = []() { const char* e = getenv("ORBGPU_EAGER_FRAME"); return e ? atoi(e) : 0; }();
+    const bool eager_frame = eager_frame_env != 0;
+    const bool async_frame = eager_frame && !ex->profiling;
     auto borders = [&](cudaStream_t s) {
         // the generic resize writes its own frame; the border kernels then only repeat it (and do level 0)
         const int sides0 = 2 * P.lv[0].h;
@@ -514,7 +519,8 @@ int launch_extract(orbgpu_extractor* ex, const uint8_t* d_images, int batch, siz
         og::k_border_caps<<<dim3(2 * og::kEdge, P.n_levels, batch), og::kBorderThreads, 0, s>>>(P);
         launches += 2;
     };
-    if (!async_frame) borders(st);
+    if (eager_frame && !async_frame) borders(st);
+    if (!eager_frame) ex->frame_pending = true;
     mark(1);
     // measured on B200: pays off while a launch cannot fill the GPU (53.5k vs 50.0k frames/s at 64 frames), costs 8 % at 1024
     const bool overlap_blur = !ex->profiling && batch <= 128;
@@ -1009,6 +1015,18 @@ static int read_plane(orbgpu_extractor* ex, const uint8_t* base, int frame, int 
 
 int orbgpu_extractor_read_level(orbgpu_extractor* ex, int frame, int level, int bordered, uint8_t* out, size_t out_stride) {
     if (!ex) return fail(ORBGPU_ERR_ARG, "null extractor");
+    if (bordered && ex->frame_pending && ex->last_batch > 0) {
+        // the frame of every level of the last call, once (ORBextractor.cc:1122-1128)
+        OG_CUDA(cudaSetDevice(ex->device));
+        og::ExtractParams P = ex->P;
+        P.batch = ex->last_batch;
+        P.frame0 = 0;
+        const int sides0 = 2 * P.lv[0].h;
+        og::k_border_sides<<<dim3((sides0 + og::kBorderThreads - 1) / og::kBorderThreads, P.n_levels, P.batch), og::kBorderThreads, 0, ex->stream>>>(P);
+        og::k_border_caps<<<dim3(2 * og::kEdge, P.n_levels, P.batch), og::kBorderThreads, 0, ex->stream>>>(P);
+        OG_CUDA(cudaGetLastError());
+        ex->frame_pending = false;
+    }
     return read_plane(ex, ex->d_pyr, frame, level, bordered, out, out_stride);
 }
 

@@ -766,9 +766,9 @@ __global__ void __launch_bounds__(kSegThreads, 5) k_fast_seg(const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// GaussianBlur 7x7 (separable, fixed point, Appendix A.2).  The level buffers carry a 19-px reflect-101 frame, which
-// is exactly what BORDER_REFLECT_101 of the isolated clone needs for taps up to 3 px outside (:1085-1086), so the
-// stencil has no border logic.  One CTA = 224 x 128 outputs of one (level, frame); the 256 x 134 input tile arrives by
+// GaussianBlur 7x7 (separable, fixed point, Appendix A.2).  BORDER_REFLECT_101 of the isolated clone (:1085-1086) reaches 3 px
+// outside the level: the tiles at a level's edges mirror those pixels inside shared memory, the stencil itself has no
+// border logic.  One CTA = 224 x 128 outputs of one (level, frame); the 256 x 134 input tile arrives by
 // TMA (16-byte aligned origin: 16 spare columns on each side).  A thread owns one 32-bit word (4 columns) and walks
 // down 32 rows: the horizontal pass is two DP4A per pixel on byte windows cut with funnel shifts, the vertical pass
 // runs on a 7-row register window (fully unrolled, so the window rotates by renaming).
@@ -799,6 +799,34 @@ __global__ void __launch_bounds__(kBlurThreads) k_blur_tma(const __grid_constant
     const int x = kBlurW * bt.tx + 4 * c;          // first of this thread's 4 interior columns
     const int ybase = kBlurH * bt.ty + 32 * band;  // first output row of this band
     mbar_wait(&mbar, 0);
+    // BORDER_REFLECT_101 of the isolated level (:1085-1086) for the 3 pixels the taps reach outside it: written into the tile here,
+    // so the kernel does not depend on the level's 19-px frame in HBM (which is materialised only on demand).  Columns first
+    // (every tile row), then rows as whole tile rows, like copyMakeBorder.
+    {
+        const int ex_ = L.w - 1 - kBlurW * bt.tx, ey = L.h - 1 - kBlurH * bt.ty;   // last image column / row in tile-local output coordinates
+        const bool fix_l = bt.tx == 0, fix_r = ex_ <= kBlurW + 2, fix_t = bt.ty == 0, fix_b = ey <= kBlurH + 2;
+        if (fix_l || fix_r) {
+            for (int r = t; r < kBlurBox; r += kBlurThreads) {
+                uint8_t* row = tile + r * 256 + 16;
+                if (fix_l) { row[-1] = row[1]; row[-2] = row[2]; row[-3] = row[3]; }
+                if (fix_r) {
+#pragma unroll
+                    for (int k = 1; k <= 3; ++k)
+                        if (16 + ex_ + k < 256) row[ex_ + k] = row[ex_ - k];
+                }
+            }
+            __syncthreads();
+        }
+        if (fix_t || fix_b) {
+            uint32_t* Tw = reinterpret_cast<uint32_t*>(tile);
+            for (int i = t; i < 3 * 64; i += kBlurThreads) {
+                const int k = i / 64 + 1, wd = i & 63;
+                if (fix_t) Tw[(3 - k) * 64 + wd] = Tw[(3 + k) * 64 + wd];
+                if (fix_b && 3 + ey + k < kBlurBox) Tw[(3 + ey + k) * 64 + wd] = Tw[(3 + ey - k) * 64 + wd];
+            }
+            __syncthreads();
+        }
+    }
     if (x >= L.w || ybase >= L.h) return;
     const uint32_t* T = reinterpret_cast<const uint32_t*>(tile) + (32 * band) * 64 + 4 + c;
     const uint32_t KLO = OG_G0 | (OG_G1 << 8) | (OG_G2 << 16) | (OG_G3 << 24), KHI = OG_G2 | (OG_G1 << 8) | (OG_G0 << 16);
