@@ -721,6 +721,40 @@ __global__ void __launch_bounds__(kSegThreads, 5) k_fast_seg(const __grid_consta
         const int ci = sg.first_cell + j;
         const Cell c = P.cells[ci];
         const int cx = j * wc, cw = c.tw;
+        uint32_t* oxy = P.cand_xy + (long long)frame * P.total_cand_cap + L.cand_base + c.slot;
+        uint8_t* orr = P.cand_resp + (long long)frame * P.total_cand_cap + L.cand_base + c.slot;
+        if (th <= 32 && cw <= 32) {
+            // the usual cell (about 30 x 30 tested pixels): one bitmap word per row, one row per lane
+            const uint32_t wmask = cw >= 32 ? ~0u : ((1u << cw) - 1u);
+            uint32_t mm = 0, mi = 0;
+            if (lane < th) {
+                const uint32_t* a = bm_min + lane * kBmWords + (cx >> 5);
+                const uint32_t* b = bm_ini + lane * kBmWords + (cx >> 5);
+                const int sh = cx & 31;
+                mm = __funnelshift_r(a[0], a[1], sh) & wmask;
+                mi = __funnelshift_r(b[0], b[1], sh) & wmask;
+            }
+            if (__any_sync(0xffffffffu, mi != 0)) mm = mi;
+            const int c0 = __popc(mm);
+            int i0 = c0;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int o0 = __shfl_up_sync(0xffffffffu, i0, d);
+                if (lane >= d) i0 += o0;
+            }
+            const int tot = __shfl_sync(0xffffffffu, i0, 31);
+            int pos = i0 - c0;
+            while (mm) {
+                const int b = __ffs((int)mm) - 1;
+                mm &= mm - 1;
+                // coordinates relative to (minBorderX, minBorderY) = (16,16) as the reference stores them (:822-823)
+                oxy[pos] = ((uint32_t)(c.y0 + lane - 16) << 16) | (uint32_t)(c.x0 + b - 16);
+                orr[pos] = score[(lane + 1) * kSegPitch + cx + b + 4];
+                ++pos;
+            }
+            if (lane == 0) P.cell_count[(long long)frame * P.total_cells + ci] = tot;
+            continue;
+        }
         const uint64_t wmask = cw >= 64 ? ~0ull : ((1ull << cw) - 1);
         uint64_t mm[2], mi[2];
 #pragma unroll
@@ -745,8 +779,6 @@ __global__ void __launch_bounds__(kSegThreads, 5) k_fast_seg(const __grid_consta
             if (lane >= d) { i0 += o0; i1 += o1; }
         }
         const int tot0 = __shfl_sync(0xffffffffu, i0, 31), tot1 = __shfl_sync(0xffffffffu, i1, 31);
-        uint32_t* oxy = P.cand_xy + (long long)frame * P.total_cand_cap + L.cand_base + c.slot;
-        uint8_t* orr = P.cand_resp + (long long)frame * P.total_cand_cap + L.cand_base + c.slot;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int row = lane + 32 * h;
@@ -755,7 +787,6 @@ __global__ void __launch_bounds__(kSegThreads, 5) k_fast_seg(const __grid_consta
             while (m) {
                 const int b = __ffsll((long long)m) - 1;
                 m &= m - 1;
-                // coordinates relative to (minBorderX, minBorderY) = (16,16) as the reference stores them (:822-823)
                 oxy[pos] = ((uint32_t)(c.y0 + row - 16) << 16) | (uint32_t)(c.x0 + b - 16);
                 orr[pos] = score[(row + 1) * kSegPitch + cx + b + 4];
                 ++pos;
@@ -896,17 +927,24 @@ __device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c) {   // uns
     return r;
 }
 
-// Both neighbourhoods of a key point arrive by TMA (one elected lane, two boxes, one mbarrier each per warp): the 31 x 31
-// disc of the level for IC_Angle and the 37 x 37 window of the blurred level for the descriptor.  A box starts at a 16-byte
-// aligned column at or left of the window (TMA's alignment rule), so it is 48 / 64 bytes wide.  tmaps: [2K + l] level boxes,
-// [3K + l] blur boxes (K = kMaxLevels).
+// Both neighbourhoods of a key point arrive by TMA (one elected lane, double-buffered boxes, one mbarrier per buffer and warp):
+// the 31 x 31 disc of the level for IC_Angle and the 37 x 37 window of the blurred level for the descriptor.  A box starts at a
+// 16-byte aligned column at or left of the window (TMA's alignment rule), so it is 48 / 64 bytes wide.  tmaps: [2K + l] level
+// boxes, [3K + l] blur boxes (K = kMaxLevels).
+// A warp owns kDescPerWarp key points and works in phases, so that everything that is ONE value per key point is computed by
+// one lane per key point instead of by all 32 lanes for one key point at a time:
+//   0. lane n looks up key point n (level, position, response);
+//   1. moments: the discs stream through two buffers, all lanes sum one disc, lane n keeps m10 / m01 of key point n;
+//   2. lane n: fastAtan2, cos / sin, the cv::KeyPoint record;
+//   3. descriptors: the blurred windows stream through the same two buffers, cos / sin of key point n come by shuffle.
 __global__ void __launch_bounds__(kDescWarps * 32, 6) k_orient_desc(const __grid_constant__ ExtractParams P, const CUtensorMap* __restrict__ tmaps,
                                                                     KeyPoint* __restrict__ kp_out, uint8_t* __restrict__ desc_out,
                                                                     int32_t* __restrict__ counts) {
+    static_assert(kDescPerWarp <= 32 && 2 * kIcSlot <= 2 * kBlurSlot, "one lane per key point; the disc buffers fit into the window buffers");
     // pattern point j of lane i (= bit_pattern_31_ point 16 i + j) at spat[j * 32 + i]: the 32 lanes of a load hit 32
     // consecutive 8-byte slots (no bank conflicts), and the coordinates are already floats (no I2F in the sample loop)
     __shared__ float2 spat[512];
-    __shared__ __align__(128) uint8_t patch[kDescWarps][kIcSlot + kBlurSlot];
+    __shared__ __align__(128) uint8_t patch[kDescWarps][2 * kBlurSlot];
     __shared__ uint64_t bars[kDescWarps][2];
     for (int i = threadIdx.x; i < 512; i += blockDim.x) spat[(i & 15) * 32 + (i >> 4)] = make_float2((float)c_pat_x[i], (float)c_pat_y[i]);
     const int frame = P.frame0 + blockIdx.y;
@@ -924,38 +962,49 @@ __global__ void __launch_bounds__(kDescWarps * 32, 6) k_orient_desc(const __grid
     for (int l = 0; l < kMaxLevels; ++l) lstart[l + 1] = lstart[l] + (l < P.n_levels ? sc[l] : 0);
     const int total = min(lstart[kMaxLevels], P.kp_cap);
     if (blockIdx.x == 0 && threadIdx.x == 0) counts[frame] = total;
-    uint8_t* ic_tile = patch[wi];
-    uint8_t* bl_tile = patch[wi] + kIcSlot;
-    const int ic_r = lane / kIcWords, ic_j = lane - ic_r * kIcWords;     // lanes 0..26: 3 disc rows x 9 words per step
+    const unsigned full = 0xffffffffu;
 
-    for (int n = 0; n < kDescPerWarp; ++n) {
-        const int idx = (blockIdx.x * kDescPerWarp + n) * kDescWarps + wi;   // index among the frame's keypoints
-        if (idx >= total) break;
-        int level = 0, first = 0;
+    // ---- 0. lane n: key point n of this warp -------------------------------------------------------------------------------
+    const int my_idx = (blockIdx.x * kDescPerWarp + lane) * kDescWarps + wi;   // index among the frame's keypoints
+    const bool mine = lane < kDescPerWarp && my_idx < total;
+    int my_level = 0, my_cx = 0, my_cy = 0, my_resp = 0;
+    if (mine) {
+        int first = 0;
 #pragma unroll
         for (int l = 1; l < kMaxLevels; ++l)
-            if (idx >= lstart[l]) { level = l; first = lstart[l]; }
-        const int off = idx - first;
-        const Level& L = P.lv[level];
-        const uint32_t xy = P.sel_xy[(long long)frame * P.total_sel_cap + L.sel_base + off];
-        const int resp = P.sel_resp[(long long)frame * P.total_sel_cap + L.sel_base + off];
-        const int cx = (int)(xy & 0xffffu) + 16, cy = (int)(xy >> 16) + 16;   // level coordinates (:840-841)
-        const int icx = kXPad + cx - kHalfPatch, blx = kXPad + cx - 18;       // first column of the disc / of the 37-wide window
-        __syncwarp();   // every lane is done with the previous key point's tiles
-        if (lane == 0) {
-            mbar_expect_tx(&bars[wi][0], kIcBoxW * kIcRows);
-            tma_load_3d(ic_tile, tmaps + 2 * kMaxLevels + level, icx & ~15, kEdge + cy - kHalfPatch, frame, &bars[wi][0]);
-            mbar_expect_tx(&bars[wi][1], kBlurBoxW * kPatchRows);
-            tma_load_3d(bl_tile, tmaps + 3 * kMaxLevels + level, blx & ~15, kEdge + cy - 18, frame, &bars[wi][1]);
-        }
-        const uint32_t phase = (uint32_t)(n & 1);
+            if (my_idx >= lstart[l]) { my_level = l; first = lstart[l]; }
+        const Level& L = P.lv[my_level];
+        const long long o = (long long)frame * P.total_sel_cap + L.sel_base + (my_idx - first);
+        const uint32_t xy = P.sel_xy[o];
+        my_resp = P.sel_resp[o];
+        my_cx = (int)(xy & 0xffffu) + 16;   // level coordinates (:840-841)
+        my_cy = (int)(xy >> 16) + 16;
+    }
+    const int nk = __popc(__ballot_sync(full, mine));   // the warp's key points are lanes 0 .. nk-1
+    if (nk == 0) return;
+    uint8_t* buf0 = patch[wi];
+    uint32_t use0 = 0, use1 = 0;   // completed phases of the two barriers
 
-        // ---- IC_Angle
+    // ---- 1. IC_Angle moments (:77-104) ------------------------------------------------------------------------------------------
+    const int ic_r = lane / kIcWords, ic_j = lane - ic_r * kIcWords;     // lanes 0..26: 3 disc rows x 9 words per step
+    auto issue_ic = [&](int n) {
+        const int lv = __shfl_sync(full, my_level, n), cx = __shfl_sync(full, my_cx, n), cy = __shfl_sync(full, my_cy, n);
+        if (lane == 0) {
+            uint64_t* bar = &bars[wi][n & 1];
+            mbar_expect_tx(bar, kIcBoxW * kIcRows);
+            tma_load_3d(buf0 + (n & 1) * kIcSlot, tmaps + 2 * kMaxLevels + lv, (kXPad + cx - kHalfPatch) & ~15, kEdge + cy - kHalfPatch, frame, bar);
+        }
+    };
+    int my_m10 = 0, my_m01 = 0;
+    issue_ic(0);
+    for (int n = 0; n < nk; ++n) {
+        if (n + 1 < nk) issue_ic(n + 1);   // its buffer was read two iterations ago (the __syncwarp below)
+        const int icx = kXPad + __shfl_sync(full, my_cx, n) - kHalfPatch;   // first column of the disc
         int m10 = 0, m01 = 0;
-        mbar_wait(&bars[wi][0], phase);
+        if (n & 1) { mbar_wait(&bars[wi][1], use1 & 1); ++use1; } else { mbar_wait(&bars[wi][0], use0 & 1); ++use0; }
         {
             const int A = icx & 3;
-            const uint32_t* base = reinterpret_cast<const uint32_t*>(ic_tile + ((icx & 15) & ~3)) + ic_j;   // aligned word holding the disc's first column
+            const uint32_t* base = reinterpret_cast<const uint32_t*>(buf0 + (n & 1) * kIcSlot + ((icx & 15) & ~3)) + ic_j;   // aligned word holding the disc's first column
             const uint2* tab = reinterpret_cast<const uint2*>(P.ic_tab) + (A * kIcRows) * kIcWords + ic_j;
             if (lane < 3 * kIcWords) {
 #pragma unroll
@@ -972,17 +1021,47 @@ __global__ void __launch_bounds__(kDescWarps * 32, 6) k_orient_desc(const __grid
         }
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) {
-            m10 += __shfl_xor_sync(0xffffffffu, m10, d);
-            m01 += __shfl_xor_sync(0xffffffffu, m01, d);
+            m10 += __shfl_xor_sync(full, m10, d);
+            m01 += __shfl_xor_sync(full, m01, d);
         }
-        const float angle = fast_atan2((float)m01, (float)m10, P.atan);
+        if (lane == n) { my_m10 = m10; my_m01 = m01; }
+        __syncwarp();   // every lane is done with this buffer
+    }
 
-        // ---- rotated BRIEF on the blurred window
-        const float ang = fmul(angle, P.factor_pi);
-        float a, b;
-        sincosf_glibc(ang, &b, &a);   // a = cos, b = sin, as glibc's sincosf returns them to the reference (:113)
-        mbar_wait(&bars[wi][1], phase);
-        const uint8_t* b0 = bl_tile + 18 * kBlurBoxW + 18 + (blx & 15);
+    // ---- 2. lane n: orientation, cos / sin, the KeyPoint record (:837-847, :1095-1103) ----------------------------------------------------
+    float my_a = 0.f, my_b = 0.f;
+    if (mine) {
+        const float angle = fast_atan2((float)my_m01, (float)my_m10, P.atan);
+        sincosf_glibc(fmul(angle, P.factor_pi), &my_b, &my_a);   // a = cos, b = sin, as glibc's sincosf returns them to the reference (:113)
+        const Level& L = P.lv[my_level];
+        KeyPoint kp;
+        const float fx = (float)my_cx, fy = (float)my_cy;
+        kp.x = my_level ? fmul(fx, L.scale) : fx;   // keypoint->pt *= scale for level != 0 (:1095-1101)
+        kp.y = my_level ? fmul(fy, L.scale) : fy;
+        kp.size = L.kp_size;
+        kp.angle = angle;
+        kp.response = (float)my_resp;
+        kp.octave = my_level;
+        kp.class_id = -1;
+        kp_out[(long long)frame * P.kp_cap + my_idx] = kp;
+    }
+
+    // ---- 3. rotated BRIEF on the blurred windows (:108-147) ----------------------------------------------------------------------------------
+    auto issue_bl = [&](int n) {
+        const int lv = __shfl_sync(full, my_level, n), cx = __shfl_sync(full, my_cx, n), cy = __shfl_sync(full, my_cy, n);
+        if (lane == 0) {
+            uint64_t* bar = &bars[wi][n & 1];
+            mbar_expect_tx(bar, kBlurBoxW * kPatchRows);
+            tma_load_3d(buf0 + (n & 1) * kBlurSlot, tmaps + 3 * kMaxLevels + lv, (kXPad + cx - 18) & ~15, kEdge + cy - 18, frame, bar);
+        }
+    };
+    issue_bl(0);
+    for (int n = 0; n < nk; ++n) {
+        if (n + 1 < nk) issue_bl(n + 1);
+        const float a = __shfl_sync(full, my_a, n), b = __shfl_sync(full, my_b, n);
+        const int blx = kXPad + __shfl_sync(full, my_cx, n) - 18;   // first column of the 37-wide window
+        if (n & 1) { mbar_wait(&bars[wi][1], use1 & 1); ++use1; } else { mbar_wait(&bars[wi][0], use0 & 1); ++use0; }
+        const uint8_t* b0 = buf0 + (n & 1) * kBlurSlot + 18 * kBlurBoxW + 18 + (blx & 15);
         int val = 0;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -993,19 +1072,9 @@ __global__ void __launch_bounds__(kDescWarps * 32, 6) k_orient_desc(const __grid
             const int t0 = b0[r0 * kBlurBoxW + q0], t1 = b0[r1 * kBlurBoxW + q1];
             val |= (t0 < t1) << k;
         }
+        const int idx = (blockIdx.x * kDescPerWarp + n) * kDescWarps + wi;
         desc_out[((long long)frame * P.kp_cap + idx) * 32 + lane] = (uint8_t)val;
-        if (lane == 0) {
-            KeyPoint kp;
-            const float fx = (float)cx, fy = (float)cy;
-            kp.x = level ? fmul(fx, L.scale) : fx;   // keypoint->pt *= scale for level != 0 (:1095-1101)
-            kp.y = level ? fmul(fy, L.scale) : fy;
-            kp.size = L.kp_size;
-            kp.angle = angle;
-            kp.response = (float)resp;
-            kp.octave = level;
-            kp.class_id = -1;
-            kp_out[(long long)frame * P.kp_cap + idx] = kp;
-        }
+        __syncwarp();   // every lane is done with this buffer
     }
 }
 
