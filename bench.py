@@ -438,6 +438,7 @@ def dist_setup(n_gpus: int):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    os.environ.setdefault("NCCL_DEBUG", "WARN")   # no "NCCL version ..." banner on stdout: rank 0 prints exactly one JSON line
     return rank, world, local
 
 
@@ -613,12 +614,30 @@ def run_ours(args):
                 traffic = float(tj["dram_bytes_per_frame"][dominant]) * B
         except Exception:
             traffic = None
+    pipes = {}
+    spath = os.path.join(ROOT, "profiles", "r2_extract_v5_B1024_ncu_full_summary.csv")
+    if os.path.exists(spath):
+        try:   # what actually binds the dominant kernel: issue slots / ALU pipe of the committed ncu --set full capture at the bench batch
+            import csv
+            rows = list(csv.reader(open(spath)))
+            hdr = rows[0]
+            kname = {"fast_cells": "k_fast_seg", "blur": "k_blur_tma", "orient_desc": "k_orient_desc", "octree": "k_octree"}.get(dominant, "")
+            for r in rows[2:]:
+                if kname and r[0].startswith(kname):
+                    px = sum(w * h for (w, h) in level_sizes())
+                    pipes = {"ncu_issue_active_pct": float(r[hdr.index("issue%")]), "ncu_alu_pipe_pct": float(r[hdr.index("alu%")]),
+                             "ncu_l1tex_pct": float(r[hdr.index("l1tex%")]), "ncu_dram_pct": float(r[hdr.index("dram%")]),
+                             "ncu_thread_inst_per_pyramid_pixel": float(r[hdr.index("warp_inst")]) * 32 / (B * px),
+                             "ncu_source": "profiles/r2_extract_v5_B1024_ncu_full_summary.csv"}
+                    break
+        except Exception:
+            pipes = {}
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": per_stage_bytes[dominant] * B,
                 "note": "FAST/NMS/octree are integer-issue bound, not bandwidth bound (SURVEY §7.3 #7); whole pipeline: "
                         f"B_alg={b_alg} B/frame -> {b_alg * value / 1e9:.1f} GB/s = {b_alg * value / 1e9 / peak:.4f} of peak",
-                "stage_ms": stage}
+                "stage_ms": stage, **pipes}
 
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
