@@ -1,3 +1,7 @@
-python -m pytest tests/test_gpu_extract.py tests/test_reference_golden.py tests/test_gpu_pipeline.py -m gpu -x -q 2>&1 | tail -3
-python tools/stage_times.py 1024 3 256 2>&1 | tail -1
-python tools/quick_bench.py 1 20 1 2>&1 | tail -2
+python tools/e2e_sweep.py
+ORBGPU_TAPER=2 python tools/e2e_sweep.py
+ORBGPU_TAPER=4 python tools/e2e_sweep.py
+ORBGPU_CHUNK=32 ORBGPU_STREAMS=4 python tools/e2e_sweep.py
+ORBGPU_CHUNK=32 ORBGPU_STREAMS=4 ORBGPU_TAPER=3 python tools/e2e_sweep.py
+ORBGPU_CHUNK=64 ORBGPU_STREAMS=3 ORBGPU_TAPER=4 python tools/e2e_sweep.py
+ORBGPU_CHUNK=24 ORBGPU_STREAMS=4 python tools/e2e_sweep.py
