@@ -546,6 +546,28 @@ def run_ours(args):
     value = world * B * args.steps / (ms / 1e3)
     kp_per_frame = float(d_cnt.float().mean().item())
 
+    # ---- the same with the 19-px frame of every level written inside every call, as the reference's ComputePyramid does ----
+    # (default: written on the first bordered read-back, since nothing on the path reads it; see include/orbgpu.h)
+    ex.set_eager_frame(True)
+    for _ in range(2):
+        step_dev()
+    ex.sync()
+    barrier()
+    e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e4.record(stream)
+    for _ in range(args.steps):
+        step_dev()
+    e5.record(stream)
+    ex.sync()
+    barrier()
+    ms_eager = e4.elapsed_time(e5)
+    if world > 1:
+        t = torch.tensor([ms_eager], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_eager = float(t.item())
+    value_eager = world * B * args.steps / (ms_eager / 1e3)
+    ex.set_eager_frame(False)
+
     # ---- per-stage durations (same steps again, events between the stages) ---------------------------------
     ex.set_profiling(True)
     stage = {k: 0.0 for k in ex.STAGES}
@@ -646,7 +668,11 @@ def run_ours(args):
         "config": {"workload": WORKLOAD, "batch_per_gpu": B, "frames_per_step": world * B, "distinct_frames": min(N_DISTINCT, B),
                    "parallelism": f"frame-sharded x{world}, no collective",
                    "l2_policy": f"inputs larger than L2: {B * W * H / 1e6:.0f} MB of frames + {B * 1.9:.0f} MB pyramid per step per GPU",
-                   "keypoints_per_frame": kp_per_frame},
+                   "keypoints_per_frame": kp_per_frame,
+                   "pyramid_frame": "the 19-px BORDER_REFLECT_101 frame around the levels (ORBextractor.cc:1122-1128) is written on the first "
+                                    "bordered read-back, not in the step: nothing in operator() or its callers reads it (the blur mirrors its "
+                                    "own 3-px halo); value_eager_frame is the same measurement with the frame written in every step"},
+        "value_eager_frame": value_eager, "ms_per_step_eager_frame": ms_eager / args.steps,
         "clocks": clocks,
         "e2e": dict({"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(B * W * H),
                      "d2h_bytes_per_step": int(B * (ex.kp_cap * 60 + 4)), "ms_per_step": ms_e2e / args.steps}, **transfer_ceiling(world, e2e_value)),

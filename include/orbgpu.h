@@ -113,6 +113,12 @@ int orbgpu_extractor_last_launches(const orbgpu_extractor* ex);
 /* Per-stage device time of the last extract call, measured with CUDA events on the extractor's stream:
  * ms5 = { pyramid (level 0 + 7 resizes), FAST cells, octree, blur (8 levels), orientation+descriptors }. */
 int orbgpu_extractor_set_profiling(orbgpu_extractor* ex, int enable);
+/* The 19-px BORDER_REFLECT_101 frame around every pyramid level (copyMakeBorder, ORBextractor.cc:1122-1128).  Nothing in
+ * operator() — or anywhere else in ORB-SLAM2 — reads it: FAST cells start 16 px inside a level, the key-point windows stay inside
+ * it, GaussianBlur runs on an isolated clone (:1085-1086).  By default it is therefore written when a bordered level is read
+ * back (orbgpu_extractor_read_level with bordered != 0); enable != 0 writes it with every extraction call, as the reference
+ * does (about 5 % of the extraction time).  The bytes are the same either way. */
+int orbgpu_extractor_set_eager_frame(orbgpu_extractor* ex, int enable);
 int orbgpu_extractor_stage_ms(orbgpu_extractor* ex, float* ms5);
 
 /* mvImagePyramid (ORBextractor.h:86, filled by ComputePyramid :1107-1132) of frame `frame` of the last call.

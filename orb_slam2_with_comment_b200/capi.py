@@ -45,6 +45,7 @@ def lib() -> C.CDLL:
     L.orbgpu_extractor_stream.argtypes = [vp, C.POINTER(vp)]
     L.orbgpu_extractor_last_launches.argtypes = [vp]
     L.orbgpu_extractor_set_profiling.argtypes = [vp, i]
+    L.orbgpu_extractor_set_eager_frame.argtypes = [vp, i]
     L.orbgpu_extractor_stage_ms.argtypes = [vp, vp]
     L.orbgpu_extractor_level_dims.argtypes = [vp, i, C.POINTER(i), C.POINTER(i)]
     L.orbgpu_extractor_read_level.argtypes = [vp, i, i, i, vp, sz]

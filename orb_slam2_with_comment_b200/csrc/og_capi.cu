@@ -80,6 +80,7 @@ struct orbgpu_extractor {
     CUtensorMap* d_tmaps = nullptr;   // [4][kMaxLevels]: FAST tile boxes, blur input boxes, IC_Angle boxes (all over pyr), descriptor boxes over blur
     int fast_smem = 0;
     bool frame_pending = false;   // the levels of the last call have no reflect-101 frame yet (written on demand)
+    bool eager_frame = false;     // orbgpu_extractor_set_eager_frame: write the frame with every call, like the reference
     int oct_direct_smem = 0;      // shared memory of the pass-free octree (max over levels, for 256 / 512 threads: [0] / [1])
     int oct_direct_smem_lat = 0;
     int oct_kcap = 0, oct_kcap_lat = 0;   // keys whose path codes the pass-free octree caches in shared memory
@@ -510,7 +511,7 @@ int launch_extract(orbgpu_extractor* ex, const uint8_t* d_images, int batch, siz
     // download) and costs the extraction nothing.  ORBGPU_EAGER_FRAME=1 writes it with every call (on the auxiliary stream
     // beside FAST, or in line when profiling) as before.
     static const int eager_frame_env = []() { const char* e = getenv("ORBGPU_EAGER_FRAME"); return e ? atoi(e) : 0; }();
-    const bool eager_frame = eager_frame_env != 0;
+    const bool eager_frame = eager_frame_env != 0 || ex->eager_frame;
     const bool async_frame = eager_frame && !ex->profiling;
     auto borders = [&](cudaStream_t s) {
         // the generic resize writes its own frame; the border kernels then only repeat it (and do level 0)
@@ -974,6 +975,12 @@ int og_extractor_last_results(orbgpu_extractor* ex, int* device, int* batch, int
 }
 
 extern "C" {
+
+int orbgpu_extractor_set_eager_frame(orbgpu_extractor* ex, int enable) {
+    if (!ex) return fail(ORBGPU_ERR_ARG, "null extractor");
+    ex->eager_frame = enable != 0;
+    return ORBGPU_OK;
+}
 
 int orbgpu_extractor_set_profiling(orbgpu_extractor* ex, int enable) {
     if (!ex) return fail(ORBGPU_ERR_ARG, "null extractor");

@@ -122,6 +122,11 @@ class ORBextractor:
     def set_profiling(self, on: bool):
         capi.check(self._lib.orbgpu_extractor_set_profiling(self._h, int(on)))
 
+    def set_eager_frame(self, on: bool):
+        """Write the 19-px reflect-101 frame of every level with each call (as the reference does) instead of on the first
+        bordered read-back; the bytes are the same either way."""
+        capi.check(self._lib.orbgpu_extractor_set_eager_frame(self._h, int(on)))
+
     def stage_ms(self):
         ms = np.zeros(5, np.float32)
         capi.check(self._lib.orbgpu_extractor_stage_ms(self._h, ms.ctypes.data))

@@ -174,6 +174,30 @@ def test_octree_stage_against_oracle(gpu, oracle):
             assert np.array_equal(got[f], exp[f]), f"iteration {it} field {f}"
 
 
+def test_frame_on_demand_and_eager_agree(gpu, oracle):
+    """The 19-px reflect-101 frame of the levels (ORBextractor.cc:1122-1128) is written on the first bordered read-back by default
+    and inside the call with set_eager_frame(True): same key points, same descriptors, same bordered levels as the oracle either
+    way, also for the frames of a batch and after interior-only reads."""
+    w, h, nf, B = 752, 480, 1200, 5
+    imgs = np.stack([synth.g_rects(w, h, 40 + i) for i in range(B)])
+    g = gpu(nf, w, h, B)
+    o = ol.Extractor(oracle, "orbo", nf, 1.2, 8, 20, 7)
+    res = {}
+    for eager in (False, True):
+        g.set_eager_frame(eager)
+        kp, desc, cnt = g.extract_batch(imgs)
+        inner = g.level(3, frame=2)                      # an interior read must not disturb the pending frame
+        res[eager] = (kp.copy(), desc.copy(), cnt.copy(), [g.level(l, frame=B - 1, bordered=True) for l in range(8)], inner)
+    g.set_eager_frame(False)
+    assert np.array_equal(res[False][2], res[True][2])
+    assert res[False][0].tobytes() == res[True][0].tobytes() and np.array_equal(res[False][1], res[True][1])
+    o.extract(imgs[B - 1])
+    for l in range(8):
+        assert np.array_equal(res[False][3][l], o.level(l, True)), f"level {l}, frame on demand"
+        assert np.array_equal(res[True][3][l], o.level(l, True)), f"level {l}, eager frame"
+    assert np.array_equal(res[False][4], res[True][4])
+
+
 def test_octree_both_device_formulations(gpu, oracle):
     """The pass-free construction (og_octree2.cuh) answers ordinary candidate sets; a tight cluster divides deeper than its cell
     histogram and goes to the division-pass state machine (og_octree.cuh).  Both equal the oracle; careful-phase-heavy cases

@@ -1,7 +1,2 @@
-python tools/e2e_sweep.py
-ORBGPU_TAPER=2 python tools/e2e_sweep.py
-ORBGPU_TAPER=4 python tools/e2e_sweep.py
-ORBGPU_CHUNK=32 ORBGPU_STREAMS=4 python tools/e2e_sweep.py
-ORBGPU_CHUNK=32 ORBGPU_STREAMS=4 ORBGPU_TAPER=3 python tools/e2e_sweep.py
-ORBGPU_CHUNK=64 ORBGPU_STREAMS=3 ORBGPU_TAPER=4 python tools/e2e_sweep.py
-ORBGPU_CHUNK=24 ORBGPU_STREAMS=4 python tools/e2e_sweep.py
+python -m pytest tests/test_gpu_extract.py -m gpu -x -q 2>&1 | tail -3
+python bench.py --no-matching --no-vocabulary > gpurun_out/b5.json 2> gpurun_out/b5.err; tail -c 300 gpurun_out/b5.err
