@@ -13,7 +13,7 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
-LIB = os.path.join(PKG, "liborbgpu.so")
+LIB = os.environ.get("ORBGPU_LIB") or os.path.join(PKG, "liborbgpu.so")   # ORBGPU_LIB: development builds (tools/dev)
 SOURCES = ["og_capi.cu", "og_match.cu", "og_vocab.cu", "og_multi.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -304,6 +304,7 @@ std::string build_geometry(const orbgpu_extractor& ex, int w, int h, int batch_c
         }
         L.n_cells = ncell;
         L.wcell = wCell;
+        L.wcell_magic = (65536 + wCell - 1) / wCell;
         // segments: runs of consecutive cells of one cell row that fit one 256-byte tile (k_fast_seg)
         {
             int th_max = 0;
@@ -491,7 +492,7 @@ int launch_extract(orbgpu_extractor* ex, const uint8_t* d_images, int batch, siz
             const int nwx = (L.w + 3) / 4, bands = (L.h + og::kResizeRows - 1) / og::kResizeRows, n_items = nwx * bands;
             const uint32_t magic = (uint32_t)((0x100000000ull + nwx - 1) / nwx);
             if (ex->resize_mlp[l])
-                og::k_resize4_mlp<<<dim3((n_items + og::kResizeThreads - 1) / og::kResizeThreads, batch), og::kResizeThreads, 0, st>>>(P, l, nwx, magic, n_items);
+                og::k_resize4_pp<<<dim3((n_items + og::kResizeThreads - 1) / og::kResizeThreads, batch), og::kResizeThreads, 0, st>>>(P, l, nwx, magic, n_items);
             else
                 og::k_resize4<<<dim3((n_items + og::kResizeThreads - 1) / og::kResizeThreads, batch), og::kResizeThreads, 0, st>>>(P, l, nwx, magic, n_items);
         } else {
@@ -562,9 +563,11 @@ int launch_extract(orbgpu_extractor* ex, const uint8_t* d_images, int batch, siz
             const int thr = oct_thr_env ? oct_thr_env : 256;   // measured at 1024 frames (division passes): 128 threads 1.62 ms, 256 1.56 ms, 512 2.19 ms
             const int db = direct_env ? (thr == 512 ? ex->oct_direct_smem_lat : ex->oct_direct_smem) : 0;
             const int kc = thr == 512 ? ex->oct_kcap_lat : ex->oct_kcap;
-            if (thr == 512) og::k_octree<512><<<dim3(P.n_levels, batch), 512, db + sm, st>>>(P, sm, db, kc);
-            else if (thr == 256) og::k_octree<256><<<dim3(P.n_levels, batch), 256, db + sm, st>>>(P, sm, db, kc);
-            else og::k_octree<og::kOctThreads><<<dim3(P.n_levels, batch), og::kOctThreads, db + sm, st>>>(P, sm, db, kc);
+            // ORBGPU_OCT_PAD: unused extra shared memory per CTA (caps the resident octree CTAs so that blur CTAs fit beside them)
+            static const int pad = []() { const char* e = getenv("ORBGPU_OCT_PAD"); return e ? atoi(e) : 0; }();
+            if (thr == 512) og::k_octree<512><<<dim3(P.n_levels, batch), 512, db + sm + pad, st>>>(P, sm, db, kc);
+            else if (thr == 256) og::k_octree<256><<<dim3(P.n_levels, batch), 256, db + sm + pad, st>>>(P, sm, db, kc);
+            else og::k_octree<og::kOctThreads><<<dim3(P.n_levels, batch), og::kOctThreads, db + sm + pad, st>>>(P, sm, db, kc);
         }
     }
     ++launches;

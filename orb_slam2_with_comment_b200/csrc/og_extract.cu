@@ -187,15 +187,20 @@ __global__ void __launch_bounds__(kResizeThreads) k_resize4(const __grid_constan
 
 // The same with all loads up front: the 8 output rows of a thread read at most kResizeSpan consecutive source rows (true for
 // scale <= 1.25, checked on the host per level).  All 3 x kResizeSpan word loads are issued back to back (the row loop above
-// waits for every row's three loads before it can start the next), their horizontal passes are parked in shared memory, and
-// the vertical pass picks its two rows from there.
-// Horizontal pass: the byte pairs of outputs 0,1 lie inside the first two of the three words and those of outputs 2,3 inside
-// two adjacent ones, so ONE byte permute gathers both pairs of two outputs into a word [p(s0) p(s0+1) p(s0') p(s0'+1)] and the
-// low / high DP2A apply the two weight pairs: 2 SEL + 2 PRMT + 4 DP2A per source row instead of 8 SEL + 4 SHF + 4 DP2A.
+// waits for every row's three loads before it can start the next).  The byte pairs of outputs 0,1 lie inside the first two of
+// the three words and those of outputs 2,3 inside two adjacent ones, so ONE byte permute per output pair gathers the source
+// bytes [p(s0) p(s0+1) p(s0') p(s0'+1)]; the two permuted words of every source row (8 bytes) are parked in shared memory (own
+// slots only: no barrier), and the vertical loop picks the two rows an output row blends and runs the horizontal pass on them
+// (low / high DP2A apply the 16-bit weight pairs).  Parking the gathered bytes instead of the four 32-bit horizontal sums halves
+// the shared-memory traffic (88 + 128 bytes per thread instead of 176 + 256) for 16 instead of 11 horizontal passes:
+// 0.99 -> 0.94 ms per 1024 KITTI frames.
 constexpr int kResizeSpan = 11;
-__global__ void __launch_bounds__(kResizeThreads, 8) k_resize4_mlp(const __grid_constant__ ExtractParams P, int level, int nwx, uint32_t nwx_magic,
-                                                                int n_items) {
-    __shared__ uint4 sg[kResizeSpan][kResizeThreads];
+#ifndef OG_RESIZE_MINB
+#define OG_RESIZE_MINB 8
+#endif
+__global__ void __launch_bounds__(kResizeThreads, OG_RESIZE_MINB) k_resize4_pp(const __grid_constant__ ExtractParams P, int level, int nwx, uint32_t nwx_magic,
+                                                               int n_items) {
+    __shared__ uint2 sp[kResizeSpan][kResizeThreads];
     const Level& L = P.lv[level];
     const Level& S = P.lv[level - 1];
     const int frame = P.frame0 + blockIdx.y;
@@ -204,40 +209,38 @@ __global__ void __launch_bounds__(kResizeThreads, 8) k_resize4_mlp(const __grid_
     const int band = (int)__umulhi((uint32_t)id, nwx_magic), wx = id - band * nwx;
     const int x = 4 * wx, y0 = band * kResizeRows;
     const uint4 ta = __ldg(reinterpret_cast<const uint4*>(L.xt + x)), tb = __ldg(reinterpret_cast<const uint4*>(L.xt + x) + 1);
-    const uint32_t tw[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};   // per output: (s0 | s1 << 16), (w0 | w1 << 16)
-    const int base = (int)(tw[0] & 0xffffu) & ~3;
-    const int o0 = (int)(tw[0] & 0xffffu) - base, o1 = (int)(tw[2] & 0xffffu) - base;   // byte offsets of the four pairs: 0..9,
-    int o2 = (int)(tw[4] & 0xffffu) - base, o3 = (int)(tw[6] & 0xffffu) - base;         // consecutive ones at most 2 apart
-    const bool hiB = o2 >= 4;   // outputs 2,3 read words 1,2 (else 0,1)
+    const int s0 = (int)(ta.x & 0xffffu), base = s0 & ~3;
+    const int o0 = s0 - base, o1 = (int)(ta.z & 0xffffu) - base;
+    int o2 = (int)(tb.x & 0xffffu) - base, o3 = (int)(tb.z & 0xffffu) - base;
+    const bool hiB = o2 >= 4;
     if (hiB) { o2 -= 4; o3 -= 4; }
     const uint32_t selA = (uint32_t)(o0 | ((o0 + 1) << 4) | (o1 << 8) | ((o1 + 1) << 12));
     const uint32_t selB = (uint32_t)(o2 | ((o2 + 1) << 4) | (o3 << 8) | ((o3 + 1) << 12));
-    const uint32_t wq0 = tw[1], wq1 = tw[3], wq2 = tw[5], wq3 = tw[7];   // (w0 | w1 << 16): the two 11-bit weights as DP2A's 16-bit pair
+    const uint32_t wq0 = ta.y, wq1 = ta.w, wq2 = tb.y, wq3 = tb.w;
     const int sfirst = L.yt[y0].s0;
     const uint8_t* src = level_ptr(P.pyr, S, frame) + (long long)(kEdge + sfirst) * S.pitch + kXPad + base;
     uint32_t W[kResizeSpan][3];
 #pragma unroll
     for (int k = 0; k < kResizeSpan; ++k) {
-        const int dy = min(k, S.h - 1 - sfirst);   // rows past the image are never selected; keep the address valid
+        const int dy = min(k, S.h - 1 - sfirst);
         const uint32_t* r = reinterpret_cast<const uint32_t*>(src + (long long)dy * S.pitch);
         W[k][0] = __ldg(r); W[k][1] = __ldg(r + 1); W[k][2] = __ldg(r + 2);
     }
 #pragma unroll
-    for (int k = 0; k < kResizeSpan; ++k) {
-        const uint32_t A = __byte_perm(W[k][0], W[k][1], selA);
-        const uint32_t B = __byte_perm(hiB ? W[k][1] : W[k][0], hiB ? W[k][2] : W[k][1], selB);
-        sg[k][threadIdx.x] = make_uint4(__dp2a_lo(wq0, A, 0u) >> 4, __dp2a_hi(wq1, A, 0u) >> 4, __dp2a_lo(wq2, B, 0u) >> 4, __dp2a_hi(wq3, B, 0u) >> 4);
-    }
+    for (int k = 0; k < kResizeSpan; ++k)
+        sp[k][threadIdx.x] = make_uint2(__byte_perm(W[k][0], W[k][1], selA), __byte_perm(hiB ? W[k][1] : W[k][0], hiB ? W[k][2] : W[k][1], selB));
     uint8_t* dst = level_ptr(P.pyr, L, frame) + (long long)kEdge * L.pitch + kXPad + x;
     const int nrows = min(kResizeRows, L.h - y0);
 #pragma unroll 2
     for (int r = 0; r < nrows; ++r) {
         const int y = y0 + r;
         const Tap ty = L.yt[y];
-        const uint4 a = sg[ty.s0 - sfirst][threadIdx.x], b = sg[ty.s1 - sfirst][threadIdx.x];   // own slots only: no barrier needed
+        const uint2 a = sp[ty.s0 - sfirst][threadIdx.x], b = sp[ty.s1 - sfirst][threadIdx.x];   // own slots only: no barrier needed
         const uint32_t b0 = (uint32_t)ty.w0 << 16, b1 = (uint32_t)ty.w1 << 16;
-        const uint32_t q0 = (__umulhi(b0, a.x) + __umulhi(b1, b.x) + 2u) >> 2, q1 = (__umulhi(b0, a.y) + __umulhi(b1, b.y) + 2u) >> 2;
-        const uint32_t q2 = (__umulhi(b0, a.z) + __umulhi(b1, b.z) + 2u) >> 2, q3 = (__umulhi(b0, a.w) + __umulhi(b1, b.w) + 2u) >> 2;
+        const uint32_t q0 = (__umulhi(b0, __dp2a_lo(wq0, a.x, 0u) >> 4) + __umulhi(b1, __dp2a_lo(wq0, b.x, 0u) >> 4) + 2u) >> 2;
+        const uint32_t q1 = (__umulhi(b0, __dp2a_hi(wq1, a.x, 0u) >> 4) + __umulhi(b1, __dp2a_hi(wq1, b.x, 0u) >> 4) + 2u) >> 2;
+        const uint32_t q2 = (__umulhi(b0, __dp2a_lo(wq2, a.y, 0u) >> 4) + __umulhi(b1, __dp2a_lo(wq2, b.y, 0u) >> 4) + 2u) >> 2;
+        const uint32_t q3 = (__umulhi(b0, __dp2a_hi(wq3, a.y, 0u) >> 4) + __umulhi(b1, __dp2a_hi(wq3, b.y, 0u) >> 4) + 2u) >> 2;
         *reinterpret_cast<uint32_t*>(dst + (long long)y * L.pitch) = q0 | (q1 << 8) | (q2 << 16) | (q3 << 24);
     }
 }
@@ -525,7 +528,7 @@ __global__ void __launch_bounds__(kSegThreads, 5) k_fast_seg(const __grid_consta
         for (int i = t; i < nz; i += kSegThreads) z[i] = make_uint4(0, 0, 0, 0);
         const int wc = L.wcell;
         for (int px = t; px < 256; px += kSegThreads) {
-            const int j = px / wc, lo = j * wc, hi = min(lo + wc, tw) - 1;
+            const int j = (px * L.wcell_magic) >> 16, lo = j * wc, hi = min(lo + wc, tw) - 1;
             lut[px] = (uint8_t)((px == lo ? 1 : 0) | (px == hi ? 2 : 0));
         }
     }
@@ -708,7 +711,7 @@ __global__ void __launch_bounds__(kSegThreads, 5) k_fast_seg(const __grid_consta
         // ---- prepare pass 1: column mask of the needy cells, empty queue (the tile is still intact) ---------------------
         {
             const int px = t - ox;
-            const bool on = px >= 0 && px < tw && need[px / wcell];
+            const bool on = px >= 0 && px < tw && need[(px * L.wcell_magic) >> 16];
             const unsigned bal = __ballot_sync(0xffffffffu, on);
             if (lane == 0) colmask[wi] = bal;
             if (t == 0) qn = 0;
@@ -914,7 +917,12 @@ __global__ void __launch_bounds__(kBlurThreads) k_blur_tma(const __grid_constant
 //   coalesced word loads; lane i produces descriptor byte i from pattern points 16i .. 16i+15.  cos/sin of the float
 //   angle are evaluated in double and rounded to float.
 // ------------------------------------------------------------------------------------------------------------
-constexpr int kDescWarps = 6, kDescPerWarp = 16;   // measured on B200 (device / host-path k frames/s): 8x4 96.3 / 82.2, 4x16 96.9 / 86.9, 6x16 97.8 / 87.1
+#ifndef OG_DESC_WARPS
+#define OG_DESC_WARPS 6
+#define OG_DESC_PER_WARP 16
+#define OG_DESC_MINB 6
+#endif
+constexpr int kDescWarps = OG_DESC_WARPS, kDescPerWarp = OG_DESC_PER_WARP;   // measured on B200 (device / host-path k frames/s): 8x4 96.3 / 82.2, 4x16 96.9 / 86.9, 6x16 97.8 / 87.1
 constexpr int kIcWords = 9, kIcRows = 31;           // table [4 alignments][31 rows][9 words][2]
 constexpr int kIcBoxW = 48, kBlurBoxW = 64, kPatchRows = 37;   // TMA boxes: 48 x 31 of the level, 64 x 37 of its blur
 constexpr int kIcSlot = 1536, kBlurSlot = 2432;     // box bytes rounded up to the 128 B a TMA destination wants
@@ -937,7 +945,7 @@ __device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c) {   // uns
 //   1. moments: the discs stream through two buffers, all lanes sum one disc, lane n keeps m10 / m01 of key point n;
 //   2. lane n: fastAtan2, cos / sin, the cv::KeyPoint record;
 //   3. descriptors: the blurred windows stream through the same two buffers, cos / sin of key point n come by shuffle.
-__global__ void __launch_bounds__(kDescWarps * 32, 6) k_orient_desc(const __grid_constant__ ExtractParams P, const CUtensorMap* __restrict__ tmaps,
+__global__ void __launch_bounds__(kDescWarps * 32, OG_DESC_MINB) k_orient_desc(const __grid_constant__ ExtractParams P, const CUtensorMap* __restrict__ tmaps,
                                                                     KeyPoint* __restrict__ kp_out, uint8_t* __restrict__ desc_out,
                                                                     int32_t* __restrict__ counts) {
     static_assert(kDescPerWarp <= 32 && 2 * kIcSlot <= 2 * kBlurSlot, "one lane per key point; the disc buffers fit into the window buffers");

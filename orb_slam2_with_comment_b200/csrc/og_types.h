@@ -42,6 +42,7 @@ struct Level {
     float kp_size;           // (float)(int)(31 * scale) (:837)
     long long ot_base;       // byte offset of this level's octree workspace inside a frame's workspace
     int wcell, hbox;         // cell pitch in x (:785); rows of the FAST tile box (tallest cell + 6)
+    int wcell_magic, pad_;   // ceil(2^16 / wcell): px / wcell = (px * wcell_magic) >> 16 for px < 256
 };
 
 // One FAST cell (:789-806): the reference runs cv::FAST on the sub-image [ini, max) and FAST itself never tests
