@@ -218,30 +218,37 @@ __global__ void __launch_bounds__(kResizeThreads, OG_RESIZE_MINB) k_resize4_pp(c
     const uint32_t selB = (uint32_t)(o2 | ((o2 + 1) << 4) | (o3 << 8) | ((o3 + 1) << 12));
     const uint32_t wq0 = ta.y, wq1 = ta.w, wq2 = tb.y, wq3 = tb.w;
     const int sfirst = L.yt[y0].s0;
-    const uint8_t* src = level_ptr(P.pyr, S, frame) + (long long)(kEdge + sfirst) * S.pitch + kXPad + base;
+    // 32-bit byte offsets from the CTA-uniform level base (a level image is far below 4 GB): one integer add per address
+    const uint8_t* sbase = level_ptr(P.pyr, S, frame);
+    const uint32_t soff = (uint32_t)(kEdge + sfirst) * (uint32_t)S.pitch + (uint32_t)(kXPad + base);
+    // Rows sfirst + k past the level's last row (k <= 10, bottom band only) are never selected by the taps; their addresses lie in
+    // the level's own bottom frame rows (kEdge = 19 of them), so no clamp is needed: the row address is one IMAD.WIDE.
+    static_assert(kResizeSpan - 1 <= kEdge, "unclamped source rows stay inside the level's frame rows");
+    const uint32_t spitch = (uint32_t)S.pitch;
     uint32_t W[kResizeSpan][3];
 #pragma unroll
     for (int k = 0; k < kResizeSpan; ++k) {
-        const int dy = min(k, S.h - 1 - sfirst);
-        const uint32_t* r = reinterpret_cast<const uint32_t*>(src + (long long)dy * S.pitch);
+        const uint32_t* r = reinterpret_cast<const uint32_t*>(sbase + (soff + spitch * (uint32_t)k));
         W[k][0] = __ldg(r); W[k][1] = __ldg(r + 1); W[k][2] = __ldg(r + 2);
     }
 #pragma unroll
     for (int k = 0; k < kResizeSpan; ++k)
         sp[k][threadIdx.x] = make_uint2(__byte_perm(W[k][0], W[k][1], selA), __byte_perm(hiB ? W[k][1] : W[k][0], hiB ? W[k][2] : W[k][1], selB));
-    uint8_t* dst = level_ptr(P.pyr, L, frame) + (long long)kEdge * L.pitch + kXPad + x;
+    uint8_t* dbase = level_ptr(P.pyr, L, frame);
+    const uint32_t dpitch = (uint32_t)L.pitch;
+    uint32_t doff = (uint32_t)(kEdge + y0) * dpitch + (uint32_t)(kXPad + x);
     const int nrows = min(kResizeRows, L.h - y0);
+    const Tap* ytp = L.yt + y0;
 #pragma unroll 2
-    for (int r = 0; r < nrows; ++r) {
-        const int y = y0 + r;
-        const Tap ty = L.yt[y];
+    for (int r = 0; r < nrows; ++r, doff += dpitch) {
+        const Tap ty = ytp[r];
         const uint2 a = sp[ty.s0 - sfirst][threadIdx.x], b = sp[ty.s1 - sfirst][threadIdx.x];   // own slots only: no barrier needed
         const uint32_t b0 = (uint32_t)ty.w0 << 16, b1 = (uint32_t)ty.w1 << 16;
         const uint32_t q0 = (__umulhi(b0, __dp2a_lo(wq0, a.x, 0u) >> 4) + __umulhi(b1, __dp2a_lo(wq0, b.x, 0u) >> 4) + 2u) >> 2;
         const uint32_t q1 = (__umulhi(b0, __dp2a_hi(wq1, a.x, 0u) >> 4) + __umulhi(b1, __dp2a_hi(wq1, b.x, 0u) >> 4) + 2u) >> 2;
         const uint32_t q2 = (__umulhi(b0, __dp2a_lo(wq2, a.y, 0u) >> 4) + __umulhi(b1, __dp2a_lo(wq2, b.y, 0u) >> 4) + 2u) >> 2;
         const uint32_t q3 = (__umulhi(b0, __dp2a_hi(wq3, a.y, 0u) >> 4) + __umulhi(b1, __dp2a_hi(wq3, b.y, 0u) >> 4) + 2u) >> 2;
-        *reinterpret_cast<uint32_t*>(dst + (long long)y * L.pitch) = q0 | (q1 << 8) | (q2 << 16) | (q3 << 24);
+        *reinterpret_cast<uint32_t*>(dbase + doff) = q0 | (q1 << 8) | (q2 << 16) | (q3 << 24);
     }
 }
 
@@ -684,9 +691,12 @@ __global__ void __launch_bounds__(kSegThreads, 5) k_fast_seg(const __grid_consta
             const int v = s[0];
             const int fl = lut[px];
             // in pass 0 the score map only holds V >= iniTh; in pass 1 a cell's map holds everything >= minTh
-            bool k = v > s[-kSegPitch] && v > s[kSegPitch];
-            if (!(fl & 1)) k = k && v > s[-1] && v > s[-kSegPitch - 1] && v > s[kSegPitch - 1];
-            if (!(fl & 2)) k = k && v > s[1] && v > s[-kSegPitch + 1] && v > s[kSegPitch + 1];
+            // all eight neighbours are loaded up front (the map has a zero margin all round); a cell's first / last column ignores the
+            // neighbours that belong to the next cell
+            const int n0 = s[-kSegPitch], n1 = s[kSegPitch], l0 = s[-1], l1 = s[-kSegPitch - 1], l2 = s[kSegPitch - 1];
+            const int r0 = s[1], r1 = s[-kSegPitch + 1], r2 = s[kSegPitch + 1];
+            const bool kl = (fl & 1) | ((v > l0) & (v > l1) & (v > l2)), kr = ((fl >> 1) & 1) | ((v > r0) & (v > r1) & (v > r2));
+            const bool k = (v > n0) & (v > n1) & kl & kr;
             if (k) {
                 // plain shared-memory reduction (atomicOr makes ptxas build a warp-aggregation loop that costs more than it saves)
                 asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(smem_u32(&bm_out[r * kBmWords + (px >> 5)])), "r"(1u << (px & 31)) : "memory");
@@ -815,7 +825,12 @@ struct BlurTile {
     int16_t level, tx, ty, pad;
 };
 
-__global__ void __launch_bounds__(kBlurThreads) k_blur_tma(const __grid_constant__ ExtractParams P, const BlurTile* __restrict__ tiles,
+#ifdef OG_BLUR_LB
+__global__ void __launch_bounds__(kBlurThreads) k_blur_tma(
+#else
+__global__ void __maxnreg__(48) k_blur_tma(   // 6 CTAs of 224 threads per SM (the two copies of the row loop would take 56)
+#endif
+    const __grid_constant__ ExtractParams P, const BlurTile* __restrict__ tiles,
                                                            const CUtensorMap* __restrict__ tmaps) {
     __shared__ __align__(1024) uint8_t tile[kBlurBox * 256];
     __shared__ uint64_t mbar;
@@ -864,47 +879,55 @@ __global__ void __launch_bounds__(kBlurThreads) k_blur_tma(const __grid_constant
     if (x >= L.w || ybase >= L.h) return;
     const uint32_t* T = reinterpret_cast<const uint32_t*>(tile) + (32 * band) * 64 + 4 + c;
     const uint32_t KLO = OG_G0 | (OG_G1 << 8) | (OG_G2 << 16) | (OG_G3 << 24), KHI = OG_G2 | (OG_G1 << 8) | (OG_G0 << 16);
-    uint8_t* dst = level_ptr(P.blur, L, frame) + (long long)(kEdge + ybase) * L.pitch + kXPad + x;
+    const size_t dpitch = (size_t)L.pitch;   // widened once: the row pointer advances by one 64-bit add per row
+    uint8_t* dst = level_ptr(P.blur, L, frame) + (size_t)(kEdge + ybase) * dpitch + (size_t)(kXPad + x);
     const int nrows = min(32, L.h - ybase);
     // Vertical pass on row PAIRS: a horizontal sum is at most 255 * 256 < 2^16, so two vertically adjacent sums share a word
-    // (pr[k] = row k | row k+1 << 16) and one DP2A applies two taps: 3 DP2A + 1 IMAD per pixel instead of 7 multiply-adds.
-    uint32_t pr[6][4], hprev[4] = {0u, 0u, 0u, 0u};
-    const uint32_t K01 = OG_G0 | (OG_G1 << 8), K23 = OG_G2 | (OG_G3 << 8), K21 = OG_G2 | (OG_G1 << 8);
+    // (pr[k] = row k | row k+1 << 16, one PRMT) and one DP2A applies two taps: 3 DP2A + 1 IMAD per pixel instead of 7 multiply-adds.
+    // Tiles with all 32 rows (all but a level's bottom tile row) run the copy of the loop without the per-row checks.
+    auto rows = [&](auto full_c) {
+        constexpr bool full = decltype(full_c)::value;
+        uint8_t* drow = dst;
+        uint32_t pr[6][4], hprev[4] = {0u, 0u, 0u, 0u};
+        const uint32_t K01 = OG_G0 | (OG_G1 << 8), K23 = OG_G2 | (OG_G3 << 8), K21 = OG_G2 | (OG_G1 << 8);
 #pragma unroll
-    for (int i = 0; i < 38; ++i) {
-        if (i >= nrows + 6) break;   // bottom tiles: nothing below the level's last row is needed
-        // horizontal pass of tile row 32*band + i
-        const uint32_t pw = T[i * 64 - 1], cw = T[i * 64], nw = T[i * 64 + 1];
-        const uint32_t m3 = __funnelshift_r(pw, cw, 8), m2 = __funnelshift_r(pw, cw, 16), m1 = __funnelshift_r(pw, cw, 24);
-        const uint32_t p1 = __funnelshift_r(cw, nw, 8), p2 = __funnelshift_r(cw, nw, 16), p3 = __funnelshift_r(cw, nw, 24);
-        uint32_t h[4];
-        h[0] = __dp4a(m3, KLO, __dp4a(p1, KHI, 0u));
-        h[1] = __dp4a(m2, KLO, __dp4a(p2, KHI, 0u));
-        h[2] = __dp4a(m1, KLO, __dp4a(p3, KHI, 0u));
-        h[3] = __dp4a(cw, KLO, __dp4a(nw, KHI, 0u));
-        if (i >= 1) {
+        for (int i = 0; i < 38; ++i) {
+            if (!full && i >= nrows + 6) break;   // bottom tiles: nothing below the level's last row is needed
+            // horizontal pass of tile row 32*band + i
+            const uint32_t pw = T[i * 64 - 1], cw = T[i * 64], nw = T[i * 64 + 1];
+            const uint32_t m3 = __funnelshift_r(pw, cw, 8), m2 = __funnelshift_r(pw, cw, 16), m1 = __funnelshift_r(pw, cw, 24);
+            const uint32_t p1 = __funnelshift_r(cw, nw, 8), p2 = __funnelshift_r(cw, nw, 16), p3 = __funnelshift_r(cw, nw, 24);
+            uint32_t h[4];
+            h[0] = __dp4a(m3, KLO, __dp4a(p1, KHI, 0u));
+            h[1] = __dp4a(m2, KLO, __dp4a(p2, KHI, 0u));
+            h[2] = __dp4a(m1, KLO, __dp4a(p3, KHI, 0u));
+            h[3] = __dp4a(cw, KLO, __dp4a(nw, KHI, 0u));
+            if (i >= 1) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) pr[(i - 1) % 6][j] = hprev[j] | (h[j] << 16);   // rows i-1, i
-        }
-        if (i >= 6) {
-            const int r = i - 6;   // output row of the band: window rows r..r+6 = pairs r, r+2, r+4 and row r+6 (= h)
-            if (r < nrows) {
-                uint32_t o[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    uint32_t acc = OG_G0 * h[j] + 32768u;
-                    acc = __dp2a_lo(pr[r % 6][j], K01, acc);
-                    acc = __dp2a_lo(pr[(r + 2) % 6][j], K23, acc);
-                    acc = __dp2a_lo(pr[(r + 4) % 6][j], K21, acc);
-                    o[j] = acc;   // result byte = bits 16..23
-                }
-                const uint32_t lo = __byte_perm(o[0], o[1], 0x0062), hi = __byte_perm(o[2], o[3], 0x0062);
-                *reinterpret_cast<uint32_t*>(dst + (long long)r * L.pitch) = __byte_perm(lo, hi, 0x5410);
+                for (int j = 0; j < 4; ++j) pr[(i - 1) % 6][j] = __byte_perm(hprev[j], h[j], 0x5410);   // rows i-1, i
             }
-        }
+            if (i >= 6) {
+                const int r = i - 6;   // output row of the band: window rows r..r+6 = pairs r, r+2, r+4 and row r+6 (= h)
+                if (full || r < nrows) {
+                    uint32_t o[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) hprev[j] = h[j];
-    }
+                    for (int j = 0; j < 4; ++j) {
+                        uint32_t acc = OG_G0 * h[j] + 32768u;
+                        acc = __dp2a_lo(pr[r % 6][j], K01, acc);
+                        acc = __dp2a_lo(pr[(r + 2) % 6][j], K23, acc);
+                        acc = __dp2a_lo(pr[(r + 4) % 6][j], K21, acc);
+                        o[j] = acc;   // result byte = bits 16..23
+                    }
+                    const uint32_t lo = __byte_perm(o[0], o[1], 0x0062), hi = __byte_perm(o[2], o[3], 0x0062);
+                    *reinterpret_cast<uint32_t*>(drow) = __byte_perm(lo, hi, 0x5410);
+                    drow += dpitch;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) hprev[j] = h[j];
+        }
+    };
+    if (nrows == 32) rows(std::true_type{}); else rows(std::false_type{});
 }
 
 // ------------------------------------------------------------------------------------------------------------
