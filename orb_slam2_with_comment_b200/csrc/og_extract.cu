@@ -748,7 +748,7 @@ __global__ void __launch_bounds__(kSegThreads, 5) k_fast_seg(const __grid_consta
                 mi = __funnelshift_r(b[0], b[1], sh) & wmask;
             }
             if (__any_sync(0xffffffffu, mi != 0)) mm = mi;
-            const int c0 = __popc(mm);
+            const int c0 = __popc(mm);   // 3x3 maxima: at most 16 in a 32-pixel row
             int i0 = c0;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
@@ -815,7 +815,7 @@ __global__ void __launch_bounds__(kSegThreads, 5) k_fast_seg(const __grid_consta
 // border logic.  One CTA = 224 x 128 outputs of one (level, frame); the 256 x 134 input tile arrives by
 // TMA (16-byte aligned origin: 16 spare columns on each side).  A thread owns one 32-bit word (4 columns) and walks
 // down 32 rows: the horizontal pass is two DP4A per pixel on byte windows cut with funnel shifts, the vertical pass
-// runs on a 7-row register window (fully unrolled, so the window rotates by renaming).
+// runs on a register window of row pairs (period 6: the row loop is rolled in steps of 6, so the window rotates by renaming).
 // ------------------------------------------------------------------------------------------------------------
 // kBlurBands bands of 32 rows, kBlurW / 4 = 56 threads each: 224 threads = 7 full warps (with 64 threads per band an eighth of the
 // lanes had no column to work on)
@@ -825,11 +825,8 @@ struct BlurTile {
     int16_t level, tx, ty, pad;
 };
 
-#ifdef OG_BLUR_LB
+// no register cap: 53 registers = 4 CTAs per SM measured faster (0.80 ms per 1024 frames) than 48 (5 CTAs, 0.82) or 40 (6 CTAs, 0.90)
 __global__ void __launch_bounds__(kBlurThreads) k_blur_tma(
-#else
-__global__ void __maxnreg__(48) k_blur_tma(   // 6 CTAs of 224 threads per SM (the two copies of the row loop would take 56)
-#endif
     const __grid_constant__ ExtractParams P, const BlurTile* __restrict__ tiles,
                                                            const CUtensorMap* __restrict__ tmaps) {
     __shared__ __align__(1024) uint8_t tile[kBlurBox * 256];
@@ -884,50 +881,70 @@ __global__ void __maxnreg__(48) k_blur_tma(   // 6 CTAs of 224 threads per SM (t
     const int nrows = min(32, L.h - ybase);
     // Vertical pass on row PAIRS: a horizontal sum is at most 255 * 256 < 2^16, so two vertically adjacent sums share a word
     // (pr[k] = row k | row k+1 << 16, one PRMT) and one DP2A applies two taps: 3 DP2A + 1 IMAD per pixel instead of 7 multiply-adds.
-    // Tiles with all 32 rows (all but a level's bottom tile row) run the copy of the loop without the per-row checks.
-    auto rows = [&](auto full_c) {
-        constexpr bool full = decltype(full_c)::value;
-        uint8_t* drow = dst;
-        uint32_t pr[6][4], hprev[4] = {0u, 0u, 0u, 0u};
-        const uint32_t K01 = OG_G0 | (OG_G1 << 8), K23 = OG_G2 | (OG_G3 << 8), K21 = OG_G2 | (OG_G1 << 8);
-#pragma unroll
-        for (int i = 0; i < 38; ++i) {
-            if (!full && i >= nrows + 6) break;   // bottom tiles: nothing below the level's last row is needed
-            // horizontal pass of tile row 32*band + i
-            const uint32_t pw = T[i * 64 - 1], cw = T[i * 64], nw = T[i * 64 + 1];
-            const uint32_t m3 = __funnelshift_r(pw, cw, 8), m2 = __funnelshift_r(pw, cw, 16), m1 = __funnelshift_r(pw, cw, 24);
-            const uint32_t p1 = __funnelshift_r(cw, nw, 8), p2 = __funnelshift_r(cw, nw, 16), p3 = __funnelshift_r(cw, nw, 24);
-            uint32_t h[4];
-            h[0] = __dp4a(m3, KLO, __dp4a(p1, KHI, 0u));
-            h[1] = __dp4a(m2, KLO, __dp4a(p2, KHI, 0u));
-            h[2] = __dp4a(m1, KLO, __dp4a(p3, KHI, 0u));
-            h[3] = __dp4a(cw, KLO, __dp4a(nw, KHI, 0u));
-            if (i >= 1) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) pr[(i - 1) % 6][j] = __byte_perm(hprev[j], h[j], 0x5410);   // rows i-1, i
-            }
-            if (i >= 6) {
-                const int r = i - 6;   // output row of the band: window rows r..r+6 = pairs r, r+2, r+4 and row r+6 (= h)
-                if (full || r < nrows) {
-                    uint32_t o[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        uint32_t acc = OG_G0 * h[j] + 32768u;
-                        acc = __dp2a_lo(pr[r % 6][j], K01, acc);
-                        acc = __dp2a_lo(pr[(r + 2) % 6][j], K23, acc);
-                        acc = __dp2a_lo(pr[(r + 4) % 6][j], K21, acc);
-                        o[j] = acc;   // result byte = bits 16..23
-                    }
-                    const uint32_t lo = __byte_perm(o[0], o[1], 0x0062), hi = __byte_perm(o[2], o[3], 0x0062);
-                    *reinterpret_cast<uint32_t*>(drow) = __byte_perm(lo, hi, 0x5410);
-                    drow += dpitch;
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) hprev[j] = h[j];
-        }
+    // The pair window has period 6, so the row loop is rolled in steps of 6 rows (window slots stay compile-time): the fully
+    // unrolled 38 rows were 37 KB of straight-line code that every warp ran through once, and instruction fetch was the kernel's
+    // first stall reason (ncu: no_instruction 3.0 warps per issue).
+    uint8_t* drow = dst;
+    uint32_t pr[6][4], hprev[4] = {0u, 0u, 0u, 0u};
+    const uint32_t K01 = OG_G0 | (OG_G1 << 8), K23 = OG_G2 | (OG_G3 << 8), K21 = OG_G2 | (OG_G1 << 8);
+    auto hpass = [&](const uint32_t* R, uint32_t (&h)[4]) {   // horizontal pass of one box row
+        const uint32_t pw = R[-1], cw = R[0], nw = R[1];
+        const uint32_t m3 = __funnelshift_r(pw, cw, 8), m2 = __funnelshift_r(pw, cw, 16), m1 = __funnelshift_r(pw, cw, 24);
+        const uint32_t p1 = __funnelshift_r(cw, nw, 8), p2 = __funnelshift_r(cw, nw, 16), p3 = __funnelshift_r(cw, nw, 24);
+        h[0] = __dp4a(m3, KLO, __dp4a(p1, KHI, 0u));
+        h[1] = __dp4a(m2, KLO, __dp4a(p2, KHI, 0u));
+        h[2] = __dp4a(m1, KLO, __dp4a(p3, KHI, 0u));
+        h[3] = __dp4a(cw, KLO, __dp4a(nw, KHI, 0u));
     };
-    if (nrows == 32) rows(std::true_type{}); else rows(std::false_type{});
+    // box rows 0..5: fill the window (pairs 0..4)
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        uint32_t h[4];
+        hpass(T + i * 64, h);
+        if (i >= 1) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) pr[i - 1][j] = __byte_perm(hprev[j], h[j], 0x5410);   // rows i-1, i
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) hprev[j] = h[j];
+    }
+    // box rows 6 + 6 g + k produce output rows r = 6 g + k: window rows r..r+6 = pairs r, r+2, r+4 (slots k, k+2, k+4 mod 6) and row r+6
+    const uint32_t* R = T + 6 * 64;
+    auto row = [&](auto k_c) {   // box row R -> output row 6 g + k
+        constexpr int k = decltype(k_c)::value;
+        uint32_t h[4];
+        hpass(R, h);
+        R += 64;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pr[(k + 5) % 6][j] = __byte_perm(hprev[j], h[j], 0x5410);   // rows r+5, r+6
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint32_t acc = OG_G0 * h[j] + 32768u;
+            acc = __dp2a_lo(pr[k][j], K01, acc);
+            acc = __dp2a_lo(pr[(k + 2) % 6][j], K23, acc);
+            acc = __dp2a_lo(pr[(k + 4) % 6][j], K21, acc);
+            o[j] = acc;   // result byte = bits 16..23
+        }
+        const uint32_t lo = __byte_perm(o[0], o[1], 0x0062), hi = __byte_perm(o[2], o[3], 0x0062);
+        *reinterpret_cast<uint32_t*>(drow) = __byte_perm(lo, hi, 0x5410);
+        drow += dpitch;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) hprev[j] = h[j];
+    };
+    int r0 = 0;
+#pragma unroll 1
+    for (; r0 + 6 <= nrows; r0 += 6) {   // whole groups: no per-row checks
+        row(std::integral_constant<int, 0>{}); row(std::integral_constant<int, 1>{}); row(std::integral_constant<int, 2>{});
+        row(std::integral_constant<int, 3>{}); row(std::integral_constant<int, 4>{}); row(std::integral_constant<int, 5>{});
+    }
+    // the last 32 - 30 = 2 rows of a full band, or what a bottom tile has left before the level's last row
+    const int left = nrows - r0;
+    if (left > 0) row(std::integral_constant<int, 0>{});
+    if (left > 1) row(std::integral_constant<int, 1>{});
+    if (left > 2) row(std::integral_constant<int, 2>{});
+    if (left > 3) row(std::integral_constant<int, 3>{});
+    if (left > 4) row(std::integral_constant<int, 4>{});
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -999,6 +1016,7 @@ __global__ void __launch_bounds__(kDescWarps * 32, OG_DESC_MINB) k_orient_desc(c
     const int my_idx = (blockIdx.x * kDescPerWarp + lane) * kDescWarps + wi;   // index among the frame's keypoints
     const bool mine = lane < kDescPerWarp && my_idx < total;
     int my_level = 0, my_cx = 0, my_cy = 0, my_resp = 0;
+    uint32_t my_xy = 0;   // my_cy << 16 | my_cx: one shuffle hands both to the warp
     if (mine) {
         int first = 0;
 #pragma unroll
@@ -1010,6 +1028,7 @@ __global__ void __launch_bounds__(kDescWarps * 32, OG_DESC_MINB) k_orient_desc(c
         my_resp = P.sel_resp[o];
         my_cx = (int)(xy & 0xffffu) + 16;   // level coordinates (:840-841)
         my_cy = (int)(xy >> 16) + 16;
+        my_xy = ((uint32_t)my_cy << 16) | (uint32_t)my_cx;
     }
     const int nk = __popc(__ballot_sync(full, mine));   // the warp's key points are lanes 0 .. nk-1
     if (nk == 0) return;
@@ -1018,19 +1037,23 @@ __global__ void __launch_bounds__(kDescWarps * 32, OG_DESC_MINB) k_orient_desc(c
 
     // ---- 1. IC_Angle moments (:77-104) ------------------------------------------------------------------------------------------
     const int ic_r = lane / kIcWords, ic_j = lane - ic_r * kIcWords;     // lanes 0..26: 3 disc rows x 9 words per step
+    // issue_*(n) returns key point n's packed position, which the loop keeps for iteration n (one position shuffle per key point)
     auto issue_ic = [&](int n) {
-        const int lv = __shfl_sync(full, my_level, n), cx = __shfl_sync(full, my_cx, n), cy = __shfl_sync(full, my_cy, n);
+        const uint32_t xy = __shfl_sync(full, my_xy, n);
+        const int lv = __shfl_sync(full, my_level, n), cx = (int)(xy & 0xffffu), cy = (int)(xy >> 16);
         if (lane == 0) {
             uint64_t* bar = &bars[wi][n & 1];
             mbar_expect_tx(bar, kIcBoxW * kIcRows);
             tma_load_3d(buf0 + (n & 1) * kIcSlot, tmaps + 2 * kMaxLevels + lv, (kXPad + cx - kHalfPatch) & ~15, kEdge + cy - kHalfPatch, frame, bar);
         }
+        return xy;
     };
     int my_m10 = 0, my_m01 = 0;
-    issue_ic(0);
+    uint32_t xy_next = issue_ic(0);
     for (int n = 0; n < nk; ++n) {
-        if (n + 1 < nk) issue_ic(n + 1);   // its buffer was read two iterations ago (the __syncwarp below)
-        const int icx = kXPad + __shfl_sync(full, my_cx, n) - kHalfPatch;   // first column of the disc
+        const uint32_t xy_cur = xy_next;
+        if (n + 1 < nk) xy_next = issue_ic(n + 1);   // its buffer was read two iterations ago (the __syncwarp below)
+        const int icx = kXPad + (int)(xy_cur & 0xffffu) - kHalfPatch;   // first column of the disc
         int m10 = 0, m01 = 0;
         if (n & 1) { mbar_wait(&bars[wi][1], use1 & 1); ++use1; } else { mbar_wait(&bars[wi][0], use0 & 1); ++use0; }
         {
@@ -1050,11 +1073,9 @@ __global__ void __launch_bounds__(kDescWarps * 32, OG_DESC_MINB) k_orient_desc(c
                 }
             }
         }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            m10 += __shfl_xor_sync(full, m10, d);
-            m01 += __shfl_xor_sync(full, m01, d);
-        }
+        // warp sums in one instruction each (REDUX) instead of five shuffle + add steps
+        m10 = __reduce_add_sync(full, m10);
+        m01 = __reduce_add_sync(full, m01);
         if (lane == n) { my_m10 = m10; my_m01 = m01; }
         __syncwarp();   // every lane is done with this buffer
     }
@@ -1079,18 +1100,21 @@ __global__ void __launch_bounds__(kDescWarps * 32, OG_DESC_MINB) k_orient_desc(c
 
     // ---- 3. rotated BRIEF on the blurred windows (:108-147) ----------------------------------------------------------------------------------
     auto issue_bl = [&](int n) {
-        const int lv = __shfl_sync(full, my_level, n), cx = __shfl_sync(full, my_cx, n), cy = __shfl_sync(full, my_cy, n);
+        const uint32_t xy = __shfl_sync(full, my_xy, n);
+        const int lv = __shfl_sync(full, my_level, n), cx = (int)(xy & 0xffffu), cy = (int)(xy >> 16);
         if (lane == 0) {
             uint64_t* bar = &bars[wi][n & 1];
             mbar_expect_tx(bar, kBlurBoxW * kPatchRows);
             tma_load_3d(buf0 + (n & 1) * kBlurSlot, tmaps + 3 * kMaxLevels + lv, (kXPad + cx - 18) & ~15, kEdge + cy - 18, frame, bar);
         }
+        return xy;
     };
-    issue_bl(0);
+    xy_next = issue_bl(0);
     for (int n = 0; n < nk; ++n) {
-        if (n + 1 < nk) issue_bl(n + 1);
+        const uint32_t xy_cur = xy_next;
+        if (n + 1 < nk) xy_next = issue_bl(n + 1);
         const float a = __shfl_sync(full, my_a, n), b = __shfl_sync(full, my_b, n);
-        const int blx = kXPad + __shfl_sync(full, my_cx, n) - 18;   // first column of the 37-wide window
+        const int blx = kXPad + (int)(xy_cur & 0xffffu) - 18;   // first column of the 37-wide window
         if (n & 1) { mbar_wait(&bars[wi][1], use1 & 1); ++use1; } else { mbar_wait(&bars[wi][0], use0 & 1); ++use0; }
         const uint8_t* b0 = buf0 + (n & 1) * kBlurSlot + 18 * kBlurBoxW + 18 + (blx & 15);
         int val = 0;
