@@ -1,6 +1,7 @@
 // og_capi.cu — the extern "C" layer of liborbgpu.so (include/orbgpu.h): extractor handle, workspace layout in
 // HBM, launch sequence.  Host-side geometry follows the reference constructor and ComputePyramid /
 // ComputeKeyPointsOctTree line by line (cited inline); no pixel is ever touched on the host.
+#include "og_nvtx.h"
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <atomic>
@@ -73,11 +74,12 @@ struct orbgpu_extractor {
     size_t color_cap = 0;
     og::Cell* d_cells = nullptr;
     og::Segment* d_segs = nullptr;
+    bool resize_tma[og::kMaxLevels] = {};   // per level: every 192 x 32 output tile reads at most a 256 x 42 source box (k_resize_tma)
     bool resize_mlp[og::kMaxLevels] = {};   // per level: every band of 8 output rows reads <= kResizeSpan source rows
     og::BlurTile* d_btiles = nullptr;
     uint32_t* d_ic_tab = nullptr;
     int n_btiles = 0;
-    CUtensorMap* d_tmaps = nullptr;   // [4][kMaxLevels]: FAST tile boxes, blur input boxes, IC_Angle boxes (all over pyr), descriptor boxes over blur
+    CUtensorMap* d_tmaps = nullptr;   // [5][kMaxLevels]: FAST tile boxes, blur input boxes, IC_Angle boxes (all over pyr), descriptor boxes over blur, resize source boxes over pyr
     int fast_smem = 0;
     bool frame_pending = false;   // the levels of the last call have no reflect-101 frame yet (written on demand)
     bool eager_frame = false;     // orbgpu_extractor_set_eager_frame: write the frame with every call, like the reference
@@ -384,7 +386,7 @@ int ensure_geometry(orbgpu_extractor* ex, int w, int h) {
     OG_CUDA(cudaMemcpyAsync(ex->d_btiles, G.btiles.data(), G.btiles.size() * sizeof(og::BlurTile), cudaMemcpyHostToDevice, ex->stream));
     ex->n_btiles = (int)G.btiles.size();
     {
-        std::vector<CUtensorMap> maps(4 * og::kMaxLevels);
+        std::vector<CUtensorMap> maps(5 * og::kMaxLevels);
         memset(maps.data(), 0, maps.size() * sizeof(CUtensorMap));
         int smem = 0;
         for (int l = 0; l < ex->nlevels; ++l) {
@@ -398,6 +400,8 @@ int ensure_geometry(orbgpu_extractor* ex, int w, int h) {
             if (e.empty())
                 e = make_level_tmap(&maps[3 * og::kMaxLevels + l], ex->d_blur + L.base, L.pitch, L.rows, L.frame_stride, ex->max_batch, og::kBlurBoxW,
                                     og::kPatchRows);
+            if (e.empty())   // source boxes of the resize into level l + 1
+                e = make_level_tmap(&maps[4 * og::kMaxLevels + l], ex->d_pyr + L.base, L.pitch, L.rows, L.frame_stride, ex->max_batch, 256, og::kRtBoxH);
             if (!e.empty()) return fail(ORBGPU_ERR_CUDA, e);
             smem = std::max(smem, og::fast_seg_smem_bytes(L.hbox, L.hbox - 6));
         }
@@ -444,6 +448,19 @@ int ensure_geometry(orbgpu_extractor* ex, int w, int h) {
             ok = yt[y1].s1 - yt[y0].s0 + 1 <= og::kResizeSpan;
         }
         ex->resize_mlp[l] = ok;
+        // k_resize_tma: the source bytes of every 192 x 32 output tile must lie inside one 256 x kRtBoxH box whose first column is
+        // 16-byte aligned in the level buffer
+        const og::Tap* xt = G.taps.data() + G.xt_off[l];
+        bool fits = true;
+        for (int X0 = 0; X0 < P.lv[l].w && fits; X0 += og::kRtW) {
+            const int X1 = std::min(X0 + og::kRtW, P.lv[l].w) - 1, gx = (og::kXPad + xt[X0].s0) & ~15;
+            fits = og::kXPad + xt[X1].s1 - gx < 256;   // (words read past a box row's end belong to the next row and are never selected)
+        }
+        for (int Y0 = 0; Y0 < P.lv[l].h && fits; Y0 += og::kRtH) {
+            const int Y1 = std::min(Y0 + og::kRtH, P.lv[l].h) - 1;
+            fits = yt[Y1].s1 - yt[Y0].s0 + 1 <= og::kRtBoxH;
+        }
+        ex->resize_tma[l] = fits;
     }
     ex->P.pyr = ex->d_pyr;
     ex->P.blur = ex->d_blur;
@@ -473,7 +490,13 @@ int launch_extract(orbgpu_extractor* ex, const uint8_t* d_images, int batch, siz
     P.kp_cap = kp_capacity;
     cudaStream_t st = on ? on : ex->stream;
     int launches = 0;
-    auto mark = [&](int i) { if (ex->profiling) cudaEventRecord(ex->ev[i], st); };
+    // stage boundaries: CUDA events when per-stage profiling is on (orbgpu_extractor_stage_ms), NVTX ranges on the host timeline always
+    static const char* const kStageName[5] = {"pyramid", "fast_cells", "octree", "blur", "orient_desc"};
+    auto mark = [&](int i) {
+        if (ex->profiling) cudaEventRecord(ex->ev[i], st);
+        if (i > 0) nvtxRangePop();
+        if (i < 5) nvtxRangePushA(kStageName[i]);
+    };
     mark(0);
     {
         const og::Level& L = P.lv[0];
@@ -491,7 +514,12 @@ int launch_extract(orbgpu_extractor* ex, const uint8_t* d_images, int batch, siz
         if ((double)P.lv[l - 1].w / L.w <= 2.0) {
             const int nwx = (L.w + 3) / 4, bands = (L.h + og::kResizeRows - 1) / og::kResizeRows, n_items = nwx * bands;
             const uint32_t magic = (uint32_t)((0x100000000ull + nwx - 1) / nwx);
-            if (ex->resize_mlp[l])
+            // ORBGPU_RESIZE_TMA=0: the register-staged kernel for every level (development; measured within 1 % of each other)
+            static const int tma_env = []() { const char* e = getenv("ORBGPU_RESIZE_TMA"); return e ? atoi(e) : 1; }();
+            if (tma_env && ex->resize_tma[l]) {
+                const int ntx = (L.w + og::kRtW - 1) / og::kRtW, nty = (L.h + og::kRtH - 1) / og::kRtH;
+                og::k_resize_tma<<<dim3(ntx * nty, batch), og::kRtThreads, 0, st>>>(P, l, ntx, ex->d_tmaps);
+            } else if (ex->resize_mlp[l])
                 og::k_resize4_pp<<<dim3((n_items + og::kResizeThreads - 1) / og::kResizeThreads, batch), og::kResizeThreads, 0, st>>>(P, l, nwx, magic, n_items);
             else
                 og::k_resize4<<<dim3((n_items + og::kResizeThreads - 1) / og::kResizeThreads, batch), og::kResizeThreads, 0, st>>>(P, l, nwx, magic, n_items);
@@ -676,7 +704,7 @@ int orbgpu_extractor_create(orbgpu_extractor** out, int device, int nfeatures, f
     alloc((void**)&ex->d_cells, ex->cap_cells * sizeof(og::Cell));
     alloc((void**)&ex->d_segs, ex->cap_cells * sizeof(og::Segment));
     alloc((void**)&ex->d_btiles, ex->cap_cells * sizeof(og::BlurTile));
-    alloc((void**)&ex->d_tmaps, 4 * og::kMaxLevels * sizeof(CUtensorMap));
+    alloc((void**)&ex->d_tmaps, 5 * og::kMaxLevels * sizeof(CUtensorMap));
     alloc((void**)&ex->d_taps, ex->cap_taps * sizeof(og::Tap));
     alloc((void**)&ex->d_cell_count, ex->cap_cellcount * B * 4);
     alloc((void**)&ex->d_cand_xy, ex->cap_cand * B * 4);
@@ -792,6 +820,7 @@ int orbgpu_extractor_static_tables(int nfeatures, float scale_factor, int nlevel
 int orbgpu_extract_batch_dev(orbgpu_extractor* ex, const uint8_t* images_dev, int batch, int width, int height,
                              size_t row_stride, size_t frame_stride, orbgpu_keypoint* kp_out_dev, uint8_t* desc_out_dev,
                              int kp_capacity, int32_t* counts_dev) {
+    OG_NVTX("orbgpu_extract_batch_dev");
     int rc = check_call(ex, batch, width, height, row_stride, kp_capacity);
     if (rc) return rc;
     if (!images_dev || !kp_out_dev || !desc_out_dev || !counts_dev) return fail(ORBGPU_ERR_ARG, "null device pointer");
@@ -837,6 +866,7 @@ int orbgpu_extract_batch_dev(orbgpu_extractor* ex, const uint8_t* images_dev, in
 
 int orbgpu_extract_batch(orbgpu_extractor* ex, const uint8_t* images, int batch, int width, int height, size_t row_stride,
                          size_t frame_stride, orbgpu_keypoint* kp_out, uint8_t* desc_out, int kp_capacity, int32_t* counts) {
+    OG_NVTX("orbgpu_extract_batch");
     int rc = check_call(ex, batch, width, height, row_stride, kp_capacity);
     if (rc) return rc;
     if (!images || !kp_out || !desc_out || !counts) return fail(ORBGPU_ERR_ARG, "null pointer");
@@ -907,6 +937,7 @@ int orbgpu_extract_batch(orbgpu_extractor* ex, const uint8_t* images, int batch,
 int orbgpu_extract_batch_color(orbgpu_extractor* ex, const uint8_t* images, int batch, int width, int height, int channels, int rgb_order,
                                size_t row_stride, size_t frame_stride, uint8_t* gray_out, orbgpu_keypoint* kp_out, uint8_t* desc_out,
                                int kp_capacity, int32_t* counts) {
+    OG_NVTX("orbgpu_extract_batch_color");
     if (channels != 3 && channels != 4) return fail(ORBGPU_ERR_ARG, "colour input must have 3 or 4 interleaved channels");
     int rc = check_call(ex, batch, width, height, row_stride / (size_t)channels, kp_capacity);
     if (rc) return rc;
@@ -939,6 +970,7 @@ int orbgpu_extract_batch_color(orbgpu_extractor* ex, const uint8_t* images, int 
 
 int orbgpu_extract(orbgpu_extractor* ex, const uint8_t* image, int width, int height, size_t row_stride,
                    orbgpu_keypoint* kp_out, uint8_t* desc_out, int kp_capacity, int* n_out) {
+    OG_NVTX("orbgpu_extract");
     if (!n_out) return fail(ORBGPU_ERR_ARG, "null n_out");
     *n_out = 0;
     if (!image || width <= 0 || height <= 0) return ORBGPU_OK;  // empty image: silent return (:1046-1047)
@@ -1236,11 +1268,13 @@ static int stereo_launch(orbgpu_extractor* L, orbgpu_extractor* R, float mb, flo
 
 int orbgpu_stereo_matches_dev(orbgpu_extractor* left, orbgpu_extractor* right, float mb, float mbf, float* u_right_dev, float* depth_dev,
                               int out_stride) {
+    OG_NVTX("orbgpu_stereo_matches_dev");
     if (!u_right_dev || !depth_dev) return fail(ORBGPU_ERR_ARG, "null output");
     return stereo_launch(left, right, mb, mbf, u_right_dev, depth_dev, out_stride);
 }
 
 int orbgpu_stereo_matches(orbgpu_extractor* left, orbgpu_extractor* right, float mb, float mbf, float* u_right, float* depth, int out_stride) {
+    OG_NVTX("orbgpu_stereo_matches");
     if (!u_right || !depth) return fail(ORBGPU_ERR_ARG, "null output");
     int rc = stereo_launch(left, right, mb, mbf, nullptr, nullptr, out_stride);
     if (rc) return rc;

@@ -1,7 +1,8 @@
 // og_extract.cu — CUDA kernels (sm_100a) of ORBextractor::operator() (ORBextractor.cc:1043-1132).
 //
 //   k_level0        the input image into the interior of level 0                     (:1127)
-//   k_resize4       cv::resize INTER_LINEAR level l-1 -> l, 4 pixels per thread       (:1120)
+//   k_resize_tma    cv::resize INTER_LINEAR level l-1 -> l: 192 x 32 output tiles, source box by TMA (:1120)
+//   k_resize4_pp / k_resize4   the same with the source words in registers (levels whose tiles do not fit the box; scale <= 2)
 //   k_resize        the same, any scale, one pass incl. frame (fallback for scale > 2)
 //   k_border_sides / k_border_caps   BORDER_REFLECT_101 frame of every level         (:1122-1128)
 //   k_fast_seg      per-cell FAST-9/16 + 3x3 NMS + iniTh/minTh fallback (TMA tiles)  (:789-829)
@@ -248,6 +249,73 @@ __global__ void __launch_bounds__(kResizeThreads, OG_RESIZE_MINB) k_resize4_pp(c
         const uint32_t q1 = (__umulhi(b0, __dp2a_hi(wq1, a.x, 0u) >> 4) + __umulhi(b1, __dp2a_hi(wq1, b.x, 0u) >> 4) + 2u) >> 2;
         const uint32_t q2 = (__umulhi(b0, __dp2a_lo(wq2, a.y, 0u) >> 4) + __umulhi(b1, __dp2a_lo(wq2, b.y, 0u) >> 4) + 2u) >> 2;
         const uint32_t q3 = (__umulhi(b0, __dp2a_hi(wq3, a.y, 0u) >> 4) + __umulhi(b1, __dp2a_hi(wq3, b.y, 0u) >> 4) + 2u) >> 2;
+        *reinterpret_cast<uint32_t*>(dbase + doff) = q0 | (q1 << 8) | (q2 << 16) | (q3 << 24);
+    }
+}
+
+// The same resize with the source staged by TMA: one CTA = 192 x 32 outputs of one (level, frame); the source pixels they
+// blend (scale <= 1.25: at most 242 columns x 42 rows, checked per level on the host) arrive as ONE 256 x 42 box of level l-1
+// (UTMALDG, 16-byte aligned start column at or left of the first source column).  A thread owns 4 output columns x 8 rows: per
+// output row it reads the three words around its source bytes in the two source rows from shared memory, gathers the byte
+// pairs with one permute per output pair and applies the weights by DP2A as above.  No global load instruction, no tag
+// look-ups, nothing parked: 33 registers instead of 64.
+// tmaps[4 K + l]: 256 x kRtBoxH boxes over level l (K = kMaxLevels).
+constexpr int kRtW = 192, kRtH = 32, kRtBoxH = 42, kRtRows = 8, kRtThreads = (kRtW / 4) * (kRtH / kRtRows);
+__global__ void __launch_bounds__(kRtThreads) k_resize_tma(const __grid_constant__ ExtractParams P, int level, int ntx, const CUtensorMap* __restrict__ tmaps) {
+    __shared__ __align__(128) uint8_t tile[kRtBoxH * 256 + 16];
+    __shared__ uint64_t mbar;
+    const Level& L = P.lv[level];
+    const int frame = P.frame0 + blockIdx.y, t = threadIdx.x;
+    const int ty_ = blockIdx.x / ntx, tx_ = blockIdx.x - ty_ * ntx;
+    const int X0 = kRtW * tx_, Y0 = kRtH * ty_;
+    const int sy0 = L.yt[Y0].s0;                                    // first source row of the tile
+    const int gx = (kXPad + (int)L.xt[X0].s0) & ~15;                // box start column (buffer coordinates)
+    if (t == 0) mbar_init(&mbar, 1);
+    __syncthreads();
+    if (t == 0) {
+        mbar_expect_tx(&mbar, kRtBoxH * 256);
+        tma_load_3d(tile, tmaps + 4 * kMaxLevels + (level - 1), gx, kEdge + sy0, frame, &mbar);
+    }
+    const int g = t / (kRtW / 4), q = t - g * (kRtW / 4);
+    const int x = X0 + 4 * q, y0 = Y0 + kRtRows * g;
+    const bool active = x < L.w && y0 < L.h;
+    uint32_t selA = 0, selB = 0, wq0 = 0, wq1 = 0, wq2 = 0, wq3 = 0;
+    int base = 0;
+    bool hiB = false;
+    if (active) {   // x taps of the 4 outputs, while the box is in flight (the table is padded to a multiple of 4 entries)
+        const uint4 ta = __ldg(reinterpret_cast<const uint4*>(L.xt + x)), tb = __ldg(reinterpret_cast<const uint4*>(L.xt + x) + 1);
+        const int c0 = kXPad - gx;                                   // source column -> byte of a box row
+        const int b0 = (int)(ta.x & 0xffffu) + c0;
+        base = b0 & ~3;
+        const int o0 = b0 - base, o1 = (int)(ta.z & 0xffffu) + c0 - base;
+        int o2 = (int)(tb.x & 0xffffu) + c0 - base, o3 = (int)(tb.z & 0xffffu) + c0 - base;
+        hiB = o2 >= 4;
+        if (hiB) { o2 -= 4; o3 -= 4; }
+        selA = (uint32_t)(o0 | ((o0 + 1) << 4) | (o1 << 8) | ((o1 + 1) << 12));
+        selB = (uint32_t)(o2 | ((o2 + 1) << 4) | (o3 << 8) | ((o3 + 1) << 12));
+        wq0 = ta.y; wq1 = ta.w; wq2 = tb.y; wq3 = tb.w;
+    }
+    mbar_wait(&mbar, 0);
+    if (!active) return;
+    const uint8_t* col = tile + base;
+    uint8_t* dbase = level_ptr(P.pyr, L, frame);
+    const uint32_t dpitch = (uint32_t)L.pitch;
+    uint32_t doff = (uint32_t)(kEdge + y0) * dpitch + (uint32_t)(kXPad + x);
+    const int nrows = min(kRtRows, L.h - y0);
+    const Tap* ytp = L.yt + y0;
+#pragma unroll 2
+    for (int r = 0; r < nrows; ++r, doff += dpitch) {
+        const Tap ty = ytp[r];
+        const uint32_t* ra = reinterpret_cast<const uint32_t*>(col + (ty.s0 - sy0) * 256);
+        const uint32_t* rb = reinterpret_cast<const uint32_t*>(col + (ty.s1 - sy0) * 256);
+        const uint32_t a0 = ra[0], a1 = ra[1], a2 = ra[2], c0 = rb[0], c1 = rb[1], c2 = rb[2];
+        const uint32_t ax = __byte_perm(a0, a1, selA), ay = __byte_perm(hiB ? a1 : a0, hiB ? a2 : a1, selB);
+        const uint32_t bx = __byte_perm(c0, c1, selA), by = __byte_perm(hiB ? c1 : c0, hiB ? c2 : c1, selB);
+        const uint32_t b0 = (uint32_t)ty.w0 << 16, b1 = (uint32_t)ty.w1 << 16;
+        const uint32_t q0 = (__umulhi(b0, __dp2a_lo(wq0, ax, 0u) >> 4) + __umulhi(b1, __dp2a_lo(wq0, bx, 0u) >> 4) + 2u) >> 2;
+        const uint32_t q1 = (__umulhi(b0, __dp2a_hi(wq1, ax, 0u) >> 4) + __umulhi(b1, __dp2a_hi(wq1, bx, 0u) >> 4) + 2u) >> 2;
+        const uint32_t q2 = (__umulhi(b0, __dp2a_lo(wq2, ay, 0u) >> 4) + __umulhi(b1, __dp2a_lo(wq2, by, 0u) >> 4) + 2u) >> 2;
+        const uint32_t q3 = (__umulhi(b0, __dp2a_hi(wq3, ay, 0u) >> 4) + __umulhi(b1, __dp2a_hi(wq3, by, 0u) >> 4) + 2u) >> 2;
         *reinterpret_cast<uint32_t*>(dbase + doff) = q0 | (q1 << 8) | (q2 << 16) | (q3 << 24);
     }
 }

@@ -14,6 +14,7 @@
 //   k_sbp_select        phase B: greedy walk over the map points in vector order           (:108-110, :142-151)
 //
 // See og_match.cuh for the two-phase scheme.  Integer/popcount work: no tensor cores.
+#include "og_nvtx.h"
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -1768,6 +1769,7 @@ int orbgpu_mappoint_set_release(orbgpu_mappoint_set_dev* mp) {
 }
 
 int orbgpu_hamming_pairs(orbgpu_matcher* m, const uint8_t* a, const uint8_t* b, int n, int32_t* dist_out) {
+    OG_NVTX("orbgpu_hamming_pairs");
     int rc = check_matcher(m);
     if (rc) return rc;
     m->last_launches = 0;
@@ -1794,6 +1796,7 @@ int orbgpu_search_by_bow_dev(orbgpu_matcher* m, const orbgpu_frame_set_dev* set1
                              const int32_t* idx1, const int32_t* idx2, float nnratio, int check_orientation, int th_low,
                              int th_inclusive, int require_mp2, const int64_t* match_off, int32_t* match12_dev,
                              int32_t* match_dist_dev, int32_t* nmatches_dev) {
+    OG_NVTX("orbgpu_search_by_bow_dev");
     int rc = check_matcher(m);
     if (rc) return rc;
     return bow_dev(m, set1, set2, n_pairs, idx1, idx2, nnratio, check_orientation, th_low, th_inclusive, require_mp2, match_off,
@@ -1805,6 +1808,7 @@ int orbgpu_search_for_triangulation_dev(orbgpu_matcher* m, const orbgpu_frame_se
                                         const float* epipole, const float* scale_factors, const float* level_sigma2,
                                         int n_levels, int only_stereo, int check_orientation, const int64_t* match_off,
                                         int32_t* match12_dev, int32_t* match_dist_dev, int32_t* nmatches_dev) {
+    OG_NVTX("orbgpu_search_for_triangulation_dev");
     int rc = check_matcher(m);
     if (rc) return rc;
     return tri_dev(m, set1, set2, n_pairs, idx1, idx2, f12, epipole, scale_factors, level_sigma2, n_levels, only_stereo,
@@ -1815,6 +1819,7 @@ int orbgpu_search_by_projection_dev(orbgpu_matcher* m, const orbgpu_frame_set_de
                                     const float* scale_factors, int n_levels, float th, float nnratio, int32_t* kp_match_dev,
                                     int32_t* mp_best_idx_dev, int32_t* mp_best_dist_dev, int32_t* mp_second_dist_dev,
                                     int32_t* nmatches_dev) {
+    OG_NVTX("orbgpu_search_by_projection_dev");
     int rc = check_matcher(m);
     if (rc) return rc;
     return sbp_dev(m, frames, mps, scale_factors, n_levels, th, nnratio, kp_match_dev, mp_best_idx_dev, mp_best_dist_dev,
@@ -1872,6 +1877,7 @@ int orbgpu_search_by_bow(orbgpu_matcher* m, const orbgpu_frame_set* set1, const 
                          const int32_t* idx1, const int32_t* idx2, float nnratio, int check_orientation, int th_low,
                          int th_inclusive, int require_mp2, const int64_t* match_off, int32_t* match12, int32_t* match_dist,
                          int32_t* nmatches) {
+    OG_NVTX("orbgpu_search_by_bow");
     BowCtx c{n_pairs, idx1, idx2, nnratio, check_orientation, th_low, th_inclusive, require_mp2, match_off};
     return node_scan_host(m, set1, set2, n_pairs, match_off, idx1, match12, match_dist, nmatches,
                           [](orbgpu_matcher* mm, const orbgpu_frame_set_dev* a, const orbgpu_frame_set_dev* b, int32_t* d12, int32_t* dd,
@@ -1888,6 +1894,7 @@ int orbgpu_search_for_triangulation(orbgpu_matcher* m, const orbgpu_frame_set* s
                                     const float* scale_factors, const float* level_sigma2, int n_levels, int only_stereo,
                                     int check_orientation, const int64_t* match_off, int32_t* match12, int32_t* match_dist,
                                     int32_t* nmatches) {
+    OG_NVTX("orbgpu_search_for_triangulation");
     TriCtx c{n_pairs, idx1, idx2, f12, epipole, scale_factors, level_sigma2, n_levels, only_stereo, check_orientation, match_off};
     return node_scan_host(m, set1, set2, n_pairs, match_off, idx1, match12, match_dist, nmatches,
                           [](orbgpu_matcher* mm, const orbgpu_frame_set_dev* a, const orbgpu_frame_set_dev* b, int32_t* d12, int32_t* dd,
@@ -1902,6 +1909,7 @@ int orbgpu_search_for_triangulation(orbgpu_matcher* m, const orbgpu_frame_set* s
 int orbgpu_search_by_projection(orbgpu_matcher* m, const orbgpu_frame_set* frames, const orbgpu_mappoint_set* mps,
                                 const float* scale_factors, int n_levels, float th, float nnratio, int32_t* kp_match,
                                 int32_t* mp_best_idx, int32_t* mp_best_dist, int32_t* mp_second_dist, int32_t* nmatches) {
+    OG_NVTX("orbgpu_search_by_projection");
     int rc = check_matcher(m);
     if (rc) return rc;
     if (!frames || !mps) return og_fail(ORBGPU_ERR_ARG, "null argument");
@@ -1938,6 +1946,7 @@ int orbgpu_search_by_projection(orbgpu_matcher* m, const orbgpu_frame_set* frame
 int orbgpu_search_windowed(orbgpu_matcher* m, const orbgpu_frame_set* frames, const orbgpu_window_query_set* queries, int th_dist,
                            int skip_any_mappoint, int check_orientation, int32_t* kp_match, int32_t* q_best_idx, int32_t* q_best_dist,
                            int32_t* nmatches) {
+    OG_NVTX("orbgpu_search_windowed");
     int rc = check_matcher(m);
     if (rc) return rc;
     return win_host(m, frames, queries, th_dist, skip_any_mappoint, check_orientation, kp_match, q_best_idx, q_best_dist, nmatches);
@@ -1974,6 +1983,7 @@ __global__ void k_gather_i32(const int32_t* __restrict__ src, const int32_t* __r
 extern "C" int orbgpu_frame_set_from_extraction(orbgpu_matcher* m, orbgpu_extractor* ex, orbgpu_vocabulary* voc, int levelsup, int kp_flag,
                                                 const float* u_right_dev, int u_right_stride, const float* grid,
                                                 orbgpu_frame_set_dev** out) {
+    OG_NVTX("orbgpu_frame_set_from_extraction");
     int rc = check_matcher(m);
     if (rc) return rc;
     if (!out) return og_fail(ORBGPU_ERR_ARG, "null out");
@@ -2181,6 +2191,7 @@ extern "C" int orbgpu_is_in_frustum_dev(orbgpu_matcher* m, int n_frames, const f
                                         float viewing_cos_limit, const int32_t* mp_off, const float* world_pos, const float* normal,
                                         const float* min_d, const float* max_d, const float* max_distance, uint8_t* in_view, float* proj_x,
                                         float* proj_y, float* proj_xr, int32_t* level, float* view_cos) {
+    OG_NVTX("orbgpu_is_in_frustum_dev");
     int rc = check_matcher(m);
     if (rc) return rc;
     m->last_launches = 0;
@@ -2212,6 +2223,7 @@ extern "C" int orbgpu_is_in_frustum(orbgpu_matcher* m, int n_frames, const float
                                     float viewing_cos_limit, const int32_t* mp_off, const float* world_pos, const float* normal,
                                     const float* min_d, const float* max_d, const float* max_distance, uint8_t* in_view, float* proj_x,
                                     float* proj_y, float* proj_xr, int32_t* level, float* view_cos) {
+    OG_NVTX("orbgpu_is_in_frustum");
     int rc = check_matcher(m);
     if (rc) return rc;
     if (n_frames < 0 || (n_frames && !mp_off)) return og_fail(ORBGPU_ERR_ARG, "is_in_frustum: null mp_off");
@@ -2293,6 +2305,7 @@ __global__ void __launch_bounds__(128) k_distinctive(const int32_t* __restrict__
 
 extern "C" int orbgpu_distinctive_descriptors(orbgpu_matcher* m, int n_points, const int32_t* obs_off, const uint8_t* desc, int32_t* best_idx,
                                               int32_t* best_median) {
+    OG_NVTX("orbgpu_distinctive_descriptors");
     int rc = check_matcher(m);
     if (rc) return rc;
     m->last_launches = 0;
@@ -2334,6 +2347,7 @@ extern "C" int orbgpu_distinctive_descriptors(orbgpu_matcher* m, int n_points, c
 extern "C" int orbgpu_search_window_best(orbgpu_matcher* m, const orbgpu_frame_set* frames, const orbgpu_window_query_set* queries,
                                          const float* inv_level_sigma2, int n_levels, int skip_flagged, int32_t* q_best_idx,
                                          int32_t* q_best_dist) {
+    OG_NVTX("orbgpu_search_window_best");
     int rc = check_matcher(m);
     if (rc) return rc;
     if (inv_level_sigma2 && n_levels < 1) return og_fail(ORBGPU_ERR_ARG, "search_window_best: n_levels");
@@ -2344,6 +2358,7 @@ extern "C" int orbgpu_search_window_best(orbgpu_matcher* m, const orbgpu_frame_s
 // ORBmatcher::SearchForInitialization (ORBmatcher.cc:493-632): see include/orbgpu.h
 extern "C" int orbgpu_search_for_initialization(orbgpu_matcher* m, const orbgpu_frame_set* frames2, const orbgpu_window_query_set* queries1,
                                                 float nnratio, int check_orientation, int32_t* match12, int32_t* nmatches) {
+    OG_NVTX("orbgpu_search_for_initialization");
     int rc = check_matcher(m);
     if (rc) return rc;
     if (!match12) return og_fail(ORBGPU_ERR_ARG, "search_for_initialization: null match12");
@@ -2356,6 +2371,7 @@ extern "C" int orbgpu_mappoint_set_project(orbgpu_matcher* m, int n_frames, cons
                                            float viewing_cos_limit, const int32_t* mp_off, const float* world_pos, const float* normal,
                                            const float* min_d, const float* max_d, const float* max_distance, const uint8_t* flags,
                                            const uint8_t* desc, orbgpu_mappoint_set_dev** out) {
+    OG_NVTX("orbgpu_mappoint_set_project");
     int rc = check_matcher(m);
     if (rc) return rc;
     if (!out) return og_fail(ORBGPU_ERR_ARG, "null out");

@@ -6,6 +6,7 @@
 // H2D -> kernels -> D2H pipeline of orbgpu_extract_batch on its range, reading the caller's images and writing the caller's
 // key-point / descriptor / count arrays at the range's offsets: the "gather" is the D2H copies landing in one caller buffer.
 // Results are byte-identical to a one-device run (each frame is processed independently by the same kernels).
+#include "og_nvtx.h"
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -137,6 +138,7 @@ int orbgpu_multi_extractor_max_keypoints(const orbgpu_multi_extractor* me) { ret
 int orbgpu_multi_extractor_last_launches(const orbgpu_multi_extractor* me) { return me ? me->last_launches : 0; }
 
 int orbgpu_multi_extractor_frame_range(const orbgpu_multi_extractor* me, int batch, int g, int* first, int* last) {
+    OG_NVTX("orbgpu_multi_extractor_frame_range");
     if (!me || g < 0 || g >= (int)me->workers.size() || batch < 0) return og_fail(ORBGPU_ERR_ARG, "frame_range: bad arguments");
     const long long G = (long long)me->workers.size();
     if (first) *first = (int)((long long)batch * g / G);
@@ -146,6 +148,7 @@ int orbgpu_multi_extractor_frame_range(const orbgpu_multi_extractor* me, int bat
 
 int orbgpu_multi_extract_batch(orbgpu_multi_extractor* me, const uint8_t* images, int batch, int width, int height, size_t row_stride,
                                size_t frame_stride, orbgpu_keypoint* kp_out, uint8_t* desc_out, int kp_capacity, int32_t* counts) {
+    OG_NVTX("orbgpu_multi_extract_batch");
     if (!me) return og_fail(ORBGPU_ERR_ARG, "null multi extractor");
     if (batch < 0) return og_fail(ORBGPU_ERR_ARG, "negative batch");
     if (batch == 0) return ORBGPU_OK;

@@ -11,6 +11,7 @@
 // keys in shared memory (bitonic), turns the runs into the two maps and normalises — the floating-point sums run
 // sequentially in ascending word order like the std::map iteration of the reference, so the doubles are bit-exact;
 // k_voc_offsets scans the per-frame sizes; k_voc_compact writes the batch-wide CSR arrays.
+#include "og_nvtx.h"
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -494,6 +495,7 @@ int orbgpu_bow_transform_dev(orbgpu_vocabulary* v, int n_frames, const int32_t* 
                              const uint8_t* desc_dev, int levelsup, int32_t* bv_off, uint32_t* bv_word, double* bv_value,
                              int32_t* fv_node_off, int32_t* fv_node_id, int32_t* fv_feat_off, int32_t* fv_feat,
                              uint32_t* word_of_feature, uint32_t* node_of_feature) {
+    OG_NVTX("orbgpu_bow_transform_dev");
     if (!v) return og_fail(ORBGPU_ERR_ARG, "null vocabulary");
     if (n_frames < 0 || n_features < 0 || (n_frames > 0 && !kp_off_dev) || (n_features > 0 && !desc_dev))
         return og_fail(ORBGPU_ERR_ARG, "bow_transform: bad arguments");
@@ -553,6 +555,7 @@ int orbgpu_bow_transform_dev(orbgpu_vocabulary* v, int n_frames, const int32_t* 
 int orbgpu_bow_transform(orbgpu_vocabulary* v, int n_frames, const int32_t* kp_off, const uint8_t* desc, int levelsup,
                          int32_t* bv_off, uint32_t* bv_word, double* bv_value, int32_t* fv_node_off, int32_t* fv_node_id,
                          int32_t* fv_feat_off, int32_t* fv_feat, uint32_t* word_of_feature, uint32_t* node_of_feature) {
+    OG_NVTX("orbgpu_bow_transform");
     if (!v) return og_fail(ORBGPU_ERR_ARG, "null vocabulary");
     if (n_frames < 0 || (n_frames > 0 && !kp_off)) return og_fail(ORBGPU_ERR_ARG, "bow_transform: bad arguments");
     if (n_frames == 0) return ORBGPU_OK;

@@ -310,3 +310,16 @@ def test_colour_input_matches_cv2_golden_and_gray_path():
     kp2, desc2 = ex(gray[0])
     assert cnt[0] == len(kp2) > 500 and kp[0, :cnt[0]].tobytes() == kp2.tobytes() and np.array_equal(desc[0, :cnt[0]], desc2)
     ex.close()
+
+
+@pytest.mark.gpu
+def test_register_staged_resize_path_in_a_fresh_process():
+    """The pyramid resize has two vectorised kernels: k_resize_tma (source box by TMA; the default wherever a 192 x 32 output tile
+    reads at most a 256 x 42 source box) and k_resize4_pp (source words in registers; the fall-back).  ORBGPU_RESIZE_TMA is read once
+    per process, so the fall-back is exercised in a child process: pyramid stages and golden fixtures against the oracle."""
+    import os, subprocess, sys
+    env = dict(os.environ, ORBGPU_RESIZE_TMA="0")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-x", "-q", "-k",
+                        "test_stages_match_oracle or test_golden_fixtures"], cwd=root, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

@@ -9,7 +9,7 @@ ik, ir, iw, it = hdr.index("kernel"), hdr.index("dram_rd"), hdr.index("dram_wr")
 units = rows[1]
 def to_bytes(v, u):
     return float(v) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[u]
-stage_of = {"k_level0": "pyramid", "k_resize4_mlp": "pyramid", "k_resize4_pp": "pyramid", "k_resize4": "pyramid", "k_resize": "pyramid", "k_border_sides": "pyramid",
+stage_of = {"k_level0": "pyramid", "k_resize4_mlp": "pyramid", "k_resize4_pp": "pyramid", "k_resize_tma": "pyramid", "k_resize4": "pyramid", "k_resize": "pyramid", "k_border_sides": "pyramid",
             "k_border_caps": "pyramid", "k_border": "pyramid", "k_fast_seg": "fast_cells", "k_blur_tma": "blur", "k_octree": "octree", "k_orient_desc": "orient_desc"}
 out, ms = {}, {}
 for r in rows[2:]:
