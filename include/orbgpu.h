@@ -434,9 +434,10 @@ int orbgpu_vocabulary_last_launches(const orbgpu_vocabulary* v);
 int orbgpu_vocabulary_stream(orbgpu_vocabulary* v, void** stream_out);
 
 /* transform(features, BowVector&, FeatureVector&, levelsup) (TemplatedVocabulary.h:1127-1197) for every frame of a batch:
- * frame f owns descriptor rows [kp_off[f], kp_off[f+1]) of `desc`.  LIMIT: at most 8192 descriptors per frame (one CTA sorts a
- * frame's (node, index) and (word, index) keys in shared memory); a larger frame fails with ORBGPU_ERR_CAPACITY — the reference
- * has no such limit, but its settings stay far below it (nFeatures 1000-2000, 2 x nFeatures for the monocular initialiser).  All outputs are sized by the
+ * frame f owns descriptor rows [kp_off[f], kp_off[f+1]) of `desc`.  No size limit, like the reference: one CTA sorts a frame's
+ * (node, index) and (word, index) keys in shared memory while the largest frame of the batch has at most 8192 descriptors
+ * (the reference's settings stay far below: nFeatures 1000-2000, 2 x nFeatures for the monocular initialiser); a batch with a
+ * larger frame runs the same kernel on a block-private workspace in HBM (slower, same results).  All outputs are sized by the
  * caller for n = kp_off[n_frames] entries (the +1 arrays for n + 1) and may be NULL when not wanted:
  *   BowVector     (std::map<WordId, WordValue>, BowVector.h:58-60): frame f owns entries [bv_off[f], bv_off[f+1]) of
  *                 bv_word (ascending) / bv_value (after addWeight / addIfNotExist and normalisation, BowVector.cpp:36-90,

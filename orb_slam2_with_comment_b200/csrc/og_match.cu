@@ -2050,7 +2050,6 @@ extern "C" int orbgpu_frame_set_from_extraction(orbgpu_matcher* m, orbgpu_extrac
         fs->has_grid = true;
     }
     if (voc) {
-        if (fs->max_kp > 8192) return bail(og_fail(ORBGPU_ERR_CAPACITY, "frame_set_from_extraction: more than 8192 key points in one frame"));
         void *d_node_off, *d_node_id, *d_feat_off, *d_feat, *d_ent;
         OGF_CUDA(alloc((size_t)(batch + 1) * 4, &d_node_off));
         OGF_CUDA(alloc(nkp * 4, &d_node_id));

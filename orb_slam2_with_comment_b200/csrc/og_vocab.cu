@@ -119,11 +119,17 @@ struct FrameArgs {
     int32_t* counts;   // [n_frames][3]: nodes, words, valid features
     int accumulate;    // TF_IDF / TF: addWeight; IDF / BINARY: addIfNotExist
     int norm;          // 0 none (DOT_PRODUCT), 1 L1, 2 L2
+    // frames with more descriptors than a CTA's shared memory can sort (p_max > kVocSmemFrame): the same arrays in HBM, frame f at
+    // gws + f * gws_stride (null: dynamic shared memory)
+    unsigned char* gws;
+    size_t gws_stride;
 };
+constexpr int kVocSmemFrame = 8192;   // descriptors of one frame (rounded up to a power of two) that fit the shared-memory sort
 
 // One block per frame.  Shared: keys[P] (u64) | vals[P] (double, also used as int head positions).
 __global__ void __launch_bounds__(kVocThreads) k_voc_frame(FrameArgs A, int p_max) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(16) unsigned char smem_dyn[];
+    unsigned char* smem_raw = A.gws ? A.gws + (size_t)blockIdx.x * A.gws_stride : smem_dyn;   // block-private either way
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
     double* vals = reinterpret_cast<double*>(smem_raw + (size_t)p_max * 8);
     int* hpos = reinterpret_cast<int*>(smem_raw + (size_t)p_max * 16);   // [p_max + 1]
@@ -370,7 +376,7 @@ struct orbgpu_vocabulary {
     int last_launches = 0;
     int frame_smem_set = 0;
     Buf b_kp_off, b_desc, b_feat_word, b_feat_node, b_feat_w, b_seg_node_id, b_seg_node_start, b_seg_feat, b_seg_word, b_seg_val, b_counts,
-        b_node_off, b_word_off, b_valid_off, b_out[7];
+        b_node_off, b_word_off, b_valid_off, b_frame_ws, b_out[7];
 };
 
 extern "C" {
@@ -380,7 +386,7 @@ int orbgpu_vocabulary_destroy(orbgpu_vocabulary* v) {
     cudaSetDevice(v->device);
     if (v->stream) cudaStreamSynchronize(v->stream);
     Buf* bs[] = {&v->b_kp_off, &v->b_desc, &v->b_feat_word, &v->b_feat_node, &v->b_feat_w, &v->b_seg_node_id, &v->b_seg_node_start,
-                 &v->b_seg_feat, &v->b_seg_word, &v->b_seg_val, &v->b_counts, &v->b_node_off, &v->b_word_off, &v->b_valid_off};
+                 &v->b_seg_feat, &v->b_seg_word, &v->b_seg_val, &v->b_counts, &v->b_node_off, &v->b_word_off, &v->b_valid_off, &v->b_frame_ws};
     for (Buf* b : bs) b->release();
     for (Buf& b : v->b_out) b.release();
     if (v->stream) cudaStreamDestroy(v->stream);
@@ -499,7 +505,6 @@ int orbgpu_bow_transform_dev(orbgpu_vocabulary* v, int n_frames, const int32_t* 
     if (!v) return og_fail(ORBGPU_ERR_ARG, "null vocabulary");
     if (n_frames < 0 || n_features < 0 || (n_frames > 0 && !kp_off_dev) || (n_features > 0 && !desc_dev))
         return og_fail(ORBGPU_ERR_ARG, "bow_transform: bad arguments");
-    if (max_per_frame > 8192) return og_fail(ORBGPU_ERR_CAPACITY, "bow_transform: more than 8192 descriptors in one frame");
     OGV_CUDA(cudaSetDevice(v->device));
     v->last_launches = 0;
     if (n_frames == 0) return ORBGPU_OK;
@@ -534,14 +539,22 @@ int orbgpu_bow_transform_dev(orbgpu_vocabulary* v, int n_frames, const int32_t* 
     }
     int p_max = 1;
     while (p_max < max_per_frame) p_max <<= 1;
-    const size_t smem = (size_t)p_max * 16 + (size_t)(p_max + 1) * 4;
-    if ((int)smem > v->frame_smem_set && smem > 48 * 1024) {
-        OGV_CUDA(cudaFuncSetAttribute(og::k_voc_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 16 + 8193 * 4));
-        v->frame_smem_set = 8192 * 16 + 8193 * 4;
+    size_t smem = (size_t)p_max * 16 + (size_t)(p_max + 1) * 4;
+    void* gws = nullptr;
+    size_t gws_stride = 0;
+    if (p_max > og::kVocSmemFrame) {
+        // a frame too large for the shared-memory sort (the reference's transform has no size limit): the same kernel on a
+        // block-private workspace in HBM - slower per frame, only taken by batches that contain such a frame
+        gws_stride = (smem + 255) & ~(size_t)255;
+        OGV_CUDA(v->b_frame_ws.grab(gws_stride * (size_t)n_frames, &gws));
+        smem = 0;
+    } else if ((int)smem > v->frame_smem_set && smem > 48 * 1024) {
+        OGV_CUDA(cudaFuncSetAttribute(og::k_voc_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, og::kVocSmemFrame * 16 + (og::kVocSmemFrame + 1) * 4));
+        v->frame_smem_set = og::kVocSmemFrame * 16 + (og::kVocSmemFrame + 1) * 4;
     }
     og::FrameArgs A = {kp_off_dev, (const uint32_t*)fw, (const uint32_t*)fn, (const double*)fwt, (int32_t*)sni, (int32_t*)sns, (int32_t*)sf,
                        (uint32_t*)sw, (double*)sv, (int32_t*)cn, (v->weighting == 0 || v->weighting == 1) ? 1 : 0,
-                       v->scoring == 5 ? 0 : (v->scoring == 1 ? 2 : 1)};
+                       v->scoring == 5 ? 0 : (v->scoring == 1 ? 2 : 1), (unsigned char*)gws, gws_stride};
     og::k_voc_frame<<<n_frames, og::kVocThreads, smem, st>>>(A, p_max);
     og::k_voc_offsets<<<1, 1024, 0, st>>>((const int32_t*)cn, n_frames, (int32_t*)no, (int32_t*)wo, (int32_t*)vo);
     og::CompactArgs C = {kp_off_dev, (const int32_t*)sni, (const int32_t*)sns, (const int32_t*)sf, (const uint32_t*)sw, (const double*)sv,

@@ -38,6 +38,21 @@ def test_transform_matches_oracle(name):
     _check_batch(out, o, kp_off, desc, levelsup)
 
 
+def test_frames_beyond_the_shared_memory_sort():
+    """A frame with more than 8192 descriptors (the reference's transform has no size limit, TemplatedVocabulary.h:1127-1197): the
+    batch runs the frame kernel on its HBM workspace; same results as the oracle for the large frame and for the small frames beside it."""
+    voc, scoring, weighting, levelsup, _, _ = vocab_cases.make("k10_L3_tfidf_l1")
+    rs = np.random.RandomState(77)
+    kp_off = np.array([0, 700, 700 + 9001, 700 + 9001 + 1300], np.int32)
+    desc = rs.randint(0, 256, (int(kp_off[-1]), 32)).astype(np.uint8)
+    o = oracle_lib.VocabularyOracle(oracle_lib.load_port(), voc, scoring, weighting)
+    v = ORBVocabulary().from_records(voc, scoring, weighting)
+    out = v.transform_batch(kp_off, desc, levelsup)
+    _check_batch(out, o, kp_off, desc, levelsup)
+    out = v.transform_batch(kp_off[:2], desc[:700], levelsup)      # and back to the shared-memory path on the same handle
+    _check_batch(out, o, kp_off[:2], desc[:700], levelsup)
+
+
 def test_text_file_and_single_frame_maps(tmp_path):
     from orb_slam2_with_comment_b200 import vocabulary
     voc, scoring, weighting, levelsup, kp_off, desc = vocab_cases.make("k4_L5_ragged_stop")
@@ -134,7 +149,5 @@ def test_argument_errors():
     with pytest.raises(capi.OrbGpuError):
         ORBVocabulary().from_records(bad)
     v = ORBVocabulary().from_records(voc)
-    with pytest.raises(capi.OrbGpuError):
-        v.transform_batch(np.array([0, 9000], np.int32), np.zeros((9000, 32), np.uint8), 2)   # > 8192 rows in one frame
     with pytest.raises(capi.OrbGpuError):
         ORBVocabulary().transform_batch(np.array([0, 1], np.int32), np.zeros((1, 32), np.uint8))
