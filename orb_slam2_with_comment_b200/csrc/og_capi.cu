@@ -118,7 +118,7 @@ struct Geometry {
     std::vector<og::Segment> segs;
     std::vector<og::BlurTile> btiles;
     std::vector<og::Tap> taps;            // all levels' x then y tables, concatenated
-    std::vector<size_t> xt_off, yt_off;   // offsets into taps
+    std::vector<size_t> xt_off, yt_off, ytw_off;   // offsets into taps (ytw: decoded vertical taps, 16 bytes = two Tap slots each)
     size_t pyr_bytes_per_frame = 0;
 };
 
@@ -264,9 +264,20 @@ std::string build_geometry(const orbgpu_extractor& ex, int w, int h, int batch_c
             while (G.taps.size() % 4) G.taps.push_back(G.taps.back());          // padded outputs repeat the last column
             G.yt_off.push_back(G.taps.size());
             make_taps(P.lv[l - 1].h, L.h, false, G.taps);
+            while (G.taps.size() % 2) G.taps.push_back(og::Tap{0, 0, 0, 0});   // 16-byte aligned
+            G.ytw_off.push_back(G.taps.size());
+            for (int y = 0; y < L.h; ++y) {
+                const og::Tap t = G.taps[G.yt_off.back() + y];
+                const uint32_t w[4] = {(uint32_t)t.s0 * 256u, (uint32_t)t.s1 * 256u, (uint32_t)(uint16_t)t.w0 << 16, (uint32_t)(uint16_t)t.w1 << 16};
+                og::Tap two[2];
+                memcpy(two, w, 16);
+                G.taps.push_back(two[0]);
+                G.taps.push_back(two[1]);
+            }
         } else {
             G.xt_off.push_back(0);
             G.yt_off.push_back(0);
+            G.ytw_off.push_back(0);
         }
         // detection grid, ORBextractor.cc:770-806
         const int minBX = og::kEdge - 3, minBY = minBX;
@@ -441,6 +452,7 @@ int ensure_geometry(orbgpu_extractor* ex, int w, int h) {
     for (int l = 1; l < ex->nlevels; ++l) {
         ex->P.lv[l].xt = ex->d_taps + G.xt_off[l];
         ex->P.lv[l].yt = ex->d_taps + G.yt_off[l];
+        ex->P.lv[l].ytw = reinterpret_cast<const uint4*>(ex->d_taps + G.ytw_off[l]);
         const og::Tap* yt = G.taps.data() + G.yt_off[l];
         bool ok = true;
         for (int y0 = 0; y0 < P.lv[l].h && ok; y0 += og::kResizeRows) {

@@ -297,26 +297,31 @@ __global__ void __launch_bounds__(kRtThreads) k_resize_tma(const __grid_constant
     }
     mbar_wait(&mbar, 0);
     if (!active) return;
-    const uint8_t* col = tile + base;
-    uint8_t* dbase = level_ptr(P.pyr, L, frame);
-    const uint32_t dpitch = (uint32_t)L.pitch;
-    uint32_t doff = (uint32_t)(kEdge + y0) * dpitch + (uint32_t)(kXPad + x);
+    const uint8_t* col = tile + base - sy0 * 256;   // the decoded taps carry source row * 256
+    const size_t dpitch = (size_t)L.pitch;          // widened once: the row pointer advances by one 64-bit add per row
+    uint8_t* drow = level_ptr(P.pyr, L, frame) + (size_t)(kEdge + y0) * dpitch + (size_t)(kXPad + x);
     const int nrows = min(kRtRows, L.h - y0);
-    const Tap* ytp = L.yt + y0;
-#pragma unroll 2
-    for (int r = 0; r < nrows; ++r, doff += dpitch) {
-        const Tap ty = ytp[r];
-        const uint32_t* ra = reinterpret_cast<const uint32_t*>(col + (ty.s0 - sy0) * 256);
-        const uint32_t* rb = reinterpret_cast<const uint32_t*>(col + (ty.s1 - sy0) * 256);
+    const uint4* ytp = L.ytw + y0;
+    auto row = [&](int r) {
+        const uint4 ty = __ldg(ytp + r);   // {s0 * 256, s1 * 256, w0 << 16, w1 << 16}
+        const uint32_t* ra = reinterpret_cast<const uint32_t*>(col + ty.x);
+        const uint32_t* rb = reinterpret_cast<const uint32_t*>(col + ty.y);
         const uint32_t a0 = ra[0], a1 = ra[1], a2 = ra[2], c0 = rb[0], c1 = rb[1], c2 = rb[2];
         const uint32_t ax = __byte_perm(a0, a1, selA), ay = __byte_perm(hiB ? a1 : a0, hiB ? a2 : a1, selB);
         const uint32_t bx = __byte_perm(c0, c1, selA), by = __byte_perm(hiB ? c1 : c0, hiB ? c2 : c1, selB);
-        const uint32_t b0 = (uint32_t)ty.w0 << 16, b1 = (uint32_t)ty.w1 << 16;
+        const uint32_t b0 = ty.z, b1 = ty.w;
         const uint32_t q0 = (__umulhi(b0, __dp2a_lo(wq0, ax, 0u) >> 4) + __umulhi(b1, __dp2a_lo(wq0, bx, 0u) >> 4) + 2u) >> 2;
         const uint32_t q1 = (__umulhi(b0, __dp2a_hi(wq1, ax, 0u) >> 4) + __umulhi(b1, __dp2a_hi(wq1, bx, 0u) >> 4) + 2u) >> 2;
         const uint32_t q2 = (__umulhi(b0, __dp2a_lo(wq2, ay, 0u) >> 4) + __umulhi(b1, __dp2a_lo(wq2, by, 0u) >> 4) + 2u) >> 2;
         const uint32_t q3 = (__umulhi(b0, __dp2a_hi(wq3, ay, 0u) >> 4) + __umulhi(b1, __dp2a_hi(wq3, by, 0u) >> 4) + 2u) >> 2;
-        *reinterpret_cast<uint32_t*>(dbase + doff) = q0 | (q1 << 8) | (q2 << 16) | (q3 << 24);
+        *reinterpret_cast<uint32_t*>(drow) = q0 | (q1 << 8) | (q2 << 16) | (q3 << 24);
+        drow += dpitch;
+    };
+    if (nrows == kRtRows) {   // all but a level's last rows: no per-row checks
+#pragma unroll
+        for (int r = 0; r < kRtRows; ++r) row(r);
+    } else {
+        for (int r = 0; r < nrows; ++r) row(r);
     }
 }
 

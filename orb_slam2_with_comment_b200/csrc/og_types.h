@@ -25,6 +25,7 @@ struct Tap {
 struct Level {
     const Tap* xt;           // [w] horizontal taps from level l-1 (null for level 0)
     const Tap* yt;           // [h] vertical taps
+    const uint4* ytw;        // [h] the same for k_resize_tma, decoded: {s0 * 256, s1 * 256, w0 << 16, w1 << 16} (one 16-byte load, no unpacking)
     int w, h;                // cvRound(cols * mvInvScaleFactor[l]) (:1112)
     int pitch, rows;         // bytes per row (multiple of 128), h + 2*kEdge
     long long frame_stride;  // pitch * rows
