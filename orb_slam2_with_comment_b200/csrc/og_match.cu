@@ -763,8 +763,14 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_sbp_topk(const __grid_c
 
 // Phase B, one warp per frame: the map points in vector order (:66), F.mvpMapPoints[bestIdx] = pMP (:149).
 __global__ void __launch_bounds__(32) k_sbp_select(const __grid_constant__ SbpArgs A) {
+    // The reference walks the map points in vector order and a match marks its key point taken for the points behind it (:108-110,
+    // :142-151).  Only that mark is sequential, so a chunk of 32 map points is evaluated SPECULATIVELY, one per lane, against the
+    // marks committed so far; a lane's result can only change if a point before it in the chunk takes the key point the lane found
+    // best or second best.  The longest prefix of lanes without such a conflict is committed at once, the first conflicting lane
+    // and everything behind it are evaluated again: one or two rounds per chunk instead of one step per map point.
     extern __shared__ uint32_t blocked[];
     const int lane = threadIdx.x, f = blockIdx.x;
+    const unsigned full = 0xffffffffu, lt = (1u << lane) - 1u;
     const int k0 = A.F.kp_off[f], n = A.F.kp_off[f + 1] - k0;
     for (int i = lane; i < (n + 31) / 32; i += 32) blocked[i] = 0;
     if (A.kp_match) for (int i = lane; i < n; i += 32) A.kp_match[k0 + i] = -1;
@@ -791,59 +797,84 @@ __global__ void __launch_bounds__(32) k_sbp_select(const __grid_constant__ SbpAr
                 if (A.mp_second_dist) A.mp_second_dist[q] = 256;
             }
         }
-        // the sequential walk only visits queries that have at least one candidate (most local map points have none)
-        unsigned act = __ballot_sync(0xffffffffu, k[0] != kEmptyKey);
-        while (act) {
-            const int l = __ffs(act) - 1;
-            act &= act - 1;
-            uint32_t kk[kTopK];
-            int cc[kTopK], oo[kTopK];
-#pragma unroll
-            for (int j = 0; j < kTopK; ++j) {
-                kk[j] = __shfl_sync(0xffffffffu, k[j], l);
-                cc[j] = __shfl_sync(0xffffffffu, ci[j], l);
-                oo[j] = __shfl_sync(0xffffffffu, co[j], l);
-            }
-            const int qfl = __shfl_sync(0xffffffffu, fl, l);
-            const int qq = base + l;
-            int cnt = 0, bestIdx = -1, d1 = 256, d2 = 256, l1 = -1, l2 = -1;
+        // only queries that have at least one candidate take part (most local map points have none)
+        unsigned pend = __ballot_sync(full, k[0] != kEmptyKey);
+        while (pend) {
+            const bool mine = (pend >> lane) & 1u;
+            // ---- every pending lane: best / second among its list entries not taken so far
+            int cnt = 0, bestIdx = -1, secondIdx = -1, d1 = 256, d2 = 256, l1 = -1, l2 = -1;
             bool complete = false;
+            if (mine) {
 #pragma unroll
-            for (int j = 0; j < kTopK; ++j) {
-                if (cnt == 2 || complete) break;
-                if (kk[j] == kEmptyKey) { complete = true; break; }
-                const int idx = cc[j];
-                if ((blocked[idx >> 5] >> (idx & 31)) & 1u) continue;
-                if (cnt == 0) { bestIdx = idx; d1 = (int)(kk[j] >> kPosBits); l1 = oo[j]; cnt = 1; }
-                else { d2 = (int)(kk[j] >> kPosBits); l2 = oo[j]; cnt = 2; }
+                for (int j = 0; j < kTopK; ++j) {
+                    if (cnt == 2 || complete) break;
+                    if (k[j] == kEmptyKey) { complete = true; break; }
+                    const int idx = ci[j];
+                    if ((blocked[idx >> 5] >> (idx & 31)) & 1u) continue;
+                    if (cnt == 0) { bestIdx = idx; d1 = (int)(k[j] >> kPosBits); l1 = co[j]; cnt = 1; }
+                    else { secondIdx = idx; d2 = (int)(k[j] >> kPosBits); l2 = co[j]; cnt = 2; }
+                }
+                if (cnt == 2) complete = true;
             }
-            if (cnt == 2) complete = true;
-            if (!complete) {
-                // truncated list exhausted: exact rescan with the blocked mask
+            const int first = __ffs(pend) - 1;
+            if (!__shfl_sync(full, (int)complete, first)) {
+                // the first pending lane has exhausted its truncated list: exact rescan with the mask, by the whole warp (its state
+                // is final: nothing before it is pending)
+                const int qq = base + first;
                 const SbpQuery Q = sbp_query(A, qq, f);
                 uint32_t out[kTopK];
                 int32_t outi[kTopK];
                 evals += sbp_scan_warp(A, Q, load_desc(A.M.desc, qq), blocked, out, outi);
-                bestIdx = -1; d1 = 256; d2 = 256; l1 = -1; l2 = -1;
-                if (out[0] != kEmptyKey) { bestIdx = outi[0]; d1 = (int)(out[0] >> kPosBits); l1 = A.F.keys[k0 + outi[0]].octave; }
-                if (out[1] != kEmptyKey) { d2 = (int)(out[1] >> kPosBits); l2 = A.F.keys[k0 + outi[1]].octave; }
+                int bI = -1, e1 = 256, e2 = 256, m1 = -1, m2 = -1;
+                if (out[0] != kEmptyKey) { bI = outi[0]; e1 = (int)(out[0] >> kPosBits); m1 = A.F.keys[k0 + outi[0]].octave; }
+                if (out[1] != kEmptyKey) { e2 = (int)(out[1] >> kPosBits); m2 = A.F.keys[k0 + outi[1]].octave; }
+                bool acc = false;
+                if (bI >= 0 && e1 <= ORBGPU_TH_HIGH) acc = !(m1 == m2 && (float)e1 > __fmul_rn(A.nnratio, (float)e2));
+                const int qfl = __shfl_sync(full, fl, first);
+                if (lane == 0) {
+                    if (A.mp_best_idx) A.mp_best_idx[qq] = bI;
+                    if (A.mp_best_dist) A.mp_best_dist[qq] = e1;
+                    if (A.mp_second_dist) A.mp_second_dist[qq] = e2;
+                    if (acc) {
+                        if (qfl & 4) blocked[bI >> 5] |= 1u << (bI & 31);
+                        if (A.kp_match) atomicMax(&A.kp_match[k0 + bI], qq - q0);
+                    }
+                }
+                nacc += acc;
+                pend &= ~(1u << first);
+                __syncwarp();
+                continue;
             }
             bool accept = false;
-            if (bestIdx >= 0 && d1 <= ORBGPU_TH_HIGH)
-                accept = !(l1 == l2 && (float)d1 > __fmul_rn(A.nnratio, (float)d2));
-            if (lane == 0) {
-                if (A.mp_best_idx) A.mp_best_idx[qq] = bestIdx;
-                if (A.mp_best_dist) A.mp_best_dist[qq] = d1;
-                if (A.mp_second_dist) A.mp_second_dist[qq] = d2;
+            if (mine && bestIdx >= 0 && d1 <= ORBGPU_TH_HIGH) accept = !(l1 == l2 && (float)d1 > __fmul_rn(A.nnratio, (float)d2));
+            // ---- conflicts: a pending lane before me takes my best or second key point (Observations() > 0 marks it taken), or I
+            // am incomplete (my rescan must see everything before me committed)
+            const bool claims = mine && accept && (fl & 4);
+            bool stop = mine && !complete;
+            unsigned cl = __ballot_sync(full, claims);
+            while (cl) {
+                const int i = __ffs(cl) - 1;
+                cl &= cl - 1;
+                const int c = __shfl_sync(full, bestIdx, i);
+                if (mine && lane > i && (c == bestIdx || c == secondIdx)) stop = true;
+            }
+            const unsigned sb = __ballot_sync(full, stop);
+            const unsigned done = sb ? (pend & ((1u << (__ffs(sb) - 1)) - 1u)) : pend;   // pending lanes before the first that must wait
+            if ((done >> lane) & 1u) {
+                if (A.mp_best_idx) A.mp_best_idx[q] = bestIdx;
+                if (A.mp_best_dist) A.mp_best_dist[q] = d1;
+                if (A.mp_second_dist) A.mp_second_dist[q] = d2;
                 if (accept) {
-                    if (qfl & 4) blocked[bestIdx >> 5] |= 1u << (bestIdx & 31);   // Observations() > 0: later candidates skip it
-                    if (A.kp_match) A.kp_match[k0 + bestIdx] = qq - q0;
+                    if (fl & 4) atomicOr(&blocked[bestIdx >> 5], 1u << (bestIdx & 31));   // Observations() > 0: later candidates skip it
+                    if (A.kp_match) atomicMax(&A.kp_match[k0 + bestIdx], q - q0);           // the last map point in vector order keeps the key point
                 }
             }
-            nacc += accept;
+            nacc += __popc(__ballot_sync(full, accept) & done);
+            pend &= ~done;
             __syncwarp();
         }
     }
+    (void)lt;
     if (lane == 0) {
         if (A.nmatches) A.nmatches[f] = nacc;
         if (evals) atomicAdd(A.evals, (unsigned long long)evals);
