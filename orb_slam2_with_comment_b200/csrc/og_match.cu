@@ -291,61 +291,80 @@ __global__ void __launch_bounds__(kSelectWarps * 32) k_bow_select(const __grid_c
                 }
             }
         }
-        unsigned act = __ballot_sync(0xffffffffu, i1 >= 0);
-        while (act) {
-            const int l = __ffs(act) - 1;
-            act &= act - 1;
-            // everything below is warp-uniform
-            uint32_t kk[kTopK];
-            int cc[kTopK];
-            float aa[kTopK];
-#pragma unroll
-            for (int j = 0; j < kTopK; ++j) {
-                kk[j] = __shfl_sync(0xffffffffu, k[j], l);
-                cc[j] = __shfl_sync(0xffffffffu, c2[j], l);
-                aa[j] = __shfl_sync(0xffffffffu, ang2[j], l);
-            }
-            const int qi1 = __shfl_sync(0xffffffffu, i1, l);
-            const int qb = __shfl_sync(0xffffffffu, nb_node, l);
-            const float qa1 = __shfl_sync(0xffffffffu, ang1, l);
-            int cnt = 0, best_c = -1, d1 = 256, d2 = 256;
+        // Speculative walk (see k_sbp_select): every pending lane takes best / second among its list entries not taken so far; a
+        // lane must wait if an accepted lane before it takes its best or second candidate, or if its truncated list ran dry (the
+        // rescan needs everything before it committed); the conflict-free prefix commits at once.
+        unsigned pend = __ballot_sync(0xffffffffu, i1 >= 0);
+        while (pend) {
+            const bool mine = (pend >> lane) & 1u;
+            int cnt = 0, best_c = -1, second_c = -1, d1 = 256, d2 = 256;
             float best_a = 0.f;
-            bool complete = false, rescanned = false;
+            bool complete = false;
+            if (mine) {
 #pragma unroll
-            for (int j = 0; j < kTopK; ++j) {
-                if (cnt == 2 || complete) break;
-                if (kk[j] == kEmptyKey) { complete = true; break; }
-                const int i2 = cc[j];
-                if ((taken[i2 >> 5] >> (i2 & 31)) & 1u) continue;
-                if (cnt == 0) { best_c = i2; best_a = aa[j]; d1 = (int)(kk[j] >> kPosBits); cnt = 1; }
-                else { d2 = (int)(kk[j] >> kPosBits); cnt = 2; }
+                for (int j = 0; j < kTopK; ++j) {
+                    if (cnt == 2 || complete) break;
+                    if (k[j] == kEmptyKey) { complete = true; break; }
+                    const int i2 = c2[j];
+                    if ((taken[i2 >> 5] >> (i2 & 31)) & 1u) continue;
+                    if (cnt == 0) { best_c = i2; best_a = ang2[j]; d1 = (int)(k[j] >> kPosBits); cnt = 1; }
+                    else { second_c = i2; d2 = (int)(k[j] >> kPosBits); cnt = 2; }
+                }
+                if (cnt == 2) complete = true;
             }
-            if (cnt == 2) complete = true;
-            if (!complete && (cnt == 0 || pass_th(d1))) {
-                // the truncated list ran out: exact rescan of this query's node with the taken mask
+            const bool rescan = mine && !complete && (cnt == 0 || pass_th(d1));
+            const int first = __ffs(pend) - 1;
+            if (__shfl_sync(0xffffffffu, (int)rescan, first)) {
+                // the first pending lane's truncated list ran out: exact rescan of its node with the taken mask, by the whole warp
+                const int qi1 = __shfl_sync(0xffffffffu, i1, first), qb = __shfl_sync(0xffffffffu, nb_node, first);
+                const float qa1 = __shfl_sync(0xffffffffu, ang1, first);
                 uint32_t out[kTopK];
                 evals += bow_scan_warp(A.S2, c.kb, qb, load_desc(A.S1.desc, c.ka + qi1), A.require_mp2, taken, 256, out);
-                best_c = -1; d1 = 256; d2 = 256;
-                rescanned = true;
+                int bc = -1, e1 = 256, e2 = 256;
                 if (out[0] != kEmptyKey) {
-                    best_c = A.S2.feat[A.S2.feat_off[qb] + (int)(out[0] & kPosMask)];
-                    d1 = (int)(out[0] >> kPosBits);
+                    bc = A.S2.feat[A.S2.feat_off[qb] + (int)(out[0] & kPosMask)];
+                    e1 = (int)(out[0] >> kPosBits);
                 }
-                if (out[1] != kEmptyKey) d2 = (int)(out[1] >> kPosBits);
-            }
-            if (best_c >= 0 && pass_th(d1) && (float)d1 < __fmul_rn(Z.nnratio, (float)d2)) {
-                int bin = 0;
-                if (Z.check_orientation) bin = rot_bin(qa1, rescanned ? A.S2.keys[c.kb + best_c].angle : best_a);
-                if (lane == 0) {
-                    taken[best_c >> 5] |= 1u << (best_c & 31);
-                    Z.match12[mo + qi1] = best_c;
-                    if (Z.match_dist) Z.match_dist[mo + qi1] = d1;
-                    Z.entry_bin[g0 + base + l] = (int8_t)bin;
-                    hist[bin] += 1;
+                if (out[1] != kEmptyKey) e2 = (int)(out[1] >> kPosBits);
+                if (bc >= 0 && pass_th(e1) && (float)e1 < __fmul_rn(Z.nnratio, (float)e2)) {
+                    int bin = 0;
+                    if (Z.check_orientation) bin = rot_bin(qa1, A.S2.keys[c.kb + bc].angle);
+                    if (lane == 0) {
+                        taken[bc >> 5] |= 1u << (bc & 31);
+                        Z.match12[mo + qi1] = bc;
+                        if (Z.match_dist) Z.match_dist[mo + qi1] = e1;
+                        Z.entry_bin[g0 + base + first] = (int8_t)bin;
+                        hist[bin] += 1;
+                    }
+                    ++nacc;
                 }
-                ++nacc;
+                pend &= ~(1u << first);
                 __syncwarp();
+                continue;
             }
+            const bool accept = mine && best_c >= 0 && pass_th(d1) && (float)d1 < __fmul_rn(Z.nnratio, (float)d2);
+            bool stop = rescan;
+            unsigned cl = __ballot_sync(0xffffffffu, accept);
+            while (cl) {
+                const int i = __ffs(cl) - 1;
+                cl &= cl - 1;
+                const int cb = __shfl_sync(0xffffffffu, best_c, i);
+                if (mine && lane > i && (cb == best_c || cb == second_c)) stop = true;
+            }
+            const unsigned sb = __ballot_sync(0xffffffffu, stop);
+            const unsigned done = sb ? (pend & ((1u << (__ffs(sb) - 1)) - 1u)) : pend;
+            if (((done >> lane) & 1u) && accept) {
+                int bin = 0;
+                if (Z.check_orientation) bin = rot_bin(ang1, best_a);
+                atomicOr(&taken[best_c >> 5], 1u << (best_c & 31));
+                Z.match12[mo + i1] = best_c;
+                if (Z.match_dist) Z.match_dist[mo + i1] = d1;
+                Z.entry_bin[g0 + e] = (int8_t)bin;
+                atomicAdd(&hist[bin], 1);
+            }
+            nacc += __popc(__ballot_sync(0xffffffffu, accept) & done);
+            pend &= ~done;
+            __syncwarp();
         }
     }
     __syncwarp();

@@ -1,0 +1,3 @@
+set -x
+python -m pytest tests/test_gpu_match.py tests/test_gpu_ref_matcher.py tests/test_gpu_pipeline.py tests/test_cpp_shell.py -m gpu -x -q 2>&1 | tail -3
+python tools/quick_match_bench.py 4096 256 2>&1 | tail -4
