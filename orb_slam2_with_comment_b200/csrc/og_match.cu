@@ -780,6 +780,121 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_sbp_topk(const __grid_c
     if (threadIdx.x == 0 && s_evals) atomicAdd(A.evals, (unsigned long long)s_evals);
 }
 
+// Phase A with G lanes per query instead of a warp: a window at th = 1 covers a handful of grid cells (one lane each) holding a
+// key point or two, so a full warp per map point left three quarters of its lanes without a cell.  The group enumerates the
+// candidates in the same order (ix outer, iy inner, ascending index in a cell) and merges its lanes' lists with group-wide
+// min / ballot / shuffle (all *_sync calls carry the group's own mask: groups of one warp run different trip counts).
+template <int G>
+__device__ __forceinline__ int sbp_scan_group(const SbpArgs& A, const SbpQuery& Q, const Desc& dq, uint32_t (&out)[kTopK], int32_t (&outi)[kTopK]) {
+    const int lane = threadIdx.x & 31, gl = lane & (G - 1);
+    const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << (lane & ~(G - 1));
+    uint32_t t[kTopK];
+    int32_t v[kTopK];
+#pragma unroll
+    for (int k = 0; k < kTopK; ++k) { t[k] = kEmptyKey; v[k] = -1; }
+    const int ny = Q.maxy - Q.miny + 1, ncell = (Q.maxx - Q.minx + 1) * ny;
+    const int32_t* cs = A.cell_start + (long long)Q.f * (kGridCells + 1);
+    const int32_t* items = A.cell_items + Q.k0;
+    const int minLevel = Q.min_level, maxLevel = Q.max_level;
+    const bool check_levels = (minLevel > 0) || (maxLevel >= 0);
+    int base = 0, evals = 0;
+    for (int c0 = 0; c0 < ncell; c0 += G) {
+        const int ci = c0 + gl;
+        int b = 0, n = 0;
+        if (ci < ncell) {
+            const int ix = Q.minx + ci / ny, iy = Q.miny + ci % ny;
+            b = cs[ix * kGridRows + iy];
+            n = cs[ix * kGridRows + iy + 1] - b;
+        }
+        if (__ballot_sync(gmask, n > 0) == 0) continue;   // these cells hold no key point
+        int inc = n;
+#pragma unroll
+        for (int d = 1; d < G; d <<= 1) {
+            const int u = __shfl_up_sync(gmask, inc, d, G);
+            if (gl >= d) inc += u;
+        }
+        const int pos0 = base + inc - n;
+        base += __shfl_sync(gmask, inc, G - 1, G);
+        for (int j = 0; j < n; ++j) {
+            const int idx = items[b + j];
+            const KeyPoint kp = A.F.keys[Q.k0 + idx];
+            if (check_levels) {
+                if (kp.octave < minLevel) continue;
+                if (maxLevel >= 0 && kp.octave > maxLevel) continue;
+            }
+            if (!(fabsf(__fsub_rn(kp.x, Q.x)) < Q.rs && fabsf(__fsub_rn(kp.y, Q.y)) < Q.rs)) continue;
+            if (A.F.flags) {
+                const int st = A.F.flags[Q.k0 + idx];
+                if (st == 1 || (A.skip_any && st != 0)) continue;
+            }
+            if (A.inv_sigma2) {
+                const float kur = A.F.u_right ? A.F.u_right[Q.k0 + idx] : -1.f;
+                const float ex = __fsub_rn(Q.x, kp.x), ey = __fsub_rn(Q.y, kp.y);
+                float e2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+                double lim = 5.99;
+                if (kur >= 0.f) {
+                    const float er = __fsub_rn(Q.xr, kur);
+                    e2 = __fadd_rn(e2, __fmul_rn(er, er));
+                    lim = 7.8;
+                }
+                if ((double)__fmul_rn(e2, A.inv_sigma2[kp.octave]) > lim) continue;
+            }
+            if (Q.use_xr && !A.no_xr_window && A.F.u_right && A.F.u_right[Q.k0 + idx] > 0.f) {
+                const float er = fabsf(__fsub_rn(Q.xr, A.F.u_right[Q.k0 + idx]));
+                if (er > Q.rs) continue;
+            }
+            const uint32_t dist = (uint32_t)hamming256(dq, load_desc(A.F.desc, Q.k0 + idx));
+            ++evals;
+            const uint32_t key = (dist << kPosBits) | (uint32_t)(pos0 + j);
+            if (key < t[kTopK - 1]) topk_insert2(t, v, key, idx);
+        }
+    }
+    if (__ballot_sync(gmask, t[0] != kEmptyKey) == 0) {
+#pragma unroll
+        for (int k = 0; k < kTopK; ++k) { out[k] = kEmptyKey; outi[k] = -1; }
+        return __reduce_add_sync(gmask, evals);
+    }
+#pragma unroll
+    for (int k = 0; k < kTopK; ++k) {
+        const uint32_t m = __reduce_min_sync(gmask, t[0]);
+        const unsigned own = __ballot_sync(gmask, t[0] == m);
+        const int32_t val = __shfl_sync(gmask, v[0], __ffs(own) - 1);
+        out[k] = m;
+        outi[k] = m == kEmptyKey ? -1 : val;
+        if (t[0] == m && m != kEmptyKey) {
+            t[0] = t[1]; t[1] = t[2]; t[2] = t[3]; t[3] = kEmptyKey;
+            v[0] = v[1]; v[1] = v[2]; v[2] = v[3]; v[3] = -1;
+        }
+    }
+    return __reduce_add_sync(gmask, evals);   // group total, identical in every lane of the group
+}
+
+#ifndef OG_SBP_GROUP
+#define OG_SBP_GROUP 8
+#endif
+constexpr int kSbpGroup = OG_SBP_GROUP;   // lanes per query in phase A
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) k_sbp_topk_g(const __grid_constant__ SbpArgs A, int total_mp) {
+    __shared__ int s_evals;
+    if (threadIdx.x == 0) s_evals = 0;
+    __syncthreads();
+    const int q = (blockIdx.x * kWarpsPerBlock * 32 + threadIdx.x) / kSbpGroup;
+    int evals = 0;
+    if (q < total_mp) {
+        const int f = upper_slot_i32(A.generic ? A.W.q_off : A.M.mp_off, 0, A.n_frames, q);
+        const SbpQuery Q = sbp_query(A, q, f);
+        uint32_t out[kTopK] = {kEmptyKey, kEmptyKey, kEmptyKey, kEmptyKey};
+        int32_t outi[kTopK] = {-1, -1, -1, -1};
+        if (Q.live) evals = sbp_scan_group<kSbpGroup>(A, Q, load_desc(A.generic ? A.W.desc : A.M.desc, q), out, outi);
+        if ((threadIdx.x & (kSbpGroup - 1)) == 0) {
+            *reinterpret_cast<uint4*>(A.topk_key + (long long)q * kTopK) = make_uint4(out[0], out[1], out[2], out[3]);
+            *reinterpret_cast<int4*>(A.topk_idx + (long long)q * kTopK) = make_int4(outi[0], outi[1], outi[2], outi[3]);
+            if (evals) atomicAdd(&s_evals, evals);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_evals) atomicAdd(A.evals, (unsigned long long)s_evals);
+}
+
 // Phase B, one warp per frame: the map points in vector order (:66), F.mvpMapPoints[bestIdx] = pMP (:149).
 __global__ void __launch_bounds__(32) k_sbp_select(const __grid_constant__ SbpArgs A) {
     // The reference walks the map points in vector order and a match marks its key point taken for the points behind it (:108-110,
@@ -1527,7 +1642,14 @@ int sbp_dev(orbgpu_matcher* m, const orbgpu_frame_set_dev* fs, const orbgpu_mapp
     k_grid_build<<<fs->n_frames, kGridThreads, 0, st>>>(A);
     m->last_launches += 1;
     if (mp->nmp > 0) {
-        k_sbp_topk<<<(mp->nmp + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock * 32, 0, st>>>(A, mp->nmp);
+        // ORBGPU_SBP_WARP=1: a whole warp per map point in phase A (development)
+        static const int sbp_warp_env = []() { const char* e = getenv("ORBGPU_SBP_WARP"); return e ? atoi(e) : 0; }();
+        if (sbp_warp_env) {
+            k_sbp_topk<<<(mp->nmp + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock * 32, 0, st>>>(A, mp->nmp);
+        } else {
+            const int per_cta = kWarpsPerBlock * 32 / kSbpGroup;
+            k_sbp_topk_g<<<(mp->nmp + per_cta - 1) / per_cta, kWarpsPerBlock * 32, 0, st>>>(A, mp->nmp);
+        }
         m->last_launches += 1;
     }
     if (smem > 48 * 1024) OGM_CUDA(cudaFuncSetAttribute(k_sbp_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1608,7 +1730,12 @@ int win_host(orbgpu_matcher* m, const orbgpu_frame_set* frames, const orbgpu_win
             cudaEventRecord(m->ev0, st);
             cudaMemsetAsync(m->d_evals, 0, 8, st);
             k_grid_build<<<nf, kGridThreads, 0, st>>>(A);
-            if (nq > 0) k_sbp_topk<<<(nq + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock * 32, 0, st>>>(A, nq);
+            if (nq > 0) {
+                static const int win_warp_env = []() { const char* e = getenv("ORBGPU_SBP_WARP"); return e ? atoi(e) : 0; }();
+                const int per_cta = kWarpsPerBlock * 32 / kSbpGroup;
+                if (win_warp_env) k_sbp_topk<<<(nq + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock * 32, 0, st>>>(A, nq);
+                else k_sbp_topk_g<<<(nq + per_cta - 1) / per_cta, kWarpsPerBlock * 32, 0, st>>>(A, nq);
+            }
             if (best_only) {
                 if (nq > 0) k_win_best<<<(nq + 255) / 256, 256, 0, st>>>(A, nq);
             } else if (init_mode) {
