@@ -1063,58 +1063,82 @@ __global__ void __launch_bounds__(32) k_win_select(const __grid_constant__ SbpAr
             if (A.mp_best_idx) A.mp_best_idx[q] = -1;
             if (A.mp_best_dist) A.mp_best_dist[q] = 256;
         }
-        unsigned act = __ballot_sync(0xffffffffu, k[0] != kEmptyKey);
-        while (act) {
-            const int l = __ffs(act) - 1;
-            act &= act - 1;
-            uint32_t kk[kTopK];
-            int cc[kTopK];
-            float aa[kTopK];
-#pragma unroll
-            for (int j = 0; j < kTopK; ++j) {
-                kk[j] = __shfl_sync(0xffffffffu, k[j], l);
-                cc[j] = __shfl_sync(0xffffffffu, ci[j], l);
-                aa[j] = __shfl_sync(0xffffffffu, ca[j], l);
-            }
-            const int qfl = __shfl_sync(0xffffffffu, fl, l);
-            const float qang = __shfl_sync(0xffffffffu, qa, l);
-            const int qq = base + l;
+        // speculative walk (see k_sbp_select): best-only, so a lane waits only if an accepted lane before it takes its best key point
+        unsigned pend = __ballot_sync(0xffffffffu, k[0] != kEmptyKey);
+        while (pend) {
+            const bool mine = (pend >> lane) & 1u;
             int bestIdx = -1, d1 = 256;
             float bang = 0.f;
-            bool complete = false, rescanned = false;
+            bool complete = false;
+            if (mine) {
 #pragma unroll
-            for (int j = 0; j < kTopK; ++j) {
-                if (bestIdx >= 0 || complete) break;
-                if (kk[j] == kEmptyKey) { complete = true; break; }
-                const int idx = cc[j];
-                if ((blocked[idx >> 5] >> (idx & 31)) & 1u) continue;
-                bestIdx = idx; d1 = (int)(kk[j] >> kPosBits); bang = aa[j];
+                for (int j = 0; j < kTopK; ++j) {
+                    if (bestIdx >= 0 || complete) break;
+                    if (k[j] == kEmptyKey) { complete = true; break; }
+                    const int idx = ci[j];
+                    if ((blocked[idx >> 5] >> (idx & 31)) & 1u) continue;
+                    bestIdx = idx; d1 = (int)(k[j] >> kPosBits); bang = ca[j];
+                }
             }
-            if (bestIdx < 0 && !complete) {
+            const bool rescan = mine && bestIdx < 0 && !complete;
+            const int first = __ffs(pend) - 1;
+            if (__shfl_sync(0xffffffffu, (int)rescan, first)) {
+                // the first pending lane's truncated list ran out: exact rescan with the mask, by the whole warp
+                const int qq = base + first;
+                const int qfl = __shfl_sync(0xffffffffu, fl, first);
+                const float qang = __shfl_sync(0xffffffffu, qa, first);
                 const SbpQuery Q = sbp_query(A, qq, f);
                 uint32_t out[kTopK];
                 int32_t outi[kTopK];
                 evals += sbp_scan_warp(A, Q, load_desc(A.W.desc, qq), blocked, out, outi);
-                rescanned = true;
-                if (out[0] != kEmptyKey) { bestIdx = outi[0]; d1 = (int)(out[0] >> kPosBits); }
-            }
-            const bool accept = bestIdx >= 0 && d1 <= A.th_dist;
-            if (accept) {
-                int bin = 0;
-                if (A.check_orientation) bin = rot_bin(qang, rescanned ? A.F.keys[k0 + bestIdx].angle : bang);
-                if (lane == 0) {
-                    // the key point now holds pMP: later candidates skip it if pMP has observations, or always under skip_any
-                    if ((qfl & 4) || A.skip_any) blocked[bestIdx >> 5] |= 1u << (bestIdx & 31);
-                    if (A.kp_match) A.kp_match[k0 + bestIdx] = qq - q0;
-                    A.q_bin[qq] = (int8_t)bin;
-                    hist[bin] += 1;
+                int bI = -1, e1 = 256;
+                if (out[0] != kEmptyKey) { bI = outi[0]; e1 = (int)(out[0] >> kPosBits); }
+                const bool acc = bI >= 0 && e1 <= A.th_dist;
+                if (acc) {
+                    int bin = 0;
+                    if (A.check_orientation) bin = rot_bin(qang, A.F.keys[k0 + bI].angle);
+                    if (lane == 0) {
+                        if ((qfl & 4) || A.skip_any) blocked[bI >> 5] |= 1u << (bI & 31);
+                        if (A.kp_match) atomicMax(&A.kp_match[k0 + bI], qq - q0);
+                        A.q_bin[qq] = (int8_t)bin;
+                        hist[bin] += 1;
+                    }
                 }
+                if (lane == 0) {
+                    if (A.mp_best_idx) A.mp_best_idx[qq] = bI;
+                    if (A.mp_best_dist) A.mp_best_dist[qq] = e1;
+                }
+                nacc += acc;
+                pend &= ~(1u << first);
+                __syncwarp();
+                continue;
             }
-            if (lane == 0) {
-                if (A.mp_best_idx) A.mp_best_idx[qq] = bestIdx;
-                if (A.mp_best_dist) A.mp_best_dist[qq] = d1;
+            const bool accept = mine && bestIdx >= 0 && d1 <= A.th_dist;
+            const bool claims = accept && ((fl & 4) || A.skip_any);   // the key point now holds pMP: later candidates skip it
+            bool stop = rescan;
+            unsigned cl = __ballot_sync(0xffffffffu, claims);
+            while (cl) {
+                const int i = __ffs(cl) - 1;
+                cl &= cl - 1;
+                const int cb = __shfl_sync(0xffffffffu, bestIdx, i);
+                if (mine && lane > i && cb == bestIdx) stop = true;
             }
-            nacc += accept;
+            const unsigned sb = __ballot_sync(0xffffffffu, stop);
+            const unsigned done = sb ? (pend & ((1u << (__ffs(sb) - 1)) - 1u)) : pend;
+            if ((done >> lane) & 1u) {
+                if (accept) {
+                    int bin = 0;
+                    if (A.check_orientation) bin = rot_bin(qa, bang);
+                    if (claims) atomicOr(&blocked[bestIdx >> 5], 1u << (bestIdx & 31));
+                    if (A.kp_match) atomicMax(&A.kp_match[k0 + bestIdx], q - q0);   // the last query in vector order keeps the key point
+                    A.q_bin[q] = (int8_t)bin;
+                    atomicAdd(&hist[bin], 1);
+                }
+                if (A.mp_best_idx) A.mp_best_idx[q] = bestIdx;
+                if (A.mp_best_dist) A.mp_best_dist[q] = d1;
+            }
+            nacc += __popc(__ballot_sync(0xffffffffu, accept) & done);
+            pend &= ~done;
             __syncwarp();
         }
     }
