@@ -869,10 +869,9 @@ __device__ __forceinline__ int sbp_scan_group(const SbpArgs& A, const SbpQuery& 
     return __reduce_add_sync(gmask, evals);   // group total, identical in every lane of the group
 }
 
-#ifndef OG_SBP_GROUP
-#define OG_SBP_GROUP 8
-#endif
-constexpr int kSbpGroup = OG_SBP_GROUP;   // lanes per query in phase A
+// G lanes per query.  Measured on 256 TUM frames x 5000 map points at th = 1 (whole search): warp 1.41 ms, G = 16 1.04, 8 0.84,
+// 4 0.73, 2 0.68, 1 0.68: 4 for the narrow windows of th <= 2, 8 for wider ones and the generic windowed searches.
+template <int kSbpGroup>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_sbp_topk_g(const __grid_constant__ SbpArgs A, int total_mp) {
     __shared__ int s_evals;
     if (threadIdx.x == 0) s_evals = 0;
@@ -1671,8 +1670,13 @@ int sbp_dev(orbgpu_matcher* m, const orbgpu_frame_set_dev* fs, const orbgpu_mapp
         if (sbp_warp_env) {
             k_sbp_topk<<<(mp->nmp + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock * 32, 0, st>>>(A, mp->nmp);
         } else {
-            const int per_cta = kWarpsPerBlock * 32 / kSbpGroup;
-            k_sbp_topk_g<<<(mp->nmp + per_cta - 1) / per_cta, kWarpsPerBlock * 32, 0, st>>>(A, mp->nmp);
+            if (A.th <= 2.0f) {
+                const int per_cta = kWarpsPerBlock * 32 / 4;
+                k_sbp_topk_g<4><<<(mp->nmp + per_cta - 1) / per_cta, kWarpsPerBlock * 32, 0, st>>>(A, mp->nmp);
+            } else {
+                const int per_cta = kWarpsPerBlock * 32 / 8;
+                k_sbp_topk_g<8><<<(mp->nmp + per_cta - 1) / per_cta, kWarpsPerBlock * 32, 0, st>>>(A, mp->nmp);
+            }
         }
         m->last_launches += 1;
     }
@@ -1756,9 +1760,9 @@ int win_host(orbgpu_matcher* m, const orbgpu_frame_set* frames, const orbgpu_win
             k_grid_build<<<nf, kGridThreads, 0, st>>>(A);
             if (nq > 0) {
                 static const int win_warp_env = []() { const char* e = getenv("ORBGPU_SBP_WARP"); return e ? atoi(e) : 0; }();
-                const int per_cta = kWarpsPerBlock * 32 / kSbpGroup;
+                const int per_cta = kWarpsPerBlock * 32 / 8;
                 if (win_warp_env) k_sbp_topk<<<(nq + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock * 32, 0, st>>>(A, nq);
-                else k_sbp_topk_g<<<(nq + per_cta - 1) / per_cta, kWarpsPerBlock * 32, 0, st>>>(A, nq);
+                else k_sbp_topk_g<8><<<(nq + per_cta - 1) / per_cta, kWarpsPerBlock * 32, 0, st>>>(A, nq);
             }
             if (best_only) {
                 if (nq > 0) k_win_best<<<(nq + 255) / 256, 256, 0, st>>>(A, nq);
