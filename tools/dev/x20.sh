@@ -1,0 +1,5 @@
+set -x
+python tools/stage_times.py 1024 3 256 2>&1 | tail -1
+ORBGPU_LIB=$PWD/tools/_build/liborbgpu_fpersist.so timeout 300 python -m pytest tests/test_gpu_extract.py -m gpu -x -q 2>&1 | tail -2
+ORBGPU_LIB=$PWD/tools/_build/liborbgpu_fpersist.so timeout 120 python tools/stage_times.py 1024 3 256 2>&1 | tail -1
+ORBGPU_LIB=$PWD/tools/_build/liborbgpu_fpersist.so timeout 120 python tools/quick_bench.py 1024 5 256 2>&1 | head -2
