@@ -212,7 +212,8 @@ EncodeTiledFn encode_tiled_fn() {
 }
 
 // u8 tensor [batch][rows][pitch] at `base`, box = box_w x box_h x 1 (zero fill outside the tensor)
-std::string make_level_tmap(CUtensorMap* out, uint8_t* base, int pitch, int rows, long long frame_stride, int batch, int box_w, int box_h) {
+std::string make_level_tmap(CUtensorMap* out, uint8_t* base, int pitch, int rows, long long frame_stride, int batch, int box_w, int box_h,
+                            CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_NONE) {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) return "cuTensorMapEncodeTiled is not available from this driver";
     const cuuint64_t gdim[3] = {(cuuint64_t)pitch, (cuuint64_t)rows, (cuuint64_t)batch};
@@ -220,7 +221,7 @@ std::string make_level_tmap(CUtensorMap* out, uint8_t* base, int pitch, int rows
     const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
     const cuuint32_t est[3] = {1, 1, 1};
     CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r);
     return "";
 }
@@ -410,7 +411,7 @@ int ensure_geometry(orbgpu_extractor* ex, int w, int h) {
                                     og::kIcRows);
             if (e.empty())
                 e = make_level_tmap(&maps[3 * og::kMaxLevels + l], ex->d_blur + L.base, L.pitch, L.rows, L.frame_stride, ex->max_batch, og::kBlurBoxW,
-                                    og::kPatchRows);
+                                    og::kPatchRows, OG_DESC_SWIZZLE ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE);
             if (e.empty())   // source boxes of the resize into level l + 1
                 e = make_level_tmap(&maps[4 * og::kMaxLevels + l], ex->d_pyr + L.base, L.pitch, L.rows, L.frame_stride, ex->max_batch, 256, og::kRtBoxH);
             if (!e.empty()) return fail(ORBGPU_ERR_CUDA, e);

@@ -1038,7 +1038,11 @@ __global__ void __launch_bounds__(kBlurThreads) k_blur_tma(
 constexpr int kDescWarps = OG_DESC_WARPS, kDescPerWarp = OG_DESC_PER_WARP;   // measured on B200 (device / host-path k frames/s): 8x4 96.3 / 82.2, 4x16 96.9 / 86.9, 6x16 97.8 / 87.1
 constexpr int kIcWords = 9, kIcRows = 31;           // table [4 alignments][31 rows][9 words][2]
 constexpr int kIcBoxW = 48, kBlurBoxW = 64, kPatchRows = 37;   // TMA boxes: 48 x 31 of the level, 64 x 37 of its blur
-constexpr int kIcSlot = 1536, kBlurSlot = 2432;     // box bytes rounded up to the 128 B a TMA destination wants
+#ifndef OG_DESC_SWIZZLE
+#define OG_DESC_SWIZZLE 1   // 0: unswizzled windows (development; 1.35 vs 1.23 ms per 1024 frames)
+#endif
+// box bytes rounded up to the 128 B a TMA destination wants (a 64-byte-swizzled destination: to the 512 B its pattern spans)
+constexpr int kIcSlot = 1536, kBlurSlot = OG_DESC_SWIZZLE ? 2560 : 2432;
 __constant__ int8_t c_pat_x[512] = {ORB_PATTERN_X_INIT};
 __constant__ int8_t c_pat_y[512] = {ORB_PATTERN_Y_INIT};
 
@@ -1065,7 +1069,7 @@ __global__ void __launch_bounds__(kDescWarps * 32, OG_DESC_MINB) k_orient_desc(c
     // pattern point j of lane i (= bit_pattern_31_ point 16 i + j) at spat[j * 32 + i]: the 32 lanes of a load hit 32
     // consecutive 8-byte slots (no bank conflicts), and the coordinates are already floats (no I2F in the sample loop)
     __shared__ float2 spat[512];
-    __shared__ __align__(128) uint8_t patch[kDescWarps][2 * kBlurSlot];
+    __shared__ __align__(1024) uint8_t patch[kDescWarps][2 * kBlurSlot];
     __shared__ uint64_t bars[kDescWarps][2];
     for (int i = threadIdx.x; i < 512; i += blockDim.x) spat[(i & 15) * 32 + (i >> 4)] = make_float2((float)c_pat_x[i], (float)c_pat_y[i]);
     const int frame = P.frame0 + blockIdx.y;
@@ -1189,7 +1193,14 @@ __global__ void __launch_bounds__(kDescWarps * 32, OG_DESC_MINB) k_orient_desc(c
         const float a = __shfl_sync(full, my_a, n), b = __shfl_sync(full, my_b, n);
         const int blx = kXPad + (int)(xy_cur & 0xffffu) - 18;   // first column of the 37-wide window
         if (n & 1) { mbar_wait(&bars[wi][1], use1 & 1); ++use1; } else { mbar_wait(&bars[wi][0], use0 & 1); ++use0; }
+#if OG_DESC_SWIZZLE
+        // 64-byte swizzle: the 16-byte chunk index (address bits 4-5) of a box row is XORed with bits 7-8 (= row / 2 mod 4), so the
+        // gathers of a warp spread over all 16 banks of their row parity instead of the 9 the window's columns cover
+        const uint8_t* bw = buf0 + (n & 1) * kBlurSlot;
+        const int boff = 18 * kBlurBoxW + 18 + (blx & 15);
+#else
         const uint8_t* b0 = buf0 + (n & 1) * kBlurSlot + 18 * kBlurBoxW + 18 + (blx & 15);
+#endif
         int val = 0;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -1197,7 +1208,12 @@ __global__ void __launch_bounds__(kDescWarps * 32, OG_DESC_MINB) k_orient_desc(c
             int r0, q0, r1, q1;
             brief_offset_f(p0.x, p0.y, a, b, &r0, &q0);
             brief_offset_f(p1.x, p1.y, a, b, &r1, &q1);
+#if OG_DESC_SWIZZLE
+            const int a0 = boff + r0 * kBlurBoxW + q0, a1 = boff + r1 * kBlurBoxW + q1;
+            const int t0 = bw[a0 ^ ((a0 >> 3) & 0x30)], t1 = bw[a1 ^ ((a1 >> 3) & 0x30)];
+#else
             const int t0 = b0[r0 * kBlurBoxW + q0], t1 = b0[r1 * kBlurBoxW + q1];
+#endif
             val |= (t0 < t1) << k;
         }
         const int idx = (blockIdx.x * kDescPerWarp + n) * kDescWarps + wi;
