@@ -1,0 +1,8 @@
+set -x
+export ORBGPU_FRAMES_CACHE=/tmp/frames256.npy
+python tools/stage_times.py 1024 5 256 2>&1 | tail -1
+ORBGPU_LIB=tools/_build/liborbgpu_ics.so python tools/stage_times.py 1024 5 256 2>&1 | tail -1
+python tools/stage_times.py 1024 5 256 2>&1 | tail -1
+ORBGPU_LIB=tools/_build/liborbgpu_ics.so python tools/stage_times.py 1024 5 256 2>&1 | tail -1
+ORBGPU_LIB=tools/_build/liborbgpu_ics.so python tools/parity_report.py 9 2>&1 | cut -c1-400
+python tools/parity_report.py 9 2>&1 | cut -c1-400

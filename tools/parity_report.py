@@ -1,6 +1,8 @@
 #!/usr/bin/env python3
-"""Parity report on a B200: CUDA extraction vs the CPU oracle over many seeded frames of the three BASELINE shapes —
-key-point fields bit-exact, angle deviation, fraction of key points whose descriptor differs (north_star: <= 0.1 %)."""
+"""Parity report on a B200: CUDA extraction vs the CPU checker over many seeded frames of the three BASELINE shapes —
+key-point fields bit-exact, angle deviation, fraction of key points whose descriptor differs (north_star: <= 0.1 %).
+The checker is the reference's own ORBextractor.cc (oracle/_ref/liborbref.so, stable tie-break at :684) when that build
+travelled to the box, else the port; the line says which."""
 import json, os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -9,10 +11,12 @@ import oracle_lib as ol
 from orb_slam2_with_comment_b200 import ORBextractor, synth
 
 n_seeds = int(sys.argv[1]) if len(sys.argv) > 1 else 48
-lib = ol.load_port()
+lib, prefix, checker = ol.load_ref(), "orbref", "reference ORBextractor.cc (oracle/_ref/liborbref.so)"
+if lib is None:
+    lib, prefix, checker = ol.load_port(), "orbo", "port (oracle/orb_oracle.cc)"
 for name, (w, h, nf) in {"kitti 1241x376/2000": (1241, 376, 2000), "tum 640x480/1000": (640, 480, 1000), "euroc 752x480/1200": (752, 480, 1200)}.items():
     g = ORBextractor(nf, 1.2, 8, 20, 7, max_width=w, max_height=h, max_batch=n_seeds)
-    o = ol.Extractor(lib, "orbo", nf, 1.2, 8, 20, 7)
+    o = ol.Extractor(lib, prefix, nf, 1.2, 8, 20, 7)
     gens = [synth.g_rects, synth.g_blurnoise, synth.g_uniform]
     imgs = np.stack([gens[s % 3](w, h, 5000 + s) for s in range(n_seeds)])
     kp, desc, cnt = g.extract_batch(imgs)
@@ -29,5 +33,5 @@ for name, (w, h, nf) in {"kitti 1241x376/2000": (1241, 376, 2000), "tum 640x480/
         tot["descriptor_rows_differing"] += int(np.count_nonzero((d != edesc).any(1)))
         tot["descriptor_bits_differing"] += int(np.unpackbits(d ^ edesc).sum())
     tot["descriptor_rows_differing_pct"] = 100.0 * tot["descriptor_rows_differing"] / tot["keypoints"]
-    print(json.dumps({"shape": name, **tot}))
+    print(json.dumps({"shape": name, "checker": checker, **tot}))
     g.close()

@@ -9,7 +9,14 @@ W, H, NF = 1241, 376, 2000
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 ND = int(sys.argv[3]) if len(sys.argv) > 3 else 64
-base = np.stack([synth.g_rects(W, H, s) for s in range(min(ND, B))])
+import os
+cache = os.environ.get("ORBGPU_FRAMES_CACHE")   # development: reuse the synthetic frames across runs of one session
+if cache and os.path.exists(cache) and len(np.load(cache, mmap_mode="r")) >= min(ND, B):
+    base = np.load(cache)[:min(ND, B)]
+else:
+    base = np.stack([synth.g_rects(W, H, s) for s in range(min(ND, B))])
+    if cache:
+        np.save(cache, base)
 imgs = np.concatenate([base] * ((B + len(base) - 1) // len(base)))[:B].copy()
 ex = ORBextractor(NF, 1.2, 8, 20, 7, max_width=W, max_height=H, max_batch=B)
 d_img = torch.from_numpy(imgs).cuda()
