@@ -1047,6 +1047,20 @@ constexpr int kIcSlot = 1536, kBlurSlot = OG_DESC_SWIZZLE ? 2560 : 2432;
 __constant__ int8_t c_pat_x[512] = {ORB_PATTERN_X_INIT};
 __constant__ int8_t c_pat_y[512] = {ORB_PATTERN_Y_INIT};
 
+// cvRound(x * b + y * a) and cvRound(x * a - y * b) of computeOrbDescriptor (:115-120) as the raw bits of round_rn_small's sum
+// (0x4B400000 + the rounded value); one byte from a shared-memory address.
+__device__ __forceinline__ uint32_t brief_row_bits(float fx, float fy, float a, float b) {
+    return __float_as_uint(__fadd_rn(fadd(fmul(fx, b), fmul(fy, a)), 12582912.f));
+}
+__device__ __forceinline__ uint32_t brief_col_bits(float fx, float fy, float a, float b) {
+    return __float_as_uint(__fadd_rn(fsub(fmul(fx, a), fmul(fy, b)), 12582912.f));
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
 __device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c) {   // unsigned bytes of a times signed bytes of b
     int r;
     asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
@@ -1204,8 +1218,12 @@ __global__ void __launch_bounds__(kDescWarps * 32, OG_DESC_MINB) k_orient_desc(c
 #if OG_DESC_SWIZZLE
         // 64-byte swizzle: the 16-byte chunk index (address bits 4-5) of a box row is XORed with bits 7-8 (= row / 2 mod 4), so the
         // gathers of a warp spread over all 16 banks of their row parity instead of the 9 the window's columns cover
-        const uint8_t* bw = buf0 + (n & 1) * kBlurSlot;
-        const int boff = 18 * kBlurBoxW + 18 + (blx & 15);
+        // The sample address is formed on the raw bits of the rounding (round_rn_small: float + 1.5 * 2^23 holds the integer in its
+        // low mantissa bits, C = 0x4B400000 more than it): (ir - C) * 64 + (iq - C) + window centre + buffer address
+        // = ir * 64 + (iq + kabs), so one add and one shift-add per point instead of five integer instructions.  The buffers
+        // start on multiples of 512 bytes, so the swizzle bits of the absolute address are those of the offset.
+        static_assert(kBlurSlot % 512 == 0 && (2 * kBlurSlot) % 1024 == 0, "swizzle bits of the absolute shared-memory address");
+        const uint32_t kabs = smem_u32(buf0 + (n & 1) * kBlurSlot) + (uint32_t)(18 * kBlurBoxW + 18 + (blx & 15)) - 65u * 0x4B400000u;
 #else
         const uint8_t* b0 = buf0 + (n & 1) * kBlurSlot + 18 * kBlurBoxW + 18 + (blx & 15);
 #endif
@@ -1213,13 +1231,15 @@ __global__ void __launch_bounds__(kDescWarps * 32, OG_DESC_MINB) k_orient_desc(c
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             const float2 p0 = __half22float2(preg[2 * k]), p1 = __half22float2(preg[2 * k + 1]);
+#if OG_DESC_SWIZZLE
+            static_assert(kBlurBoxW == 64, "row pitch of the window = the shift below");
+            const uint32_t a0 = brief_row_bits(p0.x, p0.y, a, b) * 64u + (brief_col_bits(p0.x, p0.y, a, b) + kabs);
+            const uint32_t a1 = brief_row_bits(p1.x, p1.y, a, b) * 64u + (brief_col_bits(p1.x, p1.y, a, b) + kabs);
+            const uint32_t t0 = lds_u8(a0 ^ ((a0 >> 3) & 0x30u)), t1 = lds_u8(a1 ^ ((a1 >> 3) & 0x30u));
+#else
             int r0, q0, r1, q1;
             brief_offset_f(p0.x, p0.y, a, b, &r0, &q0);
             brief_offset_f(p1.x, p1.y, a, b, &r1, &q1);
-#if OG_DESC_SWIZZLE
-            const int a0 = boff + r0 * kBlurBoxW + q0, a1 = boff + r1 * kBlurBoxW + q1;
-            const int t0 = bw[a0 ^ ((a0 >> 3) & 0x30)], t1 = bw[a1 ^ ((a1 >> 3) & 0x30)];
-#else
             const int t0 = b0[r0 * kBlurBoxW + q0], t1 = b0[r1 * kBlurBoxW + q1];
 #endif
             val |= (t0 < t1) << k;
