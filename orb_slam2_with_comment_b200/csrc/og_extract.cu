@@ -648,10 +648,17 @@ __global__ void __launch_bounds__(kSegThreads, 5) k_fast_seg(const __grid_consta
             // The threshold class is a compile-time constant of the loop (one LOP3 per test instead of a predicated pair).
             auto reject = [&](auto big_c) {
             constexpr bool big = decltype(big_c)::value;
+            // t < 127: the sum runs on the unmasked differences.  A byte >= 129 + t then carries into its left neighbour, whose
+            // bit 7 — if its own bit 7 and carry are both clear — comes out set for a difference of t already instead of t + 1:
+            // a rare extra candidate for the exact score to turn down, never a missed one (bit 7 of d itself covers d >= 128, and
+            // a carry can only raise a byte's sum), so the two mask instructions per pair are not needed.
             auto far2 = [&](uint32_t c, uint32_t xa, uint32_t xb) {
                 const uint32_t da = __vabsdiffu4(c, xa), db = __vabsdiffu4(c, xb);
-                const uint32_t sa = (da & 0x7f7f7f7fu) + kadd, sb = (db & 0x7f7f7f7fu) + kadd;
-                return big ? ((sa & da) | (sb & db)) : (sa | da | sb | db);
+                if (big) {
+                    const uint32_t sa = (da & 0x7f7f7f7fu) + kadd, sb = (db & 0x7f7f7f7fu) + kadd;
+                    return (sa & da) | (sb & db);
+                }
+                return (da + kadd) | da | (db + kadd) | db;
             };
             auto flags = [&](uint32_t ns, uint32_t ew, uint32_t d1, uint32_t d2) {
                 const uint32_t g = ns & ew & d1 & d2 & 0x80808080u;
