@@ -637,8 +637,11 @@ def run_ours(args):
         except Exception:
             traffic = None
     pipes = {}
-    spath = os.path.join(ROOT, "profiles", "r2_extract_v11_B1024_ncu_full_summary.csv")
-    if os.path.exists(spath):
+    # the final k_fast_seg was captured alone (v12); the other kernels are in the capture of the whole launch sequence (v11)
+    for sname in ("r2_fast_seg_v12_B1024_ncu_full_summary.csv", "r2_extract_v11_B1024_ncu_full_summary.csv"):
+        spath = os.path.join(ROOT, "profiles", sname)
+        if pipes or not os.path.exists(spath):
+            continue
         try:   # what actually binds the dominant kernel: issue slots / ALU pipe of the committed ncu --set full capture at the bench batch
             import csv
             rows = list(csv.reader(open(spath)))
@@ -650,7 +653,7 @@ def run_ours(args):
                     pipes = {"ncu_issue_active_pct": float(r[hdr.index("issue%")]), "ncu_alu_pipe_pct": float(r[hdr.index("alu%")]),
                              "ncu_l1tex_pct": float(r[hdr.index("l1tex%")]), "ncu_dram_pct": float(r[hdr.index("dram%")]),
                              "ncu_thread_inst_per_pyramid_pixel": float(r[hdr.index("warp_inst")]) * 32 / (B * px),
-                             "ncu_source": "profiles/r2_extract_v11_B1024_ncu_full_summary.csv"}
+                             "ncu_source": "profiles/" + sname}
                     break
         except Exception:
             pipes = {}
